@@ -1,0 +1,11 @@
+"""tensorflowasr_b200 — B200-native (sm_100a) implementation of TensorFlowASR's data-parallel training hot path.
+
+Public surface mirrors the reference (TensorSpeech/TensorFlowASR): `FeatureExtraction` / `SpeechFeaturizer`,
+`RnntLoss`, `CtcLoss`, `rnnt_loss`, the `schemas` NamedTuples, and the model wrappers, with torch CUDA tensors in
+place of tf.Tensors.  Compute runs in hand-written CUDA behind the C ABI of include/tfasr_b200.h.
+"""
+from . import schemas  # noqa: F401
+from .features import FeatureExtraction, SpeechFeaturizer  # noqa: F401
+from .losses import BaseLoss, CtcLoss, RnntLoss, ctc_loss, rnnt_loss  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,100 @@
+"""ctypes binding of libtfasr_b200.so (the C ABI declared in include/tfasr_b200.h).
+
+The product path has NO CPU fallback: if the library is missing it is built with nvcc; if that is impossible, or a
+call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_size_t, c_void_p
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libtfasr_b200.so")
+
+
+class LogmelCfg(ctypes.Structure):
+    """Mirror of `tfasr_logmel_cfg`."""
+
+    _fields_ = [
+        ("sample_rate", c_int32), ("frame_length", c_int32), ("frame_step", c_int32), ("nfft", c_int32),
+        ("num_feature_bins", c_int32), ("feature_type", c_int32), ("pad_end", c_int32), ("log_base10", c_int32),
+        ("padding", c_int32), ("preemphasis", c_float), ("epsilon", c_float), ("lower_edge_hertz", c_float),
+        ("upper_edge_hertz", c_float),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/tfasr_b200.h declares
+SIGNATURES = {
+    "tfasr_version": (c_int32, []),
+    "tfasr_status_string": (c_char_p, [c_int32]),
+    "tfasr_launch_count": (c_int32, []),
+    "tfasr_launch_count_reset": (None, []),
+    "tfasr_logmel_table_bytes": (c_size_t, [POINTER(LogmelCfg)]),
+    "tfasr_logmel_build_table": (c_int32, [POINTER(LogmelCfg), c_void_p]),
+    "tfasr_logmel_nframes": (c_int32, [POINTER(LogmelCfg), c_int32]),
+    "tfasr_logmel_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, POINTER(LogmelCfg), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tfasr_signal_normalize_f32": (c_int32, [c_void_p, c_int32, c_int32, c_float, c_void_p]),
+    "tfasr_feature_normalize_f32": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_void_p]),
+    "tfasr_rnnt_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "tfasr_rnnt_loss_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tfasr_rnnt_loss_fwd_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tfasr_rnnt_loss_bwd_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tfasr_ctc_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "tfasr_ctc_loss_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if needed) libtfasr_b200.so and bind every declared symbol. Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import _build
+
+        _build.build_library()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status == 0:
+        return
+    msg = load().tfasr_status_string(status).decode()
+    if status == 1:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what}: {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libtfasr_b200 has no CPU path: tensor must live on a CUDA device")
+    if not t.is_contiguous():
+        raise RuntimeError("libtfasr_b200 expects contiguous row-major buffers")
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: the B200 hot path has no CPU fallback; got a {t.device} tensor")

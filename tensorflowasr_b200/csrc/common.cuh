@@ -1,0 +1,56 @@
+// Shared helpers for libtfasr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/tfasr_b200.h"
+
+namespace tfasr {
+
+extern std::atomic<int> g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
+
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TFASR_OK : TFASR_EXECUTION_FAILED;
+}
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// log(exp(a) + exp(b)) with -inf handled (no NaN from inf - inf).
+__device__ __forceinline__ float log_add_exp(float a, float b) {
+  float m = fmaxf(a, b);
+  if (m == -CUDART_INF_F) return -CUDART_INF_F;
+  return m + log1pf(expf(-fabsf(a - b)));
+}
+
+// streaming 128-bit global accesses (read-once / write-once data should not pollute L1)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+
+}  // namespace tfasr
