@@ -10,7 +10,8 @@ and the masked softmax of ``models/layers/general.py:30-41`` with the fill value
 PARITY PINNING: ``compute_streaming_mask`` is pinned bit-exactly by the reference's own golden
 matrices (tests/test_mask.py:6-55, committed as tests/golden/streaming_mask.json by
 tests/golden/make_golden.py); ``rel_left_shift`` is pinned by the causal example in its docstring
-(multihead_attention.py:31-41).
+(multihead_attention.py:31-41) on the lower triangle — the code as written leaves wrap-around values in the
+upper triangle (row 0 is [3, 0, 4], not the docstring's [3, 0, 0]); those positions are masked downstream.
 """
 from __future__ import annotations
 
