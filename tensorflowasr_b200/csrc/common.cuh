@@ -42,6 +42,15 @@ __device__ __forceinline__ float log_add_exp(float a, float b) {
   if (m == -CUDART_INF_F) return -CUDART_INF_F;
   return m + log1pf(expf(-fabsf(a - b)));
 }
+// Same, on the MUFU fast path (ex2 / lg2): this sits on the critical path of the lattice wavefronts, where one step's
+// result feeds the next.  The argument of the log is in [1, 2] and of the exp in (-inf, 0]: absolute error ~1e-7, far
+// below the fp32 ulp of the lattice values themselves (|alpha| ~ 1e3 -> ulp 6e-5).
+__device__ __forceinline__ float log_add_exp_fast(float a, float b) {
+  const float m = fmaxf(a, b);
+  const float d = -fabsf(a - b);  // -inf - -inf = NaN only when both are -inf
+  const float r = m + __logf(1.0f + __expf(d));
+  return (m == -CUDART_INF_F) ? -CUDART_INF_F : r;
+}
 
 // streaming 128-bit global accesses (read-once / write-once data should not pollute L1)
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {

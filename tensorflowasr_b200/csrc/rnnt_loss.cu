@@ -99,6 +99,10 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(const int32_t* __res
   const int lane = i & 31, warp = i >> 5;
   const int Tb = logit_len[b], Ub = label_len[b];
   __shared__ float s_edge[2][32];  // [step parity][warp]: emit value leaving the last lane of each warp
+  if (Tb <= 0) {                    // empty utterance: no alignment exists
+    if (is_beta && i == 0) costs[b] = CUDART_INF_F;
+    return;
+  }
   const size_t base = (size_t)b * T * U1;
   const float* __restrict__ blank = ws.blank + base;
   const float* __restrict__ truth = ws.truth + base;
@@ -136,11 +140,11 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(const int32_t* __res
         const float bl = pb[k], tr = pt[k];
         float val;
         if (!is_beta) {
-          val = log_add_exp(stay, emit_in);
+          val = log_add_exp_fast(stay, emit_in);
           stay = val + bl;      // feeds a[t+1,u]
           new_emit = val + tr;  // feeds a[t,u+1]   (tr = -inf at u == Ub)
         } else {
-          val = log_add_exp(stay + bl, emit_in + tr);  // emit_in = be[t,u+1]; tr = -inf at u == Ub
+          val = log_add_exp_fast(stay + bl, emit_in + tr);  // emit_in = be[t,u+1]; tr = -inf at u == Ub
           stay = val;                                  // be[t,u] feeds be[t-1,u]
           new_emit = val;                              // and be[t,u-1]
         }
