@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — utterances/sec of the Conformer-S RNN-T training step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port: TF is not installable), rank 0 only
+
+One step = frontend (log-mel) -> Conformer-S encoder fwd -> prediction net -> joint -> RNN-T loss+grad -> backward ->
+gradient all-reduce -> Adam, on `configs[2]` of BASELINE.json: batch 32 x 10 s per GPU (weak scaling), 80-mel, vocab 1000,
+U = 64 labels, bf16 tensor-core operands / fp32 accumulation, dropout 0.1 on (training mode).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "utterances/sec (10 s, 80-mel) Conformer-S RNN-T training step"
+UNIT = "utterances/s"
+B_PER_GPU, N_SAMPLES, U_LABELS, VOCAB = 32, 160000, 64, 1000
+
+
+def peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        pk["_source"] = "measured"
+        return pk
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+def synth_batch(batch, seed, device="cpu", pin=False):
+    """SURVEY.md §8d synthetic inputs: 0.1*randn clipped audio, labels randint(1, V), predictions = [blank] + labels."""
+    g = torch.Generator().manual_seed(seed)
+    sig = (0.1 * torch.randn(batch, N_SAMPLES, generator=g)).clamp_(-1, 1)
+    sig_len = torch.full((batch,), N_SAMPLES, dtype=torch.int32)
+    labels = torch.randint(1, VOCAB, (batch, U_LABELS), generator=g, dtype=torch.int32)
+    lab_len = torch.full((batch,), U_LABELS, dtype=torch.int32)
+    pred = torch.cat([torch.zeros(batch, 1, dtype=torch.int32), labels], dim=1)
+    pred_len = lab_len + 1
+    ts = [sig, sig_len, pred, pred_len, labels, lab_len]
+    if pin:
+        ts = [t.pin_memory() for t in ts]
+    if device != "cpu":
+        ts = [t.to(device) for t in ts]
+    return ts
+
+
+def to_train_data(ts):
+    from tensorflowasr_b200 import schemas
+
+    sig, sig_len, pred, pred_len, labels, lab_len = ts
+    return schemas.TrainData(schemas.TrainInput(sig, sig_len, pred, pred_len), schemas.TrainLabel(labels, lab_len))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.15)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------- reference / CPU arm
+def cpu_reference_step_fn(batch):
+    """The reference's CPU path, as an oracle port (TensorFlow/Keras are not installable in this image): the torch-CPU
+    restatement in oracle/conformer.py of FeatureExtraction -> Conformer-S -> joint -> RNN-T loss, forward + backward + Adam,
+    fp32, all host threads.  Returns (step_fn, cores)."""
+    import numpy as np
+
+    from oracle import conformer as oc
+    from oracle import logmel
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = oc.ConformerConfig(vocab_size=VOCAB)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "moving" not in k) for k, v in oc.init_params(cfg, seed=42).items()}
+    leaves = [v for v in params.values() if v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=1e-4, betas=(0.9, 0.98), eps=1e-9)
+    sig, sig_len, pred, pred_len, labels, lab_len = synth_batch(batch, seed=1234)
+
+    def step():
+        feats, flen = logmel.feature_extraction(sig.numpy(), sig_len.numpy(), dtype=np.float32)
+        logits, llen = oc.transducer_forward(params, cfg, torch.from_numpy(feats), torch.from_numpy(flen).long(), pred, pred_len.long(),
+                                             training=True)
+        losses = oc.rnnt_loss_torch(logits, labels, llen.int(), lab_len, fast=True)
+        loss = losses.mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step, cores
+
+
+def time_cpu(batch, steps, warmup):
+    step, cores = cpu_reference_step_fn(batch)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.cpu_batch
+    val, ms, cores = time_cpu(batch, args.steps, args.warmup)
+    sample = f"{batch} x 10 s utterances per step (full Conformer-S train step, fp32), {args.steps} steps after {args.warmup} warm-up"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, batch_override=batch),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, batch_override=None):
+    b = batch_override if batch_override is not None else B_PER_GPU * n_gpus
+    return {"workload": "BASELINE.json configs[2]: Conformer-S Transducer (encoder-dim 144, 16 layers) RNN-T train step, batch=32x10 s per GPU",
+            "global_batch": b, "audio_seconds": 10, "labels_per_utterance": U_LABELS, "vocab": VOCAB, "mel": 80,
+            "parallelism": f"dp{n_gpus}", "dropout": 0.1,
+            "l2_policy": "no explicit flush: each step streams >6 GB (2.08 GB fp32 logits per 32 utterances) through a 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------- B200 arm
+def run_ours(args):
+    import tensorflowasr_b200 as tfasr
+    from tensorflowasr_b200 import _lib, ops
+    from tensorflowasr_b200 import dist as tdist
+
+    rank, world, dev = tdist.init_from_env()
+    assert dev.type == "cuda", "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    ops.set_precision("bf16")
+    torch.manual_seed(1234 + rank)
+    cfg = tfasr.conformer_small_config(vocab_size=VOCAB)
+    model = tfasr.Conformer(**cfg, seed=42).to(dev)
+    sched = tfasr.TransformerSchedule(dmodel=144, warmup_steps=10000, max_lr=0.05 / (144 ** 0.5), scale=2.0)
+    model.compile(optimizer=tfasr.make_optimizer(model, learning_rate=sched, beta_1=0.9, beta_2=0.98, epsilon=1e-9, weight_decay=1e-6))
+    model.train()
+
+    host = synth_batch(B_PER_GPU, seed=1234 + rank, pin=True)
+    resident = to_train_data([t.to(dev) for t in host])
+
+    def step_resident():
+        return model.train_step(resident)["loss"]
+
+    def step_e2e():
+        data = to_train_data([t.to(dev, non_blocking=True) for t in host])  # H2D from pinned memory, every step
+        losses = model.train_step(data)["loss"]
+        return losses.mean().item()  # D2H read of the step's loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item() / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    lib.tfasr_launch_count_reset()
+    ops.TIMERS.enable(True)
+    ms = timed(step_resident, args.steps)
+    kernel_ms = ops.TIMERS.report(args.steps)
+    ops.TIMERS.enable(False)
+    launches = lib.tfasr_launch_count()
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    gb = B_PER_GPU * world
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    # roofline of the dominant hand-written kernel group: RNN-T loss+grad (K1 + K2 + K3), HBM-bound.
+    T_enc, U1 = 250, U_LABELS + 1
+    alg_bytes = 8 * B_PER_GPU * T_enc * U1 * VOCAB
+    rn_ms = kernel_ms.get("rnnt_fwd", 0.0) + kernel_ms.get("rnnt_bwd", 0.0)
+    roofline = None
+    if rn_ms > 0:
+        ach = alg_bytes / (rn_ms * 1e-3) / 1e9
+        roofline = {"kernel": "rnnt_lse_kernel + rnnt_lattice_kernel + rnnt_grad_kernel (RNN-T loss+grad)", "bound": "hbm",
+                    "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                    "peak_source": pk["_source"], "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": rn_ms,
+                    "share_of_step": rn_ms / ms}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        val, cms, cores = time_cpu(args.cpu_batch, 2, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_batch} x 10 s utterances per step (full train step, fp32 oracle port), 2 steps after 1 warm-up"}
+    line = {
+        "metric": METRIC, "value": gb / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(world),
+        "e2e": {"value": gb / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "kernel_ms_per_step": kernel_ms,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=4, help="utterances per CPU step (bounded sample of the workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

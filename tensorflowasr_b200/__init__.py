@@ -9,3 +9,7 @@ from .features import FeatureExtraction, SpeechFeaturizer  # noqa: F401
 from .losses import BaseLoss, CtcLoss, RnntLoss, ctc_loss, rnnt_loss  # noqa: F401
 
 __version__ = "0.1.0"
+from . import ops  # noqa: F401,E402
+from .base_model import BaseModel, TransformerSchedule, make_optimizer  # noqa: F401,E402
+from .encoder import ConformerEncoder, Conv2dSubsampling  # noqa: F401,E402
+from .transducer import Conformer, Transducer, TransducerJoint, TransducerPrediction, conformer_small_config  # noqa: F401,E402

@@ -98,3 +98,44 @@ def stream_ptr(device=None) -> int:
 def require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{what}: the B200 hot path has no CPU fallback; got a {t.device} tensor")
+
+
+class _Timers:
+    """CUDA-event timers around named kernel groups, on the launching stream (enabled by bench.py only)."""
+
+    def __init__(self):
+        self.on = False
+        self.events = {}
+
+    def enable(self, flag: bool):
+        self.on = bool(flag)
+        if flag:
+            self.events = {}
+
+    class _Region:
+        def __init__(self, owner, name):
+            self.owner, self.name = owner, name
+
+        def __enter__(self):
+            if self.owner.on:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.owner.on:
+                self.e1.record()
+                self.owner.events.setdefault(self.name, []).append((self.e0, self.e1))
+            return False
+
+    def region(self, name):
+        return self._Region(self, name)
+
+    def report(self, steps: int) -> dict:
+        """-> {name: ms per step}; synchronises."""
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) / max(steps, 1) for k, v in self.events.items()}
+
+
+TIMERS = _Timers()

@@ -1,0 +1,243 @@
+"""BaseModel — host-side mirror of tensorflow_asr/models/base_model.py (the trainer / step functions) on B200.
+
+Keeps the reference's surface (`make`, `compile`, `train_step`, `_train_step`, `_apply_gradients`, `train_step_ga`,
+`test_step`, `predict_step`, `recognize`, `tokenizer`, base_model.py:33-331).  The distribution strategy
+(`tf.distribute.MirroredStrategy`, utils/env_util.py:57-70) becomes one process per GPU with a bucketed NCCL all-reduce of
+the gradients (`tensorflowasr_b200.dist`): the loss is scaled by 1/num_replicas and the gradients are SUMMED, exactly the
+arrangement base_model.py:166-173 describes.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import dist as tdist
+from . import schemas
+from .features import FeatureExtraction
+
+L2_DEFAULT = 1e-6  # models/encoders/conformer.py:27 (kernel_regularizer = l2(1e-6))
+
+
+class TransformerSchedule:
+    """optimizers/schedules.py:19-45: lr = scale * dmodel^-0.5 * min(step^-0.5, step * warmup^-1.5), clipped to [min_lr, max_lr]."""
+
+    def __init__(self, dmodel, scale=1.0, warmup_steps=4000, max_lr=None, min_lr=None):
+        self.dmodel, self.scale, self.warmup_steps = float(dmodel), float(scale), float(warmup_steps)
+        self.max_lr = eval(max_lr) if isinstance(max_lr, str) else max_lr
+        self.min_lr = eval(min_lr) if isinstance(min_lr, str) else min_lr
+
+    def __call__(self, current_step):
+        step = max(float(current_step), 1e-9)
+        lr = self.scale * (self.dmodel ** -0.5) * min(step ** -0.5, step * (self.warmup_steps ** -1.5))
+        if self.max_lr is not None:
+            lr = min(self.max_lr, lr)
+        if self.min_lr is not None:
+            lr = max(self.min_lr, lr)
+        return lr
+
+
+def make_optimizer(model: nn.Module, learning_rate=None, beta_1=0.9, beta_2=0.98, epsilon=1e-9, weight_decay=1e-6):
+    """Keras Adam as configured in small.yml.j2:73-87 (decoupled weight decay), on torch's fused multi-tensor Adam."""
+    lr0 = learning_rate(1) if callable(learning_rate) else (learning_rate or 1e-3)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=lr0, betas=(beta_1, beta_2), eps=epsilon, weight_decay=weight_decay or 0.0, fused=params[0].is_cuda)
+    opt._tfasr_schedule = learning_rate if callable(learning_rate) else None
+    return opt
+
+
+class BaseModel(nn.Module):
+    def __init__(self, speech_config: dict, name="base_model", **kwargs):
+        super().__init__()
+        self.name = name
+        self.feature_extraction = FeatureExtraction(**speech_config)
+        self._tokenizer = None
+        self.optimizer = None
+        self.tfasr_loss = None
+        self.use_ga = False
+        self.ga_steps = 1
+        self.gwn_config = None
+        self.gradn_config = None
+        self.l2 = L2_DEFAULT
+        self._iterations = 0
+        self._loss_sum = 0.0
+        self._loss_count = 0
+        self._reducer = None
+
+    # ------------------------------------------------------------------ misc surface
+    @property
+    def tokenizer(self):
+        return self._tokenizer
+
+    @tokenizer.setter
+    def tokenizer(self, tokenizer):
+        self._tokenizer = tokenizer
+
+    @property
+    def trainable_weights(self):
+        return [p for p in self.parameters() if p.requires_grad]
+
+    def make(self, input_shape=[None], prediction_shape=[None], batch_size=None, **kwargs) -> schemas.TrainOutput:
+        """Builds nothing (parameters exist from construction) but returns the per-replica output shapes like the reference
+        (base_model.py:68-100).  Dynamic dims stay None."""
+        assert batch_size is not None and batch_size > 0
+        self._batch_size = batch_size
+        self._per_replica_batch_size = int(batch_size / tdist.world_size())
+        n = input_shape[0]
+        u = prediction_shape[0]
+        t = None
+        if n is not None:
+            t = int(self.feature_extraction.get_nframes(n + self.feature_extraction.padding))
+            t = self._reduced_length(t)
+        return self._output_shapes(self._per_replica_batch_size, t, u)
+
+    def _reduced_length(self, t):
+        return t
+
+    def _output_shapes(self, b, t, u):
+        return schemas.TrainOutput(logits=(b, t, u, getattr(self, "vocab_size", None)), logits_length=(b,))
+
+    def compile(self, loss, optimizer=None, run_eagerly=False, ga_steps=None, gwn_config=None, gradn_config=None, **kwargs):
+        if optimizer is None or isinstance(optimizer, dict):
+            cfg = dict(optimizer or {})
+            optimizer = make_optimizer(self, **cfg.get("config", cfg))
+        self.optimizer = optimizer
+        if isinstance(ga_steps, int) and ga_steps > 1:
+            self.use_ga, self.ga_steps = True, ga_steps
+        else:
+            self.use_ga, self.ga_steps = False, 1
+        self.gwn_config = gwn_config
+        self.gradn_config = gradn_config
+        self.tfasr_loss = loss
+        self._reducer = tdist.GradientReducer(self.trainable_weights) if tdist.world_size() > 1 else None
+        return self
+
+    def call(self, inputs: schemas.TrainInput, training=False):
+        raise NotImplementedError()
+
+    def forward(self, inputs: schemas.TrainInput, training=False):
+        return self.call(inputs, training=training)
+
+    # ------------------------------------------------------------------ step functions
+    def compute_losses(self, data: schemas.TrainData, training=True):
+        """Per-utterance losses [B].  Default = the reference's route: y_pred = self(x); tfasr_loss.call(y, y_pred)."""
+        x, y = data
+        y_pred = self(x, training=training)
+        return self.tfasr_loss.call(y, y_pred)
+
+    def regularization_loss(self):
+        """Sum of the Keras l2(1e-6) regularizers attached to kernels and norm scales/offsets (conformer.py:27 and the
+        `*_regularizer=kernel_regularizer` arguments).  Applied through its gradient 2*l2*w in `_apply_gradients`."""
+        return sum(self.l2 * (p.float() ** 2).sum() for n, p in self.named_parameters() if _is_regularized(n) and p.requires_grad)
+
+    def tfasr_compute_loss(self, losses):
+        """base_model.py:137-147 + Keras `sum_over_batch_size` reduction, scaled by 1/num_replicas for the gradient SUM."""
+        return losses.mean() / tdist.world_size()
+
+    def _train_step(self, data: schemas.TrainData):
+        losses = self.compute_losses(data, training=True)
+        loss = self.tfasr_compute_loss(losses)
+        loss.backward()
+        self._last_losses = losses.detach()
+        return [p.grad for p in self.trainable_weights]
+
+    def _apply_gradients(self, gradients=None):
+        params = self.trainable_weights
+        if self._reducer is not None:
+            self._reducer.all_reduce()  # C1: one bucketed NCCL all-reduce (SUM) over NVLink
+        if self.l2:
+            reg = [p for n, p in self.named_parameters() if p.requires_grad and p.grad is not None and _is_regularized(n)]
+            if reg:
+                torch._foreach_add_([p.grad for p in reg], [p.detach() for p in reg], alpha=2.0 * self.l2)
+        self._iterations += 1
+        sched = getattr(self.optimizer, "_tfasr_schedule", None)
+        if sched is not None:
+            lr = sched(self._iterations)
+            for g in self.optimizer.param_groups:
+                g["lr"] = lr
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=False)
+        del params
+
+    def train_step(self, data: schemas.TrainData):
+        self._train_step(data)
+        self._apply_gradients()
+        return {"loss": self._last_losses}
+
+    def train_step_ga(self, data: schemas.TrainData, do_apply=None):
+        """Gradient accumulation (base_model.py:200-209): gradients accumulate in .grad across calls; apply on the last one."""
+        self._train_step(data)
+        if do_apply:
+            if self.ga_steps > 1:
+                torch._foreach_div_([p.grad for p in self.trainable_weights if p.grad is not None], float(self.ga_steps))
+            self._apply_gradients()
+        return {"loss": self._last_losses}
+
+    @torch.no_grad()
+    def test_step(self, data: schemas.TrainData):
+        losses = self.compute_losses(data, training=False)
+        return {"loss": losses}
+
+    @torch.no_grad()
+    def predict_step(self, data: schemas.TrainData):
+        x, y_true = data
+        batch_size = x.inputs.shape[0]
+        inputs = schemas.PredictInput(
+            inputs=x.inputs, inputs_length=x.inputs_length, previous_tokens=self.get_initial_tokens(batch_size=batch_size),
+            previous_encoder_states=self.get_initial_encoder_states(batch_size=batch_size),
+            previous_decoder_states=self.get_initial_decoder_states(batch_size=batch_size))
+        _tokens = self.recognize(inputs=inputs).tokens
+        _beam_tokens = self.recognize_beam(inputs=inputs).tokens
+        return {"tokens": _tokens, "beam_tokens": _beam_tokens, "labels": y_true.labels}
+
+    # ------------------------------------------------------------------ inference surface
+    def get_initial_tokens(self, batch_size=1):
+        return torch.zeros(batch_size, 1, dtype=torch.int32, device=next(self.parameters()).device)
+
+    def get_initial_encoder_states(self, batch_size=1):
+        return None
+
+    def get_initial_decoder_states(self, batch_size=1):
+        return None
+
+    def recognize(self, inputs: schemas.PredictInput, **kwargs) -> schemas.PredictOutput:
+        raise NotImplementedError()
+
+    def recognize_beam(self, inputs: schemas.PredictInput, beam_width: int = 10, **kwargs) -> schemas.PredictOutput:
+        raise NotImplementedError()
+
+    # ------------------------------------------------------------------ weights by reference name
+    def named_weights(self) -> dict:
+        """{reference-style name: tensor}, e.g. 'encoder.block_0.ln.gamma', 'prediction.lstm_0.kernel', 'joint.vocab.kernel'."""
+        out = {}
+        for prefix, mod in self._weight_groups().items():
+            for n, t in mod.named().items():
+                out[f"{prefix}.{n}"] = t
+        return out
+
+    def load_named_weights(self, tensors: dict, strict=True):
+        for prefix, mod in self._weight_groups().items():
+            mod.load_named(tensors, prefix=prefix + ".", strict=strict)
+
+    def _weight_groups(self) -> dict:
+        groups = {}
+        if hasattr(self, "encoder"):
+            groups["encoder"] = self.encoder
+            if hasattr(self.encoder, "conv_subsampling"):
+                groups["encoder.subsampling"] = self.encoder.conv_subsampling
+        if hasattr(self, "predict_net"):
+            groups["prediction"] = self.predict_net
+        if hasattr(self, "joint_net"):
+            groups["joint"] = self.joint_net
+        if hasattr(self, "decoder"):
+            groups["decoder"] = self.decoder
+        return groups
+
+
+def _is_regularized(param_name: str) -> bool:
+    """Keras: kernel_regularizer on kernels / embeddings, and on LN/BN gamma & beta; bias_regularizer is None."""
+    n = param_name.replace("__", ".")
+    if n.endswith("bias") or "attention_bias" in n:
+        return False
+    return n.endswith(("kernel", "gamma", "beta", "embeddings"))

@@ -137,11 +137,12 @@ class FeatureExtraction(torch.nn.Module):
         feats = torch.empty((B, max(T, 0), self.num_feature_bins), dtype=torch.float32, device=x.device)
         lens_in = signals_length.to(device=x.device, dtype=torch.int32).contiguous()
         lens_out = torch.empty_like(lens_in)
-        _lib.check(
-            lib.tfasr_logmel_f32(_lib.ptr(x), _lib.ptr(lens_in), B, N, ctypes.byref(cfg), _lib.ptr(table), _lib.ptr(feats),
-                                 _lib.ptr(lens_out), stream),
-            "tfasr_logmel_f32",
-        )
+        with _lib.TIMERS.region("logmel"):
+            _lib.check(
+                lib.tfasr_logmel_f32(_lib.ptr(x), _lib.ptr(lens_in), B, N, ctypes.byref(cfg), _lib.ptr(table), _lib.ptr(feats),
+                                     _lib.ptr(lens_out), stream),
+                "tfasr_logmel_f32",
+            )
         if self._normalize_zscore or self._normalize_min_max:
             mode = 0 if self._normalize_zscore else 1
             # min_value = self.logarithm(self.epsilon): logarithm() adds epsilon again (feature_extraction.py:185,215)
