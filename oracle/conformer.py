@@ -371,30 +371,71 @@ def rnnt_loss_torch(logits, labels, logit_length, label_length, fast=False):
     return _RnntLossOracleFn.apply(logits, labels, logit_length, label_length)
 
 
-def greedy_decode(enc_b, p, cfg, blank=0):
-    """Greedy transducer walk over one utterance's encoder frames (Transducer.recognize_batch, base_transducer.py:496-575):
-    on blank advance the frame, otherwise emit and update (token, LSTM state); at most 2T+1 emitted symbols.
-    Returns (tokens, smallest top-2 log-prob margin seen) — the margin tells a test whether an argmax was a near-tie."""
-    T = enc_b.shape[0]
+def _call_next(frame, tok, h, c, p):
+    """Transducer.call_next (base_transducer.py:437-464) for a batch: frame [B,1,D], tok [B,1] -> (log-probs [B,V], h, c)."""
+    emb = p["prediction.embedding.embeddings"][tok.long()]
+    y, (h2, c2) = lstm(emb, None, p, "prediction.lstm_0", state=(h, c))
+    y = layer_norm(y, p, "prediction.ln_0")
+    return torch.log_softmax(joint_net(frame, y, p)[:, 0, 0], -1), h2, c2
+
+
+def _margin(lp):
+    top = torch.topk(lp, 2, dim=-1).values
+    return float((top[..., 0] - top[..., 1]).min())
+
+
+def greedy_single(enc, nframes, p, cfg, blank=0, max_tokens_per_frame=3):
+    """Transducer.recognize_single restated (base_transducer.py:577-712); enc [1,T,D].  Returns (tokens list incl. blank padding,
+    smallest top-2 margin seen: tells a test whether an argmax was a near-tie)."""
     R = cfg.rnn_units
-    h = enc_b.new_zeros(1, R)
-    c = enc_b.new_zeros(1, R)
+    h, c = enc.new_zeros(1, R), enc.new_zeros(1, R)
     tok = torch.tensor([[blank]])
-    t, out, margin = 0, [], float("inf")
-    max_tokens = 2 * T + 1
-    while t < T and len(out) < max_tokens:
-        emb = p["prediction.embedding.embeddings"][tok.long()]
-        y, (h2, c2) = lstm(emb, None, p, "prediction.lstm_0", state=(h, c))
-        y = layer_norm(y, p, "prediction.ln_0")
-        logits = joint_net(enc_b[None, t : t + 1], y, p)[0, 0, 0]
-        lp = torch.log_softmax(logits, -1)
-        top = torch.topk(lp, 2).values
-        margin = min(margin, float(top[0] - top[1]))
-        k = int(lp.argmax())
+    toks = [blank] * (nframes * max_tokens_per_frame)
+    frame, token_index, per_frame, margin = 0, -1, 0, float("inf")
+    while frame < nframes:
+        lp, h2, c2 = _call_next(enc[:, frame : frame + 1], tok, h, c, p)
+        margin = min(margin, _margin(lp))
+        k = int(lp[0].argmax())
         if k == blank:
-            t += 1
+            frame, per_frame = frame + 1, 0
         else:
-            out.append(k)
+            per_frame += 1
+            token_index += 1
+            toks[token_index] = k
             tok = torch.tensor([[k]])
             h, c = h2, c2
-    return out, margin
+            if per_frame >= max_tokens_per_frame:
+                frame, per_frame = frame + 1, 0
+    return toks, margin
+
+
+def greedy_batch(enc, enc_len, p, cfg, blank=0):
+    """Transducer.recognize_batch restated verbatim (base_transducer.py:496-575), quirks included.  enc [B,T,D]."""
+    B, T, _ = enc.shape
+    R = cfg.rnn_units
+    h, c = enc.new_zeros(B, R), enc.new_zeros(B, R)
+    prev = torch.full((B, 1), blank, dtype=torch.long)
+    nframes = enc_len.long()[:, None]
+    frame_idx = torch.zeros(B, 1, dtype=torch.long)
+    max_tokens = 2 * T + 1
+    tokens = torch.full((B, max_tokens), blank, dtype=torch.long)
+    tok_idx = torch.ones(B, 1, dtype=torch.long)
+    rows = torch.arange(B)
+    margin = float("inf")
+    while not (bool((frame_idx >= nframes - 1).all()) or bool((tok_idx >= max_tokens - 1).all())):
+        cur_frames = enc[rows, torch.minimum(frame_idx, nframes - 1)[:, 0]].unsqueeze(1)
+        lp, h2, c2 = _call_next(cur_frames, prev, h, c, p)
+        cur = lp.argmax(-1)[:, None]
+        eq_blank = (cur == blank) | (tok_idx >= max_tokens) | (frame_idx > nframes)
+        live = ~((tok_idx >= max_tokens) | (frame_idx > nframes))[:, 0]
+        if bool(live.any()):
+            margin = min(margin, _margin(lp[live]))
+        upd_tok = torch.where(eq_blank, torch.full_like(cur, blank), cur)[:, 0]
+        upd_idx = torch.where(eq_blank, torch.zeros_like(tok_idx), torch.clamp(tok_idx + 1, max=max_tokens - 1))[:, 0]
+        tokens[rows, upd_idx] = upd_tok
+        tok_idx = torch.where(eq_blank, tok_idx, torch.clamp(tok_idx + 1, max=max_tokens - 1))
+        frame_idx = torch.where(eq_blank, frame_idx + 1, frame_idx)
+        prev = torch.where(eq_blank, prev, cur)
+        h = torch.where(eq_blank, h, h2)
+        c = torch.where(eq_blank, c, c2)
+    return tokens, margin

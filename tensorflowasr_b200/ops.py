@@ -339,7 +339,8 @@ def lstm(x, length, kernel, recurrent_kernel, bias, state=None):
         c0 = x.new_zeros(1, B, R, dtype=torch.float32)
     else:
         h0, c0 = state[0].float().reshape(1, B, R).contiguous(), state[1].float().reshape(1, B, R).contiguous()
-    y, h, c = torch._VF.lstm(x.float().contiguous(), (h0, c0), [w_ih, w_hh, b_ih, b_hh], True, 1, 0.0, False, False, True)
+    train = torch.is_grad_enabled() and (x.requires_grad or kernel.requires_grad)  # cuDNN keeps its reserve space only in train mode
+    y, h, c = torch._VF.lstm(x.float().contiguous(), (h0, c0), [w_ih, w_hh, b_ih, b_hh], True, 1, 0.0, train, False, True)
     if length is not None:
         mask = torch.arange(U, device=x.device)[None, :] < length.to(x.device)[:, None]
         y = y * mask[..., None]

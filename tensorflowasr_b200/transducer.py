@@ -173,35 +173,75 @@ class Transducer(BaseModel):
 
     @torch.no_grad()
     def recognize(self, inputs: schemas.PredictInput, max_tokens_per_frame: int = 3, **kwargs):
-        """Greedy decode (base_transducer.py:474-712): per utterance, walk the encoder frames; on blank advance the frame, otherwise
-        emit and update (token, LSTM state).  Batched over utterances; tokens [B, 2T'+1] (blank-padded), like `recognize_batch`."""
+        """Greedy decode dispatcher (base_transducer.py:474-494): batch 1 -> recognize_single, otherwise recognize_batch."""
+        if inputs.inputs.shape[0] == 1:
+            return self.recognize_single(inputs, max_tokens_per_frame=max_tokens_per_frame, **kwargs)
+        return self.recognize_batch(inputs, **kwargs)
+
+    def _encode_for_decode(self, inputs):
         features, features_length = self.feature_extraction((inputs.inputs, inputs.inputs_length), training=False)
-        enc, enc_len, _ = self.encoder.call_next(features, features_length, inputs.previous_encoder_states)
-        B, T, _ = enc.shape
+        enc, enc_len, next_enc_states = self.encoder.call_next(features, features_length, inputs.previous_encoder_states)
+        B = enc.shape[0]
         dev = enc.device
         enc_len = torch.as_tensor(enc_len, device=dev).to(torch.int64)
-        tokens_prev = (inputs.previous_tokens if inputs.previous_tokens is not None else self.get_initial_tokens(B)).to(dev).to(torch.int32)
+        prev_tok = (inputs.previous_tokens if inputs.previous_tokens is not None else self.get_initial_tokens(B)).to(dev).to(torch.int32)
         states = (inputs.previous_decoder_states if inputs.previous_decoder_states is not None else self.get_initial_decoder_states(B)).to(dev)
-        max_tokens = 2 * T + 1  # base_transducer.py:515
-        out = torch.full((B, max_tokens), self.blank, dtype=torch.int32, device=dev)
-        t_idx = torch.zeros(B, dtype=torch.int64, device=dev)
-        n_out = torch.zeros(B, dtype=torch.int64, device=dev)
+        return enc, enc_len, next_enc_states, prev_tok, states
+
+    @torch.no_grad()
+    def recognize_single(self, inputs: schemas.PredictInput, max_tokens_per_frame: int = 3, **kwargs):
+        """base_transducer.py:577-712 (batch 1): walk the frames; a frame is left on blank or after `max_tokens_per_frame`
+        non-blank symbols; tokens [1, nframes * max_tokens_per_frame], blank-padded."""
+        enc, enc_len, next_enc_states, prev_tok, states = self._encode_for_decode(inputs)
+        nframes = int(enc_len[0])
+        toks = torch.full((max(nframes, 0) * max_tokens_per_frame,), self.blank, dtype=torch.int32, device=enc.device)
+        frame, token_index, per_frame = 0, -1, 0
+        while frame < nframes:
+            logp, new_states = self.call_next(enc[:, frame : frame + 1], prev_tok, states)
+            cur = int(logp[0, 0, 0].argmax())
+            if cur == self.blank:
+                frame, per_frame = frame + 1, 0
+            else:
+                per_frame += 1
+                token_index += 1
+                toks[token_index] = cur
+                prev_tok = torch.full_like(prev_tok, cur)
+                states = new_states
+                if per_frame >= max_tokens_per_frame:
+                    frame, per_frame = frame + 1, 0
+        return schemas.PredictOutput(tokens=toks[None, :], next_tokens=prev_tok, next_encoder_states=next_enc_states, next_decoder_states=states)
+
+    @torch.no_grad()
+    def recognize_batch(self, inputs: schemas.PredictInput, **kwargs):
+        """base_transducer.py:496-575, loop semantics kept verbatim (including its quirks): the loop runs until EVERY utterance has
+        reached its last frame index (nframes - 1) or the token budget; finished utterances keep reading their clamped last frame until
+        frame_index > nframes; emitted symbols are stored from column 2 on (tokens_indices starts at 1), blanks overwrite column 0;
+        tokens [B, 2 * T' + 1]."""
+        enc, enc_len, next_enc_states, prev_tok, states = self._encode_for_decode(inputs)
+        B, T, _ = enc.shape
+        dev = enc.device
+        nframes = enc_len[:, None]  # [B,1]
+        frame_idx = torch.zeros(B, 1, dtype=torch.int64, device=dev)
+        max_tokens = T * 2 + 1
+        tokens = torch.full((B, max_tokens), self.blank, dtype=torch.int32, device=dev)
+        tok_idx = torch.ones(B, 1, dtype=torch.int64, device=dev)
         rows = torch.arange(B, device=dev)
-        for _ in range(max_tokens):
-            active = (t_idx < enc_len) & (n_out < max_tokens)
-            if not bool(active.any()):
+        while True:
+            stop = bool((frame_idx >= nframes - 1).all()) or bool((tok_idx >= max_tokens - 1).all())
+            if stop:
                 break
-            frame = enc[rows, t_idx.clamp(max=T - 1)].unsqueeze(1)
-            logp, new_states = self.call_next(frame, tokens_prev, states)
-            pred = logp[:, 0, 0].argmax(-1).to(torch.int32)
-            is_blank = pred == self.blank
-            emit = active & ~is_blank
-            out[rows[emit], n_out[emit]] = pred[emit]
-            n_out = n_out + emit.long()
-            t_idx = t_idx + (active & is_blank).long()
-            tokens_prev = torch.where(emit[:, None], pred[:, None], tokens_prev)
-            states = torch.where(emit[:, None, None, None], new_states, states)
-        return schemas.PredictOutput(tokens=out, next_tokens=tokens_prev, next_encoder_states=None, next_decoder_states=states)
+            cur_frames = enc[rows, torch.minimum(frame_idx, nframes - 1)[:, 0]].unsqueeze(1)
+            logp, new_states = self.call_next(cur_frames, prev_tok, states)
+            cur = logp[:, 0, 0].argmax(-1).to(torch.int32)[:, None]  # [B,1]
+            eq_blank = (cur == self.blank) | (tok_idx >= max_tokens) | (frame_idx > nframes)
+            upd_tok = torch.where(eq_blank, torch.full_like(cur, self.blank), cur)[:, 0]
+            upd_idx = torch.where(eq_blank, torch.zeros_like(tok_idx), torch.clamp(tok_idx + 1, max=max_tokens - 1))[:, 0]
+            tokens[rows, upd_idx] = upd_tok
+            tok_idx = torch.where(eq_blank, tok_idx, torch.clamp(tok_idx + 1, max=max_tokens - 1))
+            frame_idx = torch.where(eq_blank, frame_idx + 1, frame_idx)
+            prev_tok = torch.where(eq_blank, prev_tok, cur)
+            states = torch.where(eq_blank[:, :, None, None], states, new_states)
+        return schemas.PredictOutput(tokens=tokens, next_tokens=prev_tok, next_encoder_states=next_enc_states, next_decoder_states=states)
 
     def recognize_beam(self, inputs: schemas.PredictInput, beam_width: int = 10, **kwargs):
         """The reference's transducer beam search is a stub that returns greedy (base_transducer.py:841-842); mirrored."""
