@@ -112,6 +112,36 @@ int tfasr_ctc_loss_f32(const float* logits, const int32_t* labels, const int32_t
                        int32_t B, int32_t T, int32_t L, int32_t V, int32_t blank, float* costs, float* grads,
                        const float* grad_scale, void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * bf16 tensor-core GEMM (tcgen05 / TMEM / TMA) with fused epilogues:  C[M,N] = epilogue(alpha * A . B^T)
+ * Replaces the cuBLAS calls behind keras Dense / EinsumDense / 1x1 Conv1D in the reference
+ * (conformer.py:72-87,293-352,591; multihead_attention.py:628-654; base_transducer.py:285-292) and their backward.
+ *   default ("TN"): A [M,K] bf16 row-major (lda), B [N,K] bf16 row-major (ldb) — both K-major
+ *   a_mn_major = b_mn_major = 1: A source is [K,M] row-major, B source is [K,N] row-major (C = A^T . B; used for weight
+ *   gradients dW = X^T . dY without materialising transposes)
+ * All leading dimensions in elements; bf16 pointers 16-byte aligned, ld * 2 bytes a multiple of 16.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* bias;      /* [N] f32, added after alpha * acc; NULL = none */
+  void* aux;              /* optional bf16 [M, ld_aux]: copy of (alpha * acc + bias) before activation / GLU (kept for backward) */
+  const void* residual;   /* optional bf16 [M, ld_residual]: out = residual + residual_scale * value */
+  const void* mul;        /* optional bf16 [M, ld_mul]: value *= g(mul), g per mul_mode (backward epilogues) */
+  float* colsum;          /* optional f32 [N]: += column sums of the final value (bias gradients); must be zeroed by the caller */
+  int32_t ld_aux, ld_residual, ld_mul;
+  int32_t c_f32;          /* 0: C is bf16, 1: C is f32 */
+  int32_t activation;     /* 0 none, 1 swish, 2 relu, 3 tanh */
+  int32_t glu;            /* 1: columns are interleaved (a_j, b_j) pairs; C [M, N/2] = a * sigmoid(b)  (activations/glu.py:25-28) */
+  int32_t mul_mode;       /* 0 none, 1: d swish(mul)/d mul, 2: 1 - mul^2 (tanh'), 3: mul */
+  float residual_scale;   /* e.g. 0.5 for the macaron FFN (models/layers/residual.py:58-62) */
+  float alpha;            /* accumulator scale, normally 1 */
+  float dropout_p;        /* 0 = off; keep mask = hash(dropout_seed, row * N + col) >= p, kept values scaled by 1/(1-p) */
+  unsigned long long dropout_seed;
+} tfasr_gemm_epilogue;
+
+int tfasr_gemm_bf16(const void* A, const void* B, void* C, int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc,
+                    int32_t a_mn_major, int32_t b_mn_major, const tfasr_gemm_epilogue* epilogue /* NULL = plain bf16 store */,
+                    tfasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

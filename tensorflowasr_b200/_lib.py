@@ -26,6 +26,17 @@ class LogmelCfg(ctypes.Structure):
     ]
 
 
+class GemmEpilogue(ctypes.Structure):
+    """Mirror of `tfasr_gemm_epilogue`."""
+
+    _fields_ = [
+        ("bias", c_void_p), ("aux", c_void_p), ("residual", c_void_p), ("mul", c_void_p), ("colsum", c_void_p),
+        ("ld_aux", c_int32), ("ld_residual", c_int32), ("ld_mul", c_int32), ("c_f32", c_int32), ("activation", c_int32),
+        ("glu", c_int32), ("mul_mode", c_int32), ("residual_scale", c_float), ("alpha", c_float), ("dropout_p", c_float),
+        ("dropout_seed", ctypes.c_ulonglong),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/tfasr_b200.h declares
 SIGNATURES = {
     "tfasr_version": (c_int32, []),
@@ -45,6 +56,8 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
     "tfasr_rnnt_loss_bwd_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tfasr_gemm_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                  POINTER(GemmEpilogue), c_void_p]),
     "tfasr_ctc_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "tfasr_ctc_loss_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
