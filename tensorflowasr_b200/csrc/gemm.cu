@@ -85,7 +85,8 @@ constexpr int kBK = 64;
 
 template <int BN>
 struct GemmSmem {
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static_assert(STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1280 <= 227 * 1024, "smem budget");
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int TOTAL = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
