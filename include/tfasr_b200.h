@@ -134,13 +134,33 @@ typedef struct {
   int32_t mul_mode;       /* 0 none, 1: d swish(mul)/d mul, 2: 1 - mul^2 (tanh'), 3: mul */
   float residual_scale;   /* e.g. 0.5 for the macaron FFN (models/layers/residual.py:58-62) */
   float alpha;            /* accumulator scale, normally 1 */
-  float dropout_p;        /* 0 = off; keep mask = hash(dropout_seed, row * N + col) >= p, kept values scaled by 1/(1-p) */
-  unsigned long long dropout_seed;
+  float dropout_p;        /* 0 = off; keep mask = hash(*dropout_seed_ptr + dropout_salt, row * N + col) >= p, kept values * 1/(1-p) */
+  int32_t atomic_out;     /* 1: atomicAdd into the f32 C (split-K partial sums, gradient accumulation) */
+  int32_t k_splits;       /* > 1: split the contraction over gridDim.z CTAs (requires atomic_out) */
+  const unsigned long long* dropout_seed_ptr; /* DEVICE counter (NULL = 0): bumped once per step, so replayed CUDA graphs differ */
+  unsigned long long dropout_salt;            /* per-call-site constant */
 } tfasr_gemm_epilogue;
 
 int tfasr_gemm_bf16(const void* A, const void* B, void* C, int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc,
                     int32_t a_mn_major, int32_t b_mn_major, const tfasr_gemm_epilogue* epilogue /* NULL = plain bf16 store */,
                     tfasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise fused kernels of the Conformer block (bf16 activations, fp32 statistics).
+ *   layernorm: keras LayerNormalization(eps) over the last axis (conformer.py:63,152,284,424-499); x is bf16 or f32, y bf16.
+ *     bwd: dx = LN'(dy) (+ dres, the gradient arriving through the residual branch: models/layers/residual.py:58-62),
+ *          dgamma / dbeta accumulate (+=) into f32 [D] buffers (may be NULL).
+ *   scale_mask_colsum: out = scale * dropout_mask * in (+ add); colsum (+=) column sums of out — the module-entry step of
+ *     backward (dropout backward + bias gradient), mask regenerated from hash(*seed_ptr + salt, row * N + col).
+ *   glu_bwd: backward of a * sigmoid(b) on interleaved (a, b) column pairs (activations/glu.py:25-28).
+ * ---------------------------------------------------------------------------------------------- */
+int tfasr_layernorm_fwd(const void* x, int32_t x_is_f32, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                        int32_t M, int32_t D, float eps, tfasr_stream_t stream);
+int tfasr_layernorm_bwd(const void* dy, const void* x, int32_t x_is_f32, const float* mean, const float* rstd, const float* gamma,
+                        const void* dres, void* dx, float* dgamma, float* dbeta, int32_t M, int32_t D, tfasr_stream_t stream);
+int tfasr_scale_mask_colsum(const void* in, const void* add, void* out, float* colsum, int32_t M, int32_t N, float scale, float dropout_p,
+                            const unsigned long long* seed_ptr, unsigned long long salt, tfasr_stream_t stream);
+int tfasr_glu_bwd(const void* aux, const void* dg, void* daux, float* colsum, int32_t M, int32_t D, tfasr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ class GemmEpilogue(ctypes.Structure):
         ("bias", c_void_p), ("aux", c_void_p), ("residual", c_void_p), ("mul", c_void_p), ("colsum", c_void_p),
         ("ld_aux", c_int32), ("ld_residual", c_int32), ("ld_mul", c_int32), ("c_f32", c_int32), ("activation", c_int32),
         ("glu", c_int32), ("mul_mode", c_int32), ("residual_scale", c_float), ("alpha", c_float), ("dropout_p", c_float),
-        ("dropout_seed", ctypes.c_ulonglong),
+        ("atomic_out", c_int32), ("k_splits", c_int32), ("dropout_seed_ptr", c_void_p), ("dropout_salt", ctypes.c_ulonglong),
     ]
 
 
@@ -58,6 +58,12 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tfasr_gemm_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                   POINTER(GemmEpilogue), c_void_p]),
+    "tfasr_layernorm_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
+    "tfasr_layernorm_bwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int32, c_int32, c_void_p]),
+    "tfasr_scale_mask_colsum": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p,
+                                          ctypes.c_ulonglong, c_void_p]),
+    "tfasr_glu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "tfasr_ctc_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "tfasr_ctc_loss_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

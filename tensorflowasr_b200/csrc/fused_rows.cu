@@ -1,0 +1,259 @@
+// Row-wise fused kernels of the Conformer block (sm_100a, HBM-bound, bf16 activations / fp32 statistics).
+//
+// Replace the chains of TF/Keras elementwise + reduction kernels around every Dense layer of the reference:
+//   LayerNormalization fwd/bwd      tensorflow_asr/models/encoders/conformer.py:63,152,284,424-499 (keras LN, eps 1e-3)
+//   residual add                    models/layers/residual.py:58-62   (fused into the LN backward / GEMM epilogues)
+//   dropout backward + bias grads   models/layers/general.py Dropout   (mask regenerated from the counter-based hash)
+//   GLU backward                    models/activations/glu.py:25-28
+// One warp per row; rows are D <= 1024 wide (D = 144 in Conformer-S, 320 in the prediction net).
+#include "common.cuh"
+
+namespace tfasr {
+
+__device__ __forceinline__ float hash_uniform_(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+constexpr int kRowsWarps = 8;
+constexpr int kMaxPerLane = 32;  // D <= 1024
+
+// ---------------------------------------------------------------------------------------------- LayerNorm forward
+// NPL = values per lane (compile time, so the row lives in registers): D <= 32 * NPL.
+template <typename TIn, int NPL>
+__global__ void __launch_bounds__(kRowsWarps * 32) layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                                        float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
+                                                                        float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const TIn* xr = x + (size_t)row * D;
+  float v[NPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int j = lane + 32 * i;
+    v[i] = (j < D) ? (float)xr[j] : 0.f;
+    s += v[i];
+  }
+  s = warp_sum(s);
+  const float mean = s / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int j = lane + 32 * i;
+    const float d = (j < D) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q / (float)D + eps);
+  __nv_bfloat16* yr = y + (size_t)row * D;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int j = lane + 32 * i;
+    if (j < D) yr[j] = __float2bfloat16((v[i] - mean) * rstd * gamma[j] + beta[j]);
+  }
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm backward
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma          (+ dres: the residual branch's gradient)
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (CTA-level partial sums in SMEM, then one atomic per column per CTA)
+template <typename TIn, int NPL>
+__global__ void __launch_bounds__(kRowsWarps * 32) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x,
+                                                                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                                        const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
+                                                                        __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                                        float* __restrict__ dbeta, int M, int D, int rows_per_warp) {
+  extern __shared__ float s_acc[];  // [2][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) s_acc[j] = 0.f;
+  __syncthreads();
+  float ag[NPL], ab[NPL], gm[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int j = lane + 32 * i;
+    ag[i] = ab[i] = 0.f;
+    gm[i] = (j < D) ? gamma[j] : 0.f;
+  }
+  const int row0 = (blockIdx.x * kRowsWarps + warp) * rows_per_warp;
+  for (int r = 0; r < rows_per_warp; ++r) {
+    const int row = row0 + r;
+    if (row >= M) break;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const __nv_bfloat16* dyr = dy + (size_t)row * D;
+    const TIn* xr = x + (size_t)row * D;
+    float g[NPL], xh[NPL];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int j = lane + 32 * i;
+      const float d = (j < D) ? __bfloat162float(dyr[j]) : 0.f;
+      xh[i] = (j < D) ? ((float)xr[j] - mean) * rstd : 0.f;
+      g[i] = d * gm[i];
+      sg += g[i];
+      sgx += g[i] * xh[i];
+      ag[i] += d * xh[i];
+      ab[i] += d;
+    }
+    sg = warp_sum(sg) / (float)D;
+    sgx = warp_sum(sgx) / (float)D;
+    __nv_bfloat16* dxr = dx + (size_t)row * D;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int j = lane + 32 * i;
+      if (j < D) {
+        float o = rstd * (g[i] - sg - xh[i] * sgx);
+        if (dres) o += __bfloat162float(dres[(size_t)row * D + j]);
+        dxr[j] = __float2bfloat16(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int j = lane + 32 * i;
+    if (j < D) {
+      atomicAdd(&s_acc[j], ag[i]);
+      atomicAdd(&s_acc[D + j], ab[i]);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + j, s_acc[j]);
+    if (dbeta) atomicAdd(dbeta + j, s_acc[D + j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- elementwise helpers
+// out = scale * dropout_mask * in (bf16) [+ add], colsum += column sums of out.   [M, N] row-major, N even.
+__global__ void __launch_bounds__(256) scale_mask_colsum_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ add,
+                                                                __nv_bfloat16* __restrict__ out, float* __restrict__ colsum, int M, int N,
+                                                                float scale, float drop_p, const unsigned long long* __restrict__ seed_ptr,
+                                                                unsigned long long salt, int rows_per_block) {
+  // block = [rows_per_block rows] x all columns; thread t handles column pair (2t, 2t+1) (+ stride blockDim for wide N)
+  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const unsigned long long seed = (drop_p > 0.f && seed_ptr) ? (*seed_ptr + salt) : salt;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  for (int c = 2 * threadIdx.x; c < N; c += 2 * blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const size_t idx = (size_t)r * N + c;
+      const __nv_bfloat162 vi = *reinterpret_cast<const __nv_bfloat162*>(in + idx);
+      float a = __low2float(vi) * scale, b = __high2float(vi) * scale;
+      if (drop_p > 0.f) {
+        a = hash_uniform_(seed, idx) >= drop_p ? a * keep_scale : 0.f;
+        b = hash_uniform_(seed, idx + 1) >= drop_p ? b * keep_scale : 0.f;
+      }
+      if (add) {
+        const __nv_bfloat162 va = *reinterpret_cast<const __nv_bfloat162*>(add + idx);
+        a += __low2float(va);
+        b += __high2float(va);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(out + idx) = __floats2bfloat162_rn(a, b);
+      s0 += a;
+      s1 += b;
+    }
+    if (colsum) {
+      atomicAdd(colsum + c, s0);
+      atomicAdd(colsum + c + 1, s1);
+    }
+  }
+}
+
+// GLU backward on interleaved (a, b) pairs: aux [M, 2D] pre-GLU values, dg [M, D] -> daux [M, 2D]; colsum [2D] += column sums.
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const __nv_bfloat16* __restrict__ aux, const __nv_bfloat16* __restrict__ dg,
+                                                      __nv_bfloat16* __restrict__ daux, float* __restrict__ colsum, int M, int D,
+                                                      int rows_per_block) {
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float sa = 0.f, sb = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const __nv_bfloat162 ab = *reinterpret_cast<const __nv_bfloat162*>(aux + (size_t)r * 2 * D + 2 * c);
+      const float a = __low2float(ab), b = __high2float(ab);
+      const float g = __bfloat162float(dg[(size_t)r * D + c]);
+      const float sg = 1.0f / (1.0f + __expf(-b));
+      const float da = g * sg;
+      const float db = g * a * sg * (1.0f - sg);
+      *reinterpret_cast<__nv_bfloat162*>(daux + (size_t)r * 2 * D + 2 * c) = __floats2bfloat162_rn(da, db);
+      sa += da;
+      sb += db;
+    }
+    if (colsum) {
+      atomicAdd(colsum + 2 * c, sa);
+      atomicAdd(colsum + 2 * c + 1, sb);
+    }
+  }
+}
+
+}  // namespace tfasr
+
+using namespace tfasr;
+
+extern "C" int tfasr_layernorm_fwd(const void* x, int32_t x_is_f32, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                   int32_t M, int32_t D, float eps, tfasr_stream_t stream) {
+  if (!x || !gamma || !beta || !y || !mean || !rstd || M < 0 || D < 1 || D > 32 * kMaxPerLane) return TFASR_INVALID_VALUE;
+  if (M == 0) return TFASR_OK;
+  const unsigned grid = (unsigned)ceil_div(M, kRowsWarps);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LN_FWD(T, NPL) layernorm_fwd_kernel<T, NPL><<<grid, kRowsWarps * 32, 0, st>>>(static_cast<const T*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps)
+  if (x_is_f32) {
+    if (D <= 160) LN_FWD(float, 5); else if (D <= 320) LN_FWD(float, 10); else if (D <= 640) LN_FWD(float, 20); else LN_FWD(float, 32);
+  } else {
+    if (D <= 160) LN_FWD(__nv_bfloat16, 5); else if (D <= 320) LN_FWD(__nv_bfloat16, 10); else if (D <= 640) LN_FWD(__nv_bfloat16, 20); else LN_FWD(__nv_bfloat16, 32);
+  }
+#undef LN_FWD
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_layernorm_bwd(const void* dy, const void* x, int32_t x_is_f32, const float* mean, const float* rstd, const float* gamma,
+                                   const void* dres, void* dx, float* dgamma, float* dbeta, int32_t M, int32_t D, tfasr_stream_t stream) {
+  if (!dy || !x || !mean || !rstd || !gamma || !dx || M < 0 || D < 1 || D > 32 * kMaxPerLane) return TFASR_INVALID_VALUE;
+  if (M == 0) return TFASR_OK;
+  const int rows_per_warp = 4;
+  const unsigned grid = (unsigned)ceil_div(M, kRowsWarps * rows_per_warp);
+  const size_t smem = sizeof(float) * 2 * D;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LN_BWD(T, NPL)                                                                                                                  \
+  layernorm_bwd_kernel<T, NPL><<<grid, kRowsWarps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const T*>(x), mean, rstd, gamma, \
+                                                                     static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, M, D, rows_per_warp)
+  if (x_is_f32) {
+    if (D <= 160) LN_BWD(float, 5); else if (D <= 320) LN_BWD(float, 10); else if (D <= 640) LN_BWD(float, 20); else LN_BWD(float, 32);
+  } else {
+    if (D <= 160) LN_BWD(__nv_bfloat16, 5); else if (D <= 320) LN_BWD(__nv_bfloat16, 10); else if (D <= 640) LN_BWD(__nv_bfloat16, 20); else LN_BWD(__nv_bfloat16, 32);
+  }
+#undef LN_BWD
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_scale_mask_colsum(const void* in, const void* add, void* out, float* colsum, int32_t M, int32_t N, float scale, float dropout_p,
+                                       const unsigned long long* seed_ptr, unsigned long long salt, tfasr_stream_t stream) {
+  if (!in || !out || M < 0 || N < 2 || (N & 1)) return TFASR_INVALID_VALUE;
+  if (M == 0) return TFASR_OK;
+  const int rows_per_block = 32;
+  scale_mask_colsum_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(out), colsum, M, N, scale, dropout_p,
+      seed_ptr, salt, rows_per_block);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_glu_bwd(const void* aux, const void* dg, void* daux, float* colsum, int32_t M, int32_t D, tfasr_stream_t stream) {
+  if (!aux || !dg || !daux || M < 0 || D < 1) return TFASR_INVALID_VALUE;
+  if (M == 0) return TFASR_OK;
+  const int rows_per_block = 32;
+  glu_bwd_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(aux), static_cast<const __nv_bfloat16*>(dg), static_cast<__nv_bfloat16*>(daux), colsum, M, D, rows_per_block);
+  count_launch();
+  return check_launch();
+}

@@ -65,8 +65,10 @@ struct GemmEpi {
   int mul_mode;         // 0 none, 1: * swish'(mul), 2: * (1 - mul^2)  [tanh'], 3: * mul
   float res_scale;      // residual factor (0.5 for the macaron FFN)
   float alpha;          // scales the accumulator before bias (1 by default)
-  float drop_p;         // dropout probability (0 = off); mask = hash(seed, row * N + col)
-  unsigned long long seed;
+  float drop_p;         // dropout probability (0 = off); mask = hash(*seed_ptr + salt, row * N + col)
+  const unsigned long long* seed_ptr;  // device counter, bumped once per step (CUDA-graph replay safe)
+  unsigned long long salt;
+  int atomic_out;       // 1: atomicAdd into f32 C (split-K partial sums / gradient accumulation)
 };
 
 __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
@@ -110,7 +112,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blk = blockIdx.x, n_blk = blockIdx.y;
-  const int num_k = (K + kBK - 1) / kBK;
+  const int total_k = (K + kBK - 1) / kBK;
+  const int per_split = (total_k + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int k_begin = (int)blockIdx.z * per_split;
+  const int num_k = max(0, min(total_k, k_begin + per_split) - k_begin);
 
   if (warp == 0 && lane == 0) {
     sm100::prefetch_tensormap(&tmA);
@@ -140,17 +145,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t* a = sA + s * S::A_BYTES;
         uint8_t* b = sB + s * S::B_BYTES;
         if constexpr (!A_MN) {
-          sm100::tma_load_2d(a, &tmA, &full_bar[s], kb * kBK, m_blk * kBM);  // [128 rows(m) x 64 k]
+          sm100::tma_load_2d(a, &tmA, &full_bar[s], (k_begin + kb) * kBK, m_blk * kBM);  // [128 rows(m) x 64 k]
         } else {
           // source [K, M]: two boxes of [64 k-rows x 64 m-cols]; each box = 64 rows of 128 B
-          sm100::tma_load_2d(a, &tmA, &full_bar[s], m_blk * kBM, kb * kBK);
-          sm100::tma_load_2d(a + kBK * 128, &tmA, &full_bar[s], m_blk * kBM + 64, kb * kBK);
+          sm100::tma_load_2d(a, &tmA, &full_bar[s], m_blk * kBM, (k_begin + kb) * kBK);
+          sm100::tma_load_2d(a + kBK * 128, &tmA, &full_bar[s], m_blk * kBM + 64, (k_begin + kb) * kBK);
         }
         if constexpr (!B_MN) {
-          sm100::tma_load_2d(b, &tmB, &full_bar[s], kb * kBK, n_blk * BN);  // [BN rows(n) x 64 k]
+          sm100::tma_load_2d(b, &tmB, &full_bar[s], (k_begin + kb) * kBK, n_blk * BN);  // [BN rows(n) x 64 k]
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) sm100::tma_load_2d(b + j * kBK * 128, &tmB, &full_bar[s], n_blk * BN + j * 64, kb * kBK);
+          for (int j = 0; j < BN / 64; ++j) sm100::tma_load_2d(b + j * kBK * 128, &tmB, &full_bar[s], n_blk * BN + j * 64, (k_begin + kb) * kBK);
         }
       }
     }
@@ -174,7 +179,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         sm100::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
       }
-      sm100::umma_commit(tmem_full);  // accumulator complete
+      sm100::umma_commit(tmem_full);  // accumulator complete (fires immediately when no MMA was issued)
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
@@ -184,10 +189,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     sm100::tc_fence_after();
     const bool row_ok = row < M;
     const float keep_scale = epi.drop_p > 0.f ? 1.0f / (1.0f - epi.drop_p) : 1.0f;
+    const unsigned long long seed = (epi.drop_p > 0.f && epi.seed_ptr) ? (*epi.seed_ptr + epi.salt) : epi.salt;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       const int n0 = n_blk * BN + c0;
-      if (n0 >= N) break;  // warp-uniform
+      if (n0 >= N || num_k == 0) break;  // warp-uniform (num_k == 0: empty split, nothing to add)
       uint32_t r[16];
       sm100::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       sm100::tmem_ld_wait();
@@ -266,7 +272,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (epi.drop_p > 0.f) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float u = hash_uniform(epi.seed, (unsigned long long)row * (unsigned long long)N + (unsigned long long)(n0 + j));
+          const float u = hash_uniform(seed, (unsigned long long)row * (unsigned long long)N + (unsigned long long)(n0 + j));
           v[j] = (u >= epi.drop_p) ? v[j] * keep_scale : 0.f;
         }
       }
@@ -288,7 +294,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (row_ok) {
         if (epi.c_f32) {
           float* cp = reinterpret_cast<float*>(epi.c) + (size_t)row * epi.ldc + n0;
-          if (n0 + 16 <= N && ((epi.ldc & 3) == 0)) {
+          if (epi.atomic_out) {
+            for (int j = 0; j < 16 && n0 + j < N; ++j) atomicAdd(cp + j, v[j]);
+          } else if (n0 + 16 <= N && ((epi.ldc & 3) == 0)) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(cp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
@@ -321,7 +329,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, int N, int K, int lda, int ldb, cudaStream_t stream) {
+static int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, int N, int K, int lda, int ldb, int splits, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   CUtensorMap tmA, tmB;
   bool ok;
@@ -336,7 +344,7 @@ static int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, 
       return TFASR_EXECUTION_FAILED;
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div(M, kBM), (unsigned)ceil_div(N, BN));
+  dim3 grid((unsigned)ceil_div(M, kBM), (unsigned)ceil_div(N, BN), (unsigned)splits);
   gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, S::TOTAL, stream>>>(tmA, tmB, epi, M, N, K);
   count_launch();
   return check_launch();
@@ -356,12 +364,12 @@ static int choose_bn(int N) {
 }
 
 template <bool A_MN, bool B_MN>
-static int dispatch_bn(const void* A, const void* B, const GemmEpi& epi, int M, int N, int K, int lda, int ldb, cudaStream_t stream) {
+static int dispatch_bn(const void* A, const void* B, const GemmEpi& epi, int M, int N, int K, int lda, int ldb, int splits, cudaStream_t stream) {
   switch (choose_bn(N)) {
-    case 64: return launch_gemm<64, A_MN, B_MN>(A, B, epi, M, N, K, lda, ldb, stream);
-    case 128: return launch_gemm<128, A_MN, B_MN>(A, B, epi, M, N, K, lda, ldb, stream);
-    case 192: return launch_gemm<192, A_MN, B_MN>(A, B, epi, M, N, K, lda, ldb, stream);
-    default: return launch_gemm<256, A_MN, B_MN>(A, B, epi, M, N, K, lda, ldb, stream);
+    case 64: return launch_gemm<64, A_MN, B_MN>(A, B, epi, M, N, K, lda, ldb, splits, stream);
+    case 128: return launch_gemm<128, A_MN, B_MN>(A, B, epi, M, N, K, lda, ldb, splits, stream);
+    case 192: return launch_gemm<192, A_MN, B_MN>(A, B, epi, M, N, K, lda, ldb, splits, stream);
+    default: return launch_gemm<256, A_MN, B_MN>(A, B, epi, M, N, K, lda, ldb, splits, stream);
   }
 }
 
@@ -394,11 +402,17 @@ extern "C" int tfasr_gemm_bf16(const void* A, const void* B, void* C, int32_t M,
     epi.res_scale = e->residual_scale;
     epi.alpha = e->alpha;
     epi.drop_p = e->dropout_p;
-    epi.seed = e->dropout_seed;
+    epi.seed_ptr = e->dropout_seed_ptr;
+    epi.salt = e->dropout_salt;
+    epi.atomic_out = e->atomic_out;
   }
   if (epi.glu && ((N & 1) || epi.c_f32)) return TFASR_INVALID_VALUE;
+  if (epi.atomic_out && !epi.c_f32) return TFASR_INVALID_VALUE;
+  int splits = (e && e->k_splits > 1) ? e->k_splits : 1;
+  if (splits > 1 && !epi.atomic_out) return TFASR_INVALID_VALUE;
+  if (splits > (K + kBK - 1) / kBK) splits = (K + kBK - 1) / kBK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!a_mn_major && !b_mn_major) return dispatch_bn<false, false>(A, B, epi, M, N, K, lda, ldb, stream);
-  if (a_mn_major && b_mn_major) return dispatch_bn<true, true>(A, B, epi, M, N, K, lda, ldb, stream);
+  if (!a_mn_major && !b_mn_major) return dispatch_bn<false, false>(A, B, epi, M, N, K, lda, ldb, splits, stream);
+  if (a_mn_major && b_mn_major) return dispatch_bn<true, true>(A, B, epi, M, N, K, lda, ldb, splits, stream);
   return TFASR_INVALID_VALUE;
 }

@@ -12,7 +12,8 @@ _MUL = {None: 0, "swish_grad": 1, "tanh_grad": 2, "mul": 3}
 
 
 def gemm(a, b, *, out=None, out_dtype=torch.bfloat16, bias=None, activation=None, aux=None, residual=None, residual_scale=1.0,
-         mul=None, mul_mode=None, colsum=None, glu=False, alpha=1.0, dropout_p=0.0, dropout_seed=0, mn_major=False):
+         mul=None, mul_mode=None, colsum=None, glu=False, alpha=1.0, dropout_p=0.0, dropout_seed=None, dropout_salt=0, mn_major=False,
+         accumulate=False, k_splits=1):
     """C = epilogue(alpha * A . B^T) on the tcgen05 GEMM.
 
     default: a [M,K], b [N,K] (bf16, row-major).  mn_major=True: a [K,M], b [K,N] -> C [M,N] = a^T . b.
@@ -47,7 +48,10 @@ def gemm(a, b, *, out=None, out_dtype=torch.bfloat16, bias=None, activation=None
     e.residual_scale = float(residual_scale)
     e.alpha = float(alpha)
     e.dropout_p = float(dropout_p)
-    e.dropout_seed = int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
+    e.dropout_seed_ptr = dropout_seed.data_ptr() if dropout_seed is not None else None  # int64 device scalar
+    e.dropout_salt = int(dropout_salt) & 0xFFFFFFFFFFFFFFFF
+    e.atomic_out = int(bool(accumulate))
+    e.k_splits = int(k_splits)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
     _lib.check(
@@ -56,3 +60,46 @@ def gemm(a, b, *, out=None, out_dtype=torch.bfloat16, bias=None, activation=None
         "tfasr_gemm_bf16",
     )
     return out
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-3):
+    """x [M, D] bf16|f32 -> (y bf16 [M, D], mean f32 [M], rstd f32 [M])."""
+    lib = _lib.load()
+    M, D = x.shape
+    y = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    _lib.check(lib.tfasr_layernorm_fwd(_lib.ptr(x), int(x.dtype == torch.float32), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(y), _lib.ptr(mean),
+                                       _lib.ptr(rstd), M, D, float(eps), _lib.stream_ptr(x.device)), "tfasr_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
+    """-> dx bf16 [M, D] (= LN backward of dy, + dres); dgamma / dbeta (f32 [D]) are accumulated in place."""
+    lib = _lib.load()
+    M, D = x.shape
+    dx = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.tfasr_layernorm_bwd(_lib.ptr(dy), _lib.ptr(x), int(x.dtype == torch.float32), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
+                                       _lib.ptr(dres), _lib.ptr(dx), _lib.ptr(dgamma), _lib.ptr(dbeta), M, D, _lib.stream_ptr(x.device)),
+               "tfasr_layernorm_bwd")
+    return dx
+
+
+def scale_mask_colsum(x, scale=1.0, dropout_p=0.0, seed=None, salt=0, colsum=None, add=None):
+    """out = scale * dropout_mask * x (+ add), bf16 [M, N]; colsum (f32 [N]) += column sums of out."""
+    lib = _lib.load()
+    M, N = x.shape
+    out = torch.empty_like(x)
+    _lib.check(lib.tfasr_scale_mask_colsum(_lib.ptr(x), _lib.ptr(add), _lib.ptr(out), _lib.ptr(colsum), M, N, float(scale), float(dropout_p),
+                                           seed.data_ptr() if seed is not None else None, int(salt) & 0xFFFFFFFFFFFFFFFF,
+                                           _lib.stream_ptr(x.device)), "tfasr_scale_mask_colsum")
+    return out
+
+
+def glu_bwd(aux, dg, colsum=None):
+    """aux [M, 2D] interleaved pre-GLU (a, b) pairs, dg [M, D] -> daux [M, 2D]; colsum (f32 [2D]) += column sums."""
+    lib = _lib.load()
+    M, D = dg.shape
+    daux = torch.empty_like(aux)
+    _lib.check(lib.tfasr_glu_bwd(_lib.ptr(aux), _lib.ptr(dg), _lib.ptr(daux), _lib.ptr(colsum), M, D, _lib.stream_ptr(dg.device)), "tfasr_glu_bwd")
+    return daux

@@ -65,9 +65,11 @@ def test_epilogues():
     out = kernels.gemm(a, b, mul=th, mul_mode="tanh_grad", out_dtype=torch.float32)
     _close(out, _ref(a, b) * (1 - th.float() ** 2), 2e-3)
     # dropout: deterministic in (seed, index), right keep rate, kept values scaled
-    o1 = kernels.gemm(a, b, dropout_p=0.25, dropout_seed=123, out_dtype=torch.float32)
-    o2 = kernels.gemm(a, b, dropout_p=0.25, dropout_seed=123, out_dtype=torch.float32)
-    o3 = kernels.gemm(a, b, dropout_p=0.25, dropout_seed=124, out_dtype=torch.float32)
+    seed = torch.tensor([123], dtype=torch.int64, device="cuda")
+    o1 = kernels.gemm(a, b, dropout_p=0.25, dropout_seed=seed, dropout_salt=7, out_dtype=torch.float32)
+    o2 = kernels.gemm(a, b, dropout_p=0.25, dropout_seed=seed, dropout_salt=7, out_dtype=torch.float32)
+    seed += 1
+    o3 = kernels.gemm(a, b, dropout_p=0.25, dropout_seed=seed, dropout_salt=7, out_dtype=torch.float32)
     assert torch.equal(o1, o2) and not torch.equal(o1, o3)
     kept = o1 != 0
     assert abs(kept.float().mean().item() - 0.75) < 0.01
@@ -85,3 +87,7 @@ def test_mn_major_gemm_for_weight_gradients(shape):
     dy = (torch.randn(K, N, device="cuda") / K ** 0.5).to(torch.bfloat16)
     out = kernels.gemm(x, dy, mn_major=True, out_dtype=torch.float32)
     _close(out, _ref(x, dy, mn=True), 2e-3)
+    # split-K with atomic accumulation into an existing f32 buffer (how weight gradients land in .grad)
+    acc = torch.ones(M, N, device="cuda")
+    kernels.gemm(x, dy, mn_major=True, out=acc, accumulate=True, k_splits=8)
+    _close(acc - 1.0, _ref(x, dy, mn=True), 2e-3)
