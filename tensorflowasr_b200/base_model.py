@@ -42,7 +42,11 @@ def make_optimizer(model: nn.Module, learning_rate=None, beta_1=0.9, beta_2=0.98
     """Keras Adam as configured in small.yml.j2:73-87 (decoupled weight decay), on torch's fused multi-tensor Adam."""
     lr0 = learning_rate(1) if callable(learning_rate) else (learning_rate or 1e-3)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=lr0, betas=(beta_1, beta_2), eps=epsilon, weight_decay=weight_decay or 0.0, fused=params[0].is_cuda)
+    on_gpu = params[0].is_cuda
+    # lr lives in a device tensor so that a captured CUDA graph picks up the schedule's new value at every replay
+    lr = torch.tensor(float(lr0), device=params[0].device) if on_gpu else lr0
+    opt = torch.optim.AdamW(params, lr=lr, betas=(beta_1, beta_2), eps=epsilon, weight_decay=weight_decay or 0.0, fused=on_gpu,
+                            capturable=on_gpu)
     opt._tfasr_schedule = learning_rate if callable(learning_rate) else None
     return opt
 
@@ -110,7 +114,11 @@ class BaseModel(nn.Module):
         self.gwn_config = gwn_config
         self.gradn_config = gradn_config
         self.tfasr_loss = loss
-        self._reducer = tdist.GradientReducer(self.trainable_weights) if tdist.world_size() > 1 else None
+        # every parameter's .grad becomes a view into ONE flat fp32 buffer: the fused kernels accumulate weight gradients straight
+        # into it, zeroing is one memset, and the data-parallel all-reduce needs no packing
+        self._reducer = tdist.GradientReducer(self.trainable_weights)
+        self._graph = None
+        self._use_graph = False
         return self
 
     def call(self, inputs: schemas.TrainInput, training=False):
@@ -135,35 +143,91 @@ class BaseModel(nn.Module):
         """base_model.py:137-147 + Keras `sum_over_batch_size` reduction, scaled by 1/num_replicas for the gradient SUM."""
         return losses.mean() / tdist.world_size()
 
+    def enable_cuda_graph(self, flag: bool = True):
+        """Capture the whole training step (forward, backward, all-reduce, optimizer) in ONE CUDA graph and replay it per step:
+        the B200 replacement for `tf.function(one_step_on_data)` (base_model.py:252-269).  Shapes must stay fixed."""
+        self._use_graph = bool(flag)
+        self._graph = None
+        return self
+
     def _train_step(self, data: schemas.TrainData):
+        from . import fused
+
+        fused.STATE.bump()  # new dropout streams for this step
         losses = self.compute_losses(data, training=True)
         loss = self.tfasr_compute_loss(losses)
         loss.backward()
         self._last_losses = losses.detach()
         return [p.grad for p in self.trainable_weights]
 
-    def _apply_gradients(self, gradients=None):
+    def _apply_gradients(self, gradients=None, lr_from_host=True):
         params = self.trainable_weights
         if self._reducer is not None:
-            self._reducer.all_reduce()  # C1: one bucketed NCCL all-reduce (SUM) over NVLink
+            self._reducer.all_reduce()  # C1: one bucketed NCCL all-reduce (SUM) over NVLink (no-op on one GPU)
         if self.l2:
             reg = [p for n, p in self.named_parameters() if p.requires_grad and p.grad is not None and _is_regularized(n)]
             if reg:
                 torch._foreach_add_([p.grad for p in reg], [p.detach() for p in reg], alpha=2.0 * self.l2)
+        if lr_from_host:
+            self._advance_schedule()
+        self.optimizer.step()
+        if self._reducer is not None:
+            self._reducer.zero()
+        else:
+            self.optimizer.zero_grad(set_to_none=False)
+        del params
+
+    def _advance_schedule(self):
         self._iterations += 1
         sched = getattr(self.optimizer, "_tfasr_schedule", None)
         if sched is not None:
             lr = sched(self._iterations)
             for g in self.optimizer.param_groups:
-                g["lr"] = lr
-        self.optimizer.step()
-        self.optimizer.zero_grad(set_to_none=False)
-        del params
+                if torch.is_tensor(g["lr"]):
+                    g["lr"].fill_(lr)
+                else:
+                    g["lr"] = lr
 
     def train_step(self, data: schemas.TrainData):
+        if self._use_graph and data.inputs.inputs.is_cuda:
+            return self._graph_train_step(data)
         self._train_step(data)
         self._apply_gradients()
         return {"loss": self._last_losses}
+
+    # ------------------------------------------------------------------ CUDA-graph step
+    def _graph_train_step(self, data: schemas.TrainData):
+        flat = [data.inputs.inputs, data.inputs.inputs_length, data.inputs.predictions, data.inputs.predictions_length,
+                data.labels.labels, data.labels.labels_length]
+        key = tuple((tuple(t.shape), t.dtype) for t in flat)
+        if self._graph is None or self._graph["key"] != key:
+            static = [torch.empty_like(t) for t in flat]
+            for s, t in zip(static, flat):
+                s.copy_(t)
+            sdata = schemas.TrainData(schemas.TrainInput(*static[:4]), schemas.TrainLabel(*static[4:]))
+            # warm-up on a side stream (allocator, cuDNN / cuBLAS handles, lazily built tables), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._advance_schedule()
+                    self._train_step(sdata)
+                    self._apply_gradients(lr_from_host=False)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._train_step(sdata)
+                self._apply_gradients(lr_from_host=False)
+                out = self._last_losses.clone()
+            self._graph = {"key": key, "graph": graph, "static": static, "out": out}
+        g = self._graph
+        for s, t in zip(g["static"], flat):
+            if s.data_ptr() != t.data_ptr():
+                s.copy_(t, non_blocking=True)
+        self._advance_schedule()
+        g["graph"].replay()
+        return {"loss": g["out"]}
 
     def train_step_ga(self, data: schemas.TrainData, do_apply=None):
         """Gradient accumulation (base_model.py:200-209): gradients accumulate in .grad across calls; apply on the last one."""

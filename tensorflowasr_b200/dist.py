@@ -99,6 +99,9 @@ class GradientReducer:
         self._works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, async_op=True))
         self._launched[b] = True
 
+    def zero(self):
+        self.flat.zero_()
+
     def all_reduce(self):
         """Finish the step's gradient SUM: launch whatever has not been launched by the hooks, then wait."""
         if world_size() > 1:

@@ -9,11 +9,12 @@ kernels behind the C ABI.
 from __future__ import annotations
 
 import math
+import zlib
 
 import torch
 from torch import nn
 
-from . import ops
+from . import fused, ops
 
 
 def conv_output_length(input_length, filter_size, padding, stride, dilation=1):
@@ -252,8 +253,30 @@ class ConformerEncoder(_Params):
                     self[f"{pre}.conv_module.dw_bn.moving_mean"], self[f"{pre}.conv_module.dw_bn.moving_variance"])
         return ("layer", self[f"{pre}.conv_module.dw_ln.gamma"], self[f"{pre}.conv_module.dw_ln.beta"])
 
+    # ------------------------------------------------------------------------------------------ fused (sm_100a kernel) path
+    def _prepare_packs(self):
+        """bf16 operand copies of the GEMM weights for this forward/backward (weights change every optimizer step)."""
+        packs = {}
+        for b in range(self.num_blocks):
+            for ff in ("ff_module_1", "ff_module_2"):
+                for d in ("dense_1", "dense_2"):
+                    n = f"block_{b}.{ff}.{d}"
+                    packs[n] = fused.WeightPack(self[n + ".kernel"], self[n + ".bias"])
+        self._packs = packs
+
+    def _salt(self, pre, k):
+        return (zlib.crc32(pre.encode()) % 1000003) * 64 + k * 2 + 1
+
     def _ff(self, x, pre, training):
         # FFModule.call, conformer.py:101-109
+        if ops.fused_active(x):
+            B, T, D = x.shape
+            p = self.dropout if training else 0.0
+            blk = pre[len(self.name) + 1:] if pre.startswith(self.name + ".") else pre
+            y = fused.ff_module(x.reshape(B * T, D).to(torch.bfloat16), self[pre + ".ln.gamma"], self[pre + ".ln.beta"],
+                                self._packs[blk + ".dense_1"], self._packs[blk + ".dense_2"], self.ffm_residual_factor, p,
+                                self._salt(pre, 0), fused.STATE.seed_tensor(x.device))
+            return y.view(B, T, D)
         y = ops.layer_norm(x, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
         y = ops.linear(y, self[pre + ".dense_1.kernel"], self[pre + ".dense_1.bias"], activation="swish")
         y = ops.dropout(y, self.dropout, training)
@@ -291,6 +314,8 @@ class ConformerEncoder(_Params):
 
     def call(self, inputs, initial_state=None, training=False, return_states=False):
         x, length = inputs  # features [B, T, F, 1]
+        if ops.fused_active(x):
+            self._prepare_packs()
         x, length = self.conv_subsampling((x, length), training=training)
         x = ops.linear(x, self["linear.kernel"], self["linear.bias"])
         x = ops.dropout(x, self.dropout, training)
@@ -302,7 +327,10 @@ class ConformerEncoder(_Params):
             x = self._mhsa(x, relpe, length, pre + ".mhsa_module", training)
             x = self._conv(x, pre + ".conv_module", training)
             x = self._ff(x, pre + ".ff_module_2", training)
-            x = ops.layer_norm(x, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
+            if ops.fused_active(x):
+                x = fused.layer_norm(x.contiguous(), self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
+            else:
+                x = ops.layer_norm(x, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
         if return_states:
             return x, length, None
         return x, length

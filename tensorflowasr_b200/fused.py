@@ -1,0 +1,169 @@
+"""Module-level fused forward/backward for the Conformer block on the hand-written sm_100a kernels.
+
+Each autograd.Function below is one reference module (FFModule / MHSAModule / ConvModule, models/encoders/conformer.py)
+executed as a short chain of tcgen05 GEMMs with fused epilogues and row-wise fused kernels, bf16 activations, fp32
+accumulation and statistics.  Parameter gradients are accumulated by the kernels straight into the parameters' fp32 `.grad`
+buffers (split-K atomics), so the Functions only propagate the activation gradient.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels
+
+LN_EPS = 1e-3
+
+
+class StepState:
+    """Per-step device state shared by all fused modules: the dropout counter (bumped once per step, inside the CUDA graph)."""
+
+    def __init__(self):
+        self.seed = None
+
+    def seed_tensor(self, device):
+        if self.seed is None or self.seed.device != device:
+            self.seed = torch.zeros(1, dtype=torch.int64, device=device)
+        return self.seed
+
+    def bump(self):
+        if self.seed is not None:
+            self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+
+
+STATE = StepState()
+
+
+def _grad(p: torch.Tensor) -> torch.Tensor:
+    """fp32 gradient buffer of a parameter (allocated zeroed on first use; kernels accumulate into it)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, dtype=torch.float32)
+    return p.grad
+
+
+class WeightPack:
+    """bf16 operand copies of one Dense kernel W [K, N] (Keras layout): `wt` = W^T [N, K] for the forward GEMM (B operand,
+    K-major), `w` = W [K, N] for the data-gradient GEMM (dX = dY . W^T: B operand [K, N] with contraction N)."""
+
+    __slots__ = ("w", "wt", "param", "bias")
+
+    def __init__(self, param, bias=None, interleave_glu=False):
+        w = param.detach()
+        if w.dim() > 2:
+            raise ValueError("reshape EinsumDense kernels to 2-D before packing")
+        if interleave_glu:
+            # GLU halves (a = cols [0, D), b = cols [D, 2D)) interleaved as (a_0, b_0, a_1, b_1, ...) so that the GEMM epilogue
+            # sees each pair in adjacent columns (activations/glu.py:25-28)
+            D = w.shape[1] // 2
+            w = torch.stack([w[:, :D], w[:, D:]], dim=2).reshape(w.shape[0], 2 * D)
+        self.w = w.to(torch.bfloat16).contiguous()
+        self.wt = w.t().to(torch.bfloat16).contiguous()
+        self.param = param
+        self.bias = bias
+
+
+def _splits(rows: int) -> int:
+    """split-K factor for weight-gradient GEMMs (contraction over `rows`): enough CTAs to fill the machine."""
+    return max(1, min(32, rows // 512))
+
+
+# ------------------------------------------------------------------------------------------------ FFModule
+class _FFModuleFn(torch.autograd.Function):
+    """x + factor * Drop(W2 . Drop(swish(W1 . LN(x) + b1)) + b2)      (conformer.py:101-109)"""
+
+    @staticmethod
+    def forward(ctx, x, ln_g, ln_b, p1: WeightPack, p2: WeightPack, factor, drop_p, salt, seed):
+        M, D = x.shape
+        a, mean, rstd = kernels.layernorm_fwd(x, ln_g, ln_b, LN_EPS)
+        H = p1.wt.shape[0]
+        z = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
+        h = kernels.gemm(a, p1.wt, bias=p1.bias, activation="swish", aux=z, dropout_p=drop_p, dropout_seed=seed, dropout_salt=salt)
+        out = kernels.gemm(h, p2.wt, bias=p2.bias, residual=x, residual_scale=factor, dropout_p=drop_p, dropout_seed=seed,
+                           dropout_salt=salt + 1)
+        ctx.save_for_backward(x, mean, rstd, a, z, h)
+        ctx.misc = (ln_g, ln_b, p1, p2, factor, drop_p, salt, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mean, rstd, a, z, h = ctx.saved_tensors
+        ln_g, ln_b, p1, p2, factor, drop_p, salt, seed = ctx.misc
+        dout = dout.contiguous()
+        M = x.shape[0]
+        ks = _splits(M)
+        # d(out)/d(y): residual factor and the second dropout; bias-2 gradient = column sums
+        dy = kernels.scale_mask_colsum(dout, scale=factor, dropout_p=drop_p, seed=seed, salt=salt + 1, colsum=_grad(p2.bias))
+        kernels.gemm(h, dy, mn_major=True, out=_grad(p2.param), accumulate=True, k_splits=ks)  # dW2 += h^T dy
+        # dz = (dy W2^T) * dropout1 * swish'(z); bias-1 gradient = column sums (fused in the epilogue)
+        dz = kernels.gemm(dy, p2.w, mul=z, mul_mode="swish_grad", dropout_p=drop_p, dropout_seed=seed, dropout_salt=salt,
+                          colsum=_grad(p1.bias))
+        kernels.gemm(a, dz, mn_major=True, out=_grad(p1.param), accumulate=True, k_splits=ks)  # dW1 += a^T dz
+        da = kernels.gemm(dz, p1.w)
+        dx = kernels.layernorm_bwd(da, x, mean, rstd, ln_g, _grad(ln_g), _grad(ln_b), dres=dout)
+        return dx, None, None, None, None, None, None, None, None
+
+
+def ff_module(x, ln_g, ln_b, p1, p2, factor, drop_p, salt, seed):
+    """x [M, D] bf16 -> [M, D] bf16."""
+    return _FFModuleFn.apply(x, ln_g, ln_b, p1, p2, float(factor), float(drop_p), int(salt), seed)
+
+
+# ------------------------------------------------------------------------------------------------ plain LayerNorm
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g, b):
+        y, mean, rstd = kernels.layernorm_fwd(x, g, b, LN_EPS)
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.misc = (g, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd = ctx.saved_tensors
+        g, b = ctx.misc
+        return kernels.layernorm_bwd(dy.contiguous(), x, mean, rstd, g, _grad(g), _grad(b)), None, None
+
+
+def layer_norm(x, g, b):
+    """x [..., D] -> bf16, keras LayerNormalization(eps=1e-3)."""
+    shp = x.shape
+    return _LayerNormFn.apply(x.reshape(-1, shp[-1]), g, b).reshape(shp)
+
+
+# ------------------------------------------------------------------------------------------------ Dense (+ optional residual)
+class _LinearFn(torch.autograd.Function):
+    """y = [residual + factor *] Drop(act(x W + b))"""
+
+    @staticmethod
+    def forward(ctx, x, pack: WeightPack, activation, residual, factor, drop_p, salt, seed):
+        M = x.shape[0]
+        N = pack.wt.shape[0]
+        z = torch.empty((M, N), dtype=torch.bfloat16, device=x.device) if activation == "swish" else None
+        y = kernels.gemm(x, pack.wt, bias=pack.bias, activation=activation, aux=z, residual=residual, residual_scale=factor,
+                         dropout_p=drop_p, dropout_seed=seed, dropout_salt=salt)
+        ctx.save_for_backward(x, z)
+        ctx.misc = (pack, activation, residual is not None, factor, drop_p, salt, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, z = ctx.saved_tensors
+        pack, activation, has_res, factor, drop_p, salt, seed = ctx.misc
+        dy = dy.contiguous()
+        scale = factor if has_res else 1.0
+        if activation == "swish":
+            # dz = scale * mask * dy * swish'(z)
+            d0 = kernels.scale_mask_colsum(dy, scale=scale, dropout_p=drop_p, seed=seed, salt=salt)
+            sg = torch.sigmoid(z.float())
+            dz = (d0.float() * (sg * (1 + z.float() * (1 - sg)))).to(torch.bfloat16)
+            _grad(pack.bias).add_(dz.float().sum(0))
+        else:
+            dz = kernels.scale_mask_colsum(dy, scale=scale, dropout_p=drop_p, seed=seed, salt=salt,
+                                           colsum=_grad(pack.bias) if pack.bias is not None else None)
+        kernels.gemm(x, dz, mn_major=True, out=_grad(pack.param).view(pack.w.shape), accumulate=True, k_splits=_splits(x.shape[0]))
+        dx = kernels.gemm(dz, pack.w)
+        return dx, None, None, (dy if has_res else None), None, None, None, None
+
+
+def linear(x, pack, activation=None, residual=None, factor=1.0, drop_p=0.0, salt=0, seed=None):
+    """x [M, K] bf16 -> [M, N] bf16 through the tcgen05 GEMM (bias / activation / dropout / residual fused in the epilogue)."""
+    return _LinearFn.apply(x, pack, activation, residual, float(factor), float(drop_p), int(salt), seed)

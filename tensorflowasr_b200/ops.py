@@ -37,6 +37,19 @@ def precision() -> str:
     return _PRECISION
 
 
+_FUSED = True
+
+
+def set_fused(flag: bool):
+    """Route the Conformer modules through the hand-written fused kernels (bf16 mode on CUDA only)."""
+    global _FUSED
+    _FUSED = bool(flag)
+
+
+def fused_active(x) -> bool:
+    return _FUSED and _PRECISION == "bf16" and x.is_cuda
+
+
 def compute_dtype():
     return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
 
@@ -146,7 +159,7 @@ class _SyncBatchNormFn(torch.autograd.Function):
         C = x.shape[-1]
         xf = x.reshape(-1, C).float()
         stats = torch.stack([xf.sum(0), (xf * xf).sum(0)])
-        count = torch.tensor([float(xf.shape[0])], device=x.device)
+        count = torch.full((1,), float(xf.shape[0]), device=x.device)  # fill kernel (graph-capturable), not an H2D copy
         world = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
         if world:
             packed = torch.cat([stats.reshape(-1), count])
