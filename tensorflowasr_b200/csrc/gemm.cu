@@ -50,6 +50,21 @@ bool make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return r == CUDA_SUCCESS;
 }
 
+bool make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                  uint32_t box_cols) {
+  PFN_tmapEncodeTiled enc = get_tmap_encode();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * elem_bytes) & 15)) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // ------------------------------------------------------------------------------------------------ epilogue description
 struct GemmEpi {
   void* c;              // output [M, ldc]  (bf16 or f32); GLU: [M, N/2]
@@ -69,6 +84,7 @@ struct GemmEpi {
   const unsigned long long* seed_ptr;  // device counter, bumped once per step (CUDA-graph replay safe)
   unsigned long long salt;
   int atomic_out;       // 1: atomicAdd into f32 C (split-K partial sums / gradient accumulation)
+  int tma_store;        // 1: C leaves through SMEM staging + cp.async.bulk.tensor stores (coalesced, clipped by hardware)
 };
 
 __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
@@ -79,83 +95,107 @@ __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned 
   return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 constexpr int kGemmThreads = 192;
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 
+// Persistent, warp-specialised kernel: one CTA per SM walks output tiles (n fastest, so the N-tiles of one M-tile run
+// back to back and A is read from HBM once); the smem ring and the two TMEM accumulator buffers run continuously across
+// tiles, so the epilogue of tile i overlaps the TMA + MMA of tile i+1.
 template <int BN>
 struct GemmSmem {
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
-  static_assert(STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1280 <= 227 * 1024, "smem budget");
+  static constexpr int STAGES = (BN >= 192) ? 4 : 6;
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
-  static constexpr int TOTAL = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGE_OUT_BYTES = 4 /*epilogue warps*/ * 2 /*double buffer*/ * 32 /*rows*/ * 128 /*bytes*/;
+  static constexpr int TOTAL = STAGES * (A_BYTES + B_BYTES) + STAGE_OUT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);  // two accumulators
+  static_assert(TOTAL <= 227 * 1024, "smem budget");
 };
 
-// A_MN / B_MN: operand is MN-major in global memory (the contraction index is the ROW index of the source matrix):
-//   A_MN: A source is [K, M] row-major (e.g. X^T . dY with X stored [rows=K_contraction.., ...]) — box [kBK rows x 64 cols] x (128/64)
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpi epi, int M, int N, int K) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                 const GemmEpi epi, int M, int N, int K, int splits) {
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = sm100::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + S::STAGES * S::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * (S::A_BYTES + S::B_BYTES));
+  uint8_t* sOut = smem + S::STAGES * (S::A_BYTES + S::B_BYTES);  // [4 warps][2][32 rows x 128 B], 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + S::STAGE_OUT_BYTES);
   uint64_t* empty_bar = full_bar + S::STAGES;
-  uint64_t* tmem_full = empty_bar + S::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + S::STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blk = blockIdx.x, n_blk = blockIdx.y;
+  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
   const int total_k = (K + kBK - 1) / kBK;
-  const int per_split = (total_k + (int)gridDim.z - 1) / (int)gridDim.z;
-  const int k_begin = (int)blockIdx.z * per_split;
-  const int num_k = max(0, min(total_k, k_begin + per_split) - k_begin);
+  const int per_split = (total_k + splits - 1) / splits;
+  const int num_tiles = m_tiles * n_tiles * splits;
 
   if (warp == 0 && lane == 0) {
     sm100::prefetch_tensormap(&tmA);
     sm100::prefetch_tensormap(&tmB);
+    if (epi.tma_store) sm100::prefetch_tensormap(&tmC);
     for (int s = 0; s < S::STAGES; ++s) {
       sm100::mbar_init(&full_bar[s], 1);
       sm100::mbar_init(&empty_bar[s], 1);
     }
-    sm100::mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      sm100::mbar_init(&tmem_full[i], 1);
+      sm100::mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+    }
     sm100::fence_barrier_init();
   }
-  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  if (warp == 1) sm100::tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) sm100::tmem_alloc(tmem_slot, S::TMEM_COLS);
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile -> (split, m_blk, n_blk), n fastest
+  auto decode = [&](int tile, int& m_blk, int& n_blk, int& k_begin, int& num_k) {
+    n_blk = tile % n_tiles;
+    const int t2 = tile / n_tiles;
+    m_blk = t2 % m_tiles;
+    const int sp = t2 / m_tiles;
+    k_begin = sp * per_split;
+    num_k = max(0, min(total_k, k_begin + per_split) - k_begin);
+  };
+
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < num_k; ++kb) {
-        const int s = kb % S::STAGES;
-        const uint32_t ph = (kb / S::STAGES) & 1;
-        sm100::mbar_wait(&empty_bar[s], ph ^ 1);
-        sm100::mbar_arrive_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
-        uint8_t* a = sA + s * S::A_BYTES;
-        uint8_t* b = sB + s * S::B_BYTES;
-        if constexpr (!A_MN) {
-          sm100::tma_load_2d(a, &tmA, &full_bar[s], (k_begin + kb) * kBK, m_blk * kBM);  // [128 rows(m) x 64 k]
-        } else {
-          // source [K, M]: two boxes of [64 k-rows x 64 m-cols]; each box = 64 rows of 128 B
-          sm100::tma_load_2d(a, &tmA, &full_bar[s], m_blk * kBM, (k_begin + kb) * kBK);
-          sm100::tma_load_2d(a + kBK * 128, &tmA, &full_bar[s], m_blk * kBM + 64, (k_begin + kb) * kBK);
-        }
-        if constexpr (!B_MN) {
-          sm100::tma_load_2d(b, &tmB, &full_bar[s], (k_begin + kb) * kBK, n_blk * BN);  // [BN rows(n) x 64 k]
-        } else {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk, k_begin, num_k;
+        decode(tile, m_blk, n_blk, k_begin, num_k);
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (it / S::STAGES) & 1;
+          sm100::mbar_wait(&empty_bar[s], ph ^ 1);
+          sm100::mbar_arrive_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
+          uint8_t* a = sA + s * S::A_BYTES;
+          uint8_t* b = sB + s * S::B_BYTES;
+          const int kc = (k_begin + kb) * kBK;
+          if constexpr (!A_MN) {
+            sm100::tma_load_2d(a, &tmA, &full_bar[s], kc, m_blk * kBM);  // [128 rows(m) x 64 k]
+          } else {
+            // source [K, M]: two boxes of [64 k-rows x 64 m-cols]; each box = 64 rows of 128 B
+            sm100::tma_load_2d(a, &tmA, &full_bar[s], m_blk * kBM, kc);
+            sm100::tma_load_2d(a + kBK * 128, &tmA, &full_bar[s], m_blk * kBM + 64, kc);
+          }
+          if constexpr (!B_MN) {
+            sm100::tma_load_2d(b, &tmB, &full_bar[s], kc, n_blk * BN);  // [BN rows(n) x 64 k]
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) sm100::tma_load_2d(b + j * kBK * 128, &tmB, &full_bar[s], n_blk * BN + j * 64, (k_begin + kb) * kBK);
+            for (int j = 0; j < BN / 64; ++j) sm100::tma_load_2d(b + j * kBK * 128, &tmB, &full_bar[s], n_blk * BN + j * 64, kc);
+          }
         }
       }
     }
@@ -163,72 +203,135 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = sm100::make_idesc_bf16_f32(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int kb = 0; kb < num_k; ++kb) {
-        const int s = kb % S::STAGES;
-        const uint32_t ph = (kb / S::STAGES) & 1;
-        sm100::mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
+        int m_blk, n_blk, k_begin, num_k;
+        decode(tile, m_blk, n_blk, k_begin, num_k);
+        const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+        sm100::mbar_wait(&tmem_empty[buf], aph ^ 1);  // the epilogue has drained this accumulator
         sm100::tc_fence_after();
-        const uint32_t a0 = sm100::smem_u32(sA + s * S::A_BYTES);
-        const uint32_t b0 = sm100::smem_u32(sB + s * S::B_BYTES);
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (it / S::STAGES) & 1;
+          sm100::mbar_wait(&full_bar[s], ph);
+          sm100::tc_fence_after();
+          const uint32_t a0 = sm100::smem_u32(sA + s * S::A_BYTES);
+          const uint32_t b0 = sm100::smem_u32(sB + s * S::B_BYTES);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // K-major: 16 k = 32 B inside the 128 B swizzle row.  MN-major: 16 k-rows of 128 B = 2048 B.
-          const uint64_t ad = A_MN ? sm100::make_smem_desc(a0 + k * 2048, kBK * 128, 1024) : sm100::make_smem_desc(a0 + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? sm100::make_smem_desc(b0 + k * 2048, kBK * 128, 1024) : sm100::make_smem_desc(b0 + k * 32, 16, 1024);
-          sm100::umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // K-major: 16 k = 32 B inside the 128 B swizzle row.  MN-major: 16 k-rows of 128 B = 2048 B.
+            const uint64_t ad = A_MN ? sm100::make_smem_desc(a0 + k * 2048, kBK * 128, 1024) : sm100::make_smem_desc(a0 + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? sm100::make_smem_desc(b0 + k * 2048, kBK * 128, 1024) : sm100::make_smem_desc(b0 + k * 32, 16, 1024);
+            sm100::umma_bf16(tmem_d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          sm100::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        sm100::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        sm100::umma_commit(&tmem_full[buf]);  // accumulator complete (fires immediately when no MMA was issued)
       }
-      sm100::umma_commit(tmem_full);  // accumulator complete (fires immediately when no MMA was issued)
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m_blk * kBM + q * 32 + lane;
-    sm100::mbar_wait(tmem_full, 0);
-    sm100::tc_fence_after();
-    const bool row_ok = row < M;
-    const float keep_scale = epi.drop_p > 0.f ? 1.0f / (1.0f - epi.drop_p) : 1.0f;
-    const unsigned long long seed = (epi.drop_p > 0.f && epi.seed_ptr) ? (*epi.seed_ptr + epi.salt) : epi.salt;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      const int n0 = n_blk * BN + c0;
-      if (n0 >= N || num_k == 0) break;  // warp-uniform (num_k == 0: empty split, nothing to add)
+    const float alpha = epi.alpha;
+    const int act = epi.act, mul_mode = epi.mul_mode;
+    const bool has_drop = epi.drop_p > 0.f;
+    const float drop_p = epi.drop_p;
+    const float keep_scale = has_drop ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const unsigned long long seed = (has_drop && epi.seed_ptr) ? (*epi.seed_ptr + epi.salt) : epi.salt;
+    const float res_scale = epi.res_scale;
+    const bool vec16 = ((epi.ldc & 7) == 0) || (epi.c_f32 && (epi.ldc & 3) == 0);
+    const bool bias_vec = epi.bias && ((reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0);
+
+    auto load16 = [](const __nv_bfloat16* p, float* f) {  // 16 bf16 (32 B, 16-byte aligned) -> f32
+      const uint4 u0 = *reinterpret_cast<const uint4*>(p);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(p + 8);
+      const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[2 * j] = __uint_as_float(w[j] << 16);
+        f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+      }
+    };
+    auto store16 = [](__nv_bfloat16* p, const float* f) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      *reinterpret_cast<uint4*>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(p + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    };
+
+
+    // C staging: per warp two 32-row x 128-byte buffers in the 128B-swizzled layout the store tensor map expects
+    uint8_t* stage_base = sOut + (warp - 2) * (2 * 32 * 128);
+    const bool tma_out = epi.tma_store != 0;
+    const int group_cols = epi.c_f32 ? 32 : 64;  // columns per 128-byte staging row
+    uint32_t stage_it = 0;
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
+      int m_blk, n_blk, k_begin, num_k;
+      decode(tile, m_blk, n_blk, k_begin, num_k);
+      const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+      const int row = m_blk * kBM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const __nv_bfloat16* mul_row = epi.mul ? reinterpret_cast<const __nv_bfloat16*>(epi.mul) + (size_t)row * epi.ld_mul : nullptr;
+      const __nv_bfloat16* res_row = epi.residual ? reinterpret_cast<const __nv_bfloat16*>(epi.residual) + (size_t)row * epi.ld_res : nullptr;
+      __nv_bfloat16* aux_row = epi.aux ? reinterpret_cast<__nv_bfloat16*>(epi.aux) + (size_t)row * epi.ld_aux : nullptr;
+      const uint32_t tmem_row = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      const int n_cols = min(BN, N - n_blk * BN);  // valid columns of this tile
+      sm100::mbar_wait(&tmem_full[buf], aph);
+      sm100::tc_fence_after();
       uint32_t r[16];
-      sm100::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (num_k > 0) sm100::tmem_ld_32x32b_x16(tmem_row, r);
+#pragma unroll 1
+      for (int c0 = 0; c0 < n_cols && num_k > 0; c0 += 16) {
+      const int n0 = n_blk * BN + c0;
       sm100::tmem_ld_wait();
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + j;
-        float x = __uint_as_float(r[j]) * epi.alpha;
-        if (epi.bias && n < N) x += __ldg(epi.bias + n);
-        v[j] = x;
-      }
-      if (epi.aux && row_ok) {  // pre-activation copy
-        __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(epi.aux) + (size_t)row * epi.ld_aux + n0;
-        if (n0 + 16 <= N) {
-          uint32_t pk[8];
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      if (c0 + 16 < n_cols) sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)(c0 + 16), r);  // prefetch the next chunk
+      const bool full = (c0 + 16 <= n_cols) && vec16;
+      if (alpha != 1.0f) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            pk[j] = *reinterpret_cast<uint32_t*>(&t);
+        for (int j = 0; j < 16; ++j) v[j] *= alpha;
+      }
+      if (epi.bias) {
+        if (bias_vec && c0 + 16 <= n_cols) {  // same address in every lane: one broadcast transaction per load
+          const float4* gb = reinterpret_cast<const float4*>(epi.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = __ldg(gb + j);
+            v[4 * j] += b4.x;
+            v[4 * j + 1] += b4.y;
+            v[4 * j + 2] += b4.z;
+            v[4 * j + 3] += b4.w;
           }
-          *reinterpret_cast<uint4*>(ap) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(ap + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         } else {
-          for (int j = 0; j < 16 && n0 + j < N; ++j) ap[j] = __float2bfloat16(v[j]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < n_cols) v[j] += __ldg(epi.bias + n0 + j);
+        }
+      }
+      if (aux_row && row_ok) {
+        if (full && (epi.ld_aux & 7) == 0) store16(aux_row + n0, v);
+        else
+        {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < n_cols) aux_row[n0 + j] = __float2bfloat16(v[j]);
         }
       }
       if (epi.glu) {
-        // interleaved pairs: out[n/2] = a * sigmoid(b)
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = v[2 * j] * sigmoidf_(v[2 * j + 1]);
         if (row_ok) {
-          const int on0 = n0 >> 1;
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(epi.c) + (size_t)row * epi.ldc + on0;
-          if (n0 + 16 <= N) {
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(epi.c) + (size_t)row * epi.ldc + (n0 >> 1);
+          if (full) {
             uint32_t pk[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -237,94 +340,142 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             *reinterpret_cast<uint4*>(cp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           } else {
-            for (int j = 0; j < 8 && n0 + 2 * j + 1 < N; ++j) cp[j] = __float2bfloat16(o[j]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (c0 + 2 * j + 1 < n_cols) cp[j] = __float2bfloat16(o[j]);
           }
         }
         continue;
       }
+      if (act == 1) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = v[j];
-        if (epi.act == 1) x = x * sigmoidf_(x);
-        else if (epi.act == 2) x = fmaxf(x, 0.f);
-        else if (epi.act == 3) x = tanhf(x);
-        v[j] = x;
+        for (int j = 0; j < 16; ++j) v[j] = v[j] * sigmoidf_(v[j]);
+      } else if (act == 2) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (act == 3) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
       }
-      if (epi.mul && row_ok) {
-        const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(epi.mul) + (size_t)row * epi.ld_mul + n0;
+      if (mul_row && row_ok) {
+        float z[16];
+        if (full && (epi.ld_mul & 7) == 0) {
+          load16(mul_row + n0, z);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (n0 + j < N) {
-            const float z = __bfloat162float(mp[j]);
-            float f;
-            if (epi.mul_mode == 1) {
-              const float sg = sigmoidf_(z);
-              f = sg * (1.0f + z * (1.0f - sg));  // d swish / dz
-            } else if (epi.mul_mode == 2) {
-              f = 1.0f - z * z;  // d tanh / dz given tanh value
-            } else {
-              f = z;
-            }
-            v[j] *= f;
+          for (int j = 0; j < 16; ++j) z[j] = (c0 + j < n_cols) ? __bfloat162float(mul_row[n0 + j]) : 0.f;
+        }
+        if (mul_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float sg = sigmoidf_(z[j]);
+            v[j] *= sg * (1.0f + z[j] * (1.0f - sg));  // d swish / dz
           }
+        } else if (mul_mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= 1.0f - z[j] * z[j];  // d tanh / dz from the tanh value
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= z[j];
         }
       }
-      if (epi.drop_p > 0.f) {
+      if (has_drop) {
+        const unsigned long long base = (unsigned long long)row * (unsigned long long)N + (unsigned long long)n0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float u = hash_uniform(seed, (unsigned long long)row * (unsigned long long)N + (unsigned long long)(n0 + j));
-          v[j] = (u >= epi.drop_p) ? v[j] * keep_scale : 0.f;
-        }
+        for (int j = 0; j < 16; ++j) v[j] = (hash_uniform(seed, base + j) >= drop_p) ? v[j] * keep_scale : 0.f;
       }
-      if (epi.residual && row_ok) {
-        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(epi.residual) + (size_t)row * epi.ld_res + n0;
+      if (res_row && row_ok) {
+        float z[16];
+        if (full && (epi.ld_res & 7) == 0) {
+          load16(res_row + n0, z);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n0 + j < N) v[j] = __bfloat162float(rp[j]) + epi.res_scale * v[j];
+          for (int j = 0; j < 16; ++j) z[j] = (c0 + j < n_cols) ? __bfloat162float(res_row[n0 + j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = z[j] + res_scale * v[j];
       }
       if (epi.colsum) {
-        // column sums over this warp's 32 rows, one atomic per column per warp
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float s = row_ok ? v[j] : 0.f;
-          s = warp_sum(s);
-          if (lane == 0 && n0 + j < N) atomicAdd(epi.colsum + n0 + j, s);
+          float sj = row_ok ? v[j] : 0.f;
+          sj = warp_sum(sj);
+          if (lane == 0 && c0 + j < n_cols) atomicAdd(epi.colsum + n0 + j, sj);
         }
       }
-      if (row_ok) {
+      if (tma_out) {
+        // stage this thread's 16 values (one row) into the swizzled buffer; a full 128-byte group leaves with one TMA store
+        uint8_t* sbuf = stage_base + (stage_it & 1) * (32 * 128);
+        const int col_in_group = c0 % group_cols;
+        if (col_in_group == 0) {
+          // buffer reuse: the store issued two groups ago must have finished reading it
+          if (lane == 0) sm100::tma_store_wait_read<1>();
+          __syncwarp();
+        }
+        uint8_t* srow = sbuf + lane * 128;
+        if (epi.c_f32) {
+          const int cg = col_in_group >> 2;  // 16-byte chunk index of the first of 4 chunks
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(srow + (((cg + j) ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          const int cg = col_in_group >> 3;
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          *reinterpret_cast<uint4*>(srow + ((cg ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(srow + (((cg + 1) ^ (lane & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        const bool group_done = (col_in_group + 16 == group_cols) || (c0 + 16 >= n_cols);
+        if (group_done) {
+          sm100::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            sm100::tma_store_2d(&tmC, sbuf, n_blk * BN + (c0 - col_in_group), m_blk * kBM + q * 32);
+            sm100::tma_store_commit();
+          }
+          ++stage_it;
+        }
+      } else if (row_ok) {
         if (epi.c_f32) {
           float* cp = reinterpret_cast<float*>(epi.c) + (size_t)row * epi.ldc + n0;
           if (epi.atomic_out) {
-            for (int j = 0; j < 16 && n0 + j < N; ++j) atomicAdd(cp + j, v[j]);
-          } else if (n0 + 16 <= N && ((epi.ldc & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < n_cols) atomicAdd(cp + j, v[j]);
+          } else if (full) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(cp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            for (int j = 0; j < 16 && n0 + j < N; ++j) cp[j] = v[j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < n_cols) cp[j] = v[j];
           }
         } else {
           __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(epi.c) + (size_t)row * epi.ldc + n0;
-          if (n0 + 16 <= N && ((epi.ldc & 7) == 0)) {
-            uint32_t pk[8];
+          if (full) store16(cp, v);
+          else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              pk[j] = *reinterpret_cast<uint32_t*>(&t);
-            }
-            *reinterpret_cast<uint4*>(cp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(cp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-            for (int j = 0; j < 16 && n0 + j < N; ++j) cp[j] = __float2bfloat16(v[j]);
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < n_cols) cp[j] = __float2bfloat16(v[j]);
           }
         }
       }
     }
-    sm100::tc_fence_before();
+      // this thread's tcgen05.ld of the tile are complete: hand the accumulator buffer back to the MMA warp
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&tmem_empty[buf]);
+    }
+    if (tma_out && lane == 0) sm100::tma_store_wait_all();  // smem must outlive the in-flight stores
   }
   __syncthreads();
   if (warp == 1) {
     sm100::tc_fence_after();
-    sm100::tmem_dealloc(tmem_base, kTmemCols);
+    sm100::tmem_dealloc(tmem_base, S::TMEM_COLS);
   }
 }
 
@@ -338,14 +489,23 @@ static int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, 
   if (!B_MN) ok = ok && make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, kBK);
   else ok = ok && make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, 64);
   if (!ok) return TFASR_INVALID_VALUE;
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  GemmEpi e2 = epi;
+  e2.tma_store = 0;
+  if (!epi.glu && !epi.atomic_out) {
+    const int eb = epi.c_f32 ? 4 : 2;
+    if (make_tmap_2d(&tmC, epi.c, eb, (uint64_t)M, (uint64_t)N, (uint64_t)epi.ldc, 32, 128 / eb) && (N % (16 / eb) == 0)) e2.tma_store = 1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
       return TFASR_EXECUTION_FAILED;
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div(M, kBM), (unsigned)ceil_div(N, BN), (unsigned)splits);
-  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, S::TOTAL, stream>>>(tmA, tmB, epi, M, N, K);
+  const long long tiles = (long long)ceil_div(M, kBM) * ceil_div(N, BN) * splits;
+  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, S::TOTAL, stream>>>(tmA, tmB, tmC, e2, M, N, K, splits);
   count_launch();
   return check_launch();
 }
