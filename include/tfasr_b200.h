@@ -102,6 +102,13 @@ int tfasr_rnnt_loss_bwd_f32(const float* logits, const int32_t* labels, const in
                             const float* grad_scale, float* grads, const void* workspace, size_t workspace_bytes,
                             tfasr_stream_t stream);
 
+/* Training-head variant of the backward: the gradient is written as bf16 with row pitch ld_grads (elements, multiple of 4) — the
+ * operand format of the joint's backward GEMMs — and may be written IN PLACE over the fp32 logits (grads == logits, ld_grads = 2V).
+ * dbias [V] (f32, may be NULL) accumulates the column sums (the vocab Dense bias gradient).  Requires V % 4 == 0, V <= 2048. */
+int tfasr_rnnt_loss_bwd_bf16(const float* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
+                             int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
+                             int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * CTC loss + gradient (tf.nn.ctc_loss, dense labels, batch-major logits [B, T, V], blank_index 0).
  *   costs [B] f32; grads [B, T, V] f32 = d costs[b] / d logits (may alias logits).  Infeasible
@@ -161,6 +168,14 @@ int tfasr_layernorm_bwd(const void* dy, const void* x, int32_t x_is_f32, const f
 int tfasr_scale_mask_colsum(const void* in, const void* add, void* out, float* colsum, int32_t M, int32_t N, float scale, float dropout_p,
                             const unsigned long long* seed_ptr, unsigned long long salt, tfasr_stream_t stream);
 int tfasr_glu_bwd(const void* aux, const void* dg, void* daux, float* colsum, int32_t M, int32_t D, tfasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Transducer joint, training path (base_transducer.py:199-207,291): the elementwise / reduction halves around the GEMMs.
+ *   joint_tanh_fwd:   h[b,t,u,:] = tanh(e[b,t,:] + p[b,u,:])         e [B,T,J], p [B,U1,J], h [B,T,U1,J]  (all bf16)
+ *   joint_reduce_bwd: de[b,t,:] = sum_u dz[b,t,u,:] (written), dp[b,u,:] += sum_t dz[b,t,u,:] (accumulated; zero it first)
+ * ---------------------------------------------------------------------------------------------- */
+int tfasr_joint_tanh_fwd(const void* e, const void* p, void* h, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream);
+int tfasr_joint_reduce_bwd(const void* dz, float* de, float* dp, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream);
 
 #ifdef __cplusplus
 }

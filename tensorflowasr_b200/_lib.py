@@ -56,6 +56,10 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
     "tfasr_rnnt_loss_bwd_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tfasr_rnnt_loss_bwd_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                           c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tfasr_joint_tanh_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_joint_reduce_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_gemm_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                   POINTER(GemmEpilogue), c_void_p]),
     "tfasr_layernorm_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),

@@ -259,6 +259,109 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_grad_kernel(const float* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- K3' (training head)
+// Same gradient as K3, written as bf16 with an arbitrary row pitch (ld_g elements) — what the joint's backward GEMMs consume —
+// optionally IN PLACE over the fp32 logits (ld_g = 2V: row r's bf16 gradient occupies the first half of row r's fp32 logits,
+// which this warp has already pulled into registers).  Persistent: each warp walks rows with a grid stride and keeps per-column
+// partial sums in registers, so the vocab-bias gradient costs one atomic per column per CTA instead of one per row.
+template <int NV4>
+__global__ void __launch_bounds__(kRowWarps * 32) rnnt_grad_bf16_kernel(const float* logits, const int32_t* __restrict__ labels,
+                                                                        const int32_t* __restrict__ logit_len,
+                                                                        const int32_t* __restrict__ label_len, int B, int T, int U1, int V,
+                                                                        RnntWs ws, const float* __restrict__ costs,
+                                                                        const float* __restrict__ grad_scale, __nv_bfloat16* grads, int64_t ld_g,
+                                                                        float* __restrict__ dbias) {
+  extern __shared__ float s_cs[];  // [V] column sums of this CTA
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nrows = (int64_t)B * T * U1;
+  const int n4 = V >> 2;
+  if (dbias) {
+    for (int j = threadIdx.x; j < V; j += blockDim.x) s_cs[j] = 0.f;
+    __syncthreads();
+  }
+  float4 cs[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t row = (int64_t)blockIdx.x * kRowWarps + warp; row < nrows; row += (int64_t)gridDim.x * kRowWarps) {
+    const int u = (int)(row % U1);
+    const int t = (int)((row / U1) % T);
+    const int b = (int)(row / ((int64_t)U1 * T));
+    const int Tb = logit_len[b], Ub = label_len[b];
+    uint2* g2 = reinterpret_cast<uint2*>(grads + row * ld_g);
+    if (!((t < Tb) && (u <= Ub))) {
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const int j = lane + 32 * i;
+        if (j < n4) g2[j] = make_uint2(0u, 0u);
+      }
+      continue;
+    }
+    const float logz = -costs[b];
+    const float a = ws.alpha[row];
+    const float lse = ws.lse[row];
+    float gb = 0.f, gt = 0.f;
+    int label = -1;
+    if (t < Tb - 1) gb = -expf(a + ws.beta[row + U1] + ws.blank[row] - logz);
+    else if (u == Ub) gb = -1.0f;
+    if (u < Ub) {
+      gt = -expf(a + ws.beta[row + 1] + ws.truth[row] - logz);
+      label = labels[(int64_t)b * (U1 - 1) + u];
+    }
+    const float sc = grad_scale ? grad_scale[b] : 1.0f;
+    gb *= sc;
+    gt *= sc;
+    const float gsum = gb + gt;
+    const float4* x4 = reinterpret_cast<const float4*>(logits + row * V);
+    float4 v[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n4) v[i] = ld_stream_f4(x4 + j);
+    }
+    __syncwarp();  // in-place mode: every lane has its part of the row before any lane overwrites it
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n4) {
+        float4 o;
+        o.x = -__expf(v[i].x - lse) * gsum;
+        o.y = -__expf(v[i].y - lse) * gsum;
+        o.z = -__expf(v[i].z - lse) * gsum;
+        o.w = -__expf(v[i].w - lse) * gsum;
+        const int c0 = 4 * j;
+        if (c0 == 0) o.x += gb;
+        if (label >= c0 && label < c0 + 4) {
+          const int r = label - c0;
+          if (r == 0) o.x += gt;
+          else if (r == 1) o.y += gt;
+          else if (r == 2) o.z += gt;
+          else o.w += gt;
+        }
+        cs[i].x += o.x;
+        cs[i].y += o.y;
+        cs[i].z += o.z;
+        cs[i].w += o.w;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        g2[j] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+  }
+  if (dbias) {
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n4) {
+        atomicAdd(&s_cs[4 * j], cs[i].x);
+        atomicAdd(&s_cs[4 * j + 1], cs[i].y);
+        atomicAdd(&s_cs[4 * j + 2], cs[i].z);
+        atomicAdd(&s_cs[4 * j + 3], cs[i].w);
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < V; j += blockDim.x) atomicAdd(dbias + j, s_cs[j]);
+  }
+}
+
 static int rnnt_check(const void* logits, const int32_t* labels, const int32_t* tl, const int32_t* ul, int B, int T, int U1, int V,
                       int blank, const void* ws, size_t ws_bytes) {
   if (blank != 0) return TFASR_INVALID_VALUE;  // losses/base_loss.py:24
@@ -312,9 +415,39 @@ static int rnnt_backward(const float* logits, const int32_t* labels, const int32
   return check_launch();
 }
 
+template <int NV4>
+static void launch_grad_bf16(const float* logits, const int32_t* labels, const int32_t* tl, const int32_t* ul, int B, int T, int U1, int V,
+                             const RnntWs& ws, const float* costs, const float* grad_scale, __nv_bfloat16* grads, int64_t ld_g, float* dbias,
+                             cudaStream_t stream) {
+  const int64_t nrows = (int64_t)B * T * U1;
+  int64_t ctas = ceil_div(nrows, kRowWarps);
+  if (ctas > kNumSMs * 8) ctas = kNumSMs * 8;
+  rnnt_grad_bf16_kernel<NV4><<<(unsigned)ctas, kRowWarps * 32, dbias ? sizeof(float) * V : 0, stream>>>(logits, labels, tl, ul, B, T, U1, V, ws, costs,
+                                                                                                        grad_scale, grads, ld_g, dbias);
+}
+
 }  // namespace tfasr
 
 using namespace tfasr;
+
+extern "C" int tfasr_rnnt_loss_bwd_bf16(const float* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
+                                        int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
+                                        int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream_) {
+  int st = rnnt_check(logits, labels, logit_len, label_len, B, T, U1, V, blank, workspace, workspace_bytes);
+  if (st != TFASR_OK) return st;
+  if (!costs || !grads || ld_grads < V || (ld_grads & 3)) return TFASR_INVALID_VALUE;
+  if ((V & 3) || V > 2048 || (reinterpret_cast<uintptr_t>(logits) & 15) || (reinterpret_cast<uintptr_t>(grads) & 7)) return TFASR_INVALID_VALUE;
+  if (B == 0) return TFASR_OK;
+  const RnntWs ws = rnnt_ws_carve(const_cast<void*>(workspace), B, T, U1);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  __nv_bfloat16* g = static_cast<__nv_bfloat16*>(grads);
+  if (V <= 256) launch_grad_bf16<2>(logits, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, ld_grads, dbias, stream);
+  else if (V <= 512) launch_grad_bf16<4>(logits, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, ld_grads, dbias, stream);
+  else if (V <= 1024) launch_grad_bf16<8>(logits, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, ld_grads, dbias, stream);
+  else launch_grad_bf16<16>(logits, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, ld_grads, dbias, stream);
+  count_launch();
+  return check_launch();
+}
 
 extern "C" size_t tfasr_rnnt_workspace_bytes(int32_t B, int32_t T, int32_t U1, int32_t V) {
   (void)V;

@@ -167,3 +167,64 @@ class _LinearFn(torch.autograd.Function):
 def linear(x, pack, activation=None, residual=None, factor=1.0, drop_p=0.0, salt=0, seed=None):
     """x [M, K] bf16 -> [M, N] bf16 through the tcgen05 GEMM (bias / activation / dropout / residual fused in the epilogue)."""
     return _LinearFn.apply(x, pack, activation, residual, float(factor), float(drop_p), int(salt), seed)
+
+
+# ------------------------------------------------------------------------------------------------ joint + RNN-T loss head
+class _TransducerHeadFn(torch.autograd.Function):
+    """Joint network + RNN-T loss for training on the hand-written kernels (base_transducer.py:199-207,280-293 + losses/impl/rnnt.py):
+
+      forward   h = tanh(e + p) (bf16)  ->  logits = h Wv + bv (tcgen05 GEMM, f32 out)  ->  K1 (lse) + K2 (alpha/beta wavefronts)
+      backward  K3' writes d logits as bf16 IN PLACE over the fp32 logits (+ vocab-bias gradient)  ->
+                dz = (dlogits Wv^T) * (1 - h^2) (GEMM epilogue)  ->  dWv += h^T dlogits (MN-major split-K GEMM)  ->
+                de = sum_u dz, dp = sum_t dz
+    The [B,T,U+1,V] tensor exists once (fp32 logits, then reused for its own gradient).
+    """
+
+    @staticmethod
+    def forward(ctx, e, p, pack: WeightPack, labels, logit_length, label_length):
+        from . import _lib
+
+        lib = _lib.load()
+        B, T, J = e.shape
+        U1 = p.shape[1]
+        V = pack.wt.shape[0]
+        M = B * T * U1
+        h = kernels.joint_tanh_fwd(e.contiguous(), p.contiguous())
+        logits = kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out_dtype=torch.float32)
+        ws_bytes = lib.tfasr_rnnt_workspace_bytes(B, T, U1, V)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=e.device)
+        costs = torch.empty(B, dtype=torch.float32, device=e.device)
+        with _lib.TIMERS.region("rnnt_fwd"):
+            _lib.check(lib.tfasr_rnnt_loss_fwd_f32(logits.data_ptr(), labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(),
+                                                   B, T, U1, V, 0, costs.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(e.device)),
+                       "tfasr_rnnt_loss_fwd_f32")
+        ctx.save_for_backward(h, logits, labels, logit_length, label_length, costs, ws)
+        ctx.misc = (pack, (B, T, U1, J, V), e.dtype, p.dtype)
+        return costs
+
+    @staticmethod
+    def backward(ctx, dcosts):
+        from . import _lib
+
+        lib = _lib.load()
+        h, logits, labels, logit_length, label_length, costs, ws = ctx.saved_tensors
+        pack, (B, T, U1, J, V), de_dtype, dp_dtype = ctx.misc
+        M = B * T * U1
+        scale = dcosts.float().contiguous()
+        dl = logits.view(M, V).view(torch.bfloat16)  # [M, 2V] bf16 view of the same memory; gradient lands in [:, :V]
+        with _lib.TIMERS.region("rnnt_bwd"):
+            _lib.check(lib.tfasr_rnnt_loss_bwd_bf16(logits.data_ptr(), labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(),
+                                                    B, T, U1, V, 0, costs.data_ptr(), scale.data_ptr(), dl.data_ptr(), 2 * V,
+                                                    _grad(pack.bias).data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(h.device)),
+                       "tfasr_rnnt_loss_bwd_bf16")
+        dlv = dl[:, :V]
+        h2 = h.view(M, J)
+        dz = kernels.gemm(dlv, pack.w, mul=h2, mul_mode="tanh_grad")  # [M, J]
+        kernels.gemm(h2, dlv, mn_major=True, out=_grad(pack.param), accumulate=True, k_splits=32)  # dWv [J, V]
+        de, dp = kernels.joint_reduce_bwd(dz.view(B, T, U1, J))
+        return de.to(de_dtype), dp.to(dp_dtype), None, None, None, None
+
+
+def transducer_head(e, p, pack, labels, logit_length, label_length):
+    """e [B,T,J], p [B,U1,J] bf16 -> per-utterance RNN-T costs [B] f32."""
+    return _TransducerHeadFn.apply(e, p, pack, labels, logit_length, label_length)

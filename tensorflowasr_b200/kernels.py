@@ -103,3 +103,23 @@ def glu_bwd(aux, dg, colsum=None):
     daux = torch.empty_like(aux)
     _lib.check(lib.tfasr_glu_bwd(_lib.ptr(aux), _lib.ptr(dg), _lib.ptr(daux), _lib.ptr(colsum), M, D, _lib.stream_ptr(dg.device)), "tfasr_glu_bwd")
     return daux
+
+
+def joint_tanh_fwd(e, p):
+    """e [B,T,J], p [B,U1,J] (bf16) -> h [B,T,U1,J] bf16 = tanh(e[:, :, None] + p[:, None])."""
+    lib = _lib.load()
+    B, T, J = e.shape
+    U1 = p.shape[1]
+    h = torch.empty((B, T, U1, J), dtype=torch.bfloat16, device=e.device)
+    _lib.check(lib.tfasr_joint_tanh_fwd(_lib.ptr(e), _lib.ptr(p), _lib.ptr(h), B, T, U1, J, _lib.stream_ptr(e.device)), "tfasr_joint_tanh_fwd")
+    return h
+
+
+def joint_reduce_bwd(dz):
+    """dz [B,T,U1,J] bf16 -> (de [B,T,J] f32 = sum over u, dp [B,U1,J] f32 = sum over t)."""
+    lib = _lib.load()
+    B, T, U1, J = dz.shape
+    de = torch.empty((B, T, J), dtype=torch.float32, device=dz.device)
+    dp = torch.zeros((B, U1, J), dtype=torch.float32, device=dz.device)
+    _lib.check(lib.tfasr_joint_reduce_bwd(_lib.ptr(dz), _lib.ptr(de), _lib.ptr(dp), B, T, U1, J, _lib.stream_ptr(dz.device)), "tfasr_joint_reduce_bwd")
+    return de, dp

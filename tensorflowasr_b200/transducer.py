@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops, schemas
+from . import fused, ops, schemas
 from .base_model import BaseModel
 from .encoder import ConformerEncoder, _Params
 from .losses import RnntLoss
@@ -152,6 +152,9 @@ class Transducer(BaseModel):
         label_length = y.labels_length.to(device=dev, dtype=torch.int32)
         labels = y.labels.to(device=dev, dtype=torch.int32).contiguous()
         logit_length = torch.where(logit_length < label_length, label_length, logit_length).contiguous()  # base_loss.py:36
+        if ops.fused_active(e):
+            pack = fused.WeightPack(self.joint_net["vocab.kernel"], self.joint_net["vocab.bias"])
+            return fused.transducer_head(e.to(torch.bfloat16), p.to(torch.bfloat16), pack, labels, logit_length, label_length.contiguous())
         return ops.transducer_loss_head(e, p, self.joint_net["vocab.kernel"], self.joint_net["vocab.bias"], labels, logit_length,
                                         label_length.contiguous())
 
