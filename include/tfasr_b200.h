@@ -177,6 +177,28 @@ int tfasr_glu_bwd(const void* aux, const void* dg, void* daux, float* colsum, in
 int tfasr_joint_tanh_fwd(const void* e, const void* p, void* h, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream);
 int tfasr_joint_reduce_bwd(const void* dz, float* de, float* dp, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Conv2dSubsampling pieces and BatchNorm (+ swish), channels-last bf16 (subsampling.py:163-230, convolution.py:25-37,132-144;
+ * keras BatchNormalization eps 1e-3 with batch statistics over all leading axes, as in conformer.py:326-333 / subsampling.py:199-206).
+ *   conv1_3x3s2_fwd / wgrad : first conv (Cin = 1): x [B,T,F] f32, w [3,3,1,C] f32 -> y [B,ceil(T/2),ceil(F/2),C] bf16; causal pad
+ *   im2col_3x3s2 / col2im_3x3s2 : a [B,T1,F1,C] <-> col [B*T2*F2, 9C] (column order kh,kw,c) feeding the tcgen05 GEMM of conv 2
+ *   bn_stats        : sums[0][c] += sum x, sums[1][c] += sum x^2 over the R rows of x [R,C]
+ *   bn_apply        : y = act(x * scale[c] + shift[c]), act 0 none / 1 swish
+ *   bn_bwd_stats    : d = dy * act'(.), sums[0][c] += sum d, sums[1][c] += sum d * xhat
+ *   bn_bwd_apply    : dx = scale * (d - sums[0]/count - xhat * sums[1]/count)   (count <= 0: fixed statistics, dx = scale * d)
+ * ---------------------------------------------------------------------------------------------- */
+int tfasr_conv1_3x3s2_fwd(const float* x, const float* w, const float* bias, void* y, int32_t B, int32_t T, int32_t F, int32_t C,
+                          tfasr_stream_t stream);
+int tfasr_conv1_3x3s2_wgrad(const float* x, const void* dy, float* dw, int32_t B, int32_t T, int32_t F, int32_t C, tfasr_stream_t stream);
+int tfasr_im2col_3x3s2(const void* a, void* col, int32_t B, int32_t T1, int32_t F1, int32_t C, tfasr_stream_t stream);
+int tfasr_col2im_3x3s2(const void* dcol, void* da, int32_t B, int32_t T1, int32_t F1, int32_t C, tfasr_stream_t stream);
+int tfasr_bn_stats(const void* x, float* sums, int64_t R, int32_t C, tfasr_stream_t stream);
+int tfasr_bn_apply(const void* x, const float* scale, const float* shift, void* y, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream);
+int tfasr_bn_bwd_stats(const void* dy, const void* x, const float* scale, const float* shift, const float* mean, const float* rstd,
+                       float* sums, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream);
+int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* scale, const float* shift, const float* mean, const float* rstd,
+                       const float* sums, float count, void* dx, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,16 @@ SIGNATURES = {
                                            c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tfasr_joint_tanh_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_joint_reduce_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_conv1_3x3s2_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_conv1_3x3s2_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_im2col_3x3s2": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_col2im_3x3s2": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_bn_stats": (c_int32, [c_void_p, c_void_p, ctypes.c_int64, c_int32, c_void_p]),
+    "tfasr_bn_apply": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int32, c_int32, c_void_p]),
+    "tfasr_bn_bwd_stats": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int32, c_int32,
+                                     c_void_p]),
+    "tfasr_bn_bwd_apply": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                     ctypes.c_int64, c_int32, c_int32, c_void_p]),
     "tfasr_gemm_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                   POINTER(GemmEpilogue), c_void_p]),
     "tfasr_layernorm_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),

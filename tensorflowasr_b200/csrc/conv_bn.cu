@@ -1,0 +1,401 @@
+// Conv2dSubsampling and BatchNorm kernels for sm_100a (channels-last bf16 activations, fp32 statistics).
+//
+// Replaces, around the tcgen05 GEMM that does the dense part of conv 2:
+//   Conv2D(3x3, stride 2, causal) #1, Cin = 1         tensorflow_asr/models/layers/subsampling.py:218-230 + convolution.py:132-144
+//   im2col / col2im of Conv2D #2 (Cin = 144)          (the reference hands this to cuDNN)
+//   BatchNormalization(sync) + swish, fwd and bwd      subsampling.py:199-206, conformer.py:326-333,371-372 (keras BN: eps 1e-3,
+//                                                      batch statistics over every leading axis, biased variance)
+// All of these are HBM-bound streaming kernels; per-channel reductions use CTA-level partial sums + one atomic per channel per CTA.
+#include "common.cuh"
+
+namespace tfasr {
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------- conv 1 (Cin = 1), forward
+// x [B, T, F] f32 -> y [B, T1, F1, C] bf16 with T1 = ceil(T/2), F1 = ceil(F/2); causal pad (2 top, 2 left), VALID, stride 2.
+// w [3, 3, 1, C] f32, bias [C].  block: (C/2 threads, PY positions); each thread owns a channel pair.
+constexpr int kConv1PY = 8;
+__global__ void __launch_bounds__(1024) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ y, int B, int T, int F, int T1, int F1, int C,
+                                                         int pos_per_block) {
+  const int c2 = threadIdx.x;  // channel pair
+  float w0[9], w1[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    w0[k] = w[k * C + 2 * c2];
+    w1[k] = w[k * C + 2 * c2 + 1];
+  }
+  const float b0 = bias[2 * c2], b1 = bias[2 * c2 + 1];
+  const int64_t npos = (int64_t)B * T1 * F1;
+  const int64_t p0 = (int64_t)blockIdx.x * pos_per_block;
+  for (int64_t p = p0 + threadIdx.y; p < min(npos, p0 + pos_per_block); p += blockDim.y) {
+    const int f1 = (int)(p % F1);
+    const int t1 = (int)((p / F1) % T1);
+    const int b = (int)(p / ((int64_t)F1 * T1));
+    const float* xb = x + (size_t)b * T * F;
+    float a0 = b0, a1 = b1;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int t = 2 * t1 + kh - 2;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int f = 2 * f1 + kw - 2;
+        const float v = (t >= 0 && t < T && f >= 0 && f < F) ? __ldg(xb + (size_t)t * F + f) : 0.f;
+        a0 = fmaf(v, w0[kh * 3 + kw], a0);
+        a1 = fmaf(v, w1[kh * 3 + kw], a1);
+      }
+    }
+    *reinterpret_cast<__nv_bfloat162*>(y + (size_t)p * C + 2 * c2) = __floats2bfloat162_rn(a0, a1);
+  }
+}
+
+// conv 1 weight gradient: dw[k, c] += sum_pos dy[pos, c] * x[pos shifted by tap k]
+__global__ void __launch_bounds__(1024) conv1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw,
+                                                           int B, int T, int F, int T1, int F1, int C, int pos_per_block) {
+  extern __shared__ float s_dw[];  // [9][C]
+  const int c2 = threadIdx.x;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nth = blockDim.x * blockDim.y;
+  for (int i = tid; i < 9 * C; i += nth) s_dw[i] = 0.f;
+  __syncthreads();
+  float g0[9], g1[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g0[k] = g1[k] = 0.f;
+  const int64_t npos = (int64_t)B * T1 * F1;
+  const int64_t p0 = (int64_t)blockIdx.x * pos_per_block;
+  for (int64_t p = p0 + threadIdx.y; p < min(npos, p0 + pos_per_block); p += blockDim.y) {
+    const int f1 = (int)(p % F1);
+    const int t1 = (int)((p / F1) % T1);
+    const int b = (int)(p / ((int64_t)F1 * T1));
+    const float* xb = x + (size_t)b * T * F;
+    const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(dy + (size_t)p * C + 2 * c2);
+    const float d0 = __low2float(d), d1 = __high2float(d);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int t = 2 * t1 + kh - 2;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int f = 2 * f1 + kw - 2;
+        const float v = (t >= 0 && t < T && f >= 0 && f < F) ? __ldg(xb + (size_t)t * F + f) : 0.f;
+        g0[kh * 3 + kw] = fmaf(v, d0, g0[kh * 3 + kw]);
+        g1[kh * 3 + kw] = fmaf(v, d1, g1[kh * 3 + kw]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    atomicAdd(&s_dw[k * C + 2 * c2], g0[k]);
+    atomicAdd(&s_dw[k * C + 2 * c2 + 1], g1[k]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * C; i += nth) atomicAdd(dw + i, s_dw[i]);
+}
+
+// ---------------------------------------------------------------------------------------------- im2col / col2im (3x3, stride 2, causal)
+// a [B, T1, F1, C] bf16 -> col [B*T2*F2, 9*C] bf16 (column order kh, kw, c = the Keras kernel [kh,kw,cin,cout] flattened).
+// One thread per 16-byte chunk (8 channels).
+__global__ void __launch_bounds__(256) im2col_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ col, int B, int T1, int F1,
+                                                     int T2, int F2, int C) {
+  const int c8n = C >> 3;
+  const int64_t total = (int64_t)B * T2 * F2 * 9 * c8n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    const int k = (int)((i / c8n) % 9);
+    const int64_t p = i / ((int64_t)c8n * 9);
+    const int f2 = (int)(p % F2);
+    const int t2 = (int)((p / F2) % T2);
+    const int b = (int)(p / ((int64_t)F2 * T2));
+    const int t = 2 * t2 + k / 3 - 2, f = 2 * f2 + k % 3 - 2;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t >= 0 && t < T1 && f >= 0 && f < F1) v = *reinterpret_cast<const uint4*>(a + (((size_t)b * T1 + t) * F1 + f) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(col + (size_t)p * 9 * C + (size_t)k * C + c8 * 8) = v;
+  }
+}
+
+// dcol [B*T2*F2, 9*C] -> da [B, T1, F1, C]: each input element gathers the <= 4 taps that read it (no atomics).
+__global__ void __launch_bounds__(256) col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ da, int B, int T1, int F1,
+                                                     int T2, int F2, int C) {
+  const int c8n = C >> 3;
+  const int64_t total = (int64_t)B * T1 * F1 * c8n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    const int64_t q = i / c8n;
+    const int f = (int)(q % F1);
+    const int t = (int)((q / F1) % T1);
+    const int b = (int)(q / ((int64_t)F1 * T1));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int tt = t + 2 - kh;  // = 2 * t2
+      if (tt < 0 || (tt & 1)) continue;
+      const int t2 = tt >> 1;
+      if (t2 >= T2) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ff = f + 2 - kw;
+        if (ff < 0 || (ff & 1)) continue;
+        const int f2 = ff >> 1;
+        if (f2 >= F2) continue;
+        const size_t p = ((size_t)b * T2 + t2) * F2 + f2;
+        const uint4 u = *reinterpret_cast<const uint4*>(dcol + p * 9 * C + (size_t)(kh * 3 + kw) * C + c8 * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(w[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+      }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(da + (size_t)q * C + c8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- BatchNorm (+ swish), channels-last [R, C]
+// stats: sums[0][c] += sum_r x, sums[1][c] += sum_r x^2.   block (C/2, RY).
+__global__ void __launch_bounds__(1024) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, int64_t R, int C,
+                                                        int rows_per_block) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int c2 = threadIdx.x;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nth = blockDim.x * blockDim.y;
+  for (int i = tid; i < 2 * C; i += nth) s_acc[i] = 0.f;
+  __syncthreads();
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  for (int64_t r = r0 + threadIdx.y; r < min(R, r0 + rows_per_block); r += blockDim.y) {
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + (size_t)r * C + 2 * c2);
+    const float a = __low2float(v), b = __high2float(v);
+    s0 += a;
+    s1 += b;
+    q0 = fmaf(a, a, q0);
+    q1 = fmaf(b, b, q1);
+  }
+  atomicAdd(&s_acc[2 * c2], s0);
+  atomicAdd(&s_acc[2 * c2 + 1], s1);
+  atomicAdd(&s_acc[C + 2 * c2], q0);
+  atomicAdd(&s_acc[C + 2 * c2 + 1], q1);
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += nth) atomicAdd(sums + i, s_acc[i]);
+}
+
+// y = act(x * scale[c] + shift[c]);  act: 0 none, 1 swish.   scale = gamma * rstd, shift = beta - mean * scale.
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int64_t R, int C, int act) {
+  const int c2n = C >> 1;
+  const int64_t total = R * c2n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c2 = (int)(i % c2n);
+    const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(x)[i];
+    float a = fmaf(__low2float(v), scale[2 * c2], shift[2 * c2]);
+    float b = fmaf(__high2float(v), scale[2 * c2 + 1], shift[2 * c2 + 1]);
+    if (act == 1) {
+      a *= sigmoid_f(a);
+      b *= sigmoid_f(b);
+    }
+    reinterpret_cast<__nv_bfloat162*>(y)[i] = __floats2bfloat162_rn(a, b);
+  }
+}
+
+// backward pass 1: d = dy * act'(x * scale + shift);  sums[0][c] += sum d, sums[1][c] += sum d * xhat   (xhat = (x - mean) * rstd)
+__global__ void __launch_bounds__(1024) bn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            float* __restrict__ sums, int64_t R, int C, int act, int rows_per_block) {
+  extern __shared__ float s_acc[];
+  const int c2 = threadIdx.x;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nth = blockDim.x * blockDim.y;
+  for (int i = tid; i < 2 * C; i += nth) s_acc[i] = 0.f;
+  __syncthreads();
+  const float sc0 = scale[2 * c2], sc1 = scale[2 * c2 + 1], sh0 = shift[2 * c2], sh1 = shift[2 * c2 + 1];
+  const float m0 = mean[2 * c2], m1 = mean[2 * c2 + 1], rs0 = rstd[2 * c2], rs1 = rstd[2 * c2 + 1];
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  for (int64_t r = r0 + threadIdx.y; r < min(R, r0 + rows_per_block); r += blockDim.y) {
+    const size_t idx = (size_t)r * C + 2 * c2;
+    const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(x + idx);
+    const __nv_bfloat162 dv = *reinterpret_cast<const __nv_bfloat162*>(dy + idx);
+    const float x0 = __low2float(xv), x1 = __high2float(xv);
+    float d0 = __low2float(dv), d1 = __high2float(dv);
+    if (act == 1) {
+      const float z0 = fmaf(x0, sc0, sh0), z1 = fmaf(x1, sc1, sh1);
+      const float g0 = sigmoid_f(z0), g1 = sigmoid_f(z1);
+      d0 *= g0 * (1.0f + z0 * (1.0f - g0));
+      d1 *= g1 * (1.0f + z1 * (1.0f - g1));
+    }
+    s0 += d0;
+    s1 += d1;
+    q0 = fmaf(d0, (x0 - m0) * rs0, q0);
+    q1 = fmaf(d1, (x1 - m1) * rs1, q1);
+  }
+  atomicAdd(&s_acc[2 * c2], s0);
+  atomicAdd(&s_acc[2 * c2 + 1], s1);
+  atomicAdd(&s_acc[C + 2 * c2], q0);
+  atomicAdd(&s_acc[C + 2 * c2 + 1], q1);
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += nth) atomicAdd(sums + i, s_acc[i]);
+}
+
+// backward pass 2: dx = gamma * rstd * (d - mean_d - xhat * mean_dxhat),  mean_d = sums[0]/count, mean_dxhat = sums[1]/count.
+// (inference-style BN with fixed statistics: pass count <= 0 -> dx = scale * d)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ sums, float count, __nv_bfloat16* __restrict__ dx, int64_t R,
+                                                           int C, int act) {
+  const int c2n = C >> 1;
+  const int64_t total = R * c2n;
+  const float inv = count > 0.f ? 1.0f / count : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c2 = (int)(i % c2n);
+    const __nv_bfloat162 xv = reinterpret_cast<const __nv_bfloat162*>(x)[i];
+    const __nv_bfloat162 dv = reinterpret_cast<const __nv_bfloat162*>(dy)[i];
+    float o[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = 2 * c2 + h;
+      const float xx = h ? __high2float(xv) : __low2float(xv);
+      float d = h ? __high2float(dv) : __low2float(dv);
+      if (act == 1) {
+        const float z = fmaf(xx, scale[c], shift[c]);
+        const float g = sigmoid_f(z);
+        d *= g * (1.0f + z * (1.0f - g));
+      }
+      const float xh = (xx - mean[c]) * rstd[c];
+      o[h] = scale[c] * (d - sums[c] * inv - xh * sums[C + c] * inv);
+    }
+    reinterpret_cast<__nv_bfloat162*>(dx)[i] = __floats2bfloat162_rn(o[0], o[1]);
+  }
+}
+
+static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+static int rows_block_cfg(int C, dim3& block, int& rows_per_block, int64_t R, unsigned& grid) {
+  if (C < 2 || (C & 1) || C / 2 > 1024) return TFASR_INVALID_VALUE;
+  int ry = 1024 / (C / 2);
+  if (ry > 16) ry = 16;
+  if (ry < 1) ry = 1;
+  block = dim3(C / 2, ry);
+  int64_t target_blocks = kNumSMs * 4;
+  int64_t rpb = ceil_div(R, target_blocks);
+  if (rpb < ry) rpb = ry;
+  rows_per_block = (int)rpb;
+  grid = (unsigned)ceil_div(R, rpb);
+  return TFASR_OK;
+}
+
+}  // namespace tfasr
+
+using namespace tfasr;
+
+extern "C" int tfasr_conv1_3x3s2_fwd(const float* x, const float* w, const float* bias, void* y, int32_t B, int32_t T, int32_t F, int32_t C,
+                                     tfasr_stream_t stream) {
+  if (!x || !w || !bias || !y || B < 0 || T < 1 || F < 1) return TFASR_INVALID_VALUE;
+  if (B == 0) return TFASR_OK;
+  const int T1 = (T + 1) / 2, F1 = (F + 1) / 2;
+  dim3 block;
+  int ppb;
+  unsigned grid;
+  int st = rows_block_cfg(C, block, ppb, (int64_t)B * T1 * F1, grid);
+  if (st) return st;
+  conv1_fwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, static_cast<__nv_bfloat16*>(y), B, T, F, T1, F1, C, ppb);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_conv1_3x3s2_wgrad(const float* x, const void* dy, float* dw, int32_t B, int32_t T, int32_t F, int32_t C, tfasr_stream_t stream) {
+  if (!x || !dy || !dw || B < 0 || T < 1 || F < 1) return TFASR_INVALID_VALUE;
+  if (B == 0) return TFASR_OK;
+  const int T1 = (T + 1) / 2, F1 = (F + 1) / 2;
+  dim3 block;
+  int ppb;
+  unsigned grid;
+  int st = rows_block_cfg(C, block, ppb, (int64_t)B * T1 * F1, grid);
+  if (st) return st;
+  conv1_wgrad_kernel<<<grid, block, sizeof(float) * 9 * C, static_cast<cudaStream_t>(stream)>>>(x, static_cast<const __nv_bfloat16*>(dy), dw, B, T, F, T1,
+                                                                                                 F1, C, ppb);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_im2col_3x3s2(const void* a, void* col, int32_t B, int32_t T1, int32_t F1, int32_t C, tfasr_stream_t stream) {
+  if (!a || !col || B < 0 || T1 < 1 || F1 < 1 || C < 8 || (C & 7)) return TFASR_INVALID_VALUE;
+  if (B == 0) return TFASR_OK;
+  const int T2 = (T1 + 1) / 2, F2 = (F1 + 1) / 2;
+  const int64_t total = (int64_t)B * T2 * F2 * 9 * (C >> 3);
+  unsigned grid = (unsigned)min64(ceil_div(total, 256), kNumSMs * 32);
+  im2col_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(col), B, T1, F1, T2,
+                                                                      F2, C);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_col2im_3x3s2(const void* dcol, void* da, int32_t B, int32_t T1, int32_t F1, int32_t C, tfasr_stream_t stream) {
+  if (!dcol || !da || B < 0 || T1 < 1 || F1 < 1 || C < 8 || (C & 7)) return TFASR_INVALID_VALUE;
+  if (B == 0) return TFASR_OK;
+  const int T2 = (T1 + 1) / 2, F2 = (F1 + 1) / 2;
+  const int64_t total = (int64_t)B * T1 * F1 * (C >> 3);
+  unsigned grid = (unsigned)min64(ceil_div(total, 256), kNumSMs * 32);
+  col2im_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dcol), static_cast<__nv_bfloat16*>(da), B, T1, F1,
+                                                                      T2, F2, C);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_bn_stats(const void* x, float* sums, int64_t R, int32_t C, tfasr_stream_t stream) {
+  if (!x || !sums || R < 0) return TFASR_INVALID_VALUE;
+  if (R == 0) return TFASR_OK;
+  dim3 block;
+  int rpb;
+  unsigned grid;
+  int st = rows_block_cfg(C, block, rpb, R, grid);
+  if (st) return st;
+  bn_stats_kernel<<<grid, block, sizeof(float) * 2 * C, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), sums, R, C, rpb);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_bn_apply(const void* x, const float* scale, const float* shift, void* y, int64_t R, int32_t C, int32_t act,
+                              tfasr_stream_t stream) {
+  if (!x || !scale || !shift || !y || R < 0 || C < 2 || (C & 1)) return TFASR_INVALID_VALUE;
+  if (R == 0) return TFASR_OK;
+  const int64_t total = R * (C >> 1);
+  unsigned grid = (unsigned)min64(ceil_div(total, 256), kNumSMs * 32);
+  bn_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), scale, shift, static_cast<__nv_bfloat16*>(y), R,
+                                                                        C, act);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_bn_bwd_stats(const void* dy, const void* x, const float* scale, const float* shift, const float* mean, const float* rstd,
+                                  float* sums, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream) {
+  if (!dy || !x || !scale || !shift || !mean || !rstd || !sums || R < 0) return TFASR_INVALID_VALUE;
+  if (R == 0) return TFASR_OK;
+  dim3 block;
+  int rpb;
+  unsigned grid;
+  int st = rows_block_cfg(C, block, rpb, R, grid);
+  if (st) return st;
+  bn_bwd_stats_kernel<<<grid, block, sizeof(float) * 2 * C, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), scale, shift, mean, rstd, sums, R, C, act, rpb);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* scale, const float* shift, const float* mean, const float* rstd,
+                                  const float* sums, float count, void* dx, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream) {
+  if (!dy || !x || !scale || !shift || !mean || !rstd || !sums || !dx || R < 0 || C < 2 || (C & 1)) return TFASR_INVALID_VALUE;
+  if (R == 0) return TFASR_OK;
+  const int64_t total = R * (C >> 1);
+  unsigned grid = (unsigned)min64(ceil_div(total, 256), kNumSMs * 32);
+  bn_bwd_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), scale,
+                                                                            shift, mean, rstd, sums, count, static_cast<__nv_bfloat16*>(dx), R, C, act);
+  count_launch();
+  return check_launch();
+}

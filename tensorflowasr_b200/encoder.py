@@ -123,8 +123,18 @@ class Conv2dSubsampling(_Params):
             nfeat = conv_output_length(nfeat, self.kernels[i][1], self.paddings[i], self.strides[i][1])
         return nfeat * self.filters[-1]
 
+    def _fusable(self):
+        return (len(self.filters) == 2 and self.filters[0] == self.filters[1] and self.filters[0] % 8 == 0 and self.norms == ["batch", "batch"]
+                and self.activations == ["swish", "swish"] and self.paddings == ["causal", "causal"]
+                and self.kernels == [(3, 3), (3, 3)] and self.strides == [(2, 2), (2, 2)])
+
     def forward(self, inputs, training=False):
         x, length = inputs  # x [B, T, F, C]
+        if ops.fused_active(x) and x.shape[-1] == 1 and self._fusable():
+            y = fused.conv2d_subsampling(x, self, training)
+            for i in range(2):
+                length = conv_output_length(length, 3, "causal", 2)
+            return y, length
         for i in range(len(self.filters)):
             x = ops.conv2d_block(
                 x, self[f"conv_{i}.kernel"], self[f"conv_{i}.bias"], stride=self.strides[i], padding=self.paddings[i],

@@ -228,3 +228,113 @@ class _TransducerHeadFn(torch.autograd.Function):
 def transducer_head(e, p, pack, labels, logit_length, label_length):
     """e [B,T,J], p [B,U1,J] bf16 -> per-utterance RNN-T costs [B] f32."""
     return _TransducerHeadFn.apply(e, p, pack, labels, logit_length, label_length)
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm (+ swish) helpers
+BN_EPS = 1e-3
+BN_MOMENTUM = 0.99
+
+
+def _world():
+    d = torch.distributed
+    return d.get_world_size() if d.is_available() and d.is_initialized() else 1
+
+
+def bn_train_fwd(x2d, gamma, beta, moving_mean, moving_var, act=1):
+    """Training-mode keras BatchNormalization(synchronized=True) (+ swish) on x2d [R, C] bf16.
+    Returns (y, saved) where saved = (scale, shift, mean, rstd, count) for the backward.  Updates the moving statistics."""
+    R, C = x2d.shape
+    sums = kernels.bn_stats(x2d)
+    world = _world()
+    if world > 1:
+        torch.distributed.all_reduce(sums)  # C2: sync-BN statistics
+    count = float(R * world)
+    mean = sums[0] / count
+    var = (sums[1] / count - mean * mean).clamp_min_(0.0)
+    rstd = torch.rsqrt(var + BN_EPS)
+    scale = gamma.detach().float() * rstd
+    shift = beta.detach().float() - mean * scale
+    y = kernels.bn_apply(x2d, scale, shift, act)
+    with torch.no_grad():
+        moving_mean.mul_(BN_MOMENTUM).add_(mean, alpha=1.0 - BN_MOMENTUM)
+        moving_var.mul_(BN_MOMENTUM).add_(var, alpha=1.0 - BN_MOMENTUM)
+    return y, (scale, shift, mean, rstd, count)
+
+
+def bn_train_bwd(dy2d, x2d, saved, gamma, beta, act=1):
+    """-> dx2d; accumulates dgamma / dbeta into the parameters' .grad."""
+    scale, shift, mean, rstd, count = saved
+    sums = kernels.bn_bwd_stats(dy2d, x2d, scale, shift, mean, rstd, act)
+    _grad(gamma).add_(sums[1])  # local contribution; the gradient all-reduce sums over replicas
+    _grad(beta).add_(sums[0])
+    if _world() > 1:
+        sums = sums.clone()
+        torch.distributed.all_reduce(sums)
+    return kernels.bn_bwd_apply(dy2d, x2d, scale, shift, mean, rstd, sums, count, act)
+
+
+def bn_eval(x2d, gamma, beta, moving_mean, moving_var, act=1):
+    scale = gamma.detach().float() * torch.rsqrt(moving_var.float() + BN_EPS)
+    shift = beta.detach().float() - moving_mean.float() * scale
+    return kernels.bn_apply(x2d, scale, shift, act)
+
+
+# ------------------------------------------------------------------------------------------------ Conv2dSubsampling
+class _SubsamplingFn(torch.autograd.Function):
+    """Conv2dSubsampling with filters [C, C], 3x3 kernels, stride 2, causal padding, batch norms, swish (the Conformer-S
+    configuration, small.yml.j2:26-33; subsampling.py:218-230):
+        conv1 (direct, Cin = 1) -> BN + swish -> im2col -> tcgen05 GEMM (conv2) -> BN + swish -> merge (F, C)
+    Conv biases sit in front of a batch norm, so their gradients are identically zero and are not computed."""
+
+    @staticmethod
+    def forward(ctx, feats, sub, training):
+        B, T, F = feats.shape[0], feats.shape[1], feats.shape[2]
+        x = feats.reshape(B, T, F).float().contiguous()
+        w1, b1 = sub["conv_0.kernel"], sub["conv_0.bias"]
+        w2, b2 = sub["conv_1.kernel"], sub["conv_1.bias"]
+        C = w1.shape[-1]
+        y1 = kernels.conv1_fwd(x, w1.detach().float().contiguous(), b1.detach().float())
+        T1, F1 = y1.shape[1], y1.shape[2]
+        y1f = y1.view(-1, C)
+        bn0 = (sub["bn_0.gamma"], sub["bn_0.beta"], sub["bn_0.moving_mean"], sub["bn_0.moving_variance"])
+        bn1 = (sub["bn_1.gamma"], sub["bn_1.beta"], sub["bn_1.moving_mean"], sub["bn_1.moving_variance"])
+        if training:
+            a1, s0 = bn_train_fwd(y1f, *bn0)
+        else:
+            a1, s0 = bn_eval(y1f, *bn0), None
+        a1 = a1.view(B, T1, F1, C)
+        col = kernels.im2col(a1)
+        pack = WeightPack(w2.reshape(9 * C, C), b2)
+        pack.param = w2
+        y2 = kernels.gemm(col, pack.wt, bias=b2.detach().float())
+        del col
+        if training:
+            a2, s1 = bn_train_fwd(y2, *bn1)
+        else:
+            a2, s1 = bn_eval(y2, *bn1), None
+        T2, F2 = (T1 + 1) // 2, (F1 + 1) // 2
+        ctx.save_for_backward(x, y1, a1, y2)
+        ctx.misc = (sub, pack, s0, s1, (B, T, F, T1, F1, T2, F2, C), training)
+        return a2.view(B, T2, F2 * C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y1, a1, y2 = ctx.saved_tensors
+        sub, pack, s0, s1, (B, T, F, T1, F1, T2, F2, C), training = ctx.misc
+        if not training:
+            raise RuntimeError("Conv2dSubsampling fused backward needs training-mode batch statistics")
+        dy2 = bn_train_bwd(dout.contiguous().view(-1, C), y2, s1, sub["bn_1.gamma"], sub["bn_1.beta"])
+        col = kernels.im2col(a1)  # recomputed: cheaper than keeping 9x the activation alive
+        kernels.gemm(col, dy2, mn_major=True, out=_grad(pack.param).view(9 * C, C), accumulate=True, k_splits=32)
+        del col
+        dcol = kernels.gemm(dy2, pack.w)  # [M2, 9C]
+        da1 = kernels.col2im(dcol, (B, T1, F1, C))
+        del dcol
+        dy1 = bn_train_bwd(da1.view(-1, C), y1.view(-1, C), s0, sub["bn_0.gamma"], sub["bn_0.beta"])
+        kernels.conv1_wgrad(x, dy1, _grad(sub["conv_0.kernel"]))
+        return None, None, None
+
+
+def conv2d_subsampling(feats, sub, training):
+    """feats [B,T,F,1] -> [B, ceil(ceil(T/2)/2), F'' * C] bf16."""
+    return _SubsamplingFn.apply(feats, sub, training)

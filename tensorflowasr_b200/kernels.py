@@ -123,3 +123,77 @@ def joint_reduce_bwd(dz):
     dp = torch.zeros((B, U1, J), dtype=torch.float32, device=dz.device)
     _lib.check(lib.tfasr_joint_reduce_bwd(_lib.ptr(dz), _lib.ptr(de), _lib.ptr(dp), B, T, U1, J, _lib.stream_ptr(dz.device)), "tfasr_joint_reduce_bwd")
     return de, dp
+
+
+# ------------------------------------------------------------------------------------------------ conv subsampling / batch norm
+def _st(t):
+    return _lib.stream_ptr(t.device)
+
+
+def conv1_fwd(x, w, bias):
+    """x [B,T,F] f32, w [3,3,1,C] f32 -> y [B,T1,F1,C] bf16 (3x3, stride 2, causal)."""
+    lib = _lib.load()
+    B, T, F = x.shape
+    C = w.shape[-1]
+    y = torch.empty((B, (T + 1) // 2, (F + 1) // 2, C), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.tfasr_conv1_3x3s2_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), B, T, F, C, _st(x)), "tfasr_conv1_3x3s2_fwd")
+    return y
+
+
+def conv1_wgrad(x, dy, dw):
+    lib = _lib.load()
+    B, T, F = x.shape
+    C = dy.shape[-1]
+    _lib.check(lib.tfasr_conv1_3x3s2_wgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), B, T, F, C, _st(x)), "tfasr_conv1_3x3s2_wgrad")
+
+
+def im2col(a):
+    """a [B,T1,F1,C] bf16 -> col [B*T2*F2, 9C]."""
+    lib = _lib.load()
+    B, T1, F1, C = a.shape
+    T2, F2 = (T1 + 1) // 2, (F1 + 1) // 2
+    col = torch.empty((B * T2 * F2, 9 * C), dtype=torch.bfloat16, device=a.device)
+    _lib.check(lib.tfasr_im2col_3x3s2(_lib.ptr(a), _lib.ptr(col), B, T1, F1, C, _st(a)), "tfasr_im2col_3x3s2")
+    return col
+
+
+def col2im(dcol, shape):
+    lib = _lib.load()
+    B, T1, F1, C = shape
+    da = torch.empty(shape, dtype=torch.bfloat16, device=dcol.device)
+    _lib.check(lib.tfasr_col2im_3x3s2(_lib.ptr(dcol), _lib.ptr(da), B, T1, F1, C, _st(dcol)), "tfasr_col2im_3x3s2")
+    return da
+
+
+def bn_stats(x2d):
+    lib = _lib.load()
+    R, C = x2d.shape
+    sums = torch.zeros((2, C), dtype=torch.float32, device=x2d.device)
+    _lib.check(lib.tfasr_bn_stats(_lib.ptr(x2d), _lib.ptr(sums), R, C, _st(x2d)), "tfasr_bn_stats")
+    return sums
+
+
+def bn_apply(x2d, scale, shift, act=1):
+    lib = _lib.load()
+    R, C = x2d.shape
+    y = torch.empty_like(x2d)
+    _lib.check(lib.tfasr_bn_apply(_lib.ptr(x2d), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(y), R, C, int(act), _st(x2d)), "tfasr_bn_apply")
+    return y
+
+
+def bn_bwd_stats(dy, x2d, scale, shift, mean, rstd, act=1):
+    lib = _lib.load()
+    R, C = x2d.shape
+    sums = torch.zeros((2, C), dtype=torch.float32, device=x2d.device)
+    _lib.check(lib.tfasr_bn_bwd_stats(_lib.ptr(dy), _lib.ptr(x2d), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(sums),
+                                      R, C, int(act), _st(x2d)), "tfasr_bn_bwd_stats")
+    return sums
+
+
+def bn_bwd_apply(dy, x2d, scale, shift, mean, rstd, sums, count, act=1):
+    lib = _lib.load()
+    R, C = x2d.shape
+    dx = torch.empty_like(x2d)
+    _lib.check(lib.tfasr_bn_bwd_apply(_lib.ptr(dy), _lib.ptr(x2d), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(sums),
+                                      float(count), _lib.ptr(dx), R, C, int(act), _st(x2d)), "tfasr_bn_bwd_apply")
+    return dx

@@ -186,3 +186,59 @@ def test_transducer_head_kernels_vs_torch():
     _close(p1.grad, p2.grad, 3e-2)
     _close(W.grad, W2.grad, 3e-2)
     _close(bias.grad, b2.grad, 3e-2)
+
+
+def test_subsampling_kernels_vs_torch():
+    """conv1 direct / im2col / col2im / BN+swish fwd+bwd vs PyTorch fp32 ops."""
+    import torch.nn.functional as F
+
+    from tensorflowasr_b200 import kernels
+
+    torch.manual_seed(0)
+    B, T, Fq, C = 2, 37, 21, 16
+    x = torch.randn(B, T, Fq, device="cuda")
+    w = torch.randn(3, 3, 1, C, device="cuda") * 0.3
+    bias = torch.randn(C, device="cuda") * 0.1
+    y = kernels.conv1_fwd(x, w, bias)
+    ref = F.conv2d(F.pad(x[:, None], (2, 0, 2, 0)), w.permute(3, 2, 0, 1), bias, stride=2).permute(0, 2, 3, 1)
+    _close(y, ref)
+    dy = torch.randn_like(ref).to(torch.bfloat16)
+    dw = torch.zeros(3, 3, 1, C, device="cuda")
+    kernels.conv1_wgrad(x, dy, dw)
+    wr = w.clone().requires_grad_(True)
+    F.conv2d(F.pad(x[:, None], (2, 0, 2, 0)), wr.permute(3, 2, 0, 1), bias, stride=2).permute(0, 2, 3, 1).backward(dy.float())
+    _close(dw, wr.grad, 2e-3)
+    # im2col + GEMM == conv2d ; col2im == its data gradient
+    a = torch.randn(B, 19, 11, C, device="cuda").to(torch.bfloat16)
+    w2 = (torch.randn(3, 3, C, C, device="cuda") * 0.1)
+    col = kernels.im2col(a)
+    y2 = col.float() @ w2.reshape(9 * C, C).to(torch.bfloat16).float()
+    ar = a.float().requires_grad_(True)
+    ref2 = F.conv2d(F.pad(ar.permute(0, 3, 1, 2), (2, 0, 2, 0)), w2.to(torch.bfloat16).float().permute(3, 2, 0, 1), None, stride=2).permute(0, 2, 3, 1)
+    _close(y2.view_as(ref2), ref2, 2e-3)
+    dy2 = torch.randn_like(ref2).to(torch.bfloat16)
+    ref2.backward(dy2.float())
+    dcol = (dy2.float().view(-1, C) @ w2.reshape(9 * C, C).to(torch.bfloat16).float().t()).to(torch.bfloat16)
+    da = kernels.col2im(dcol, tuple(a.shape))
+    _close(da, ar.grad, 2e-2)
+    # BN + swish training fwd / bwd
+    from tensorflowasr_b200 import fused
+
+    R, C2 = 5000, 144
+    xb = (torch.randn(R, C2, device="cuda") * 2 + 0.3).to(torch.bfloat16)
+    gamma = torch.nn.Parameter(torch.randn(C2, device="cuda") * 0.2 + 1)
+    beta = torch.nn.Parameter(torch.randn(C2, device="cuda") * 0.1)
+    mm, mv = torch.zeros(C2, device="cuda"), torch.ones(C2, device="cuda")
+    yb, saved = fused.bn_train_fwd(xb, gamma, beta, mm, mv)
+    xr = xb.float().requires_grad_(True)
+    g2, b2 = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    mean, var = xr.mean(0), xr.var(0, unbiased=False)
+    yr = F.silu((xr - mean) * torch.rsqrt(var + 1e-3) * g2 + b2)
+    _close(yb, yr)
+    _close(mm, 0.01 * mean.detach(), 1e-2)
+    dyb = torch.randn(R, C2, device="cuda").to(torch.bfloat16)
+    yr.backward(dyb.float())
+    dxb = fused.bn_train_bwd(dyb, xb, saved, gamma, beta)
+    _close(dxb, xr.grad, 2e-2)
+    _close(gamma.grad, g2.grad, 5e-3)
+    _close(beta.grad, b2.grad, 5e-3)
