@@ -178,6 +178,21 @@ int tfasr_joint_tanh_fwd(const void* e, const void* p, void* h, int32_t B, int32
 int tfasr_joint_reduce_bwd(const void* dz, float* de, float* dp, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Relative-position multi-head self-attention core (multihead_attention.py:543-582; rel_left_shift :27-64 as index arithmetic;
+ * masked softmax general.py:30-41; streaming mask :104-143 when chunk > 0).
+ *   qkv  [B*T, ld_qkv] bf16: q at column n*H, k at N*H + n*H, v at 2*N*H + n*H      pos [B*(2T-1), N*H] bf16 (projected relpe)
+ *   ubias / vbias [N, H] f32 (content / positional attention bias)                   length [B] i32 or NULL (query-side mask)
+ *   fwd:  ctx [B*T, N*H] bf16, probs [B, N, T, T] bf16 (kept for backward)
+ *   bwd:  dqkv [B*T, ld_qkv] bf16, dpos [B*(2T-1), N*H] bf16 (written), du / dvb [N, H] f32 (accumulated); ds_ws [B,N,T,T] bf16 scratch
+ * ---------------------------------------------------------------------------------------------- */
+int tfasr_rel_attention_fwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias, const int32_t* length,
+                            int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, void* ctx, void* probs,
+                            tfasr_stream_t stream);
+int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias, const int32_t* length,
+                            int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, const void* probs, const void* dctx,
+                            void* ds_ws, void* dqkv, void* dpos, float* du, float* dvb, tfasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Conv2dSubsampling pieces and BatchNorm (+ swish), channels-last bf16 (subsampling.py:163-230, convolution.py:25-37,132-144;
  * keras BatchNormalization eps 1e-3 with batch statistics over all leading axes, as in conformer.py:326-333 / subsampling.py:199-206).
  *   conv1_3x3s2_fwd / wgrad : first conv (Cin = 1): x [B,T,F] f32, w [3,3,1,C] f32 -> y [B,ceil(T/2),ceil(F/2),C] bf16; causal pad

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) scale_mask_colsum_kernel(const __nv_bfloa
         a += __low2float(va);
         b += __high2float(va);
       }
-      *reinterpret_cast<__nv_bfloat162*>(out + idx) = __floats2bfloat162_rn(a, b);
+      if (out) *reinterpret_cast<__nv_bfloat162*>(out + idx) = __floats2bfloat162_rn(a, b);
       s0 += a;
       s1 += b;
     }
@@ -238,7 +238,7 @@ extern "C" int tfasr_layernorm_bwd(const void* dy, const void* x, int32_t x_is_f
 
 extern "C" int tfasr_scale_mask_colsum(const void* in, const void* add, void* out, float* colsum, int32_t M, int32_t N, float scale, float dropout_p,
                                        const unsigned long long* seed_ptr, unsigned long long salt, tfasr_stream_t stream) {
-  if (!in || !out || M < 0 || N < 2 || (N & 1)) return TFASR_INVALID_VALUE;
+  if (!in || (!out && !colsum) || M < 0 || N < 2 || (N & 1)) return TFASR_INVALID_VALUE;  // out == NULL: column sums only
   if (M == 0) return TFASR_OK;
   const int rows_per_block = 32;
   scale_mask_colsum_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(

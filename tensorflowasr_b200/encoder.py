@@ -272,6 +272,7 @@ class ConformerEncoder(_Params):
                 for d in ("dense_1", "dense_2"):
                     n = f"block_{b}.{ff}.{d}"
                     packs[n] = fused.WeightPack(self[n + ".kernel"], self[n + ".bias"])
+            packs[f"block_{b}.mhsa_module"] = fused.MhsaPack(self, f"block_{b}.mhsa_module")
         self._packs = packs
 
     def _salt(self, pre, k):
@@ -298,6 +299,14 @@ class ConformerEncoder(_Params):
         # MHSAModule.call, conformer.py:209-239 -> MultiHeadRelativeAttention.call, multihead_attention.py:584-667
         D, N, H = self.dmodel, self.num_heads, self.head_size
         m = pre + ".mhsa"
+        if ops.fused_active(x):
+            B, T, _ = x.shape
+            p = self.dropout if training else 0.0
+            ln = torch.as_tensor(length, device=x.device).to(torch.int32).contiguous()
+            y = fused.mhsa_module(x.reshape(B * T, D).to(torch.bfloat16), relpe.reshape(-1, D).to(torch.bfloat16).contiguous(),
+                                  self[pre + ".ln.gamma"], self[pre + ".ln.beta"], self._packs[pre], ln, B, T, self.mhsam_residual_factor, p,
+                                  self._salt(pre, 0), fused.STATE.seed_tensor(x.device), self.chunk_size, self.history_size)
+            return y.view(B, T, D)
         y = ops.layer_norm(x, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
         q = ops.linear(y, self[m + ".query.kernel"].reshape(D, N * H), self[m + ".query.bias"].reshape(N * H))
         k = ops.linear(y, self[m + ".key.kernel"].reshape(D, N * H), self[m + ".key.bias"].reshape(N * H))

@@ -287,10 +287,12 @@ class _SubsamplingFn(torch.autograd.Function):
     Conv biases sit in front of a batch norm, so their gradients are identically zero and are not computed."""
 
     @staticmethod
-    def forward(ctx, feats, sub, training):
+    def forward(ctx, feats, w1, sub, training):
+        # w1 (conv_0.kernel) is an explicit autograd input: the features carry no gradient, and a Function with no
+        # differentiable input would never have its backward called.
         B, T, F = feats.shape[0], feats.shape[1], feats.shape[2]
         x = feats.reshape(B, T, F).float().contiguous()
-        w1, b1 = sub["conv_0.kernel"], sub["conv_0.bias"]
+        b1 = sub["conv_0.bias"]
         w2, b2 = sub["conv_1.kernel"], sub["conv_1.bias"]
         C = w1.shape[-1]
         y1 = kernels.conv1_fwd(x, w1.detach().float().contiguous(), b1.detach().float())
@@ -331,10 +333,86 @@ class _SubsamplingFn(torch.autograd.Function):
         da1 = kernels.col2im(dcol, (B, T1, F1, C))
         del dcol
         dy1 = bn_train_bwd(da1.view(-1, C), y1.view(-1, C), s0, sub["bn_0.gamma"], sub["bn_0.beta"])
-        kernels.conv1_wgrad(x, dy1, _grad(sub["conv_0.kernel"]))
-        return None, None, None
+        dw1 = torch.zeros_like(sub["conv_0.kernel"], dtype=torch.float32)
+        kernels.conv1_wgrad(x, dy1, dw1)
+        return None, dw1, None, None
 
 
 def conv2d_subsampling(feats, sub, training):
     """feats [B,T,F,1] -> [B, ceil(ceil(T/2)/2), F'' * C] bf16."""
-    return _SubsamplingFn.apply(feats, sub, training)
+    return _SubsamplingFn.apply(feats, sub["conv_0.kernel"], sub, training)
+
+
+# ------------------------------------------------------------------------------------------------ MHSAModule
+class MhsaPack:
+    """Operand copies for one MHSAModule: fused Q/K/V projection [D, 3NH], position projection [D, NH], output projection [NH, D]."""
+
+    def __init__(self, enc, pre):
+        m = pre + ".mhsa"
+        D, N, H = enc.dmodel, enc.num_heads, enc.head_size
+        self.params = {k: (enc[f"{m}.{k}.kernel"], enc[f"{m}.{k}.bias"]) for k in ("query", "key", "value", "encoding", "attention_output")}
+        wqkv = torch.cat([self.params[k][0].detach().reshape(D, N * H) for k in ("query", "key", "value")], dim=1)
+        self.bqkv = torch.cat([self.params[k][1].detach().reshape(N * H) for k in ("query", "key", "value")]).float().contiguous()
+        self.wqkv = wqkv.to(torch.bfloat16).contiguous()  # [D, 3NH]   (dgrad operand)
+        self.wqkv_t = wqkv.t().to(torch.bfloat16).contiguous()  # [3NH, D]   (forward operand)
+        wpos = self.params["encoding"][0].detach().reshape(D, N * H)
+        self.wpos_t = wpos.t().to(torch.bfloat16).contiguous()
+        self.bpos = self.params["encoding"][1].detach().reshape(N * H).float().contiguous()
+        wo = self.params["attention_output"][0].detach().reshape(N * H, D)
+        self.wo = wo.to(torch.bfloat16).contiguous()  # [NH, D]
+        self.wo_t = wo.t().to(torch.bfloat16).contiguous()  # [D, NH]
+        self.bo = self.params["attention_output"][1]
+        self.u, self.v = enc["content_attention_bias"], enc["positional_attention_bias"]
+        self.D, self.N, self.H = D, N, H
+
+
+class _MHSAModuleFn(torch.autograd.Function):
+    """x + factor * Drop(Wo . RelAttention(Wq|Wk|Wv . LN(x), Wpos . relpe) + bo)     (conformer.py:209-239, multihead_attention.py:584-667)"""
+
+    @staticmethod
+    def forward(ctx, x, relpe2d, ln_g, ln_b, pk: MhsaPack, length, B, T, factor, drop_p, salt, seed, chunk, history):
+        N, H = pk.N, pk.H
+        a, mean, rstd = kernels.layernorm_fwd(x, ln_g, ln_b, LN_EPS)
+        qkv = kernels.gemm(a, pk.wqkv_t, bias=pk.bqkv)
+        pos = kernels.gemm(relpe2d, pk.wpos_t, bias=pk.bpos)
+        u32, v32 = pk.u.detach().float().contiguous(), pk.v.detach().float().contiguous()
+        cv, probs = kernels.rel_attention_fwd(qkv, pos, u32, v32, length, B, T, N, H, chunk, history)
+        out = kernels.gemm(cv, pk.wo_t, bias=pk.bo.detach().float(), residual=x, residual_scale=factor, dropout_p=drop_p, dropout_seed=seed,
+                           dropout_salt=salt)
+        ctx.save_for_backward(x, mean, rstd, a, qkv, pos, cv, probs, relpe2d, u32, v32)
+        ctx.misc = (ln_g, ln_b, pk, length, B, T, factor, drop_p, salt, seed, chunk, history)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mean, rstd, a, qkv, pos, cv, probs, relpe2d, u32, v32 = ctx.saved_tensors
+        ln_g, ln_b, pk, length, B, T, factor, drop_p, salt, seed, chunk, history = ctx.misc
+        N, H, D = pk.N, pk.H, pk.D
+        NH = N * H
+        dout = dout.contiguous()
+        M = x.shape[0]
+        ks = _splits(M)
+        wo_p, bo_p = pk.params["attention_output"]
+        dy = kernels.scale_mask_colsum(dout, scale=factor, dropout_p=drop_p, seed=seed, salt=salt, colsum=_grad(bo_p))
+        kernels.gemm(cv, dy, mn_major=True, out=_grad(wo_p).view(NH, D), accumulate=True, k_splits=ks)
+        dctx = kernels.gemm(dy, pk.wo)  # [M, NH]
+        dqkv, dpos = kernels.rel_attention_bwd(qkv, pos, u32, v32, length, B, T, N, H, probs, dctx, _grad(pk.u), _grad(pk.v), chunk, history)
+        # fused QKV projection: one weight-gradient GEMM into a scratch [D, 3NH], then slices to the three parameters
+        dw = torch.zeros((D, 3 * NH), dtype=torch.float32, device=x.device)
+        kernels.gemm(a, dqkv, mn_major=True, out=dw, accumulate=True, k_splits=ks)
+        db = torch.zeros(3 * NH, dtype=torch.float32, device=x.device)
+        kernels.colsum(dqkv, db)
+        for i, k in enumerate(("query", "key", "value")):
+            wp, bp = pk.params[k]
+            _grad(wp).view(D, NH).add_(dw[:, i * NH:(i + 1) * NH])
+            _grad(bp).view(NH).add_(db[i * NH:(i + 1) * NH])
+        wpos_p, bpos_p = pk.params["encoding"]
+        kernels.gemm(relpe2d, dpos, mn_major=True, out=_grad(wpos_p).view(D, NH), accumulate=True, k_splits=_splits(relpe2d.shape[0]))
+        kernels.colsum(dpos, _grad(bpos_p).view(NH))
+        da = kernels.gemm(dqkv, pk.wqkv)
+        dx = kernels.layernorm_bwd(da, x, mean, rstd, ln_g, _grad(ln_g), _grad(ln_b), dres=dout)
+        return (dx,) + (None,) * 13
+
+
+def mhsa_module(x, relpe2d, ln_g, ln_b, pk, length, B, T, factor, drop_p, salt, seed, chunk=None, history=None):
+    return _MHSAModuleFn.apply(x, relpe2d, ln_g, ln_b, pk, length, B, T, float(factor), float(drop_p), int(salt), seed, chunk, history)

@@ -85,11 +85,11 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
     return dx
 
 
-def scale_mask_colsum(x, scale=1.0, dropout_p=0.0, seed=None, salt=0, colsum=None, add=None):
+def scale_mask_colsum(x, scale=1.0, dropout_p=0.0, seed=None, salt=0, colsum=None, add=None, write_out=True):
     """out = scale * dropout_mask * x (+ add), bf16 [M, N]; colsum (f32 [N]) += column sums of out."""
     lib = _lib.load()
     M, N = x.shape
-    out = torch.empty_like(x)
+    out = torch.empty_like(x) if write_out else None
     _lib.check(lib.tfasr_scale_mask_colsum(_lib.ptr(x), _lib.ptr(add), _lib.ptr(out), _lib.ptr(colsum), M, N, float(scale), float(dropout_p),
                                            seed.data_ptr() if seed is not None else None, int(salt) & 0xFFFFFFFFFFFFFFFF,
                                            _lib.stream_ptr(x.device)), "tfasr_scale_mask_colsum")
@@ -197,3 +197,34 @@ def bn_bwd_apply(dy, x2d, scale, shift, mean, rstd, sums, count, act=1):
     _lib.check(lib.tfasr_bn_bwd_apply(_lib.ptr(dy), _lib.ptr(x2d), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(sums),
                                       float(count), _lib.ptr(dx), R, C, int(act), _st(x2d)), "tfasr_bn_bwd_apply")
     return dx
+
+
+def colsum(x2d, out):
+    """out (f32 [N]) += column sums of x2d [M, N] bf16."""
+    scale_mask_colsum(x2d, colsum=out, write_out=False)
+
+
+def rel_attention_fwd(qkv, pos, ubias, vbias, length, B, T, N, H, chunk=None, history=None):
+    """-> (ctx [B*T, N*H] bf16, probs [B,N,T,T] bf16)."""
+    lib = _lib.load()
+    ctx = torch.empty((B * T, N * H), dtype=torch.bfloat16, device=qkv.device)
+    probs = torch.empty((B, N, T, T), dtype=torch.bfloat16, device=qkv.device)
+    ch = int(chunk) if (chunk is not None and history is not None) else 0
+    hi = int(history) if (chunk is not None and history is not None) else 0
+    _lib.check(lib.tfasr_rel_attention_fwd(_lib.ptr(qkv), qkv.stride(0), _lib.ptr(pos), _lib.ptr(ubias), _lib.ptr(vbias), _lib.ptr(length), B, T, N, H,
+                                           ch, hi, _lib.ptr(ctx), _lib.ptr(probs), _st(qkv)), "tfasr_rel_attention_fwd")
+    return ctx, probs
+
+
+def rel_attention_bwd(qkv, pos, ubias, vbias, length, B, T, N, H, probs, dctx, du, dvb, chunk=None, history=None):
+    """-> (dqkv like qkv, dpos like pos); du / dvb (f32 [N,H]) accumulated."""
+    lib = _lib.load()
+    dqkv = torch.empty_like(qkv)
+    dpos = torch.empty_like(pos)
+    ds = torch.empty_like(probs)
+    ch = int(chunk) if (chunk is not None and history is not None) else 0
+    hi = int(history) if (chunk is not None and history is not None) else 0
+    _lib.check(lib.tfasr_rel_attention_bwd(_lib.ptr(qkv), qkv.stride(0), _lib.ptr(pos), _lib.ptr(ubias), _lib.ptr(vbias), _lib.ptr(length), B, T, N, H,
+                                           ch, hi, _lib.ptr(probs), _lib.ptr(dctx), _lib.ptr(ds), _lib.ptr(dqkv), _lib.ptr(dpos), _lib.ptr(du),
+                                           _lib.ptr(dvb), _st(qkv)), "tfasr_rel_attention_bwd")
+    return dqkv, dpos
