@@ -300,12 +300,21 @@ class ConformerEncoder(_Params):
         D, N, H = self.dmodel, self.num_heads, self.head_size
         m = pre + ".mhsa"
         if ops.fused_active(x):
+            # LN, the fused Q|K|V projection, the position projection and the output projection (+ dropout + residual) run on the
+            # tcgen05 GEMM / fused row kernels; the attention core itself is still the LIBRARY path (ops.rel_attention).
             B, T, _ = x.shape
+            NH = N * H
             p = self.dropout if training else 0.0
-            ln = torch.as_tensor(length, device=x.device).to(torch.int32).contiguous()
-            y = fused.mhsa_module(x.reshape(B * T, D).to(torch.bfloat16), relpe.reshape(-1, D).to(torch.bfloat16).contiguous(),
-                                  self[pre + ".ln.gamma"], self[pre + ".ln.beta"], self._packs[pre], ln, B, T, self.mhsam_residual_factor, p,
-                                  self._salt(pre, 0), fused.STATE.seed_tensor(x.device), self.chunk_size, self.history_size)
+            pk = self._packs[pre]
+            seed = fused.STATE.seed_tensor(x.device)
+            x2 = x.reshape(B * T, D).to(torch.bfloat16)
+            a = fused.layer_norm(x2, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
+            qkv = fused.linear(a, pk.qkv).view(B, T, 3 * NH)
+            pos = fused.linear(relpe.reshape(-1, D).to(torch.bfloat16).contiguous(), pk.pos).view(B, -1, NH)
+            ctx = ops.rel_attention(qkv[..., :NH], qkv[..., NH:2 * NH], qkv[..., 2 * NH:], pos, self["content_attention_bias"],
+                                    self["positional_attention_bias"], length, N, H, chunk_size=self.chunk_size, history_size=self.history_size)
+            y = fused.linear(ctx.reshape(B * T, NH).contiguous(), pk.out, residual=x2, factor=self.mhsam_residual_factor, drop_p=p,
+                             salt=self._salt(pre, 0), seed=seed)
             return y.view(B, T, D)
         y = ops.layer_norm(x, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
         q = ops.linear(y, self[m + ".query.kernel"].reshape(D, N * H), self[m + ".query.bias"].reshape(N * H))

@@ -44,7 +44,6 @@ class WeightPack:
     """bf16 operand copies of one Dense kernel W [K, N] (Keras layout): `wt` = W^T [N, K] for the forward GEMM (B operand,
     K-major), `w` = W [K, N] for the data-gradient GEMM (dX = dY . W^T: B operand [K, N] with contraction N)."""
 
-    __slots__ = ("w", "wt", "param", "bias")
 
     def __init__(self, param, bias=None, interleave_glu=False):
         w = param.detach()
@@ -59,6 +58,16 @@ class WeightPack:
         self.wt = w.t().to(torch.bfloat16).contiguous()
         self.param = param
         self.bias = bias
+
+    # hooks used by the generic Dense backward (overridden by packs that fan out to several parameters)
+    def bias_f32(self):
+        return None if self.bias is None else self.bias.detach().float().reshape(-1)
+
+    def bias_grad_target(self):
+        return None if self.bias is None else _grad(self.bias).view(-1)
+
+    def accumulate_wgrad(self, x, dz):
+        kernels.gemm(x, dz, mn_major=True, out=_grad(self.param).view(self.w.shape), accumulate=True, k_splits=_splits(x.shape[0]))
 
 
 def _splits(rows: int) -> int:
@@ -138,7 +147,7 @@ class _LinearFn(torch.autograd.Function):
         M = x.shape[0]
         N = pack.wt.shape[0]
         z = torch.empty((M, N), dtype=torch.bfloat16, device=x.device) if activation == "swish" else None
-        y = kernels.gemm(x, pack.wt, bias=pack.bias, activation=activation, aux=z, residual=residual, residual_scale=factor,
+        y = kernels.gemm(x, pack.wt, bias=pack.bias_f32(), activation=activation, aux=z, residual=residual, residual_scale=factor,
                          dropout_p=drop_p, dropout_seed=seed, dropout_salt=salt)
         ctx.save_for_backward(x, z)
         ctx.misc = (pack, activation, residual is not None, factor, drop_p, salt, seed)
@@ -155,11 +164,17 @@ class _LinearFn(torch.autograd.Function):
             d0 = kernels.scale_mask_colsum(dy, scale=scale, dropout_p=drop_p, seed=seed, salt=salt)
             sg = torch.sigmoid(z.float())
             dz = (d0.float() * (sg * (1 + z.float() * (1 - sg)))).to(torch.bfloat16)
-            _grad(pack.bias).add_(dz.float().sum(0))
+            if pack.bias_grad_target() is not None:
+                kernels.colsum(dz, pack.bias_grad_target())
+        elif scale == 1.0 and drop_p == 0.0:
+            dz = dy
+            if pack.bias_grad_target() is not None:
+                kernels.colsum(dz, pack.bias_grad_target())
         else:
-            dz = kernels.scale_mask_colsum(dy, scale=scale, dropout_p=drop_p, seed=seed, salt=salt,
-                                           colsum=_grad(pack.bias) if pack.bias is not None else None)
-        kernels.gemm(x, dz, mn_major=True, out=_grad(pack.param).view(pack.w.shape), accumulate=True, k_splits=_splits(x.shape[0]))
+            dz = kernels.scale_mask_colsum(dy, scale=scale, dropout_p=drop_p, seed=seed, salt=salt, colsum=pack.bias_grad_target())
+        pack.accumulate_wgrad(x, dz)
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, (dy if has_res else None), None, None, None, None
         dx = kernels.gemm(dz, pack.w)
         return dx, None, None, (dy if has_res else None), None, None, None, None
 
@@ -343,76 +358,46 @@ def conv2d_subsampling(feats, sub, training):
     return _SubsamplingFn.apply(feats, sub["conv_0.kernel"], sub, training)
 
 
-# ------------------------------------------------------------------------------------------------ MHSAModule
-class MhsaPack:
-    """Operand copies for one MHSAModule: fused Q/K/V projection [D, 3NH], position projection [D, NH], output projection [NH, D]."""
+# ------------------------------------------------------------------------------------------------ MHSAModule packs
+class QkvPack(WeightPack):
+    """Fused Q/K/V projection: one GEMM [D -> 3NH]; its weight / bias gradients fan out to the three Keras EinsumDense layers."""
 
     def __init__(self, enc, pre):
         m = pre + ".mhsa"
         D, N, H = enc.dmodel, enc.num_heads, enc.head_size
-        self.params = {k: (enc[f"{m}.{k}.kernel"], enc[f"{m}.{k}.bias"]) for k in ("query", "key", "value", "encoding", "attention_output")}
-        wqkv = torch.cat([self.params[k][0].detach().reshape(D, N * H) for k in ("query", "key", "value")], dim=1)
-        self.bqkv = torch.cat([self.params[k][1].detach().reshape(N * H) for k in ("query", "key", "value")]).float().contiguous()
-        self.wqkv = wqkv.to(torch.bfloat16).contiguous()  # [D, 3NH]   (dgrad operand)
-        self.wqkv_t = wqkv.t().to(torch.bfloat16).contiguous()  # [3NH, D]   (forward operand)
-        wpos = self.params["encoding"][0].detach().reshape(D, N * H)
-        self.wpos_t = wpos.t().to(torch.bfloat16).contiguous()
-        self.bpos = self.params["encoding"][1].detach().reshape(N * H).float().contiguous()
-        wo = self.params["attention_output"][0].detach().reshape(N * H, D)
-        self.wo = wo.to(torch.bfloat16).contiguous()  # [NH, D]
-        self.wo_t = wo.t().to(torch.bfloat16).contiguous()  # [D, NH]
-        self.bo = self.params["attention_output"][1]
-        self.u, self.v = enc["content_attention_bias"], enc["positional_attention_bias"]
-        self.D, self.N, self.H = D, N, H
+        self.parts = [(enc[f"{m}.{k}.kernel"], enc[f"{m}.{k}.bias"]) for k in ("query", "key", "value")]
+        w = torch.cat([k.detach().reshape(D, N * H) for k, _ in self.parts], dim=1)
+        self.w = w.to(torch.bfloat16).contiguous()
+        self.wt = w.t().to(torch.bfloat16).contiguous()
+        self._bias = torch.cat([b.detach().reshape(N * H) for _, b in self.parts]).float().contiguous()
+        self.param, self.bias = None, self._bias
+        self.D, self.NH = D, N * H
+        self._db = None
 
+    def bias_f32(self):
+        return self._bias
 
-class _MHSAModuleFn(torch.autograd.Function):
-    """x + factor * Drop(Wo . RelAttention(Wq|Wk|Wv . LN(x), Wpos . relpe) + bo)     (conformer.py:209-239, multihead_attention.py:584-667)"""
+    def bias_grad_target(self):
+        self._db = torch.zeros(3 * self.NH, dtype=torch.float32, device=self.w.device)
+        return self._db
 
-    @staticmethod
-    def forward(ctx, x, relpe2d, ln_g, ln_b, pk: MhsaPack, length, B, T, factor, drop_p, salt, seed, chunk, history):
-        N, H = pk.N, pk.H
-        a, mean, rstd = kernels.layernorm_fwd(x, ln_g, ln_b, LN_EPS)
-        qkv = kernels.gemm(a, pk.wqkv_t, bias=pk.bqkv)
-        pos = kernels.gemm(relpe2d, pk.wpos_t, bias=pk.bpos)
-        u32, v32 = pk.u.detach().float().contiguous(), pk.v.detach().float().contiguous()
-        cv, probs = kernels.rel_attention_fwd(qkv, pos, u32, v32, length, B, T, N, H, chunk, history)
-        out = kernels.gemm(cv, pk.wo_t, bias=pk.bo.detach().float(), residual=x, residual_scale=factor, dropout_p=drop_p, dropout_seed=seed,
-                           dropout_salt=salt)
-        ctx.save_for_backward(x, mean, rstd, a, qkv, pos, cv, probs, relpe2d, u32, v32)
-        ctx.misc = (ln_g, ln_b, pk, length, B, T, factor, drop_p, salt, seed, chunk, history)
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        x, mean, rstd, a, qkv, pos, cv, probs, relpe2d, u32, v32 = ctx.saved_tensors
-        ln_g, ln_b, pk, length, B, T, factor, drop_p, salt, seed, chunk, history = ctx.misc
-        N, H, D = pk.N, pk.H, pk.D
-        NH = N * H
-        dout = dout.contiguous()
-        M = x.shape[0]
-        ks = _splits(M)
-        wo_p, bo_p = pk.params["attention_output"]
-        dy = kernels.scale_mask_colsum(dout, scale=factor, dropout_p=drop_p, seed=seed, salt=salt, colsum=_grad(bo_p))
-        kernels.gemm(cv, dy, mn_major=True, out=_grad(wo_p).view(NH, D), accumulate=True, k_splits=ks)
-        dctx = kernels.gemm(dy, pk.wo)  # [M, NH]
-        dqkv, dpos = kernels.rel_attention_bwd(qkv, pos, u32, v32, length, B, T, N, H, probs, dctx, _grad(pk.u), _grad(pk.v), chunk, history)
-        # fused QKV projection: one weight-gradient GEMM into a scratch [D, 3NH], then slices to the three parameters
+    def accumulate_wgrad(self, x, dz):
+        D, NH = self.D, self.NH
         dw = torch.zeros((D, 3 * NH), dtype=torch.float32, device=x.device)
-        kernels.gemm(a, dqkv, mn_major=True, out=dw, accumulate=True, k_splits=ks)
-        db = torch.zeros(3 * NH, dtype=torch.float32, device=x.device)
-        kernels.colsum(dqkv, db)
-        for i, k in enumerate(("query", "key", "value")):
-            wp, bp = pk.params[k]
+        kernels.gemm(x, dz, mn_major=True, out=dw, accumulate=True, k_splits=_splits(x.shape[0]))
+        for i, (wp, bp) in enumerate(self.parts):
             _grad(wp).view(D, NH).add_(dw[:, i * NH:(i + 1) * NH])
-            _grad(bp).view(NH).add_(db[i * NH:(i + 1) * NH])
-        wpos_p, bpos_p = pk.params["encoding"]
-        kernels.gemm(relpe2d, dpos, mn_major=True, out=_grad(wpos_p).view(D, NH), accumulate=True, k_splits=_splits(relpe2d.shape[0]))
-        kernels.colsum(dpos, _grad(bpos_p).view(NH))
-        da = kernels.gemm(dqkv, pk.wqkv)
-        dx = kernels.layernorm_bwd(da, x, mean, rstd, ln_g, _grad(ln_g), _grad(ln_b), dres=dout)
-        return (dx,) + (None,) * 13
+            if self._db is not None:
+                _grad(bp).view(NH).add_(self._db[i * NH:(i + 1) * NH])
+        self._db = None
 
 
-def mhsa_module(x, relpe2d, ln_g, ln_b, pk, length, B, T, factor, drop_p, salt, seed, chunk=None, history=None):
-    return _MHSAModuleFn.apply(x, relpe2d, ln_g, ln_b, pk, length, B, T, float(factor), float(drop_p), int(salt), seed, chunk, history)
+class MhsaPack:
+    def __init__(self, enc, pre):
+        m = pre + ".mhsa"
+        D, N, H = enc.dmodel, enc.num_heads, enc.head_size
+        self.qkv = QkvPack(enc, pre)
+        self.pos = WeightPack(enc[f"{m}.encoding.kernel"].view(D, N * H), enc[f"{m}.encoding.bias"])
+        self.pos.param = enc[f"{m}.encoding.kernel"]
+        self.out = WeightPack(enc[f"{m}.attention_output.kernel"].view(N * H, D), enc[f"{m}.attention_output.bias"])
+        self.out.param = enc[f"{m}.attention_output.kernel"]
