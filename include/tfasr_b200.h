@@ -214,6 +214,15 @@ int tfasr_bn_bwd_stats(const void* dy, const void* x, const float* scale, const 
 int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* scale, const float* shift, const float* mean, const float* rstd,
                        const float* sums, float count, void* dx, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Causal depthwise 1-D convolution of the ConvModule (convolution.py:159-216, conformer.py:311-323,370): channels-last bf16 [B,T,C],
+ * w [K,C] f32 (keras depthwise kernel [K,C,1]), bias [C] f32 or NULL.  bwd writes dx and accumulates (+=) dw [K,C] / dbias [C] (or NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int tfasr_dwconv_causal_fwd(const void* x, const float* w, const float* bias, void* y, int32_t B, int32_t T, int32_t C, int32_t K,
+                            tfasr_stream_t stream);
+int tfasr_dwconv_causal_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, float* dbias, int32_t B, int32_t T, int32_t C,
+                            int32_t K, tfasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

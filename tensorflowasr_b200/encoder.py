@@ -273,6 +273,9 @@ class ConformerEncoder(_Params):
                     n = f"block_{b}.{ff}.{d}"
                     packs[n] = fused.WeightPack(self[n + ".kernel"], self[n + ".bias"])
             packs[f"block_{b}.mhsa_module"] = fused.MhsaPack(self, f"block_{b}.mhsa_module")
+            cm = f"block_{b}.conv_module"
+            packs[cm + ".pw_conv_1"] = fused.GluPack(self[cm + ".pw_conv_1.kernel"], self[cm + ".pw_conv_1.bias"])
+            packs[cm + ".pw_conv_2"] = fused.WeightPack(self[cm + ".pw_conv_2.kernel"], self[cm + ".pw_conv_2.bias"])
         self._packs = packs
 
     def _salt(self, pre, k):
@@ -329,6 +332,15 @@ class ConformerEncoder(_Params):
 
     def _conv(self, x, pre, training):
         # ConvModule.call, conformer.py:366-377
+        if ops.fused_active(x) and self.dw_norm_type == "batch" and (training or not torch.is_grad_enabled()):
+            B, T, D = x.shape
+            p = self.dropout if training else 0.0
+            bn = (self[pre + ".dw_bn.gamma"], self[pre + ".dw_bn.beta"], self[pre + ".dw_bn.moving_mean"], self[pre + ".dw_bn.moving_variance"])
+            y = fused.conv_module(x.reshape(B * T, D).to(torch.bfloat16), self[pre + ".ln.gamma"], self[pre + ".ln.beta"],
+                                  self._packs[pre + ".pw_conv_1"], self[pre + ".dw_conv.kernel"], self[pre + ".dw_conv.bias"], bn,
+                                  self._packs[pre + ".pw_conv_2"], B, T, self.convm_residual_factor, p, self._salt(pre, 1),
+                                  fused.STATE.seed_tensor(x.device), training)
+            return y.view(B, T, D)
         y = ops.layer_norm(x, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
         y = ops.linear(y, self[pre + ".pw_conv_1.kernel"], self[pre + ".pw_conv_1.bias"])
         y = ops.glu_dwconv_norm_swish(y, self[pre + ".dw_conv.kernel"], self[pre + ".dw_conv.bias"], self._dw_norm(pre.rsplit(".", 1)[0]),

@@ -143,7 +143,8 @@ class _LinearFn(torch.autograd.Function):
     """y = [residual + factor *] Drop(act(x W + b))"""
 
     @staticmethod
-    def forward(ctx, x, pack: WeightPack, activation, residual, factor, drop_p, salt, seed):
+    def forward(ctx, x, pack: WeightPack, activation, residual, factor, drop_p, salt, seed, anchor=None):
+        # `anchor`: a parameter passed only so that autograd records this node when x itself carries no gradient
         M = x.shape[0]
         N = pack.wt.shape[0]
         z = torch.empty((M, N), dtype=torch.bfloat16, device=x.device) if activation == "swish" else None
@@ -174,14 +175,17 @@ class _LinearFn(torch.autograd.Function):
             dz = kernels.scale_mask_colsum(dy, scale=scale, dropout_p=drop_p, seed=seed, salt=salt, colsum=pack.bias_grad_target())
         pack.accumulate_wgrad(x, dz)
         if not ctx.needs_input_grad[0]:
-            return None, None, None, (dy if has_res else None), None, None, None, None
+            return None, None, None, (dy if has_res else None), None, None, None, None, None
         dx = kernels.gemm(dz, pack.w)
-        return dx, None, None, (dy if has_res else None), None, None, None, None
+        return dx, None, None, (dy if has_res else None), None, None, None, None, None
 
 
 def linear(x, pack, activation=None, residual=None, factor=1.0, drop_p=0.0, salt=0, seed=None):
     """x [M, K] bf16 -> [M, N] bf16 through the tcgen05 GEMM (bias / activation / dropout / residual fused in the epilogue)."""
-    return _LinearFn.apply(x, pack, activation, residual, float(factor), float(drop_p), int(salt), seed)
+    anchor = None
+    if not x.requires_grad and torch.is_grad_enabled():
+        anchor = pack.param if pack.param is not None else pack.parts[0][0]
+    return _LinearFn.apply(x, pack, activation, residual, float(factor), float(drop_p), int(salt), seed, anchor)
 
 
 # ------------------------------------------------------------------------------------------------ joint + RNN-T loss head
@@ -401,3 +405,80 @@ class MhsaPack:
         self.pos.param = enc[f"{m}.encoding.kernel"]
         self.out = WeightPack(enc[f"{m}.attention_output.kernel"].view(N * H, D), enc[f"{m}.attention_output.bias"])
         self.out.param = enc[f"{m}.attention_output.kernel"]
+
+
+# ------------------------------------------------------------------------------------------------ ConvModule
+class GluPack(WeightPack):
+    """pw_conv_1 [D, 2D] with its GLU halves interleaved column-wise (a_0, b_0, a_1, b_1, ...) so that the GEMM epilogue applies
+    a * sigmoid(b) on adjacent columns; gradients are de-interleaved back into the Keras layout."""
+
+    def __init__(self, param, bias):
+        super().__init__(param, bias, interleave_glu=True)
+        D2 = param.shape[1]
+        self.D = D2 // 2
+        b = bias.detach().float()
+        self._bias = torch.stack([b[: self.D], b[self.D:]], dim=1).reshape(D2).contiguous()
+        self._db = None
+
+    def bias_f32(self):
+        return self._bias
+
+    def deinterleave_add(self, dw_inter, db_inter):
+        K = dw_inter.shape[0]
+        g = _grad(self.param)
+        d3 = dw_inter.view(K, self.D, 2)
+        g[:, : self.D].add_(d3[:, :, 0])
+        g[:, self.D:].add_(d3[:, :, 1])
+        gb = _grad(self.bias)
+        b2 = db_inter.view(self.D, 2)
+        gb[: self.D].add_(b2[:, 0])
+        gb[self.D:].add_(b2[:, 1])
+
+
+class _ConvModuleFn(torch.autograd.Function):
+    """x + factor * Drop(PW2 . swish(BN(DWconv_causal(GLU(PW1 . LN(x))))))     (conformer.py:366-377), batch-norm variant."""
+
+    @staticmethod
+    def forward(ctx, x, ln_g, ln_b, p1: GluPack, dw_w, dw_b, bn, p2: WeightPack, B, T, factor, drop_p, salt, seed, training):
+        M, D = x.shape
+        a, mean, rstd = kernels.layernorm_fwd(x, ln_g, ln_b, LN_EPS)
+        aux = torch.empty((M, 2 * D), dtype=torch.bfloat16, device=x.device)
+        g = kernels.gemm(a, p1.wt, bias=p1.bias_f32(), glu=True, aux=aux)  # [M, D]
+        w32 = dw_w.detach().float().contiguous()
+        c = kernels.dwconv_fwd(g.view(B, T, D), w32, dw_b.detach().float()).view(M, D)
+        gamma, beta, mm, mv = bn
+        if training:
+            y, saved = bn_train_fwd(c, gamma, beta, mm, mv)
+        else:
+            y, saved = bn_eval(c, gamma, beta, mm, mv), None
+        out = kernels.gemm(y, p2.wt, bias=p2.bias_f32(), residual=x, residual_scale=factor, dropout_p=drop_p, dropout_seed=seed, dropout_salt=salt)
+        ctx.save_for_backward(x, mean, rstd, a, aux, g, c, y, w32)
+        ctx.misc = (ln_g, ln_b, p1, dw_w, dw_b, bn, p2, B, T, factor, drop_p, salt, seed, saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mean, rstd, a, aux, g, c, y, w32 = ctx.saved_tensors
+        ln_g, ln_b, p1, dw_w, dw_b, bn, p2, B, T, factor, drop_p, salt, seed, saved = ctx.misc
+        if saved is None:
+            raise RuntimeError("ConvModule fused backward needs training-mode batch statistics")
+        M, D = x.shape
+        dout = dout.contiguous()
+        dy = kernels.scale_mask_colsum(dout, scale=factor, dropout_p=drop_p, seed=seed, salt=salt, colsum=p2.bias_grad_target())
+        p2.accumulate_wgrad(y, dy)
+        dyb = kernels.gemm(dy, p2.w)
+        dc = bn_train_bwd(dyb, c, saved, bn[0], bn[1])
+        # the depthwise bias sits in front of a batch norm: its gradient is identically zero
+        dg = kernels.dwconv_bwd(dc.view(B, T, D), g.view(B, T, D), w32, _grad(dw_w).view(-1, D), None).view(M, D)
+        db1 = torch.zeros(2 * D, dtype=torch.float32, device=x.device)
+        daux = kernels.glu_bwd(aux, dg, colsum=db1)
+        dw1 = torch.zeros((D, 2 * D), dtype=torch.float32, device=x.device)
+        kernels.gemm(a, daux, mn_major=True, out=dw1, accumulate=True, k_splits=_splits(M))
+        p1.deinterleave_add(dw1, db1)
+        da = kernels.gemm(daux, p1.w)
+        dx = kernels.layernorm_bwd(da, x, mean, rstd, ln_g, _grad(ln_g), _grad(ln_b), dres=dout)
+        return (dx,) + (None,) * 14
+
+
+def conv_module(x, ln_g, ln_b, p1, dw_w, dw_b, bn, p2, B, T, factor, drop_p, salt, seed, training):
+    return _ConvModuleFn.apply(x, ln_g, ln_b, p1, dw_w, dw_b, bn, p2, B, T, float(factor), float(drop_p), int(salt), seed, bool(training))

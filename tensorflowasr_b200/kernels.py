@@ -228,3 +228,22 @@ def rel_attention_bwd(qkv, pos, ubias, vbias, length, B, T, N, H, probs, dctx, d
                                            ch, hi, _lib.ptr(probs), _lib.ptr(dctx), _lib.ptr(ds), _lib.ptr(dqkv), _lib.ptr(dpos), _lib.ptr(du),
                                            _lib.ptr(dvb), _st(qkv)), "tfasr_rel_attention_bwd")
     return dqkv, dpos
+
+
+def dwconv_fwd(x, w, bias):
+    """x [B,T,C] bf16, w [K,C] f32 -> y [B,T,C] bf16 (causal depthwise conv)."""
+    lib = _lib.load()
+    B, T, C = x.shape
+    y = torch.empty_like(x)
+    _lib.check(lib.tfasr_dwconv_causal_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), B, T, C, w.shape[0], _st(x)), "tfasr_dwconv_causal_fwd")
+    return y
+
+
+def dwconv_bwd(dy, x, w, dw, dbias=None):
+    """-> dx [B,T,C] bf16; dw (f32 [K,C]) and dbias (f32 [C] or None) accumulated."""
+    lib = _lib.load()
+    B, T, C = x.shape
+    dx = torch.empty_like(x)
+    _lib.check(lib.tfasr_dwconv_causal_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(dbias), B, T, C, w.shape[0],
+                                           _st(x)), "tfasr_dwconv_causal_bwd")
+    return dx

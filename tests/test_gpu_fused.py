@@ -276,3 +276,29 @@ def test_rel_attention_kernels_vs_torch(cfg):
     _close(dpos.view(B, R, NH), p3.grad, 3e-2)
     _close(du, ur.grad, 3e-2)
     _close(dv, vr.grad, 3e-2)
+
+
+def test_dwconv_kernels_vs_torch():
+    import torch.nn.functional as F
+
+    from tensorflowasr_b200 import kernels
+
+    torch.manual_seed(1)
+    B, T, C, K = 3, 150, 144, 31
+    x = torch.randn(B, T, C, device="cuda").to(torch.bfloat16)
+    w = torch.randn(K, C, device="cuda") * 0.2
+    bias = torch.randn(C, device="cuda") * 0.1
+    y = kernels.dwconv_fwd(x, w, bias)
+    xr = x.float().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    ref = F.conv1d(F.pad(xr.transpose(1, 2), (K - 1, 0)), wr.t().unsqueeze(1), br, groups=C).transpose(1, 2)
+    _close(y, ref)
+    dy = torch.randn(B, T, C, device="cuda").to(torch.bfloat16)
+    ref.backward(dy.float())
+    dw = torch.zeros(K, C, device="cuda")
+    db = torch.zeros(C, device="cuda")
+    dx = kernels.dwconv_bwd(dy, x, w, dw, db)
+    _close(dx, xr.grad)
+    _close(dw, wr.grad, 5e-3)
+    _close(db, br.grad, 5e-3)
