@@ -7,16 +7,9 @@
 //   GLU backward                    models/activations/glu.py:25-28
 // One warp per row; rows are D <= 1024 wide (D = 144 in Conformer-S, 320 in the prediction net).
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace tfasr {
-
-__device__ __forceinline__ float hash_uniform_(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
-}
 
 constexpr int kRowsWarps = 8;
 constexpr int kMaxPerLane = 32;  // D <= 1024
@@ -140,6 +133,7 @@ __global__ void __launch_bounds__(256) scale_mask_colsum_kernel(const __nv_bfloa
   // block = [rows_per_block rows] x all columns; thread t handles column pair (2t, 2t+1) (+ stride blockDim for wide N)
   const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   const unsigned long long seed = (drop_p > 0.f && seed_ptr) ? (*seed_ptr + salt) : salt;
+  const uint32_t drop_thr = dropout_threshold(drop_p);
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
   for (int c = 2 * threadIdx.x; c < N; c += 2 * blockDim.x) {
@@ -149,8 +143,9 @@ __global__ void __launch_bounds__(256) scale_mask_colsum_kernel(const __nv_bfloa
       const __nv_bfloat162 vi = *reinterpret_cast<const __nv_bfloat162*>(in + idx);
       float a = __low2float(vi) * scale, b = __high2float(vi) * scale;
       if (drop_p > 0.f) {
-        a = hash_uniform_(seed, idx) >= drop_p ? a * keep_scale : 0.f;
-        b = hash_uniform_(seed, idx + 1) >= drop_p ? b * keep_scale : 0.f;
+        const uint32_t hsh = dropout_hash(seed, idx);  // idx is even: one hash serves the column pair
+        a = ((hsh & 0xFFFFu) >= drop_thr) ? a * keep_scale : 0.f;
+        b = ((hsh >> 16) >= drop_thr) ? b * keep_scale : 0.f;
       }
       if (add) {
         const __nv_bfloat162 va = *reinterpret_cast<const __nv_bfloat162*>(add + idx);

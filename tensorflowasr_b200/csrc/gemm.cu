@@ -16,6 +16,7 @@
 // launch/latency bound — see DESIGN.md.
 #include "common.cuh"
 #include "sm100.cuh"
+#include "dropout.cuh"
 
 #include <string.h>
 
@@ -86,14 +87,6 @@ struct GemmEpi {
   int atomic_out;       // 1: atomicAdd into f32 C (split-K partial sums / gradient accumulation)
   int tma_store;        // 1: C leaves through SMEM staging + cp.async.bulk.tensor stores (coalesced, clipped by hardware)
 };
-
-__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
-}
 
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
@@ -238,6 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_drop = epi.drop_p > 0.f;
     const float drop_p = epi.drop_p;
     const float keep_scale = has_drop ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const uint32_t drop_thr = dropout_threshold(drop_p);
     const unsigned long long seed = (has_drop && epi.seed_ptr) ? (*epi.seed_ptr + epi.salt) : epi.salt;
     const float res_scale = epi.res_scale;
     const bool vec16 = ((epi.ldc & 7) == 0) || (epi.c_f32 && (epi.ldc & 3) == 0);
@@ -382,7 +376,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (has_drop) {
         const unsigned long long base = (unsigned long long)row * (unsigned long long)N + (unsigned long long)n0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (hash_uniform(seed, base + j) >= drop_p) ? v[j] * keep_scale : 0.f;
+        for (int j = 0; j < 16; j += 2) {
+          const uint32_t hsh = dropout_hash(seed, base + j);  // base is even (n0 % 16 == 0, N even)
+          v[j] = ((hsh & 0xFFFFu) >= drop_thr) ? v[j] * keep_scale : 0.f;
+          v[j + 1] = ((hsh >> 16) >= drop_thr) ? v[j + 1] * keep_scale : 0.f;
+        }
       }
       if (res_row && row_ok) {
         float z[16];
