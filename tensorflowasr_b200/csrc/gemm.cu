@@ -88,9 +88,14 @@ struct GemmEpi {
   int tma_store;        // 1: C leaves through SMEM staging + cp.async.bulk.tensor stores (coalesced, clipped by hardware)
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid(x) = 0.5 tanh(0.5 x) + 0.5 : one MUFU op (tanh.approx) instead of ex2 + rcp
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 
@@ -102,7 +107,7 @@ struct GemmSmem {
   static constexpr int STAGES = (BN >= 192) ? 4 : 6;
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
-  static constexpr int STAGE_OUT_BYTES = 4 /*epilogue warps*/ * 2 /*double buffer*/ * 32 /*rows*/ * 128 /*bytes*/;
+  static constexpr int STAGE_OUT_BYTES = 8 /*epilogue warps*/ * 32 /*rows*/ * 128 /*bytes*/;
   static constexpr int TOTAL = STAGES * (A_BYTES + B_BYTES) + STAGE_OUT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);  // two accumulators
   static_assert(TOTAL <= 227 * 1024, "smem budget");
@@ -141,7 +146,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&tmem_full[i], 1);
-      sm100::mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+      sm100::mbar_init(&tmem_empty[i], 8);  // one arrival per epilogue warp
     }
     sm100::fence_barrier_init();
   }
@@ -260,10 +265,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 
     // C staging: per warp two 32-row x 128-byte buffers in the 128B-swizzled layout the store tensor map expects
-    uint8_t* stage_base = sOut + (warp - 2) * (2 * 32 * 128);
+    uint8_t* sbuf = sOut + (warp - 2) * (32 * 128);  // this warp's staging buffer (1024-byte aligned)
+    const int half = (warp - 2) >> 2;               // which column range of the tile this warp drains
     const bool tma_out = epi.tma_store != 0;
     const int group_cols = epi.c_f32 ? 32 : 64;  // columns per 128-byte staging row
-    uint32_t stage_it = 0;
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
       int m_blk, n_blk, k_begin, num_k;
@@ -278,16 +283,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n_cols = min(BN, N - n_blk * BN);  // valid columns of this tile
       sm100::mbar_wait(&tmem_full[buf], aph);
       sm100::tc_fence_after();
+      // column split between the two warps of a lane quarter, in whole staging groups (64 bf16 / 32 f32 columns)
+      const int groups = (BN + group_cols - 1) / group_cols;
+      const int g_split = (groups + 1) / 2;
+      const int c_begin = half == 0 ? 0 : g_split * group_cols;
+      const int c_end = min(n_cols, half == 0 ? g_split * group_cols : BN);
+      const int valid_rows = max(0, min(32, M - (m_blk * kBM + q * 32)));
       uint32_t r[16];
-      if (num_k > 0) sm100::tmem_ld_32x32b_x16(tmem_row, r);
+      if (num_k > 0 && c_begin < c_end) sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)c_begin, r);
 #pragma unroll 1
-      for (int c0 = 0; c0 < n_cols && num_k > 0; c0 += 16) {
+      for (int c0 = c_begin; c0 < c_end && num_k > 0; c0 += 16) {
       const int n0 = n_blk * BN + c0;
       sm100::tmem_ld_wait();
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-      if (c0 + 16 < n_cols) sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)(c0 + 16), r);  // prefetch the next chunk
+      if (c0 + 16 < c_end) sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)(c0 + 16), r);  // prefetch the next chunk
       const bool full = (c0 + 16 <= n_cols) && vec16;
       if (alpha != 1.0f) {
 #pragma unroll
@@ -393,7 +404,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = z[j] + res_scale * v[j];
       }
-      if (epi.colsum) {
+      if (epi.colsum && !tma_out) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float sj = row_ok ? v[j] : 0.f;
@@ -403,11 +414,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (tma_out) {
         // stage this thread's 16 values (one row) into the swizzled buffer; a full 128-byte group leaves with one TMA store
-        uint8_t* sbuf = stage_base + (stage_it & 1) * (32 * 128);
-        const int col_in_group = c0 % group_cols;
+        const int col_in_group = (c0 - c_begin) % group_cols;
         if (col_in_group == 0) {
-          // buffer reuse: the store issued two groups ago must have finished reading it
-          if (lane == 0) sm100::tma_store_wait_read<1>();
+          // buffer reuse: the previous store must have finished reading it
+          if (lane == 0) sm100::tma_store_wait_read<0>();
           __syncwarp();
         }
         uint8_t* srow = sbuf + lane * 128;
@@ -427,7 +437,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           *reinterpret_cast<uint4*>(srow + ((cg ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(srow + (((cg + 1) ^ (lane & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        const bool group_done = (col_in_group + 16 == group_cols) || (c0 + 16 >= n_cols);
+        const bool group_done = (col_in_group + 16 == group_cols) || (c0 + 16 >= c_end);
         if (group_done) {
           sm100::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
@@ -435,7 +445,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sm100::tma_store_2d(&tmC, sbuf, n_blk * BN + (c0 - col_in_group), m_blk * kBM + q * 32);
             sm100::tma_store_commit();
           }
-          ++stage_it;
+          if (epi.colsum) {
+            // column sums straight from the staged tile: each lane owns one 4-byte column slot (2 bf16 / 1 f32 columns)
+            const int gcol0 = n_blk * BN + (c0 - col_in_group);
+            const int ncols_here = min(group_cols, c_end - (c0 - col_in_group));
+            float s0 = 0.f, s1 = 0.f;
+            for (int rr = 0; rr < valid_rows; ++rr) {
+              const uint32_t wv = *reinterpret_cast<const uint32_t*>(sbuf + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
+              if (epi.c_f32) {
+                s0 += __uint_as_float(wv);
+              } else {
+                s0 += __uint_as_float(wv << 16);
+                s1 += __uint_as_float(wv & 0xFFFF0000u);
+              }
+            }
+            if (epi.c_f32) {
+              if (lane < ncols_here) atomicAdd(epi.colsum + gcol0 + lane, s0);
+            } else {
+              if (2 * lane < ncols_here) atomicAdd(epi.colsum + gcol0 + 2 * lane, s0);
+              if (2 * lane + 1 < ncols_here) atomicAdd(epi.colsum + gcol0 + 2 * lane + 1, s1);
+            }
+          }
         }
       } else if (row_ok) {
         if (epi.c_f32) {
