@@ -209,7 +209,8 @@ class _TransducerHeadFn(torch.autograd.Function):
         V = pack.wt.shape[0]
         M = B * T * U1
         h = kernels.joint_tanh_fwd(e.contiguous(), p.contiguous())
-        logits = kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out_dtype=torch.float32)
+        with _lib.TIMERS.region("joint_gemm_fwd"):
+            logits = kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out_dtype=torch.float32)
         ws_bytes = lib.tfasr_rnnt_workspace_bytes(B, T, U1, V)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=e.device)
         costs = torch.empty(B, dtype=torch.float32, device=e.device)
@@ -238,8 +239,10 @@ class _TransducerHeadFn(torch.autograd.Function):
                        "tfasr_rnnt_loss_bwd_bf16")
         dlv = dl[:, :V]
         h2 = h.view(M, J)
-        dz = kernels.gemm(dlv, pack.w, mul=h2, mul_mode="tanh_grad")  # [M, J]
-        kernels.gemm(h2, dlv, mn_major=True, out=_grad(pack.param), accumulate=True, k_splits=32)  # dWv [J, V]
+        with _lib.TIMERS.region("joint_gemm_dgrad"):
+            dz = kernels.gemm(dlv, pack.w, mul=h2, mul_mode="tanh_grad")  # [M, J]
+        with _lib.TIMERS.region("joint_gemm_wgrad"):
+            kernels.gemm(h2, dlv, mn_major=True, out=_grad(pack.param), accumulate=True, k_splits=32)  # dWv [J, V]
         de, dp = kernels.joint_reduce_bwd(dz.view(B, T, U1, J))
         return de.to(de_dtype), dp.to(dp_dtype), None, None, None, None
 
