@@ -13,3 +13,5 @@ from . import ops  # noqa: F401,E402
 from .base_model import BaseModel, TransformerSchedule, make_optimizer  # noqa: F401,E402
 from .encoder import ConformerEncoder, Conv2dSubsampling  # noqa: F401,E402
 from .transducer import Conformer, Transducer, TransducerJoint, TransducerPrediction, conformer_small_config  # noqa: F401,E402
+from .ctc_models import (ContextNet, ContextNetEncoder, CtcModel, DeepSpeech2, DeepSpeech2Encoder, contextnet_config,  # noqa: F401,E402
+                         deepspeech2_base_config)

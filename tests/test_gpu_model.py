@@ -153,3 +153,97 @@ def test_greedy_decode_tokens_bit_exact_vs_oracle():
     ref1, margin1 = oc.greedy_single(enc1, int(elen1[0]), p, ocfg)
     if margin1 > 1e-3:
         assert out1.tokens[0].cpu().tolist() == ref1
+
+
+def _load_rand(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    ws = {}
+    for n, t in model.named_weights().items():
+        if "moving_variance" in n:
+            v = torch.rand(t.shape, generator=g) * 0.5 + 0.75
+        elif n.endswith("gamma"):
+            v = torch.randn(t.shape, generator=g) * 0.1 + 1
+        elif n.endswith(("bias", "beta", "moving_mean")):
+            v = torch.randn(t.shape, generator=g) * 0.1
+        else:
+            v = t.detach().cpu().clone()
+        ws[n] = v
+    model.load_named_weights(ws)
+    return ws
+
+
+def test_deepspeech2_ctc_model_vs_oracle():
+    """BASELINE config 2 family: spectrogram frontend kernel -> DeepSpeech2 encoder -> vocab Dense -> CTC loss kernel; greedy CTC tokens
+    bit-exact vs the oracle's tf.nn.ctc_greedy_decoder restatement."""
+    import tensorflowasr_b200 as tfasr
+    from oracle import ctc as octc
+    from oracle import other_models as om
+    from tensorflowasr_b200 import ops, schemas
+
+    ops.set_precision("fp32")
+    cfg = tfasr.deepspeech2_base_config(vocab_size=29)
+    cfg.update(rnn_nlayers=2, rnn_units=32, fc_units=48, rnn_dropout=0.0, fc_dropout=0.0)
+    model = tfasr.DeepSpeech2(**cfg, seed=2).cuda()
+    ws = _load_rand(model, 9)
+    B, N, L = 3, 16000, 12
+    g = torch.Generator().manual_seed(0)
+    sig = (0.1 * torch.randn(B, N, generator=g)).clamp(-1, 1)
+    sig_len = torch.tensor([N, N - 3100, N // 2], dtype=torch.int32)
+    labels = torch.randint(1, 29, (B, L), generator=g, dtype=torch.int32)
+    lab_len = torch.tensor([L, 7, 3], dtype=torch.int32)
+    x = schemas.TrainInput(sig.cuda(), sig_len.cuda(), None, None)
+    model.eval()
+    out = model(x, training=False)
+    feats, flen = ologmel.feature_extraction(sig.numpy().astype(np.float64), sig_len.numpy(), feature_type="spectrogram", num_feature_bins=160, dtype=np.float64)
+    p = {k: v.double() for k, v in ws.items()}
+    ocfg = dict(conv_kernels=[(11, 41), (11, 21)], conv_strides=[(2, 2), (1, 2)], rnn_nlayers=2, rnn_units=32, fc_nlayers=1)
+    ref, rl = om.deepspeech2_forward(p, ocfg, torch.from_numpy(feats), torch.from_numpy(flen).long(), training=False)
+    assert out.logits_length.tolist() == rl.tolist()
+    for b in range(B):
+        n = int(rl[b])
+        np.testing.assert_allclose(out.logits[b, :n].detach().cpu().double().numpy(), ref[b, :n].numpy(), rtol=1e-3, atol=2e-3)
+    loss = tfasr.CtcLoss().call(schemas.TrainLabel(labels.cuda(), lab_len.cuda()), out)
+    rc, _ = octc.ctc_loss(ref.numpy(), labels.numpy(), rl.numpy(), lab_len.numpy())
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), rc, rtol=1e-3)
+    toks = model.recognize(schemas.PredictInput(sig.cuda(), sig_len.cuda())).tokens.cpu()
+    want = om.ctc_greedy(ref, rl)
+    for b in range(B):
+        assert [t for t in toks[b].tolist()][: len(want[b])] == want[b] and all(t == 0 for t in toks[b].tolist()[len(want[b]):])
+    # one training step runs and is finite
+    ops.set_precision("bf16")
+    try:
+        model.compile(optimizer=tfasr.make_optimizer(model, learning_rate=1e-3))
+        model.train()
+        l0 = model.train_step(schemas.TrainData(x, schemas.TrainLabel(labels.cuda(), lab_len.cuda())))["loss"]
+        assert torch.isfinite(l0).all()
+    finally:
+        ops.set_precision("fp32")
+
+
+def test_contextnet_transducer_vs_oracle():
+    """BASELINE config 4 family (ContextNet transducer): encoder + fused loss head vs the oracle, fp32."""
+    import tensorflowasr_b200 as tfasr
+    from oracle import other_models as om
+    from tensorflowasr_b200 import ops, schemas
+
+    ops.set_precision("fp32")
+    blocks = [dict(nlayers=1, kernel_size=5, filters=64, strides=1, residual=False, activation="silu", padding="causal"),
+              dict(nlayers=3, kernel_size=5, filters=64, strides=2, residual=True, activation="silu", padding="causal"),
+              dict(nlayers=2, kernel_size=5, filters=96, strides=2, residual=True, activation="silu", padding="causal")]
+    V = 40
+    cfg = tfasr.contextnet_config(vocab_size=V, alpha=0.5)
+    cfg.update(encoder_blocks=blocks, prediction_embed_dim=32, prediction_rnn_units=32, joint_dim=48)
+    model = tfasr.ContextNet(**cfg, seed=4).cuda()
+    ws = _load_rand(model, 11)
+    data, host = _batch(B=3, N=12000, U=5, V=V)
+    model.eval()
+    losses = model.compute_losses(data, training=False).detach().cpu().double()
+    sig, sig_len, pred, pred_len, labels, lab_len = host
+    feats, flen = ologmel.feature_extraction(sig.numpy().astype(np.float64), sig_len.numpy(), dtype=np.float64)
+    p = {k: v.double() for k, v in ws.items()}
+    enc, elen = om.contextnet_forward(p, [dict(b, filters=int(b["filters"] * 0.5)) for b in blocks], torch.from_numpy(feats),
+                                      torch.from_numpy(flen).long(), training=False)
+    pr = oc.prediction_net(pred, pred_len.long(), p, oc.ConformerConfig(vocab_size=V, embed_dim=32, rnn_units=32))
+    logits = oc.joint_net(enc, pr, p)
+    ref = oc.rnnt_loss_torch(logits, labels, elen.int(), lab_len)
+    np.testing.assert_allclose(losses.numpy(), ref.numpy(), rtol=1e-3)
