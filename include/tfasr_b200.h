@@ -223,6 +223,15 @@ int tfasr_dwconv_causal_fwd(const void* x, const float* w, const float* bias, vo
 int tfasr_dwconv_causal_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, float* dbias, int32_t B, int32_t T, int32_t C,
                             int32_t K, tfasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SpecAugment on the features, in place (augmentations/augmentation.py:67-90, methods/specaugment.py:58-137): n_freq frequency masks
+ * (width < freq_factor) then n_time time masks (width < floor(len * p_upperbound)) per utterance, each applied with its probability,
+ * masked cells set to mask_value.  Random stream = counter hash of (*seed_ptr + salt, utterance, mask).
+ * ---------------------------------------------------------------------------------------------- */
+int tfasr_specaugment_f32(float* feat /*[B,T,F]*/, const int32_t* length /*[B] frames, or NULL*/, int32_t B, int32_t T, int32_t F, int32_t n_time,
+                          float p_upperbound, float time_prob, int32_t n_freq, int32_t freq_factor, float freq_prob, float mask_value,
+                          const unsigned long long* seed_ptr, unsigned long long salt, tfasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

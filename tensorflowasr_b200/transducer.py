@@ -296,10 +296,13 @@ class Conformer(Transducer):
 
 
 def conformer_small_config(vocab_size=1000):
-    """examples/models/transducer/conformer/small.yml.j2:5-65 (SpecAugment left to the caller)."""
+    """examples/models/transducer/conformer/small.yml.j2:5-65, SpecAugment included."""
     return dict(
         blank=0, vocab_size=vocab_size,
-        speech_config=dict(sample_rate=16000, frame_ms=25, stride_ms=10, nfft=512, num_feature_bins=80, feature_type="log_mel_spectrogram"),
+        speech_config=dict(sample_rate=16000, frame_ms=25, stride_ms=10, nfft=512, num_feature_bins=80, feature_type="log_mel_spectrogram",
+                           augmentation_config=dict(feature_augment=dict(  # small.yml.j2:12-24 (active in training mode only)
+                               time_masking=dict(prob=1.0, num_masks=10, mask_factor=-1, p_upperbound=0.05, mask_value=0),
+                               freq_masking=dict(prob=1.0, num_masks=1, mask_factor=27, mask_value=0)))),
         encoder_subsampling=dict(class_name="tensorflow_asr.models.layers.subsampling>Conv2dSubsampling",
                                  config=dict(filters=[144, 144], kernels=[3, 3], strides=[2, 2], paddings=["causal", "causal"],
                                              norms=["batch", "batch"], activations=["swish", "swish"])),
