@@ -12,6 +12,7 @@
 // Sizes here are small (T' = 250, H = 36 per head): the kernels keep K, V and the needed window of the position table in SMEM and
 // run on the FP32 pipes; they are latency / SMEM-bandwidth bound, not tensor-core candidates at H = 36.
 #include "common.cuh"
+#include "attention_mma.cuh"
 
 namespace tfasr {
 
@@ -332,6 +333,634 @@ __global__ void __launch_bounds__(64) rel_attention_bwd_cols_kernel(const AttPar
   }
 }
 
+// ================================================================================================ tensor-core forward
+// One CTA = (utterance b, head n, 64 query rows); 4 warps x 16 rows.  K, V, the position-table window and (q+u), (q+v) live in SMEM as
+// bf16 with a row stride that is an odd multiple of 16 bytes (conflict-free ldmatrix).  Per warp:
+//   A  positional block  S_pos[16 x (T+15)] = Qv . Pos[window]^T  -> f32 scratch           (mma.sync)
+//   B  content tiles     S[16 x 8] = Qu . K^T + S_pos[i][j + 15 - i]  (the rel-shift is this index), mask -> scratch in place
+//   C  row softmax       -> bf16 probabilities to HBM (kept for backward) and in place into the scratch (A operand of D)
+//   D  O = P . V         (mma.sync, V through ldmatrix.trans) -> ctx
+template <int KS>  // k-steps of 16 over the head dimension: H <= 16 * KS
+struct AttMma {
+  static constexpr int HS = KS == 3 ? 56 : (KS == 4 ? 72 : (KS == 2 ? 40 : 24));  // bf16 row stride: odd multiple of 16 B
+  static constexpr int TQ = 64;
+};
+
+__host__ __device__ inline int att_mma_tk(int T) { return (T + 15) / 16 * 16; }
+__host__ __device__ inline int att_mma_sw(int T) {  // f32 scratch row stride: >= Tk + 16 and (SW * 4) an odd multiple of 16 B
+  int sw = att_mma_tk(T) + 16;
+  while (((sw * 4) / 16) % 2 == 0 || (sw * 4) % 16) sw += 1;
+  return sw;
+}
+__host__ __device__ inline int att_mma_pw(int T) { return (T + 64 + 16 + 7) / 8 * 8; }
+
+template <int KS>
+static size_t att_mma_fwd_smem(int T) {
+  using C = AttMma<KS>;
+  const int Tk = att_mma_tk(T);
+  size_t b = (size_t)(2 * C::TQ + 2 * Tk + att_mma_pw(T)) * C::HS * 2;
+  b = align_up(b, 16);
+  b += (size_t)4 * 16 * att_mma_sw(T) * 4;
+  return b;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(128) rel_attention_fwd_mma_kernel(const AttParams p, __nv_bfloat16* __restrict__ ctx,
+                                                                    __nv_bfloat16* __restrict__ probs) {
+  using C = AttMma<KS>;
+  constexpr int HS = C::HS;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  const int T = p.T, H = p.H, NH = p.N * p.H, R = p.R;
+  const int b = blockIdx.z, n = blockIdx.y, t0 = blockIdx.x * C::TQ;
+  const int Tk = att_mma_tk(T), SW = att_mma_sw(T), PW = att_mma_pw(T);
+  __nv_bfloat16* sQu = reinterpret_cast<__nv_bfloat16*>(att_smem);
+  __nv_bfloat16* sQv = sQu + C::TQ * HS;
+  __nv_bfloat16* sK = sQv + C::TQ * HS;
+  __nv_bfloat16* sV = sK + (size_t)Tk * HS;
+  __nv_bfloat16* sP = sV + (size_t)Tk * HS;
+  float* sS = reinterpret_cast<float*>(att_smem + align_up((size_t)(2 * C::TQ + 2 * Tk + PW) * HS * 2, 16));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int len = p.length ? p.length[b] : T;
+  const int r_lo = T - 1 - (t0 + C::TQ - 1);  // may be negative: rows below 0 are zero
+  // ---- stage operands (zero padded to 16 * KS columns)
+  {
+    constexpr int HP2 = KS * 8;  // bf16x2 per padded row
+    const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+    for (int i = threadIdx.x; i < Tk * HP2; i += 128) {
+      const int j = i / HP2, h2 = i % HP2;
+      __nv_bfloat162 kk = z2, vv = z2;
+      if (j < T && 2 * h2 < H) {
+        const size_t gidx = ((size_t)b * T + j) * p.ld_qkv + (size_t)n * H + 2 * h2;
+        kk = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + gidx + NH);
+        vv = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + gidx + 2 * NH);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(sK + j * HS + 2 * h2) = kk;
+      *reinterpret_cast<__nv_bfloat162*>(sV + j * HS + 2 * h2) = vv;
+    }
+    for (int i = threadIdx.x; i < PW * HP2; i += 128) {
+      const int rr = i / HP2, h2 = i % HP2;
+      const int r = r_lo + rr;
+      __nv_bfloat162 v = z2;
+      if (r >= 0 && r < R && 2 * h2 < H) v = *reinterpret_cast<const __nv_bfloat162*>(p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 2 * h2);
+      *reinterpret_cast<__nv_bfloat162*>(sP + rr * HS + 2 * h2) = v;
+    }
+    for (int i = threadIdx.x; i < C::TQ * HP2; i += 128) {
+      const int rr = i / HP2, h2 = i % HP2;
+      const int t = t0 + rr;
+      __nv_bfloat162 qu = z2, qv = z2;
+      if (t < T && 2 * h2 < H) {
+        const __nv_bfloat162 q = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + ((size_t)b * T + t) * p.ld_qkv + (size_t)n * H + 2 * h2);
+        const float q0 = __low2float(q), q1 = __high2float(q);
+        const float* ub = p.ubias + n * H + 2 * h2;
+        const float* vb = p.vbias + n * H + 2 * h2;
+        qu = __floats2bfloat162_rn((q0 + ub[0]) * p.scale, (q1 + ub[1]) * p.scale);
+        qv = __floats2bfloat162_rn((q0 + vb[0]) * p.scale, (q1 + vb[1]) * p.scale);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(sQu + rr * HS + 2 * h2) = qu;
+      *reinterpret_cast<__nv_bfloat162*>(sQv + rr * HS + 2 * h2) = qv;
+    }
+  }
+  __syncthreads();
+  const int tw = t0 + warp * 16;  // first query row of this warp
+  if (tw >= T) return;
+  float* myS = sS + (size_t)warp * 16 * SW;
+  // A fragments of (q+u) and (q+v): rows warp*16 .. +15
+  uint32_t aqu[KS][4], aqv[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int rrow = warp * 16 + (lane & 15), col = ks * 16 + (lane >> 4) * 8;
+    mma::ldsm_x4(aqu[ks], sQu + rrow * HS + col);
+    mma::ldsm_x4(aqv[ks], sQv + rrow * HS + col);
+  }
+  // ---- A: positional block.  Window row of this warp's first needed position: r = T-1-(tw+15) -> rr0 = r - r_lo = 48 - 16*warp
+  const int rr0 = (C::TQ - 16) - warp * 16;
+  const int npos_tiles = (T + 15 + 7) / 8;
+  for (int nt = 0; nt < npos_tiles; ++nt) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t bfr[2];
+      mma::ldsm_x2(bfr, sP + (rr0 + nt * 8 + (lane & 7)) * HS + ks * 16 + ((lane >> 3) & 1) * 8);
+      mma::mma_16816(acc, aqv[ks], bfr);
+    }
+    float* d0 = myS + (size_t)g * SW + nt * 8 + 2 * tq;
+    float* d1 = myS + (size_t)(g + 8) * SW + nt * 8 + 2 * tq;
+    d0[0] = acc[0];
+    d0[1] = acc[1];
+    d1[0] = acc[2];
+    d1[1] = acc[3];
+  }
+  __syncwarp();
+  // ---- B: content scores + shifted positional term + masks, written back in place (column j of row i)
+  const int i0 = g, i1 = g + 8;
+  const int tA = tw + i0, tB = tw + i1;
+  for (int nt = 0; nt < Tk / 8; ++nt) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t bfr[2];
+      mma::ldsm_x2(bfr, sK + (nt * 8 + (lane & 7)) * HS + ks * 16 + ((lane >> 3) & 1) * 8);
+      mma::mma_16816(acc, aqu[ks], bfr);
+    }
+    const int j0 = nt * 8 + 2 * tq;
+    const float p00 = myS[(size_t)i0 * SW + j0 + 15 - i0], p01 = myS[(size_t)i0 * SW + j0 + 1 + 15 - i0];
+    const float p10 = myS[(size_t)i1 * SW + j0 + 15 - i1], p11 = myS[(size_t)i1 * SW + j0 + 1 + 15 - i1];
+    __syncwarp();  // every lane has read this tile's positional terms before the in-place writes below
+    float s00 = acc[0] + p00, s01 = acc[1] + p01, s10 = acc[2] + p10, s11 = acc[3] + p11;
+    if (!att_allowed(tA, j0, len, T, p.chunk, p.history)) s00 = -1e9f;
+    if (!att_allowed(tA, j0 + 1, len, T, p.chunk, p.history)) s01 = -1e9f;
+    if (!att_allowed(tB, j0, len, T, p.chunk, p.history)) s10 = -1e9f;
+    if (!att_allowed(tB, j0 + 1, len, T, p.chunk, p.history)) s11 = -1e9f;
+    myS[(size_t)i0 * SW + j0] = s00;
+    myS[(size_t)i0 * SW + j0 + 1] = s01;
+    myS[(size_t)i1 * SW + j0] = s10;
+    myS[(size_t)i1 * SW + j0 + 1] = s11;
+  }
+  __syncwarp();
+  // ---- C: softmax per row; bf16 probabilities to HBM and in place (A operand of P.V)
+  const int nit = Tk / 32 + ((Tk % 32) ? 1 : 0);
+  for (int i = 0; i < 16; ++i) {
+    const int t = tw + i;
+    float* srow = myS + (size_t)i * SW;
+    float sc[16];  // Tk <= 512
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int j = lane + 32 * it;
+      sc[it] = (it < nit && j < T) ? srow[j] : -CUDART_INF_F;
+      m = fmaxf(m, sc[it]);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const float e = (sc[it] > -CUDART_INF_F) ? __expf(sc[it] - m) : 0.f;
+      sc[it] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    __syncwarp();  // whole row is in registers: safe to overwrite it with bf16
+    __nv_bfloat16* prow_s = reinterpret_cast<__nv_bfloat16*>(srow);
+    __nv_bfloat16* prow_g = probs + (((size_t)b * p.N + n) * T + min(t, T - 1)) * T;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int j = lane + 32 * it;
+      if (it < nit && j < Tk) {
+        const __nv_bfloat16 pb = __float2bfloat16(sc[it] * inv);
+        prow_s[j] = pb;  // zero for j >= T (sc = 0)
+        if (j < T && t < T) prow_g[j] = pb;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- D: O = P . V
+  float o[KS * 2][4];
+#pragma unroll
+  for (int nh = 0; nh < KS * 2; ++nh) o[nh][0] = o[nh][1] = o[nh][2] = o[nh][3] = 0.f;
+  const __nv_bfloat16* pr_base = reinterpret_cast<const __nv_bfloat16*>(myS);
+  const int prs = SW * 2;  // bf16 elements per scratch row
+  for (int kt = 0; kt < Tk / 16; ++kt) {
+    uint32_t afr[4];
+    mma::ldsm_x4(afr, pr_base + (size_t)(lane & 15) * prs + kt * 16 + (lane >> 4) * 8);
+#pragma unroll
+    for (int nh = 0; nh < KS * 2; ++nh) {
+      uint32_t bfr[2];
+      mma::ldsm_x2_trans(bfr, sV + (kt * 16 + (lane & 15)) * HS + nh * 8);
+      mma::mma_16816(o[nh], afr, bfr);
+    }
+  }
+#pragma unroll
+  for (int nh = 0; nh < KS * 2; ++nh) {
+    const int h = nh * 8 + 2 * tq;
+    if (h < H) {
+      if (tA < T) *reinterpret_cast<__nv_bfloat162*>(ctx + ((size_t)b * T + tA) * NH + (size_t)n * H + h) = __floats2bfloat162_rn(o[nh][0], o[nh][1]);
+      if (tB < T) *reinterpret_cast<__nv_bfloat162*>(ctx + ((size_t)b * T + tB) * NH + (size_t)n * H + h) = __floats2bfloat162_rn(o[nh][2], o[nh][3]);
+    }
+  }
+}
+
+template <int KS>
+static int launch_att_fwd_mma(const AttParams& p, __nv_bfloat16* ctx, __nv_bfloat16* probs, cudaStream_t stream) {
+  const size_t smem = att_mma_fwd_smem<KS>(p.T);
+  if (smem > 227 * 1024 || p.T > 512) return -1;  // caller falls back to the FP32 kernel
+  if (cudaFuncSetAttribute(rel_attention_fwd_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return TFASR_EXECUTION_FAILED;
+  dim3 grid((unsigned)ceil_div(p.T, AttMma<KS>::TQ), p.N, p.B);
+  rel_attention_fwd_mma_kernel<KS><<<grid, 128, smem, stream>>>(p, ctx, probs);
+  count_launch();
+  return check_launch();
+}
+
+// ================================================================================================ tensor-core backward, rows
+// Same CTA shape as the forward.  Per warp (16 query rows):
+//   pass 1  dP = dO . V^T tile by tile, delta_i = sum_j P_ij dP_ij        (P rows staged in SMEM; dP never stored)
+//   pass 2  dP again (recomputed: 3 MMAs per tile are cheaper than 128 registers or an FP32 scratch), dS = P (dP - delta), masked -> 0;
+//           bf16 dS -> HBM (for the column kernel), in place over P, and skewed (column j + 15 - i) for the positional product
+//   dQ = scale-folded:  dS . K  +  dS_skewed . Pos[window]     (K and Pos through ldmatrix.trans);  du / dvb = column sums
+__host__ __device__ inline int att_mma_ps(int T) { return att_mma_tk(T) + 8; }    // bf16 row stride of the P / dS buffer
+__host__ __device__ inline int att_mma_qs(int T) { return att_mma_tk(T) + 24; }   // bf16 row stride of the skewed dS buffer
+
+template <int KS>
+static size_t att_mma_bwd_rows_smem(int T) {
+  using C = AttMma<KS>;
+  const int Tk = att_mma_tk(T);
+  size_t b = (size_t)(C::TQ + 2 * Tk + att_mma_pw(T)) * C::HS * 2;
+  b += (size_t)4 * 16 * (att_mma_ps(T) + att_mma_qs(T)) * 2;
+  b = align_up(b, 16);
+  b += 2 * 64 * sizeof(float);
+  return b;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(128) rel_attention_bwd_rows_mma_kernel(const AttParams p, const __nv_bfloat16* __restrict__ probs,
+                                                                         const __nv_bfloat16* __restrict__ dctx,
+                                                                         __nv_bfloat16* __restrict__ ds_out, __nv_bfloat16* __restrict__ dqkv,
+                                                                         float* __restrict__ du, float* __restrict__ dvb) {
+  using C = AttMma<KS>;
+  constexpr int HS = C::HS;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  const int T = p.T, H = p.H, NH = p.N * p.H, R = p.R;
+  const int b = blockIdx.z, n = blockIdx.y, t0 = blockIdx.x * C::TQ;
+  const int Tk = att_mma_tk(T), PW = att_mma_pw(T), PS = att_mma_ps(T), QS = att_mma_qs(T);
+  __nv_bfloat16* sdO = reinterpret_cast<__nv_bfloat16*>(att_smem);
+  __nv_bfloat16* sK = sdO + C::TQ * HS;
+  __nv_bfloat16* sV = sK + (size_t)Tk * HS;
+  __nv_bfloat16* sP = sV + (size_t)Tk * HS;
+  __nv_bfloat16* sPr = sP + (size_t)PW * HS;           // [4][16][PS]  P then dS
+  __nv_bfloat16* sSk = sPr + (size_t)4 * 16 * PS;      // [4][16][QS]  skewed dS
+  float* sAcc = reinterpret_cast<float*>(att_smem + align_up((size_t)((C::TQ + 2 * Tk + PW) * HS + 4 * 16 * (PS + QS)) * 2, 16));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int len = p.length ? p.length[b] : T;
+  const int r_lo = T - 1 - (t0 + C::TQ - 1);
+  const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+  {
+    constexpr int HP2 = KS * 8;
+    for (int i = threadIdx.x; i < Tk * HP2; i += 128) {
+      const int j = i / HP2, h2 = i % HP2;
+      __nv_bfloat162 kk = z2, vv = z2;
+      if (j < T && 2 * h2 < H) {
+        const size_t gidx = ((size_t)b * T + j) * p.ld_qkv + (size_t)n * H + 2 * h2;
+        kk = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + gidx + NH);
+        vv = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + gidx + 2 * NH);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(sK + j * HS + 2 * h2) = kk;
+      *reinterpret_cast<__nv_bfloat162*>(sV + j * HS + 2 * h2) = vv;
+    }
+    for (int i = threadIdx.x; i < PW * HP2; i += 128) {
+      const int rr = i / HP2, h2 = i % HP2;
+      const int r = r_lo + rr;
+      __nv_bfloat162 v = z2;
+      if (r >= 0 && r < R && 2 * h2 < H) v = *reinterpret_cast<const __nv_bfloat162*>(p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 2 * h2);
+      *reinterpret_cast<__nv_bfloat162*>(sP + rr * HS + 2 * h2) = v;
+    }
+    for (int i = threadIdx.x; i < C::TQ * HP2; i += 128) {
+      const int rr = i / HP2, h2 = i % HP2;
+      const int t = t0 + rr;
+      __nv_bfloat162 v = z2;
+      if (t < T && 2 * h2 < H) v = *reinterpret_cast<const __nv_bfloat162*>(dctx + ((size_t)b * T + t) * NH + (size_t)n * H + 2 * h2);
+      *reinterpret_cast<__nv_bfloat162*>(sdO + rr * HS + 2 * h2) = v;
+    }
+    for (int i = threadIdx.x; i < 128; i += 128) sAcc[i] = 0.f;
+  }
+  const int tw = t0 + warp * 16;
+  __nv_bfloat16* myP = sPr + (size_t)warp * 16 * PS;
+  __nv_bfloat16* myS = sSk + (size_t)warp * 16 * QS;
+  const __nv_bfloat16* pbase = probs + ((size_t)b * p.N + n) * T * T;
+  {  // this warp's probability rows (zero beyond T) and a cleared skew buffer
+    for (int i = 0; i < 16; ++i) {
+      const int t = tw + i;
+      const __nv_bfloat16* prow = pbase + (size_t)min(t, T - 1) * T;
+      if ((T & 1) == 0) {
+        for (int j2 = lane; j2 < PS / 2; j2 += 32) {
+          __nv_bfloat162 v = z2;
+          if (t < T && 2 * j2 < T) v = *reinterpret_cast<const __nv_bfloat162*>(prow + 2 * j2);
+          *reinterpret_cast<__nv_bfloat162*>(myP + i * PS + 2 * j2) = v;
+        }
+      } else {
+        for (int j = lane; j < PS; j += 32) myP[i * PS + j] = (t < T && j < T) ? prow[j] : __float2bfloat16(0.f);
+      }
+      for (int j2 = lane; j2 < QS / 2; j2 += 32) *reinterpret_cast<__nv_bfloat162*>(myS + i * QS + 2 * j2) = z2;
+    }
+  }
+  __syncthreads();
+  float accC[KS * 2][4], accP[KS * 2][4];
+#pragma unroll
+  for (int nh = 0; nh < KS * 2; ++nh) {
+    accC[nh][0] = accC[nh][1] = accC[nh][2] = accC[nh][3] = 0.f;
+    accP[nh][0] = accP[nh][1] = accP[nh][2] = accP[nh][3] = 0.f;
+  }
+  if (tw < T) {
+    uint32_t ado[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) mma::ldsm_x4(ado[ks], sdO + (warp * 16 + (lane & 15)) * HS + ks * 16 + (lane >> 4) * 8);
+    const int i0 = g, i1 = g + 8;
+    const int tA = tw + i0, tB = tw + i1;
+    // ---- pass 1: delta
+    float d0 = 0.f, d1 = 0.f;
+    for (int nt = 0; nt < Tk / 8; ++nt) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bfr[2];
+        mma::ldsm_x2(bfr, sV + (nt * 8 + (lane & 7)) * HS + ks * 16 + ((lane >> 3) & 1) * 8);
+        mma::mma_16816(acc, ado[ks], bfr);
+      }
+      const int j0 = nt * 8 + 2 * tq;
+      const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(myP + i0 * PS + j0);
+      const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(myP + i1 * PS + j0);
+      d0 = fmaf(__low2float(pa), acc[0], fmaf(__high2float(pa), acc[1], d0));
+      d1 = fmaf(__low2float(pb), acc[2], fmaf(__high2float(pb), acc[3], d1));
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    // ---- pass 2: dS
+    __nv_bfloat16* dsA = ds_out + (((size_t)b * p.N + n) * T + min(tA, T - 1)) * T;
+    __nv_bfloat16* dsB = ds_out + (((size_t)b * p.N + n) * T + min(tB, T - 1)) * T;
+    for (int nt = 0; nt < Tk / 8; ++nt) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bfr[2];
+        mma::ldsm_x2(bfr, sV + (nt * 8 + (lane & 7)) * HS + ks * 16 + ((lane >> 3) & 1) * 8);
+        mma::mma_16816(acc, ado[ks], bfr);
+      }
+      const int j0 = nt * 8 + 2 * tq;
+      const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(myP + i0 * PS + j0);
+      const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(myP + i1 * PS + j0);
+      float s00 = __low2float(pa) * (acc[0] - d0), s01 = __high2float(pa) * (acc[1] - d0);
+      float s10 = __low2float(pb) * (acc[2] - d1), s11 = __high2float(pb) * (acc[3] - d1);
+      if (!att_allowed(tA, j0, len, T, p.chunk, p.history)) s00 = 0.f;  // masked scores are constants
+      if (!att_allowed(tA, j0 + 1, len, T, p.chunk, p.history)) s01 = 0.f;
+      if (!att_allowed(tB, j0, len, T, p.chunk, p.history)) s10 = 0.f;
+      if (!att_allowed(tB, j0 + 1, len, T, p.chunk, p.history)) s11 = 0.f;
+      const __nv_bfloat162 da = __floats2bfloat162_rn(s00, s01), db = __floats2bfloat162_rn(s10, s11);
+      *reinterpret_cast<__nv_bfloat162*>(myP + i0 * PS + j0) = da;
+      *reinterpret_cast<__nv_bfloat162*>(myP + i1 * PS + j0) = db;
+      myS[i0 * QS + j0 + 15 - i0] = __low2bfloat16(da);
+      myS[i0 * QS + j0 + 16 - i0] = __high2bfloat16(da);
+      myS[i1 * QS + j0 + 15 - i1] = __low2bfloat16(db);
+      myS[i1 * QS + j0 + 16 - i1] = __high2bfloat16(db);
+      if (tA < T) {
+        if (j0 < T) dsA[j0] = __low2bfloat16(da);
+        if (j0 + 1 < T) dsA[j0 + 1] = __high2bfloat16(da);
+      }
+      if (tB < T) {
+        if (j0 < T) dsB[j0] = __low2bfloat16(db);
+        if (j0 + 1 < T) dsB[j0 + 1] = __high2bfloat16(db);
+      }
+    }
+    __syncwarp();
+    // ---- dQ (content): dS . K
+    for (int kt = 0; kt < Tk / 16; ++kt) {
+      uint32_t afr[4];
+      mma::ldsm_x4(afr, myP + (lane & 15) * PS + kt * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int nh = 0; nh < KS * 2; ++nh) {
+        uint32_t bfr[2];
+        mma::ldsm_x2_trans(bfr, sK + (kt * 16 + (lane & 15)) * HS + nh * 8);
+        mma::mma_16816(accC[nh], afr, bfr);
+      }
+    }
+    // ---- dQ (positional): dS_skewed . Pos[window]
+    const int rr0 = (C::TQ - 16) - warp * 16;
+    const int nkt = (T + 15 + 15) / 16;
+    for (int kt = 0; kt < nkt; ++kt) {
+      uint32_t afr[4];
+      mma::ldsm_x4(afr, myS + (lane & 15) * QS + kt * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int nh = 0; nh < KS * 2; ++nh) {
+        uint32_t bfr[2];
+        mma::ldsm_x2_trans(bfr, sP + (rr0 + kt * 16 + (lane & 15)) * HS + nh * 8);
+        mma::mma_16816(accP[nh], afr, bfr);
+      }
+    }
+    // scores were computed from (q+u)*scale, (q+v)*scale: no extra factor on dq (the scale is in K-side gradients through Qu, Qv)
+#pragma unroll
+    for (int nh = 0; nh < KS * 2; ++nh) {
+      const int h = nh * 8 + 2 * tq;
+      if (h < H) {
+        if (tA < T)
+          *reinterpret_cast<__nv_bfloat162*>(dqkv + ((size_t)b * T + tA) * p.ld_qkv + (size_t)n * H + h) =
+              __floats2bfloat162_rn((accC[nh][0] + accP[nh][0]) * p.scale, (accC[nh][1] + accP[nh][1]) * p.scale);
+        if (tB < T)
+          *reinterpret_cast<__nv_bfloat162*>(dqkv + ((size_t)b * T + tB) * p.ld_qkv + (size_t)n * H + h) =
+              __floats2bfloat162_rn((accC[nh][2] + accP[nh][2]) * p.scale, (accC[nh][3] + accP[nh][3]) * p.scale);
+      }
+    }
+  }
+  // ---- du / dvb: column sums over the CTA's rows (rows >= T contribute exact zeros)
+#pragma unroll
+  for (int nh = 0; nh < KS * 2; ++nh) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float c = accC[nh][e] + accC[nh][e + 2], q = accP[nh][e] + accP[nh][e + 2];
+#pragma unroll
+      for (int m = 4; m <= 16; m <<= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, m);
+        q += __shfl_xor_sync(0xffffffffu, q, m);
+      }
+      const int h = nh * 8 + 2 * tq + e;
+      if (g == 0 && h < H) {
+        atomicAdd(&sAcc[h], c * p.scale);
+        atomicAdd(&sAcc[64 + h], q * p.scale);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += 128) {
+    atomicAdd(du + n * H + i, sAcc[i]);
+    atomicAdd(dvb + n * H + i, sAcc[64 + i]);
+  }
+}
+
+// ================================================================================================ tensor-core backward, columns
+// One CTA (16 warps) per (utterance, head) streams P and dS once, 16 query rows at a time, double-buffered in SMEM:
+//   dV[j]  += P^T  . dO        warp w owns keys 16w .. 16w+15        (A = P block through ldmatrix.trans)
+//   dK[j]  += dS^T . (q+u)s
+//   dPos[r] += dS_skew^T . (q+v)s   with r = 16 (q0 - blk) + c',  c' = j + 15 - i + rem:   the diagonal gather of the rel-shift becomes
+//                                   a block-constant row offset, so warp w accumulates position rows 32w .. 32w+31 in registers.
+template <int KS>
+struct AttCols {
+  static constexpr int HS = AttMma<KS>::HS;
+  static constexpr int THREADS = 512;
+};
+__host__ __device__ inline int att_cols_qs(int T) { return att_mma_tk(T) + 32 + 8; }
+
+template <int KS>
+static size_t att_mma_bwd_cols_smem(int T) {
+  return (size_t)2 * 16 * (2 * att_mma_ps(T) + att_cols_qs(T) + 3 * AttMma<KS>::HS) * 2;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(512) rel_attention_bwd_cols_mma_kernel(const AttParams p, const __nv_bfloat16* __restrict__ probs,
+                                                                         const __nv_bfloat16* __restrict__ ds,
+                                                                         const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv,
+                                                                         __nv_bfloat16* __restrict__ dpos) {
+  constexpr int HS = AttMma<KS>::HS;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  const int T = p.T, H = p.H, NH = p.N * p.H, R = p.R;
+  const int b = blockIdx.y, n = blockIdx.x;
+  const int Tk = att_mma_tk(T), PS = att_mma_ps(T), QS = att_cols_qs(T);
+  const int stage_elems = 16 * (2 * PS + QS + 3 * HS);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int q0 = (T - 16) / 16, rem = (T - 16) % 16;  // T >= 16
+  const int nct = (rem + T + 15 + 15) / 16;           // 16-wide tiles of the skewed coordinate c'
+  const int nblk = Tk / 16;
+  const __nv_bfloat16* pbase = probs + ((size_t)b * p.N + n) * T * T;
+  const __nv_bfloat16* dbase = ds + ((size_t)b * p.N + n) * T * T;
+  const __nv_bfloat16 z1 = __float2bfloat16(0.f);
+  const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+
+  auto stage = [&](int blk, int buf) {
+    __nv_bfloat16* sPb = reinterpret_cast<__nv_bfloat16*>(att_smem) + (size_t)buf * stage_elems;
+    __nv_bfloat16* sDb = sPb + 16 * PS;
+    __nv_bfloat16* sSk = sDb + 16 * PS;
+    __nv_bfloat16* sQu = sSk + 16 * QS;
+    __nv_bfloat16* sQv = sQu + 16 * HS;
+    __nv_bfloat16* sdO = sQv + 16 * HS;
+    const int tb = blk * 16;
+    if ((T & 1) == 0) {
+      const int PS2 = PS / 2;
+      for (int i = threadIdx.x; i < 16 * PS2; i += 512) {
+        const int r = i / PS2, j2 = i % PS2;
+        const int t = tb + r;
+        __nv_bfloat162 a = z2, d = z2;
+        if (t < T && 2 * j2 < T) {
+          a = *reinterpret_cast<const __nv_bfloat162*>(pbase + (size_t)t * T + 2 * j2);
+          d = *reinterpret_cast<const __nv_bfloat162*>(dbase + (size_t)t * T + 2 * j2);
+        }
+        *reinterpret_cast<__nv_bfloat162*>(sPb + r * PS + 2 * j2) = a;
+        *reinterpret_cast<__nv_bfloat162*>(sDb + r * PS + 2 * j2) = d;
+      }
+    } else {
+      for (int i = threadIdx.x; i < 16 * PS; i += 512) {
+        const int r = i / PS, j = i % PS;
+        const int t = tb + r;
+        const bool ok = t < T && j < T;
+        sPb[r * PS + j] = ok ? pbase[(size_t)t * T + j] : z1;
+        sDb[r * PS + j] = ok ? dbase[(size_t)t * T + j] : z1;
+      }
+    }
+    for (int i = threadIdx.x; i < 16 * QS; i += 512) {
+      const int r = i / QS, c = i % QS;
+      const int t = tb + r, j = c - 15 + r - rem;
+      sSk[r * QS + c] = (t < T && j >= 0 && j < T) ? dbase[(size_t)t * T + j] : z1;
+    }
+    constexpr int HP2 = KS * 8;
+    for (int i = threadIdx.x; i < 16 * HP2; i += 512) {
+      const int r = i / HP2, h2 = i % HP2;
+      const int t = tb + r;
+      __nv_bfloat162 qu = z2, qv = z2, dd = z2;
+      if (t < T && 2 * h2 < H) {
+        const __nv_bfloat162 q = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + ((size_t)b * T + t) * p.ld_qkv + (size_t)n * H + 2 * h2);
+        const float qa = __low2float(q), qb = __high2float(q);
+        const float* ub = p.ubias + n * H + 2 * h2;
+        const float* vb = p.vbias + n * H + 2 * h2;
+        qu = __floats2bfloat162_rn((qa + ub[0]) * p.scale, (qb + ub[1]) * p.scale);
+        qv = __floats2bfloat162_rn((qa + vb[0]) * p.scale, (qb + vb[1]) * p.scale);
+        dd = *reinterpret_cast<const __nv_bfloat162*>(dctx + ((size_t)b * T + t) * NH + (size_t)n * H + 2 * h2);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(sQu + r * HS + 2 * h2) = qu;
+      *reinterpret_cast<__nv_bfloat162*>(sQv + r * HS + 2 * h2) = qv;
+      *reinterpret_cast<__nv_bfloat162*>(sdO + r * HS + 2 * h2) = dd;
+    }
+  };
+
+  float aV[KS * 2][4], aK[KS * 2][4], aP[2][KS * 2][4];
+#pragma unroll
+  for (int nh = 0; nh < KS * 2; ++nh)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) aV[nh][e] = aK[nh][e] = aP[0][nh][e] = aP[1][nh][e] = 0.f;
+
+  stage(0, 0);
+  __syncthreads();
+  const int ak = (lane & 7) + (lane >> 4) * 8;   // ldmatrix.trans A: source row (k)
+  const int am = ((lane >> 3) & 1) * 8;          // and column offset (m)
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int buf = blk & 1;
+    if (blk + 1 < nblk) stage(blk + 1, buf ^ 1);
+    const __nv_bfloat16* sPb = reinterpret_cast<const __nv_bfloat16*>(att_smem) + (size_t)buf * stage_elems;
+    const __nv_bfloat16* sDb = sPb + 16 * PS;
+    const __nv_bfloat16* sSk = sDb + 16 * PS;
+    const __nv_bfloat16* sQu = sSk + 16 * QS;
+    const __nv_bfloat16* sQv = sQu + 16 * HS;
+    const __nv_bfloat16* sdO = sQv + 16 * HS;
+    if (warp < nblk) {
+      uint32_t afp[4], afd[4];
+      mma::ldsm_x4_trans(afp, sPb + ak * PS + warp * 16 + am);
+      mma::ldsm_x4_trans(afd, sDb + ak * PS + warp * 16 + am);
+#pragma unroll
+      for (int nh = 0; nh < KS * 2; ++nh) {
+        uint32_t bo[2], bq[2];
+        mma::ldsm_x2_trans(bo, sdO + (lane & 15) * HS + nh * 8);
+        mma::ldsm_x2_trans(bq, sQu + (lane & 15) * HS + nh * 8);
+        mma::mma_16816(aV[nh], afp, bo);
+        mma::mma_16816(aK[nh], afd, bq);
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int ct = (2 * warp + mi) - q0 + blk;  // skewed-coordinate tile feeding position rows 16 (2w + mi) ..
+      if (ct >= 0 && ct < nct) {
+        uint32_t afs[4];
+        mma::ldsm_x4_trans(afs, sSk + ak * QS + ct * 16 + am);
+#pragma unroll
+        for (int nh = 0; nh < KS * 2; ++nh) {
+          uint32_t bq[2];
+          mma::ldsm_x2_trans(bq, sQv + (lane & 15) * HS + nh * 8);
+          mma::mma_16816(aP[mi][nh], afs, bq);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- outputs
+#pragma unroll
+  for (int nh = 0; nh < KS * 2; ++nh) {
+    const int h = nh * 8 + 2 * tq;
+    if (h >= H) continue;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j = warp * 16 + g + half * 8;
+      if (j < T) {
+        __nv_bfloat16* row = dqkv + ((size_t)b * T + j) * p.ld_qkv + (size_t)n * H + h;
+        *reinterpret_cast<__nv_bfloat162*>(row + NH) = __floats2bfloat162_rn(aK[nh][2 * half], aK[nh][2 * half + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(row + 2 * NH) = __floats2bfloat162_rn(aV[nh][2 * half], aV[nh][2 * half + 1]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int r = (2 * warp + mi) * 16 + g + half * 8;
+        if (r < R)
+          *reinterpret_cast<__nv_bfloat162*>(dpos + ((size_t)b * R + r) * NH + (size_t)n * H + h) =
+              __floats2bfloat162_rn(aP[mi][nh][2 * half], aP[mi][nh][2 * half + 1]);
+      }
+    }
+  }
+}
+
+template <int KS>
+static int launch_att_bwd_mma(const AttParams& p, const __nv_bfloat16* probs, const __nv_bfloat16* dctx, __nv_bfloat16* ds_ws,
+                              __nv_bfloat16* dqkv, __nv_bfloat16* dpos, float* du, float* dvb, cudaStream_t stream) {
+  const size_t smem1 = att_mma_bwd_rows_smem<KS>(p.T), smem2 = att_mma_bwd_cols_smem<KS>(p.T);
+  if (smem1 > 227 * 1024 || smem2 > 227 * 1024 || p.T > 256 || p.T < 16) return -1;
+  if (cudaFuncSetAttribute(rel_attention_bwd_rows_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(rel_attention_bwd_cols_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return TFASR_EXECUTION_FAILED;
+  dim3 grid((unsigned)ceil_div(p.T, AttMma<KS>::TQ), p.N, p.B);
+  rel_attention_bwd_rows_mma_kernel<KS><<<grid, 128, smem1, stream>>>(p, probs, dctx, ds_ws, dqkv, du, dvb);
+  count_launch();
+  dim3 grid2(p.N, p.B);
+  rel_attention_bwd_cols_mma_kernel<KS><<<grid2, 512, smem2, stream>>>(p, probs, ds_ws, dctx, dqkv, dpos);
+  count_launch();
+  return check_launch();
+}
+
 static size_t att_rows_smem(int T, int H, bool bwd) {
   const int S = ((H + 2) | 2);
   size_t bytes = (size_t)(2 * T + T + kAttTQ - 1) * S * 2;
@@ -388,6 +1017,16 @@ extern "C" int tfasr_rel_attention_fwd(const void* qkv, int32_t ld_qkv, const vo
   if (st || !ctx || !probs) return st ? st : TFASR_INVALID_VALUE;
   if (B == 0) return TFASR_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  {
+    // tensor-core path when the operands fit in SMEM (T <= ~256 at H <= 48); otherwise the FP32 kernel below
+    int r = -1;
+    const int ks = (H + 15) / 16;
+    if (ks <= 1) r = launch_att_fwd_mma<1>(p, static_cast<__nv_bfloat16*>(ctx), static_cast<__nv_bfloat16*>(probs), stream);
+    else if (ks == 2) r = launch_att_fwd_mma<2>(p, static_cast<__nv_bfloat16*>(ctx), static_cast<__nv_bfloat16*>(probs), stream);
+    else if (ks == 3) r = launch_att_fwd_mma<3>(p, static_cast<__nv_bfloat16*>(ctx), static_cast<__nv_bfloat16*>(probs), stream);
+    else if (ks == 4) r = launch_att_fwd_mma<4>(p, static_cast<__nv_bfloat16*>(ctx), static_cast<__nv_bfloat16*>(probs), stream);
+    if (r >= 0) return r;
+  }
   const size_t smem = att_rows_smem(T, H, false);
   if (smem > 220 * 1024) return TFASR_INVALID_VALUE;
   dim3 grid((unsigned)ceil_div(T, kAttTQ), N, B);
@@ -411,6 +1050,20 @@ extern "C" int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const vo
   if (st || !probs || !dctx || !ds_ws || !dqkv || !dpos || !du || !dvb) return st ? st : TFASR_INVALID_VALUE;
   if (B == 0) return TFASR_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  {
+    int r = -1;
+    const int ks = (H + 15) / 16;
+#define BWD_MMA(KS_)                                                                                                                  \
+  r = launch_att_bwd_mma<KS_>(p, static_cast<const __nv_bfloat16*>(probs), static_cast<const __nv_bfloat16*>(dctx),                   \
+                              static_cast<__nv_bfloat16*>(ds_ws), static_cast<__nv_bfloat16*>(dqkv), static_cast<__nv_bfloat16*>(dpos), \
+                              du, dvb, stream)
+    if (ks <= 1) BWD_MMA(1);
+    else if (ks == 2) BWD_MMA(2);
+    else if (ks == 3) BWD_MMA(3);
+    else if (ks == 4) BWD_MMA(4);
+#undef BWD_MMA
+    if (r >= 0) return r;
+  }
   const size_t smem = att_rows_smem(T, H, true);
   if (smem > 220 * 1024) return TFASR_INVALID_VALUE;
   dim3 grid((unsigned)ceil_div(T, kAttTQ), N, B);

@@ -304,7 +304,7 @@ class ConformerEncoder(_Params):
         m = pre + ".mhsa"
         if ops.fused_active(x):
             # LN, the fused Q|K|V projection, the position projection and the output projection (+ dropout + residual) run on the
-            # tcgen05 GEMM / fused row kernels; the attention core itself is still the LIBRARY path (ops.rel_attention).
+            # tcgen05 GEMM / fused row kernels; the attention core on the mma.sync kernels of csrc/attention.cu.
             B, T, _ = x.shape
             NH = N * H
             p = self.dropout if training else 0.0
@@ -312,11 +312,11 @@ class ConformerEncoder(_Params):
             seed = fused.STATE.seed_tensor(x.device)
             x2 = x.reshape(B * T, D).to(torch.bfloat16)
             a = fused.layer_norm(x2, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
-            qkv = fused.linear(a, pk.qkv).view(B, T, 3 * NH)
-            pos = fused.linear(relpe.reshape(-1, D).to(torch.bfloat16).contiguous(), pk.pos).view(B, -1, NH)
-            ctx = ops.rel_attention(qkv[..., :NH], qkv[..., NH:2 * NH], qkv[..., 2 * NH:], pos, self["content_attention_bias"],
-                                    self["positional_attention_bias"], length, N, H, chunk_size=self.chunk_size, history_size=self.history_size)
-            y = fused.linear(ctx.reshape(B * T, NH).contiguous(), pk.out, residual=x2, factor=self.mhsam_residual_factor, drop_p=p,
+            qkv = fused.linear(a, pk.qkv)
+            pos = fused.linear(relpe.reshape(-1, D).to(torch.bfloat16).contiguous(), pk.pos)
+            ctx = fused.rel_attention(qkv, pos, self["content_attention_bias"], self["positional_attention_bias"], length.to(torch.int32),
+                                      B, T, N, H, self.chunk_size, self.history_size)
+            y = fused.linear(ctx, pk.out, residual=x2, factor=self.mhsam_residual_factor, drop_p=p,
                              salt=self._salt(pre, 0), seed=seed)
             return y.view(B, T, D)
         y = ops.layer_norm(x, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])

@@ -410,6 +410,30 @@ class MhsaPack:
         self.out.param = enc[f"{m}.attention_output.kernel"]
 
 
+class _RelAttentionFn(torch.autograd.Function):
+    """Relative-position attention core (multihead_attention.py:543-582) on the tensor-core kernels of csrc/attention.cu.
+    qkv [B*T, 3NH] bf16 (output of the fused projection), pos [B*R, NH] bf16 -> ctx [B*T, NH] bf16."""
+
+    @staticmethod
+    def forward(ctx, qkv, pos, u, v, length, B, T, N, H, chunk, history):
+        out, probs = kernels.rel_attention_fwd(qkv, pos, u.detach(), v.detach(), length, B, T, N, H, chunk, history)
+        ctx.save_for_backward(qkv, pos, probs, length)
+        ctx.misc = (u, v, B, T, N, H, chunk, history)
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        qkv, pos, probs, length = ctx.saved_tensors
+        u, v, B, T, N, H, chunk, history = ctx.misc
+        dqkv, dpos = kernels.rel_attention_bwd(qkv, pos, u.detach(), v.detach(), length, B, T, N, H, probs, dctx.contiguous(), _grad(u), _grad(v),
+                                               chunk, history)
+        return dqkv, dpos, None, None, None, None, None, None, None, None, None
+
+
+def rel_attention(qkv, pos, u, v, length, B, T, N, H, chunk=None, history=None):
+    return _RelAttentionFn.apply(qkv, pos, u, v, length, B, T, N, H, chunk, history)
+
+
 # ------------------------------------------------------------------------------------------------ ConvModule
 class GluPack(WeightPack):
     """pw_conv_1 [D, 2D] with its GLU halves interleaved column-wise (a_0, b_0, a_1, b_1, ...) so that the GEMM epilogue applies

@@ -248,7 +248,8 @@ def test_subsampling_kernels_vs_torch():
     _close(beta.grad, b2.grad, 5e-3)
 
 
-@pytest.mark.parametrize("cfg", [(3, 50, 4, 36, None, None), (2, 37, 2, 16, 4, 8), (1, 250, 4, 36, None, None)])
+@pytest.mark.parametrize("cfg", [(3, 50, 4, 36, None, None), (2, 37, 2, 16, 4, 8), (1, 250, 4, 36, None, None), (2, 64, 2, 64, None, None),
+                                 (2, 129, 3, 36, 16, 32), (1, 300, 2, 36, None, None), (2, 9, 2, 36, None, None), (3, 250, 4, 36, 32, 64)])
 def test_rel_attention_kernels_vs_torch(cfg):
     """Fused relative-position attention fwd/bwd vs the torch restatement (ops.rel_attention) in fp32 on the same bf16 inputs."""
     from tensorflowasr_b200 import kernels, ops
