@@ -183,14 +183,15 @@ int tfasr_joint_reduce_bwd(const void* dz, float* de, float* dp, int32_t B, int3
  *   qkv  [B*T, ld_qkv] bf16: q at column n*H, k at N*H + n*H, v at 2*N*H + n*H      pos [B*(2T-1), N*H] bf16 (projected relpe)
  *   ubias / vbias [N, H] f32 (content / positional attention bias)                   length [B] i32 or NULL (query-side mask)
  *   fwd:  ctx [B*T, N*H] bf16, probs [B, N, T, T] bf16 (kept for backward)
- *   bwd:  dqkv [B*T, ld_qkv] bf16, dpos [B*(2T-1), N*H] bf16 (written), du / dvb [N, H] f32 (accumulated); ds_ws [B,N,T,T] bf16 scratch
+ *   bwd:  ctx = the forward's output (delta = dctx . ctx; NULL selects the FP32 kernels that sum P dP instead);
+ *         dqkv [B*T, ld_qkv] bf16, dpos [B*(2T-1), N*H] bf16 (written), du / dvb [N, H] f32 (accumulated); ds_ws [B,N,T,T] bf16 scratch
  * ---------------------------------------------------------------------------------------------- */
 int tfasr_rel_attention_fwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias, const int32_t* length,
                             int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, void* ctx, void* probs,
                             tfasr_stream_t stream);
 int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias, const int32_t* length,
                             int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, const void* probs, const void* dctx,
-                            void* ds_ws, void* dqkv, void* dpos, float* du, float* dvb, tfasr_stream_t stream);
+                            const void* ctx, void* ds_ws, void* dqkv, void* dpos, float* du, float* dvb, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv2dSubsampling pieces and BatchNorm (+ swish), channels-last bf16 (subsampling.py:163-230, convolution.py:25-37,132-144;

@@ -334,201 +334,253 @@ __global__ void __launch_bounds__(64) rel_attention_bwd_cols_kernel(const AttPar
 }
 
 // ================================================================================================ tensor-core forward
-// One CTA = (utterance b, head n, 64 query rows); 4 warps x 16 rows.  K, V, the position-table window and (q+u), (q+v) live in SMEM as
-// bf16 with a row stride that is an odd multiple of 16 bytes (conflict-free ldmatrix).  Per warp:
-//   A  positional block  S_pos[16 x (T+15)] = Qv . Pos[window]^T  -> f32 scratch           (mma.sync)
-//   B  content tiles     S[16 x 8] = Qu . K^T + S_pos[i][j + 15 - i]  (the rel-shift is this index), mask -> scratch in place
-//   C  row softmax       -> bf16 probabilities to HBM (kept for backward) and in place into the scratch (A operand of D)
-//   D  O = P . V         (mma.sync, V through ldmatrix.trans) -> ctx
+// One CTA (16 warps) = one (utterance, head): all T <= 256 query rows, 16 per warp, so K, V and the projected position table are staged
+// once and four warps share every SM scheduler.  Operands live in SMEM as bf16 with a row stride that is an odd multiple of 16 bytes
+// (conflict-free ldmatrix).  Each warp walks the keys in chunks of 64, twice (row max / sum, then probabilities), recomputing the
+// scores instead of keeping a [16 x T] FP32 row buffer - the MMAs are cheap, SMEM and latency are not:
+//   positional block  S_pos[16 x 80] = Qv . Pos[window]^T  -> per-warp FP32 scratch            (mma.sync m16n8k16)
+//   content tiles     S[16 x 8] = Qu . K^T + S_pos[i][jl + 15 - i]   (the rel-shift is this read index), masks
+//   pass 2            P = exp(S - m) / l  -> bf16 to HBM (kept for backward) and, straight from the accumulator registers, the A operand
+//                     of O += P . V   (V through ldmatrix.trans)
 template <int KS>  // k-steps of 16 over the head dimension: H <= 16 * KS
 struct AttMma {
   static constexpr int HS = KS == 3 ? 56 : (KS == 4 ? 72 : (KS == 2 ? 40 : 24));  // bf16 row stride: odd multiple of 16 B
-  static constexpr int TQ = 64;
+  static constexpr int CH = 64;                                                    // keys per chunk
+  static constexpr int SCW = 84;                                                   // f32 scratch row stride (80 columns used)
+  static constexpr int SKW = 88;                                                   // bf16 skew-buffer row stride (backward)
 };
 
 __host__ __device__ inline int att_mma_tk(int T) { return (T + 15) / 16 * 16; }
-__host__ __device__ inline int att_mma_sw(int T) {  // f32 scratch row stride: >= Tk + 16 and (SW * 4) an odd multiple of 16 B
-  int sw = att_mma_tk(T) + 16;
-  while (((sw * 4) / 16) % 2 == 0 || (sw * 4) % 16) sw += 1;
-  return sw;
-}
-__host__ __device__ inline int att_mma_pw(int T) { return (T + 64 + 16 + 7) / 8 * 8; }
+__host__ __device__ inline int att_mma_tc(int T) { return (T + 63) / 64 * 64; }       // keys padded to whole chunks
+__host__ __device__ inline int att_mma_prow(int T) { return att_mma_tk(T) + att_mma_tc(T) + 16; }  // staged position-table rows
+__host__ __device__ inline int att_mma_ps(int T) { return att_mma_tk(T) + 8; }        // bf16 row stride of the P / dS blocks (columns kernel)
 
 template <int KS>
 static size_t att_mma_fwd_smem(int T) {
   using C = AttMma<KS>;
-  const int Tk = att_mma_tk(T);
-  size_t b = (size_t)(2 * C::TQ + 2 * Tk + att_mma_pw(T)) * C::HS * 2;
-  b = align_up(b, 16);
-  b += (size_t)4 * 16 * att_mma_sw(T) * 4;
-  return b;
+  const size_t kv = (size_t)2 * att_mma_tc(T) * C::HS * 2, pos = (size_t)att_mma_prow(T) * C::HS * 2;
+  const size_t q = (size_t)2 * att_mma_tk(T) * C::HS * 2, scratch = (size_t)16 * 16 * C::SCW * 4;
+  return kv + pos + (q > scratch ? q : scratch);
+}
+
+// 8-byte (4 x bf16) staging copies; H % 4 == 0 keeps every head slice 8-byte aligned (checked by the launcher)
+__device__ __forceinline__ uint2 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ void st8(__nv_bfloat16* p, uint2 v) { *reinterpret_cast<uint2*>(p) = v; }
+
+// K, V [Tc][HS] and the position window [prow][HS]: window row rr holds table row r = rr - (Tk - T)
+template <int KS>
+__device__ __forceinline__ void att_stage_kvp(const AttParams& p, int b, int n, __nv_bfloat16* sK, __nv_bfloat16* sV, __nv_bfloat16* sP,
+                                              bool want_v) {
+  constexpr int HS = AttMma<KS>::HS, HP4 = KS * 4;
+  const int T = p.T, H = p.H, NH = p.N * p.H, R = p.R;
+  const int Tk = att_mma_tk(T), Tc = att_mma_tc(T), PR = att_mma_prow(T);
+  const uint2 z = make_uint2(0u, 0u);
+  for (int i = threadIdx.x; i < Tc * HP4; i += blockDim.x) {
+    const int j = i / HP4, h4 = i % HP4;
+    uint2 kk = z, vv = z;
+    if (j < T && 4 * h4 < H) {
+      const __nv_bfloat16* g = p.qkv + ((size_t)b * T + j) * p.ld_qkv + (size_t)n * H + 4 * h4;
+      kk = ld8(g + NH);
+      if (want_v) vv = ld8(g + 2 * NH);
+    }
+    st8(sK + j * HS + 4 * h4, kk);
+    if (want_v) st8(sV + j * HS + 4 * h4, vv);
+  }
+  for (int i = threadIdx.x; i < PR * HP4; i += blockDim.x) {
+    const int rr = i / HP4, h4 = i % HP4;
+    const int r = rr - (Tk - T);
+    uint2 v = z;
+    if (r >= 0 && r < R && 4 * h4 < H) v = ld8(p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 4 * h4);
+    st8(sP + rr * HS + 4 * h4, v);
+  }
+}
+
+// (q + u) * scale and (q + v) * scale rows [Tk][HS], zero beyond T / H
+template <int KS>
+__device__ __forceinline__ void att_stage_q(const AttParams& p, int b, int n, __nv_bfloat16* sQu, __nv_bfloat16* sQv) {
+  constexpr int HS = AttMma<KS>::HS, HP2 = KS * 8;
+  const int T = p.T, H = p.H, Tk = att_mma_tk(T);
+  const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+  for (int i = threadIdx.x; i < Tk * HP2; i += blockDim.x) {
+    const int t = i / HP2, h2 = i % HP2;
+    __nv_bfloat162 qu = z2, qv = z2;
+    if (t < T && 2 * h2 < H) {
+      const __nv_bfloat162 q = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + ((size_t)b * T + t) * p.ld_qkv + (size_t)n * H + 2 * h2);
+      const float q0 = __low2float(q), q1 = __high2float(q);
+      const float* ub = p.ubias + n * H + 2 * h2;
+      const float* vb = p.vbias + n * H + 2 * h2;
+      qu = __floats2bfloat162_rn((q0 + ub[0]) * p.scale, (q1 + ub[1]) * p.scale);
+      qv = __floats2bfloat162_rn((q0 + vb[0]) * p.scale, (q1 + vb[1]) * p.scale);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(sQu + t * HS + 2 * h2) = qu;
+    *reinterpret_cast<__nv_bfloat162*>(sQv + t * HS + 2 * h2) = qv;
+  }
+}
+
+// Scores of this warp's 16 rows against keys [c0, c0 + 64): s[nt][0..1] row g, s[nt][2..3] row g + 8, columns c0 + 8 nt + 2 tq (+1).
+template <int KS>
+__device__ __forceinline__ void att_chunk_scores(float (&s)[8][4], const uint32_t (&aqu)[KS][4], const uint32_t (&aqv)[KS][4],
+                                                 const __nv_bfloat16* sK, const __nv_bfloat16* sP, float* scratch, int rr0, int c0, int lane,
+                                                 int tA, int tB, int len, const AttParams& p) {
+  constexpr int HS = AttMma<KS>::HS, SCW = AttMma<KS>::SCW;
+  const int g = lane >> 2, tq = lane & 3;
+  const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int nt = 0; nt < 10; ++nt) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t bfr[2];
+      mma::ldsm_x2(bfr, sP + (rr0 + c0 + nt * 8 + brow) * HS + ks * 16 + bcol);
+      mma::mma_16816(acc, aqv[ks], bfr);
+    }
+    *reinterpret_cast<float2*>(scratch + g * SCW + nt * 8 + 2 * tq) = make_float2(acc[0], acc[1]);
+    *reinterpret_cast<float2*>(scratch + (g + 8) * SCW + nt * 8 + 2 * tq) = make_float2(acc[2], acc[3]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t bfr[2];
+      mma::ldsm_x2(bfr, sK + (c0 + nt * 8 + brow) * HS + ks * 16 + bcol);
+      mma::mma_16816(acc, aqu[ks], bfr);
+    }
+    const int jl = nt * 8 + 2 * tq, j = c0 + jl;
+    const float* ra = scratch + g * SCW + jl + 15 - g;
+    const float* rb = scratch + (g + 8) * SCW + jl + 7 - g;
+    float s0 = acc[0] + ra[0], s1 = acc[1] + ra[1], s2 = acc[2] + rb[0], s3 = acc[3] + rb[1];
+    // masked_fill(-1e9) of general.py:30-41; padded key columns do not exist (-inf)
+    if (!att_allowed(tA, j, len, p.T, p.chunk, p.history)) s0 = -1e9f;
+    if (!att_allowed(tA, j + 1, len, p.T, p.chunk, p.history)) s1 = -1e9f;
+    if (!att_allowed(tB, j, len, p.T, p.chunk, p.history)) s2 = -1e9f;
+    if (!att_allowed(tB, j + 1, len, p.T, p.chunk, p.history)) s3 = -1e9f;
+    if (j >= p.T) s0 = s2 = -CUDART_INF_F;
+    if (j + 1 >= p.T) s1 = s3 = -CUDART_INF_F;
+    s[nt][0] = s0;
+    s[nt][1] = s1;
+    s[nt][2] = s2;
+    s[nt][3] = s3;
+  }
+  __syncwarp();  // the scratch is rewritten by the next chunk
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 template <int KS>
-__global__ void __launch_bounds__(128) rel_attention_fwd_mma_kernel(const AttParams p, __nv_bfloat16* __restrict__ ctx,
-                                                                    __nv_bfloat16* __restrict__ probs) {
+__global__ void __launch_bounds__(512, 1) rel_attention_fwd_mma_kernel(const AttParams p, __nv_bfloat16* __restrict__ ctx,
+                                                                       __nv_bfloat16* __restrict__ probs) {
   using C = AttMma<KS>;
   constexpr int HS = C::HS;
   extern __shared__ __align__(16) uint8_t att_smem[];
-  const int T = p.T, H = p.H, NH = p.N * p.H, R = p.R;
-  const int b = blockIdx.z, n = blockIdx.y, t0 = blockIdx.x * C::TQ;
-  const int Tk = att_mma_tk(T), SW = att_mma_sw(T), PW = att_mma_pw(T);
-  __nv_bfloat16* sQu = reinterpret_cast<__nv_bfloat16*>(att_smem);
-  __nv_bfloat16* sQv = sQu + C::TQ * HS;
-  __nv_bfloat16* sK = sQv + C::TQ * HS;
-  __nv_bfloat16* sV = sK + (size_t)Tk * HS;
-  __nv_bfloat16* sP = sV + (size_t)Tk * HS;
-  float* sS = reinterpret_cast<float*>(att_smem + align_up((size_t)(2 * C::TQ + 2 * Tk + PW) * HS * 2, 16));
+  const int T = p.T, H = p.H, NH = p.N * p.H;
+  const int b = blockIdx.y, n = blockIdx.x;
+  const int Tk = att_mma_tk(T), Tc = att_mma_tc(T);
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
+  __nv_bfloat16* sV = sK + (size_t)Tc * HS;
+  __nv_bfloat16* sP = sV + (size_t)Tc * HS;
+  uint8_t* U = reinterpret_cast<uint8_t*>(sP + (size_t)att_mma_prow(T) * HS);
+  __nv_bfloat16* sQu = reinterpret_cast<__nv_bfloat16*>(U);
+  __nv_bfloat16* sQv = sQu + (size_t)Tk * HS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tq = lane & 3;
   const int len = p.length ? p.length[b] : T;
-  const int r_lo = T - 1 - (t0 + C::TQ - 1);  // may be negative: rows below 0 are zero
-  // ---- stage operands (zero padded to 16 * KS columns)
-  {
-    constexpr int HP2 = KS * 8;  // bf16x2 per padded row
-    const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
-    for (int i = threadIdx.x; i < Tk * HP2; i += 128) {
-      const int j = i / HP2, h2 = i % HP2;
-      __nv_bfloat162 kk = z2, vv = z2;
-      if (j < T && 2 * h2 < H) {
-        const size_t gidx = ((size_t)b * T + j) * p.ld_qkv + (size_t)n * H + 2 * h2;
-        kk = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + gidx + NH);
-        vv = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + gidx + 2 * NH);
-      }
-      *reinterpret_cast<__nv_bfloat162*>(sK + j * HS + 2 * h2) = kk;
-      *reinterpret_cast<__nv_bfloat162*>(sV + j * HS + 2 * h2) = vv;
-    }
-    for (int i = threadIdx.x; i < PW * HP2; i += 128) {
-      const int rr = i / HP2, h2 = i % HP2;
-      const int r = r_lo + rr;
-      __nv_bfloat162 v = z2;
-      if (r >= 0 && r < R && 2 * h2 < H) v = *reinterpret_cast<const __nv_bfloat162*>(p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 2 * h2);
-      *reinterpret_cast<__nv_bfloat162*>(sP + rr * HS + 2 * h2) = v;
-    }
-    for (int i = threadIdx.x; i < C::TQ * HP2; i += 128) {
-      const int rr = i / HP2, h2 = i % HP2;
-      const int t = t0 + rr;
-      __nv_bfloat162 qu = z2, qv = z2;
-      if (t < T && 2 * h2 < H) {
-        const __nv_bfloat162 q = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + ((size_t)b * T + t) * p.ld_qkv + (size_t)n * H + 2 * h2);
-        const float q0 = __low2float(q), q1 = __high2float(q);
-        const float* ub = p.ubias + n * H + 2 * h2;
-        const float* vb = p.vbias + n * H + 2 * h2;
-        qu = __floats2bfloat162_rn((q0 + ub[0]) * p.scale, (q1 + ub[1]) * p.scale);
-        qv = __floats2bfloat162_rn((q0 + vb[0]) * p.scale, (q1 + vb[1]) * p.scale);
-      }
-      *reinterpret_cast<__nv_bfloat162*>(sQu + rr * HS + 2 * h2) = qu;
-      *reinterpret_cast<__nv_bfloat162*>(sQv + rr * HS + 2 * h2) = qv;
-    }
-  }
+  att_stage_kvp<KS>(p, b, n, sK, sV, sP, true);
+  att_stage_q<KS>(p, b, n, sQu, sQv);
   __syncthreads();
-  const int tw = t0 + warp * 16;  // first query row of this warp
-  if (tw >= T) return;
-  float* myS = sS + (size_t)warp * 16 * SW;
-  // A fragments of (q+u) and (q+v): rows warp*16 .. +15
+  const int tw = warp * 16;
+  const bool active = tw < T;
   uint32_t aqu[KS][4], aqv[KS][4];
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    const int rrow = warp * 16 + (lane & 15), col = ks * 16 + (lane >> 4) * 8;
-    mma::ldsm_x4(aqu[ks], sQu + rrow * HS + col);
-    mma::ldsm_x4(aqv[ks], sQv + rrow * HS + col);
-  }
-  // ---- A: positional block.  Window row of this warp's first needed position: r = T-1-(tw+15) -> rr0 = r - r_lo = 48 - 16*warp
-  const int rr0 = (C::TQ - 16) - warp * 16;
-  const int npos_tiles = (T + 15 + 7) / 8;
-  for (int nt = 0; nt < npos_tiles; ++nt) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      uint32_t bfr[2];
-      mma::ldsm_x2(bfr, sP + (rr0 + nt * 8 + (lane & 7)) * HS + ks * 16 + ((lane >> 3) & 1) * 8);
-      mma::mma_16816(acc, aqv[ks], bfr);
-    }
-    float* d0 = myS + (size_t)g * SW + nt * 8 + 2 * tq;
-    float* d1 = myS + (size_t)(g + 8) * SW + nt * 8 + 2 * tq;
-    d0[0] = acc[0];
-    d0[1] = acc[1];
-    d1[0] = acc[2];
-    d1[1] = acc[3];
-  }
-  __syncwarp();
-  // ---- B: content scores + shifted positional term + masks, written back in place (column j of row i)
-  const int i0 = g, i1 = g + 8;
-  const int tA = tw + i0, tB = tw + i1;
-  for (int nt = 0; nt < Tk / 8; ++nt) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      uint32_t bfr[2];
-      mma::ldsm_x2(bfr, sK + (nt * 8 + (lane & 7)) * HS + ks * 16 + ((lane >> 3) & 1) * 8);
-      mma::mma_16816(acc, aqu[ks], bfr);
-    }
-    const int j0 = nt * 8 + 2 * tq;
-    const float p00 = myS[(size_t)i0 * SW + j0 + 15 - i0], p01 = myS[(size_t)i0 * SW + j0 + 1 + 15 - i0];
-    const float p10 = myS[(size_t)i1 * SW + j0 + 15 - i1], p11 = myS[(size_t)i1 * SW + j0 + 1 + 15 - i1];
-    __syncwarp();  // every lane has read this tile's positional terms before the in-place writes below
-    float s00 = acc[0] + p00, s01 = acc[1] + p01, s10 = acc[2] + p10, s11 = acc[3] + p11;
-    if (!att_allowed(tA, j0, len, T, p.chunk, p.history)) s00 = -1e9f;
-    if (!att_allowed(tA, j0 + 1, len, T, p.chunk, p.history)) s01 = -1e9f;
-    if (!att_allowed(tB, j0, len, T, p.chunk, p.history)) s10 = -1e9f;
-    if (!att_allowed(tB, j0 + 1, len, T, p.chunk, p.history)) s11 = -1e9f;
-    myS[(size_t)i0 * SW + j0] = s00;
-    myS[(size_t)i0 * SW + j0 + 1] = s01;
-    myS[(size_t)i1 * SW + j0] = s10;
-    myS[(size_t)i1 * SW + j0 + 1] = s11;
-  }
-  __syncwarp();
-  // ---- C: softmax per row; bf16 probabilities to HBM and in place (A operand of P.V)
-  const int nit = Tk / 32 + ((Tk % 32) ? 1 : 0);
-  for (int i = 0; i < 16; ++i) {
-    const int t = tw + i;
-    float* srow = myS + (size_t)i * SW;
-    float sc[16];  // Tk <= 512
-    float m = -CUDART_INF_F;
-#pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int j = lane + 32 * it;
-      sc[it] = (it < nit && j < T) ? srow[j] : -CUDART_INF_F;
-      m = fmaxf(m, sc[it]);
-    }
-    m = warp_max(m);
-    float sum = 0.f;
-#pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const float e = (sc[it] > -CUDART_INF_F) ? __expf(sc[it] - m) : 0.f;
-      sc[it] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    __syncwarp();  // whole row is in registers: safe to overwrite it with bf16
-    __nv_bfloat16* prow_s = reinterpret_cast<__nv_bfloat16*>(srow);
-    __nv_bfloat16* prow_g = probs + (((size_t)b * p.N + n) * T + min(t, T - 1)) * T;
-#pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int j = lane + 32 * it;
-      if (it < nit && j < Tk) {
-        const __nv_bfloat16 pb = __float2bfloat16(sc[it] * inv);
-        prow_s[j] = pb;  // zero for j >= T (sc = 0)
-        if (j < T && t < T) prow_g[j] = pb;
-      }
+      mma::ldsm_x4(aqu[ks], sQu + (tw + (lane & 15)) * HS + ks * 16 + (lane >> 4) * 8);
+      mma::ldsm_x4(aqv[ks], sQv + (tw + (lane & 15)) * HS + ks * 16 + (lane >> 4) * 8);
     }
   }
-  __syncwarp();
-  // ---- D: O = P . V
+  __syncthreads();  // every warp holds its Q fragments: the Q region becomes the per-warp scratch
+  if (!active) return;
+  float* scratch = reinterpret_cast<float*>(U) + (size_t)warp * 16 * C::SCW;
+  const int rr0 = Tk - 16 - tw;
+  const int tA = tw + g, tB = tw + g + 8;
+  // ---- pass 1: row max and sum
+  float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+  for (int c0 = 0; c0 < Tc; c0 += C::CH) {
+    float s[8][4];
+    att_chunk_scores<KS>(s, aqu, aqv, sK, sP, scratch, rr0, c0, lane, tA, tB, len, p);
+    float x0 = -CUDART_INF_F, x1 = -CUDART_INF_F;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      x0 = fmaxf(x0, fmaxf(s[nt][0], s[nt][1]));
+      x1 = fmaxf(x1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    const float n0 = fmaxf(m0, quad_max(x0)), n1 = fmaxf(m1, quad_max(x1));  // finite from the first chunk on (key 0 exists)
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      a0 += __expf(s[nt][0] - n0) + __expf(s[nt][1] - n0);
+      a1 += __expf(s[nt][2] - n1) + __expf(s[nt][3] - n1);
+    }
+    l0 = l0 * __expf(m0 - n0) + a0;
+    l1 = l1 * __expf(m1 - n1) + a1;
+    m0 = n0;
+    m1 = n1;
+  }
+  const float inv0 = 1.0f / quad_sum(l0), inv1 = 1.0f / quad_sum(l1);
+  // ---- pass 2: probabilities and O = P . V
   float o[KS * 2][4];
 #pragma unroll
   for (int nh = 0; nh < KS * 2; ++nh) o[nh][0] = o[nh][1] = o[nh][2] = o[nh][3] = 0.f;
-  const __nv_bfloat16* pr_base = reinterpret_cast<const __nv_bfloat16*>(myS);
-  const int prs = SW * 2;  // bf16 elements per scratch row
-  for (int kt = 0; kt < Tk / 16; ++kt) {
-    uint32_t afr[4];
-    mma::ldsm_x4(afr, pr_base + (size_t)(lane & 15) * prs + kt * 16 + (lane >> 4) * 8);
+  __nv_bfloat16* prA = probs + (((size_t)b * p.N + n) * T + min(tA, T - 1)) * T;
+  __nv_bfloat16* prB = probs + (((size_t)b * p.N + n) * T + min(tB, T - 1)) * T;
+  const bool even = (T & 1) == 0;
+  for (int c0 = 0; c0 < Tc; c0 += C::CH) {
+    float s[8][4];
+    att_chunk_scores<KS>(s, aqu, aqv, sK, sP, scratch, rr0, c0, lane, tA, tB, len, p);
+    uint32_t pa[8], pb[8];
 #pragma unroll
-    for (int nh = 0; nh < KS * 2; ++nh) {
-      uint32_t bfr[2];
-      mma::ldsm_x2_trans(bfr, sV + (kt * 16 + (lane & 15)) * HS + nh * 8);
-      mma::mma_16816(o[nh], afr, bfr);
+    for (int nt = 0; nt < 8; ++nt) {
+      pa[nt] = pack_bf16(__expf(s[nt][0] - m0) * inv0, __expf(s[nt][1] - m0) * inv0);
+      pb[nt] = pack_bf16(__expf(s[nt][2] - m1) * inv1, __expf(s[nt][3] - m1) * inv1);
+      const int j = c0 + nt * 8 + 2 * tq;
+      if (even) {
+        if (j < T) {
+          if (tA < T) *reinterpret_cast<uint32_t*>(prA + j) = pa[nt];
+          if (tB < T) *reinterpret_cast<uint32_t*>(prB + j) = pb[nt];
+        }
+      } else {
+        const __nv_bfloat162 va = *reinterpret_cast<const __nv_bfloat162*>(&pa[nt]), vb = *reinterpret_cast<const __nv_bfloat162*>(&pb[nt]);
+        if (tA < T) {
+          if (j < T) prA[j] = __low2bfloat16(va);
+          if (j + 1 < T) prA[j + 1] = __high2bfloat16(va);
+        }
+        if (tB < T) {
+          if (j < T) prB[j] = __low2bfloat16(vb);
+          if (j + 1 < T) prB[j + 1] = __high2bfloat16(vb);
+        }
+      }
+    }
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const uint32_t afr[4] = {pa[2 * kt], pb[2 * kt], pa[2 * kt + 1], pb[2 * kt + 1]};
+#pragma unroll
+      for (int nh = 0; nh < KS * 2; ++nh) {
+        uint32_t bfr[2];
+        mma::ldsm_x2_trans(bfr, sV + (c0 + kt * 16 + (lane & 15)) * HS + nh * 8);
+        mma::mma_16816(o[nh], afr, bfr);
+      }
     }
   }
 #pragma unroll
@@ -544,202 +596,196 @@ __global__ void __launch_bounds__(128) rel_attention_fwd_mma_kernel(const AttPar
 template <int KS>
 static int launch_att_fwd_mma(const AttParams& p, __nv_bfloat16* ctx, __nv_bfloat16* probs, cudaStream_t stream) {
   const size_t smem = att_mma_fwd_smem<KS>(p.T);
-  if (smem > 227 * 1024 || p.T > 512) return -1;  // caller falls back to the FP32 kernel
+  if (smem > 227 * 1024 || p.T > 256 || (p.H & 3) || (p.ld_qkv & 3)) return -1;  // caller falls back to the FP32 kernel
   if (cudaFuncSetAttribute(rel_attention_fwd_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return TFASR_EXECUTION_FAILED;
-  dim3 grid((unsigned)ceil_div(p.T, AttMma<KS>::TQ), p.N, p.B);
-  rel_attention_fwd_mma_kernel<KS><<<grid, 128, smem, stream>>>(p, ctx, probs);
+  dim3 grid(p.N, p.B);
+  rel_attention_fwd_mma_kernel<KS><<<grid, 512, smem, stream>>>(p, ctx, probs);
   count_launch();
   return check_launch();
 }
 
 // ================================================================================================ tensor-core backward, rows
-// Same CTA shape as the forward.  Per warp (16 query rows):
-//   pass 1  dP = dO . V^T tile by tile, delta_i = sum_j P_ij dP_ij        (P rows staged in SMEM; dP never stored)
-//   pass 2  dP again (recomputed: 3 MMAs per tile are cheaper than 128 registers or an FP32 scratch), dS = P (dP - delta), masked -> 0;
-//           bf16 dS -> HBM (for the column kernel), in place over P, and skewed (column j + 15 - i) for the positional product
-//   dQ = scale-folded:  dS . K  +  dS_skewed . Pos[window]     (K and Pos through ldmatrix.trans);  du / dvb = column sums
-__host__ __device__ inline int att_mma_ps(int T) { return att_mma_tk(T) + 8; }    // bf16 row stride of the P / dS buffer
-__host__ __device__ inline int att_mma_qs(int T) { return att_mma_tk(T) + 24; }   // bf16 row stride of the skewed dS buffer
-
+// Same CTA shape as the forward.  Per warp (16 query rows), one pass over the keys in chunks of 64:
+//   delta_i = dO_i . O_i   (= sum_j P_ij dP_ij, from the forward's output instead of a second sweep)
+//   dP = dO . V^T  ->  dS = P (dP - delta), masked -> 0;   bf16 dS -> HBM (for the column kernel), kept in registers as the A operand of
+//   dQ += dS . K, and written skewed (column jl + 15 - i) to a per-warp SMEM buffer for  dQ += dS_skewed . Pos[window]
+//   du / dvb = column sums of the two dQ parts
 template <int KS>
 static size_t att_mma_bwd_rows_smem(int T) {
   using C = AttMma<KS>;
-  const int Tk = att_mma_tk(T);
-  size_t b = (size_t)(C::TQ + 2 * Tk + att_mma_pw(T)) * C::HS * 2;
-  b += (size_t)4 * 16 * (att_mma_ps(T) + att_mma_qs(T)) * 2;
-  b = align_up(b, 16);
-  b += 2 * 64 * sizeof(float);
-  return b;
+  const size_t kv = (size_t)2 * att_mma_tc(T) * C::HS * 2, pos = (size_t)att_mma_prow(T) * C::HS * 2;
+  const size_t dox = (size_t)att_mma_tk(T) * C::HS * 2, skew = (size_t)16 * 16 * C::SKW * 2;
+  return kv + pos + (dox > skew ? dox : skew) + 2 * 64 * sizeof(float);
 }
 
 template <int KS>
-__global__ void __launch_bounds__(128) rel_attention_bwd_rows_mma_kernel(const AttParams p, const __nv_bfloat16* __restrict__ probs,
-                                                                         const __nv_bfloat16* __restrict__ dctx,
-                                                                         __nv_bfloat16* __restrict__ ds_out, __nv_bfloat16* __restrict__ dqkv,
-                                                                         float* __restrict__ du, float* __restrict__ dvb) {
+__global__ void __launch_bounds__(512, 1) rel_attention_bwd_rows_mma_kernel(const AttParams p, const __nv_bfloat16* __restrict__ probs,
+                                                                            const __nv_bfloat16* __restrict__ dctx,
+                                                                            const __nv_bfloat16* __restrict__ octx,
+                                                                            __nv_bfloat16* __restrict__ ds_out, __nv_bfloat16* __restrict__ dqkv,
+                                                                            float* __restrict__ du, float* __restrict__ dvb) {
   using C = AttMma<KS>;
-  constexpr int HS = C::HS;
+  constexpr int HS = C::HS, SKW = C::SKW;
   extern __shared__ __align__(16) uint8_t att_smem[];
-  const int T = p.T, H = p.H, NH = p.N * p.H, R = p.R;
-  const int b = blockIdx.z, n = blockIdx.y, t0 = blockIdx.x * C::TQ;
-  const int Tk = att_mma_tk(T), PW = att_mma_pw(T), PS = att_mma_ps(T), QS = att_mma_qs(T);
-  __nv_bfloat16* sdO = reinterpret_cast<__nv_bfloat16*>(att_smem);
-  __nv_bfloat16* sK = sdO + C::TQ * HS;
-  __nv_bfloat16* sV = sK + (size_t)Tk * HS;
-  __nv_bfloat16* sP = sV + (size_t)Tk * HS;
-  __nv_bfloat16* sPr = sP + (size_t)PW * HS;           // [4][16][PS]  P then dS
-  __nv_bfloat16* sSk = sPr + (size_t)4 * 16 * PS;      // [4][16][QS]  skewed dS
-  float* sAcc = reinterpret_cast<float*>(att_smem + align_up((size_t)((C::TQ + 2 * Tk + PW) * HS + 4 * 16 * (PS + QS)) * 2, 16));
+  const int T = p.T, H = p.H, NH = p.N * p.H;
+  const int b = blockIdx.y, n = blockIdx.x;
+  const int Tk = att_mma_tk(T), Tc = att_mma_tc(T);
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
+  __nv_bfloat16* sV = sK + (size_t)Tc * HS;
+  __nv_bfloat16* sP = sV + (size_t)Tc * HS;
+  uint8_t* U = reinterpret_cast<uint8_t*>(sP + (size_t)att_mma_prow(T) * HS);
+  const size_t usz = max((size_t)Tk * HS * 2, (size_t)16 * 16 * SKW * 2);
+  float* sAcc = reinterpret_cast<float*>(U + usz);
+  __nv_bfloat16* sdO = reinterpret_cast<__nv_bfloat16*>(U);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tq = lane & 3;
   const int len = p.length ? p.length[b] : T;
-  const int r_lo = T - 1 - (t0 + C::TQ - 1);
-  const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+  att_stage_kvp<KS>(p, b, n, sK, sV, sP, true);
   {
-    constexpr int HP2 = KS * 8;
-    for (int i = threadIdx.x; i < Tk * HP2; i += 128) {
-      const int j = i / HP2, h2 = i % HP2;
-      __nv_bfloat162 kk = z2, vv = z2;
-      if (j < T && 2 * h2 < H) {
-        const size_t gidx = ((size_t)b * T + j) * p.ld_qkv + (size_t)n * H + 2 * h2;
-        kk = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + gidx + NH);
-        vv = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + gidx + 2 * NH);
-      }
-      *reinterpret_cast<__nv_bfloat162*>(sK + j * HS + 2 * h2) = kk;
-      *reinterpret_cast<__nv_bfloat162*>(sV + j * HS + 2 * h2) = vv;
+    constexpr int HP4 = KS * 4;
+    const uint2 z = make_uint2(0u, 0u);
+    for (int i = threadIdx.x; i < Tk * HP4; i += 512) {
+      const int t = i / HP4, h4 = i % HP4;
+      uint2 v = z;
+      if (t < T && 4 * h4 < H) v = ld8(dctx + ((size_t)b * T + t) * NH + (size_t)n * H + 4 * h4);
+      st8(sdO + t * HS + 4 * h4, v);
     }
-    for (int i = threadIdx.x; i < PW * HP2; i += 128) {
-      const int rr = i / HP2, h2 = i % HP2;
-      const int r = r_lo + rr;
-      __nv_bfloat162 v = z2;
-      if (r >= 0 && r < R && 2 * h2 < H) v = *reinterpret_cast<const __nv_bfloat162*>(p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 2 * h2);
-      *reinterpret_cast<__nv_bfloat162*>(sP + rr * HS + 2 * h2) = v;
-    }
-    for (int i = threadIdx.x; i < C::TQ * HP2; i += 128) {
-      const int rr = i / HP2, h2 = i % HP2;
-      const int t = t0 + rr;
-      __nv_bfloat162 v = z2;
-      if (t < T && 2 * h2 < H) v = *reinterpret_cast<const __nv_bfloat162*>(dctx + ((size_t)b * T + t) * NH + (size_t)n * H + 2 * h2);
-      *reinterpret_cast<__nv_bfloat162*>(sdO + rr * HS + 2 * h2) = v;
-    }
-    for (int i = threadIdx.x; i < 128; i += 128) sAcc[i] = 0.f;
-  }
-  const int tw = t0 + warp * 16;
-  __nv_bfloat16* myP = sPr + (size_t)warp * 16 * PS;
-  __nv_bfloat16* myS = sSk + (size_t)warp * 16 * QS;
-  const __nv_bfloat16* pbase = probs + ((size_t)b * p.N + n) * T * T;
-  {  // this warp's probability rows (zero beyond T) and a cleared skew buffer
-    for (int i = 0; i < 16; ++i) {
-      const int t = tw + i;
-      const __nv_bfloat16* prow = pbase + (size_t)min(t, T - 1) * T;
-      if ((T & 1) == 0) {
-        for (int j2 = lane; j2 < PS / 2; j2 += 32) {
-          __nv_bfloat162 v = z2;
-          if (t < T && 2 * j2 < T) v = *reinterpret_cast<const __nv_bfloat162*>(prow + 2 * j2);
-          *reinterpret_cast<__nv_bfloat162*>(myP + i * PS + 2 * j2) = v;
-        }
-      } else {
-        for (int j = lane; j < PS; j += 32) myP[i * PS + j] = (t < T && j < T) ? prow[j] : __float2bfloat16(0.f);
-      }
-      for (int j2 = lane; j2 < QS / 2; j2 += 32) *reinterpret_cast<__nv_bfloat162*>(myS + i * QS + 2 * j2) = z2;
-    }
+    if (threadIdx.x < 128) sAcc[threadIdx.x] = 0.f;
   }
   __syncthreads();
+  const int tw = warp * 16;
+  const bool active = tw < T;
+  uint32_t ado[KS][4];
+  if (active) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) mma::ldsm_x4(ado[ks], sdO + (tw + (lane & 15)) * HS + ks * 16 + (lane >> 4) * 8);
+  }
+  __syncthreads();  // dO fragments are in registers: the region becomes the per-warp skew buffers
   float accC[KS * 2][4], accP[KS * 2][4];
 #pragma unroll
   for (int nh = 0; nh < KS * 2; ++nh) {
     accC[nh][0] = accC[nh][1] = accC[nh][2] = accC[nh][3] = 0.f;
     accP[nh][0] = accP[nh][1] = accP[nh][2] = accP[nh][3] = 0.f;
   }
-  if (tw < T) {
-    uint32_t ado[KS][4];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) mma::ldsm_x4(ado[ks], sdO + (warp * 16 + (lane & 15)) * HS + ks * 16 + (lane >> 4) * 8);
-    const int i0 = g, i1 = g + 8;
-    const int tA = tw + i0, tB = tw + i1;
-    // ---- pass 1: delta
+  if (active) {
+    __nv_bfloat16* skew = reinterpret_cast<__nv_bfloat16*>(U) + (size_t)warp * 16 * SKW;
+    for (int i = lane; i < 16 * SKW / 2; i += 32) reinterpret_cast<uint32_t*>(skew)[i] = 0u;  // outside the band stays zero
+    const int rr0 = Tk - 16 - tw;
+    const int tA = tw + g, tB = tw + g + 8;
+    const int rA = min(tA, T - 1), rB = min(tB, T - 1);
+    // delta = dO . O over the head dimension (quad-split)
     float d0 = 0.f, d1 = 0.f;
-    for (int nt = 0; nt < Tk / 8; ++nt) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        uint32_t bfr[2];
-        mma::ldsm_x2(bfr, sV + (nt * 8 + (lane & 7)) * HS + ks * 16 + ((lane >> 3) & 1) * 8);
-        mma::mma_16816(acc, ado[ks], bfr);
-      }
-      const int j0 = nt * 8 + 2 * tq;
-      const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(myP + i0 * PS + j0);
-      const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(myP + i1 * PS + j0);
-      d0 = fmaf(__low2float(pa), acc[0], fmaf(__high2float(pa), acc[1], d0));
-      d1 = fmaf(__low2float(pb), acc[2], fmaf(__high2float(pb), acc[3], d1));
-    }
-    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
-    d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-    // ---- pass 2: dS
-    __nv_bfloat16* dsA = ds_out + (((size_t)b * p.N + n) * T + min(tA, T - 1)) * T;
-    __nv_bfloat16* dsB = ds_out + (((size_t)b * p.N + n) * T + min(tB, T - 1)) * T;
-    for (int nt = 0; nt < Tk / 8; ++nt) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        uint32_t bfr[2];
-        mma::ldsm_x2(bfr, sV + (nt * 8 + (lane & 7)) * HS + ks * 16 + ((lane >> 3) & 1) * 8);
-        mma::mma_16816(acc, ado[ks], bfr);
-      }
-      const int j0 = nt * 8 + 2 * tq;
-      const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(myP + i0 * PS + j0);
-      const __nv_bfloat162 pb = *reinterpret_cast<const __nv_bfloat162*>(myP + i1 * PS + j0);
-      float s00 = __low2float(pa) * (acc[0] - d0), s01 = __high2float(pa) * (acc[1] - d0);
-      float s10 = __low2float(pb) * (acc[2] - d1), s11 = __high2float(pb) * (acc[3] - d1);
-      if (!att_allowed(tA, j0, len, T, p.chunk, p.history)) s00 = 0.f;  // masked scores are constants
-      if (!att_allowed(tA, j0 + 1, len, T, p.chunk, p.history)) s01 = 0.f;
-      if (!att_allowed(tB, j0, len, T, p.chunk, p.history)) s10 = 0.f;
-      if (!att_allowed(tB, j0 + 1, len, T, p.chunk, p.history)) s11 = 0.f;
-      const __nv_bfloat162 da = __floats2bfloat162_rn(s00, s01), db = __floats2bfloat162_rn(s10, s11);
-      *reinterpret_cast<__nv_bfloat162*>(myP + i0 * PS + j0) = da;
-      *reinterpret_cast<__nv_bfloat162*>(myP + i1 * PS + j0) = db;
-      myS[i0 * QS + j0 + 15 - i0] = __low2bfloat16(da);
-      myS[i0 * QS + j0 + 16 - i0] = __high2bfloat16(da);
-      myS[i1 * QS + j0 + 15 - i1] = __low2bfloat16(db);
-      myS[i1 * QS + j0 + 16 - i1] = __high2bfloat16(db);
-      if (tA < T) {
-        if (j0 < T) dsA[j0] = __low2bfloat16(da);
-        if (j0 + 1 < T) dsA[j0 + 1] = __high2bfloat16(da);
-      }
-      if (tB < T) {
-        if (j0 < T) dsB[j0] = __low2bfloat16(db);
-        if (j0 + 1 < T) dsB[j0 + 1] = __high2bfloat16(db);
+    for (int nh = 0; nh < KS * 2; ++nh) {
+      const int h = nh * 8 + 2 * tq;
+      if (h < H) {
+        const size_t ia = ((size_t)b * T + rA) * NH + (size_t)n * H + h, ib = ((size_t)b * T + rB) * NH + (size_t)n * H + h;
+        const __nv_bfloat162 xa = *reinterpret_cast<const __nv_bfloat162*>(dctx + ia), ya = *reinterpret_cast<const __nv_bfloat162*>(octx + ia);
+        const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162*>(dctx + ib), yb = *reinterpret_cast<const __nv_bfloat162*>(octx + ib);
+        d0 += __low2float(xa) * __low2float(ya) + __high2float(xa) * __high2float(ya);
+        d1 += __low2float(xb) * __low2float(yb) + __high2float(xb) * __high2float(yb);
       }
     }
+    d0 = quad_sum(d0);
+    d1 = quad_sum(d1);
+    const __nv_bfloat16* prA = probs + (((size_t)b * p.N + n) * T + rA) * T;
+    const __nv_bfloat16* prB = probs + (((size_t)b * p.N + n) * T + rB) * T;
+    __nv_bfloat16* dsA = ds_out + (((size_t)b * p.N + n) * T + rA) * T;
+    __nv_bfloat16* dsB = ds_out + (((size_t)b * p.N + n) * T + rB) * T;
+    const bool even = (T & 1) == 0;
+    const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
     __syncwarp();
-    // ---- dQ (content): dS . K
-    for (int kt = 0; kt < Tk / 16; ++kt) {
-      uint32_t afr[4];
-      mma::ldsm_x4(afr, myP + (lane & 15) * PS + kt * 16 + (lane >> 4) * 8);
+    for (int c0 = 0; c0 < Tc; c0 += C::CH) {
+      // this chunk's probabilities (issued first: their latency hides behind the dP MMAs)
+      float2 pA[8], pB[8];
 #pragma unroll
-      for (int nh = 0; nh < KS * 2; ++nh) {
-        uint32_t bfr[2];
-        mma::ldsm_x2_trans(bfr, sK + (kt * 16 + (lane & 15)) * HS + nh * 8);
-        mma::mma_16816(accC[nh], afr, bfr);
+      for (int nt = 0; nt < 8; ++nt) {
+        const int j = c0 + nt * 8 + 2 * tq;
+        pA[nt] = pB[nt] = make_float2(0.f, 0.f);
+        if (even) {
+          if (j < T) {
+            pA[nt] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(prA + j));
+            pB[nt] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(prB + j));
+          }
+        } else {
+          if (j < T) {
+            pA[nt].x = __bfloat162float(prA[j]);
+            pB[nt].x = __bfloat162float(prB[j]);
+          }
+          if (j + 1 < T) {
+            pA[nt].y = __bfloat162float(prA[j + 1]);
+            pB[nt].y = __bfloat162float(prB[j + 1]);
+          }
+        }
       }
-    }
-    // ---- dQ (positional): dS_skewed . Pos[window]
-    const int rr0 = (C::TQ - 16) - warp * 16;
-    const int nkt = (T + 15 + 15) / 16;
-    for (int kt = 0; kt < nkt; ++kt) {
-      uint32_t afr[4];
-      mma::ldsm_x4(afr, myS + (lane & 15) * QS + kt * 16 + (lane >> 4) * 8);
+      uint32_t da[8], db[8];
 #pragma unroll
-      for (int nh = 0; nh < KS * 2; ++nh) {
-        uint32_t bfr[2];
-        mma::ldsm_x2_trans(bfr, sP + (rr0 + kt * 16 + (lane & 15)) * HS + nh * 8);
-        mma::mma_16816(accP[nh], afr, bfr);
+      for (int nt = 0; nt < 8; ++nt) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          uint32_t bfr[2];
+          mma::ldsm_x2(bfr, sV + (c0 + nt * 8 + brow) * HS + ks * 16 + bcol);
+          mma::mma_16816(acc, ado[ks], bfr);
+        }
+        const int jl = nt * 8 + 2 * tq, j = c0 + jl;
+        float s0 = pA[nt].x * (acc[0] - d0), s1 = pA[nt].y * (acc[1] - d0);
+        float s2 = pB[nt].x * (acc[2] - d1), s3 = pB[nt].y * (acc[3] - d1);
+        if (tA >= T || !att_allowed(tA, j, len, T, p.chunk, p.history)) s0 = 0.f;  // masked scores are constants
+        if (tA >= T || !att_allowed(tA, j + 1, len, T, p.chunk, p.history)) s1 = 0.f;
+        if (tB >= T || !att_allowed(tB, j, len, T, p.chunk, p.history)) s2 = 0.f;
+        if (tB >= T || !att_allowed(tB, j + 1, len, T, p.chunk, p.history)) s3 = 0.f;
+        da[nt] = pack_bf16(s0, s1);
+        db[nt] = pack_bf16(s2, s3);
+        const __nv_bfloat162 va = *reinterpret_cast<const __nv_bfloat162*>(&da[nt]), vb = *reinterpret_cast<const __nv_bfloat162*>(&db[nt]);
+        skew[g * SKW + jl + 15 - g] = __low2bfloat16(va);
+        skew[g * SKW + jl + 16 - g] = __high2bfloat16(va);
+        skew[(g + 8) * SKW + jl + 7 - g] = __low2bfloat16(vb);
+        skew[(g + 8) * SKW + jl + 8 - g] = __high2bfloat16(vb);
+        if (even) {
+          if (j < T) {
+            if (tA < T) *reinterpret_cast<uint32_t*>(dsA + j) = da[nt];
+            if (tB < T) *reinterpret_cast<uint32_t*>(dsB + j) = db[nt];
+          }
+        } else {
+          if (tA < T) {
+            if (j < T) dsA[j] = __low2bfloat16(va);
+            if (j + 1 < T) dsA[j + 1] = __high2bfloat16(va);
+          }
+          if (tB < T) {
+            if (j < T) dsB[j] = __low2bfloat16(vb);
+            if (j + 1 < T) dsB[j + 1] = __high2bfloat16(vb);
+          }
+        }
       }
+      __syncwarp();
+      // dQ (content): dS . K, A operand straight from the registers
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        const uint32_t afr[4] = {da[2 * kt], db[2 * kt], da[2 * kt + 1], db[2 * kt + 1]};
+#pragma unroll
+        for (int nh = 0; nh < KS * 2; ++nh) {
+          uint32_t bfr[2];
+          mma::ldsm_x2_trans(bfr, sK + (c0 + kt * 16 + (lane & 15)) * HS + nh * 8);
+          mma::mma_16816(accC[nh], afr, bfr);
+        }
+      }
+      // dQ (positional): dS_skewed [16 x 80] . Pos[window rows rr0 + c0 ..]
+#pragma unroll
+      for (int kt = 0; kt < 5; ++kt) {
+        uint32_t afr[4];
+        mma::ldsm_x4(afr, skew + (lane & 15) * SKW + kt * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int nh = 0; nh < KS * 2; ++nh) {
+          uint32_t bfr[2];
+          mma::ldsm_x2_trans(bfr, sP + (rr0 + c0 + kt * 16 + (lane & 15)) * HS + nh * 8);
+          mma::mma_16816(accP[nh], afr, bfr);
+        }
+      }
+      __syncwarp();  // the skew buffer is rewritten by the next chunk
     }
-    // scores were computed from (q+u)*scale, (q+v)*scale: no extra factor on dq (the scale is in K-side gradients through Qu, Qv)
+    // scores came from (q + u) * scale and (q + v) * scale: dq carries the scale once
 #pragma unroll
     for (int nh = 0; nh < KS * 2; ++nh) {
       const int h = nh * 8 + 2 * tq;
@@ -772,7 +818,7 @@ __global__ void __launch_bounds__(128) rel_attention_bwd_rows_mma_kernel(const A
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < H; i += 128) {
+  for (int i = threadIdx.x; i < H; i += 512) {
     atomicAdd(du + n * H + i, sAcc[i]);
     atomicAdd(dvb + n * H + i, sAcc[64 + i]);
   }
@@ -945,18 +991,17 @@ __global__ void __launch_bounds__(512) rel_attention_bwd_cols_mma_kernel(const A
 }
 
 template <int KS>
-static int launch_att_bwd_mma(const AttParams& p, const __nv_bfloat16* probs, const __nv_bfloat16* dctx, __nv_bfloat16* ds_ws,
-                              __nv_bfloat16* dqkv, __nv_bfloat16* dpos, float* du, float* dvb, cudaStream_t stream) {
+static int launch_att_bwd_mma(const AttParams& p, const __nv_bfloat16* probs, const __nv_bfloat16* dctx, const __nv_bfloat16* octx,
+                              __nv_bfloat16* ds_ws, __nv_bfloat16* dqkv, __nv_bfloat16* dpos, float* du, float* dvb, cudaStream_t stream) {
   const size_t smem1 = att_mma_bwd_rows_smem<KS>(p.T), smem2 = att_mma_bwd_cols_smem<KS>(p.T);
-  if (smem1 > 227 * 1024 || smem2 > 227 * 1024 || p.T > 256 || p.T < 16) return -1;
+  if (smem1 > 227 * 1024 || smem2 > 227 * 1024 || p.T > 256 || p.T < 16 || (p.H & 3) || (p.ld_qkv & 3) || !octx) return -1;
   if (cudaFuncSetAttribute(rel_attention_bwd_rows_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(rel_attention_bwd_cols_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return TFASR_EXECUTION_FAILED;
-  dim3 grid((unsigned)ceil_div(p.T, AttMma<KS>::TQ), p.N, p.B);
-  rel_attention_bwd_rows_mma_kernel<KS><<<grid, 128, smem1, stream>>>(p, probs, dctx, ds_ws, dqkv, du, dvb);
+  dim3 grid(p.N, p.B);
+  rel_attention_bwd_rows_mma_kernel<KS><<<grid, 512, smem1, stream>>>(p, probs, dctx, octx, ds_ws, dqkv, du, dvb);
   count_launch();
-  dim3 grid2(p.N, p.B);
-  rel_attention_bwd_cols_mma_kernel<KS><<<grid2, 512, smem2, stream>>>(p, probs, ds_ws, dctx, dqkv, dpos);
+  rel_attention_bwd_cols_mma_kernel<KS><<<grid, 512, smem2, stream>>>(p, probs, ds_ws, dctx, dqkv, dpos);
   count_launch();
   return check_launch();
 }
@@ -1043,8 +1088,8 @@ extern "C" int tfasr_rel_attention_fwd(const void* qkv, int32_t ld_qkv, const vo
 
 extern "C" int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias,
                                        const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history,
-                                       const void* probs, const void* dctx, void* ds_ws, void* dqkv, void* dpos, float* du, float* dvb,
-                                       tfasr_stream_t stream_) {
+                                       const void* probs, const void* dctx, const void* ctx, void* ds_ws, void* dqkv, void* dpos, float* du,
+                                       float* dvb, tfasr_stream_t stream_) {
   AttParams p = make_att(qkv, ld_qkv, pos, ubias, vbias, length, B, T, N, H, chunk, history);
   int st = att_check(p);
   if (st || !probs || !dctx || !ds_ws || !dqkv || !dpos || !du || !dvb) return st ? st : TFASR_INVALID_VALUE;
@@ -1055,7 +1100,7 @@ extern "C" int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const vo
     const int ks = (H + 15) / 16;
 #define BWD_MMA(KS_)                                                                                                                  \
   r = launch_att_bwd_mma<KS_>(p, static_cast<const __nv_bfloat16*>(probs), static_cast<const __nv_bfloat16*>(dctx),                   \
-                              static_cast<__nv_bfloat16*>(ds_ws), static_cast<__nv_bfloat16*>(dqkv), static_cast<__nv_bfloat16*>(dpos), \
+                              static_cast<const __nv_bfloat16*>(ctx), static_cast<__nv_bfloat16*>(ds_ws), static_cast<__nv_bfloat16*>(dqkv), static_cast<__nv_bfloat16*>(dpos), \
                               du, dvb, stream)
     if (ks <= 1) BWD_MMA(1);
     else if (ks == 2) BWD_MMA(2);

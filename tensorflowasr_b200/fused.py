@@ -417,16 +417,16 @@ class _RelAttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, pos, u, v, length, B, T, N, H, chunk, history):
         out, probs = kernels.rel_attention_fwd(qkv, pos, u.detach(), v.detach(), length, B, T, N, H, chunk, history)
-        ctx.save_for_backward(qkv, pos, probs, length)
+        ctx.save_for_backward(qkv, pos, probs, length, out)
         ctx.misc = (u, v, B, T, N, H, chunk, history)
         return out
 
     @staticmethod
     def backward(ctx, dctx):
-        qkv, pos, probs, length = ctx.saved_tensors
+        qkv, pos, probs, length, out = ctx.saved_tensors
         u, v, B, T, N, H, chunk, history = ctx.misc
         dqkv, dpos = kernels.rel_attention_bwd(qkv, pos, u.detach(), v.detach(), length, B, T, N, H, probs, dctx.contiguous(), _grad(u), _grad(v),
-                                               chunk, history)
+                                               chunk, history, ctx=out)
         return dqkv, dpos, None, None, None, None, None, None, None, None, None
 
 

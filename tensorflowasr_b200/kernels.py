@@ -216,8 +216,8 @@ def rel_attention_fwd(qkv, pos, ubias, vbias, length, B, T, N, H, chunk=None, hi
     return ctx, probs
 
 
-def rel_attention_bwd(qkv, pos, ubias, vbias, length, B, T, N, H, probs, dctx, du, dvb, chunk=None, history=None):
-    """-> (dqkv like qkv, dpos like pos); du / dvb (f32 [N,H]) accumulated."""
+def rel_attention_bwd(qkv, pos, ubias, vbias, length, B, T, N, H, probs, dctx, du, dvb, chunk=None, history=None, ctx=None):
+    """-> (dqkv like qkv, dpos like pos); du / dvb (f32 [N,H]) accumulated.  `ctx`: the forward's output (tensor-core path)."""
     lib = _lib.load()
     dqkv = torch.empty_like(qkv)
     dpos = torch.empty_like(pos)
@@ -225,7 +225,7 @@ def rel_attention_bwd(qkv, pos, ubias, vbias, length, B, T, N, H, probs, dctx, d
     ch = int(chunk) if (chunk is not None and history is not None) else 0
     hi = int(history) if (chunk is not None and history is not None) else 0
     _lib.check(lib.tfasr_rel_attention_bwd(_lib.ptr(qkv), qkv.stride(0), _lib.ptr(pos), _lib.ptr(ubias), _lib.ptr(vbias), _lib.ptr(length), B, T, N, H,
-                                           ch, hi, _lib.ptr(probs), _lib.ptr(dctx), _lib.ptr(ds), _lib.ptr(dqkv), _lib.ptr(dpos), _lib.ptr(du),
+                                           ch, hi, _lib.ptr(probs), _lib.ptr(dctx), _lib.ptr(ctx), _lib.ptr(ds), _lib.ptr(dqkv), _lib.ptr(dpos), _lib.ptr(du),
                                            _lib.ptr(dvb), _st(qkv)), "tfasr_rel_attention_bwd")
     return dqkv, dpos
 

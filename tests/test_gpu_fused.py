@@ -273,7 +273,7 @@ def test_rel_attention_kernels_vs_torch(cfg):
     ref.backward(dctx.float().view(B, T, NH))
     du = torch.zeros(N, H, device="cuda")
     dv = torch.zeros(N, H, device="cuda")
-    dqkv, dpos = kernels.rel_attention_bwd(qkv, pos, u, v, length, B, T, N, H, probs, dctx, du, dv, chunk, hist)
+    dqkv, dpos = kernels.rel_attention_bwd(qkv, pos, u, v, length, B, T, N, H, probs, dctx, du, dv, chunk, hist, ctx=ctx)
     _close(dqkv.view(B, T, 3 * NH), q3.grad, 3e-2)
     _close(dpos.view(B, R, NH), p3.grad, 3e-2)
     _close(du, ur.grad, 3e-2)
