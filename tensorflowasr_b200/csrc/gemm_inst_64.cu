@@ -1,0 +1,6 @@
+// tcgen05 GEMM kernels for the 64-column tile (all epilogue feature classes): see gemm_kernel.cuh
+#include "gemm_kernel.cuh"
+
+namespace tfasr {
+TFASR_GEMM_INSTANTIATE(64)
+}

@@ -46,6 +46,17 @@ def main():
             model.train_step(data)
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=args.rows, max_name_column_width=90))
+    # device-side kernels only, every one of them, per step
+    kern = {}
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            k = kern.setdefault(ev.name, [0.0, 0])
+            k[0] += ev.device_time
+            k[1] += 1
+    total = sum(v[0] for v in kern.values())
+    print(f"\n== device kernels per step: {total / 2e3:.3f} ms over {sum(v[1] for v in kern.values()) // 2} launches")
+    for name, (t, c) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
+        print(f"{t / 2e3:8.3f} ms {c // 2:5d} x {t / c:8.1f} us  {name[:150]}")
 
 
 if __name__ == "__main__":
