@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) scale_mask_colsum_kernel(const __nv_bfloa
       const __nv_bfloat162 vi = *reinterpret_cast<const __nv_bfloat162*>(in + idx);
       float a = __low2float(vi) * scale, b = __high2float(vi) * scale;
       if (drop_p > 0.f) {
-        const uint32_t hsh = dropout_hash(seed, idx);  // idx is even: one hash serves the column pair
+        const uint32_t hsh = dropout_hash(dropout_rowkey(seed, (unsigned long long)r), (uint32_t)c);  // c is even: one hash serves the column pair
         a = ((hsh & 0xFFFFu) >= drop_thr) ? a * keep_scale : 0.f;
         b = ((hsh >> 16) >= drop_thr) ? b * keep_scale : 0.f;
       }

@@ -58,7 +58,8 @@ bool make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t r
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_cols * elem_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,  // bf16 groups: 64-byte rows
+                   box_cols * elem_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_NONE  // GLU output groups: 32-byte rows
+                                               : (box_cols * elem_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -69,10 +70,21 @@ bool make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t r
   extern template int launch_gemm<BN, false, false, 0u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   extern template int launch_gemm<BN, false, false, 1u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   extern template int launch_gemm<BN, false, false, 2u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  extern template int launch_gemm<BN, false, false, 3u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   extern template int launch_gemm<BN, false, false, 4u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  extern template int launch_gemm<BN, false, false, 6u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   extern template int launch_gemm<BN, false, false, 7u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   extern template int launch_gemm<BN, true, true, 0u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t);   \
   extern template int launch_gemm<BN, true, true, 7u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t);
+#define TFASR_GEMM_EXTERN_KMAJOR(BN)                                                                                                        \
+  extern template int launch_gemm<BN, false, false, 0u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  extern template int launch_gemm<BN, false, false, 1u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  extern template int launch_gemm<BN, false, false, 2u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  extern template int launch_gemm<BN, false, false, 3u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  extern template int launch_gemm<BN, false, false, 4u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  extern template int launch_gemm<BN, false, false, 6u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  extern template int launch_gemm<BN, false, false, 7u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t);
+TFASR_GEMM_EXTERN_KMAJOR(160)
 TFASR_GEMM_EXTERN(64)
 TFASR_GEMM_EXTERN(128)
 TFASR_GEMM_EXTERN(192)
@@ -82,10 +94,12 @@ TFASR_GEMM_EXTERN(256)
 unsigned long long* g_gemm_trace_host = nullptr;
 #endif
 
-static int choose_bn(int N) {
-  const int cands[4] = {64, 128, 192, 256};
+// tile width with the least padded work; ties go to the wider tile (A is re-read once per column tile)
+static int choose_bn(int N, bool mn_major) {
+  const int cands[5] = {64, 128, 160, 192, 256};
   int best = 256, best_cost = 1 << 30;
   for (int c : cands) {
+    if (mn_major && (c % 64)) continue;
     const int cost = (int)ceil_div(N, c) * c;
     if (cost < best_cost || (cost == best_cost && c > best)) {
       best = c;
@@ -102,7 +116,7 @@ static uint32_t feature_class(const GemmEpi& e, bool mn_major) {
   if (e.drop_p > 0.f || e.residual) need |= 2u;
   if (e.mul || e.colsum) need |= 4u;
   if (mn_major) return need ? 7u : 0u;
-  return (need == 0u || need == 1u || need == 2u || need == 4u) ? need : 7u;
+  return need == 5u ? 7u : need;
 }
 
 template <int BN, bool MN>
@@ -116,6 +130,8 @@ static int dispatch_feat(const void* A, const void* B, const GemmEpi& epi, int M
       case 0u: return launch_gemm<BN, false, false, 0u>(A, B, epi, M, N, K, lda, ldb, splits, stream);
       case 1u: return launch_gemm<BN, false, false, 1u>(A, B, epi, M, N, K, lda, ldb, splits, stream);
       case 2u: return launch_gemm<BN, false, false, 2u>(A, B, epi, M, N, K, lda, ldb, splits, stream);
+      case 3u: return launch_gemm<BN, false, false, 3u>(A, B, epi, M, N, K, lda, ldb, splits, stream);
+      case 6u: return launch_gemm<BN, false, false, 6u>(A, B, epi, M, N, K, lda, ldb, splits, stream);
       case 4u: return launch_gemm<BN, false, false, 4u>(A, B, epi, M, N, K, lda, ldb, splits, stream);
       default: return launch_gemm<BN, false, false, 7u>(A, B, epi, M, N, K, lda, ldb, splits, stream);
     }
@@ -124,7 +140,11 @@ static int dispatch_feat(const void* A, const void* B, const GemmEpi& epi, int M
 
 template <bool MN>
 static int dispatch_bn(const void* A, const void* B, const GemmEpi& epi, int M, int N, int K, int lda, int ldb, int splits, cudaStream_t stream) {
-  switch (choose_bn(N)) {
+  const int bn = choose_bn(N, MN);
+  if constexpr (!MN) {
+    if (bn == 160) return dispatch_feat<160, false>(A, B, epi, M, N, K, lda, ldb, splits, stream);
+  }
+  switch (bn) {
     case 64: return dispatch_feat<64, MN>(A, B, epi, M, N, K, lda, ldb, splits, stream);
     case 128: return dispatch_feat<128, MN>(A, B, epi, M, N, K, lda, ldb, splits, stream);
     case 192: return dispatch_feat<192, MN>(A, B, epi, M, N, K, lda, ldb, splits, stream);

@@ -20,6 +20,7 @@
 #include "dropout.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <string.h>
 
 namespace tfasr {
@@ -66,6 +67,7 @@ struct GemmEpi {
   int atomic_out;       // 1: atomicAdd into f32 C (split-K partial sums / gradient accumulation)
   int tma_store;        // 1: C leaves through SMEM staging + cp.async.bulk.tensor stores (coalesced, clipped by hardware)
   int tma_side;         // 1: residual, 2: mul arrives through a TMA load into the staging buffer ahead of the accumulator
+  int tma_aux;          // 1: the pre-activation copy leaves through its own staging buffer + TMA store
 #ifdef TFASR_GEMM_TRACE
   unsigned long long* trace;
 #endif
@@ -78,6 +80,17 @@ __device__ __forceinline__ float sigmoidf_(float x) {
   return fmaf(0.5f, t, 0.5f);
 }
 
+// two sigmoids per MUFU op: tanh.approx.f16x2 (11-bit mantissa: error 2^-12 on the sigmoid, far below the bf16 rounding of the output);
+// the epilogue of the activation GEMMs is MUFU-bound otherwise (16 tanh per 16 columns, 8 warps)
+__device__ __forceinline__ void sigmoid2_(float a, float b, float& sa, float& sb) {
+  const __half2 h = __floats2half2_rn(0.5f * a, 0.5f * b);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&h)));
+  const float2 tf = __half22float2(*reinterpret_cast<const __half2*>(&t));
+  sa = fmaf(0.5f, tf.x, 0.5f);
+  sb = fmaf(0.5f, tf.y, 0.5f);
+}
+
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kBM = 128;
 constexpr int kBK = 64;
@@ -87,7 +100,7 @@ constexpr int kBK = 64;
 // tiles, so the epilogue of tile i overlaps the TMA + MMA of tile i+1.
 template <int BN>
 struct GemmSmem {
-  static constexpr int STAGES = (BN >= 256) ? 3 : ((BN >= 192) ? 4 : ((BN >= 128) ? 5 : 6));
+  static constexpr int STAGES = (BN >= 256) ? 3 : ((BN >= 160) ? 4 : ((BN >= 128) ? 5 : 6));
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int STAGE_OUT_BYTES = 8 /*epilogue warps*/ * 2 /*buffers*/ * 32 /*rows*/ * 128 /*bytes*/;
@@ -120,12 +133,17 @@ __device__ __forceinline__ void store16(__nv_bfloat16* p, const float* f) {
   *reinterpret_cast<uint4*>(p + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
 // Epilogue feature classes (compile-time): what a class does not name is not in the instruction stream.
 //   0 lean: alpha, bias, bf16 / f32 output (TMA store, TMA reduce-add, or direct)      -> projections, dgrad, wgrad, joint logits
 //   1 fwd : + activation, pre-activation copy (aux), GLU                               -> FFN-1, pointwise conv 1
 //   2 dr  : + dropout, residual (side input by TMA)                                    -> FFN-2, attention output, pointwise conv 2, linear
 //   4 bwd : + multiply by f'(saved) (side input by TMA), column sums (bias gradients)  -> backward epilogues
-//   7 all
+//   3 = 1|2 (FFN-1: swish + aux + dropout),  6 = 2|4 (FFN backward: dropout mask * swish'),  7 all
 template <uint32_t FEAT>
 struct EpiFeat {
   static constexpr bool fwd = (FEAT & 1u) != 0, dr = (FEAT & 2u) != 0, bwd = (FEAT & 4u) != 0;
@@ -134,7 +152,8 @@ struct EpiFeat {
 template <int BN, bool A_MN, bool B_MN, uint32_t FEAT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                 const __grid_constant__ CUtensorMap tmR, const GemmEpi epi, int M, int N, int K, int splits) {
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmX, const GemmEpi epi, int M, int N, int K,
+                 int splits) {
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = sm100::smem_u32(smem_raw);
@@ -162,6 +181,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     sm100::prefetch_tensormap(&tmB);
     if (epi.tma_store) sm100::prefetch_tensormap(&tmC);
     if (epi.tma_side) sm100::prefetch_tensormap(&tmR);
+    if (epi.tma_aux) sm100::prefetch_tensormap(&tmX);
     for (int i = 0; i < 32; ++i) sm100::mbar_init(&side_bar[i], 1);
     for (int s = 0; s < S::STAGES; ++s) {
       sm100::mbar_init(&full_bar[s], 1);
@@ -269,6 +289,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int side = (F::dr || F::bwd) ? (tma_out ? epi.tma_side : 0) : 0;  // 1 residual / 2 mul staged by TMA ahead of the accumulator
     const int gbytes = c_f32 ? 4096 : 2048;  // one group = 32 rows x 32 columns: 128-byte (f32, 128B swizzle) or 64-byte (bf16, 64B swizzle) rows
     const int nbuf_mask = c_f32 ? 1 : 3;     // staging buffers per warp: 2 (f32) or 4 (bf16) -> every bf16 group of a tile has its own
+    const int aux_tma = F::fwd ? (tma_out ? epi.tma_aux : 0) : 0;  // the aux copy takes every second buffer
     uint8_t* sbuf0 = sOut + ew * 8192;
     const int etid = threadIdx.x - 64;  // 0..255 over the epilogue warps
     [[maybe_unused]] const bool has_drop = F::dr && epi.drop_p > 0.f;
@@ -286,6 +307,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = m_blk * kBM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < M;
+      [[maybe_unused]] const uint32_t rowkey = has_drop ? dropout_rowkey(seed, (unsigned long long)row) : 0u;
       const uint32_t tmem_row = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
       const int n_cols = min(BN, N - n_blk * BN);  // valid columns of this tile
       const int n_groups = (n_cols + 31) >> 5;
@@ -316,14 +338,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int gi = 0; gi < my_groups && num_k > 0; ++gi) {
         const int cg0 = c_begin + gi * 32;
-        uint8_t* sbuf = sbuf0 + (gi & nbuf_mask) * gbytes;
+        uint8_t* sbuf = sbuf0 + ((aux_tma ? 2 * gi : gi) & nbuf_mask) * gbytes;
+        [[maybe_unused]] uint8_t* abuf = sbuf0 + ((2 * gi + 1) & 3) * 2048;
         uint32_t r[2][16];
         const bool two = cg0 + 16 < c_end;
         sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)cg0, r[0]);
         if (two) sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)(cg0 + 16), r[1]);
-        if (tma_out && c_f32 && gi >= 2) {
-          // third / fourth f32 group: the store issued two groups ago must have finished reading this buffer
-          if (lane == 0) sm100::tma_store_wait_read<1>();
+        if (tma_out && gi >= 2 && (c_f32 || aux_tma)) {
+          // buffers come round again: the stores issued two groups ago must have finished reading them
+          if (lane == 0) {
+            if (aux_tma) sm100::tma_store_wait_read<2>();
+            else sm100::tma_store_wait_read<1>();
+          }
           __syncwarp();
         }
         if (side) {
@@ -356,7 +382,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if constexpr (F::fwd) {
-            if (epi.aux && row_ok) {
+            if (aux_tma) {
+              uint8_t* arow = abuf + lane * 64;
+              const int swz = (lane >> 1) & 3;
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk[j] = pack2(v[2 * j], v[2 * j + 1]);
+              *reinterpret_cast<uint4*>(arow + (((2 * ci) ^ swz) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(arow + (((2 * ci + 1) ^ swz) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else if (epi.aux && row_ok) {
               __nv_bfloat16* aux_row = reinterpret_cast<__nv_bfloat16*>(epi.aux) + (size_t)row * epi.ld_aux;
               if (full && (epi.ld_aux & 7) == 0) store16(aux_row + n0, v);
               else {
@@ -368,8 +402,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (epi.glu) {
               float o[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = v[2 * j] * sigmoidf_(v[2 * j + 1]);
-              if (row_ok) {
+              for (int j = 0; j < 8; j += 2) {
+                float s0, s1;
+                sigmoid2_(v[2 * j + 1], v[2 * j + 3], s0, s1);
+                o[j] = v[2 * j] * s0;
+                o[j + 1] = v[2 * j + 2] * s1;
+              }
+              if (tma_out) {  // 16 output columns per group: 32-byte rows, no swizzle
+                *reinterpret_cast<uint4*>(sbuf + lane * 32 + ci * 16) = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+              } else if (row_ok) {
                 __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(epi.c) + (size_t)row * epi.ldc + (n0 >> 1);
                 if (full) {
                   uint32_t pk[4];
@@ -390,7 +431,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int act = epi.act;
             if (act == 1) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = v[j] * sigmoidf_(v[j]);
+              for (int j = 0; j < 16; j += 2) {
+                float s0, s1;
+                sigmoid2_(v[j], v[j + 1], s0, s1);
+                v[j] *= s0;
+                v[j + 1] *= s1;
+              }
             } else if (act == 2) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -431,9 +477,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int mul_mode = epi.mul_mode;
               if (mul_mode == 1) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float sg = sigmoidf_(z[j]);
-                  v[j] *= sg * (1.0f + z[j] * (1.0f - sg));  // d swish / dz
+                for (int j = 0; j < 16; j += 2) {
+                  float s0, s1;
+                  sigmoid2_(z[j], z[j + 1], s0, s1);
+                  v[j] *= s0 * (1.0f + z[j] * (1.0f - s0));  // d swish / dz
+                  v[j + 1] *= s1 * (1.0f + z[j + 1] * (1.0f - s1));
                 }
               } else if (mul_mode == 2) {
 #pragma unroll
@@ -446,10 +494,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if constexpr (F::dr) {
             if (has_drop) {
-              const unsigned long long base = (unsigned long long)row * (unsigned long long)N + (unsigned long long)n0;
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                const uint32_t hsh = dropout_hash(seed, base + j);  // base is even (n0 % 16 == 0, N even)
+                const uint32_t hsh = dropout_hash(rowkey, (uint32_t)(n0 + j));  // n0 % 16 == 0: one hash per column pair
                 v[j] = ((hsh & 0xFFFFu) >= drop_thr) ? v[j] * keep_scale : 0.f;
                 v[j + 1] = ((hsh >> 16) >= drop_thr) ? v[j + 1] * keep_scale : 0.f;
               }
@@ -529,8 +576,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           sm100::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
+            if (aux_tma) {
+              sm100::tma_store_2d(&tmX, abuf, n_blk * BN + cg0, row0);
+              sm100::tma_store_commit();
+            }
             if (epi.atomic_out) sm100::tma_reduce_add_2d(&tmC, sbuf, n_blk * BN + cg0, row0);
-            else sm100::tma_store_2d(&tmC, sbuf, n_blk * BN + cg0, row0);
+            else sm100::tma_store_2d(&tmC, sbuf, (F::fwd && epi.glu) ? ((n_blk * BN + cg0) >> 1) : (n_blk * BN + cg0), row0);
             sm100::tma_store_commit();
           }
           if constexpr (F::bwd) {
@@ -588,23 +639,33 @@ int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, int N, 
   if (!B_MN) ok = ok && make_tmap_bf16_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, kBK);
   else ok = ok && make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, kBK, 64);
   if (!ok) return TFASR_INVALID_VALUE;
-  CUtensorMap tmC, tmR;
+  CUtensorMap tmC, tmR, tmX;
   memset(&tmC, 0, sizeof(tmC));
   memset(&tmR, 0, sizeof(tmR));
+  memset(&tmX, 0, sizeof(tmX));
   GemmEpi e2 = epi;
   e2.tma_store = 0;
   e2.tma_side = 0;
+  e2.tma_aux = 0;
 #ifdef TFASR_GEMM_TRACE
   e2.trace = g_gemm_trace_host;
 #endif
-  if (!epi.glu && (!epi.atomic_out || epi.c_f32)) {
+  if (epi.glu) {
+    // GLU halves the width: 16 output columns per 32-column accumulator group
+    if ((FEAT & 1u) && !epi.c_f32 && !epi.atomic_out && ((N / 2) % 8 == 0) &&
+        make_tmap_2d(&tmC, epi.c, 2, (uint64_t)M, (uint64_t)(N / 2), (uint64_t)epi.ldc, 32, 16))
+      e2.tma_store = 1;
+  } else if (!epi.atomic_out || epi.c_f32) {
     const int eb = epi.c_f32 ? 4 : 2;
     if (make_tmap_2d(&tmC, epi.c, eb, (uint64_t)M, (uint64_t)N, (uint64_t)epi.ldc, 32, 32) && (N % (16 / eb) == 0)) e2.tma_store = 1;
   }
   if (e2.tma_store && !epi.c_f32) {
+    if ((FEAT & 1u) && epi.aux && (N % 8 == 0) && make_tmap_2d(&tmX, epi.aux, 2, (uint64_t)M, (uint64_t)N, (uint64_t)epi.ld_aux, 32, 32)) e2.tma_aux = 1;
     // one bf16 side input of the output's shape rides a TMA load into the staging buffer (residual first, else the `mul` operand)
-    if ((FEAT & 2u) && epi.residual && make_tmap_2d(&tmR, epi.residual, 2, (uint64_t)M, (uint64_t)N, (uint64_t)epi.ld_res, 32, 32)) e2.tma_side = 1;
-    else if ((FEAT & 4u) && epi.mul && make_tmap_2d(&tmR, epi.mul, 2, (uint64_t)M, (uint64_t)N, (uint64_t)epi.ld_mul, 32, 32)) e2.tma_side = 2;
+    if (!e2.tma_aux && !epi.glu) {
+      if ((FEAT & 2u) && epi.residual && make_tmap_2d(&tmR, epi.residual, 2, (uint64_t)M, (uint64_t)N, (uint64_t)epi.ld_res, 32, 32)) e2.tma_side = 1;
+      else if ((FEAT & 4u) && epi.mul && make_tmap_2d(&tmR, epi.mul, 2, (uint64_t)M, (uint64_t)N, (uint64_t)epi.ld_mul, 32, 32)) e2.tma_side = 2;
+    }
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -614,7 +675,7 @@ int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, int N, 
   }
   const long long tiles = (long long)ceil_div(M, kBM) * ceil_div(N, BN) * splits;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  gemm_bf16_kernel<BN, A_MN, B_MN, FEAT><<<grid, kGemmThreads, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, e2, M, N, K, splits);
+  gemm_bf16_kernel<BN, A_MN, B_MN, FEAT><<<grid, kGemmThreads, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, tmX, e2, M, N, K, splits);
   count_launch();
   return check_launch();
 }
@@ -624,9 +685,21 @@ int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, int N, 
   template int launch_gemm<BN, false, false, 0u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   template int launch_gemm<BN, false, false, 1u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   template int launch_gemm<BN, false, false, 2u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  template int launch_gemm<BN, false, false, 3u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   template int launch_gemm<BN, false, false, 4u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  template int launch_gemm<BN, false, false, 6u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   template int launch_gemm<BN, false, false, 7u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   template int launch_gemm<BN, true, true, 0u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t);   \
   template int launch_gemm<BN, true, true, 7u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t);
+
+// K-major operands only (MN-major B boxes are 64 columns wide: tile widths that are not a multiple of 64 are not offered there)
+#define TFASR_GEMM_INSTANTIATE_KMAJOR(BN)                                                                                            \
+  template int launch_gemm<BN, false, false, 0u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  template int launch_gemm<BN, false, false, 1u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  template int launch_gemm<BN, false, false, 2u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  template int launch_gemm<BN, false, false, 3u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  template int launch_gemm<BN, false, false, 4u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  template int launch_gemm<BN, false, false, 6u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
+  template int launch_gemm<BN, false, false, 7u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t);
 
 }  // namespace tfasr

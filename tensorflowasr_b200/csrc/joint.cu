@@ -69,6 +69,78 @@ __global__ void __launch_bounds__(512) joint_reduce_bwd_kernel(const __nv_bfloat
   for (int i = threadIdx.x; i < U1 * J; i += blockDim.x) atomicAdd(dpb + i, s_dp[i]);
 }
 
+
+// Wide variant (the one the step uses): the lattice of one utterance is streamed once with 16-byte loads.  Threads = (J/8 column vectors) x UW
+// label lanes; a thread keeps the prediction-side partial sums of its <= 9 labels x 8 columns in registers over the CTA's frames, the
+// encoder-side sums go through a small SMEM reduction per frame.  HBM-bound: 2 bytes per lattice node and joint column.
+constexpr int kJrNU = 9;
+template <int UW>
+__global__ void __launch_bounds__(512) joint_reduce_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dz, float* __restrict__ de,
+                                                                     float* __restrict__ dp, int T, int U1, int J, int tch) {
+  extern __shared__ float s_e[];  // [UW][J]
+  const int JV = J >> 3;
+  const int cv = threadIdx.x % JV, uw = threadIdx.x / JV;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * tch, t1 = min(T, t0 + tch);
+  float dpa[kJrNU][8];
+#pragma unroll
+  for (int k = 0; k < kJrNU; ++k)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dpa[k][c] = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const __nv_bfloat16* base = dz + (((size_t)b * T + t) * U1) * J + cv * 8;
+    uint4 raw[kJrNU];
+#pragma unroll
+    for (int k = 0; k < kJrNU; ++k) {
+      const int u = uw + UW * k;
+      raw[k] = (u < U1) ? ld_stream_u4(base + (size_t)u * J) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kJrNU; ++k) {
+      const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float lo = __uint_as_float(w[c] << 16), hi = __uint_as_float(w[c] & 0xFFFF0000u);
+        e[2 * c] += lo;
+        e[2 * c + 1] += hi;
+        dpa[k][2 * c] += lo;
+        dpa[k][2 * c + 1] += hi;
+      }
+    }
+    float4* se = reinterpret_cast<float4*>(s_e + uw * J + cv * 8);
+    se[0] = make_float4(e[0], e[1], e[2], e[3]);
+    se[1] = make_float4(e[4], e[5], e[6], e[7]);
+    __syncthreads();
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < UW; ++w) acc += s_e[w * J + j];
+      de[((size_t)b * T + t) * J + j] = acc;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < kJrNU; ++k) {
+    const int u = uw + UW * k;
+    if (u < U1) {
+      float4* dst = reinterpret_cast<float4*>(dp + ((size_t)b * U1 + u) * J + cv * 8);
+      atomicAdd(dst, make_float4(dpa[k][0], dpa[k][1], dpa[k][2], dpa[k][3]));  // red.global.add.v4.f32
+      atomicAdd(dst + 1, make_float4(dpa[k][4], dpa[k][5], dpa[k][6], dpa[k][7]));
+    }
+  }
+}
+
+template <int UW>
+static int launch_joint_reduce_wide(const __nv_bfloat16* dz, float* de, float* dp, int B, int T, int U1, int J, cudaStream_t stream) {
+  const int threads = (J / 8) * UW;
+  const int chunks = T < 5 ? 1 : 5;  // ~1 CTA per SM at B = 32; each keeps 9 x 16-byte loads per thread in flight
+  const int tch = (T + chunks - 1) / chunks;
+  joint_reduce_bwd_wide_kernel<UW><<<dim3((unsigned)ceil_div(T, tch), B), threads, sizeof(float) * UW * J, stream>>>(dz, de, dp, T, U1, J, tch);
+  count_launch();
+  return check_launch();
+}
+
 }  // namespace tfasr
 
 using namespace tfasr;
@@ -85,6 +157,14 @@ extern "C" int tfasr_joint_tanh_fwd(const void* e, const void* p, void* h, int32
 extern "C" int tfasr_joint_reduce_bwd(const void* dz, float* de, float* dp, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream) {
   if (!dz || !de || !dp || B < 0 || T < 1 || U1 < 1 || J < 2 || (J & 1) || B > 65535) return TFASR_INVALID_VALUE;
   if (B == 0) return TFASR_OK;
+  if ((J & 7) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0 && (reinterpret_cast<uintptr_t>(dp) & 15) == 0) {
+    const __nv_bfloat16* dzb = static_cast<const __nv_bfloat16*>(dz);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int jv = J / 8;
+    // 72 + 36 live registers per thread: at most 512 threads per CTA
+    if (U1 <= 8 * kJrNU && jv * 8 <= 512) return launch_joint_reduce_wide<8>(dzb, de, dp, B, T, U1, J, st);
+    if (U1 <= 16 * kJrNU && jv * 16 <= 512) return launch_joint_reduce_wide<16>(dzb, de, dp, B, T, U1, J, st);
+  }
   const size_t smem = sizeof(float) * (size_t)U1 * J;
   if (smem > 200 * 1024) return TFASR_INVALID_VALUE;
   static bool attr_set = false;

@@ -55,8 +55,13 @@ def main():
         cases.append((f"gemm_{name}_plain_{m}x{n}x{k}", lambda a=a, b=b, out=out: kernels.gemm(a, b, out=out)))
         cases.append((f"gemm_{name}_bias", lambda a=a, b=b, out=out, bias=bias: kernels.gemm(a, b, out=out, bias=bias)))
         if name == "ffn1":
+            cases.append((f"gemm_{name}_bias_swish", lambda a=a, b=b, out=out, bias=bias: kernels.gemm(a, b, out=out, bias=bias, activation="swish")))
+            cases.append((f"gemm_{name}_bias_aux", lambda a=a, b=b, out=out, bias=bias, aux=aux: kernels.gemm(a, b, out=out, bias=bias, aux=aux)))
             cases.append((f"gemm_{name}_bias_swish_aux", lambda a=a, b=b, out=out, bias=bias, aux=aux: kernels.gemm(a, b, out=out, bias=bias, activation="swish", aux=aux)))
         if name in ("ffn2", "out"):
+            cases.append((f"gemm_{name}_bias_res", lambda a=a, b=b, out=out, bias=bias, r=res_in: kernels.gemm(a, b, out=out, bias=bias, residual=r, residual_scale=0.5)))
+            cases.append((f"gemm_{name}_bias_drop", lambda a=a, b=b, out=out, bias=bias, seed=seed: kernels.gemm(
+                a, b, out=out, bias=bias, dropout_p=0.1, dropout_seed=seed, dropout_salt=3)))
             cases.append((f"gemm_{name}_bias_drop_res", lambda a=a, b=b, out=out, bias=bias, r=res_in, seed=seed: kernels.gemm(
                 a, b, out=out, bias=bias, residual=r, residual_scale=0.5, dropout_p=0.1, dropout_seed=seed, dropout_salt=3)))
         cases.append((f"cublas_{name}", lambda a=a, b=b: torch.matmul(a, b.t())))
