@@ -216,6 +216,26 @@ int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* scale, const 
                        const float* sums, float count, void* dx, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Parameter-side kernels: the whole optimizer update and all bf16 weight-operand copies are one launch each.
+ *   tfasr_adamw_flat_f32 : AdamW (Keras Adam + decoupled weight decay, small.yml.j2:73-87; per-variable `optimizer.apply`,
+ *                          base_model.py:196-215) over flat fp32 buffers p, g, m, v [n] (n % 4 == 0, 16-byte aligned);
+ *                          g' = g * grad_scale + 2 * l2 * p where l2_mask[i] != 0 (Keras l2 regularizers, conformer.py:27);
+ *                          lr / step are device scalars (step = 1, 2, ...); zero_grad != 0 clears g for the next step.
+ *   tfasr_pack_weights   : table (device memory) of n_entries tfasr_pack_entry; entry = fp32 [K, N] source scattered to
+ *                          dst_w[k, c0 + n * cs] (bf16, or fp32 when flags & 1) and dst_wt[c0 + n * cs, k] (bf16); NULL = skip.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tfasr_pack_entry {
+  const float* src;
+  void* dst_w;
+  void* dst_wt;
+  int32_t K, N, src_ld, ldw, ldwt, c0, cs, flags;
+} tfasr_pack_entry;
+int tfasr_adamw_flat_f32(float* p, float* g, float* m, float* v, const uint8_t* l2_mask, int64_t n, const float* lr, const float* step,
+                         float beta1, float beta2, float eps, float weight_decay, float l2, float grad_scale, int32_t zero_grad,
+                         tfasr_stream_t stream);
+int tfasr_pack_weights(const void* table, int32_t n_entries, tfasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Causal depthwise 1-D convolution of the ConvModule (convolution.py:159-216, conformer.py:311-323,370): channels-last bf16 [B,T,C],
  * w [K,C] f32 (keras depthwise kernel [K,C,1]), bias [C] f32 or NULL.  bwd writes dx and accumulates (+=) dw [K,C] / dbias [C] (or NULL).
  * ---------------------------------------------------------------------------------------------- */

@@ -38,15 +38,21 @@ class TransformerSchedule:
         return lr
 
 
-def make_optimizer(model: nn.Module, learning_rate=None, beta_1=0.9, beta_2=0.98, epsilon=1e-9, weight_decay=1e-6):
-    """Keras Adam as configured in small.yml.j2:73-87 (decoupled weight decay), on torch's fused multi-tensor Adam."""
+def make_optimizer(model: nn.Module, learning_rate=None, beta_1=0.9, beta_2=0.98, epsilon=1e-9, weight_decay=1e-6, flat=True):
+    """Keras Adam as configured in small.yml.j2:73-87 (decoupled weight decay): on CUDA the single-launch FlatAdamW (optim.py), on CPU
+    (tests of the host logic) torch's AdamW."""
     lr0 = learning_rate(1) if callable(learning_rate) else (learning_rate or 1e-3)
     params = [p for p in model.parameters() if p.requires_grad]
     on_gpu = params[0].is_cuda
     # lr lives in a device tensor so that a captured CUDA graph picks up the schedule's new value at every replay
     lr = torch.tensor(float(lr0), device=params[0].device) if on_gpu else lr0
-    opt = torch.optim.AdamW(params, lr=lr, betas=(beta_1, beta_2), eps=epsilon, weight_decay=weight_decay or 0.0, fused=on_gpu,
-                            capturable=on_gpu)
+    if on_gpu and flat:
+        from .optim import FlatAdamW
+
+        opt = FlatAdamW(params, lr=lr, betas=(beta_1, beta_2), eps=epsilon, weight_decay=weight_decay or 0.0)  # one launch per step
+    else:
+        opt = torch.optim.AdamW(params, lr=lr, betas=(beta_1, beta_2), eps=epsilon, weight_decay=weight_decay or 0.0, fused=on_gpu,
+                                capturable=on_gpu)
     opt._tfasr_schedule = learning_rate if callable(learning_rate) else None
     return opt
 
@@ -68,6 +74,7 @@ class BaseModel(nn.Module):
         self._loss_sum = 0.0
         self._loss_count = 0
         self._reducer = None
+        self._flat_opt = False
 
     # ------------------------------------------------------------------ misc surface
     @property
@@ -117,6 +124,20 @@ class BaseModel(nn.Module):
         # every parameter's .grad becomes a view into ONE flat fp32 buffer: the fused kernels accumulate weight gradients straight
         # into it, zeroing is one memset, and the data-parallel all-reduce needs no packing
         self._reducer = tdist.GradientReducer(self.trainable_weights)
+        self._flat_opt = False
+        from .optim import FlatAdamW
+
+        if isinstance(self.optimizer, FlatAdamW):
+            self.optimizer.attach_grads(self._reducer.flat, self._reducer.params)
+            mask = torch.zeros(self._reducer.flat.numel(), dtype=torch.uint8, device=self._reducer.flat.device)
+            by_id = {id(p): n for n, p in self.named_parameters()}
+            off = 0
+            for p in self._reducer.params:
+                if _is_regularized(by_id[id(p)]):
+                    mask[off:off + p.numel()] = 1
+                off += p.numel()
+            self.optimizer.set_l2(mask, self.l2)
+            self._flat_opt = True
         self._graph = None
         self._use_graph = False
         return self
@@ -164,6 +185,12 @@ class BaseModel(nn.Module):
         params = self.trainable_weights
         if self._reducer is not None:
             self._reducer.all_reduce()  # C1: one bucketed NCCL all-reduce (SUM) over NVLink (no-op on one GPU)
+        if self._flat_opt:
+            # l2-regularizer gradient, AdamW and the zeroing of the flat gradient buffer: one kernel
+            if lr_from_host:
+                self._advance_schedule()
+            self.optimizer.step(zero_grad=True)
+            return
         if self.l2:
             reg = [p for n, p in self.named_parameters() if p.requires_grad and p.grad is not None and _is_regularized(n)]
             if reg:

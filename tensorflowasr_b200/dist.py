@@ -59,7 +59,7 @@ class GradientReducer:
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros((total + 3) // 4 * 4, dtype=torch.float32, device=dev)  # padded: float4 kernels run over it
         off = 0
         self.buckets = []  # (start, end, [param indices])
         cur_start, cur_idx = 0, []

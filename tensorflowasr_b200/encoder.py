@@ -265,18 +265,22 @@ class ConformerEncoder(_Params):
 
     # ------------------------------------------------------------------------------------------ fused (sm_100a kernel) path
     def _prepare_packs(self):
-        """bf16 operand copies of the GEMM weights for this forward/backward (weights change every optimizer step)."""
-        packs = {}
-        for b in range(self.num_blocks):
-            for ff in ("ff_module_1", "ff_module_2"):
-                for d in ("dense_1", "dense_2"):
-                    n = f"block_{b}.{ff}.{d}"
-                    packs[n] = fused.WeightPack(self[n + ".kernel"], self[n + ".bias"])
-            packs[f"block_{b}.mhsa_module"] = fused.MhsaPack(self, f"block_{b}.mhsa_module")
-            cm = f"block_{b}.conv_module"
-            packs[cm + ".pw_conv_1"] = fused.GluPack(self[cm + ".pw_conv_1.kernel"], self[cm + ".pw_conv_1.bias"])
-            packs[cm + ".pw_conv_2"] = fused.WeightPack(self[cm + ".pw_conv_2.kernel"], self[cm + ".pw_conv_2.bias"])
-        self._packs = packs
+        """bf16 operand copies of the GEMM weights for this forward/backward (weights change every optimizer step): persistent
+        buffers, refreshed by one batched launch (fused.PackPlan)."""
+        if getattr(self, "_packs", None) is None or self._pack_plan is None:
+            plan = fused.PackPlan()
+            packs = {}
+            for b in range(self.num_blocks):
+                for ff in ("ff_module_1", "ff_module_2"):
+                    for d in ("dense_1", "dense_2"):
+                        n = f"block_{b}.{ff}.{d}"
+                        packs[n] = fused.WeightPack(self[n + ".kernel"], self[n + ".bias"], plan=plan)
+                packs[f"block_{b}.mhsa_module"] = fused.MhsaPack(self, f"block_{b}.mhsa_module", plan)
+                cm = f"block_{b}.conv_module"
+                packs[cm + ".pw_conv_1"] = fused.GluPack(self[cm + ".pw_conv_1.kernel"], self[cm + ".pw_conv_1.bias"], plan)
+                packs[cm + ".pw_conv_2"] = fused.WeightPack(self[cm + ".pw_conv_2.kernel"], self[cm + ".pw_conv_2.bias"], plan=plan)
+            self._packs, self._pack_plan = packs, plan
+        self._pack_plan.run()
 
     def _salt(self, pre, k):
         return (zlib.crc32(pre.encode()) % 1000003) * 64 + k * 2 + 1

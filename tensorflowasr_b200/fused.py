@@ -40,24 +40,77 @@ def _grad(p: torch.Tensor) -> torch.Tensor:
     return p.grad
 
 
+class PackPlan:
+    """All bf16 operand copies of the GEMM weights refreshed by ONE launch (csrc/param_ops.cu: pack_weights_kernel).  Entries name the
+    Parameter (not a view of it) so that the device table can be rebuilt when parameter storage moves (FlatAdamW, .to())."""
+
+    _DT = None
+
+    def __init__(self):
+        self.entries = []  # (param, byte_off, K, N, src_ld, dst_w, ldw, dst_wt, ldwt, c0, cs, flags)
+        self.table = None
+        self._ptrs = None
+
+    def add(self, param, K, N, dst_w=None, dst_wt=None, ldw=0, ldwt=0, c0=0, cs=1, src_ld=None, src_col0=0, f32=False):
+        assert param.dtype == torch.float32 and param.is_contiguous()
+        self.entries.append((param, 4 * src_col0, K, N, N if src_ld is None else src_ld, dst_w, ldw, dst_wt, ldwt, c0, cs, 1 if f32 else 0))
+
+    def _build(self, ptrs):
+        import numpy as np
+
+        if PackPlan._DT is None:
+            PackPlan._DT = np.dtype([("src", "<u8"), ("dst_w", "<u8"), ("dst_wt", "<u8"), ("K", "<i4"), ("N", "<i4"), ("src_ld", "<i4"),
+                                    ("ldw", "<i4"), ("ldwt", "<i4"), ("c0", "<i4"), ("cs", "<i4"), ("flags", "<i4")])
+        arr = np.zeros(len(self.entries), dtype=PackPlan._DT)
+        for i, (prm, off, K, N, sld, dw, ldw, dwt, ldwt, c0, cs, fl) in enumerate(self.entries):
+            arr[i] = (ptrs[i] + off, 0 if dw is None else dw.data_ptr(), 0 if dwt is None else dwt.data_ptr(), K, N, sld, ldw, ldwt, c0, cs, fl)
+        dev = self.entries[0][0].device
+        self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+        self._ptrs = ptrs
+
+    def run(self):
+        if not self.entries:
+            return
+        ptrs = [e[0].data_ptr() for e in self.entries]
+        if ptrs != self._ptrs:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PackPlan: parameter storage moved during CUDA-graph capture")
+            self._build(ptrs)
+        from . import _lib
+
+        lib = _lib.load()
+        _lib.check(lib.tfasr_pack_weights(self.table.data_ptr(), len(self.entries), _lib.stream_ptr(self.table.device)), "tfasr_pack_weights")
+
+
 class WeightPack:
     """bf16 operand copies of one Dense kernel W [K, N] (Keras layout): `wt` = W^T [N, K] for the forward GEMM (B operand,
-    K-major), `w` = W [K, N] for the data-gradient GEMM (dX = dY . W^T: B operand [K, N] with contraction N)."""
+    K-major), `w` = W [K, N] for the data-gradient GEMM (dX = dY . W^T: B operand [K, N] with contraction N).
+    With a `plan` the copies are persistent buffers refreshed by the plan's single launch; without, they are made here."""
 
-
-    def __init__(self, param, bias=None, interleave_glu=False):
-        w = param.detach()
-        if w.dim() > 2:
-            raise ValueError("reshape EinsumDense kernels to 2-D before packing")
+    def __init__(self, param, bias=None, interleave_glu=False, plan: PackPlan = None, shape2d=None):
+        K, N = shape2d if shape2d is not None else param.shape
+        self.param = param
+        self.bias = bias
+        self.shape2d = (K, N)
+        if plan is not None:
+            dev = param.device
+            self.w = torch.empty((K, N), dtype=torch.bfloat16, device=dev)
+            self.wt = torch.empty((N, K), dtype=torch.bfloat16, device=dev)
+            if interleave_glu:
+                D = N // 2
+                plan.add(param, K, D, self.w, self.wt, ldw=N, ldwt=K, c0=0, cs=2, src_ld=N, src_col0=0)
+                plan.add(param, K, D, self.w, self.wt, ldw=N, ldwt=K, c0=1, cs=2, src_ld=N, src_col0=D)
+            else:
+                plan.add(param, K, N, self.w, self.wt, ldw=N, ldwt=K)
+            return
+        w = param.detach().reshape(K, N)
         if interleave_glu:
             # GLU halves (a = cols [0, D), b = cols [D, 2D)) interleaved as (a_0, b_0, a_1, b_1, ...) so that the GEMM epilogue
             # sees each pair in adjacent columns (activations/glu.py:25-28)
-            D = w.shape[1] // 2
-            w = torch.stack([w[:, :D], w[:, D:]], dim=2).reshape(w.shape[0], 2 * D)
+            D = N // 2
+            w = torch.stack([w[:, :D], w[:, D:]], dim=2).reshape(K, N)
         self.w = w.to(torch.bfloat16).contiguous()
         self.wt = w.t().to(torch.bfloat16).contiguous()
-        self.param = param
-        self.bias = bias
 
     # hooks used by the generic Dense backward (overridden by packs that fan out to several parameters)
     def bias_f32(self):
@@ -369,17 +422,27 @@ def conv2d_subsampling(feats, sub, training):
 class QkvPack(WeightPack):
     """Fused Q/K/V projection: one GEMM [D -> 3NH]; its weight / bias gradients fan out to the three Keras EinsumDense layers."""
 
-    def __init__(self, enc, pre):
+    def __init__(self, enc, pre, plan: PackPlan = None):
         m = pre + ".mhsa"
         D, N, H = enc.dmodel, enc.num_heads, enc.head_size
+        NH = N * H
         self.parts = [(enc[f"{m}.{k}.kernel"], enc[f"{m}.{k}.bias"]) for k in ("query", "key", "value")]
-        w = torch.cat([k.detach().reshape(D, N * H) for k, _ in self.parts], dim=1)
-        self.w = w.to(torch.bfloat16).contiguous()
-        self.wt = w.t().to(torch.bfloat16).contiguous()
-        self._bias = torch.cat([b.detach().reshape(N * H) for _, b in self.parts]).float().contiguous()
-        self.param, self.bias = None, self._bias
-        self.D, self.NH = D, N * H
+        self.param, self.D, self.NH = None, D, NH
         self._db = None
+        if plan is not None:
+            dev = self.parts[0][0].device
+            self.w = torch.empty((D, 3 * NH), dtype=torch.bfloat16, device=dev)
+            self.wt = torch.empty((3 * NH, D), dtype=torch.bfloat16, device=dev)
+            self._bias = torch.empty(3 * NH, dtype=torch.float32, device=dev)
+            for i, (wp, bp) in enumerate(self.parts):
+                plan.add(wp, D, NH, self.w, self.wt, ldw=3 * NH, ldwt=D, c0=i * NH)
+                plan.add(bp, 1, NH, self._bias, None, ldw=3 * NH, c0=i * NH, f32=True)
+        else:
+            w = torch.cat([k.detach().reshape(D, NH) for k, _ in self.parts], dim=1)
+            self.w = w.to(torch.bfloat16).contiguous()
+            self.wt = w.t().to(torch.bfloat16).contiguous()
+            self._bias = torch.cat([b.detach().reshape(NH) for _, b in self.parts]).float().contiguous()
+        self.bias = self._bias
 
     def bias_f32(self):
         return self._bias
@@ -400,14 +463,12 @@ class QkvPack(WeightPack):
 
 
 class MhsaPack:
-    def __init__(self, enc, pre):
+    def __init__(self, enc, pre, plan: PackPlan = None):
         m = pre + ".mhsa"
         D, N, H = enc.dmodel, enc.num_heads, enc.head_size
-        self.qkv = QkvPack(enc, pre)
-        self.pos = WeightPack(enc[f"{m}.encoding.kernel"].view(D, N * H), enc[f"{m}.encoding.bias"])
-        self.pos.param = enc[f"{m}.encoding.kernel"]
-        self.out = WeightPack(enc[f"{m}.attention_output.kernel"].view(N * H, D), enc[f"{m}.attention_output.bias"])
-        self.out.param = enc[f"{m}.attention_output.kernel"]
+        self.qkv = QkvPack(enc, pre, plan)
+        self.pos = WeightPack(enc[f"{m}.encoding.kernel"], enc[f"{m}.encoding.bias"], plan=plan, shape2d=(D, N * H))
+        self.out = WeightPack(enc[f"{m}.attention_output.kernel"], enc[f"{m}.attention_output.bias"], plan=plan, shape2d=(N * H, D))
 
 
 class _RelAttentionFn(torch.autograd.Function):
@@ -439,12 +500,17 @@ class GluPack(WeightPack):
     """pw_conv_1 [D, 2D] with its GLU halves interleaved column-wise (a_0, b_0, a_1, b_1, ...) so that the GEMM epilogue applies
     a * sigmoid(b) on adjacent columns; gradients are de-interleaved back into the Keras layout."""
 
-    def __init__(self, param, bias):
-        super().__init__(param, bias, interleave_glu=True)
-        D2 = param.shape[1]
+    def __init__(self, param, bias, plan: PackPlan = None):
+        super().__init__(param, bias, interleave_glu=True, plan=plan)
+        D2 = self.shape2d[1]
         self.D = D2 // 2
-        b = bias.detach().float()
-        self._bias = torch.stack([b[: self.D], b[self.D:]], dim=1).reshape(D2).contiguous()
+        if plan is not None:
+            self._bias = torch.empty(D2, dtype=torch.float32, device=param.device)
+            plan.add(bias, 1, self.D, self._bias, None, ldw=D2, c0=0, cs=2, src_ld=D2, src_col0=0, f32=True)
+            plan.add(bias, 1, self.D, self._bias, None, ldw=D2, c0=1, cs=2, src_ld=D2, src_col0=self.D, f32=True)
+        else:
+            b = bias.detach().float()
+            self._bias = torch.stack([b[: self.D], b[self.D:]], dim=1).reshape(D2).contiguous()
         self._db = None
 
     def bias_f32(self):

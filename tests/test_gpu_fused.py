@@ -304,3 +304,70 @@ def test_dwconv_kernels_vs_torch():
     _close(dx, xr.grad)
     _close(dw, wr.grad, 5e-3)
     _close(db, br.grad, 5e-3)
+
+
+def test_flat_adamw_matches_torch_adamw():
+    """One-launch AdamW over flat buffers (csrc/param_ops.cu) vs torch.optim.AdamW, incl. the l2-regularizer gradient and zeroing."""
+    from tensorflowasr_b200.optim import FlatAdamW
+
+    torch.manual_seed(0)
+    shapes = [(37, 5), (144,), (3, 7, 11), (1,)]
+    ps = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    l2 = 1e-3
+    opt = FlatAdamW(ps, lr=3e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-2)
+    topt = torch.optim.AdamW(ref, lr=3e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-2)
+    mask = torch.zeros(opt.flat_p.numel(), dtype=torch.uint8, device="cuda")
+    mask[: ps[0].numel()] = 1  # only the first tensor carries the regularizer
+    opt.set_l2(mask, l2)
+    for it in range(5):
+        gs = [torch.randn_like(p) for p in ps]
+        for p, r, g in zip(ps, ref, gs):
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            r.grad = g.clone()
+        ref[0].grad.add_(ref[0].detach(), alpha=2 * l2)
+        opt.step(zero_grad=True)
+        topt.step()
+        for p, r in zip(ps, ref):
+            assert torch.allclose(p.detach(), r.detach(), rtol=2e-5, atol=2e-6), (it, (p - r).abs().max())
+            assert float(p.grad.abs().max()) == 0.0
+    # parameters are views of one buffer
+    assert ps[1].data_ptr() == opt.flat_p.data_ptr() + 4 * ps[0].numel()
+
+
+def test_pack_plan_matches_eager_packs():
+    """Batched weight-pack launch (Q|K|V concatenation, GLU interleave, transposes) vs the per-tensor torch packing."""
+    from tensorflowasr_b200 import fused
+
+    model = _mini_model(num_blocks=1)
+    enc = model.encoder
+    plan = fused.PackPlan()
+    pre = "block_0"
+    lazy = {
+        "ff": fused.WeightPack(enc[pre + ".ff_module_1.dense_1.kernel"], enc[pre + ".ff_module_1.dense_1.bias"], plan=plan),
+        "mhsa": fused.MhsaPack(enc, pre + ".mhsa_module", plan),
+        "glu": fused.GluPack(enc[pre + ".conv_module.pw_conv_1.kernel"], enc[pre + ".conv_module.pw_conv_1.bias"], plan),
+    }
+    plan.run()
+    torch.cuda.synchronize()
+    eager = {
+        "ff": fused.WeightPack(enc[pre + ".ff_module_1.dense_1.kernel"], enc[pre + ".ff_module_1.dense_1.bias"]),
+        "mhsa": fused.MhsaPack(enc, pre + ".mhsa_module"),
+        "glu": fused.GluPack(enc[pre + ".conv_module.pw_conv_1.kernel"], enc[pre + ".conv_module.pw_conv_1.bias"]),
+    }
+    pairs = [(lazy["ff"], eager["ff"]), (lazy["mhsa"].qkv, eager["mhsa"].qkv), (lazy["mhsa"].pos, eager["mhsa"].pos),
+             (lazy["mhsa"].out, eager["mhsa"].out), (lazy["glu"], eager["glu"])]
+    for a, b in pairs:
+        assert torch.equal(a.w, b.w) and torch.equal(a.wt, b.wt)
+    assert torch.equal(lazy["mhsa"].qkv._bias, eager["mhsa"].qkv._bias)
+    assert torch.equal(lazy["glu"]._bias, eager["glu"]._bias)
+    # the table follows the parameters when their storage moves
+    with torch.no_grad():
+        p = enc[pre + ".ff_module_1.dense_1.kernel"]
+        p.data = (p.data * 2).clone()
+    plan.run()
+    torch.cuda.synchronize()
+    assert torch.equal(lazy["ff"].w, (p.detach()).to(torch.bfloat16))
