@@ -131,19 +131,25 @@ __global__ void __launch_bounds__(256) scale_mask_colsum_kernel(const __nv_bfloa
                                                                 float scale, float drop_p, const unsigned long long* __restrict__ seed_ptr,
                                                                 unsigned long long salt, int rows_per_block) {
   // block = [rows_per_block rows] x all columns; thread t handles column pair (2t, 2t+1) (+ stride blockDim for wide N)
+  extern __shared__ uint32_t s_rowkey[];  // dropout row keys of this block's rows (64-bit work once per row, not per element)
   const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   const unsigned long long seed = (drop_p > 0.f && seed_ptr) ? (*seed_ptr + salt) : salt;
   const uint32_t drop_thr = dropout_threshold(drop_p);
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
+  if (drop_p > 0.f) {
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) s_rowkey[r - r0] = dropout_rowkey(seed, (unsigned long long)r);
+    __syncthreads();
+  }
   for (int c = 2 * threadIdx.x; c < N; c += 2 * blockDim.x) {
     float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
     for (int r = r0; r < r1; ++r) {
       const size_t idx = (size_t)r * N + c;
       const __nv_bfloat162 vi = *reinterpret_cast<const __nv_bfloat162*>(in + idx);
       float a = __low2float(vi) * scale, b = __high2float(vi) * scale;
       if (drop_p > 0.f) {
-        const uint32_t hsh = dropout_hash(dropout_rowkey(seed, (unsigned long long)r), (uint32_t)c);  // c is even: one hash serves the column pair
+        const uint32_t hsh = dropout_hash(s_rowkey[r - r0], (uint32_t)c);  // c is even: one hash serves the column pair
         a = ((hsh & 0xFFFFu) >= drop_thr) ? a * keep_scale : 0.f;
         b = ((hsh >> 16) >= drop_thr) ? b * keep_scale : 0.f;
       }
@@ -160,6 +166,75 @@ __global__ void __launch_bounds__(256) scale_mask_colsum_kernel(const __nv_bfloa
       atomicAdd(colsum + c, s0);
       atomicAdd(colsum + c + 1, s1);
     }
+  }
+}
+
+// Vector variant (N % 8 == 0, N / 8 <= 256): thread = (row lane, 8-column vector), 16-byte loads / stores, column sums reduced in SMEM.
+__global__ void __launch_bounds__(256) scale_mask_colsum_vec_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ add,
+                                                                    __nv_bfloat16* __restrict__ out, float* __restrict__ colsum, int M, int N,
+                                                                    float scale, float drop_p, const unsigned long long* __restrict__ seed_ptr,
+                                                                    unsigned long long salt, int rows_per_block) {
+  extern __shared__ float s_col[];  // [N]
+  const int NV = N >> 3, RL = blockDim.x / NV;
+  const int cv = threadIdx.x % NV, rl = threadIdx.x / NV;
+  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const unsigned long long seed = (drop_p > 0.f && seed_ptr) ? (*seed_ptr + salt) : salt;
+  const uint32_t drop_thr = dropout_threshold(drop_p);
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  if (colsum) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_col[i] = 0.f;
+    __syncthreads();
+  }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < RL) {
+    for (int r = r0 + rl; r < r1; r += RL) {
+      const size_t idx = (size_t)r * N + cv * 8;
+      const uint4 raw = *reinterpret_cast<const uint4*>(in + idx);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[2 * j] = __uint_as_float(w[j] << 16) * scale;
+        v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u) * scale;
+      }
+      if (drop_p > 0.f) {
+        const uint32_t key = dropout_rowkey(seed, (unsigned long long)r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t hsh = dropout_hash(key, (uint32_t)(cv * 8 + 2 * j));
+          v[2 * j] = ((hsh & 0xFFFFu) >= drop_thr) ? v[2 * j] * keep_scale : 0.f;
+          v[2 * j + 1] = ((hsh >> 16) >= drop_thr) ? v[2 * j + 1] * keep_scale : 0.f;
+        }
+      }
+      if (add) {
+        const uint4 ra = *reinterpret_cast<const uint4*>(add + idx);
+        const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[2 * j] += __uint_as_float(wa[j] << 16);
+          v[2 * j + 1] += __uint_as_float(wa[j] & 0xFFFF0000u);
+        }
+      }
+      if (out) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+  if (colsum) {
+    if (rl < RL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_col[cv * 8 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(colsum + i, s_col[i]);
   }
 }
 
@@ -235,8 +310,18 @@ extern "C" int tfasr_scale_mask_colsum(const void* in, const void* add, void* ou
                                        const unsigned long long* seed_ptr, unsigned long long salt, tfasr_stream_t stream) {
   if (!in || (!out && !colsum) || M < 0 || N < 2 || (N & 1)) return TFASR_INVALID_VALUE;  // out == NULL: column sums only
   if (M == 0) return TFASR_OK;
+  if ((N & 7) == 0 && (N >> 3) <= 256 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const int RL = 256 / (N >> 3);
+    int rows_per_block = RL * 4;
+    while ((long long)ceil_div(M, rows_per_block) > 8LL * kNumSMs) rows_per_block *= 2;  // bounded atomic traffic on colsum
+    scale_mask_colsum_vec_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, sizeof(float) * N, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(out), colsum, M, N, scale, dropout_p,
+        seed_ptr, salt, rows_per_block);
+    count_launch();
+    return check_launch();
+  }
   const int rows_per_block = 32;
-  scale_mask_colsum_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  scale_mask_colsum_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, sizeof(uint32_t) * rows_per_block, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(out), colsum, M, N, scale, dropout_p,
       seed_ptr, salt, rows_per_block);
   count_launch();

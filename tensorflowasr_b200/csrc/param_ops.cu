@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackEntry* __re
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int kt_n = (e.K + 31) / 32, nt_n = (e.N + 31) / 32;
-  for (int t = 0; t < kt_n * nt_n; ++t) {
+  for (int t = blockIdx.y; t < kt_n * nt_n; t += gridDim.y) {  // tiles of one matrix are spread over gridDim.y CTAs
     const int k0 = (t / nt_n) * 32, n0 = (t % nt_n) * 32;
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
@@ -123,7 +123,7 @@ extern "C" int tfasr_pack_weights(const void* table, int32_t n_entries, tfasr_st
   static_assert(sizeof(PackEntry) == sizeof(tfasr_pack_entry), "C ABI struct layout");
   if (!table || n_entries < 0) return TFASR_INVALID_VALUE;
   if (n_entries == 0) return TFASR_OK;
-  pack_weights_kernel<<<n_entries, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const PackEntry*>(table));
+  pack_weights_kernel<<<dim3((unsigned)n_entries, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const PackEntry*>(table));
   count_launch();
   return check_launch();
 }

@@ -241,6 +241,46 @@ def linear(x, pack, activation=None, residual=None, factor=1.0, drop_p=0.0, salt
     return _LinearFn.apply(x, pack, activation, residual, float(factor), float(drop_p), int(salt), seed, anchor)
 
 
+# ------------------------------------------------------------------------------------------------ prediction-network LSTM
+class _LstmFn(torch.autograd.Function):
+    """keras LSTM over the label axis (base_transducer.py:74-88): x . W_ih + b on the tcgen05 GEMM, the time loop on the cluster kernel of
+    csrc/lstm.cu, and the weight / input gradients as GEMMs over all steps at once."""
+
+    @staticmethod
+    def forward(ctx, x, length, kernel, recurrent_kernel, bias):
+        B, U, E = x.shape
+        R = recurrent_kernel.shape[0]
+        x2 = x.reshape(B * U, E).to(torch.bfloat16).contiguous()
+        pack = WeightPack(kernel)  # [E, 4R]
+        gx = kernels.gemm(x2, pack.wt, bias=bias.detach().float(), out_dtype=torch.float32).view(B, U, 4 * R)
+        whh = recurrent_kernel.detach().float().contiguous()
+        y, saved, _ = kernels.lstm_rec_fwd(gx, whh, length)
+        ctx.save_for_backward(x2, y, saved, whh, length)
+        ctx.misc = (kernel, recurrent_kernel, bias, pack, B, U, E, R, x.requires_grad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, y, saved, whh, length = ctx.saved_tensors
+        kernel, recurrent_kernel, bias, pack, B, U, E, R, need_dx = ctx.misc
+        dg = kernels.lstm_rec_bwd(dy.to(torch.bfloat16).contiguous(), saved, whh, length).view(B * U, 4 * R)
+        kernels.colsum(dg, _grad(bias).view(-1))
+        ks = _splits(B * U)
+        kernels.gemm(x2, dg, mn_major=True, out=_grad(kernel).view(E, 4 * R), accumulate=True, k_splits=ks)  # dW_ih += x^T dgates
+        # h_{t-1}: the outputs shifted by one label step (masked steps carry zero gate gradients, so their zeros are harmless)
+        hprev = torch.zeros_like(y)
+        hprev[:, 1:] = y[:, :-1]
+        kernels.gemm(hprev.view(B * U, R), dg, mn_major=True, out=_grad(recurrent_kernel).view(R, 4 * R), accumulate=True, k_splits=ks)
+        dx = kernels.gemm(dg, pack.w).view(B, U, E) if need_dx else None
+        return dx, None, None, None, None
+
+
+def lstm(x, length, kernel, recurrent_kernel, bias):
+    """x [B,U,E] -> y [B,U,R] bf16 (zeros at t >= length).  Training / full-sequence path (no carried state)."""
+    length = None if length is None else length.to(device=x.device, dtype=torch.int32)
+    return _LstmFn.apply(x, length, kernel, recurrent_kernel, bias)
+
+
 # ------------------------------------------------------------------------------------------------ joint + RNN-T loss head
 class _TransducerHeadFn(torch.autograd.Function):
     """Joint network + RNN-T loss for training on the hand-written kernels (base_transducer.py:199-207,280-293 + losses/impl/rnnt.py):

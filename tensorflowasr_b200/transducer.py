@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import torch
 
-from . import fused, ops, schemas
+from . import fused, kernels, ops, schemas
 from .base_model import BaseModel
 from .encoder import ConformerEncoder, _Params
 from .losses import RnntLoss
@@ -53,7 +53,11 @@ class TransducerPrediction(_Params):
         tokens, length = inputs
         y = ops.embedding(tokens, self["embedding.embeddings"])
         for i in range(self.num_rnns):
-            y, _ = ops.lstm(y, length, self[f"lstm_{i}.kernel"], self[f"lstm_{i}.recurrent_kernel"], self[f"lstm_{i}.bias"])
+            if ops.fused_active(y) and kernels.lstm_supported(self.rnn_units):
+                # input projection on the tcgen05 GEMM, time loop on the cluster kernel (csrc/lstm.cu)
+                y = fused.lstm(y, length, self[f"lstm_{i}.kernel"], self[f"lstm_{i}.recurrent_kernel"], self[f"lstm_{i}.bias"])
+            else:
+                y, _ = ops.lstm(y, length, self[f"lstm_{i}.kernel"], self[f"lstm_{i}.recurrent_kernel"], self[f"lstm_{i}.bias"])
             if self.use_ln:
                 y = ops.layer_norm(y, self[f"ln_{i}.gamma"], self[f"ln_{i}.beta"])
             if self.projection_units > 0:

@@ -371,3 +371,44 @@ def test_pack_plan_matches_eager_packs():
     plan.run()
     torch.cuda.synchronize()
     assert torch.equal(lazy["ff"].w, (p.detach()).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("cfg", [(32, 65, 320, 320), (5, 7, 64, 64), (33, 3, 48, 128)])
+def test_lstm_cluster_kernels_vs_torch(cfg):
+    """Cluster LSTM (csrc/lstm.cu) forward / backward vs torch's LSTM cell recurrence in fp32 (keras gate order i, f, c, o = torch's
+    i, f, g, o), masked outputs, all parameter gradients."""
+    from tensorflowasr_b200 import fused, kernels
+
+    B, U, E, R = cfg
+    assert kernels.lstm_supported(R)
+    torch.manual_seed(B * 1000 + U)
+    x = (torch.randn(B, U, E, device="cuda") * 0.5).to(torch.bfloat16)
+    kernel = torch.nn.Parameter(torch.randn(E, 4 * R, device="cuda") * (1.0 / E ** 0.5))
+    rk = torch.nn.Parameter(torch.randn(R, 4 * R, device="cuda") * (1.0 / R ** 0.5))
+    bias = torch.nn.Parameter(torch.randn(4 * R, device="cuda") * 0.1)
+    length = torch.randint(1, U + 1, (B,), device="cuda", dtype=torch.int32)
+    length[0] = U
+    xg = x.clone().requires_grad_(True)
+    y = fused.lstm(xg, length, kernel, rk, bias)
+    # fp32 reference on the same bf16 inputs
+    xr = x.float().requires_grad_(True)
+    kr, rr, br = kernel.detach().clone().requires_grad_(True), rk.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    h = torch.zeros(B, R, device="cuda")
+    c = torch.zeros(B, R, device="cuda")
+    outs = []
+    for t in range(U):
+        pre = xr[:, t] @ kr + h @ rr + br
+        i, f, g, o = pre.split(R, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h)
+    mask = (torch.arange(U, device="cuda")[None, :] < length[:, None]).float()[..., None]
+    ref = torch.stack(outs, dim=1) * mask
+    _close(y, ref, 3e-2)
+    dy = (torch.randn(B, U, R, device="cuda") * 0.5).to(torch.bfloat16)
+    y.backward(dy)
+    ref.backward(dy.float())
+    _close(xg.grad, xr.grad, 5e-2)
+    _close(kernel.grad, kr.grad, 5e-2)
+    _close(rk.grad, rr.grad, 5e-2)
+    _close(bias.grad, br.grad, 5e-2)
