@@ -131,11 +131,9 @@ class BaseModel(nn.Module):
             self.optimizer.attach_grads(self._reducer.flat, self._reducer.params)
             mask = torch.zeros(self._reducer.flat.numel(), dtype=torch.uint8, device=self._reducer.flat.device)
             by_id = {id(p): n for n, p in self.named_parameters()}
-            off = 0
-            for p in self._reducer.params:
+            for p, off in zip(self._reducer.params, self._reducer.offsets):
                 if _is_regularized(by_id[id(p)]):
                     mask[off:off + p.numel()] = 1
-                off += p.numel()
             self.optimizer.set_l2(mask, self.l2)
             self._flat_opt = True
         self._graph = None

@@ -375,25 +375,28 @@ __device__ __forceinline__ void att_stage_kvp(const AttParams& p, int b, int n, 
   const int T = p.T, H = p.H, NH = p.N * p.H, R = p.R;
   const int Tk = att_mma_tk(T), Tc = att_mma_tc(T), PR = att_mma_prow(T);
   const uint2 z = make_uint2(0u, 0u);
+  // valid elements travel as 8-byte cp.async copies (all in flight at once; the caller waits with att_stage_wait()), padding is zeroed
   for (int i = threadIdx.x; i < Tc * HP4; i += blockDim.x) {
     const int j = i / HP4, h4 = i % HP4;
-    uint2 kk = z, vv = z;
     if (j < T && 4 * h4 < H) {
       const __nv_bfloat16* g = p.qkv + ((size_t)b * T + j) * p.ld_qkv + (size_t)n * H + 4 * h4;
-      kk = ld8(g + NH);
-      if (want_v) vv = ld8(g + 2 * NH);
+      mma::cp_async8(sK + j * HS + 4 * h4, g + NH);
+      if (want_v) mma::cp_async8(sV + j * HS + 4 * h4, g + 2 * NH);
+    } else {
+      st8(sK + j * HS + 4 * h4, z);
+      if (want_v) st8(sV + j * HS + 4 * h4, z);
     }
-    st8(sK + j * HS + 4 * h4, kk);
-    if (want_v) st8(sV + j * HS + 4 * h4, vv);
   }
   for (int i = threadIdx.x; i < PR * HP4; i += blockDim.x) {
     const int rr = i / HP4, h4 = i % HP4;
     const int r = rr - (Tk - T);
-    uint2 v = z;
-    if (r >= 0 && r < R && 4 * h4 < H) v = ld8(p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 4 * h4);
-    st8(sP + rr * HS + 4 * h4, v);
+    if (r >= 0 && r < R && 4 * h4 < H) mma::cp_async8(sP + rr * HS + 4 * h4, p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 4 * h4);
+    else st8(sP + rr * HS + 4 * h4, z);
   }
+  mma::cp_async_commit();
 }
+
+__device__ __forceinline__ void att_stage_wait() { mma::cp_async_wait<0>(); }
 
 // (q + u) * scale and (q + v) * scale rows [Tk][HS], zero beyond T / H
 template <int KS>
@@ -499,6 +502,7 @@ __global__ void __launch_bounds__(512, 1) rel_attention_fwd_mma_kernel(const Att
   const int len = p.length ? p.length[b] : T;
   att_stage_kvp<KS>(p, b, n, sK, sV, sP, true);
   att_stage_q<KS>(p, b, n, sQu, sQv);
+  att_stage_wait();
   __syncthreads();
   const int tw = warp * 16;
   const bool active = tw < T;
@@ -647,12 +651,13 @@ __global__ void __launch_bounds__(512, 1) rel_attention_bwd_rows_mma_kernel(cons
     const uint2 z = make_uint2(0u, 0u);
     for (int i = threadIdx.x; i < Tk * HP4; i += 512) {
       const int t = i / HP4, h4 = i % HP4;
-      uint2 v = z;
-      if (t < T && 4 * h4 < H) v = ld8(dctx + ((size_t)b * T + t) * NH + (size_t)n * H + 4 * h4);
-      st8(sdO + t * HS + 4 * h4, v);
+      if (t < T && 4 * h4 < H) mma::cp_async8(sdO + t * HS + 4 * h4, dctx + ((size_t)b * T + t) * NH + (size_t)n * H + 4 * h4);
+      else st8(sdO + t * HS + 4 * h4, z);
     }
+    mma::cp_async_commit();
     if (threadIdx.x < 128) sAcc[threadIdx.x] = 0.f;
   }
+  att_stage_wait();
   __syncthreads();
   const int tw = warp * 16;
   const bool active = tw < T;
@@ -990,6 +995,162 @@ __global__ void __launch_bounds__(512) rel_attention_bwd_cols_mma_kernel(const A
   }
 }
 
+// Pipelined variant of the column kernel for even T (probability rows are 4-byte aligned): the P and dS blocks of the next two
+// 16-row steps are always in flight as cp.async copies (three SMEM stages), the skewed copy is built SMEM -> SMEM, and the (q+u), (q+v),
+// dO rows of the next step wait in registers - the global-load latency that dominated the first version (16 exposed round trips per
+// CTA) is off the critical path.
+template <int KS>
+static size_t att_mma_bwd_cols2_smem(int T) {
+  return (size_t)(3 * 2 * 16 * att_mma_ps(T) + 16 * att_cols_qs(T) + 2 * 3 * 16 * AttMma<KS>::HS) * 2;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(512) rel_attention_bwd_cols_mma2_kernel(const AttParams p, const __nv_bfloat16* __restrict__ probs,
+                                                                          const __nv_bfloat16* __restrict__ ds,
+                                                                          const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv,
+                                                                          __nv_bfloat16* __restrict__ dpos) {
+  constexpr int HS = AttMma<KS>::HS;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  const int T = p.T, H = p.H, NH = p.N * p.H, R = p.R;
+  const int b = blockIdx.y, n = blockIdx.x;
+  const int Tk = att_mma_tk(T), PS = att_mma_ps(T), QS = att_cols_qs(T);
+  const int T2 = T >> 1;
+  __nv_bfloat16* sRaw = reinterpret_cast<__nv_bfloat16*>(att_smem);  // [3 stages][P block | dS block][16][PS]
+  __nv_bfloat16* sSk = sRaw + (size_t)3 * 2 * 16 * PS;                // [16][QS]
+  __nv_bfloat16* sQ = sSk + (size_t)16 * QS;                          // [2][Qu | Qv | dO][16][HS]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int q0 = (T - 16) / 16, rem = (T - 16) % 16;  // T >= 16
+  const int nct = (rem + T + 15 + 15) / 16;
+  const int nblk = Tk / 16;
+  const __nv_bfloat16* pbase = probs + ((size_t)b * p.N + n) * T * T;
+  const __nv_bfloat16* dbase = ds + ((size_t)b * p.N + n) * T * T;
+  const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+  // zero everything once: padding columns / rows are never written by the async copies
+  for (int i = threadIdx.x; i < (3 * 2 * 16 * PS + 16 * QS + 2 * 3 * 16 * HS) / 2; i += 512) reinterpret_cast<__nv_bfloat162*>(att_smem)[i] = z2;
+  __syncthreads();
+
+  auto issue = [&](int blk) {  // P and dS rows of step blk -> stage blk % 3
+    __nv_bfloat16* dP = sRaw + (size_t)(blk % 3) * 2 * 16 * PS;
+    __nv_bfloat16* dD = dP + 16 * PS;
+    const int tb = blk * 16;
+    for (int i = threadIdx.x; i < 16 * T2; i += 512) {
+      const int r = i / T2, j2 = i % T2;
+      const int t = tb + r;
+      if (t < T) {
+        mma::cp_async4(dP + r * PS + 2 * j2, pbase + (size_t)t * T + 2 * j2);
+        mma::cp_async4(dD + r * PS + 2 * j2, dbase + (size_t)t * T + 2 * j2);
+      } else {  // rows beyond T (last step only): the stage may hold an earlier step's rows
+        *reinterpret_cast<__nv_bfloat162*>(dP + r * PS + 2 * j2) = z2;
+        *reinterpret_cast<__nv_bfloat162*>(dD + r * PS + 2 * j2) = z2;
+      }
+    }
+    mma::cp_async_commit();
+  };
+  // (q+u) s, (q+v) s, dO of one step: 16 rows x KS*8 column pairs <= 512 items: one per thread, prefetched into registers
+  constexpr int HP2 = KS * 8;
+  const bool qd_lane = threadIdx.x < 16 * HP2;
+  const int qr = threadIdx.x / HP2, qh2 = threadIdx.x % HP2;
+  __nv_bfloat162 pqu = z2, pqv = z2, pdo = z2;
+  auto fetch_q = [&](int blk) {
+    pqu = pqv = pdo = z2;
+    const int t = blk * 16 + qr;
+    if (qd_lane && blk < nblk && t < T && 2 * qh2 < H) {
+      const __nv_bfloat162 q = *reinterpret_cast<const __nv_bfloat162*>(p.qkv + ((size_t)b * T + t) * p.ld_qkv + (size_t)n * H + 2 * qh2);
+      const float qa = __low2float(q), qb = __high2float(q);
+      const float* ub = p.ubias + n * H + 2 * qh2;
+      const float* vb = p.vbias + n * H + 2 * qh2;
+      pqu = __floats2bfloat162_rn((qa + ub[0]) * p.scale, (qb + ub[1]) * p.scale);
+      pqv = __floats2bfloat162_rn((qa + vb[0]) * p.scale, (qb + vb[1]) * p.scale);
+      pdo = *reinterpret_cast<const __nv_bfloat162*>(dctx + ((size_t)b * T + t) * NH + (size_t)n * H + 2 * qh2);
+    }
+  };
+
+  float aV[KS * 2][4], aK[KS * 2][4], aP[2][KS * 2][4];
+#pragma unroll
+  for (int nh = 0; nh < KS * 2; ++nh)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) aV[nh][e] = aK[nh][e] = aP[0][nh][e] = aP[1][nh][e] = 0.f;
+
+  issue(0);
+  if (nblk > 1) issue(1);
+  fetch_q(0);
+  const int ak = (lane & 7) + (lane >> 4) * 8;  // ldmatrix.trans A: source row (k)
+  const int am = ((lane >> 3) & 1) * 8;         // and column offset (m)
+  for (int blk = 0; blk < nblk; ++blk) {
+    if (blk + 1 < nblk) mma::cp_async_wait<1>();
+    else mma::cp_async_wait<0>();
+    __nv_bfloat16* sQu = sQ + (size_t)(blk & 1) * 3 * 16 * HS;
+    __nv_bfloat16* sQv = sQu + 16 * HS;
+    __nv_bfloat16* sdO = sQv + 16 * HS;
+    if (qd_lane) {
+      *reinterpret_cast<__nv_bfloat162*>(sQu + qr * HS + 2 * qh2) = pqu;
+      *reinterpret_cast<__nv_bfloat162*>(sQv + qr * HS + 2 * qh2) = pqv;
+      *reinterpret_cast<__nv_bfloat162*>(sdO + qr * HS + 2 * qh2) = pdo;
+    }
+    __syncthreads();  // step blk's rows are visible; every warp is done with step blk - 1
+    if (blk + 2 < nblk) issue(blk + 2);
+    fetch_q(blk + 1);
+    const __nv_bfloat16* sPb = sRaw + (size_t)(blk % 3) * 2 * 16 * PS;
+    const __nv_bfloat16* sDb = sPb + 16 * PS;
+    // skewed copy: sSk[r][c'] = dS[t][c' - 15 + r - rem]
+    for (int i = threadIdx.x; i < 16 * QS; i += 512) {
+      const int r = i / QS, c = i % QS;
+      const int j = c - 15 + r - rem;
+      sSk[i] = (j >= 0 && j < T) ? sDb[r * PS + j] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    if (warp < nblk) {
+      uint32_t afp[4], afd[4];
+      mma::ldsm_x4_trans(afp, sPb + ak * PS + warp * 16 + am);
+      mma::ldsm_x4_trans(afd, sDb + ak * PS + warp * 16 + am);
+#pragma unroll
+      for (int nh = 0; nh < KS * 2; ++nh) {
+        uint32_t bo[2], bq[2];
+        mma::ldsm_x2_trans(bo, sdO + (lane & 15) * HS + nh * 8);
+        mma::ldsm_x2_trans(bq, sQu + (lane & 15) * HS + nh * 8);
+        mma::mma_16816(aV[nh], afp, bo);
+        mma::mma_16816(aK[nh], afd, bq);
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int ct = (2 * warp + mi) - q0 + blk;
+      if (ct >= 0 && ct < nct) {
+        uint32_t afs[4];
+        mma::ldsm_x4_trans(afs, sSk + ak * QS + ct * 16 + am);
+#pragma unroll
+        for (int nh = 0; nh < KS * 2; ++nh) {
+          uint32_t bq[2];
+          mma::ldsm_x2_trans(bq, sQv + (lane & 15) * HS + nh * 8);
+          mma::mma_16816(aP[mi][nh], afs, bq);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int nh = 0; nh < KS * 2; ++nh) {
+    const int h = nh * 8 + 2 * tq;
+    if (h >= H) continue;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j = warp * 16 + g + half * 8;
+      if (j < T) {
+        __nv_bfloat16* row = dqkv + ((size_t)b * T + j) * p.ld_qkv + (size_t)n * H + h;
+        *reinterpret_cast<__nv_bfloat162*>(row + NH) = __floats2bfloat162_rn(aK[nh][2 * half], aK[nh][2 * half + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(row + 2 * NH) = __floats2bfloat162_rn(aV[nh][2 * half], aV[nh][2 * half + 1]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int r = (2 * warp + mi) * 16 + g + half * 8;
+        if (r < R)
+          *reinterpret_cast<__nv_bfloat162*>(dpos + ((size_t)b * R + r) * NH + (size_t)n * H + h) =
+              __floats2bfloat162_rn(aP[mi][nh][2 * half], aP[mi][nh][2 * half + 1]);
+      }
+    }
+  }
+}
+
 template <int KS>
 static int launch_att_bwd_mma(const AttParams& p, const __nv_bfloat16* probs, const __nv_bfloat16* dctx, const __nv_bfloat16* octx,
                               __nv_bfloat16* ds_ws, __nv_bfloat16* dqkv, __nv_bfloat16* dpos, float* du, float* dvb, cudaStream_t stream) {
@@ -1001,7 +1162,14 @@ static int launch_att_bwd_mma(const AttParams& p, const __nv_bfloat16* probs, co
   dim3 grid(p.N, p.B);
   rel_attention_bwd_rows_mma_kernel<KS><<<grid, 512, smem1, stream>>>(p, probs, dctx, octx, ds_ws, dqkv, du, dvb);
   count_launch();
-  rel_attention_bwd_cols_mma_kernel<KS><<<grid, 512, smem2, stream>>>(p, probs, ds_ws, dctx, dqkv, dpos);
+  const size_t smem3 = att_mma_bwd_cols2_smem<KS>(p.T);
+  if ((p.T & 1) == 0 && smem3 <= 227 * 1024) {
+    if (cudaFuncSetAttribute(rel_attention_bwd_cols_mma2_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return TFASR_EXECUTION_FAILED;
+    rel_attention_bwd_cols_mma2_kernel<KS><<<grid, 512, smem3, stream>>>(p, probs, ds_ws, dctx, dqkv, dpos);
+  } else {
+    rel_attention_bwd_cols_mma_kernel<KS><<<grid, 512, smem2, stream>>>(p, probs, ds_ws, dctx, dqkv, dpos);
+  }
   count_launch();
   return check_launch();
 }

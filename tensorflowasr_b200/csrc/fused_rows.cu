@@ -124,6 +124,93 @@ __global__ void __launch_bounds__(kRowsWarps * 32) layernorm_bwd_kernel(const __
   }
 }
 
+// bf16 x, even D: column pairs per lane (4-byte loads, 128 B per warp instruction), the rows of a warp loaded up front (RPW x 2 x NP2
+// independent loads in flight per lane) - the scalar kernel above ran at 0.7 TB/s on [8000, 144].
+template <int NP2, int RPW>
+__global__ void __launch_bounds__(kRowsWarps * 32) layernorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                                            const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
+                                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                                            float* __restrict__ dbeta, int M, int D) {
+  extern __shared__ float s_acc[];  // [2][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D2 = D >> 1;
+  for (int j = threadIdx.x; j < 2 * D; j += blockDim.x) s_acc[j] = 0.f;
+  __syncthreads();
+  float2 ag[NP2], ab[NP2], gm[NP2];
+#pragma unroll
+  for (int i = 0; i < NP2; ++i) {
+    const int pi = lane + 32 * i;
+    ag[i] = ab[i] = make_float2(0.f, 0.f);
+    gm[i] = (pi < D2) ? make_float2(gamma[2 * pi], gamma[2 * pi + 1]) : make_float2(0.f, 0.f);  // parameters are only 4-byte aligned in general
+  }
+  const int row0 = (blockIdx.x * kRowsWarps + warp) * RPW;
+  __nv_bfloat162 dv[RPW][NP2], xv[RPW][NP2], rv[RPW][NP2];
+  float mu[RPW], rs[RPW];
+  const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+    const bool ok = row < M;
+    mu[r] = ok ? mean_in[row] : 0.f;
+    rs[r] = ok ? rstd_in[row] : 0.f;
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) {
+      const int pi = lane + 32 * i;
+      const bool in = ok && pi < D2;
+      dv[r][i] = in ? *reinterpret_cast<const __nv_bfloat162*>(dy + (size_t)row * D + 2 * pi) : z2;
+      xv[r][i] = in ? *reinterpret_cast<const __nv_bfloat162*>(x + (size_t)row * D + 2 * pi) : z2;
+      rv[r][i] = (in && dres) ? *reinterpret_cast<const __nv_bfloat162*>(dres + (size_t)row * D + 2 * pi) : z2;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+    if (row >= M) break;
+    float2 g[NP2], xh[NP2];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) {
+      const int pi = lane + 32 * i;
+      const float2 d = __bfloat1622float2(dv[r][i]), xx = __bfloat1622float2(xv[r][i]);
+      xh[i] = (pi < D2) ? make_float2((xx.x - mu[r]) * rs[r], (xx.y - mu[r]) * rs[r]) : make_float2(0.f, 0.f);
+      g[i] = make_float2(d.x * gm[i].x, d.y * gm[i].y);
+      sg += g[i].x + g[i].y;
+      sgx += g[i].x * xh[i].x + g[i].y * xh[i].y;
+      ag[i].x += d.x * xh[i].x;
+      ag[i].y += d.y * xh[i].y;
+      ab[i].x += d.x;
+      ab[i].y += d.y;
+    }
+    sg = warp_sum(sg) / (float)D;
+    sgx = warp_sum(sgx) / (float)D;
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) {
+      const int pi = lane + 32 * i;
+      if (pi < D2) {
+        const float2 rr = __bfloat1622float2(rv[r][i]);
+        const float o0 = rs[r] * (g[i].x - sg - xh[i].x * sgx) + rr.x, o1 = rs[r] * (g[i].y - sg - xh[i].y * sgx) + rr.y;
+        *reinterpret_cast<__nv_bfloat162*>(dx + (size_t)row * D + 2 * pi) = __floats2bfloat162_rn(o0, o1);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NP2; ++i) {
+    const int pi = lane + 32 * i;
+    if (pi < D2) {
+      atomicAdd(&s_acc[2 * pi], ag[i].x);
+      atomicAdd(&s_acc[2 * pi + 1], ag[i].y);
+      atomicAdd(&s_acc[D + 2 * pi], ab[i].x);
+      atomicAdd(&s_acc[D + 2 * pi + 1], ab[i].y);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + j, s_acc[j]);
+    if (dbeta) atomicAdd(dbeta + j, s_acc[D + j]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- elementwise helpers
 // out = scale * dropout_mask * in (bf16) [+ add], colsum += column sums of out.   [M, N] row-major, N even.
 __global__ void __launch_bounds__(256) scale_mask_colsum_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ add,
@@ -293,6 +380,16 @@ extern "C" int tfasr_layernorm_bwd(const void* dy, const void* x, int32_t x_is_f
   const unsigned grid = (unsigned)ceil_div(M, kRowsWarps * rows_per_warp);
   const size_t smem = sizeof(float) * 2 * D;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!x_is_f32 && (D & 1) == 0 && D <= 512) {
+#define LN_BWD_VEC(NP2)                                                                                                                 \
+  layernorm_bwd_vec_kernel<NP2, 4><<<grid, kRowsWarps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), \
+                                                                        mean, rstd, gamma, static_cast<const __nv_bfloat16*>(dres),       \
+                                                                        static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, M, D)
+    if (D <= 192) LN_BWD_VEC(3); else if (D <= 320) LN_BWD_VEC(5); else LN_BWD_VEC(8);
+#undef LN_BWD_VEC
+    count_launch();
+    return check_launch();
+  }
 #define LN_BWD(T, NPL)                                                                                                                  \
   layernorm_bwd_kernel<T, NPL><<<grid, kRowsWarps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const T*>(x), mean, rstd, gamma, \
                                                                      static_cast<const __nv_bfloat16*>(dres), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, M, D, rows_per_warp)

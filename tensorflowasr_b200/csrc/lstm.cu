@@ -42,8 +42,7 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
   const int WS = 4 * UPC + 8;                          // sW row stride (bf16): odd multiple of 16 B
   const int HS = R + 8;                                // sH row stride
   __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(lstm_smem);          // [R][WS]   W_hh[:, own gate columns]
-  __nv_bfloat16* sH = sW + (size_t)R * WS;                                   // [32][HS]  h_{t-1}, all units
-  __nv_bfloat16* sOwn = sH + (size_t)kLstmRows * HS;                         // [2][32][UPC] this CTA's slice of h_t
+  __nv_bfloat16* sH = sW + (size_t)R * WS;                                   // [2][32][HS]  h_{t-1} (read) / h_t (written by all 8 CTAs)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g8 = lane >> 2, tq = lane & 3;
   const int b0 = blockIdx.y * kLstmRows;
@@ -59,6 +58,9 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
     const int b = b0 + r;
     sH[(size_t)r * HS + k] = __float2bfloat16((h0 && b < p.B) ? h0[(size_t)b * R + k] : 0.f);
   }
+  __nv_bfloat16* peerH[kLstmCluster];  // the same buffer in every CTA of the cluster (DSMEM)
+#pragma unroll
+  for (int j = 0; j < kLstmCluster; ++j) peerH[j] = cluster.map_shared_rank(sH, j);
   const bool active = warp < n_items;
   const int mt = warp & 1, ut = warp >> 1;      // m-tile, unit-tile of this warp
   const int rowA = mt * 16 + g8, rowB = rowA + 8;  // rows inside the 32-row block
@@ -92,9 +94,11 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
       float acc[4][4];
 #pragma unroll
       for (int gate = 0; gate < 4; ++gate) acc[gate][0] = acc[gate][1] = acc[gate][2] = acc[gate][3] = 0.f;
+      const __nv_bfloat16* hcur = sH + (size_t)(t & 1) * kLstmRows * HS;
+#pragma unroll 4
       for (int ks = 0; ks < R / 16; ++ks) {
         uint32_t afr[4];
-        mma::ldsm_x4(afr, sH + (size_t)(mt * 16 + (lane & 15)) * HS + ks * 16 + (lane >> 4) * 8);
+        mma::ldsm_x4(afr, hcur + (size_t)(mt * 16 + (lane & 15)) * HS + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
         for (int gate = 0; gate < 4; ++gate) {
           uint32_t bfr[2];
@@ -122,9 +126,17 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
           sv[1][e][0] = i_; sv[1][e][1] = f_; sv[1][e][2] = g_; sv[1][e][3] = o_; sv[1][e][4] = cB[e];
         }
       }
-      __nv_bfloat16* own = sOwn + (size_t)(t & 1) * kLstmRows * UPC;
-      *reinterpret_cast<__nv_bfloat162*>(own + rowA * UPC + ul0) = __floats2bfloat162_rn(hA[0], hA[1]);
-      *reinterpret_cast<__nv_bfloat162*>(own + rowB * UPC + ul0) = __floats2bfloat162_rn(hB[0], hB[1]);
+      // publish h_t: straight into the next-step buffer of all 8 CTAs (fire-and-forget DSMEM stores, ordered by the cluster barrier)
+      {
+        const __nv_bfloat162 va = __floats2bfloat162_rn(hA[0], hA[1]), vb = __floats2bfloat162_rn(hB[0], hB[1]);
+        const size_t offA = (size_t)((t + 1) & 1) * kLstmRows * HS + (size_t)rowA * HS + ug0;
+        const size_t offB = (size_t)((t + 1) & 1) * kLstmRows * HS + (size_t)rowB * HS + ug0;
+#pragma unroll
+        for (int j = 0; j < kLstmCluster; ++j) {
+          *reinterpret_cast<__nv_bfloat162*>(peerH[j] + offA) = va;
+          *reinterpret_cast<__nv_bfloat162*>(peerH[j] + offB) = vb;
+        }
+      }
       if (bA < p.B) {
         const bool on = t < lenA;
         *reinterpret_cast<__nv_bfloat162*>(y + ((size_t)bA * U + t) * R + ug0) = __floats2bfloat162_rn(on ? hA[0] : 0.f, on ? hA[1] : 0.f);
@@ -140,19 +152,7 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
         for (int q = 0; q < 5; ++q) *reinterpret_cast<float2*>(s + (size_t)q * R) = make_float2(sv[1][0][q], sv[1][1][q]);
       }
     }
-    cluster.sync();  // slices of h_t are published
-    // pull the 8 slices into the full h_t tile (16-byte DSMEM reads)
-    {
-      const int vec_per_row = UPC / 8;  // uint4 per slice row
-      const int total = kLstmCluster * kLstmRows * vec_per_row;
-      for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int src = i / (kLstmRows * vec_per_row), rem = i % (kLstmRows * vec_per_row);
-        const int r = rem / vec_per_row, v = rem % vec_per_row;
-        const __nv_bfloat16* remote = cluster.map_shared_rank(sOwn + (size_t)(t & 1) * kLstmRows * UPC, src);
-        *reinterpret_cast<uint4*>(sH + (size_t)r * HS + src * UPC + v * 8) = *reinterpret_cast<const uint4*>(remote + r * UPC + v * 8);
-      }
-    }
-    __syncthreads();
+    cluster.sync();  // h_t is complete in every CTA; nobody reads h_{t-1} any more
   }
   if (active) {
     if (bA < p.B) {
@@ -170,6 +170,9 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
 // ---------------------------------------------------------------------------------------------- backward
 // dy [B, U, R] bf16 (gradient of the masked output), saved as written by the forward, c0 [B, R] or null, whh [R, 4R] f32
 // -> dgates [B, U, 4R] bf16 (gradient of the pre-activations: feeds dW_ih, dW_hh, dbias, dx as plain GEMMs), dh0 / dc0 [B, R] f32 or null
+// Per step: cell backward for the CTA's own units (registers) -> its [32 x 4 R/8] gate-gradient slice in local SMEM -> partial
+// dh_{t-1}[32 x R] = slice . W_hh[:, own gate columns]^T by mma.sync -> each 8-unit tile of the partial sums is pushed (DSMEM) to the CTA
+// that owns those units (reduce-scatter) -> cluster barrier -> the owner adds the 8 partials.  Exchange: 5 KB per CTA pair and step.
 __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
     lstm_rec_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ saved, const float* __restrict__ c0,
                         const float* __restrict__ whh, const int32_t* __restrict__ length, __nv_bfloat16* __restrict__ dgates,
@@ -178,18 +181,19 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int R = p.R, U = p.U, UPC = R / kLstmCluster;
-  const int G = 4 * R;
-  const int GS = G + 8;  // row stride of the gate-gradient tile and of the transposed weight slice
-  __nv_bfloat16* sWt = reinterpret_cast<__nv_bfloat16*>(lstm_smem);  // [UPC][GS]  W_hh[own units (as rows r'), all gate columns]
-  __nv_bfloat16* sDG = sWt + (size_t)UPC * GS;                        // [32][GS]   gate gradients of the step, all columns
-  __nv_bfloat16* sOwn = sDG + (size_t)kLstmRows * GS;                 // [2][32][4 * UPC] this CTA's slice (gate-major)
+  const int G = 4 * R, GL = 4 * UPC;  // all gate columns / this CTA's gate columns
+  const int WS = GL + 8;              // row stride of sW and sOwn (bf16)
+  __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(lstm_smem);  // [R][WS]   W_hh[r', own gate columns]  (B operand, k = gate column)
+  __nv_bfloat16* sOwn = sW + (size_t)R * WS;                         // [32][WS]  gate gradients of this CTA's units (A operand)
+  float* sSlot = reinterpret_cast<float*>(sOwn + (size_t)kLstmRows * WS);  // [2][8 sources][32][UPC] partial dh for this CTA's units
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g8 = lane >> 2, tq = lane & 3;
   const int b0 = blockIdx.y * kLstmRows;
   const int n_items = 2 * (UPC / 8);
-  for (int i = threadIdx.x; i < UPC * G; i += blockDim.x) {
-    const int rl = i / G, n = i % G;
-    sWt[(size_t)rl * GS + n] = __float2bfloat16(whh[(size_t)(rank * UPC + rl) * G + n]);
+  for (int i = threadIdx.x; i < R * GL; i += blockDim.x) {
+    const int k = i / GL, n = i % GL;
+    const int gate = n / UPC, ul = n % UPC;
+    sW[(size_t)k * WS + n] = __float2bfloat16(whh[(size_t)k * G + gate * R + rank * UPC + ul]);
   }
   const bool active = warp < n_items;
   const int mt = warp & 1, ut = warp >> 1;
@@ -198,7 +202,9 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
   const int ul0 = ut * 8 + 2 * tq, ug0 = rank * UPC + ul0;
   const int lenA = (length && bA < p.B) ? length[bA] : U, lenB = (length && bB < p.B) ? length[bB] : U;
   float dcA[2] = {0.f, 0.f}, dcB[2] = {0.f, 0.f};  // dL/dc flowing to the previous step
-  float dhr[4] = {0.f, 0.f, 0.f, 0.f};             // recurrent dL/dh (rows A: [0..1], rows B: [2..3]) from the MMA of the later step
+  float dhr[4] = {0.f, 0.f, 0.f, 0.f};             // recurrent dL/dh for this thread's (row, unit) pairs
+  // MMA work split: warp w < 2 * 5 takes m-tile (w & 1) and the 8 unit tiles {w >> 1, w >> 1 + 5, ...} of R / 8 = 40 (UPC / 8 per owner)
+  const int n_tiles_total = R / 8, n_warps_mma = n_items;  // same 10 warps
   __syncthreads();
   cluster.sync();
   for (int t = U - 1; t >= 0; --t) {
@@ -213,9 +219,9 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
         float2 sv[5] = {}, cp = make_float2(0.f, 0.f);
         float2 dyv = make_float2(0.f, 0.f);
         if (b < p.B) {
-          const float* s = saved + (((size_t)b * U + t) * 5) * R + ug0;
+          const float* sp = saved + (((size_t)b * U + t) * 5) * R + ug0;
 #pragma unroll
-          for (int q = 0; q < 5; ++q) sv[q] = *reinterpret_cast<const float2*>(s + (size_t)q * R);
+          for (int q = 0; q < 5; ++q) sv[q] = *reinterpret_cast<const float2*>(sp + (size_t)q * R);
           if (t > 0) cp = *reinterpret_cast<const float2*>(saved + (((size_t)b * U + t - 1) * 5 + 4) * R + ug0);
           else if (c0) cp = *reinterpret_cast<const float2*>(c0 + (size_t)b * R + ug0);
           if (t < len) dyv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + ((size_t)b * U + t) * R + ug0));
@@ -234,41 +240,48 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
           dc[e] = dct * f_;
         }
       }
-      __nv_bfloat16* own = sOwn + (size_t)(t & 1) * kLstmRows * 4 * UPC;
 #pragma unroll
       for (int gate = 0; gate < 4; ++gate) {
         const __nv_bfloat162 va = __floats2bfloat162_rn(dgA[0][gate], dgA[1][gate]), vb = __floats2bfloat162_rn(dgB[0][gate], dgB[1][gate]);
-        *reinterpret_cast<__nv_bfloat162*>(own + (size_t)rowA * 4 * UPC + gate * UPC + ul0) = va;
-        *reinterpret_cast<__nv_bfloat162*>(own + (size_t)rowB * 4 * UPC + gate * UPC + ul0) = vb;
+        *reinterpret_cast<__nv_bfloat162*>(sOwn + (size_t)rowA * WS + gate * UPC + ul0) = va;
+        *reinterpret_cast<__nv_bfloat162*>(sOwn + (size_t)rowB * WS + gate * UPC + ul0) = vb;
         if (bA < p.B) *reinterpret_cast<__nv_bfloat162*>(dgates + ((size_t)bA * U + t) * G + gate * R + ug0) = va;
         if (bB < p.B) *reinterpret_cast<__nv_bfloat162*>(dgates + ((size_t)bB * U + t) * G + gate * R + ug0) = vb;
       }
     }
-    cluster.sync();
-    {
-      const int vec_per_seg = UPC / 8;  // uint4 per (row, gate) segment
-      const int total = kLstmCluster * kLstmRows * 4 * vec_per_seg;
-      for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int src = i / (kLstmRows * 4 * vec_per_seg), rem = i % (kLstmRows * 4 * vec_per_seg);
-        const int r = rem / (4 * vec_per_seg), gv = rem % (4 * vec_per_seg);
-        const int gate = gv / vec_per_seg, v = gv % vec_per_seg;
-        const __nv_bfloat16* remote = cluster.map_shared_rank(sOwn + (size_t)(t & 1) * kLstmRows * 4 * UPC, src);
-        *reinterpret_cast<uint4*>(sDG + (size_t)r * GS + gate * R + src * UPC + v * 8) =
-            *reinterpret_cast<const uint4*>(remote + (size_t)r * 4 * UPC + gate * UPC + v * 8);
+    __syncthreads();  // the CTA's gate-gradient slice is complete
+    if (warp < n_warps_mma) {
+      // partial dh_{t-1}[row, r'] over this CTA's gate columns, for every unit r'
+      float* slot_base = nullptr;
+      for (int nt = ut; nt < n_tiles_total; nt += UPC / 8) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int ks = 0; ks < GL / 16; ++ks) {
+          uint32_t afr[4], bfr[2];
+          mma::ldsm_x4(afr, sOwn + (size_t)(mt * 16 + (lane & 15)) * WS + ks * 16 + (lane >> 4) * 8);
+          mma::ldsm_x2(bfr, sW + (size_t)(nt * 8 + (lane & 7)) * WS + ks * 16 + ((lane >> 3) & 1) * 8);
+          mma::mma_16816(acc, afr, bfr);
+        }
+        // unit tile nt belongs to CTA `owner`; this CTA's partial goes into slot [t & 1][rank] there
+        const int owner = (nt * 8) / UPC, ul = (nt * 8) % UPC + 2 * tq;
+        slot_base = cluster.map_shared_rank(sSlot, owner) + ((size_t)((t & 1) * kLstmCluster + rank) * kLstmRows) * UPC;
+        *reinterpret_cast<float2*>(slot_base + (size_t)rowA * UPC + ul) = make_float2(acc[0], acc[1]);
+        *reinterpret_cast<float2*>(slot_base + (size_t)rowB * UPC + ul) = make_float2(acc[2], acc[3]);
       }
     }
-    __syncthreads();
+    cluster.sync();  // all partial sums of this step have arrived; sOwn may be rewritten
     if (active) {
-      // dh_{t-1}[b, r'] = sum_n dgates_t[b, n] W_hh[r', n]   for this CTA's units r'
       dhr[0] = dhr[1] = dhr[2] = dhr[3] = 0.f;
-      for (int ks = 0; ks < G / 16; ++ks) {
-        uint32_t afr[4], bfr[2];
-        mma::ldsm_x4(afr, sDG + (size_t)(mt * 16 + (lane & 15)) * GS + ks * 16 + (lane >> 4) * 8);
-        mma::ldsm_x2(bfr, sWt + (size_t)(ut * 8 + (lane & 7)) * GS + ks * 16 + ((lane >> 3) & 1) * 8);
-        mma::mma_16816(dhr, afr, bfr);
+#pragma unroll
+      for (int src = 0; src < kLstmCluster; ++src) {
+        const float* sl = sSlot + ((size_t)((t & 1) * kLstmCluster + src) * kLstmRows) * UPC;
+        const float2 a = *reinterpret_cast<const float2*>(sl + (size_t)rowA * UPC + ul0), b = *reinterpret_cast<const float2*>(sl + (size_t)rowB * UPC + ul0);
+        dhr[0] += a.x;
+        dhr[1] += a.y;
+        dhr[2] += b.x;
+        dhr[3] += b.y;
       }
     }
-    __syncthreads();  // sDG is rewritten by the next step's pull only after every warp has read it
   }
   if (active) {
     if (bA < p.B) {
@@ -285,11 +298,11 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
 
 static size_t lstm_fwd_smem(int R) {
   const int UPC = R / kLstmCluster;
-  return ((size_t)R * (4 * UPC + 8) + (size_t)kLstmRows * (R + 8) + (size_t)2 * kLstmRows * UPC) * 2;
+  return ((size_t)R * (4 * UPC + 8) + (size_t)2 * kLstmRows * (R + 8)) * 2;
 }
 static size_t lstm_bwd_smem(int R) {
   const int UPC = R / kLstmCluster;
-  return ((size_t)UPC * (4 * R + 8) + (size_t)kLstmRows * (4 * R + 8) + (size_t)2 * kLstmRows * 4 * UPC) * 2;
+  return ((size_t)R * (4 * UPC + 8) + (size_t)kLstmRows * (4 * UPC + 8)) * 2 + (size_t)2 * kLstmCluster * kLstmRows * UPC * 4;
 }
 static bool lstm_supported(int R) { return R > 0 && R % 64 == 0 && 2 * (R / 64) <= 16 && lstm_fwd_smem(R) <= 227 * 1024 && lstm_bwd_smem(R) <= 227 * 1024; }
 

@@ -54,25 +54,36 @@ def shard_batch(n_global: int, rank_: int | None = None, world: int | None = Non
     return rank_ * per, (rank_ + 1) * per
 
 
+FLAT_ALIGN = 64  # elements: every parameter's slice of a flat buffer starts on a 256-byte boundary (TMA / float4 kernels address them)
+
+
+def flat_layout(params, align: int = FLAT_ALIGN):
+    """-> (offsets, total): element offsets of `params` in a flat buffer, each aligned to `align` elements; total padded likewise."""
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += (p.numel() + align - 1) // align * align
+    return offs, off
+
+
 class GradientReducer:
     def __init__(self, params, bucket_bytes: int = 25 * 1024 * 1024, overlap: bool = True):
         self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        self.offsets, total = flat_layout(self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros((total + 3) // 4 * 4, dtype=torch.float32, device=dev)  # padded: float4 kernels run over it
-        off = 0
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.buckets = []  # (start, end, [param indices])
         cur_start, cur_idx = 0, []
         for i, p in enumerate(self.params):
-            n = p.numel()
+            off, n = self.offsets[i], p.numel()
             p.grad = self.flat[off : off + n].view_as(p)
             cur_idx.append(i)
-            off += n
-            if (off - cur_start) * 4 >= bucket_bytes:
-                self.buckets.append((cur_start, off, cur_idx))
-                cur_start, cur_idx = off, []
+            end = self.offsets[i + 1] if i + 1 < len(self.params) else total
+            if (end - cur_start) * 4 >= bucket_bytes:
+                self.buckets.append((cur_start, end, cur_idx))
+                cur_start, cur_idx = end, []
         if cur_idx:
-            self.buckets.append((cur_start, off, cur_idx))
+            self.buckets.append((cur_start, total, cur_idx))
         self._bucket_of = {}
         for b, (_, _, idx) in enumerate(self.buckets):
             for i in idx:

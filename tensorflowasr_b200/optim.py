@@ -23,16 +23,16 @@ class FlatAdamW(torch.optim.Optimizer):
             lr = torch.tensor(float(lr), device=dev)
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._params = params
+        from .dist import flat_layout
+
+        self.offsets, padded = flat_layout(params)
         self.total = sum(p.numel() for p in params)
-        padded = (self.total + 3) // 4 * 4
         self.flat_p = torch.zeros(padded, dtype=torch.float32, device=dev)
-        off = 0
         with torch.no_grad():
-            for p in params:
+            for p, off in zip(params, self.offsets):
                 n = p.numel()
                 self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[off:off + n].view(p.shape)
-                off += n
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -45,8 +45,8 @@ class FlatAdamW(torch.optim.Optimizer):
         """`flat_g`: the GradientReducer's flat buffer, laid out over the same parameters in the same order."""
         if [id(p) for p in params] != [id(p) for p in self._params]:
             raise ValueError("FlatAdamW and the gradient buffer must be built over the same parameter list")
-        if flat_g.numel() < self.flat_p.numel() or flat_g.dtype != torch.float32:
-            raise ValueError("gradient buffer must be fp32 and padded to a multiple of 4 elements")
+        if flat_g.numel() != self.flat_p.numel() or flat_g.dtype != torch.float32:
+            raise ValueError("gradient buffer must be fp32 with the layout of dist.flat_layout")
         self.flat_g = flat_g
 
     def set_l2(self, mask: torch.Tensor, l2: float):
@@ -56,14 +56,11 @@ class FlatAdamW(torch.optim.Optimizer):
 
     def _own_grads(self):
         self.flat_g = torch.zeros_like(self.flat_p)
-        off = 0
-        for p in self._params:
-            n = p.numel()
-            view = self.flat_g[off:off + n].view(p.shape)
+        for p, off in zip(self._params, self.offsets):
+            view = self.flat_g[off:off + p.numel()].view(p.shape)
             if p.grad is not None:
                 view.copy_(p.grad)
             p.grad = view
-            off += n
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0, zero_grad: bool = False):

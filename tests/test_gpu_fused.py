@@ -318,7 +318,7 @@ def test_flat_adamw_matches_torch_adamw():
     opt = FlatAdamW(ps, lr=3e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-2)
     topt = torch.optim.AdamW(ref, lr=3e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-2)
     mask = torch.zeros(opt.flat_p.numel(), dtype=torch.uint8, device="cuda")
-    mask[: ps[0].numel()] = 1  # only the first tensor carries the regularizer
+    mask[: ps[0].numel()] = 1  # only the first tensor carries the regularizer (offset 0)
     opt.set_l2(mask, l2)
     for it in range(5):
         gs = [torch.randn_like(p) for p in ps]
@@ -335,7 +335,7 @@ def test_flat_adamw_matches_torch_adamw():
             assert torch.allclose(p.detach(), r.detach(), rtol=2e-5, atol=2e-6), (it, (p - r).abs().max())
             assert float(p.grad.abs().max()) == 0.0
     # parameters are views of one buffer
-    assert ps[1].data_ptr() == opt.flat_p.data_ptr() + 4 * ps[0].numel()
+    assert ps[1].data_ptr() == opt.flat_p.data_ptr() + 4 * opt.offsets[1] and opt.offsets[1] % 64 == 0
 
 
 def test_pack_plan_matches_eager_packs():
