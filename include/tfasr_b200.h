@@ -220,16 +220,16 @@ int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* scale, const 
  * loop of TF's cuDNN RNN as ONE persistent kernel per direction (an 8-CTA cluster per 32 utterances keeps W_hh in SMEM).
  *   fwd: gx [B, U, 4R] f32 = x . kernel + bias (a GEMM before this call), whh [R, 4R] f32 = recurrent_kernel, h0 / c0 [B, R] f32 or
  *        NULL (zeros), length [B] or NULL (outputs at t >= length are zeros, state keeps evolving: zero_output_for_mask)
- *        -> y [B, U, R] bf16, saved [B, U, 5, R] f32 (i, f, g, o, c), hT / cT [B, R] f32 or NULL
+ *        -> y [B, U, R] bf16, saved_g [B, U, 4R] bf16 (i, f, g, o interleaved per unit pair), saved_c [B, U, R] f32, hT / cT [B, R] f32 or NULL
  *   bwd: dy [B, U, R] bf16 -> dgates [B, U, 4R] bf16 (pre-activation gradients; dW_ih, dW_hh, dbias, dx follow as plain GEMMs /
  *        column sums), dh0 / dc0 [B, R] f32 or NULL
  * tfasr_lstm_supported(R): 1 when R % 64 == 0 and the weight slices fit in SMEM (R <= 384); else the calls return 1 (invalid value).
  * ---------------------------------------------------------------------------------------------- */
 int tfasr_lstm_supported(int32_t R);
-int tfasr_lstm_rec_fwd(const float* gx, const float* whh, const float* h0, const float* c0, const int32_t* length, void* y, float* saved,
-                       float* hT, float* cT, int32_t B, int32_t U, int32_t R, tfasr_stream_t stream);
-int tfasr_lstm_rec_bwd(const void* dy, const float* saved, const float* c0, const float* whh, const int32_t* length, void* dgates, float* dh0,
-                       float* dc0, int32_t B, int32_t U, int32_t R, tfasr_stream_t stream);
+int tfasr_lstm_rec_fwd(const float* gx, const float* whh, const float* h0, const float* c0, const int32_t* length, void* y, void* saved_g,
+                       float* saved_c, float* hT, float* cT, int32_t B, int32_t U, int32_t R, tfasr_stream_t stream);
+int tfasr_lstm_rec_bwd(const void* dy, const void* saved_g, const float* saved_c, const float* c0, const float* whh, const int32_t* length,
+                       void* dgates, float* dh0, float* dc0, int32_t B, int32_t U, int32_t R, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Parameter-side kernels: the whole optimizer update and all bf16 weight-operand copies are one launch each.

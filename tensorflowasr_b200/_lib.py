@@ -75,8 +75,8 @@ SIGNATURES = {
     "tfasr_rel_attention_bwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                           c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tfasr_lstm_supported": (c_int32, [c_int32]),
-    "tfasr_lstm_rec_fwd": (c_int32, [c_void_p] * 9 + [c_int32] * 3 + [c_void_p]),
-    "tfasr_lstm_rec_bwd": (c_int32, [c_void_p] * 8 + [c_int32] * 3 + [c_void_p]),
+    "tfasr_lstm_rec_fwd": (c_int32, [c_void_p] * 10 + [c_int32] * 3 + [c_void_p]),
+    "tfasr_lstm_rec_bwd": (c_int32, [c_void_p] * 9 + [c_int32] * 3 + [c_void_p]),
     "tfasr_adamw_flat_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_float, c_float,
                                        c_float, c_float, c_float, c_float, c_int32, c_void_p]),
     "tfasr_pack_weights": (c_int32, [c_void_p, c_int32, c_void_p]),

@@ -1030,19 +1030,21 @@ __global__ void __launch_bounds__(512) rel_attention_bwd_cols_mma2_kernel(const 
   for (int i = threadIdx.x; i < (3 * 2 * 16 * PS + 16 * QS + 2 * 3 * 16 * HS) / 2; i += 512) reinterpret_cast<__nv_bfloat162*>(att_smem)[i] = z2;
   __syncthreads();
 
-  auto issue = [&](int blk) {  // P and dS rows of step blk -> stage blk % 3
-    __nv_bfloat16* dP = sRaw + (size_t)(blk % 3) * 2 * 16 * PS;
+  auto issue = [&](int blk) {  // P and dS rows of step blk -> stage blk % 3; warp w copies row w (no index divisions in the loop)
+    __nv_bfloat16* dP = sRaw + (size_t)(blk % 3) * 2 * 16 * PS + warp * PS;
     __nv_bfloat16* dD = dP + 16 * PS;
-    const int tb = blk * 16;
-    for (int i = threadIdx.x; i < 16 * T2; i += 512) {
-      const int r = i / T2, j2 = i % T2;
-      const int t = tb + r;
-      if (t < T) {
-        mma::cp_async4(dP + r * PS + 2 * j2, pbase + (size_t)t * T + 2 * j2);
-        mma::cp_async4(dD + r * PS + 2 * j2, dbase + (size_t)t * T + 2 * j2);
-      } else {  // rows beyond T (last step only): the stage may hold an earlier step's rows
-        *reinterpret_cast<__nv_bfloat162*>(dP + r * PS + 2 * j2) = z2;
-        *reinterpret_cast<__nv_bfloat162*>(dD + r * PS + 2 * j2) = z2;
+    const int t = blk * 16 + warp;
+    if (t < T) {
+      const __nv_bfloat16* gp = pbase + (size_t)t * T;
+      const __nv_bfloat16* gd = dbase + (size_t)t * T;
+      for (int j2 = lane; j2 < T2; j2 += 32) {
+        mma::cp_async4(dP + 2 * j2, gp + 2 * j2);
+        mma::cp_async4(dD + 2 * j2, gd + 2 * j2);
+      }
+    } else {  // rows beyond T (last step only): the stage may hold an earlier step's rows
+      for (int j2 = lane; j2 < T2; j2 += 32) {
+        *reinterpret_cast<__nv_bfloat162*>(dP + 2 * j2) = z2;
+        *reinterpret_cast<__nv_bfloat162*>(dD + 2 * j2) = z2;
       }
     }
     mma::cp_async_commit();
@@ -1094,10 +1096,14 @@ __global__ void __launch_bounds__(512) rel_attention_bwd_cols_mma2_kernel(const 
     const __nv_bfloat16* sPb = sRaw + (size_t)(blk % 3) * 2 * 16 * PS;
     const __nv_bfloat16* sDb = sPb + 16 * PS;
     // skewed copy: sSk[r][c'] = dS[t][c' - 15 + r - rem]
-    for (int i = threadIdx.x; i < 16 * QS; i += 512) {
-      const int r = i / QS, c = i % QS;
-      const int j = c - 15 + r - rem;
-      sSk[i] = (j >= 0 && j < T) ? sDb[r * PS + j] : __float2bfloat16(0.f);
+    {  // warp w skews row w
+      const int shift = 15 - warp + rem;  // c' = j + shift
+      const __nv_bfloat16* src = sDb + warp * PS;
+      __nv_bfloat16* dst = sSk + warp * QS;
+      for (int c = lane; c < QS; c += 32) {
+        const int j = c - shift;
+        dst[c] = (j >= 0 && j < T) ? src[j] : __float2bfloat16(0.f);
+      }
     }
     __syncthreads();
     if (warp < nblk) {

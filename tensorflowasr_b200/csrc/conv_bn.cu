@@ -274,6 +274,148 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- vector variants (C % 8 == 0)
+// All four BatchNorm passes as one templated kernel: thread = (8-channel vector, row lane), 16-byte loads / stores, per-channel
+// parameters in registers, rows of a thread unrolled 4-fold (independent loads in flight), statistics reduced in SMEM then one
+// atomic per channel and CTA.  The scalar kernels above stay for odd channel counts.
+//   MODE 0 stats      sums[0] += x, sums[1] += x^2
+//   MODE 1 apply      y = act(x * scale + shift)
+//   MODE 2 bwd stats  d = dy * act'(x * scale + shift); sums[0] += d, sums[1] += d * xhat
+//   MODE 3 bwd apply  dx = scale * (d - sums[0] / count - xhat * sums[1] / count)
+struct BnVecArgs {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* dy;
+  __nv_bfloat16* out;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  const float* sums_in;
+  float* sums_out;
+  int64_t R;
+  int C, act, rows_per_block;
+  float inv_count;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint32_t pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+  }
+  return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_vec_kernel(const BnVecArgs a) {
+  extern __shared__ float s_acc[];  // [2][C] (stats modes)
+  const int C = a.C, cv = threadIdx.x, ty = threadIdx.y, RY = blockDim.y;
+  const int tid = ty * blockDim.x + cv, nth = blockDim.x * blockDim.y;
+  if (MODE == 0 || MODE == 2) {
+    for (int i = tid; i < 2 * C; i += nth) s_acc[i] = 0.f;
+    __syncthreads();
+  }
+  float sc[8], sh[8], mu[8], rs[8], k0[8], k1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    sc[j] = (MODE != 0) ? a.scale[c] : 0.f;
+    sh[j] = (MODE != 0) ? a.shift[c] : 0.f;
+    mu[j] = (MODE >= 2) ? a.mean[c] : 0.f;
+    rs[j] = (MODE >= 2) ? a.rstd[c] : 0.f;
+    k0[j] = (MODE == 3) ? a.sums_in[c] * a.inv_count : 0.f;
+    k1[j] = (MODE == 3) ? a.sums_in[C + c] * a.inv_count : 0.f;
+  }
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_block;
+  const int64_t r1 = r0 + a.rows_per_block < a.R ? r0 + a.rows_per_block : a.R;
+  for (int64_t rb = r0 + ty; rb < r1; rb += 4 * RY) {
+    uint4 xv[4], dv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t r = rb + (int64_t)k * RY;
+      if (r < r1) {
+        xv[k] = *reinterpret_cast<const uint4*>(a.x + (size_t)r * C + cv * 8);
+        if (MODE >= 2) dv[k] = *reinterpret_cast<const uint4*>(a.dy + (size_t)r * C + cv * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t r = rb + (int64_t)k * RY;
+      if (r >= r1) break;
+      float xf[8], df[8], o[8];
+      unpack8(xv[k], xf);
+      if (MODE >= 2) unpack8(dv[k], df);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (MODE == 0) {
+          s0[j] += xf[j];
+          s1[j] = fmaf(xf[j], xf[j], s1[j]);
+        } else if (MODE == 1) {
+          float z = fmaf(xf[j], sc[j], sh[j]);
+          if (a.act == 1) z *= sigmoid_f(z);
+          o[j] = z;
+        } else {
+          float d = df[j];
+          if (a.act == 1) {
+            const float z = fmaf(xf[j], sc[j], sh[j]);
+            const float g = sigmoid_f(z);
+            d *= g * (1.0f + z * (1.0f - g));
+          }
+          const float xh = (xf[j] - mu[j]) * rs[j];
+          if (MODE == 2) {
+            s0[j] += d;
+            s1[j] = fmaf(d, xh, s1[j]);
+          } else {
+            o[j] = sc[j] * (d - k0[j] - xh * k1[j]);
+          }
+        }
+      }
+      if (MODE == 1 || MODE == 3) *reinterpret_cast<uint4*>(a.out + (size_t)r * C + cv * 8) = pack8(o);
+    }
+  }
+  if (MODE == 0 || MODE == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_acc[cv * 8 + j], s0[j]);
+      atomicAdd(&s_acc[C + cv * 8 + j], s1[j]);
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * C; i += nth) atomicAdd(a.sums_out + i, s_acc[i]);
+  }
+}
+
+// -> true when the vector kernel ran
+template <int MODE>
+static bool launch_bn_vec(BnVecArgs a, cudaStream_t stream, int* status) {
+  const int C = a.C;
+  if ((C & 7) || C / 8 > 256) return false;
+  if ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.dy) | reinterpret_cast<uintptr_t>(a.out)) & 15) return false;
+  const int cvn = C / 8;
+  int ry = 256 / cvn;
+  if (ry > 16) ry = 16;
+  // ~2 CTAs per SM, at least 4 rows per thread
+  int64_t rpb = ceil_div(a.R, (int64_t)2 * kNumSMs);
+  if (rpb < 4 * ry) rpb = 4 * ry;
+  a.rows_per_block = (int)rpb;
+  const unsigned grid = (unsigned)ceil_div(a.R, rpb);
+  bn_vec_kernel<MODE><<<grid, dim3(cvn, ry), (MODE == 0 || MODE == 2) ? sizeof(float) * 2 * C : 0, stream>>>(a);
+  count_launch();
+  *status = check_launch();
+  return true;
+}
+
 static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 static int rows_block_cfg(int C, dim3& block, int& rows_per_block, int64_t R, unsigned& grid) {
@@ -351,6 +493,15 @@ extern "C" int tfasr_col2im_3x3s2(const void* dcol, void* da, int32_t B, int32_t
 extern "C" int tfasr_bn_stats(const void* x, float* sums, int64_t R, int32_t C, tfasr_stream_t stream) {
   if (!x || !sums || R < 0) return TFASR_INVALID_VALUE;
   if (R == 0) return TFASR_OK;
+  {
+    BnVecArgs a{};
+    a.x = static_cast<const __nv_bfloat16*>(x);
+    a.sums_out = sums;
+    a.R = R;
+    a.C = C;
+    int vst = 0;
+    if (launch_bn_vec<0>(a, static_cast<cudaStream_t>(stream), &vst)) return vst;
+  }
   dim3 block;
   int rpb;
   unsigned grid;
@@ -365,6 +516,18 @@ extern "C" int tfasr_bn_apply(const void* x, const float* scale, const float* sh
                               tfasr_stream_t stream) {
   if (!x || !scale || !shift || !y || R < 0 || C < 2 || (C & 1)) return TFASR_INVALID_VALUE;
   if (R == 0) return TFASR_OK;
+  {
+    BnVecArgs a{};
+    a.x = static_cast<const __nv_bfloat16*>(x);
+    a.out = static_cast<__nv_bfloat16*>(y);
+    a.scale = scale;
+    a.shift = shift;
+    a.R = R;
+    a.C = C;
+    a.act = act;
+    int vst = 0;
+    if (launch_bn_vec<1>(a, static_cast<cudaStream_t>(stream), &vst)) return vst;
+  }
   const int64_t total = R * (C >> 1);
   unsigned grid = (unsigned)min64(ceil_div(total, 256), kNumSMs * 32);
   bn_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), scale, shift, static_cast<__nv_bfloat16*>(y), R,
@@ -377,6 +540,21 @@ extern "C" int tfasr_bn_bwd_stats(const void* dy, const void* x, const float* sc
                                   float* sums, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream) {
   if (!dy || !x || !scale || !shift || !mean || !rstd || !sums || R < 0) return TFASR_INVALID_VALUE;
   if (R == 0) return TFASR_OK;
+  {
+    BnVecArgs a{};
+    a.x = static_cast<const __nv_bfloat16*>(x);
+    a.dy = static_cast<const __nv_bfloat16*>(dy);
+    a.scale = scale;
+    a.shift = shift;
+    a.mean = mean;
+    a.rstd = rstd;
+    a.sums_out = sums;
+    a.R = R;
+    a.C = C;
+    a.act = act;
+    int vst = 0;
+    if (launch_bn_vec<2>(a, static_cast<cudaStream_t>(stream), &vst)) return vst;
+  }
   dim3 block;
   int rpb;
   unsigned grid;
@@ -392,6 +570,23 @@ extern "C" int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* sc
                                   const float* sums, float count, void* dx, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream) {
   if (!dy || !x || !scale || !shift || !mean || !rstd || !sums || !dx || R < 0 || C < 2 || (C & 1)) return TFASR_INVALID_VALUE;
   if (R == 0) return TFASR_OK;
+  {
+    BnVecArgs a{};
+    a.x = static_cast<const __nv_bfloat16*>(x);
+    a.dy = static_cast<const __nv_bfloat16*>(dy);
+    a.out = static_cast<__nv_bfloat16*>(dx);
+    a.scale = scale;
+    a.shift = shift;
+    a.mean = mean;
+    a.rstd = rstd;
+    a.sums_in = sums;
+    a.inv_count = count > 0.f ? 1.0f / count : 0.f;
+    a.R = R;
+    a.C = C;
+    a.act = act;
+    int vst = 0;
+    if (launch_bn_vec<3>(a, static_cast<cudaStream_t>(stream), &vst)) return vst;
+  }
   const int64_t total = R * (C >> 1);
   unsigned grid = (unsigned)min64(ceil_div(total, 256), kNumSMs * 32);
   bn_bwd_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), scale,

@@ -124,6 +124,69 @@ __global__ void __launch_bounds__(1024) dwconv_bwd_weight_kernel(const __nv_bflo
     for (int i = tid; i < C; i += nth) atomicAdd(dbias + i, sacc[K * C + i]);
 }
 
+// ---------------------------------------------------------------------------------------------- register-blocked forward / data gradient
+// One thread = one channel pair x 8 consecutive frames: the K + 7 inputs slide through registers (each SMEM value is read once and
+// used by up to 8 outputs) and the tap weights are fetched once per thread.  3x fewer instructions per output than the per-frame
+// kernels above, which stay as the generic fallback.
+//   REVERSE = false: y[t]  = bias + sum_k w[k] x[t - (K-1) + k]      (window starts K-1 frames before the tile)
+//   REVERSE = true : dx[t] =        sum_k w[K-1-k] dy[t + k]         (window starts at the tile; frames >= T are zero)
+template <int K, bool REVERSE>
+__global__ void __launch_bounds__(640) dwconv_sliding_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int T, int C) {
+  constexpr int TPT = 8;  // frames per thread; kDwTT / TPT row groups per CTA
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  __nv_bfloat162* sx = reinterpret_cast<__nv_bfloat162*>(dw_smem);  // [(TT + K - 1)][C/2]
+  const int C2 = C >> 1;
+  const int b = blockIdx.y, t0 = blockIdx.x * kDwTT;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nth = blockDim.x * blockDim.y;
+  const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(in + (size_t)b * T * C);
+  const int tstart = REVERSE ? t0 : t0 - (K - 1);
+  for (int r = threadIdx.y; r < kDwTT + K - 1; r += blockDim.y) {
+    const int t = tstart + r;
+    sx[(size_t)r * C2 + threadIdx.x] = (t >= 0 && t < T) ? xb[(size_t)t * C2 + threadIdx.x] : __floats2bfloat162_rn(0.f, 0.f);
+  }
+  (void)tid;
+  (void)nth;
+  const int c2 = threadIdx.x;
+  float w0[K], w1[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int kk = REVERSE ? (K - 1 - k) : k;
+    w0[k] = w[kk * C + 2 * c2];
+    w1[k] = w[kk * C + 2 * c2 + 1];
+  }
+  const float b0 = (!REVERSE && bias) ? bias[2 * c2] : 0.f, b1 = (!REVERSE && bias) ? bias[2 * c2 + 1] : 0.f;
+  __syncthreads();
+  for (int grp = threadIdx.y; grp < kDwTT / TPT; grp += blockDim.y) {
+    const int tt0 = grp * TPT;
+    if (t0 + tt0 >= T) break;
+    float a0[TPT], a1[TPT];
+#pragma unroll
+    for (int o = 0; o < TPT; ++o) {
+      a0[o] = b0;
+      a1[o] = b1;
+    }
+    // out[tt0 + o] = sum_k w[k] * win[tt0 + o + k]: walk the window once, each value feeds the (o, k) pairs with o + k = i
+#pragma unroll
+    for (int i = 0; i < TPT + K - 1; ++i) {
+      const float2 v = __bfloat1622float2(sx[(size_t)(tt0 + i) * C2 + c2]);
+#pragma unroll
+      for (int o = 0; o < TPT; ++o) {
+        const int k = i - o;
+        if (k >= 0 && k < K) {
+          a0[o] = fmaf(v.x, w0[k], a0[o]);
+          a1[o] = fmaf(v.y, w1[k], a1[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < TPT; ++o) {
+      const int t = t0 + tt0 + o;
+      if (t < T) reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * T + t) * C)[c2] = __floats2bfloat162_rn(a0[o], a1[o]);
+    }
+  }
+}
+
 static int dw_cfg(int C, int K, dim3& block, size_t& smem_fwd, size_t& smem_w) {
   if (C < 2 || (C & 1) || C / 2 > 512 || K < 1 || K > 128) return TFASR_INVALID_VALUE;
   int ty = 1024 / (C / 2);
@@ -147,6 +210,15 @@ extern "C" int tfasr_dwconv_causal_fwd(const void* x, const float* w, const floa
   int st = dw_cfg(C, K, block, sf, sw);
   if (st) return st;
   if (B == 0) return TFASR_OK;
+  if (K == 31 && block.x * block.y <= 640) {  // the Conformer kernel size: register-blocked variant (62 tap weights in registers)
+    const size_t smem = (size_t)(kDwTT + K - 1) * C * 2;
+    if (cudaFuncSetAttribute(dwconv_sliding_kernel<31, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return TFASR_EXECUTION_FAILED;
+    dwconv_sliding_kernel<31, false><<<dim3((unsigned)ceil_div(T, kDwTT), B), block, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), w, bias, static_cast<__nv_bfloat16*>(y), T, C);
+    count_launch();
+    return check_launch();
+  }
   if (cudaFuncSetAttribute(dwconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return TFASR_EXECUTION_FAILED;
   dwconv_fwd_kernel<<<dim3((unsigned)ceil_div(T, kDwTT), B), block, sf, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), w, bias, static_cast<__nv_bfloat16*>(y), T, C, K);
@@ -166,7 +238,14 @@ extern "C" int tfasr_dwconv_causal_bwd(const void* dy, const void* x, const floa
   if (cudaFuncSetAttribute(dwconv_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return TFASR_EXECUTION_FAILED;
   if (cudaFuncSetAttribute(dwconv_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return TFASR_EXECUTION_FAILED;
   dim3 grid((unsigned)ceil_div(T, kDwTT), B);
-  dwconv_bwd_data_kernel<<<grid, block, sf, stream>>>(static_cast<const __nv_bfloat16*>(dy), w, static_cast<__nv_bfloat16*>(dx), T, C, K);
+  if (K == 31 && block.x * block.y <= 640) {
+    const size_t smem = (size_t)(kDwTT + K - 1) * C * 2;
+    if (cudaFuncSetAttribute(dwconv_sliding_kernel<31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return TFASR_EXECUTION_FAILED;
+    dwconv_sliding_kernel<31, true><<<grid, block, smem, stream>>>(static_cast<const __nv_bfloat16*>(dy), w, nullptr, static_cast<__nv_bfloat16*>(dx), T, C);
+  } else {
+    dwconv_bwd_data_kernel<<<grid, block, sf, stream>>>(static_cast<const __nv_bfloat16*>(dy), w, static_cast<__nv_bfloat16*>(dx), T, C, K);
+  }
   count_launch();
   dwconv_bwd_weight_kernel<<<grid, block, sw, stream>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), dw, dbias, T, C, K);
   count_launch();

@@ -21,7 +21,17 @@ namespace tfasr {
 constexpr int kLstmCluster = 8;
 constexpr int kLstmRows = 32;  // utterances per cluster (two 16-row MMA tiles)
 
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// one MUFU op per activation (tanh.approx.f32, relative error ~2^-11): h is rounded to bf16 (2^-9) right after
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
 
 struct LstmParams {
   int B, U, R;
@@ -30,10 +40,12 @@ struct LstmParams {
 // ---------------------------------------------------------------------------------------------- forward
 // gx [B, U, 4R] f32 (input projection + bias), whh [R, 4R] f32 (keras recurrent_kernel), h0 / c0 [B, R] f32 or null,
 // length [B] or null (outputs at t >= length are written as zeros; the state keeps evolving, as with zero_output_for_mask)
-// -> y [B, U, R] bf16, saved [B, U, 5, R] f32 (i, f, g, o, c after the step), hT / cT [B, R] f32 (state after the last step)
+// -> y [B, U, R] bf16, saved_g [B, U, R/2] x 16 B (i, f, g, o of a unit pair as bf16), saved_c [B, U, R] f32 (cell state after the step),
+//    hT / cT [B, R] f32 (state after the last step)
 __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
     lstm_rec_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ whh, const float* __restrict__ h0, const float* __restrict__ c0,
-                        const int32_t* __restrict__ length, __nv_bfloat16* __restrict__ y, float* __restrict__ saved, float* __restrict__ hT,
+                        const int32_t* __restrict__ length, __nv_bfloat16* __restrict__ y, uint4* __restrict__ saved_g, float* __restrict__ saved_c,
+                        float* __restrict__ hT,
                         float* __restrict__ cT, const LstmParams p) {
   extern __shared__ __align__(16) uint8_t lstm_smem[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -95,8 +107,12 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
 #pragma unroll
       for (int gate = 0; gate < 4; ++gate) acc[gate][0] = acc[gate][1] = acc[gate][2] = acc[gate][3] = 0.f;
       const __nv_bfloat16* hcur = sH + (size_t)(t & 1) * kLstmRows * HS;
+#ifdef LSTM_PROBE_NO_MMA
+      for (int ks = 0; ks < 0; ++ks) {
+#else
 #pragma unroll 4
       for (int ks = 0; ks < R / 16; ++ks) {
+#endif
         uint32_t afr[4];
         mma::ldsm_x4(afr, hcur + (size_t)(mt * 16 + (lane & 15)) * HS + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
@@ -113,16 +129,16 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
       for (int e = 0; e < 2; ++e) {
         {
           const float i_ = sigmoid_acc(acc[0][e] + (e ? ga[0].y : ga[0].x)), f_ = sigmoid_acc(acc[1][e] + (e ? ga[1].y : ga[1].x));
-          const float g_ = tanhf(acc[2][e] + (e ? ga[2].y : ga[2].x)), o_ = sigmoid_acc(acc[3][e] + (e ? ga[3].y : ga[3].x));
+          const float g_ = tanh_fast(acc[2][e] + (e ? ga[2].y : ga[2].x)), o_ = sigmoid_acc(acc[3][e] + (e ? ga[3].y : ga[3].x));
           cA[e] = f_ * cA[e] + i_ * g_;
-          hA[e] = o_ * tanhf(cA[e]);
+          hA[e] = o_ * tanh_fast(cA[e]);
           sv[0][e][0] = i_; sv[0][e][1] = f_; sv[0][e][2] = g_; sv[0][e][3] = o_; sv[0][e][4] = cA[e];
         }
         {
           const float i_ = sigmoid_acc(acc[0][2 + e] + (e ? gb[0].y : gb[0].x)), f_ = sigmoid_acc(acc[1][2 + e] + (e ? gb[1].y : gb[1].x));
-          const float g_ = tanhf(acc[2][2 + e] + (e ? gb[2].y : gb[2].x)), o_ = sigmoid_acc(acc[3][2 + e] + (e ? gb[3].y : gb[3].x));
+          const float g_ = tanh_fast(acc[2][2 + e] + (e ? gb[2].y : gb[2].x)), o_ = sigmoid_acc(acc[3][2 + e] + (e ? gb[3].y : gb[3].x));
           cB[e] = f_ * cB[e] + i_ * g_;
-          hB[e] = o_ * tanhf(cB[e]);
+          hB[e] = o_ * tanh_fast(cB[e]);
           sv[1][e][0] = i_; sv[1][e][1] = f_; sv[1][e][2] = g_; sv[1][e][3] = o_; sv[1][e][4] = cB[e];
         }
       }
@@ -132,7 +148,11 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
         const size_t offA = (size_t)((t + 1) & 1) * kLstmRows * HS + (size_t)rowA * HS + ug0;
         const size_t offB = (size_t)((t + 1) & 1) * kLstmRows * HS + (size_t)rowB * HS + ug0;
 #pragma unroll
+#ifdef LSTM_PROBE_NO_PUSH
+        for (int j = rank; j <= rank; ++j) {
+#else
         for (int j = 0; j < kLstmCluster; ++j) {
+#endif
           *reinterpret_cast<__nv_bfloat162*>(peerH[j] + offA) = va;
           *reinterpret_cast<__nv_bfloat162*>(peerH[j] + offB) = vb;
         }
@@ -140,19 +160,23 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
       if (bA < p.B) {
         const bool on = t < lenA;
         *reinterpret_cast<__nv_bfloat162*>(y + ((size_t)bA * U + t) * R + ug0) = __floats2bfloat162_rn(on ? hA[0] : 0.f, on ? hA[1] : 0.f);
-        float* s = saved + (((size_t)bA * U + t) * 5) * R + ug0;
-#pragma unroll
-        for (int q = 0; q < 5; ++q) *reinterpret_cast<float2*>(s + (size_t)q * R) = make_float2(sv[0][0][q], sv[0][1][q]);
+        saved_g[((size_t)bA * U + t) * (R / 2) + (ug0 >> 1)] =
+            make_uint4(pack_bf2(sv[0][0][0], sv[0][1][0]), pack_bf2(sv[0][0][1], sv[0][1][1]), pack_bf2(sv[0][0][2], sv[0][1][2]), pack_bf2(sv[0][0][3], sv[0][1][3]));
+        *reinterpret_cast<float2*>(saved_c + ((size_t)bA * U + t) * R + ug0) = make_float2(sv[0][0][4], sv[0][1][4]);
       }
       if (bB < p.B) {
         const bool on = t < lenB;
         *reinterpret_cast<__nv_bfloat162*>(y + ((size_t)bB * U + t) * R + ug0) = __floats2bfloat162_rn(on ? hB[0] : 0.f, on ? hB[1] : 0.f);
-        float* s = saved + (((size_t)bB * U + t) * 5) * R + ug0;
-#pragma unroll
-        for (int q = 0; q < 5; ++q) *reinterpret_cast<float2*>(s + (size_t)q * R) = make_float2(sv[1][0][q], sv[1][1][q]);
+        saved_g[((size_t)bB * U + t) * (R / 2) + (ug0 >> 1)] =
+            make_uint4(pack_bf2(sv[1][0][0], sv[1][1][0]), pack_bf2(sv[1][0][1], sv[1][1][1]), pack_bf2(sv[1][0][2], sv[1][1][2]), pack_bf2(sv[1][0][3], sv[1][1][3]));
+        *reinterpret_cast<float2*>(saved_c + ((size_t)bB * U + t) * R + ug0) = make_float2(sv[1][0][4], sv[1][1][4]);
       }
     }
+#ifdef LSTM_PROBE_NO_SYNC
+    __syncthreads();
+#else
     cluster.sync();  // h_t is complete in every CTA; nobody reads h_{t-1} any more
+#endif
   }
   if (active) {
     if (bA < p.B) {
@@ -174,7 +198,8 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
 // dh_{t-1}[32 x R] = slice . W_hh[:, own gate columns]^T by mma.sync -> each 8-unit tile of the partial sums is pushed (DSMEM) to the CTA
 // that owns those units (reduce-scatter) -> cluster barrier -> the owner adds the 8 partials.  Exchange: 5 KB per CTA pair and step.
 __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
-    lstm_rec_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ saved, const float* __restrict__ c0,
+    lstm_rec_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint4* __restrict__ saved_g, const float* __restrict__ saved_c,
+                        const float* __restrict__ c0,
                         const float* __restrict__ whh, const int32_t* __restrict__ length, __nv_bfloat16* __restrict__ dgates,
                         float* __restrict__ dh0, float* __restrict__ dc0, const LstmParams p) {
   extern __shared__ __align__(16) uint8_t lstm_smem[];
@@ -219,10 +244,13 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
         float2 sv[5] = {}, cp = make_float2(0.f, 0.f);
         float2 dyv = make_float2(0.f, 0.f);
         if (b < p.B) {
-          const float* sp = saved + (((size_t)b * U + t) * 5) * R + ug0;
-#pragma unroll
-          for (int q = 0; q < 5; ++q) sv[q] = *reinterpret_cast<const float2*>(sp + (size_t)q * R);
-          if (t > 0) cp = *reinterpret_cast<const float2*>(saved + (((size_t)b * U + t - 1) * 5 + 4) * R + ug0);
+          const uint4 gq = saved_g[((size_t)b * U + t) * (R / 2) + (ug0 >> 1)];
+          sv[0] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq.x));
+          sv[1] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq.y));
+          sv[2] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq.z));
+          sv[3] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq.w));
+          sv[4] = *reinterpret_cast<const float2*>(saved_c + ((size_t)b * U + t) * R + ug0);
+          if (t > 0) cp = *reinterpret_cast<const float2*>(saved_c + ((size_t)b * U + t - 1) * R + ug0);
           else if (c0) cp = *reinterpret_cast<const float2*>(c0 + (size_t)b * R + ug0);
           if (t < len) dyv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + ((size_t)b * U + t) * R + ug0));
         }
@@ -231,7 +259,7 @@ __global__ void __cluster_dims__(kLstmCluster, 1, 1) __launch_bounds__(512, 1)
           const float i_ = e ? sv[0].y : sv[0].x, f_ = e ? sv[1].y : sv[1].x, g_ = e ? sv[2].y : sv[2].x, o_ = e ? sv[3].y : sv[3].x;
           const float c_ = e ? sv[4].y : sv[4].x, cprev = e ? cp.y : cp.x;
           const float dh = (e ? dyv.y : dyv.x) + dhr[2 * half + e];
-          const float tc = tanhf(c_);
+          const float tc = tanh_fast(c_);
           const float dct = dh * o_ * (1.0f - tc * tc) + dc[e];
           dg[e][0] = dct * g_ * i_ * (1.0f - i_);
           dg[e][1] = dct * cprev * f_ * (1.0f - f_);
@@ -312,28 +340,30 @@ using namespace tfasr;
 
 extern "C" int tfasr_lstm_supported(int32_t R) { return lstm_supported(R) ? 1 : 0; }
 
-extern "C" int tfasr_lstm_rec_fwd(const float* gx, const float* whh, const float* h0, const float* c0, const int32_t* length, void* y, float* saved,
-                                  float* hT, float* cT, int32_t B, int32_t U, int32_t R, tfasr_stream_t stream) {
-  if (!gx || !whh || !y || !saved || B < 0 || U < 1 || !lstm_supported(R)) return TFASR_INVALID_VALUE;
+extern "C" int tfasr_lstm_rec_fwd(const float* gx, const float* whh, const float* h0, const float* c0, const int32_t* length, void* y, void* saved_g,
+                                  float* saved_c, float* hT, float* cT, int32_t B, int32_t U, int32_t R, tfasr_stream_t stream) {
+  if (!gx || !whh || !y || !saved_g || !saved_c || B < 0 || U < 1 || !lstm_supported(R)) return TFASR_INVALID_VALUE;
   if (B == 0) return TFASR_OK;
   const size_t smem = lstm_fwd_smem(R);
   if (cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TFASR_EXECUTION_FAILED;
   LstmParams p{B, U, R};
   dim3 grid(kLstmCluster, (unsigned)ceil_div(B, kLstmRows));
-  lstm_rec_fwd_kernel<<<grid, 512, smem, static_cast<cudaStream_t>(stream)>>>(gx, whh, h0, c0, length, static_cast<__nv_bfloat16*>(y), saved, hT, cT, p);
+  lstm_rec_fwd_kernel<<<grid, 512, smem, static_cast<cudaStream_t>(stream)>>>(gx, whh, h0, c0, length, static_cast<__nv_bfloat16*>(y), static_cast<uint4*>(saved_g),
+                                                                              saved_c, hT, cT, p);
   count_launch();
   return check_launch();
 }
 
-extern "C" int tfasr_lstm_rec_bwd(const void* dy, const float* saved, const float* c0, const float* whh, const int32_t* length, void* dgates,
-                                  float* dh0, float* dc0, int32_t B, int32_t U, int32_t R, tfasr_stream_t stream) {
-  if (!dy || !saved || !whh || !dgates || B < 0 || U < 1 || !lstm_supported(R)) return TFASR_INVALID_VALUE;
+extern "C" int tfasr_lstm_rec_bwd(const void* dy, const void* saved_g, const float* saved_c, const float* c0, const float* whh, const int32_t* length,
+                                  void* dgates, float* dh0, float* dc0, int32_t B, int32_t U, int32_t R, tfasr_stream_t stream) {
+  if (!dy || !saved_g || !saved_c || !whh || !dgates || B < 0 || U < 1 || !lstm_supported(R)) return TFASR_INVALID_VALUE;
   if (B == 0) return TFASR_OK;
   const size_t smem = lstm_bwd_smem(R);
   if (cudaFuncSetAttribute(lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TFASR_EXECUTION_FAILED;
   LstmParams p{B, U, R};
   dim3 grid(kLstmCluster, (unsigned)ceil_div(B, kLstmRows));
-  lstm_rec_bwd_kernel<<<grid, 512, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dy), saved, c0, whh, length,
+  lstm_rec_bwd_kernel<<<grid, 512, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const uint4*>(saved_g), saved_c, c0, whh,
+                                                                              length,
                                                                               static_cast<__nv_bfloat16*>(dgates), dh0, dc0, p);
   count_launch();
   return check_launch();

@@ -255,15 +255,15 @@ class _LstmFn(torch.autograd.Function):
         gx = kernels.gemm(x2, pack.wt, bias=bias.detach().float(), out_dtype=torch.float32).view(B, U, 4 * R)
         whh = recurrent_kernel.detach().float().contiguous()
         y, saved, _ = kernels.lstm_rec_fwd(gx, whh, length)
-        ctx.save_for_backward(x2, y, saved, whh, length)
+        ctx.save_for_backward(x2, y, saved[0], saved[1], whh, length)
         ctx.misc = (kernel, recurrent_kernel, bias, pack, B, U, E, R, x.requires_grad)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x2, y, saved, whh, length = ctx.saved_tensors
+        x2, y, saved_g, saved_c, whh, length = ctx.saved_tensors
         kernel, recurrent_kernel, bias, pack, B, U, E, R, need_dx = ctx.misc
-        dg = kernels.lstm_rec_bwd(dy.to(torch.bfloat16).contiguous(), saved, whh, length).view(B * U, 4 * R)
+        dg = kernels.lstm_rec_bwd(dy.to(torch.bfloat16).contiguous(), (saved_g, saved_c), whh, length).view(B * U, 4 * R)
         kernels.colsum(dg, _grad(bias).view(-1))
         ks = _splits(B * U)
         kernels.gemm(x2, dg, mn_major=True, out=_grad(kernel).view(E, 4 * R), accumulate=True, k_splits=ks)  # dW_ih += x^T dgates

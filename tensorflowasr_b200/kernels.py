@@ -254,17 +254,18 @@ def lstm_supported(R: int) -> bool:
 
 
 def lstm_rec_fwd(gx, whh, length=None, h0=None, c0=None, want_state=False):
-    """gx [B,U,4R] f32, whh [R,4R] f32 -> (y [B,U,R] bf16, saved [B,U,5,R] f32, (hT, cT) or None)."""
+    """gx [B,U,4R] f32, whh [R,4R] f32 -> (y [B,U,R] bf16, saved = (gates [B,U,4R] bf16, c [B,U,R] f32), (hT, cT) or None)."""
     lib = _lib.load()
     B, U, G = gx.shape
     R = G // 4
     y = torch.empty((B, U, R), dtype=torch.bfloat16, device=gx.device)
-    saved = torch.empty((B, U, 5, R), dtype=torch.float32, device=gx.device)
+    saved_g = torch.empty((B, U, 4 * R), dtype=torch.bfloat16, device=gx.device)
+    saved_c = torch.empty((B, U, R), dtype=torch.float32, device=gx.device)
     hT = torch.empty((B, R), dtype=torch.float32, device=gx.device) if want_state else None
     cT = torch.empty((B, R), dtype=torch.float32, device=gx.device) if want_state else None
-    _lib.check(lib.tfasr_lstm_rec_fwd(_lib.ptr(gx), _lib.ptr(whh), _lib.ptr(h0), _lib.ptr(c0), _lib.ptr(length), _lib.ptr(y), _lib.ptr(saved),
-                                      _lib.ptr(hT), _lib.ptr(cT), B, U, R, _st(gx)), "tfasr_lstm_rec_fwd")
-    return y, saved, ((hT, cT) if want_state else None)
+    _lib.check(lib.tfasr_lstm_rec_fwd(_lib.ptr(gx), _lib.ptr(whh), _lib.ptr(h0), _lib.ptr(c0), _lib.ptr(length), _lib.ptr(y), _lib.ptr(saved_g),
+                                      _lib.ptr(saved_c), _lib.ptr(hT), _lib.ptr(cT), B, U, R, _st(gx)), "tfasr_lstm_rec_fwd")
+    return y, (saved_g, saved_c), ((hT, cT) if want_state else None)
 
 
 def lstm_rec_bwd(dy, saved, whh, length=None, c0=None):
@@ -272,6 +273,6 @@ def lstm_rec_bwd(dy, saved, whh, length=None, c0=None):
     lib = _lib.load()
     B, U, R = dy.shape
     dgates = torch.empty((B, U, 4 * R), dtype=torch.bfloat16, device=dy.device)
-    _lib.check(lib.tfasr_lstm_rec_bwd(_lib.ptr(dy), _lib.ptr(saved), _lib.ptr(c0), _lib.ptr(whh), _lib.ptr(length), _lib.ptr(dgates), None, None,
+    _lib.check(lib.tfasr_lstm_rec_bwd(_lib.ptr(dy), _lib.ptr(saved[0]), _lib.ptr(saved[1]), _lib.ptr(c0), _lib.ptr(whh), _lib.ptr(length), _lib.ptr(dgates), None, None,
                                       B, U, R, _st(dy)), "tfasr_lstm_rec_bwd")
     return dgates

@@ -50,13 +50,15 @@ def main():
     kern = {}
     for ev in prof.events():
         if ev.device_type == torch.autograd.DeviceType.CUDA:
-            k = kern.setdefault(ev.name, [0.0, 0])
+            k = kern.setdefault(ev.name, [0.0, 0, 1e30, 0.0])
             k[0] += ev.device_time
             k[1] += 1
+            k[2] = min(k[2], ev.device_time)
+            k[3] = max(k[3], ev.device_time)
     total = sum(v[0] for v in kern.values())
     print(f"\n== device kernels per step: {total / 2e3:.3f} ms over {sum(v[1] for v in kern.values()) // 2} launches")
-    for name, (t, c) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
-        print(f"{t / 2e3:8.3f} ms {c // 2:5d} x {t / c:8.1f} us  {name[:150]}")
+    for name, (t, c, lo, hi) in sorted(kern.items(), key=lambda kv: -kv[1][0]):
+        print(f"{t / 2e3:8.3f} ms {c // 2:5d} x {t / c:8.1f} us [{lo:7.1f} .. {hi:7.1f}]  {name[:130]}")
 
 
 if __name__ == "__main__":
