@@ -214,6 +214,17 @@ def workload_config(n_gpus, batch_override=None):
 
 # ---------------------------------------------------------------------------------------------------- B200 arm
 def run_ours(args):
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner at communicator creation) are sent to
+    # stderr for the duration of the run; the result line goes to the saved descriptor
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        _run_ours(args, real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _run_ours(args, real_stdout):
     import tensorflowasr_b200 as tfasr
     from tensorflowasr_b200 import _lib, ops
     from tensorflowasr_b200 import dist as tdist
@@ -328,7 +339,7 @@ def run_ours(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_rnnt": roofline_rnnt, "cpu_baseline": cpu,
         "kernel_ms_per_step": kernel_ms,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
 
 
 def main():

@@ -212,6 +212,11 @@ int tfasr_bn_stats(const void* x, float* sums, int64_t R, int32_t C, tfasr_strea
 int tfasr_bn_apply(const void* x, const float* scale, const float* shift, void* y, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream);
 int tfasr_bn_bwd_stats(const void* dy, const void* x, const float* scale, const float* shift, const float* mean, const float* rstd,
                        float* sums, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream);
+/* per-channel bookkeeping in one launch: out [4][C] = scale, shift, mean, rstd from sums [2][C] (sum x, sum x^2) over `count` elements;
+ * moving statistics updated in place (may be NULL); bwd: dgamma += sums[1], dbeta += sums[0]. */
+int tfasr_bn_finalize(const float* sums, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* out, int32_t C,
+                      float count, float eps, float momentum, tfasr_stream_t stream);
+int tfasr_bn_bwd_finalize(const float* sums, float* dgamma, float* dbeta, int32_t C, tfasr_stream_t stream);
 int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* scale, const float* shift, const float* mean, const float* rstd,
                        const float* sums, float count, void* dx, int64_t R, int32_t C, int32_t act, tfasr_stream_t stream);
 
@@ -250,6 +255,9 @@ int tfasr_adamw_flat_f32(float* p, float* g, float* m, float* v, const uint8_t* 
                          float beta1, float beta2, float eps, float weight_decay, float l2, float grad_scale, int32_t zero_grad,
                          tfasr_stream_t stream);
 int tfasr_pack_weights(const void* table, int32_t n_entries, tfasr_stream_t stream);
+/* inverse for gradients: entry.src = parameter gradient (fp32 [K, N], row stride src_ld), entry.dst_w = packed fp32 buffer:
+ * grad[k, n] += packed[k, c0 + n * cs]; packed[...] = 0.  One launch per step for all fused Q|K|V / GLU projections. */
+int tfasr_unpack_add(const void* table, int32_t n_entries, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Causal depthwise 1-D convolution of the ConvModule (convolution.py:159-216, conformer.py:311-323,370): channels-last bf16 [B,T,C],

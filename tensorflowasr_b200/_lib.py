@@ -80,6 +80,9 @@ SIGNATURES = {
     "tfasr_adamw_flat_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_float, c_float,
                                        c_float, c_float, c_float, c_float, c_int32, c_void_p]),
     "tfasr_pack_weights": (c_int32, [c_void_p, c_int32, c_void_p]),
+    "tfasr_unpack_add": (c_int32, [c_void_p, c_int32, c_void_p]),
+    "tfasr_bn_finalize": (c_int32, [c_void_p] * 6 + [c_int32, c_float, c_float, c_float, c_void_p]),
+    "tfasr_bn_bwd_finalize": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "tfasr_dwconv_causal_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_dwconv_causal_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_specaugment_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_int32, c_int32, c_float,

@@ -416,6 +416,33 @@ static bool launch_bn_vec(BnVecArgs a, cudaStream_t stream, int* status) {
   return true;
 }
 
+// Per-channel bookkeeping of a training-mode BatchNorm in one launch (C threads) instead of ~14 elementwise launches:
+//   mean = sums[0] / count, var = max(sums[1] / count - mean^2, 0), rstd = rsqrt(var + eps), scale = gamma rstd, shift = beta - mean scale,
+//   moving = momentum * moving + (1 - momentum) * batch statistic        (keras BatchNormalization, momentum 0.99)
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ out, int C, float count,
+                                   float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = sums[c] / count;
+  const float var = fmaxf(sums[C + c] / count - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float scale = gamma[c] * rstd;
+  out[c] = scale;                      // scale
+  out[C + c] = beta[c] - mean * scale;  // shift
+  out[2 * C + c] = mean;
+  out[3 * C + c] = rstd;
+  if (moving_mean) moving_mean[c] = momentum * moving_mean[c] + (1.0f - momentum) * mean;
+  if (moving_var) moving_var[c] = momentum * moving_var[c] + (1.0f - momentum) * var;
+}
+// dgamma += sums[1], dbeta += sums[0]   (local contribution; taken before the sync-BN all-reduce of the backward sums)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dgamma[c] += sums[C + c];
+  dbeta[c] += sums[c];
+}
+
 static inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 static int rows_block_cfg(int C, dim3& block, int& rows_per_block, int64_t R, unsigned& grid) {
@@ -591,6 +618,22 @@ extern "C" int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* sc
   unsigned grid = (unsigned)min64(ceil_div(total, 256), kNumSMs * 32);
   bn_bwd_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), scale,
                                                                             shift, mean, rstd, sums, count, static_cast<__nv_bfloat16*>(dx), R, C, act);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_bn_finalize(const float* sums, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* out,
+                                 int32_t C, float count, float eps, float momentum, tfasr_stream_t stream) {
+  if (!sums || !gamma || !beta || !out || C < 1 || !(count > 0.f)) return TFASR_INVALID_VALUE;
+  bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, gamma, beta, moving_mean, moving_var, out, C, count,
+                                                                                                  eps, momentum);
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_bn_bwd_finalize(const float* sums, float* dgamma, float* dbeta, int32_t C, tfasr_stream_t stream) {
+  if (!sums || !dgamma || !dbeta || C < 1) return TFASR_INVALID_VALUE;
+  bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, dgamma, dbeta, C);
   count_launch();
   return check_launch();
 }

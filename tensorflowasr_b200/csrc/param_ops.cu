@@ -97,6 +97,23 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackEntry* __re
   }
 }
 
+// Inverse of the pack for gradients: the weight-gradient GEMMs of the fused Q|K|V and GLU-interleaved projections accumulate into
+// persistent packed fp32 buffers; at the end of the backward ONE launch adds every slice into its parameter's gradient
+//   grad[k, n] += packed[k, c0 + n * cs]      and clears the packed element for the next step.
+// Same table format: src = destination gradient (fp32 [K, N], row stride src_ld), dst_w = packed buffer (row stride ldw).
+__global__ void __launch_bounds__(256) unpack_add_kernel(const PackEntry* __restrict__ table) {
+  const PackEntry e = table[blockIdx.x];
+  float* grad = const_cast<float*>(e.src);
+  float* packed = static_cast<float*>(e.dst_w);
+  const int total = e.K * e.N;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+    const int k = i / e.N, n = i - k * e.N;
+    const size_t o = (size_t)k * e.ldw + e.c0 + (size_t)n * e.cs;
+    grad[(size_t)k * e.src_ld + n] += packed[o];
+    packed[o] = 0.f;
+  }
+}
+
 }  // namespace tfasr
 
 using namespace tfasr;
@@ -124,6 +141,14 @@ extern "C" int tfasr_pack_weights(const void* table, int32_t n_entries, tfasr_st
   if (!table || n_entries < 0) return TFASR_INVALID_VALUE;
   if (n_entries == 0) return TFASR_OK;
   pack_weights_kernel<<<dim3((unsigned)n_entries, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const PackEntry*>(table));
+  count_launch();
+  return check_launch();
+}
+
+extern "C" int tfasr_unpack_add(const void* table, int32_t n_entries, tfasr_stream_t stream) {
+  if (!table || n_entries < 0) return TFASR_INVALID_VALUE;
+  if (n_entries == 0) return TFASR_OK;
+  unpack_add_kernel<<<dim3((unsigned)n_entries, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const PackEntry*>(table));
   count_launch();
   return check_launch();
 }

@@ -269,17 +269,18 @@ class ConformerEncoder(_Params):
         buffers, refreshed by one batched launch (fused.PackPlan)."""
         if getattr(self, "_packs", None) is None or self._pack_plan is None:
             plan = fused.PackPlan()
+            unplan = fused.UnpackPlan()
             packs = {}
             for b in range(self.num_blocks):
                 for ff in ("ff_module_1", "ff_module_2"):
                     for d in ("dense_1", "dense_2"):
                         n = f"block_{b}.{ff}.{d}"
                         packs[n] = fused.WeightPack(self[n + ".kernel"], self[n + ".bias"], plan=plan)
-                packs[f"block_{b}.mhsa_module"] = fused.MhsaPack(self, f"block_{b}.mhsa_module", plan)
+                packs[f"block_{b}.mhsa_module"] = fused.MhsaPack(self, f"block_{b}.mhsa_module", plan, unplan)
                 cm = f"block_{b}.conv_module"
-                packs[cm + ".pw_conv_1"] = fused.GluPack(self[cm + ".pw_conv_1.kernel"], self[cm + ".pw_conv_1.bias"], plan)
+                packs[cm + ".pw_conv_1"] = fused.GluPack(self[cm + ".pw_conv_1.kernel"], self[cm + ".pw_conv_1.bias"], plan, unplan)
                 packs[cm + ".pw_conv_2"] = fused.WeightPack(self[cm + ".pw_conv_2.kernel"], self[cm + ".pw_conv_2.bias"], plan=plan)
-            self._packs, self._pack_plan = packs, plan
+            self._packs, self._pack_plan, self._unpack_plan = packs, plan, unplan
         self._pack_plan.run()
 
     def _salt(self, pre, k):

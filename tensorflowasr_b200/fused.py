@@ -82,6 +82,53 @@ class PackPlan:
         _lib.check(lib.tfasr_pack_weights(self.table.data_ptr(), len(self.entries), _lib.stream_ptr(self.table.device)), "tfasr_pack_weights")
 
 
+class UnpackPlan:
+    """Gradient-side counterpart of PackPlan: fused projections (Q|K|V, GLU-interleaved) accumulate their weight / bias gradients in
+    persistent packed fp32 buffers; ONE launch at the end of the backward pass (autograd engine callback) adds every slice into its
+    parameter's gradient and clears the packed buffers (csrc/param_ops.cu: unpack_add_kernel)."""
+
+    def __init__(self):
+        self.entries = []  # (param, grad_byte_off, K, N, grad_ld, packed, ldw, c0, cs)
+        self.table = None
+        self._ptrs = None
+        self._queued = False
+
+    def add(self, param, K, N, packed, ldw, c0=0, cs=1, grad_ld=None, grad_col0=0):
+        self.entries.append((param, 4 * grad_col0, K, N, N if grad_ld is None else grad_ld, packed, ldw, c0, cs))
+
+    def request(self):
+        """Called from a backward node: flush once when the whole backward pass has finished."""
+        if not self._queued:
+            self._queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._flush)
+
+    def _flush(self):
+        self._queued = False
+        self.run()
+
+    def run(self):
+        if not self.entries:
+            return
+        import numpy as np
+
+        ptrs = [_grad(e[0]).data_ptr() for e in self.entries]
+        if ptrs != self._ptrs:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("UnpackPlan: gradient storage moved during CUDA-graph capture")
+            if PackPlan._DT is None:
+                PackPlan._DT = np.dtype([("src", "<u8"), ("dst_w", "<u8"), ("dst_wt", "<u8"), ("K", "<i4"), ("N", "<i4"), ("src_ld", "<i4"),
+                                        ("ldw", "<i4"), ("ldwt", "<i4"), ("c0", "<i4"), ("cs", "<i4"), ("flags", "<i4")])
+            arr = np.zeros(len(self.entries), dtype=PackPlan._DT)
+            for i, (prm, off, K, N, gld, packed, ldw, c0, cs) in enumerate(self.entries):
+                arr[i] = (ptrs[i] + off, packed.data_ptr(), 0, K, N, gld, ldw, 0, c0, cs, 0)
+            self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(self.entries[0][5].device)
+            self._ptrs = ptrs
+        from . import _lib
+
+        lib = _lib.load()
+        _lib.check(lib.tfasr_unpack_add(self.table.data_ptr(), len(self.entries), _lib.stream_ptr(self.table.device)), "tfasr_unpack_add")
+
+
 class WeightPack:
     """bf16 operand copies of one Dense kernel W [K, N] (Keras layout): `wt` = W^T [N, K] for the forward GEMM (B operand,
     K-major), `w` = W [K, N] for the data-gradient GEMM (dX = dY . W^T: B operand [K, N] with contraction N).
@@ -364,15 +411,10 @@ def bn_train_fwd(x2d, gamma, beta, moving_mean, moving_var, act=1):
     if world > 1:
         torch.distributed.all_reduce(sums)  # C2: sync-BN statistics
     count = float(R * world)
-    mean = sums[0] / count
-    var = (sums[1] / count - mean * mean).clamp_min_(0.0)
-    rstd = torch.rsqrt(var + BN_EPS)
-    scale = gamma.detach().float() * rstd
-    shift = beta.detach().float() - mean * scale
-    y = kernels.bn_apply(x2d, scale, shift, act)
     with torch.no_grad():
-        moving_mean.mul_(BN_MOMENTUM).add_(mean, alpha=1.0 - BN_MOMENTUM)
-        moving_var.mul_(BN_MOMENTUM).add_(var, alpha=1.0 - BN_MOMENTUM)
+        out = kernels.bn_finalize(sums, gamma.detach(), beta.detach(), moving_mean, moving_var, count, BN_EPS, BN_MOMENTUM)
+    scale, shift, mean, rstd = out[0], out[1], out[2], out[3]
+    y = kernels.bn_apply(x2d, scale, shift, act)
     return y, (scale, shift, mean, rstd, count)
 
 
@@ -380,8 +422,7 @@ def bn_train_bwd(dy2d, x2d, saved, gamma, beta, act=1):
     """-> dx2d; accumulates dgamma / dbeta into the parameters' .grad."""
     scale, shift, mean, rstd, count = saved
     sums = kernels.bn_bwd_stats(dy2d, x2d, scale, shift, mean, rstd, act)
-    _grad(gamma).add_(sums[1])  # local contribution; the gradient all-reduce sums over replicas
-    _grad(beta).add_(sums[0])
+    kernels.bn_bwd_finalize(sums, _grad(gamma).view(-1), _grad(beta).view(-1))  # local contribution; the gradient all-reduce sums over replicas
     if _world() > 1:
         sums = sums.clone()
         torch.distributed.all_reduce(sums)
@@ -462,13 +503,21 @@ def conv2d_subsampling(feats, sub, training):
 class QkvPack(WeightPack):
     """Fused Q/K/V projection: one GEMM [D -> 3NH]; its weight / bias gradients fan out to the three Keras EinsumDense layers."""
 
-    def __init__(self, enc, pre, plan: PackPlan = None):
+    def __init__(self, enc, pre, plan: PackPlan = None, unplan: UnpackPlan = None):
         m = pre + ".mhsa"
         D, N, H = enc.dmodel, enc.num_heads, enc.head_size
         NH = N * H
         self.parts = [(enc[f"{m}.{k}.kernel"], enc[f"{m}.{k}.bias"]) for k in ("query", "key", "value")]
         self.param, self.D, self.NH = None, D, NH
         self._db = None
+        self.unplan = unplan
+        if unplan is not None:
+            dev = self.parts[0][0].device
+            self.dw_packed = torch.zeros((D, 3 * NH), dtype=torch.float32, device=dev)
+            self.db_packed = torch.zeros(3 * NH, dtype=torch.float32, device=dev)
+            for i, (wp, bp) in enumerate(self.parts):
+                unplan.add(wp, D, NH, self.dw_packed, 3 * NH, c0=i * NH)
+                unplan.add(bp, 1, NH, self.db_packed, 3 * NH, c0=i * NH)
         if plan is not None:
             dev = self.parts[0][0].device
             self.w = torch.empty((D, 3 * NH), dtype=torch.bfloat16, device=dev)
@@ -488,11 +537,17 @@ class QkvPack(WeightPack):
         return self._bias
 
     def bias_grad_target(self):
+        if self.unplan is not None:
+            return self.db_packed
         self._db = torch.zeros(3 * self.NH, dtype=torch.float32, device=self.w.device)
         return self._db
 
     def accumulate_wgrad(self, x, dz):
         D, NH = self.D, self.NH
+        if self.unplan is not None:  # packed accumulation; fanned out to the three layers by the plan's single launch
+            kernels.gemm(x, dz, mn_major=True, out=self.dw_packed, accumulate=True, k_splits=_splits(x.shape[0]))
+            self.unplan.request()
+            return
         dw = torch.zeros((D, 3 * NH), dtype=torch.float32, device=x.device)
         kernels.gemm(x, dz, mn_major=True, out=dw, accumulate=True, k_splits=_splits(x.shape[0]))
         for i, (wp, bp) in enumerate(self.parts):
@@ -503,10 +558,10 @@ class QkvPack(WeightPack):
 
 
 class MhsaPack:
-    def __init__(self, enc, pre, plan: PackPlan = None):
+    def __init__(self, enc, pre, plan: PackPlan = None, unplan: UnpackPlan = None):
         m = pre + ".mhsa"
         D, N, H = enc.dmodel, enc.num_heads, enc.head_size
-        self.qkv = QkvPack(enc, pre, plan)
+        self.qkv = QkvPack(enc, pre, plan, unplan)
         self.pos = WeightPack(enc[f"{m}.encoding.kernel"], enc[f"{m}.encoding.bias"], plan=plan, shape2d=(D, N * H))
         self.out = WeightPack(enc[f"{m}.attention_output.kernel"], enc[f"{m}.attention_output.bias"], plan=plan, shape2d=(N * H, D))
 
@@ -540,10 +595,17 @@ class GluPack(WeightPack):
     """pw_conv_1 [D, 2D] with its GLU halves interleaved column-wise (a_0, b_0, a_1, b_1, ...) so that the GEMM epilogue applies
     a * sigmoid(b) on adjacent columns; gradients are de-interleaved back into the Keras layout."""
 
-    def __init__(self, param, bias, plan: PackPlan = None):
+    def __init__(self, param, bias, plan: PackPlan = None, unplan: UnpackPlan = None):
         super().__init__(param, bias, interleave_glu=True, plan=plan)
-        D2 = self.shape2d[1]
+        K, D2 = self.shape2d
         self.D = D2 // 2
+        self.unplan = unplan
+        if unplan is not None:
+            self.dw_packed = torch.zeros((K, D2), dtype=torch.float32, device=param.device)
+            self.db_packed = torch.zeros(D2, dtype=torch.float32, device=param.device)
+            for half in (0, 1):
+                unplan.add(param, K, self.D, self.dw_packed, D2, c0=half, cs=2, grad_ld=D2, grad_col0=half * self.D)
+                unplan.add(bias, 1, self.D, self.db_packed, D2, c0=half, cs=2, grad_ld=D2, grad_col0=half * self.D)
         if plan is not None:
             self._bias = torch.empty(D2, dtype=torch.float32, device=param.device)
             plan.add(bias, 1, self.D, self._bias, None, ldw=D2, c0=0, cs=2, src_ld=D2, src_col0=0, f32=True)
@@ -603,11 +665,16 @@ class _ConvModuleFn(torch.autograd.Function):
         dc = bn_train_bwd(dyb, c, saved, bn[0], bn[1])
         # the depthwise bias sits in front of a batch norm: its gradient is identically zero
         dg = kernels.dwconv_bwd(dc.view(B, T, D), g.view(B, T, D), w32, _grad(dw_w).view(-1, D), None).view(M, D)
-        db1 = torch.zeros(2 * D, dtype=torch.float32, device=x.device)
-        daux = kernels.glu_bwd(aux, dg, colsum=db1)
-        dw1 = torch.zeros((D, 2 * D), dtype=torch.float32, device=x.device)
-        kernels.gemm(a, daux, mn_major=True, out=dw1, accumulate=True, k_splits=_splits(M))
-        p1.deinterleave_add(dw1, db1)
+        if getattr(p1, "unplan", None) is not None:
+            daux = kernels.glu_bwd(aux, dg, colsum=p1.db_packed)
+            kernels.gemm(a, daux, mn_major=True, out=p1.dw_packed, accumulate=True, k_splits=_splits(M))
+            p1.unplan.request()
+        else:
+            db1 = torch.zeros(2 * D, dtype=torch.float32, device=x.device)
+            daux = kernels.glu_bwd(aux, dg, colsum=db1)
+            dw1 = torch.zeros((D, 2 * D), dtype=torch.float32, device=x.device)
+            kernels.gemm(a, daux, mn_major=True, out=dw1, accumulate=True, k_splits=_splits(M))
+            p1.deinterleave_add(dw1, db1)
         da = kernels.gemm(daux, p1.w)
         dx = kernels.layernorm_bwd(da, x, mean, rstd, ln_g, _grad(ln_g), _grad(ln_b), dres=dout)
         return (dx,) + (None,) * 14

@@ -173,6 +173,21 @@ def bn_stats(x2d):
     return sums
 
 
+def bn_finalize(sums, gamma, beta, moving_mean, moving_var, count, eps, momentum):
+    """-> out [4, C] f32 = (scale, shift, mean, rstd); moving statistics updated in place."""
+    lib = _lib.load()
+    C = sums.shape[1]
+    out = torch.empty((4, C), dtype=torch.float32, device=sums.device)
+    _lib.check(lib.tfasr_bn_finalize(_lib.ptr(sums), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(moving_mean), _lib.ptr(moving_var), _lib.ptr(out), C,
+                                     float(count), float(eps), float(momentum), _st(sums)), "tfasr_bn_finalize")
+    return out
+
+
+def bn_bwd_finalize(sums, dgamma, dbeta):
+    lib = _lib.load()
+    _lib.check(lib.tfasr_bn_bwd_finalize(_lib.ptr(sums), _lib.ptr(dgamma), _lib.ptr(dbeta), sums.shape[1], _st(sums)), "tfasr_bn_bwd_finalize")
+
+
 def bn_apply(x2d, scale, shift, act=1):
     lib = _lib.load()
     R, C = x2d.shape
