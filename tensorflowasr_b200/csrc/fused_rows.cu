@@ -274,45 +274,58 @@ __global__ void __launch_bounds__(256) scale_mask_colsum_vec_kernel(const __nv_b
   }
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (rl < RL) {
-    for (int r = r0 + rl; r < r1; r += RL) {
-      const size_t idx = (size_t)r * N + cv * 8;
-      const uint4 raw = *reinterpret_cast<const uint4*>(in + idx);
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-      float v[8];
+    for (int rb = r0 + rl; rb < r1; rb += 4 * RL) {
+      // four rows per trip, all loads issued before the first use (the scalar loop exposed one L2 round trip per row)
+      uint4 raw4[4], add4[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[2 * j] = __uint_as_float(w[j] << 16) * scale;
-        v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u) * scale;
-      }
-      if (drop_p > 0.f) {
-        const uint32_t key = dropout_rowkey(seed, (unsigned long long)r);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t hsh = dropout_hash(key, (uint32_t)(cv * 8 + 2 * j));
-          v[2 * j] = ((hsh & 0xFFFFu) >= drop_thr) ? v[2 * j] * keep_scale : 0.f;
-          v[2 * j + 1] = ((hsh >> 16) >= drop_thr) ? v[2 * j + 1] * keep_scale : 0.f;
+      for (int k = 0; k < 4; ++k) {
+        const int r = rb + k * RL;
+        if (r < r1) {
+          raw4[k] = *reinterpret_cast<const uint4*>(in + (size_t)r * N + cv * 8);
+          if (add) add4[k] = *reinterpret_cast<const uint4*>(add + (size_t)r * N + cv * 8);
         }
       }
-      if (add) {
-        const uint4 ra = *reinterpret_cast<const uint4*>(add + idx);
-        const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = rb + k * RL;
+        if (r >= r1) break;
+        const size_t idx = (size_t)r * N + cv * 8;
+        const uint32_t w[4] = {raw4[k].x, raw4[k].y, raw4[k].z, raw4[k].w};
+        float v[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          v[2 * j] += __uint_as_float(wa[j] << 16);
-          v[2 * j + 1] += __uint_as_float(wa[j] & 0xFFFF0000u);
+          v[2 * j] = __uint_as_float(w[j] << 16) * scale;
+          v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u) * scale;
         }
-      }
-      if (out) {
-        uint32_t pk[4];
+        if (drop_p > 0.f) {
+          const uint32_t key = dropout_rowkey(seed, (unsigned long long)r);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t hsh = dropout_hash(key, (uint32_t)(cv * 8 + 2 * j));
+            v[2 * j] = ((hsh & 0xFFFFu) >= drop_thr) ? v[2 * j] * keep_scale : 0.f;
+            v[2 * j + 1] = ((hsh >> 16) >= drop_thr) ? v[2 * j + 1] * keep_scale : 0.f;
+          }
         }
-        *reinterpret_cast<uint4*>(out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
+        if (add) {
+          const uint32_t wa[4] = {add4[k].x, add4[k].y, add4[k].z, add4[k].w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+          for (int j = 0; j < 4; ++j) {
+            v[2 * j] += __uint_as_float(wa[j] << 16);
+            v[2 * j + 1] += __uint_as_float(wa[j] & 0xFFFF0000u);
+          }
+        }
+        if (out) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          *reinterpret_cast<uint4*>(out + idx) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
     }
   }
   if (colsum) {
@@ -425,9 +438,79 @@ extern "C" int tfasr_scale_mask_colsum(const void* in, const void* add, void* ou
   return check_launch();
 }
 
+namespace tfasr {
+// Vector variant (D % 4 == 0, D / 4 <= 256): thread = (row lane, 4 GLU outputs): 16-byte aux / daux accesses (4 interleaved (a, b) pairs),
+// 8-byte dg loads, four rows per trip with the loads issued first, column sums reduced in SMEM.
+__global__ void __launch_bounds__(256) glu_bwd_vec_kernel(const __nv_bfloat16* __restrict__ aux, const __nv_bfloat16* __restrict__ dg,
+                                                          __nv_bfloat16* __restrict__ daux, float* __restrict__ colsum, int M, int D,
+                                                          int rows_per_block) {
+  extern __shared__ float s_col[];  // [2 D]
+  const int NV = D >> 2, RL = blockDim.x / NV;
+  const int cv = threadIdx.x % NV, rl = threadIdx.x / NV;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  if (colsum) {
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) s_col[i] = 0.f;
+    __syncthreads();
+  }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < RL) {
+    for (int rb = r0 + rl; rb < r1; rb += 4 * RL) {
+      uint4 ab4[4];
+      uint2 g4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = rb + k * RL;
+        if (r < r1) {
+          ab4[k] = *reinterpret_cast<const uint4*>(aux + (size_t)r * 2 * D + cv * 8);
+          g4[k] = *reinterpret_cast<const uint2*>(dg + (size_t)r * D + cv * 4);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = rb + k * RL;
+        if (r >= r1) break;
+        const uint32_t w[4] = {ab4[k].x, ab4[k].y, ab4[k].z, ab4[k].w};
+        const uint32_t gw[2] = {g4[k].x, g4[k].y};
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = __uint_as_float(w[j] << 16), b = __uint_as_float(w[j] & 0xFFFF0000u);
+          const float g = (j & 1) ? __uint_as_float(gw[j >> 1] & 0xFFFF0000u) : __uint_as_float(gw[j >> 1] << 16);
+          const float sg = 1.0f / (1.0f + __expf(-b));
+          const float da = g * sg, db = g * a * sg * (1.0f - sg);
+          const __nv_bfloat162 t = __floats2bfloat162_rn(da, db);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+          acc[2 * j] += da;
+          acc[2 * j + 1] += db;
+        }
+        *reinterpret_cast<uint4*>(daux + (size_t)r * 2 * D + cv * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  if (colsum) {
+    if (rl < RL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_col[cv * 8 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) atomicAdd(colsum + i, s_col[i]);
+  }
+}
+}  // namespace tfasr
+
 extern "C" int tfasr_glu_bwd(const void* aux, const void* dg, void* daux, float* colsum, int32_t M, int32_t D, tfasr_stream_t stream) {
   if (!aux || !dg || !daux || M < 0 || D < 1) return TFASR_INVALID_VALUE;
   if (M == 0) return TFASR_OK;
+  if ((D & 3) == 0 && (D >> 2) <= 256 &&
+      ((reinterpret_cast<uintptr_t>(aux) | reinterpret_cast<uintptr_t>(daux)) & 15) == 0 && (reinterpret_cast<uintptr_t>(dg) & 7) == 0) {
+    const int RL = 256 / (D >> 2);
+    int rpb = RL * 4;
+    while ((long long)ceil_div(M, rpb) > 8LL * kNumSMs) rpb *= 2;
+    glu_bwd_vec_kernel<<<(unsigned)ceil_div(M, rpb), 256, sizeof(float) * 2 * D, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(aux), static_cast<const __nv_bfloat16*>(dg), static_cast<__nv_bfloat16*>(daux), colsum, M, D, rpb);
+    count_launch();
+    return check_launch();
+  }
   const int rows_per_block = 32;
   glu_bwd_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(aux), static_cast<const __nv_bfloat16*>(dg), static_cast<__nv_bfloat16*>(daux), colsum, M, D, rows_per_block);
