@@ -277,6 +277,50 @@ int tfasr_specaugment_f32(float* feat /*[B,T,F]*/, const int32_t* length /*[B] f
                           float p_upperbound, float time_prob, int32_t n_freq, int32_t freq_factor, float freq_prob, float mask_value,
                           const unsigned long long* seed_ptr, unsigned long long salt, tfasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * ContextNet encoder body (tensorflow_asr/models/encoders/contextnet.py).  Activations channels-last bf16 [B,T,C]
+ * (C % 8 == 0, 16-byte aligned), parameters / statistics fp32.  act codes: 0 linear, 1 swish (silu), 2 relu (contextnet.py:29-36).
+ *   tfasr_seq_dwconv_fwd/bwd : depthwise half of SeparableConv1D(padding="causal", strides=s) (contextnet.py:53-63, causal pad
+ *                         convolution.py:25-37): y [B, ceil(T/s), C] = sum_k w[k,c] x[b, j s - (K-1) + k, c]; w [K,C] f32 (keras
+ *                         depthwise_kernel [K,C,1]).  bwd writes dx [B,T,C] (NULL = skip) and accumulates (+=) dw [K,C]; K <= 32.
+ *                         (the pointwise half + bias is tfasr_gemm_bf16, the BatchNorm + activation tfasr_bn_*)
+ *   tfasr_seq_masked_mean  : GlobalAveragePooling1D with the sequence mask (contextnet.py:137,156): m [B,C] f32 = mean over t < length[b]
+ *   tfasr_se_fc_fwd/bwd    : SEModule fc1 -> activation -> fc2 -> sigmoid (contextnet.py:157-160).  W1 [C,H], b1 [H], W2 [H,C], b2 [C];
+ *                         fwd -> z1 [B,H] (pre-activation, saved), s [B,C].  bwd: ds [B,C] -> dm [B,C] (gradient of the masked mean's
+ *                         INPUT frames, i.e. already divided by length), accumulates (+=) dW1 / db1 / dW2 / db2; dz2 [B,C], dz1 [B,H] scratch.
+ *   tfasr_se_apply_fwd     : out = act(y * s[b,:] + res)   (SEModule.call :162-163 + ConvBlock.call :258-261; res NULL = no residual)
+ *   tfasr_se_apply_bwd     : dres [B,T,C] bf16 = dout * act'(y s + res) (also the residual branch's gradient); ds [B,C] = sum_t dres * y
+ *   tfasr_se_dy            : dy = dres * s[b,:] + (t < length[b] ? dm[b,:] : 0)
+ * ---------------------------------------------------------------------------------------------- */
+int tfasr_seq_dwconv_fwd(const void* x, const float* w, void* y, int32_t B, int32_t T, int32_t C, int32_t K, int32_t stride, tfasr_stream_t stream);
+int tfasr_seq_dwconv_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, int32_t B, int32_t T, int32_t C, int32_t K,
+                         int32_t stride, tfasr_stream_t stream);
+int tfasr_seq_masked_mean(const void* y, const int32_t* length, float* m, int32_t B, int32_t T, int32_t C, tfasr_stream_t stream);
+int tfasr_se_fc_fwd(const float* m, const float* W1, const float* b1, const float* W2, const float* b2, float* z1, float* s, int32_t B, int32_t C,
+                    int32_t H, int32_t act, tfasr_stream_t stream);
+int tfasr_se_fc_bwd(const float* ds, const float* s, const float* z1, const float* m, const float* W1, const float* W2, const int32_t* length,
+                    float* dz2, float* dz1, float* dm, float* dW1, float* db1, float* dW2, float* db2, int32_t B, int32_t T, int32_t C, int32_t H,
+                    int32_t act, tfasr_stream_t stream);
+int tfasr_se_apply_fwd(const void* y, const float* s, const void* res, void* out, int32_t B, int32_t T, int32_t C, int32_t act,
+                       tfasr_stream_t stream);
+int tfasr_se_apply_bwd(const void* dout, const void* y, const float* s, const void* res, void* dres, float* ds, int32_t B, int32_t T, int32_t C,
+                       int32_t act, tfasr_stream_t stream);
+int tfasr_se_dy(const void* dres, const float* s, const float* dm, const int32_t* length, void* dy, int32_t B, int32_t T, int32_t C,
+                tfasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conv2D lowering for the DeepSpeech2 conv module (models/encoders/deepspeech2.py:56-60,105-117): general kernel
+ * (kh, kw), strides (sh, sw), zero padding of pt rows / pl columns in front ("same": total // 2, causal: k - 1).  The convolution is
+ * col [B*To*Fo, Kp] . W[Kp, Cout] on tfasr_gemm_bf16 with Kp = round_up(kh*kw*Cin, 8) (zero columns beyond kh*kw*Cin).
+ *   tfasr_conv_im2col : x [B,T,F,Cin] (fp32 when x_f32 != 0 — the feature tensor —, else bf16) -> col bf16, column (i*kw + j)*Cin + ci
+ *   tfasr_conv_col2im : dcol -> da [B,T,F,Cin] bf16 (Cin % 8 == 0), the data gradient
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tfasr_conv_geom {
+  int32_t B, T, F, Cin, To, Fo, kh, kw, sh, sw, pt, pl, Kp;
+} tfasr_conv_geom;
+int tfasr_conv_im2col(const void* x, int32_t x_f32, void* col, const tfasr_conv_geom* geom, tfasr_stream_t stream);
+int tfasr_conv_col2im(const void* dcol, void* da, const tfasr_conv_geom* geom, tfasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,12 @@ class LogmelCfg(ctypes.Structure):
     ]
 
 
+class ConvGeom(ctypes.Structure):
+    """Mirror of `tfasr_conv_geom`."""
+
+    _fields_ = [(n, c_int32) for n in ("B", "T", "F", "Cin", "To", "Fo", "kh", "kw", "sh", "sw", "pt", "pl", "Kp")]
+
+
 class GemmEpilogue(ctypes.Structure):
     """Mirror of `tfasr_gemm_epilogue`."""
 
@@ -95,6 +101,16 @@ SIGNATURES = {
     "tfasr_scale_mask_colsum": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p,
                                           ctypes.c_ulonglong, c_void_p]),
     "tfasr_glu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "tfasr_seq_dwconv_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_seq_dwconv_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_seq_masked_mean": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_se_fc_fwd": (c_int32, [c_void_p] * 7 + [c_int32] * 4 + [c_void_p]),
+    "tfasr_se_fc_bwd": (c_int32, [c_void_p] * 14 + [c_int32] * 5 + [c_void_p]),
+    "tfasr_se_apply_fwd": (c_int32, [c_void_p] * 4 + [c_int32] * 4 + [c_void_p]),
+    "tfasr_se_apply_bwd": (c_int32, [c_void_p] * 6 + [c_int32] * 4 + [c_void_p]),
+    "tfasr_se_dy": (c_int32, [c_void_p] * 5 + [c_int32] * 3 + [c_void_p]),
+    "tfasr_conv_im2col": (c_int32, [c_void_p, c_int32, c_void_p, POINTER(ConvGeom), c_void_p]),
+    "tfasr_conv_col2im": (c_int32, [c_void_p, c_void_p, POINTER(ConvGeom), c_void_p]),
     "tfasr_ctc_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "tfasr_ctc_loss_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

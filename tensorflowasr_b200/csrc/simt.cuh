@@ -1,0 +1,68 @@
+// Portability shim for the plain-SIMT kernel headers (*_kernels.cuh).
+//
+// Device build (nvcc, sm_100a): common.cuh + 16-byte access helpers.
+// Emulation build (g++ -DTFASR_EMU_BUILD -I tests/emu): tests/emu/cuda_emu.h supplies threadIdx / __syncthreads / shuffles / atomics / bf16
+// so the SAME kernel source runs on the CPU inside the `-m "not gpu"` suite (tests/test_emu_kernels.py).  Test infrastructure only: the
+// emulation build never produces libtfasr_b200.so.
+#pragma once
+#ifdef TFASR_EMU_BUILD
+#include "cuda_emu.h"
+namespace tfasr {
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+constexpr int kNumSMs = 148;
+}  // namespace tfasr
+#else
+#include "common.cuh"
+#define TFASR_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
+
+namespace tfasr {
+
+// 16-byte global accesses (8 bf16).  The emulation build aborts on a misaligned address, as the hardware would fault.
+__device__ __forceinline__ uint4 ld16(const void* p) {
+#ifdef TFASR_EMU_BUILD
+  if (reinterpret_cast<uintptr_t>(p) & 15) abort();
+#endif
+  return *reinterpret_cast<const uint4*>(p);
+}
+__device__ __forceinline__ void st16(void* p, const uint4& v) {
+#ifdef TFASR_EMU_BUILD
+  if (reinterpret_cast<uintptr_t>(p) & 15) abort();
+#endif
+  *reinterpret_cast<uint4*>(p) = v;
+}
+__device__ __forceinline__ void bf8_unpack(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint4 bf8_pack(const float* f) {
+  uint32_t pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    pk[j] = (uint32_t)(*reinterpret_cast<const uint16_t*>(&t.x)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&t.y)) << 16);
+  }
+  return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+__device__ __forceinline__ float simt_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// activation codes shared with the BatchNorm kernels: 0 none, 1 swish, 2 relu
+__device__ __forceinline__ float simt_act(float z, int act) {
+  if (act == 1) return z * simt_sigmoid(z);
+  if (act == 2) return fmaxf(z, 0.f);
+  return z;
+}
+__device__ __forceinline__ float simt_act_grad(float z, int act) {
+  if (act == 1) {
+    const float g = simt_sigmoid(z);
+    return g * (1.0f + z * (1.0f - g));
+  }
+  if (act == 2) return z > 0.f ? 1.0f : 0.f;
+  return 1.0f;
+}
+
+}  // namespace tfasr

@@ -291,3 +291,122 @@ def lstm_rec_bwd(dy, saved, whh, length=None, c0=None):
     _lib.check(lib.tfasr_lstm_rec_bwd(_lib.ptr(dy), _lib.ptr(saved[0]), _lib.ptr(saved[1]), _lib.ptr(c0), _lib.ptr(whh), _lib.ptr(length), _lib.ptr(dgates), None, None,
                                       B, U, R, _st(dy)), "tfasr_lstm_rec_bwd")
     return dgates
+
+
+# ------------------------------------------------------------------------------------------------ ContextNet / DeepSpeech2 encoder bodies
+_BN_ACT = {None: 0, "linear": 0, "none": 0, "swish": 1, "silu": 1, "relu": 2}
+
+
+def act_code(name) -> int:
+    return _BN_ACT[name]
+
+
+def seq_dwconv_fwd(x, w, stride=1):
+    """x [B,T,C] bf16, w [K,C] f32 -> y [B, ceil(T/stride), C] bf16 (causal depthwise conv, contextnet.py:53-63)."""
+    lib = _lib.load()
+    B, T, C = x.shape
+    y = torch.empty((B, -(-T // stride), C), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.tfasr_seq_dwconv_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), B, T, C, w.shape[0], int(stride), _st(x)), "tfasr_seq_dwconv_fwd")
+    return y
+
+
+def seq_dwconv_bwd(dy, x, w, dw, stride=1, need_dx=True):
+    """-> dx [B,T,C] bf16 (or None); dw (f32 [K,C]) accumulated."""
+    lib = _lib.load()
+    B, T, C = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    _lib.check(lib.tfasr_seq_dwconv_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), _lib.ptr(dx), _lib.ptr(dw), B, T, C, w.shape[0], int(stride), _st(x)),
+               "tfasr_seq_dwconv_bwd")
+    return dx
+
+
+def seq_masked_mean(y, length):
+    """y [B,T,C] bf16, length [B] int32 -> m [B,C] f32 (mean over the valid frames)."""
+    lib = _lib.load()
+    B, T, C = y.shape
+    m = torch.empty((B, C), dtype=torch.float32, device=y.device)
+    _lib.check(lib.tfasr_seq_masked_mean(_lib.ptr(y), _lib.ptr(length), _lib.ptr(m), B, T, C, _st(y)), "tfasr_seq_masked_mean")
+    return m
+
+
+def se_fc_fwd(m, W1, b1, W2, b2, act):
+    """-> (z1 [B,H] f32, s [B,C] f32 = sigmoid(act(m W1 + b1) W2 + b2))."""
+    lib = _lib.load()
+    B, C = m.shape
+    H = W1.shape[1]
+    z1 = torch.empty((B, H), dtype=torch.float32, device=m.device)
+    s = torch.empty((B, C), dtype=torch.float32, device=m.device)
+    _lib.check(lib.tfasr_se_fc_fwd(_lib.ptr(m), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2), _lib.ptr(b2), _lib.ptr(z1), _lib.ptr(s), B, C, H, int(act),
+                                   _st(m)), "tfasr_se_fc_fwd")
+    return z1, s
+
+
+def se_fc_bwd(ds, s, z1, m, W1, W2, length, T, act, dW1, db1, dW2, db2):
+    """-> dm [B,C] f32 (already divided by the utterance length); parameter gradients accumulated."""
+    lib = _lib.load()
+    B, C = m.shape
+    H = W1.shape[1]
+    dz2 = torch.empty_like(s)
+    dz1 = torch.empty_like(z1)
+    dm = torch.empty_like(s)
+    _lib.check(lib.tfasr_se_fc_bwd(_lib.ptr(ds), _lib.ptr(s), _lib.ptr(z1), _lib.ptr(m), _lib.ptr(W1), _lib.ptr(W2), _lib.ptr(length), _lib.ptr(dz2),
+                                   _lib.ptr(dz1), _lib.ptr(dm), _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW2), _lib.ptr(db2), B, int(T), C, H, int(act),
+                                   _st(m)), "tfasr_se_fc_bwd")
+    return dm
+
+
+def se_apply_fwd(y, s, res, act):
+    lib = _lib.load()
+    B, T, C = y.shape
+    out = torch.empty_like(y)
+    _lib.check(lib.tfasr_se_apply_fwd(_lib.ptr(y), _lib.ptr(s), _lib.ptr(res), _lib.ptr(out), B, T, C, int(act), _st(y)), "tfasr_se_apply_fwd")
+    return out
+
+
+def se_apply_bwd(dout, y, s, res, act):
+    """-> (dres [B,T,C] bf16, ds [B,C] f32)."""
+    lib = _lib.load()
+    B, T, C = y.shape
+    dres = torch.empty_like(y)
+    ds = torch.empty((B, C), dtype=torch.float32, device=y.device)
+    _lib.check(lib.tfasr_se_apply_bwd(_lib.ptr(dout), _lib.ptr(y), _lib.ptr(s), _lib.ptr(res), _lib.ptr(dres), _lib.ptr(ds), B, T, C, int(act), _st(y)),
+               "tfasr_se_apply_bwd")
+    return dres, ds
+
+
+def se_dy(dres, s, dm, length):
+    lib = _lib.load()
+    B, T, C = dres.shape
+    dy = torch.empty_like(dres)
+    _lib.check(lib.tfasr_se_dy(_lib.ptr(dres), _lib.ptr(s), _lib.ptr(dm), _lib.ptr(length), _lib.ptr(dy), B, T, C, _st(dres)), "tfasr_se_dy")
+    return dy
+
+
+def conv_geom(B, T, F, Cin, kh, kw, sh, sw, padding):
+    """Geometry of Conv2D(kernel (kh,kw), strides (sh,sw), padding) on [B,T,F,Cin]: keras "same" (total = max((ceil(n/s)-1) s + k - n, 0),
+    total // 2 in front) or the reference's causal padding (k - 1 in front, then VALID; convolution.py:25-37)."""
+    if padding == "same":
+        To, Fo = -(-T // sh), -(-F // sw)
+        pt = max((To - 1) * sh + kh - T, 0) // 2
+        pl = max((Fo - 1) * sw + kw - F, 0) // 2
+    elif padding == "causal":
+        pt, pl = kh - 1, kw - 1
+        To, Fo = (T + pt - kh) // sh + 1, (F + pl - kw) // sw + 1
+    else:
+        raise ValueError(padding)
+    return _lib.ConvGeom(B, T, F, Cin, To, Fo, kh, kw, sh, sw, pt, pl, (kh * kw * Cin + 7) // 8 * 8)
+
+
+def conv_im2col(x, g):
+    """x [B,T,F,Cin] f32 | bf16 -> col [B*To*Fo, Kp] bf16."""
+    lib = _lib.load()
+    col = torch.empty((g.B * g.To * g.Fo, g.Kp), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.tfasr_conv_im2col(_lib.ptr(x), int(x.dtype == torch.float32), _lib.ptr(col), ctypes.byref(g), _st(x)), "tfasr_conv_im2col")
+    return col
+
+
+def conv_col2im(dcol, g):
+    lib = _lib.load()
+    da = torch.empty((g.B, g.T, g.F, g.Cin), dtype=torch.bfloat16, device=dcol.device)
+    _lib.check(lib.tfasr_conv_col2im(_lib.ptr(dcol), _lib.ptr(da), ctypes.byref(g), _st(dcol)), "tfasr_conv_col2im")
+    return da

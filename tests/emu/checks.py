@@ -1,0 +1,321 @@
+"""numpy checks of the plain-SIMT kernels running on the CPU emulator (tests/emu/cuda_emu.h) through their C ABI.
+
+numpy only (no torch) so the same checks can run in a subprocess under AddressSanitizer (`python tests/emu/checks.py --asan`, with
+libasan preloaded): every buffer handed to the emulated kernels is an exact-size heap block, so an out-of-bounds global or shared
+access of a kernel is a hard ASan error — the CPU stand-in for compute-sanitizer memcheck.  Test infrastructure only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+c_i32, c_vp = ctypes.c_int32, ctypes.c_void_p
+
+
+class ConvGeom(ctypes.Structure):
+    _fields_ = [(n, c_i32) for n in ("B", "T", "F", "Cin", "To", "Fo", "kh", "kw", "sh", "sw", "pt", "pl", "Kp")]
+
+
+def load(asan=False):
+    import build_emu
+
+    lib = ctypes.CDLL(build_emu.build(asan=asan))
+    for name in ("tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+                 "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
+        getattr(lib, name).restype = c_i32
+    return lib
+
+
+# ------------------------------------------------------------------------------------------------ bf16 <-> numpy
+def to_bf16(x):
+    """f32 -> uint16 bf16 bit patterns, round to nearest even."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) >> 16
+    return u.astype(np.uint16)
+
+
+def from_bf16(u):
+    return (u.astype(np.uint32) << 16).view(np.float32)
+
+
+def rbf(x):
+    """round an array to bf16 precision (as f32)."""
+    return from_bf16(to_bf16(x))
+
+
+def heap(a):
+    """exact-size, 16-byte aligned heap copy (numpy's allocator aligns to 16/64 bytes); returns (array, pointer)."""
+    a = np.require(np.array(a, copy=True), requirements=["C", "A", "O", "W"])
+    assert a.ctypes.data % 16 == 0
+    return a, c_vp(a.ctypes.data)
+
+
+def close(got, ref, rel, what):
+    scale = max(float(np.max(np.abs(ref))), 1e-6)
+    err = float(np.max(np.abs(np.asarray(got, np.float64) - np.asarray(ref, np.float64))))
+    assert err <= rel * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e} > {rel})"
+
+
+def act_f(z, act):
+    if act == 1:
+        return z / (1.0 + np.exp(-z))
+    if act == 2:
+        return np.maximum(z, 0.0)
+    return z
+
+
+def act_g(z, act):
+    if act == 1:
+        g = 1.0 / (1.0 + np.exp(-z))
+        return g * (1.0 + z * (1.0 - g))
+    if act == 2:
+        return (z > 0).astype(np.float64)
+    return np.ones_like(z)
+
+
+# ------------------------------------------------------------------------------------------------ depthwise conv
+def check_dwconv(lib, B, T, C, K, s, seed=0):
+    rng = np.random.default_rng(seed)
+    To = -(-T // s)
+    x = rbf(rng.standard_normal((B, T, C)))
+    w = (rng.standard_normal((K, C)) * 0.3).astype(np.float32)
+    dy = rbf(rng.standard_normal((B, To, C)))
+    xp = np.concatenate([np.zeros((B, K - 1, C)), x.astype(np.float64)], 1)
+    y_ref = np.zeros((B, To, C))
+    dxp = np.zeros_like(xp)
+    dw_ref = np.zeros((K, C))
+    for j in range(To):
+        for k in range(K):
+            y_ref[:, j] += w[k] * xp[:, j * s + k]
+            dxp[:, j * s + k] += w[k] * dy[:, j]
+            dw_ref[k] += (dy[:, j].astype(np.float64) * xp[:, j * s + k]).sum(0)
+    dx_ref = dxp[:, K - 1:]
+    xb, xptr = heap(to_bf16(x))
+    wb, wptr = heap(w)
+    yb, yptr = heap(np.zeros((B, To, C), np.uint16))
+    assert lib.tfasr_seq_dwconv_fwd(xptr, wptr, yptr, B, T, C, K, s, None) == 0
+    close(from_bf16(yb), y_ref, 5e-3, f"dwconv fwd {(B, T, C, K, s)}")
+    dyb, dyptr = heap(to_bf16(dy))
+    dxb, dxptr = heap(np.zeros((B, T, C), np.uint16))
+    init = rng.standard_normal((K, C)).astype(np.float32)  # the call accumulates
+    dwb, dwptr = heap(init)
+    assert lib.tfasr_seq_dwconv_bwd(dyptr, xptr, wptr, dxptr, dwptr, B, T, C, K, s, None) == 0
+    close(from_bf16(dxb), dx_ref, 5e-3, f"dwconv dx {(B, T, C, K, s)}")
+    close(dwb - init, dw_ref, 2e-4, f"dwconv dw {(B, T, C, K, s)}")
+    dwb2, dwptr2 = heap(np.zeros((K, C), np.float32))
+    assert lib.tfasr_seq_dwconv_bwd(dyptr, xptr, wptr, None, dwptr2, B, T, C, K, s, None) == 0  # dx = NULL: first layer
+    close(dwb2, dw_ref, 2e-4, "dwconv dw (dx skipped)")
+
+
+# ------------------------------------------------------------------------------------------------ masked mean
+def check_masked_mean(lib, B, T, C, lengths, seed=1):
+    rng = np.random.default_rng(seed)
+    y = rbf(rng.standard_normal((B, T, C)))
+    ln = np.asarray(lengths, np.int32)
+    ref = np.zeros((B, C))
+    for b in range(B):
+        n = int(min(max(ln[b], 0), T))
+        ref[b] = y[b, :n].astype(np.float64).sum(0) / max(n, 1)
+    yb, yptr = heap(to_bf16(y))
+    lb, lptr = heap(ln)
+    mb, mptr = heap(np.full((B, C), 7.0, np.float32))  # the call overwrites
+    assert lib.tfasr_seq_masked_mean(yptr, lptr, mptr, B, T, C, None) == 0
+    close(mb, ref, 1e-5, f"masked mean {(B, T, C)}")
+
+
+# ------------------------------------------------------------------------------------------------ squeeze-excite FC pair
+def se_fc_ref(m, W1, b1, W2, b2, act):
+    z1 = m @ W1 + b1
+    h = act_f(z1, act)
+    z2 = h @ W2 + b2
+    return z1, h, 1.0 / (1.0 + np.exp(-z2))
+
+
+def check_se_fc(lib, B, T, C, H, act, lengths, seed=2):
+    rng = np.random.default_rng(seed)
+    m = rng.standard_normal((B, C)).astype(np.float32)
+    W1 = (rng.standard_normal((C, H)) / np.sqrt(C)).astype(np.float32)
+    b1 = (rng.standard_normal(H) * 0.1).astype(np.float32)
+    W2 = (rng.standard_normal((H, C)) / np.sqrt(H)).astype(np.float32)
+    b2 = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    ds = rng.standard_normal((B, C)).astype(np.float32)
+    ln = np.asarray(lengths, np.int32)
+    m64, W164, b164, W264, b264 = (a.astype(np.float64) for a in (m, W1, b1, W2, b2))
+    z1, h, s = se_fc_ref(m64, W164, b164, W264, b264, act)
+    dz2 = ds * s * (1 - s)
+    dh = dz2 @ W264.T
+    dz1 = dh * act_g(z1, act)
+    inv = 1.0 / np.maximum(np.clip(ln, 0, T), 1)
+    dm = (dz1 @ W164.T) * inv[:, None]
+    # the analytic reference itself against central differences of L = sum(ds * s) (float64)
+    eps = 1e-6
+    for (bi, ci) in ((0, 0), (B - 1, C - 1)):
+        mp, mm = m64.copy(), m64.copy()
+        mp[bi, ci] += eps
+        mm[bi, ci] -= eps
+        fd = ((ds * se_fc_ref(mp, W164, b164, W264, b264, act)[2]).sum() - (ds * se_fc_ref(mm, W164, b164, W264, b264, act)[2]).sum()) / (2 * eps)
+        assert abs(fd - (dz1 @ W164.T)[bi, ci]) < 1e-5 * max(1.0, abs(fd)), "se_fc reference derivative"
+    arrs = [heap(a) for a in (m, W1, b1, W2, b2)]
+    z1b, z1p = heap(np.zeros((B, H), np.float32))
+    sb, sp = heap(np.zeros((B, C), np.float32))
+    assert lib.tfasr_se_fc_fwd(arrs[0][1], arrs[1][1], arrs[2][1], arrs[3][1], arrs[4][1], z1p, sp, B, C, H, act, None) == 0
+    close(z1b, z1, 1e-5, "se_fc z1")
+    close(sb, s, 1e-5, "se_fc s")
+    dsb, dsp = heap(ds)
+    lb, lp = heap(ln)
+    outs = {k: heap(np.zeros(shape, np.float32)) for k, shape in
+            dict(dz2=(B, C), dz1=(B, H), dm=(B, C)).items()}
+    init = {k: rng.standard_normal(shape).astype(np.float32) for k, shape in dict(dW1=(C, H), db1=(H,), dW2=(H, C), db2=(C,)).items()}
+    grads = {k: heap(v) for k, v in init.items()}
+    assert lib.tfasr_se_fc_bwd(dsp, sp, z1p, arrs[0][1], arrs[1][1], arrs[3][1], lp, outs["dz2"][1], outs["dz1"][1], outs["dm"][1],
+                               grads["dW1"][1], grads["db1"][1], grads["dW2"][1], grads["db2"][1], B, T, C, H, act, None) == 0
+    close(outs["dm"][0], dm, 2e-5, "se_fc dm")
+    close(grads["dW1"][0] - init["dW1"], m64.T @ dz1, 2e-5, "se_fc dW1")
+    close(grads["db1"][0] - init["db1"], dz1.sum(0), 2e-5, "se_fc db1")
+    close(grads["dW2"][0] - init["dW2"], h.T @ dz2, 2e-5, "se_fc dW2")
+    close(grads["db2"][0] - init["db2"], dz2.sum(0), 2e-5, "se_fc db2")
+
+
+# ------------------------------------------------------------------------------------------------ scale + residual + activation
+def check_se_apply(lib, B, T, C, act, with_res, lengths, seed=3):
+    rng = np.random.default_rng(seed)
+    y = rbf(rng.standard_normal((B, T, C)))
+    res = rbf(rng.standard_normal((B, T, C))) if with_res else None
+    s = rng.uniform(0.05, 0.95, (B, C)).astype(np.float32)
+    dout = rbf(rng.standard_normal((B, T, C)))
+    dm = (rng.standard_normal((B, C)) * 0.1).astype(np.float32)
+    ln = np.asarray(lengths, np.int32)
+    z = y.astype(np.float64) * s[:, None, :] + (res.astype(np.float64) if with_res else 0.0)
+    out_ref = act_f(z, act)
+    dpre = dout * act_g(z, act)
+    yb, yp = heap(to_bf16(y))
+    sb, sp = heap(s)
+    rp = None
+    if with_res:
+        rb, rp = heap(to_bf16(res))
+    ob, op = heap(np.zeros((B, T, C), np.uint16))
+    assert lib.tfasr_se_apply_fwd(yp, sp, rp, op, B, T, C, act, None) == 0
+    close(from_bf16(ob), out_ref, 5e-3, f"se_apply fwd act={act} res={with_res}")
+    db, dp = heap(to_bf16(dout))
+    drb, drp = heap(np.zeros((B, T, C), np.uint16))
+    dsb, dsp = heap(np.full((B, C), 3.0, np.float32))  # overwritten
+    assert lib.tfasr_se_apply_bwd(dp, yp, sp, rp, drp, dsp, B, T, C, act, None) == 0
+    close(from_bf16(drb), dpre, 5e-3, "se_apply dres")
+    close(dsb, (dpre * y).sum(1), 2e-3, "se_apply ds")  # ds sums the fp32 dpre, the reference too: only order differs
+    dmb, dmp = heap(dm)
+    lb, lp = heap(ln)
+    dyb, dyp = heap(np.zeros((B, T, C), np.uint16))
+    assert lib.tfasr_se_dy(drp, sp, dmp, lp, dyp, B, T, C, None) == 0
+    valid = (np.arange(T)[None, :] < ln[:, None])[..., None]
+    dy_ref = from_bf16(drb).astype(np.float64) * s[:, None, :] + np.where(valid, dm[:, None, :], 0.0)
+    close(from_bf16(dyb), dy_ref, 5e-3, "se_dy")
+
+
+# ------------------------------------------------------------------------------------------------ Conv2D lowering
+def conv_geom(B, T, F, Cin, kh, kw, sh, sw, padding):
+    if padding == "same":
+        To, Fo = -(-T // sh), -(-F // sw)
+        pt = max((To - 1) * sh + kh - T, 0) // 2
+        pl = max((Fo - 1) * sw + kw - F, 0) // 2
+    else:  # causal: k - 1 in front, then VALID
+        pt, pl = kh - 1, kw - 1
+        To, Fo = (T + pt - kh) // sh + 1, (F + pl - kw) // sw + 1
+    Kp = (kh * kw * Cin + 7) // 8 * 8
+    return ConvGeom(B, T, F, Cin, To, Fo, kh, kw, sh, sw, pt, pl, Kp)
+
+
+def im2col_ref(x, g):
+    col = np.zeros((g.B, g.To, g.Fo, g.Kp), np.float64)
+    for i in range(g.kh):
+        for j in range(g.kw):
+            for to in range(g.To):
+                t = to * g.sh - g.pt + i
+                if t < 0 or t >= g.T:
+                    continue
+                for fo in range(g.Fo):
+                    f = fo * g.sw - g.pl + j
+                    if 0 <= f < g.F:
+                        col[:, to, fo, (i * g.kw + j) * g.Cin:(i * g.kw + j + 1) * g.Cin] = x[:, t, f, :]
+    return col
+
+
+def check_conv_lowering(lib, B, T, F, Cin, kh, kw, sh, sw, padding, x_f32, seed=4):
+    rng = np.random.default_rng(seed)
+    g = conv_geom(B, T, F, Cin, kh, kw, sh, sw, padding)
+    x = rng.standard_normal((B, T, F, Cin)).astype(np.float32)
+    if not x_f32:
+        x = rbf(x)
+    ref = im2col_ref(x.astype(np.float64), g)
+    xb, xp = heap(x if x_f32 else to_bf16(x))
+    cb, cp = heap(np.full((B * g.To * g.Fo, g.Kp), 0x7FC0, np.uint16))  # NaN-filled: every column must be written
+    assert lib.tfasr_conv_im2col(xp, int(x_f32), cp, ctypes.byref(g), None) == 0
+    got = from_bf16(cb).reshape(ref.shape)
+    assert np.isfinite(got).all(), "im2col left columns unwritten"
+    close(got, rbf(ref.astype(np.float32)), 1e-6, f"im2col {(B, T, F, Cin, kh, kw, sh, sw, padding)}")
+    if Cin % 8 == 0:
+        dcol = rbf(rng.standard_normal(ref.shape))
+        dcb, dcp = heap(to_bf16(dcol))
+        dab, dap = heap(np.zeros((B, T, F, Cin), np.uint16))
+        assert lib.tfasr_conv_col2im(dcp, dap, ctypes.byref(g), None) == 0
+        da = from_bf16(dab).astype(np.float64)
+        # adjoint identity <im2col(x), dcol> == <x, col2im(dcol)> (up to the bf16 rounding of da), plus an explicit scatter reference
+        da_ref = np.zeros((B, T, F, Cin))
+        for i in range(kh):
+            for j in range(kw):
+                for to in range(g.To):
+                    t = to * sh - g.pt + i
+                    if t < 0 or t >= T:
+                        continue
+                    for fo in range(g.Fo):
+                        f = fo * sw - g.pl + j
+                        if 0 <= f < F:
+                            da_ref[:, t, f, :] += dcol[:, to, fo, (i * kw + j) * Cin:(i * kw + j + 1) * Cin]
+        close(da, da_ref, 5e-3, "col2im")
+        lhs, rhs = float((ref * dcol).sum()), float((x.astype(np.float64) * da_ref).sum())
+        assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs)), "adjoint identity of the reference"
+
+
+# ------------------------------------------------------------------------------------------------ error behaviour
+def check_invalid(lib):
+    a, p = heap(np.zeros(64, np.float32))
+    assert lib.tfasr_seq_dwconv_fwd(p, p, p, 1, 4, 12, 3, 1, None) == 1  # C % 8 != 0
+    assert lib.tfasr_seq_dwconv_fwd(None, p, p, 1, 4, 8, 3, 1, None) == 1
+    assert lib.tfasr_seq_dwconv_bwd(p, p, p, p, p, 1, 4, 8, 33, 1, None) == 1  # K > 32
+    assert lib.tfasr_se_apply_fwd(p, p, None, p, 1, 1, 8, 3, None) == 1  # unknown activation
+    assert lib.tfasr_seq_dwconv_fwd(p, p, p, 0, 4, 8, 3, 1, None) == 0  # empty batch is a no-op
+    g = conv_geom(1, 4, 4, 8, 3, 3, 2, 2, "same")
+    g.Kp += 8
+    assert lib.tfasr_conv_im2col(p, 0, p, ctypes.byref(g), None) == 1  # inconsistent padded width
+
+
+CASES = [
+    ("dwconv_k5_s1", lambda lib: check_dwconv(lib, 2, 37, 24, 5, 1)),
+    ("dwconv_k5_s2", lambda lib: check_dwconv(lib, 3, 50, 80, 5, 2)),
+    ("dwconv_k3_s3_odd", lambda lib: check_dwconv(lib, 1, 33, 8, 3, 3)),
+    ("dwconv_k11_wide", lambda lib: check_dwconv(lib, 2, 70, 264, 11, 1)),  # C/2 > 128: two wgrad column blocks; KMAX = 32 path
+    ("dwconv_k1", lambda lib: check_dwconv(lib, 2, 5, 16, 1, 2)),
+    ("masked_mean", lambda lib: check_masked_mean(lib, 5, 45, 24, [45, 0, 17, 60, -3])),
+    ("masked_mean_wide", lambda lib: check_masked_mean(lib, 2, 130, 272, [130, 33])),
+    ("se_fc_swish", lambda lib: check_se_fc(lib, 3, 20, 40, 5, 1, [20, 7, 0])),
+    ("se_fc_relu", lambda lib: check_se_fc(lib, 2, 20, 264, 33, 2, [11, 25])),
+    ("se_apply_swish_res", lambda lib: check_se_apply(lib, 3, 41, 24, 1, True, [41, 5, 0])),
+    ("se_apply_relu", lambda lib: check_se_apply(lib, 2, 19, 520, 2, False, [19, 3])),  # C > 256: two channel blocks in the bwd
+    ("se_apply_linear_res", lambda lib: check_se_apply(lib, 1, 70, 8, 0, True, [64])),
+    ("conv_same_cin1_f32", lambda lib: check_conv_lowering(lib, 2, 13, 21, 1, 11, 5, 2, 2, "same", True)),
+    ("conv_same_cin8", lambda lib: check_conv_lowering(lib, 2, 9, 10, 8, 5, 3, 1, 2, "same", False)),
+    ("conv_causal_cin16", lambda lib: check_conv_lowering(lib, 1, 8, 7, 16, 3, 3, 2, 2, "causal", False)),
+    ("conv_same_cin3_bf16", lambda lib: check_conv_lowering(lib, 1, 6, 6, 3, 3, 3, 1, 1, "same", False)),
+    ("invalid_arguments", check_invalid),
+]
+
+if __name__ == "__main__":
+    lib = load(asan="--asan" in sys.argv)
+    for name, fn in CASES:
+        fn(lib)
+        print("ok", name, flush=True)

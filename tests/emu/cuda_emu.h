@@ -1,0 +1,186 @@
+// CPU emulation of the CUDA SIMT execution model — TEST INFRASTRUCTURE ONLY (never linked into libtfasr_b200.so).
+//
+// Purpose: the plain-SIMT kernels of tensorflowasr_b200/csrc/*_kernels.cuh (no TMA / tcgen05 / cp.async: thread and block indices,
+// shared memory, __syncthreads, warp shuffles, atomics, bf16 conversions) are compiled a second time with g++ against this header
+// and executed block by block with one OS thread per CUDA thread.  That gives the `-m "not gpu"` suite a bit-level check of the
+// kernels' indexing, masking, reductions and launch geometry against torch CPU references — and, under AddressSanitizer with
+// exact-size heap buffers, what compute-sanitizer memcheck would report (out-of-bounds global / shared accesses, misaligned vector
+// accesses through the ld/st helpers below).  It says nothing about performance or about device-only intrinsics' rounding
+// (__expf etc. map to the libm functions here).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <barrier>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define TFASR_EMU 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define __shared__ static  // blocks run one after another, so a function-local static is exactly one block's shared variable
+
+struct uint3 {
+  unsigned x, y, z;
+};
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct float2 {
+  float x, y;
+};
+struct alignas(16) float4 {
+  float x, y, z, w;
+};
+struct alignas(16) uint4 {
+  uint32_t x, y, z, w;
+};
+inline float2 make_float2(float x, float y) { return {x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return {x, y, z, w}; }
+
+// ------------------------------------------------------------------------------------------------ bf16 (round-to-nearest-even)
+struct __nv_bfloat16 {
+  uint16_t v;
+};
+struct alignas(4) __nv_bfloat162 {
+  __nv_bfloat16 x, y;
+};
+inline float __uint_as_float(uint32_t u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline uint32_t __float_as_uint(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+inline float __bfloat162float(__nv_bfloat16 h) { return __uint_as_float((uint32_t)h.v << 16); }
+inline __nv_bfloat16 __float2bfloat16(float f) {
+  uint32_t u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return {(uint16_t)0x7fff};  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return {(uint16_t)(u >> 16)};
+}
+inline __nv_bfloat16 __float2bfloat16_rn(float f) { return __float2bfloat16(f); }
+inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return {__float2bfloat16(a), __float2bfloat16(b)}; }
+inline float __low2float(__nv_bfloat162 v) { return __bfloat162float(v.x); }
+inline float __high2float(__nv_bfloat162 v) { return __bfloat162float(v.y); }
+inline float2 __bfloat1622float2(__nv_bfloat162 v) { return {__bfloat162float(v.x), __bfloat162float(v.y)}; }
+
+// ------------------------------------------------------------------------------------------------ device math on the host
+inline float __expf(float x) { return expf(x); }
+inline float __logf(float x) { return logf(x); }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline float __ldg(const float* p) { return *p; }
+inline int __ldg(const int* p) { return *p; }
+template <class T>
+inline T min(T a, T b) { return a < b ? a : b; }
+template <class T>
+inline T max(T a, T b) { return a > b ? a : b; }
+#define CUDART_INF_F (__builtin_inff())
+
+// ------------------------------------------------------------------------------------------------ execution model
+namespace emu {
+
+struct Warp {
+  int n;  // live threads in this warp
+  std::barrier<> bar;
+  uint64_t buf[32];
+  explicit Warp(int n_) : n(n_), bar(n_) {}
+};
+
+struct BlockCtx {
+  std::barrier<>* bar;
+  std::vector<std::unique_ptr<Warp>>* warps;
+};
+
+inline thread_local uint3 t_threadIdx, t_blockIdx;
+inline thread_local dim3 t_blockDim, t_gridDim;
+inline thread_local Warp* t_warp;
+inline thread_local int t_lane;
+inline thread_local std::barrier<>* t_bar;
+inline uint8_t* g_dyn_smem = nullptr;  // exact-size heap block: ASan sees overruns
+inline std::atomic<long> g_launches{0};
+
+template <class F>
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
+  const int nth = (int)(block.x * block.y * block.z);
+  if (nth <= 0 || nth > 1024) abort();
+  g_launches++;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        std::barrier<> bar(nth);
+        std::vector<std::unique_ptr<Warp>> warps;
+        for (int w = 0; w * 32 < nth; ++w) warps.emplace_back(new Warp(nth - w * 32 < 32 ? nth - w * 32 : 32));
+        uint8_t* smem = smem_bytes ? (uint8_t*)aligned_alloc(16, (smem_bytes + 15) / 16 * 16) : nullptr;
+        // aligned_alloc rounds the request up to 16: the tail (< 16 bytes) is the only slack ASan cannot see
+        g_dyn_smem = smem;
+        std::vector<std::thread> ths;
+        ths.reserve(nth);
+        for (int t = 0; t < nth; ++t)
+          ths.emplace_back([&, t] {
+            t_threadIdx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+            t_blockIdx = {bx, by, bz};
+            t_blockDim = block;
+            t_gridDim = grid;
+            t_warp = warps[t / 32].get();
+            t_lane = t % 32;
+            t_bar = &bar;
+            body();
+          });
+        for (auto& th : ths) th.join();
+        free(smem);
+        g_dyn_smem = nullptr;
+      }
+}
+
+template <class T>
+inline T shfl(T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  Warp& w = *t_warp;
+  memcpy(&w.buf[t_lane], &v, sizeof(T));
+  w.bar.arrive_and_wait();
+  T r = v;
+  if (src_lane >= 0 && src_lane < w.n) memcpy(&r, &w.buf[src_lane], sizeof(T));
+  w.bar.arrive_and_wait();
+  return r;
+}
+
+}  // namespace emu
+
+#define threadIdx (emu::t_threadIdx)
+#define blockIdx (emu::t_blockIdx)
+#define blockDim (emu::t_blockDim)
+#define gridDim (emu::t_gridDim)
+
+inline void __syncthreads() { emu::t_bar->arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) {
+  emu::t_warp->bar.arrive_and_wait();
+}
+// full-mask, convergent shuffles only (what the kernels use)
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu::shfl(v, emu::t_lane ^ lane_mask); }
+template <class T>
+inline T __shfl_down_sync(unsigned, T v, int delta) { return emu::shfl(v, emu::t_lane + delta); }
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl(v, src); }
+
+inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
+inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_relaxed); }
+
+// dynamic shared memory: kernels declare it with TFASR_DYN_SMEM(name)
+#define TFASR_DYN_SMEM(name) uint8_t* name = emu::g_dyn_smem

@@ -1,0 +1,46 @@
+"""The plain-SIMT kernels of csrc/seqconv_kernels.cuh (ContextNet / DeepSpeech2 encoder bodies) executed on the
+CPU emulator (tests/emu) through their C ABI and checked against numpy references; then once more under AddressSanitizer, the CPU
+stand-in for compute-sanitizer memcheck.  The GPU parity tests of the same entry points are in tests/test_gpu_seqconv.py."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    import checks
+
+    return checks.load()
+
+
+def _case_names():
+    import checks
+
+    return [n for n, _ in checks.CASES]
+
+
+@pytest.mark.parametrize("name", _case_names())
+def test_emulated_kernel(emu_lib, name):
+    import checks
+
+    dict(checks.CASES)[name](emu_lib)
+
+
+def test_emulated_kernels_under_address_sanitizer():
+    import build_emu
+
+    rt = build_emu.asan_runtime()
+    if rt is None:
+        pytest.skip("libasan not available")
+    build_emu.build(asan=True)
+    env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "checks.py"), "--asan"], capture_output=True, text=True, env=env, timeout=1500)
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
