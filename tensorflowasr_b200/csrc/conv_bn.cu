@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(1024) bn_stats_kernel(const __nv_bfloat16* __r
   for (int i = tid; i < 2 * C; i += nth) atomicAdd(sums + i, s_acc[i]);
 }
 
-// y = act(x * scale[c] + shift[c]);  act: 0 none, 1 swish.   scale = gamma * rstd, shift = beta - mean * scale.
+// y = act(x * scale[c] + shift[c]);  act: 0 none, 1 swish, 2 relu.   scale = gamma * rstd, shift = beta - mean * scale.
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int64_t R, int C, int act) {
   const int c2n = C >> 1;
@@ -198,6 +198,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
     if (act == 1) {
       a *= sigmoid_f(a);
       b *= sigmoid_f(b);
+    } else if (act == 2) {
+      a = fmaxf(a, 0.f);
+      b = fmaxf(b, 0.f);
     }
     reinterpret_cast<__nv_bfloat162*>(y)[i] = __floats2bfloat162_rn(a, b);
   }
@@ -228,6 +231,9 @@ __global__ void __launch_bounds__(1024) bn_bwd_stats_kernel(const __nv_bfloat16*
       const float g0 = sigmoid_f(z0), g1 = sigmoid_f(z1);
       d0 *= g0 * (1.0f + z0 * (1.0f - g0));
       d1 *= g1 * (1.0f + z1 * (1.0f - g1));
+    } else if (act == 2) {
+      if (fmaf(x0, sc0, sh0) <= 0.f) d0 = 0.f;
+      if (fmaf(x1, sc1, sh1) <= 0.f) d1 = 0.f;
     }
     s0 += d0;
     s1 += d1;
@@ -266,6 +272,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
         const float z = fmaf(xx, scale[c], shift[c]);
         const float g = sigmoid_f(z);
         d *= g * (1.0f + z * (1.0f - g));
+      } else if (act == 2) {
+        if (fmaf(xx, scale[c], shift[c]) <= 0.f) d = 0.f;
       }
       const float xh = (xx - mean[c]) * rstd[c];
       o[h] = scale[c] * (d - sums[c] * inv - xh * sums[C + c] * inv);
@@ -365,6 +373,7 @@ __global__ void __launch_bounds__(256) bn_vec_kernel(const BnVecArgs a) {
         } else if (MODE == 1) {
           float z = fmaf(xf[j], sc[j], sh[j]);
           if (a.act == 1) z *= sigmoid_f(z);
+          else if (a.act == 2) z = fmaxf(z, 0.f);
           o[j] = z;
         } else {
           float d = df[j];
@@ -372,6 +381,8 @@ __global__ void __launch_bounds__(256) bn_vec_kernel(const BnVecArgs a) {
             const float z = fmaf(xf[j], sc[j], sh[j]);
             const float g = sigmoid_f(z);
             d *= g * (1.0f + z * (1.0f - g));
+          } else if (a.act == 2) {
+            if (fmaf(xf[j], sc[j], sh[j]) <= 0.f) d = 0.f;
           }
           const float xh = (xf[j] - mu[j]) * rs[j];
           if (MODE == 2) {

@@ -2,10 +2,10 @@
 tensorflow_asr/models/ctc/{base_ctc,deepspeech2}.py, models/encoders/{deepspeech2,contextnet}.py and
 models/transducer/contextnet.py.
 
-The frontend (log-mel / spectrogram) and the CTC / RNN-T losses run on the hand-written kernels behind the C ABI; the encoder
-bodies of these two model families (large-kernel Conv2D + BiLSTM for DeepSpeech2, separable convs + squeeze-excite for
-ContextNet) currently run on the LIBRARY path (cuDNN / cuBLAS through torch) — they are §8a rows A22 / A23, next in the kernel
-queue after the Conformer path.  Parameter names follow the Keras layer names.
+The frontend (log-mel / spectrogram) and the CTC / RNN-T losses run on the hand-written kernels behind the C ABI.  The encoder bodies
+(§8a rows A22 / A23) have two routes: the LIBRARY route below (cuDNN / cuBLAS through torch; the fp32 parity route and the default
+in this round) and the fused route of fused_seq.py (own depthwise-conv / squeeze-excite / Conv2D-lowering kernels + tcgen05 GEMM +
+BatchNorm kernels + cluster LSTM), taken in bf16 mode when `ops.set_fused_seq(True)` is set.  Parameter names follow the Keras layers.
 """
 from __future__ import annotations
 
@@ -14,7 +14,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from . import ops, schemas
+from . import fused, fused_seq, kernels, ops, schemas
 from .base_model import BaseModel
 from .encoder import _Params, conv_output_length
 from .losses import CtcLoss
@@ -97,8 +97,57 @@ class DeepSpeech2Encoder(_Params):
     def forward(self, inputs, training=False):
         return self.call(inputs, training=training)
 
+    # ---- fused route (fused_seq.py)
+    def _fusable(self, training):
+        return (self.conv_padding in ("same", "causal") and self.conv_activation in ("relu", "swish", "silu", "linear", None)
+                and all(c % 8 == 0 for c in self.conv_filters) and self.fc_activation in ("relu", None)
+                and (training or not torch.is_grad_enabled()))
+
+    def _prepare_packs(self):
+        if getattr(self, "_packs", None) is None:
+            plan, packs = fused.PackPlan(), {}
+            for i in range(len(self.conv_kernels)):
+                pre = f"conv_module.block_{i}"
+                packs[pre] = fused_seq.ConvPack(self[f"{pre}.conv2d.kernel"], self[f"{pre}.conv2d.bias"], plan)
+            for i in range(self.fc_nlayers):
+                pre = f"fc_module.block_{i}.fc"
+                packs[pre] = fused.WeightPack(self[f"{pre}.kernel"], self[f"{pre}.bias"], plan=plan)
+            self._packs, self._pack_plan = packs, plan
+        self._pack_plan.run()
+
+    def _call_fused(self, x, length, training):
+        """conv module: im2col -> tcgen05 GEMM -> BN + activation kernels; BiLSTM: input projections on the GEMM, recurrence on the cluster
+        LSTM kernels when rnn_units <= 384 (else cuDNN, LIBRARY); fc module: GEMM with bias + relu + dropout in the epilogue."""
+        self._prepare_packs()
+        act = kernels.act_code(self.conv_activation)
+        y = x.float().contiguous()  # [B,T,F,1]
+        for i, (k, s) in enumerate(zip(self.conv_kernels, self.conv_strides)):
+            pre = f"conv_module.block_{i}"
+            bn = (self[f"{pre}.bn.gamma"], self[f"{pre}.bn.beta"], self[f"{pre}.bn.moving_mean"], self[f"{pre}.bn.moving_variance"])
+            y = fused_seq.conv2d_bn(y, self._packs[pre], bn, k, s, self.conv_padding, act, training)
+            length = conv_output_length(length, k[0], self.conv_padding, s[0])
+        B, T, Fq, C = y.shape
+        y = y.reshape(B, T, Fq * C)
+        len32 = torch.as_tensor(length, device=y.device).to(torch.int32).contiguous()
+        seed = fused.STATE.seed_tensor(y.device)
+        own_lstm = kernels.lstm_supported(self.rnn_units)
+        for i in range(self.rnn_nlayers):
+            if own_lstm:
+                ws = [tuple(self[f"rnn_module.block_{i}.blstm.{d}_lstm.{n}"] for n in ("kernel", "recurrent_kernel", "bias")) for d in ("forward", "backward")]
+                y = fused_seq.bilstm(y, len32, ws[0], ws[1])
+            else:
+                y = self._bilstm(y, length, i).to(torch.bfloat16)
+            y = ops.dropout(y, self.rnn_dropout, training)
+        y2 = y.reshape(B * T, -1).contiguous()
+        for i in range(self.fc_nlayers):
+            p = self.fc_dropout if training else 0.0
+            y2 = fused_seq.dense_act_drop(y2, self._packs[f"fc_module.block_{i}.fc"], self.fc_activation, p, salt=0xD52 + i, seed=seed)
+        return y2.view(B, T, -1), length
+
     def call(self, inputs, training=False):
         x, length = inputs  # [B,T,F,1]
+        if ops.fused_seq_active(x) and self._fusable(training):
+            return self._call_fused(x, length, training)
         dt = ops.compute_dtype()
         y = x.to(dt).permute(0, 3, 1, 2)
         for i, (k, s) in enumerate(zip(self.conv_kernels, self.conv_strides)):
@@ -264,9 +313,58 @@ class ContextNetEncoder(_Params):
     def forward(self, inputs, training=False):
         return self.call(inputs, training=training)
 
+    # ---- fused route (fused_seq.py)
+    def _fusable(self, nfeat, training):
+        if not (training or not torch.is_grad_enabled()) or nfeat % 8:
+            return False
+        for cfg in self.blocks_cfg:
+            f = int(cfg["filters"] * self.alpha)
+            if f % 8 or f < 8 or cfg["kernel_size"] > 32 or cfg.get("activation", "silu") not in ("silu", "swish", "relu", "linear"):
+                return False
+        return True
+
+    def _prepare_packs(self):
+        if getattr(self, "_packs", None) is None:
+            plan, packs = fused.PackPlan(), {}
+            for n in self.names():
+                if n.endswith(".conv.pointwise_kernel"):
+                    pre = n[: -len(".conv.pointwise_kernel")]
+                    packs[pre] = fused.WeightPack(self[n], self[f"{pre}.conv.bias"], plan=plan)
+            self._packs, self._pack_plan = packs, plan
+        self._pack_plan.run()
+
+    def _conv_module_fused(self, x, length, pre, k, stride, act, training):
+        bn = (self[f"{pre}.bn.gamma"], self[f"{pre}.bn.beta"], self[f"{pre}.bn.moving_mean"], self[f"{pre}.bn.moving_variance"])
+        y = fused_seq.sepconv_bn(x, self[f"{pre}.conv.depthwise_kernel"], self._packs[pre], bn, stride, act, training)
+        return y, conv_output_length(length, k, "causal", stride)
+
+    def _call_fused(self, x, length, training):
+        """Every ConvModule = depthwise kernel -> tcgen05 GEMM (pointwise + bias) -> BN + activation kernels; every block tail = masked-mean,
+        squeeze-excite FC and scale + residual + activation kernels (fused_seq.py)."""
+        self._prepare_packs()
+        B, T, Fq, C = x.shape
+        y = x.reshape(B, T, Fq * C).to(torch.bfloat16).contiguous()
+        length = torch.as_tensor(length, device=x.device)
+        for bi, cfg in enumerate(self.blocks_cfg):
+            k, actn, stride = cfg["kernel_size"], cfg.get("activation", "silu"), cfg.get("strides", 1)
+            act = kernels.act_code(actn)
+            inp, inp_len = y, length
+            for i in range(cfg["nlayers"]):
+                last = i == cfg["nlayers"] - 1
+                y, length = self._conv_module_fused(y, length, f"block_{bi}.conv_module_{i}", k, stride if last else 1, act, training)
+            y, length = self._conv_module_fused(y, length, f"block_{bi}.se.conv_module", k, 1, act, training)
+            res = None
+            if cfg.get("residual", True):
+                res, _ = self._conv_module_fused(inp, inp_len, f"block_{bi}.residual", k, stride, 0, training)
+            y = fused_seq.se_block(y, res, length.to(torch.int32).contiguous(), self[f"block_{bi}.se.fc1.kernel"], self[f"block_{bi}.se.fc1.bias"],
+                                   self[f"block_{bi}.se.fc2.kernel"], self[f"block_{bi}.se.fc2.bias"], act)
+        return y, length
+
     def call(self, inputs, training=False):
         x, length = inputs  # [B,T,F,1]
         B, T, Fq, C = x.shape
+        if ops.fused_seq_active(x) and self._fusable(Fq * C, training):
+            return self._call_fused(x, length, training)
         y = x.reshape(B, T, Fq * C)  # Reshape (merge_two_last_dims)
         for bi, cfg in enumerate(self.blocks_cfg):
             k, act, stride = cfg["kernel_size"], cfg.get("activation", "silu"), cfg.get("strides", 1)

@@ -50,6 +50,22 @@ def fused_active(x) -> bool:
     return _FUSED and _PRECISION == "bf16" and x.is_cuda
 
 
+import os as _os
+
+_FUSED_SEQ = _os.environ.get("TFASR_FUSED_SEQCONV", "0") == "1"
+
+
+def set_fused_seq(flag: bool):
+    """Route the ContextNet / DeepSpeech2 encoder bodies through fused_seq.py's kernels.  Off by default until the
+    GPU parity tests of that path (tests/test_gpu_zz_seqconv.py, written without GPU time) have run green on a B200."""
+    global _FUSED_SEQ
+    _FUSED_SEQ = bool(flag)
+
+
+def fused_seq_active(x) -> bool:
+    return _FUSED_SEQ and fused_active(x)
+
+
 def compute_dtype():
     return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
 
