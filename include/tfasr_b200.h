@@ -321,6 +321,30 @@ typedef struct tfasr_conv_geom {
 int tfasr_conv_im2col(const void* x, int32_t x_f32, void* col, const tfasr_conv_geom* geom, tfasr_stream_t stream);
 int tfasr_conv_col2im(const void* dcol, void* da, const tfasr_conv_geom* geom, tfasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Persistent greedy transducer decode: the `tf.while_loop` of Transducer.recognize_batch / recognize_single
+ * (models/transducer/base_transducer.py:496-575, :577-712; one call_next :437-464 per iteration) as ONE launch, one CTA per utterance.
+ * All buffers fp32 / int32 device memory.  Weights in their Keras layouts: emb [V,E], w_ih [E,4R], w_hh [R,4R], b [4R] (gate order
+ * i,f,c,o), ln_g / ln_b [R] or both NULL, wp [R,J], bp [J], wv [J,V], bv [V]; e_proj [B,T,J] = encoder output . joint.enc kernel + bias.
+ * State (in/out): prev_tok [B], states [B,2,R] (h, c), frame_idx [B], tok_idx [B], tokens [B,max_tokens].
+ *   mode 0  recognize_batch trajectory of each utterance until ITS frame index reaches nframes - 1 (-> iters[b] = iterations run, or -1
+ *           when max_iters was hit first; cap_iter[b] = first iteration whose loop test saw tok_idx >= max_tokens - 1, or -1)
+ *   mode 1  the same trajectory for exactly iters[b] further iterations (the loop stops when ALL utterances are done: the host takes
+ *           L = max_b iters[b] after mode 0 and runs mode 1 with L - iters[b])
+ *   mode 2  recognize_single: a frame is left on blank or after per_frame_cap symbols; tok_idx = index of the last written token (-1)
+ * `threads`: CTA size, a multiple of 32 in [32, 1024].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tfasr_greedy_params {
+  const float* e_proj;
+  const int32_t* nframes;
+  const float *emb, *w_ih, *w_hh, *b, *ln_g, *ln_b, *wp, *bp, *wv, *bv;
+  int32_t* prev_tok;
+  float* states;
+  int32_t *frame_idx, *tok_idx, *tokens, *iters, *cap_iter;
+  int32_t T, E, R, J, V, max_tokens, blank, mode, max_iters, per_frame_cap;
+} tfasr_greedy_params;
+int tfasr_greedy_decode_f32(const tfasr_greedy_params* params, int32_t B, int32_t threads, tfasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

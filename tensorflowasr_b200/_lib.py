@@ -32,6 +32,14 @@ class ConvGeom(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in ("B", "T", "F", "Cin", "To", "Fo", "kh", "kw", "sh", "sw", "pt", "pl", "Kp")]
 
 
+class GreedyParams(ctypes.Structure):
+    """Mirror of `tfasr_greedy_params`."""
+
+    _fields_ = ([(n, c_void_p) for n in ("e_proj", "nframes", "emb", "w_ih", "w_hh", "b", "ln_g", "ln_b", "wp", "bp", "wv", "bv", "prev_tok", "states",
+                                         "frame_idx", "tok_idx", "tokens", "iters", "cap_iter")]
+                + [(n, c_int32) for n in ("T", "E", "R", "J", "V", "max_tokens", "blank", "mode", "max_iters", "per_frame_cap")])
+
+
 class GemmEpilogue(ctypes.Structure):
     """Mirror of `tfasr_gemm_epilogue`."""
 
@@ -111,6 +119,7 @@ SIGNATURES = {
     "tfasr_se_dy": (c_int32, [c_void_p] * 5 + [c_int32] * 3 + [c_void_p]),
     "tfasr_conv_im2col": (c_int32, [c_void_p, c_int32, c_void_p, POINTER(ConvGeom), c_void_p]),
     "tfasr_conv_col2im": (c_int32, [c_void_p, c_void_p, POINTER(ConvGeom), c_void_p]),
+    "tfasr_greedy_decode_f32": (c_int32, [POINTER(GreedyParams), c_int32, c_int32, c_void_p]),
     "tfasr_ctc_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "tfasr_ctc_loss_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -410,3 +410,28 @@ def conv_col2im(dcol, g):
     da = torch.empty((g.B, g.T, g.F, g.Cin), dtype=torch.bfloat16, device=dcol.device)
     _lib.check(lib.tfasr_conv_col2im(_lib.ptr(dcol), _lib.ptr(da), ctypes.byref(g), _st(dcol)), "tfasr_conv_col2im")
     return da
+
+
+# ------------------------------------------------------------------------------------------------ persistent greedy decode
+def greedy_decode(weights, e_proj, nframes, prev_tok, states, frame_idx, tok_idx, tokens, iters, cap_iter, blank, mode, max_iters=0, per_frame_cap=1,
+                  threads=512):
+    """One launch of the persistent greedy transducer decode kernel (include/tfasr_b200.h: tfasr_greedy_decode_f32).  `weights` = dict of fp32
+    contiguous tensors emb [V,E], w_ih [E,4R], w_hh [R,4R], b [4R], ln_g / ln_b [R] or None, wp [R,J], bp [J], wv [J,V], bv [V]; e_proj [B,T,J] f32;
+    the remaining tensors are the in/out decoder state (int32 except states [B,2,R] f32)."""
+    lib = _lib.load()
+    B, T, J = e_proj.shape
+    P = _lib.GreedyParams()
+    for n in ("emb", "w_ih", "w_hh", "b", "ln_g", "ln_b", "wp", "bp", "wv", "bv"):
+        t = weights.get(n)
+        assert t is None or (t.dtype == torch.float32), n
+        setattr(P, n, _lib.ptr(t))
+    for n, t in (("e_proj", e_proj), ("nframes", nframes), ("prev_tok", prev_tok), ("states", states), ("frame_idx", frame_idx), ("tok_idx", tok_idx),
+                 ("tokens", tokens), ("iters", iters), ("cap_iter", cap_iter)):
+        assert t.dtype == (torch.float32 if n in ("e_proj", "states") else torch.int32), n
+        setattr(P, n, _lib.ptr(t))
+    V, E = weights["emb"].shape
+    R = weights["w_hh"].shape[0]
+    assert weights["w_ih"].shape == (E, 4 * R) and weights["wp"].shape == (R, J) and weights["wv"].shape == (J, V) and states.shape == (B, 2, R)
+    P.T, P.E, P.R, P.J, P.V, P.max_tokens, P.blank = T, E, R, J, V, tokens.shape[1], int(blank)
+    P.mode, P.max_iters, P.per_frame_cap = int(mode), int(max_iters), int(per_frame_cap)
+    _lib.check(lib.tfasr_greedy_decode_f32(ctypes.byref(P), B, int(threads), _st(e_proj)), "tfasr_greedy_decode_f32")

@@ -66,6 +66,20 @@ def fused_seq_active(x) -> bool:
     return _FUSED_SEQ and fused_active(x)
 
 
+_PERSISTENT_DECODE = _os.environ.get("TFASR_PERSISTENT_DECODE", "0") == "1"
+
+
+def set_persistent_decode(flag: bool):
+    """Greedy decoding through the one-launch persistent kernel (csrc/decode.cu) instead of the host-driven loop.  Off by
+    default until tests/test_gpu_zz_decode.py (written without GPU time; emulator-verified) has run green on a B200."""
+    global _PERSISTENT_DECODE
+    _PERSISTENT_DECODE = bool(flag)
+
+
+def persistent_decode_active() -> bool:
+    return _PERSISTENT_DECODE
+
+
 def compute_dtype():
     return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
 

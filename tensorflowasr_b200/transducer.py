@@ -195,12 +195,79 @@ class Transducer(BaseModel):
         states = (inputs.previous_decoder_states if inputs.previous_decoder_states is not None else self.get_initial_decoder_states(B)).to(dev)
         return enc, enc_len, next_enc_states, prev_tok, states
 
+    # ------------------------------------------------------------------ persistent decode kernel (csrc/decode.cu)
+    def _persistent_ok(self):
+        pn = self.predict_net
+        return ops.persistent_decode_active() and pn.num_rnns == 1 and pn.projection_units == 0
+
+    def _decode_weights(self):
+        pn, jn = self.predict_net, self.joint_net
+
+        def f(t):
+            return t.detach().float().contiguous()
+
+        return dict(emb=f(pn["embedding.embeddings"]), w_ih=f(pn["lstm_0.kernel"]), w_hh=f(pn["lstm_0.recurrent_kernel"]), b=f(pn["lstm_0.bias"]),
+                    ln_g=f(pn["ln_0.gamma"]) if pn.use_ln else None, ln_b=f(pn["ln_0.beta"]) if pn.use_ln else None,
+                    wp=f(jn["pred.kernel"]), bp=f(jn["pred.bias"]), wv=f(jn["vocab.kernel"]), bv=f(jn["vocab.bias"]))
+
+    def _encoder_projection(self, enc):
+        """joint.enc Dense for all frames at once (the only encoder-side term of call_next): [B,T,J] fp32."""
+        return ops.linear(enc, self.joint_net["enc.kernel"], self.joint_net["enc.bias"]).float().contiguous()
+
+    def _recognize_batch_persistent(self, enc, enc_len, next_enc_states, prev_tok, states):
+        """recognize_batch as two launches of the persistent kernel.  The reference loop runs until EVERY utterance has reached its last
+        frame, and utterances that got there earlier keep evolving meanwhile: pass 1 (mode 0) runs each utterance to its own frame
+        condition and reports its iteration count, the loop length is L = max_b iters[b], pass 2 (mode 1) runs the remaining
+        L - iters[b] iterations.  Returns None when the token-budget stop of the reference loop could have fired first (all utterances
+        at 2T' tokens): the caller then takes the host loop, which implements that case verbatim."""
+        B, T, _ = enc.shape
+        dev = enc.device
+        max_tokens = 2 * T + 1
+        w = self._decode_weights()
+        e_proj = self._encoder_projection(enc)
+        nframes = enc_len.to(torch.int32).contiguous()
+        pt = prev_tok[:, 0].to(torch.int32).contiguous().clone()
+        st = states[:, 0].float().contiguous().clone()
+        fi = torch.zeros(B, dtype=torch.int32, device=dev)
+        ti = torch.ones(B, dtype=torch.int32, device=dev)
+        toks = torch.full((B, max_tokens), self.blank, dtype=torch.int32, device=dev)
+        iters = torch.zeros(B, dtype=torch.int32, device=dev)
+        cap = torch.zeros(B, dtype=torch.int32, device=dev)
+        kernels.greedy_decode(w, e_proj, nframes, pt, st, fi, ti, toks, iters, cap, self.blank, mode=0, max_iters=4 * max_tokens + 8)
+        host = torch.stack([iters, cap]).cpu()  # the one host round trip of the decode
+        i_b, j_b = host[0], host[1]
+        if bool((i_b < 0).any()):
+            return None
+        L = int(i_b.max())
+        if bool((j_b >= 0).all()) and int(j_b.max()) < L:
+            return None
+        budget = (L - iters).contiguous()
+        kernels.greedy_decode(w, e_proj, nframes, pt, st, fi, ti, toks, budget, cap, self.blank, mode=1)
+        if bool((ti >= max_tokens - 1).all()):
+            return None
+        return schemas.PredictOutput(tokens=toks, next_tokens=pt[:, None], next_encoder_states=next_enc_states, next_decoder_states=st[:, None])
+
+    def _recognize_single_persistent(self, enc, nframes, next_enc_states, prev_tok, states, max_tokens_per_frame):
+        dev = enc.device
+        n = max(nframes, 0) * max_tokens_per_frame
+        w = self._decode_weights()
+        e_proj = self._encoder_projection(enc)
+        pt = prev_tok[:, 0].to(torch.int32).contiguous().clone()
+        st = states[:, 0].float().contiguous().clone()
+        toks = torch.full((1, max(n, 1)), self.blank, dtype=torch.int32, device=dev)
+        z = torch.zeros(1, dtype=torch.int32, device=dev)
+        kernels.greedy_decode(w, e_proj, torch.full((1,), nframes, dtype=torch.int32, device=dev), pt, st, z.clone(), torch.full_like(z, -1), toks, z.clone(),
+                              z.clone(), self.blank, mode=2, per_frame_cap=max_tokens_per_frame)
+        return schemas.PredictOutput(tokens=toks[:, :n], next_tokens=pt[:, None], next_encoder_states=next_enc_states, next_decoder_states=st[:, None])
+
     @torch.no_grad()
     def recognize_single(self, inputs: schemas.PredictInput, max_tokens_per_frame: int = 3, **kwargs):
         """base_transducer.py:577-712 (batch 1): walk the frames; a frame is left on blank or after `max_tokens_per_frame`
         non-blank symbols; tokens [1, nframes * max_tokens_per_frame], blank-padded."""
         enc, enc_len, next_enc_states, prev_tok, states = self._encode_for_decode(inputs)
         nframes = int(enc_len[0])
+        if self._persistent_ok():
+            return self._recognize_single_persistent(enc, nframes, next_enc_states, prev_tok, states, max_tokens_per_frame)
         toks = torch.full((max(nframes, 0) * max_tokens_per_frame,), self.blank, dtype=torch.int32, device=enc.device)
         frame, token_index, per_frame = 0, -1, 0
         while frame < nframes:
@@ -225,6 +292,10 @@ class Transducer(BaseModel):
         frame_index > nframes; emitted symbols are stored from column 2 on (tokens_indices starts at 1), blanks overwrite column 0;
         tokens [B, 2 * T' + 1]."""
         enc, enc_len, next_enc_states, prev_tok, states = self._encode_for_decode(inputs)
+        if self._persistent_ok():
+            out = self._recognize_batch_persistent(enc, enc_len, next_enc_states, prev_tok, states)
+            if out is not None:
+                return out
         B, T, _ = enc.shape
         dev = enc.device
         nframes = enc_len[:, None]  # [B,1]

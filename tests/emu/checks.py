@@ -22,11 +22,17 @@ class ConvGeom(ctypes.Structure):
     _fields_ = [(n, c_i32) for n in ("B", "T", "F", "Cin", "To", "Fo", "kh", "kw", "sh", "sw", "pt", "pl", "Kp")]
 
 
+class GreedyParams(ctypes.Structure):
+    _fields_ = ([(n, c_vp) for n in ("e_proj", "nframes", "emb", "w_ih", "w_hh", "b", "ln_g", "ln_b", "wp", "bp", "wv", "bv", "prev_tok", "states",
+                                     "frame_idx", "tok_idx", "tokens", "iters", "cap_iter")]
+                + [(n, c_i32) for n in ("T", "E", "R", "J", "V", "max_tokens", "blank", "mode", "max_iters", "per_frame_cap")])
+
+
 def load(asan=False):
     import build_emu
 
     lib = ctypes.CDLL(build_emu.build(asan=asan))
-    for name in ("tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+    for name in ("tfasr_greedy_decode_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
     return lib
@@ -52,6 +58,7 @@ def rbf(x):
 def heap(a):
     """exact-size, 16-byte aligned heap copy (numpy's allocator aligns to 16/64 bytes); returns (array, pointer)."""
     a = np.require(np.array(a, copy=True), requirements=["C", "A", "O", "W"])
+    assert a.dtype != np.float64, "kernels take float32 / bf16 / int32 buffers"
     assert a.ctypes.data % 16 == 0
     return a, c_vp(a.ctypes.data)
 
@@ -281,6 +288,163 @@ def check_conv_lowering(lib, B, T, F, Cin, kh, kw, sh, sw, padding, x_f32, seed=
         assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs)), "adjoint identity of the reference"
 
 
+# ------------------------------------------------------------------------------------------------ persistent greedy decode
+def _sig(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+class GreedyModel:
+    """float64 restatement of Transducer.call_next (base_transducer.py:437-464) on random weights."""
+
+    def __init__(self, rng, B, T, E, R, J, V, ln=True, blank_bias=1.0):
+        f = lambda *s: rng.standard_normal(s).astype(np.float32)  # noqa: E731
+        self.B, self.T, self.E, self.R, self.J, self.V = B, T, E, R, J, V
+        self.e_proj = f(B, T, J)
+        self.emb = f(V, E) * 0.5
+        self.w_ih, self.w_hh = f(E, 4 * R) / np.sqrt(E), f(R, 4 * R) / np.sqrt(R)
+        self.b = f(4 * R) * 0.1
+        self.ln_g, self.ln_b = (1 + 0.1 * f(R), 0.1 * f(R)) if ln else (None, None)
+        self.wp, self.bp = f(R, J) / np.sqrt(R), f(J) * 0.1
+        self.wv, self.bv = f(J, V) * (2.0 / np.sqrt(J)), f(V) * 0.1
+        self.bv[0] += blank_bias
+        for k, v in list(vars(self).items()):  # numpy scalars (np.sqrt) promote float32 arrays to float64: the kernel reads float32
+            if isinstance(v, np.ndarray):
+                setattr(self, k, np.ascontiguousarray(v, dtype=np.float32))
+        self.min_margin = np.inf
+
+    def step(self, b, t, tok, h, c):
+        R = self.R
+        z = self.emb[tok].astype(np.float64) @ self.w_ih + h @ self.w_hh.astype(np.float64) + self.b
+        c2 = _sig(z[R:2 * R]) * c + _sig(z[:R]) * np.tanh(z[2 * R:3 * R])
+        h2 = _sig(z[3 * R:]) * np.tanh(c2)
+        y = h2
+        if self.ln_g is not None:
+            y = (h2 - h2.mean()) / np.sqrt(h2.var() + 1e-3) * self.ln_g + self.ln_b
+        logits = np.tanh(self.e_proj[b, t] + y @ self.wp + self.bp) @ self.wv + self.bv
+        srt = np.sort(logits)
+        self.min_margin = min(self.min_margin, srt[-1] - srt[-2])
+        return int(np.argmax(logits)), h2, c2
+
+
+def greedy_batch_ref(m, nframes, blank=0):
+    """Transducer.recognize_batch, base_transducer.py:496-575, verbatim (global loop over the batch)."""
+    B, T = m.B, m.T
+    max_tokens = 2 * T + 1
+    frame, tok_idx = np.zeros(B, np.int64), np.ones(B, np.int64)
+    tokens = np.full((B, max_tokens), blank, np.int32)
+    prev = np.full(B, blank, np.int64)
+    h, c = np.zeros((B, m.R)), np.zeros((B, m.R))
+    iters = 0
+    while not ((frame >= nframes - 1).all() or (tok_idx >= max_tokens - 1).all()):
+        if iters > 50 * max_tokens:
+            raise RuntimeError("reference greedy loop does not terminate on this random model: pick another seed")
+        for b in range(B):
+            t = max(min(frame[b], nframes[b] - 1), 0)
+            cur, h2, c2 = m.step(b, t, prev[b], h[b], c[b])
+            eq_blank = cur == blank or tok_idx[b] >= max_tokens or frame[b] > nframes[b]
+            if eq_blank:
+                tokens[b, 0] = blank
+                frame[b] += 1
+            else:
+                tok_idx[b] = min(tok_idx[b] + 1, max_tokens - 1)
+                tokens[b, tok_idx[b]] = cur
+                prev[b], h[b], c[b] = cur, h2, c2
+        iters += 1
+    return tokens, prev, h, c, frame, tok_idx, iters
+
+
+def greedy_single_ref(m, nframes, cap, blank=0):
+    """Transducer.recognize_single, base_transducer.py:577-712 (batch 1)."""
+    toks = np.full(max(nframes, 0) * cap, blank, np.int32)
+    frame, ti, per = 0, -1, 0
+    prev, h, c = blank, np.zeros(m.R), np.zeros(m.R)
+    while frame < nframes:
+        cur, h2, c2 = m.step(0, frame, prev, h, c)
+        if ti > 50 * (len(toks) + 1):
+            raise RuntimeError("reference greedy loop does not terminate on this random model: pick another seed")
+        if cur == blank:
+            frame, per = frame + 1, 0
+        else:
+            per, ti = per + 1, ti + 1
+            toks[ti] = cur
+            prev, h, c = cur, h2, c2
+            if per >= cap:
+                frame, per = frame + 1, 0
+    return toks, prev, h, c
+
+
+def _greedy_params(m, bufs, max_tokens, mode, max_iters=0, cap=1, blank=0):
+    P = GreedyParams()
+    for name in ("e_proj", "emb", "w_ih", "w_hh", "b", "wp", "bp", "wv", "bv"):
+        setattr(P, name, bufs[name][1])
+    P.ln_g = bufs["ln_g"][1] if m.ln_g is not None else None
+    P.ln_b = bufs["ln_b"][1] if m.ln_g is not None else None
+    for name in ("nframes", "prev_tok", "states", "frame_idx", "tok_idx", "tokens", "iters", "cap_iter"):
+        setattr(P, name, bufs[name][1])
+    P.T, P.E, P.R, P.J, P.V, P.max_tokens, P.blank = m.T, m.E, m.R, m.J, m.V, max_tokens, blank
+    P.mode, P.max_iters, P.per_frame_cap = mode, max_iters, cap
+    return P
+
+
+def _model_bufs(m):
+    bufs = {n: heap(getattr(m, n)) for n in ("e_proj", "emb", "w_ih", "w_hh", "b", "wp", "bp", "wv", "bv")}
+    if m.ln_g is not None:
+        bufs["ln_g"], bufs["ln_b"] = heap(m.ln_g.astype(np.float32)), heap(m.ln_b.astype(np.float32))
+    return bufs
+
+
+def check_greedy_batch(lib, B, T, E, R, J, V, nframes, threads, ln=True, seed=5, blank_bias=1.0):
+    rng = np.random.default_rng(seed)
+    m = GreedyModel(rng, B, T, E, R, J, V, ln=ln, blank_bias=blank_bias)
+    nframes = np.asarray(nframes, np.int64)
+    tokens, prev, h, c, frame, tok_idx, L = greedy_batch_ref(m, nframes)
+    assert m.min_margin > 1e-4, f"pick another seed: arg-max margin {m.min_margin:.2e} is within fp32 noise"
+    assert (tokens[:, 2:] != 0).sum() >= 2, "degenerate case: the reference emitted (almost) nothing"
+    max_tokens = 2 * T + 1
+    bufs = _model_bufs(m)
+    bufs["nframes"] = heap(nframes.astype(np.int32))
+    bufs["prev_tok"] = heap(np.zeros(B, np.int32))
+    bufs["states"] = heap(np.zeros((B, 2, R), np.float32))
+    bufs["frame_idx"] = heap(np.zeros(B, np.int32))
+    bufs["tok_idx"] = heap(np.ones(B, np.int32))
+    bufs["tokens"] = heap(np.zeros((B, max_tokens), np.int32))
+    bufs["iters"] = heap(np.zeros(B, np.int32))
+    bufs["cap_iter"] = heap(np.zeros(B, np.int32))
+    P = _greedy_params(m, bufs, max_tokens, mode=0, max_iters=4 * max_tokens)
+    assert lib.tfasr_greedy_decode_f32(ctypes.byref(P), B, threads, None) == 0
+    it0 = bufs["iters"][0].copy()
+    assert (it0 >= 0).all() and int(it0.max()) == L, (it0, L)
+    bufs["iters"][0][:] = L - it0  # the loop runs until EVERY utterance is done: the others keep evolving
+    P.mode = 1
+    assert lib.tfasr_greedy_decode_f32(ctypes.byref(P), B, threads, None) == 0
+    assert (bufs["tokens"][0] == tokens).all(), (bufs["tokens"][0], tokens)
+    assert (bufs["prev_tok"][0] == prev).all() and (bufs["frame_idx"][0] == frame).all() and (bufs["tok_idx"][0] == tok_idx).all()
+    close(bufs["states"][0][:, 0], h, 1e-4, "greedy h")
+    close(bufs["states"][0][:, 1], c, 1e-4, "greedy c")
+
+
+def check_greedy_single(lib, T, E, R, J, V, nframes, cap, threads, seed=6, blank_bias=0.5):
+    rng = np.random.default_rng(seed)
+    m = GreedyModel(rng, 1, T, E, R, J, V, ln=True, blank_bias=blank_bias)
+    toks, prev, h, c = greedy_single_ref(m, nframes, cap)
+    assert m.min_margin > 1e-4 and (toks != 0).sum() >= 2
+    max_tokens = max(nframes * cap, 1)
+    bufs = _model_bufs(m)
+    bufs["nframes"] = heap(np.array([nframes], np.int32))
+    bufs["prev_tok"] = heap(np.zeros(1, np.int32))
+    bufs["states"] = heap(np.zeros((1, 2, R), np.float32))
+    bufs["frame_idx"] = heap(np.zeros(1, np.int32))
+    bufs["tok_idx"] = heap(np.full(1, -1, np.int32))
+    bufs["tokens"] = heap(np.zeros((1, max_tokens), np.int32))
+    bufs["iters"] = heap(np.zeros(1, np.int32))
+    bufs["cap_iter"] = heap(np.zeros(1, np.int32))
+    P = _greedy_params(m, bufs, max_tokens, mode=2, cap=cap)
+    assert lib.tfasr_greedy_decode_f32(ctypes.byref(P), 1, threads, None) == 0
+    assert (bufs["tokens"][0][0, :len(toks)] == toks).all(), (bufs["tokens"][0], toks)
+    assert int(bufs["prev_tok"][0][0]) == prev and int(bufs["frame_idx"][0][0]) == nframes
+    close(bufs["states"][0][0, 0], h, 1e-4, "greedy single h")
+
+
 # ------------------------------------------------------------------------------------------------ error behaviour
 def check_invalid(lib):
     a, p = heap(np.zeros(64, np.float32))
@@ -311,6 +475,11 @@ CASES = [
     ("conv_same_cin8", lambda lib: check_conv_lowering(lib, 2, 9, 10, 8, 5, 3, 1, 2, "same", False)),
     ("conv_causal_cin16", lambda lib: check_conv_lowering(lib, 1, 8, 7, 16, 3, 3, 2, 2, "causal", False)),
     ("conv_same_cin3_bf16", lambda lib: check_conv_lowering(lib, 1, 6, 6, 3, 3, 3, 1, 1, "same", False)),
+    # (seeds / blank biases picked so that the random model's reference loop terminates through the frame condition with some emissions)
+    ("greedy_batch_vec", lambda lib: check_greedy_batch(lib, 3, 7, 16, 24, 20, 12, [7, 4, 1], 128, seed=9, blank_bias=2.5)),  # float4 path, split-K up to 8
+    ("greedy_batch_scalar", lambda lib: check_greedy_batch(lib, 2, 6, 10, 12, 9, 29, [6, 5], 64, seed=1, blank_bias=3.0)),  # odd J, V: one column per thread
+    ("greedy_batch_small_cta", lambda lib: check_greedy_batch(lib, 2, 5, 8, 16, 8, 16, [5, 3], 32, seed=16, blank_bias=3.0)),  # little or no split
+    ("greedy_single", lambda lib: check_greedy_single(lib, 6, 16, 24, 20, 12, 6, 3, 96, seed=8, blank_bias=0.5)),
     ("invalid_arguments", check_invalid),
 ]
 

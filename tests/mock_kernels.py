@@ -234,6 +234,28 @@ def conv_col2im(dcol, g):
     return da
 
 
+def greedy_decode(weights, e_proj, nframes, prev_tok, states, frame_idx, tok_idx, tokens, iters, cap_iter, blank, mode, max_iters=0, per_frame_cap=1,
+                  threads=128):
+    """kernels.greedy_decode on the CPU emulator (the real kernel source, host pointers)."""
+    import checks
+
+    B, T, J = e_proj.shape
+    P = checks.GreedyParams()
+    for n in ("emb", "w_ih", "w_hh", "b", "ln_g", "ln_b", "wp", "bp", "wv", "bv"):
+        t = weights.get(n)
+        assert t is None or t.dtype == torch.float32
+        setattr(P, n, _p(t))
+    for n, t in (("e_proj", e_proj), ("nframes", nframes), ("prev_tok", prev_tok), ("states", states), ("frame_idx", frame_idx), ("tok_idx", tok_idx),
+                 ("tokens", tokens), ("iters", iters), ("cap_iter", cap_iter)):
+        assert t.dtype == (torch.float32 if n in ("e_proj", "states") else torch.int32), n
+        setattr(P, n, _p(t))
+    V, E = weights["emb"].shape
+    R = weights["w_hh"].shape[0]
+    P.T, P.E, P.R, P.J, P.V, P.max_tokens, P.blank = T, E, R, J, V, tokens.shape[1], int(blank)
+    P.mode, P.max_iters, P.per_frame_cap = int(mode), int(max_iters), int(per_frame_cap)
+    _ok(_lib().tfasr_greedy_decode_f32(ctypes.byref(P), B, min(int(threads), 128), None), "greedy_decode")
+
+
 # ------------------------------------------------------------------------------------------------ "ideal" mode: fp32 storage, no bf16 rounding
 # Precision-agnostic torch implementations of the seqconv contracts (include/tfasr_b200.h) so that the fused route can be compared with
 # the fp32 library route at ~1e-4: any wiring mistake in fused_seq.py is an O(1) difference there.  (That the real kernels honour the
@@ -330,7 +352,7 @@ class _TorchProxy:
 
 PATCHED = ["gemm", "bn_stats", "bn_finalize", "bn_apply", "bn_bwd_stats", "bn_bwd_finalize", "bn_bwd_apply", "scale_mask_colsum", "colsum",
            "lstm_supported", "seq_dwconv_fwd", "seq_dwconv_bwd", "seq_masked_mean", "se_fc_fwd", "se_fc_bwd", "se_apply_fwd", "se_apply_bwd", "se_dy",
-           "conv_im2col", "conv_col2im"]
+           "conv_im2col", "conv_col2im", "greedy_decode"]
 
 
 def install(monkeypatch, ideal=False):
