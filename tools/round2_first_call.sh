@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+# First gpurun call of the next round: everything that was written without GPU time in round 1, in one box.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Results land in gpurun_out/ (merged back): r2_unverified_tests.log, seqconv_bench.json, decode_bench.json, ncu launch lists.
+set -u
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+# 1. the GPU parity tests marked xfail(strict=False) in round 1, as real tests (--runxfail), each file in its own process so that a
+#    sticky CUDA error in one cannot poison the other
+for f in tests/test_gpu_zz_seqconv.py tests/test_gpu_zz_decode.py; do
+  timeout 600 python -m pytest "$f" -m gpu --runxfail -q -x --tb=short 2>&1 | tail -40 >> gpurun_out/r2_unverified_tests.log
+  echo "=== $f exit ${PIPESTATUS[0]}" >> gpurun_out/r2_unverified_tests.log
+done
+# 2. microbenchmarks of the new routes (each guarded: a failure keeps the rest)
+timeout 600 python tools/seqconv_bench.py --out gpurun_out/seqconv_bench.json > gpurun_out/seqconv_bench.log 2>&1
+timeout 300 python tools/decode_bench.py --out gpurun_out/decode_bench.json > gpurun_out/decode_bench.log 2>&1
+# 3. ncu launch lists (durations only; per-launch times are cold-cache and serialised)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'seq_|se_|conv_im2col|conv_col2im' -c 200 --csv \
+  --log-file gpurun_out/seqconv_launches_r02.csv python tools/seqconv_bench.py --batch 16 --seconds 10 > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:greedy_decode -c 1 -o gpurun_out/greedy_decode_r02 \
+  python tools/decode_bench.py --batch 32 --frames 60 > /dev/null 2>&1
+tail -5 gpurun_out/r2_unverified_tests.log
