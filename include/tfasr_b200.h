@@ -102,6 +102,17 @@ int tfasr_rnnt_loss_bwd_f32(const float* logits, const int32_t* labels, const in
                             const float* grad_scale, float* grads, const void* workspace, size_t workspace_bytes,
                             tfasr_stream_t stream);
 
+/* Forward without the log-sum-exp pass over the logits (first step): `rowstats` [B*T*U1, parts, 2] f32 are the per-slice
+ * (max, sum exp(v - max)) pairs left by tfasr_gemm_bf16 with epilogue->rowstats set (parts = 2 * ceil(V / 256)).
+ * tfasr_rnnt_lse_from_rowstats_f32 is the combining step alone (lse / blank / truth planes [B,T,U1] f32, rows outside the lattice untouched);
+ * tfasr_rnnt_loss_fwd_rowstats_f32 = that step + the alpha / beta wavefronts, same outputs and workspace layout as tfasr_rnnt_loss_fwd_f32. */
+int tfasr_rnnt_lse_from_rowstats_f32(const float* logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
+                                     const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V, float* lse, float* blank,
+                                     float* truth, tfasr_stream_t stream);
+int tfasr_rnnt_loss_fwd_rowstats_f32(const float* logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
+                                     const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V, int32_t blank, float* costs,
+                                     void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
+
 /* Training-head variant of the backward: the gradient is written as bf16 with row pitch ld_grads (elements, multiple of 4) — the
  * operand format of the joint's backward GEMMs — and may be written IN PLACE over the fp32 logits (grads == logits, ld_grads = 2V).
  * dbias [V] (f32, may be NULL) accumulates the column sums (the vocab Dense bias gradient).  Requires V % 4 == 0, V <= 2048. */
@@ -146,6 +157,10 @@ typedef struct {
   int32_t k_splits;       /* > 1: split the contraction over gridDim.z CTAs (requires atomic_out) */
   const unsigned long long* dropout_seed_ptr; /* DEVICE counter (NULL = 0): bumped once per step, so replayed CUDA graphs differ */
   unsigned long long dropout_salt;            /* per-call-site constant */
+  float* rowstats; /* optional f32 [M, P, 2], P = 2 * ceil(N / 256): per row and column slice s the pair (max_s, sum exp(v - max_s)) of the
+                      final values, so that logsumexp(row) = M + log sum_s exp(max_s - M) sum_s' with M = max_s max_s — the log-softmax
+                      normaliser of the joint logits without a second pass over them (tfasr_rnnt_loss_fwd_rowstats_f32).  Empty slices
+                      hold (-inf, 0).  Lean epilogue only (bias / alpha; no activation, residual, dropout, mul, colsum, split-K). */
 } tfasr_gemm_epilogue;
 
 int tfasr_gemm_bf16(const void* A, const void* B, void* C, int32_t M, int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc,

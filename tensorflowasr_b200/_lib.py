@@ -48,6 +48,7 @@ class GemmEpilogue(ctypes.Structure):
         ("ld_aux", c_int32), ("ld_residual", c_int32), ("ld_mul", c_int32), ("c_f32", c_int32), ("activation", c_int32),
         ("glu", c_int32), ("mul_mode", c_int32), ("residual_scale", c_float), ("alpha", c_float), ("dropout_p", c_float),
         ("atomic_out", c_int32), ("k_splits", c_int32), ("dropout_seed_ptr", c_void_p), ("dropout_salt", ctypes.c_ulonglong),
+        ("rowstats", c_void_p),
     ]
 
 
@@ -68,6 +69,10 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tfasr_rnnt_loss_fwd_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tfasr_rnnt_lse_from_rowstats_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tfasr_rnnt_loss_fwd_rowstats_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                                   c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tfasr_rnnt_loss_bwd_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tfasr_rnnt_loss_bwd_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,

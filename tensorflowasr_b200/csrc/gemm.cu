@@ -89,6 +89,7 @@ TFASR_GEMM_EXTERN(64)
 TFASR_GEMM_EXTERN(128)
 TFASR_GEMM_EXTERN(192)
 TFASR_GEMM_EXTERN(256)
+extern template int launch_gemm<256, false, false, 8u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t);
 
 #ifdef TFASR_GEMM_TRACE
 unsigned long long* g_gemm_trace_host = nullptr;
@@ -140,6 +141,14 @@ static int dispatch_feat(const void* A, const void* B, const GemmEpi& epi, int M
 
 template <bool MN>
 static int dispatch_bn(const void* A, const void* B, const GemmEpi& epi, int M, int N, int K, int lda, int ldb, int splits, cudaStream_t stream) {
+  if (epi.rowstats) {
+    // row statistics ride on the lean epilogue of the 256-column tile only (K-major operands, f32 or bf16 output, no split-K)
+    if constexpr (MN) return TFASR_INVALID_VALUE;
+    else {
+      if (feature_class(epi, false) != 0u || splits != 1 || epi.atomic_out) return TFASR_INVALID_VALUE;
+      return launch_gemm<256, false, false, 8u>(A, B, epi, M, N, K, lda, ldb, splits, stream);
+    }
+  }
   const int bn = choose_bn(N, MN);
   if constexpr (!MN) {
     if (bn == 160) return dispatch_feat<160, false>(A, B, epi, M, N, K, lda, ldb, splits, stream);
@@ -184,6 +193,8 @@ extern "C" int tfasr_gemm_bf16(const void* A, const void* B, void* C, int32_t M,
     epi.seed_ptr = e->dropout_seed_ptr;
     epi.salt = e->dropout_salt;
     epi.atomic_out = e->atomic_out;
+    epi.rowstats = e->rowstats;
+    epi.rs_parts = 2 * ((N + 255) / 256);
   }
   if (epi.glu && ((N & 1) || epi.c_f32)) return TFASR_INVALID_VALUE;
   if (epi.atomic_out && !epi.c_f32) return TFASR_INVALID_VALUE;

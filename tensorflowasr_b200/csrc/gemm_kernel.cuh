@@ -68,6 +68,8 @@ struct GemmEpi {
   int tma_store;        // 1: C leaves through SMEM staging + cp.async.bulk.tensor stores (coalesced, clipped by hardware)
   int tma_side;         // 1: residual, 2: mul arrives through a TMA load into the staging buffer ahead of the accumulator
   int tma_aux;          // 1: the pre-activation copy leaves through its own staging buffer + TMA store
+  float* rowstats;      // feature class 8 only: [M, rs_parts, 2] f32 = per row and column slice (max, sum exp(v - max)) of the final values
+  int rs_parts;         // 2 * ceil(N / BN): every tile contributes two slices per row (the two epilogue warps of a TMEM lane quarter)
 #ifdef TFASR_GEMM_TRACE
   unsigned long long* trace;
 #endif
@@ -144,9 +146,11 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 //   2 dr  : + dropout, residual (side input by TMA)                                    -> FFN-2, attention output, pointwise conv 2, linear
 //   4 bwd : + multiply by f'(saved) (side input by TMA), column sums (bias gradients)  -> backward epilogues
 //   3 = 1|2 (FFN-1: swish + aux + dropout),  6 = 2|4 (FFN backward: dropout mask * swish'),  7 all
+//   8 rs  : lean + per-row softmax statistics of the output (online max / sum-exp per column slice) -> joint logits feeding the RNN-T
+//           loss without a separate log-sum-exp pass over the 2 GB of logits (first step)
 template <uint32_t FEAT>
 struct EpiFeat {
-  static constexpr bool fwd = (FEAT & 1u) != 0, dr = (FEAT & 2u) != 0, bwd = (FEAT & 4u) != 0;
+  static constexpr bool fwd = (FEAT & 1u) != 0, dr = (FEAT & 2u) != 0, bwd = (FEAT & 4u) != 0, rs = (FEAT & 8u) != 0;
 };
 
 template <int BN, bool A_MN, bool B_MN, uint32_t FEAT>
@@ -331,6 +335,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      [[maybe_unused]] float rs_m = -CUDART_INF_F, rs_s = 0.f;  // F::rs: this thread's row, this warp's column slice of the tile
       sm100::mbar_wait(&tmem_full[buf], aph);
       sm100::tc_fence_after();
       if (warp == 2 && lane == 0 && acc_it < 2) TRACE(5 + 2 * acc_it);
@@ -379,6 +384,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[4 * j + 1] += b4.y;
               v[4 * j + 2] += b4.z;
               v[4 * j + 3] += b4.w;
+            }
+          }
+          if constexpr (F::rs) {
+            // online log-sum-exp over the valid columns of this 16-column chunk
+            float cm = -CUDART_INF_F;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < n_cols) cm = fmaxf(cm, v[j]);
+            if (cm > -CUDART_INF_F) {
+              const float mn = fmaxf(rs_m, cm);
+              float acc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < n_cols) acc += __expf(v[j] - mn);
+              rs_s = fmaf(rs_s, __expf(rs_m - mn), acc);  // rs_m = -inf on the first chunk: exp(-inf) = 0
+              rs_m = mn;
             }
           }
           if constexpr (F::fwd) {
@@ -610,6 +631,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+        }
+      }
+      if constexpr (F::rs) {
+        if (epi.rowstats && row_ok && num_k > 0) {  // (-inf, 0) when this warp had no columns in the tile
+          float2* rp = reinterpret_cast<float2*>(epi.rowstats) + (size_t)row * epi.rs_parts + (n_blk * 2 + half);
+          *rp = make_float2(rs_m, rs_s);
         }
       }
       // this thread's tcgen05.ld of the tile are complete: hand the accumulator buffer back to the MMA warp

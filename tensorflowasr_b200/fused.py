@@ -348,16 +348,28 @@ class _TransducerHeadFn(torch.autograd.Function):
         U1 = p.shape[1]
         V = pack.wt.shape[0]
         M = B * T * U1
+        from . import ops
+
         h = kernels.joint_tanh_fwd(e.contiguous(), p.contiguous())
+        fused_lse = ops.fused_lse_active()
+        parts = 2 * ((V + 255) // 256)
+        rowstats = torch.empty((M, parts, 2), dtype=torch.float32, device=e.device) if fused_lse else None
         with _lib.TIMERS.region("joint_gemm_fwd"):
-            logits = kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out_dtype=torch.float32)
+            logits = kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out_dtype=torch.float32, rowstats=rowstats)
         ws_bytes = lib.tfasr_rnnt_workspace_bytes(B, T, U1, V)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=e.device)
         costs = torch.empty(B, dtype=torch.float32, device=e.device)
         with _lib.TIMERS.region("rnnt_fwd"):
-            _lib.check(lib.tfasr_rnnt_loss_fwd_f32(logits.data_ptr(), labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(),
-                                                   B, T, U1, V, 0, costs.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(e.device)),
-                       "tfasr_rnnt_loss_fwd_f32")
+            if fused_lse:
+                # the log-softmax normaliser comes from the GEMM epilogue's row statistics: the logits are not read again before K3
+                _lib.check(lib.tfasr_rnnt_loss_fwd_rowstats_f32(logits.data_ptr(), rowstats.data_ptr(), parts, labels.data_ptr(),
+                                                                logit_length.data_ptr(), label_length.data_ptr(), B, T, U1, V, 0, costs.data_ptr(),
+                                                                ws.data_ptr(), ws_bytes, _lib.stream_ptr(e.device)),
+                           "tfasr_rnnt_loss_fwd_rowstats_f32")
+            else:
+                _lib.check(lib.tfasr_rnnt_loss_fwd_f32(logits.data_ptr(), labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(),
+                                                       B, T, U1, V, 0, costs.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(e.device)),
+                           "tfasr_rnnt_loss_fwd_f32")
         ctx.save_for_backward(h, logits, labels, logit_length, label_length, costs, ws)
         ctx.misc = (pack, (B, T, U1, J, V), e.dtype, p.dtype)
         return costs

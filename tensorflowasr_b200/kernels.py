@@ -13,8 +13,9 @@ _MUL = {None: 0, "swish_grad": 1, "tanh_grad": 2, "mul": 3}
 
 def gemm(a, b, *, out=None, out_dtype=torch.bfloat16, bias=None, activation=None, aux=None, residual=None, residual_scale=1.0,
          mul=None, mul_mode=None, colsum=None, glu=False, alpha=1.0, dropout_p=0.0, dropout_seed=None, dropout_salt=0, mn_major=False,
-         accumulate=False, k_splits=1):
+         accumulate=False, k_splits=1, rowstats=None):
     """C = epilogue(alpha * A . B^T) on the tcgen05 GEMM.
+    rowstats: optional f32 [M, 2 * ceil(N / 256), 2] receiving per-row, per-column-slice (max, sum exp(v - max)) of the output.
 
     default: a [M,K], b [N,K] (bf16, row-major).  mn_major=True: a [K,M], b [K,N] -> C [M,N] = a^T . b.
     """
@@ -52,6 +53,9 @@ def gemm(a, b, *, out=None, out_dtype=torch.bfloat16, bias=None, activation=None
     e.dropout_salt = int(dropout_salt) & 0xFFFFFFFFFFFFFFFF
     e.atomic_out = int(bool(accumulate))
     e.k_splits = int(k_splits)
+    if rowstats is not None:
+        assert rowstats.dtype == torch.float32 and rowstats.is_contiguous() and rowstats.shape == (M, 2 * ((N + 255) // 256), 2)
+        e.rowstats = rowstats.data_ptr()
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
     _lib.check(

@@ -66,6 +66,21 @@ def fused_seq_active(x) -> bool:
     return _FUSED_SEQ and fused_active(x)
 
 
+_FUSED_LSE = _os.environ.get("TFASR_FUSED_LSE", "0") == "1"
+
+
+def set_fused_lse(flag: bool):
+    """Training head: take the RNN-T log-softmax normaliser from softmax statistics computed in the joint GEMM's epilogue (gemm feature
+    class 8 + csrc/rnnt_combine.cu) instead of a separate pass over the 2 GB of logits (first step).  Off by default until
+    tests/test_gpu_zz_lse.py has run green on a B200."""
+    global _FUSED_LSE
+    _FUSED_LSE = bool(flag)
+
+
+def fused_lse_active() -> bool:
+    return _FUSED_LSE
+
+
 _PERSISTENT_DECODE = _os.environ.get("TFASR_PERSISTENT_DECODE", "0") == "1"
 
 

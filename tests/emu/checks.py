@@ -32,7 +32,7 @@ def load(asan=False):
     import build_emu
 
     lib = ctypes.CDLL(build_emu.build(asan=asan))
-    for name in ("tfasr_greedy_decode_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+    for name in ("tfasr_greedy_decode_f32", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
     return lib
@@ -445,6 +445,59 @@ def check_greedy_single(lib, T, E, R, J, V, nframes, cap, threads, seed=6, blank
     close(bufs["states"][0][0, 0], h, 1e-4, "greedy single h")
 
 
+# ------------------------------------------------------------------------------------------------ RNN-T normaliser from GEMM row statistics
+def gemm_rowstats_ref(logits2d, BN=256):
+    """What the tcgen05 GEMM's feature-class-8 epilogue leaves per row (gemm_kernel.cuh): for every 256-column tile two slices — the 32-column
+    groups of the tile split between the two epilogue warps of a TMEM lane quarter — each as (max, sum exp(v - max)); (-inf, 0) when empty."""
+    M, N = logits2d.shape
+    nt = -(-N // BN)
+    out = np.zeros((M, 2 * nt, 2), np.float32)
+    for nb in range(nt):
+        n_cols = min(BN, N - nb * BN)
+        n_groups = (n_cols + 31) // 32
+        g_mid = (n_groups + 1) // 2
+        for half, (g0, g1) in enumerate(((0, g_mid), (g_mid, n_groups))):
+            c0, c1 = nb * BN + g0 * 32, nb * BN + min(n_cols, g1 * 32)
+            if c1 <= c0:
+                out[:, 2 * nb + half] = (-np.inf, 0.0)
+                continue
+            blk = logits2d[:, c0:c1].astype(np.float64)
+            m = blk.max(1)
+            out[:, 2 * nb + half, 0] = m
+            out[:, 2 * nb + half, 1] = np.exp(blk - m[:, None]).sum(1)
+    return out
+
+
+def check_rnnt_combine(lib, B, T, U1, V, logit_len, label_len, seed=12):
+    rng = np.random.default_rng(seed)
+    logits = (rng.standard_normal((B, T, U1, V)) * 3).astype(np.float32)
+    labels = rng.integers(1, V, (B, max(U1 - 1, 1))).astype(np.int32)
+    tl, ul = np.asarray(logit_len, np.int32), np.asarray(label_len, np.int32)
+    stats = gemm_rowstats_ref(logits.reshape(-1, V))
+    x = logits.astype(np.float64)
+    mx = x.max(-1, keepdims=True)
+    lse_ref = (mx + np.log(np.exp(x - mx).sum(-1, keepdims=True)))[..., 0]
+    bufs = [heap(a) for a in (logits, stats, labels, tl, ul)]
+    outs = [heap(np.full((B, T, U1), np.nan, np.float32)) for _ in range(3)]
+    assert lib.tfasr_rnnt_lse_from_rowstats_f32(bufs[0][1], bufs[1][1], stats.shape[1], bufs[2][1], bufs[3][1], bufs[4][1], B, T, U1, V,
+                                                outs[0][1], outs[1][1], outs[2][1], None) == 0
+    lse, blank, truth = (o[0] for o in outs)
+    for b in range(B):
+        Tb, Ub = int(tl[b]), int(ul[b])
+        inside = np.zeros((T, U1), bool)
+        inside[:Tb, :Ub + 1] = True
+        assert np.isnan(lse[b][~inside]).all(), "rows outside the lattice must stay untouched"
+        if not inside.any():
+            continue  # empty utterance: nothing to compare
+        close(lse[b][inside], lse_ref[b][inside], 1e-5, "lse from row statistics")
+        close(blank[b][inside], (x[b, :, :, 0] - lse_ref[b])[inside], 1e-5, "blank log-prob")
+        for u in range(Ub + 1):
+            if u < Ub:
+                close(truth[b, :Tb, u], x[b, :Tb, u, labels[b, u]] - lse_ref[b, :Tb, u], 1e-5, "truth log-prob")
+            else:
+                assert np.isneginf(truth[b, :Tb, u]).all()
+
+
 # ------------------------------------------------------------------------------------------------ error behaviour
 def check_invalid(lib):
     a, p = heap(np.zeros(64, np.float32))
@@ -480,6 +533,8 @@ CASES = [
     ("greedy_batch_scalar", lambda lib: check_greedy_batch(lib, 2, 6, 10, 12, 9, 29, [6, 5], 64, seed=1, blank_bias=3.0)),  # odd J, V: one column per thread
     ("greedy_batch_small_cta", lambda lib: check_greedy_batch(lib, 2, 5, 8, 16, 8, 16, [5, 3], 32, seed=16, blank_bias=3.0)),  # little or no split
     ("greedy_single", lambda lib: check_greedy_single(lib, 6, 16, 24, 20, 12, 6, 3, 96, seed=8, blank_bias=0.5)),
+    ("rnnt_combine_v1000", lambda lib: check_rnnt_combine(lib, 2, 5, 4, 1000, [5, 3], [3, 1])),  # 4 tiles, last one 232 columns wide
+    ("rnnt_combine_small_v", lambda lib: check_rnnt_combine(lib, 3, 4, 3, 40, [4, 0, 2], [2, 2, 0])),  # one tile, second slice empty for 1 group
     ("invalid_arguments", check_invalid),
 ]
 

@@ -1,0 +1,59 @@
+"""GPU parity of the fused log-sum-exp path (first step): softmax row statistics from the joint GEMM's epilogue (gemm feature
+class 8) + csrc/rnnt_combine.cu in place of the K1 pass over the logits.
+
+STATUS: written in a session with no GPU minutes left (the combine kernel is emulator-verified, the tcgen05 epilogue addition is not
+verifiable without a GPU; the SASS of every pre-existing GEMM instantiation is unchanged).  xfail(strict=False), sorts last; the path is
+opt-in (`ops.set_fused_lse(True)` / TFASR_FUSED_LSE=1)."""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet run on a B200")]
+
+
+@pytest.mark.parametrize("shape", [(4097, 1000, 320), (300, 256, 64), (129, 40, 320), (1000, 1024, 128), (77, 520, 64)])
+def test_gemm_row_statistics_give_logsumexp(shape):
+    from tensorflowasr_b200 import kernels
+
+    M, N, K = shape
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda") * (3.0 / K ** 0.5)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    parts = 2 * ((N + 255) // 256)
+    stats = torch.full((M, parts, 2), float("nan"), device="cuda")
+    out = kernels.gemm(a, b, bias=bias, out_dtype=torch.float32, rowstats=stats)
+    ref = a.float() @ b.float().t() + bias
+    assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    assert torch.isfinite(stats[..., 1]).all()
+    m = stats[..., 0].max(1, keepdim=True).values
+    lse = (m + torch.log((stats[..., 1] * torch.exp(stats[..., 0] - m)).sum(1, keepdim=True)))[:, 0]
+    torch.testing.assert_close(lse, torch.logsumexp(out, dim=1), rtol=1e-5, atol=1e-4)
+    # the slices partition the row: their sum-exp terms add up to the row's
+    torch.testing.assert_close((stats[..., 1] * torch.exp(stats[..., 0] - m)).sum(1), torch.exp(out - m).sum(1), rtol=1e-4, atol=1e-5)
+
+
+def test_transducer_head_costs_and_gradients_match_with_fused_lse():
+    from tensorflowasr_b200 import fused, ops
+
+    torch.manual_seed(2)
+    B, T, U1, J, V = 3, 37, 9, 64, 1000
+    e = (torch.randn(B, T, J, device="cuda") * 0.5).to(torch.bfloat16)
+    p = (torch.randn(B, U1, J, device="cuda") * 0.5).to(torch.bfloat16)
+    labels = torch.randint(1, V, (B, U1 - 1), device="cuda", dtype=torch.int32)
+    tl = torch.tensor([37, 20, 5], device="cuda", dtype=torch.int32)
+    ul = torch.tensor([8, 3, 0], device="cuda", dtype=torch.int32)
+    res = {}
+    try:
+        for flag in (False, True):
+            ops.set_fused_lse(flag)
+            w = torch.nn.Parameter((torch.randn(J, V, generator=torch.Generator().manual_seed(5)) / J ** 0.5).cuda())
+            bvec = torch.nn.Parameter(torch.randn(V, generator=torch.Generator().manual_seed(6)).cuda() * 0.1)
+            er, pr = e.clone().requires_grad_(True), p.clone().requires_grad_(True)
+            costs = fused.transducer_head(er, pr, fused.WeightPack(w, bvec), labels, tl, ul)
+            costs.sum().backward()
+            res[flag] = (costs.detach().clone(), er.grad.clone(), pr.grad.clone(), w.grad.clone(), bvec.grad.clone())
+    finally:
+        ops.set_fused_lse(False)
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=1e-5, atol=1e-4)
+    for a, b in zip(res[True][1:], res[False][1:]):
+        assert (a.float() - b.float()).abs().max().item() <= 2e-3 * (b.float().abs().max().item() + 1e-6)

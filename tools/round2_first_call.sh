@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 # 1. the GPU parity tests marked xfail(strict=False) in round 1, as real tests (--runxfail), each file in its own process so that a
 #    sticky CUDA error in one cannot poison the other
-for f in tests/test_gpu_zz_seqconv.py tests/test_gpu_zz_decode.py; do
+for f in tests/test_gpu_zz_seqconv.py tests/test_gpu_zz_decode.py tests/test_gpu_zz_lse.py; do
   timeout 600 python -m pytest "$f" -m gpu --runxfail -q -x --tb=short 2>&1 | tail -40 >> gpurun_out/r2_unverified_tests.log
   echo "=== $f exit ${PIPESTATUS[0]}" >> gpurun_out/r2_unverified_tests.log
 done
@@ -20,3 +20,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:greedy_decode -c 1 -o gpurun_out/greedy_decode_r02 \
   python tools/decode_bench.py --batch 32 --frames 60 > /dev/null 2>&1
 tail -5 gpurun_out/r2_unverified_tests.log
+# 4. fused log-sum-exp (gemm feature class 8): the headline bench with and without it
+TFASR_FUSED_LSE=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fused_lse.json 2> gpurun_out/bench_fused_lse.err
+timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
