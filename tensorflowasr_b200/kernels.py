@@ -134,13 +134,20 @@ def _st(t):
     return _lib.stream_ptr(t.device)
 
 
+def _conv1_v2(C):
+    from . import ops
+
+    return ops.conv1_v2_active() and C % 8 == 0 and C <= 256
+
+
 def conv1_fwd(x, w, bias):
     """x [B,T,F] f32, w [3,3,1,C] f32 -> y [B,T1,F1,C] bf16 (3x3, stride 2, causal)."""
     lib = _lib.load()
     B, T, F = x.shape
     C = w.shape[-1]
     y = torch.empty((B, (T + 1) // 2, (F + 1) // 2, C), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.tfasr_conv1_3x3s2_fwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), B, T, F, C, _st(x)), "tfasr_conv1_3x3s2_fwd")
+    fn, name = (lib.tfasr_conv1_3x3s2_fwd_v2, "tfasr_conv1_3x3s2_fwd_v2") if _conv1_v2(C) else (lib.tfasr_conv1_3x3s2_fwd, "tfasr_conv1_3x3s2_fwd")
+    _lib.check(fn(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(y), B, T, F, C, _st(x)), name)
     return y
 
 
@@ -148,7 +155,8 @@ def conv1_wgrad(x, dy, dw):
     lib = _lib.load()
     B, T, F = x.shape
     C = dy.shape[-1]
-    _lib.check(lib.tfasr_conv1_3x3s2_wgrad(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), B, T, F, C, _st(x)), "tfasr_conv1_3x3s2_wgrad")
+    fn, name = (lib.tfasr_conv1_3x3s2_wgrad_v2, "tfasr_conv1_3x3s2_wgrad_v2") if _conv1_v2(C) else (lib.tfasr_conv1_3x3s2_wgrad, "tfasr_conv1_3x3s2_wgrad")
+    _lib.check(fn(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), B, T, F, C, _st(x)), name)
 
 
 def im2col(a):

@@ -66,6 +66,19 @@ def fused_seq_active(x) -> bool:
     return _FUSED_SEQ and fused_active(x)
 
 
+_CONV1_V2 = _os.environ.get("TFASR_CONV1_V2", "0") == "1"
+
+
+def set_conv1_v2(flag: bool):
+    """Conv2dSubsampling's first conv on the second-generation kernels (csrc/conv1.cu).  Off by default until measured on a B200."""
+    global _CONV1_V2
+    _CONV1_V2 = bool(flag)
+
+
+def conv1_v2_active() -> bool:
+    return _CONV1_V2
+
+
 _FUSED_LSE = _os.environ.get("TFASR_FUSED_LSE", "0") == "1"
 
 

@@ -32,7 +32,7 @@ def load(asan=False):
     import build_emu
 
     lib = ctypes.CDLL(build_emu.build(asan=asan))
-    for name in ("tfasr_greedy_decode_f32", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+    for name in ("tfasr_greedy_decode_f32", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
     return lib
@@ -498,6 +498,36 @@ def check_rnnt_combine(lib, B, T, U1, V, logit_len, label_len, seed=12):
                 assert np.isneginf(truth[b, :Tb, u]).all()
 
 
+# ------------------------------------------------------------------------------------------------ first conv of the subsampling, v2
+def check_conv1_v2(lib, B, T, F, C, seed=13):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, T, F)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 1, C)) * 0.3).astype(np.float32)
+    bias = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    T1, F1 = (T + 1) // 2, (F + 1) // 2
+    xp = np.zeros((B, 2 * T1 + 2, 2 * F1 + 2))
+    xp[:, 2:2 + T, 2:2 + F] = x
+    y_ref = np.zeros((B, T1, F1, C)) + bias
+    dy = rbf(rng.standard_normal((B, T1, F1, C)))
+    dw_ref = np.zeros((3, 3, 1, C))
+    for kh in range(3):
+        for kw in range(3):
+            patch = xp[:, kh:kh + 2 * T1:2, kw:kw + 2 * F1:2]  # x[b, 2 t1 + kh - 2, 2 f1 + kw - 2]
+            y_ref += patch[..., None] * w[kh, kw, 0]
+            dw_ref[kh, kw, 0] = (patch[..., None] * dy.astype(np.float64)).sum((0, 1, 2))
+    xb, xp_ = heap(x)
+    wb, wp = heap(w)
+    bb, bp = heap(bias)
+    yb, yp = heap(np.zeros((B, T1, F1, C), np.uint16))
+    assert lib.tfasr_conv1_3x3s2_fwd_v2(xp_, wp, bp, yp, B, T, F, C, None) == 0
+    close(from_bf16(yb), y_ref, 5e-3, f"conv1 v2 fwd {(B, T, F, C)}")
+    dyb, dyp = heap(to_bf16(dy))
+    init = rng.standard_normal((3, 3, 1, C)).astype(np.float32)
+    dwb, dwp = heap(init)
+    assert lib.tfasr_conv1_3x3s2_wgrad_v2(xp_, dyp, dwp, B, T, F, C, None) == 0
+    close(dwb - init, dw_ref, 2e-4, f"conv1 v2 wgrad {(B, T, F, C)}")
+
+
 # ------------------------------------------------------------------------------------------------ error behaviour
 def check_invalid(lib):
     a, p = heap(np.zeros(64, np.float32))
@@ -535,6 +565,9 @@ CASES = [
     ("greedy_single", lambda lib: check_greedy_single(lib, 6, 16, 24, 20, 12, 6, 3, 96, seed=8, blank_bias=0.5)),
     ("rnnt_combine_v1000", lambda lib: check_rnnt_combine(lib, 2, 5, 4, 1000, [5, 3], [3, 1])),  # 4 tiles, last one 232 columns wide
     ("rnnt_combine_small_v", lambda lib: check_rnnt_combine(lib, 3, 4, 3, 40, [4, 0, 2], [2, 2, 0])),  # one tile, second slice empty for 1 group
+    ("conv1_v2_even", lambda lib: check_conv1_v2(lib, 2, 22, 16, 24)),
+    ("conv1_v2_odd", lambda lib: check_conv1_v2(lib, 2, 37, 13, 16)),  # odd T and F, T1 not a multiple of the rows per CTA
+    ("conv1_v2_tiny", lambda lib: check_conv1_v2(lib, 1, 1, 1, 8)),
     ("invalid_arguments", check_invalid),
 ]
 

@@ -57,3 +57,27 @@ def test_transducer_head_costs_and_gradients_match_with_fused_lse():
     torch.testing.assert_close(res[True][0], res[False][0], rtol=1e-5, atol=1e-4)
     for a, b in zip(res[True][1:], res[False][1:]):
         assert (a.float() - b.float()).abs().max().item() <= 2e-3 * (b.float().abs().max().item() + 1e-6)
+
+
+def test_conv1_v2_matches_first_generation_kernels():
+    """csrc/conv1.cu (opt-in, TFASR_CONV1_V2) against the verified conv_bn.cu kernels: identical contract."""
+    from tensorflowasr_b200 import kernels, ops
+
+    torch.manual_seed(4)
+    for (B, T, F, C) in [(4, 1000, 80, 144), (2, 37, 13, 16), (1, 1, 1, 8)]:
+        x = torch.randn(B, T, F, device="cuda")
+        w = torch.randn(3, 3, 1, C, device="cuda") * 0.3
+        bias = torch.randn(C, device="cuda") * 0.1
+        res = {}
+        try:
+            for flag in (False, True):
+                ops.set_conv1_v2(flag)
+                y = kernels.conv1_fwd(x, w, bias)
+                dy = torch.randn(y.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)).to(torch.bfloat16)
+                dw = torch.zeros_like(w)
+                kernels.conv1_wgrad(x, dy, dw)
+                res[flag] = (y.float(), dw)
+        finally:
+            ops.set_conv1_v2(False)
+        assert (res[True][0] - res[False][0]).abs().max().item() <= 1e-2 * res[False][0].abs().max().item()
+        assert (res[True][1] - res[False][1]).abs().max().item() <= 2e-3 * res[False][1].abs().max().item() + 1e-6

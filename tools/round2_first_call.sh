@@ -23,3 +23,5 @@ tail -5 gpurun_out/r2_unverified_tests.log
 # 4. fused log-sum-exp (gemm feature class 8): the headline bench with and without it
 TFASR_FUSED_LSE=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fused_lse.json 2> gpurun_out/bench_fused_lse.err
 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+# 5. second-generation conv1 kernels (csrc/conv1.cu) in the headline step
+TFASR_CONV1_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_conv1_v2.json 2> gpurun_out/bench_conv1_v2.err
