@@ -64,3 +64,29 @@ def test_no_cpu_fallback():
         FeatureExtraction()((torch.zeros(1, 1600), torch.tensor([1600])))
     with pytest.raises(RuntimeError):
         rnnt_loss(torch.zeros(1, 2, 3, 5), torch.tensor([2]), torch.zeros(1, 2, dtype=torch.int32), torch.tensor([2]))
+
+
+def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct of include/tfasr_b200.h as gcc lays it out == the ctypes mirrors in _lib.py."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {"tfasr_logmel_cfg": _lib.LogmelCfg, "tfasr_gemm_epilogue": _lib.GemmEpilogue, "tfasr_conv_geom": _lib.ConvGeom,
+               "tfasr_greedy_params": _lib.GreedyParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tfasr_b200.h"', "int main(void) {"]
+    for cname, mirror in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, mirror in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(mirror), cname
+        for fname, _ in mirror._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(mirror, fname).offset, f"{cname}.{fname}"
