@@ -119,6 +119,11 @@ int tfasr_rnnt_loss_fwd_rowstats_f32(const float* logits, const float* rowstats,
 int tfasr_rnnt_loss_bwd_bf16(const float* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
                              int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
                              int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
+/* second generation of the same kernel (csrc/rnnt_grad_v2.cu: rows processed in two halves, bias partial sums in warp-private shared memory:
+ * 72 registers instead of 126, three CTAs per SM); identical contract.  Opt-in until measured on a B200. */
+int tfasr_rnnt_loss_bwd_bf16_v2(const float* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
+                                int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
+                                int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CTC loss + gradient (tf.nn.ctc_loss, dense labels, batch-major logits [B, T, V], blank_index 0).

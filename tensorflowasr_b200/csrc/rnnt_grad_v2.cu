@@ -1,0 +1,178 @@
+// RNN-T gradient kernel K3', second generation (opt-in: ops.set_rnnt_grad_v2 / TFASR_RNNT_GRAD_V2=1).  Same contract as
+// tfasr_rnnt_loss_bwd_bf16 (rnnt_loss.cu): grads = g - softmax * sum(g) (losses/impl/rnnt.py:233-275) scaled by the upstream gradient
+// (:321-324), written as bf16 with row pitch ld_grads, optionally IN PLACE over the fp32 logits, plus the vocab-bias gradient.
+//
+// Why: the first-generation kernel holds a whole row (8 float4 per lane at V = 1000) AND its per-column bias partial sums (8 more float4)
+// in registers: 126 registers -> 2 CTAs per SM = 25 % occupancy, 4.2 TB/s on 3.09 GB (profiles/rnnt_ncu_r01.txt).  Here
+//   * a row is processed in two halves (4 float4 per lane live at a time).  In-place safety: the bf16 gradient of columns [0, 4 h4) lands
+//     in bytes [0, 8 h4) of the row = fp32 columns [0, 2 h4) — inside the first half, which every lane has in registers (one __syncwarp)
+//     before any lane stores; the second half's gradient lands in fp32 columns [2 h4, 2 n4) <= first half again, already consumed, and
+//     the second half's loads (fp32 float4 index >= h4) are never touched by first-half stores (float4 index < h4 / 2).
+//   * the bias partial sums live in warp-private SMEM rows (plain read-modify-write, no atomics, no bank conflicts within a warp)
+//     and are reduced once per CTA.
+// HBM-bound byte work (12 B per lattice node and vocabulary entry incl. the second read); no tensor cores.  Plain SIMT: builds twice.
+#include "simt.cuh"
+
+#ifdef TFASR_EMU_BUILD
+#include "../../include/tfasr_b200.h"
+typedef void* cudaStream_t;
+#endif
+
+namespace tfasr {
+
+constexpr int kG2Warps = 8;
+
+struct RnntPlanes {  // the workspace planes of rnnt_loss.cu (rnnt_ws_carve): [B, T, U1] f32 each
+  const float *lse, *blank, *truth, *alpha, *beta;
+};
+
+// NV4H = float4 per lane per half row (V <= 256 * NV4H)
+template <int NV4H>
+__global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_v2_kernel(const float* logits, const int32_t* __restrict__ labels,
+                                                                             const int32_t* __restrict__ logit_len,
+                                                                             const int32_t* __restrict__ label_len, int B, int T, int U1, int V,
+                                                                             RnntPlanes ws, const float* __restrict__ costs,
+                                                                             const float* __restrict__ grad_scale, __nv_bfloat16* grads, int64_t ld_g,
+                                                                             float* __restrict__ dbias) {
+  TFASR_DYN_SMEM(smem_raw);
+  float* s_cs = reinterpret_cast<float*>(smem_raw);  // [kG2Warps][V] when dbias
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nrows = (int64_t)B * T * U1;
+  const int n4 = V >> 2, h4 = (n4 + 1) >> 1;
+  if (dbias) {
+    for (int j = threadIdx.x; j < kG2Warps * V; j += blockDim.x) s_cs[j] = 0.f;
+    __syncthreads();
+  }
+  float4* cs4 = reinterpret_cast<float4*>(s_cs + (size_t)warp * V);
+  for (int64_t row = (int64_t)blockIdx.x * kG2Warps + warp; row < nrows; row += (int64_t)gridDim.x * kG2Warps) {
+    const int u = (int)(row % U1);
+    const int t = (int)((row / U1) % T);
+    const int b = (int)(row / ((int64_t)U1 * T));
+    const int Tb = logit_len[b], Ub = label_len[b];
+    uint2* g2 = reinterpret_cast<uint2*>(grads + row * ld_g);
+    if (!((t < Tb) && (u <= Ub))) {
+      for (int j = lane; j < n4; j += 32) g2[j] = make_uint2(0u, 0u);
+      continue;
+    }
+    const float logz = -costs[b];
+    const float a = ws.alpha[row];
+    const float lse = ws.lse[row];
+    float gb = 0.f, gt = 0.f;
+    int label = -1;
+    if (t < Tb - 1) gb = -expf(a + ws.beta[row + U1] + ws.blank[row] - logz);
+    else if (u == Ub) gb = -1.0f;
+    if (u < Ub) {
+      gt = -expf(a + ws.beta[row + 1] + ws.truth[row] - logz);
+      label = labels[(int64_t)b * (U1 - 1) + u];
+    }
+    const float sc = grad_scale ? grad_scale[b] : 1.0f;
+    gb *= sc;
+    gt *= sc;
+    const float gsum = gb + gt;
+    const float4* x4 = reinterpret_cast<const float4*>(logits + row * V);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j0 = half ? h4 : 0, j1 = half ? n4 : h4;
+      float4 v[NV4H];
+#pragma unroll
+      for (int i = 0; i < NV4H; ++i) {
+        const int j = j0 + lane + 32 * i;
+        if (j < j1) v[i] = simt_ld_stream_f4(x4 + j);
+      }
+      if (half == 0) __syncwarp();  // in-place mode: the whole first half is in registers before any lane overwrites part of it
+#pragma unroll
+      for (int i = 0; i < NV4H; ++i) {
+        const int j = j0 + lane + 32 * i;
+        if (j < j1) {
+          float4 o;
+          o.x = -__expf(v[i].x - lse) * gsum;
+          o.y = -__expf(v[i].y - lse) * gsum;
+          o.z = -__expf(v[i].z - lse) * gsum;
+          o.w = -__expf(v[i].w - lse) * gsum;
+          const int c0 = 4 * j;
+          if (c0 == 0) o.x += gb;
+          if (label >= c0 && label < c0 + 4) {
+            const int r = label - c0;
+            if (r == 0) o.x += gt;
+            else if (r == 1) o.y += gt;
+            else if (r == 2) o.z += gt;
+            else o.w += gt;
+          }
+          if (dbias) {
+            float4 c = cs4[j];
+            c.x += o.x;
+            c.y += o.y;
+            c.z += o.z;
+            c.w += o.w;
+            cs4[j] = c;
+          }
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          g2[j] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+      }
+    }
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kG2Warps; ++w) s += s_cs[(size_t)w * V + j];
+      atomicAdd(dbias + j, s);
+    }
+  }
+}
+
+}  // namespace tfasr
+
+using namespace tfasr;
+
+extern "C" int tfasr_rnnt_loss_bwd_bf16_v2(const float* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
+                                           int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
+                                           int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream_) {
+  if (blank != 0 || B < 0 || T < 1 || U1 < 1 || V < 2 || U1 > 1024) return TFASR_INVALID_VALUE;
+  if (!logits || !logit_len || !label_len || !workspace || (U1 > 1 && !labels) || !costs || !grads || ld_grads < V || (ld_grads & 3))
+    return TFASR_INVALID_VALUE;
+  if ((V & 3) || V > 2048 || (reinterpret_cast<uintptr_t>(logits) & 15) || (reinterpret_cast<uintptr_t>(grads) & 7)) return TFASR_INVALID_VALUE;
+  // workspace layout of rnnt_loss.cu (rnnt_ws_carve): five [B,T,U1] f32 planes, each rounded up to 256 bytes: lse, blank, truth, alpha, beta
+  const size_t plane = (sizeof(float) * (size_t)B * T * U1 + 255) / 256 * 256;
+  if (workspace_bytes < 5 * plane) return TFASR_WORKSPACE_TOO_SMALL;
+  if (B == 0) return TFASR_OK;
+  const char* wp = static_cast<const char*>(workspace);
+  RnntPlanes ws;
+  ws.lse = reinterpret_cast<const float*>(wp);
+  ws.blank = reinterpret_cast<const float*>(wp + plane);
+  ws.truth = reinterpret_cast<const float*>(wp + 2 * plane);
+  ws.alpha = reinterpret_cast<const float*>(wp + 3 * plane);
+  ws.beta = reinterpret_cast<const float*>(wp + 4 * plane);
+  const int64_t nrows = (int64_t)B * T * U1;
+  int64_t ctas = ceil_div(nrows, kG2Warps);
+  if (ctas > (int64_t)kNumSMs * 12) ctas = (int64_t)kNumSMs * 12;
+  const size_t smem = dbias ? sizeof(float) * (size_t)kG2Warps * V : 0;
+  __nv_bfloat16* g = static_cast<__nv_bfloat16*>(grads);
+#ifdef TFASR_EMU_BUILD
+  (void)stream_;
+#define G2_LAUNCH(N) \
+  emu::launch(dim3((unsigned)ctas), dim3(kG2Warps * 32), smem, [&] { rnnt_grad_bf16_v2_kernel<N>(logits, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, ld_grads, dbias); })
+#else
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+#define G2_LAUNCH(N)                                                                                                                         \
+  do {                                                                                                                                       \
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(rnnt_grad_bf16_v2_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+      return TFASR_EXECUTION_FAILED;                                                                                                         \
+    rnnt_grad_bf16_v2_kernel<N><<<(unsigned)ctas, kG2Warps * 32, smem, stream>>>(logits, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, \
+                                                                                 g, ld_grads, dbias);                                       \
+    count_launch();                                                                                                                          \
+  } while (0)
+#endif
+  if (V <= 256) G2_LAUNCH(1);
+  else if (V <= 512) G2_LAUNCH(2);
+  else if (V <= 1024) G2_LAUNCH(4);
+  else G2_LAUNCH(8);
+#undef G2_LAUNCH
+#ifdef TFASR_EMU_BUILD
+  return TFASR_OK;
+#else
+  return check_launch();
+#endif
+}

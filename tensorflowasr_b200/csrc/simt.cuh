@@ -49,6 +49,16 @@ __device__ __forceinline__ uint4 bf8_pack(const float* f) {
   return make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
+// read-once 16-byte global load (device: ld.global.L1::no_allocate; emulator: plain load with the alignment check)
+__device__ __forceinline__ float4 simt_ld_stream_f4(const float4* p) {
+#ifdef TFASR_EMU_BUILD
+  if (reinterpret_cast<uintptr_t>(p) & 15) abort();
+  return *p;
+#else
+  return ld_stream_f4(p);
+#endif
+}
+
 __device__ __forceinline__ float simt_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // activation codes shared with the BatchNorm kernels: 0 none, 1 swish, 2 relu
 __device__ __forceinline__ float simt_act(float z, int act) {

@@ -384,11 +384,14 @@ class _TransducerHeadFn(torch.autograd.Function):
         M = B * T * U1
         scale = dcosts.float().contiguous()
         dl = logits.view(M, V).view(torch.bfloat16)  # [M, 2V] bf16 view of the same memory; gradient lands in [:, :V]
+        from . import ops
+
+        bwd_fn, bwd_name = ((lib.tfasr_rnnt_loss_bwd_bf16_v2, "tfasr_rnnt_loss_bwd_bf16_v2") if ops.rnnt_grad_v2_active()
+                            else (lib.tfasr_rnnt_loss_bwd_bf16, "tfasr_rnnt_loss_bwd_bf16"))
         with _lib.TIMERS.region("rnnt_bwd"):
-            _lib.check(lib.tfasr_rnnt_loss_bwd_bf16(logits.data_ptr(), labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(),
-                                                    B, T, U1, V, 0, costs.data_ptr(), scale.data_ptr(), dl.data_ptr(), 2 * V,
-                                                    _grad(pack.bias).data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(h.device)),
-                       "tfasr_rnnt_loss_bwd_bf16")
+            _lib.check(bwd_fn(logits.data_ptr(), labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(), B, T, U1, V, 0,
+                              costs.data_ptr(), scale.data_ptr(), dl.data_ptr(), 2 * V, _grad(pack.bias).data_ptr(), ws.data_ptr(), ws.numel(),
+                              _lib.stream_ptr(h.device)), bwd_name)
         dlv = dl[:, :V]
         h2 = h.view(M, J)
         with _lib.TIMERS.region("joint_gemm_dgrad"):

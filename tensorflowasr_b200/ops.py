@@ -66,6 +66,19 @@ def fused_seq_active(x) -> bool:
     return _FUSED_SEQ and fused_active(x)
 
 
+_RNNT_GRAD_V2 = _os.environ.get("TFASR_RNNT_GRAD_V2", "0") == "1"
+
+
+def set_rnnt_grad_v2(flag: bool):
+    """Training head: RNN-T gradient on the second-generation kernel (csrc/rnnt_grad_v2.cu).  Off by default until measured on a B200."""
+    global _RNNT_GRAD_V2
+    _RNNT_GRAD_V2 = bool(flag)
+
+
+def rnnt_grad_v2_active() -> bool:
+    return _RNNT_GRAD_V2
+
+
 _CONV1_V2 = _os.environ.get("TFASR_CONV1_V2", "0") == "1"
 
 

@@ -32,7 +32,7 @@ def load(asan=False):
     import build_emu
 
     lib = ctypes.CDLL(build_emu.build(asan=asan))
-    for name in ("tfasr_greedy_decode_f32", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+    for name in ("tfasr_greedy_decode_f32", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
     return lib
@@ -498,6 +498,107 @@ def check_rnnt_combine(lib, B, T, U1, V, logit_len, label_len, seed=12):
                 assert np.isneginf(truth[b, :Tb, u]).all()
 
 
+# ------------------------------------------------------------------------------------------------ RNN-T gradient kernel, v2
+def rnnt_planes_ref(x, labels, Tb, Ub):
+    """float64 forward-backward of one utterance (losses/impl/rnnt.py:108-178): x [T,U1,V] -> lse, blank, truth, alpha, beta [T,U1], cost."""
+    T, U1, V = x.shape
+    mx = x.max(-1, keepdims=True)
+    lse = (mx + np.log(np.exp(x - mx).sum(-1, keepdims=True)))[..., 0]
+    blank = x[..., 0] - lse
+    truth = np.full((T, U1), -np.inf)
+    for u in range(Ub):
+        truth[:, u] = x[:, u, labels[u]] - lse[:, u]
+    alpha = np.full((T, U1), -np.inf)
+    beta = np.full((T, U1), -np.inf)
+    for t in range(Tb):
+        for u in range(Ub + 1):
+            if t == 0 and u == 0:
+                alpha[0, 0] = 0.0
+                continue
+            a = alpha[t - 1, u] + blank[t - 1, u] if t > 0 else -np.inf
+            b = alpha[t, u - 1] + truth[t, u - 1] if u > 0 else -np.inf
+            alpha[t, u] = np.logaddexp(a, b)
+    for t in range(Tb - 1, -1, -1):
+        for u in range(Ub, -1, -1):
+            if t == Tb - 1 and u == Ub:
+                beta[t, u] = blank[t, u]
+                continue
+            a = beta[t + 1, u] + blank[t, u] if t < Tb - 1 else -np.inf
+            b = beta[t, u + 1] + truth[t, u] if u < Ub else -np.inf
+            beta[t, u] = np.logaddexp(a, b)
+    return lse, blank, truth, alpha, beta, -beta[0, 0]
+
+
+def rnnt_grad_ref(x, labels, Tb, Ub, planes):
+    lse, blank, truth, alpha, beta, cost = planes
+    T, U1, V = x.shape
+    g = np.zeros_like(x)
+    logz = -cost
+    for t in range(Tb):
+        for u in range(Ub + 1):
+            gb = -np.exp(alpha[t, u] + beta[t + 1, u] + blank[t, u] - logz) if t < Tb - 1 else (-1.0 if u == Ub else 0.0)
+            gt = -np.exp(alpha[t, u] + beta[t, u + 1] + truth[t, u] - logz) if u < Ub else 0.0
+            g[t, u] = -np.exp(x[t, u] - lse[t, u]) * (gb + gt)
+            g[t, u, 0] += gb
+            if u < Ub:
+                g[t, u, labels[u]] += gt
+    return g
+
+
+def check_rnnt_grad_v2(lib, B, T, U1, V, logit_len, label_len, in_place, seed=14):
+    rng = np.random.default_rng(seed)
+    logits = rng.standard_normal((B, T, U1, V)).astype(np.float32)
+    labels = rng.integers(1, V, (B, max(U1 - 1, 1))).astype(np.int32)
+    tl, ul = np.asarray(logit_len, np.int32), np.asarray(label_len, np.int32)
+    scale = rng.uniform(0.5, 1.5, B).astype(np.float32)
+    plane_elems = B * T * U1
+    plane_pad = (4 * plane_elems + 255) // 256 * 256 // 4
+    ws = np.zeros(5 * plane_pad, np.float32)
+    costs = np.zeros(B, np.float32)
+    g_ref = np.zeros((B, T, U1, V))
+    for b in range(B):
+        Tb, Ub = int(tl[b]), int(ul[b])
+        if Tb <= 0:
+            continue
+        x = logits[b].astype(np.float64)
+        planes = rnnt_planes_ref(x, labels[b], Tb, Ub)
+        if b == 0:  # the reference formula itself against central differences of the cost
+            for (t, u, v) in ((0, 0, 0), (Tb - 1, Ub, 0), (0, 0, int(labels[b, 0])) if Ub > 0 else (0, 0, 1), (Tb // 2, Ub // 2, V - 1)):
+                xp, xm = x.copy(), x.copy()
+                xp[t, u, v] += 1e-5
+                xm[t, u, v] -= 1e-5
+                fd = (rnnt_planes_ref(xp, labels[b], Tb, Ub)[5] - rnnt_planes_ref(xm, labels[b], Tb, Ub)[5]) / 2e-5
+                assert abs(fd - rnnt_grad_ref(x, labels[b], Tb, Ub, planes)[t, u, v]) < 1e-6, "RNN-T gradient reference"
+        g_ref[b] = rnnt_grad_ref(x, labels[b], Tb, Ub, planes) * scale[b]
+        costs[b] = planes[5]
+        for k in range(5):
+            pl = np.where(np.isfinite(planes[k]), planes[k], -np.inf if k >= 2 else 0.0)
+            ws[k * plane_pad + b * T * U1:k * plane_pad + (b + 1) * T * U1] = pl.reshape(-1)
+    wsb, wsp = heap(ws)
+    cb, cp = heap(costs)
+    lb, lp = heap(labels)
+    tb, tp = heap(tl)
+    ub, up = heap(ul)
+    sb, sp = heap(scale)
+    dbias0 = rng.standard_normal(V).astype(np.float32)
+    db, dp = heap(dbias0)
+    xb, xp_ = heap(logits)
+    if in_place:
+        gp, ld = xp_, 2 * V  # bf16 gradient of row r in the first half of row r's fp32 logits
+    else:
+        gb_, gp = heap(np.full((B, T, U1, V + 4), 0x7FC0, np.uint16))
+        ld = V + 4
+    st = lib.tfasr_rnnt_loss_bwd_bf16_v2(xp_, lp, tp, up, B, T, U1, V, 0, cp, sp, gp, ctypes.c_int64(ld), dp, wsp, ctypes.c_size_t(ws.nbytes), None)
+    assert st == 0, st
+    if in_place:
+        got = from_bf16(xb.view(np.uint16).reshape(B, T, U1, 2 * V)[..., :V])
+    else:
+        got = from_bf16(gb_[..., :V])
+        assert (gb_[..., V:] == 0x7FC0).all(), "wrote past the row's V columns"
+    close(got, g_ref, 6e-3, f"rnnt grad v2 in_place={in_place}")
+    close(db - dbias0, rbf(g_ref.astype(np.float32)).astype(np.float64).sum((0, 1, 2)), 2e-3, "vocab bias gradient")
+
+
 # ------------------------------------------------------------------------------------------------ first conv of the subsampling, v2
 def check_conv1_v2(lib, B, T, F, C, seed=13):
     rng = np.random.default_rng(seed)
@@ -565,6 +666,9 @@ CASES = [
     ("greedy_single", lambda lib: check_greedy_single(lib, 6, 16, 24, 20, 12, 6, 3, 96, seed=8, blank_bias=0.5)),
     ("rnnt_combine_v1000", lambda lib: check_rnnt_combine(lib, 2, 5, 4, 1000, [5, 3], [3, 1])),  # 4 tiles, last one 232 columns wide
     ("rnnt_combine_small_v", lambda lib: check_rnnt_combine(lib, 3, 4, 3, 40, [4, 0, 2], [2, 2, 0])),  # one tile, second slice empty for 1 group
+    ("rnnt_grad_v2_in_place", lambda lib: check_rnnt_grad_v2(lib, 3, 5, 4, 1000, [5, 3, 0], [3, 1, 2], True)),  # V = 1000: 4 float4 per lane and half
+    ("rnnt_grad_v2_pitched", lambda lib: check_rnnt_grad_v2(lib, 2, 4, 3, 40, [4, 2], [2, 0], False)),  # small V, separate output, ragged
+    ("rnnt_grad_v2_wide_in_place", lambda lib: check_rnnt_grad_v2(lib, 1, 3, 2, 1500, [3], [1], True)),  # V > 1024: 8 float4 per lane and half
     ("conv1_v2_even", lambda lib: check_conv1_v2(lib, 2, 22, 16, 24)),
     ("conv1_v2_odd", lambda lib: check_conv1_v2(lib, 2, 37, 13, 16)),  # odd T and F, T1 not a multiple of the rows per CTA
     ("conv1_v2_tiny", lambda lib: check_conv1_v2(lib, 1, 1, 1, 8)),

@@ -39,6 +39,10 @@ struct dim3 {
 struct float2 {
   float x, y;
 };
+struct alignas(8) uint2 {
+  uint32_t x, y;
+};
+inline uint2 make_uint2(uint32_t x, uint32_t y) { return {x, y}; }
 struct alignas(16) float4 {
   float x, y, z, w;
 };

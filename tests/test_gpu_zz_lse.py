@@ -81,3 +81,35 @@ def test_conv1_v2_matches_first_generation_kernels():
             ops.set_conv1_v2(False)
         assert (res[True][0] - res[False][0]).abs().max().item() <= 1e-2 * res[False][0].abs().max().item()
         assert (res[True][1] - res[False][1]).abs().max().item() <= 2e-3 * res[False][1].abs().max().item() + 1e-6
+
+
+def test_rnnt_grad_v2_matches_first_generation_kernel():
+    """csrc/rnnt_grad_v2.cu (opt-in, TFASR_RNNT_GRAD_V2) against tfasr_rnnt_loss_bwd_bf16 through the training head: same costs, same
+    gradients (in-place bf16 over the logits) incl. the vocab-bias gradient; also with the fused log-sum-exp forward."""
+    from tensorflowasr_b200 import fused, ops
+
+    torch.manual_seed(7)
+    B, T, U1, J, V = 4, 41, 11, 64, 1000
+    e = (torch.randn(B, T, J, device="cuda") * 0.5).to(torch.bfloat16)
+    p = (torch.randn(B, U1, J, device="cuda") * 0.5).to(torch.bfloat16)
+    labels = torch.randint(1, V, (B, U1 - 1), device="cuda", dtype=torch.int32)
+    tl = torch.tensor([41, 30, 7, 1], device="cuda", dtype=torch.int32)
+    ul = torch.tensor([10, 4, 0, 2], device="cuda", dtype=torch.int32)
+    res = {}
+    try:
+        for key, (g2, lse) in {"base": (False, False), "grad_v2": (True, False), "both": (True, True)}.items():
+            ops.set_rnnt_grad_v2(g2)
+            ops.set_fused_lse(lse)
+            w = torch.nn.Parameter((torch.randn(J, V, generator=torch.Generator().manual_seed(5)) / J ** 0.5).cuda())
+            bvec = torch.nn.Parameter(torch.randn(V, generator=torch.Generator().manual_seed(6)).cuda() * 0.1)
+            er, pr = e.clone().requires_grad_(True), p.clone().requires_grad_(True)
+            costs = fused.transducer_head(er, pr, fused.WeightPack(w, bvec), labels, tl, ul)
+            (costs * torch.tensor([1.0, 0.5, 2.0, 1.5], device="cuda")).sum().backward()
+            res[key] = (costs.detach().clone(), er.grad.clone(), pr.grad.clone(), w.grad.clone(), bvec.grad.clone())
+    finally:
+        ops.set_rnnt_grad_v2(False)
+        ops.set_fused_lse(False)
+    for key in ("grad_v2", "both"):
+        torch.testing.assert_close(res[key][0], res["base"][0], rtol=1e-5, atol=1e-4)
+        for a, b in zip(res[key][1:], res["base"][1:]):
+            assert (a.float() - b.float()).abs().max().item() <= 2e-3 * (b.float().abs().max().item() + 1e-6), key

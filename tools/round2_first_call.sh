@@ -25,3 +25,6 @@ TFASR_FUSED_LSE=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-bas
 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 # 5. second-generation conv1 kernels (csrc/conv1.cu) in the headline step
 TFASR_CONV1_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_conv1_v2.json 2> gpurun_out/bench_conv1_v2.err
+# 6. second-generation RNN-T gradient kernel, alone and together with the fused log-sum-exp and conv1 v2 (the candidate new default)
+TFASR_RNNT_GRAD_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_rnnt_grad_v2.json 2> gpurun_out/bench_rnnt_grad_v2.err
+TFASR_RNNT_GRAD_V2=1 TFASR_FUSED_LSE=1 TFASR_CONV1_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_all_v2.json 2> gpurun_out/bench_all_v2.err
