@@ -196,6 +196,10 @@ int tfasr_glu_bwd(const void* aux, const void* dg, void* daux, float* colsum, in
  * ---------------------------------------------------------------------------------------------- */
 int tfasr_joint_tanh_fwd(const void* e, const void* p, void* h, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream);
 int tfasr_joint_reduce_bwd(const void* dz, float* de, float* dp, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream);
+/* second generation of the two (csrc/joint_v2.cu: 16-byte accesses, column vector fixed per thread, de reduced by warp shuffles — no CTA
+ * barrier in the frame loop); same contracts (J % 8 == 0, U1 <= 72 for the reduction).  Opt-in until measured on a B200. */
+int tfasr_joint_tanh_fwd_v2(const void* e, const void* p, void* h, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream);
+int tfasr_joint_reduce_bwd_v2(const void* dz, float* de, float* dp, int32_t B, int32_t T, int32_t U1, int32_t J, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Relative-position multi-head self-attention core (multihead_attention.py:543-582; rel_left_shift :27-64 as index arithmetic;

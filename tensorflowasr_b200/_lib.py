@@ -81,6 +81,8 @@ SIGNATURES = {
                                               c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tfasr_joint_tanh_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_joint_reduce_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_joint_tanh_fwd_v2": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_joint_reduce_bwd_v2": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_conv1_3x3s2_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_conv1_3x3s2_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_conv1_3x3s2_fwd_v2": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -109,13 +109,20 @@ def glu_bwd(aux, dg, colsum=None):
     return daux
 
 
+def _joint_v2(U1, J):
+    from . import ops
+
+    return ops.joint_v2_active() and J % 8 == 0 and J <= 4096 and U1 <= 72
+
+
 def joint_tanh_fwd(e, p):
     """e [B,T,J], p [B,U1,J] (bf16) -> h [B,T,U1,J] bf16 = tanh(e[:, :, None] + p[:, None])."""
     lib = _lib.load()
     B, T, J = e.shape
     U1 = p.shape[1]
     h = torch.empty((B, T, U1, J), dtype=torch.bfloat16, device=e.device)
-    _lib.check(lib.tfasr_joint_tanh_fwd(_lib.ptr(e), _lib.ptr(p), _lib.ptr(h), B, T, U1, J, _lib.stream_ptr(e.device)), "tfasr_joint_tanh_fwd")
+    fn, name = (lib.tfasr_joint_tanh_fwd_v2, "tfasr_joint_tanh_fwd_v2") if _joint_v2(U1, J) else (lib.tfasr_joint_tanh_fwd, "tfasr_joint_tanh_fwd")
+    _lib.check(fn(_lib.ptr(e), _lib.ptr(p), _lib.ptr(h), B, T, U1, J, _lib.stream_ptr(e.device)), name)
     return h
 
 
@@ -125,7 +132,8 @@ def joint_reduce_bwd(dz):
     B, T, U1, J = dz.shape
     de = torch.empty((B, T, J), dtype=torch.float32, device=dz.device)
     dp = torch.zeros((B, U1, J), dtype=torch.float32, device=dz.device)
-    _lib.check(lib.tfasr_joint_reduce_bwd(_lib.ptr(dz), _lib.ptr(de), _lib.ptr(dp), B, T, U1, J, _lib.stream_ptr(dz.device)), "tfasr_joint_reduce_bwd")
+    fn, name = (lib.tfasr_joint_reduce_bwd_v2, "tfasr_joint_reduce_bwd_v2") if _joint_v2(U1, J) else (lib.tfasr_joint_reduce_bwd, "tfasr_joint_reduce_bwd")
+    _lib.check(fn(_lib.ptr(dz), _lib.ptr(de), _lib.ptr(dp), B, T, U1, J, _lib.stream_ptr(dz.device)), name)
     return de, dp
 
 

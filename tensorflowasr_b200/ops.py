@@ -66,6 +66,20 @@ def fused_seq_active(x) -> bool:
     return _FUSED_SEQ and fused_active(x)
 
 
+_JOINT_V2 = _os.environ.get("TFASR_JOINT_V2", "0") == "1"
+
+
+def set_joint_v2(flag: bool):
+    """Training head: tanh(e + p) and the de / dp reductions on the second-generation kernels (csrc/joint_v2.cu).  Off by default until
+    measured on a B200."""
+    global _JOINT_V2
+    _JOINT_V2 = bool(flag)
+
+
+def joint_v2_active() -> bool:
+    return _JOINT_V2
+
+
 _RNNT_GRAD_V2 = _os.environ.get("TFASR_RNNT_GRAD_V2", "0") == "1"
 
 

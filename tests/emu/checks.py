@@ -32,7 +32,7 @@ def load(asan=False):
     import build_emu
 
     lib = ctypes.CDLL(build_emu.build(asan=asan))
-    for name in ("tfasr_greedy_decode_f32", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+    for name in ("tfasr_greedy_decode_f32", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
     return lib
@@ -599,6 +599,27 @@ def check_rnnt_grad_v2(lib, B, T, U1, V, logit_len, label_len, in_place, seed=14
     close(db - dbias0, rbf(g_ref.astype(np.float32)).astype(np.float64).sum((0, 1, 2)), 2e-3, "vocab bias gradient")
 
 
+# ------------------------------------------------------------------------------------------------ joint elementwise / reduction, v2
+def check_joint_v2(lib, B, T, U1, J, seed=15):
+    rng = np.random.default_rng(seed)
+    e = rbf(rng.standard_normal((B, T, J)))
+    p = rbf(rng.standard_normal((B, U1, J)))
+    h_ref = np.tanh(e[:, :, None, :].astype(np.float64) + p[:, None, :, :])
+    eb, ep = heap(to_bf16(e))
+    pb, pp = heap(to_bf16(p))
+    hb, hp = heap(np.zeros((B, T, U1, J), np.uint16))
+    assert lib.tfasr_joint_tanh_fwd_v2(ep, pp, hp, B, T, U1, J, None) == 0
+    close(from_bf16(hb), h_ref, 5e-3, f"joint tanh v2 {(B, T, U1, J)}")
+    dz = rbf(rng.standard_normal((B, T, U1, J)))
+    dzb, dzp = heap(to_bf16(dz))
+    deb, dep = heap(np.full((B, T, J), np.nan, np.float32))
+    init = rng.standard_normal((B, U1, J)).astype(np.float32)
+    dpb, dpp = heap(init)
+    assert lib.tfasr_joint_reduce_bwd_v2(dzp, dep, dpp, B, T, U1, J, None) == 0
+    close(deb, dz.astype(np.float64).sum(2), 1e-5, "joint reduce v2 de")
+    close(dpb - init, dz.astype(np.float64).sum(1), 1e-4, "joint reduce v2 dp")
+
+
 # ------------------------------------------------------------------------------------------------ first conv of the subsampling, v2
 def check_conv1_v2(lib, B, T, F, C, seed=13):
     rng = np.random.default_rng(seed)
@@ -669,6 +690,9 @@ CASES = [
     ("rnnt_grad_v2_in_place", lambda lib: check_rnnt_grad_v2(lib, 3, 5, 4, 1000, [5, 3, 0], [3, 1, 2], True)),  # V = 1000: 4 float4 per lane and half
     ("rnnt_grad_v2_pitched", lambda lib: check_rnnt_grad_v2(lib, 2, 4, 3, 40, [4, 2], [2, 0], False)),  # small V, separate output, ragged
     ("rnnt_grad_v2_wide_in_place", lambda lib: check_rnnt_grad_v2(lib, 1, 3, 2, 1500, [3], [1], True)),  # V > 1024: 8 float4 per lane and half
+    ("joint_v2", lambda lib: check_joint_v2(lib, 2, 7, 11, 40)),  # JV = 5: a warp's 4 column vectors straddle the end
+    ("joint_v2_wide", lambda lib: check_joint_v2(lib, 1, 3, 65, 320)),  # the Conformer-S lattice width: U1 = 65, J = 320
+    ("joint_v2_tiny", lambda lib: check_joint_v2(lib, 3, 1, 1, 8)),
     ("conv1_v2_even", lambda lib: check_conv1_v2(lib, 2, 22, 16, 24)),
     ("conv1_v2_odd", lambda lib: check_conv1_v2(lib, 2, 37, 13, 16)),  # odd T and F, T1 not a multiple of the rows per CTA
     ("conv1_v2_tiny", lambda lib: check_conv1_v2(lib, 1, 1, 1, 8)),

@@ -184,6 +184,12 @@ template <class T>
 inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl(v, src); }
 
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
+inline void atomicAdd(float4* p, float4 v) {  // red.global.add.v4.f32: four independent float adds
+  atomicAdd(&p->x, v.x);
+  atomicAdd(&p->y, v.y);
+  atomicAdd(&p->z, v.z);
+  atomicAdd(&p->w, v.w);
+}
 inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_relaxed); }
 
 // dynamic shared memory: kernels declare it with TFASR_DYN_SMEM(name)

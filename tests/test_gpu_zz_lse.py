@@ -113,3 +113,26 @@ def test_rnnt_grad_v2_matches_first_generation_kernel():
         torch.testing.assert_close(res[key][0], res["base"][0], rtol=1e-5, atol=1e-4)
         for a, b in zip(res[key][1:], res["base"][1:]):
             assert (a.float() - b.float()).abs().max().item() <= 2e-3 * (b.float().abs().max().item() + 1e-6), key
+
+
+def test_joint_v2_matches_first_generation_kernels():
+    """csrc/joint_v2.cu (opt-in, TFASR_JOINT_V2) against joint.cu: identical contracts."""
+    from tensorflowasr_b200 import kernels, ops
+
+    torch.manual_seed(8)
+    for (B, T, U1, J) in [(4, 250, 65, 320), (2, 7, 11, 40), (3, 1, 1, 8)]:
+        e = torch.randn(B, T, J, device="cuda").to(torch.bfloat16)
+        p = torch.randn(B, U1, J, device="cuda").to(torch.bfloat16)
+        dz = torch.randn(B, T, U1, J, device="cuda").to(torch.bfloat16)
+        res = {}
+        try:
+            for flag in (False, True):
+                ops.set_joint_v2(flag)
+                res[flag] = (kernels.joint_tanh_fwd(e, p).float(),) + tuple(kernels.joint_reduce_bwd(dz))
+        finally:
+            ops.set_joint_v2(False)
+        ref_h = torch.tanh(e.float()[:, :, None, :] + p.float()[:, None, :, :])
+        assert (res[True][0] - ref_h).abs().max().item() <= 1e-2
+        assert (res[True][0] - res[False][0]).abs().max().item() <= 1e-2
+        torch.testing.assert_close(res[True][1], dz.float().sum(2), rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(res[True][2], dz.float().sum(1), rtol=1e-4, atol=1e-3)
