@@ -235,6 +235,10 @@ int tfasr_conv1_3x3s2_wgrad(const float* x, const void* dy, float* dw, int32_t B
 int tfasr_conv1_3x3s2_fwd_v2(const float* x, const float* w, const float* bias, void* y, int32_t B, int32_t T, int32_t F, int32_t C,
                              tfasr_stream_t stream);
 int tfasr_conv1_3x3s2_wgrad_v2(const float* x, const void* dy, float* dw, int32_t B, int32_t T, int32_t F, int32_t C, tfasr_stream_t stream);
+/* second generation of im2col_3x3s2 / col2im_3x3s2 (csrc/subsample_v2.cu: one CTA per output / input row, 32-bit indexing, 16-byte accesses);
+ * same contracts.  Opt-in until measured on a B200. */
+int tfasr_im2col_3x3s2_v2(const void* a, void* col, int32_t B, int32_t T1, int32_t F1, int32_t C, tfasr_stream_t stream);
+int tfasr_col2im_3x3s2_v2(const void* dcol, void* da, int32_t B, int32_t T1, int32_t F1, int32_t C, tfasr_stream_t stream);
 int tfasr_im2col_3x3s2(const void* a, void* col, int32_t B, int32_t T1, int32_t F1, int32_t C, tfasr_stream_t stream);
 int tfasr_col2im_3x3s2(const void* dcol, void* da, int32_t B, int32_t T1, int32_t F1, int32_t C, tfasr_stream_t stream);
 int tfasr_bn_stats(const void* x, float* sums, int64_t R, int32_t C, tfasr_stream_t stream);

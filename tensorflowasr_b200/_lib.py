@@ -87,6 +87,8 @@ SIGNATURES = {
     "tfasr_conv1_3x3s2_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_conv1_3x3s2_fwd_v2": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_conv1_3x3s2_wgrad_v2": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_im2col_3x3s2_v2": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "tfasr_col2im_3x3s2_v2": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_im2col_3x3s2": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_col2im_3x3s2": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_bn_stats": (c_int32, [c_void_p, c_void_p, ctypes.c_int64, c_int32, c_void_p]),

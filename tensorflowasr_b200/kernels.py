@@ -167,13 +167,20 @@ def conv1_wgrad(x, dy, dw):
     _lib.check(fn(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), B, T, F, C, _st(x)), name)
 
 
+def _im2col_v2(C):
+    from . import ops
+
+    return ops.im2col_v2_active() and C % 8 == 0 and C <= 4096
+
+
 def im2col(a):
     """a [B,T1,F1,C] bf16 -> col [B*T2*F2, 9C]."""
     lib = _lib.load()
     B, T1, F1, C = a.shape
     T2, F2 = (T1 + 1) // 2, (F1 + 1) // 2
     col = torch.empty((B * T2 * F2, 9 * C), dtype=torch.bfloat16, device=a.device)
-    _lib.check(lib.tfasr_im2col_3x3s2(_lib.ptr(a), _lib.ptr(col), B, T1, F1, C, _st(a)), "tfasr_im2col_3x3s2")
+    fn, name = (lib.tfasr_im2col_3x3s2_v2, "tfasr_im2col_3x3s2_v2") if _im2col_v2(C) else (lib.tfasr_im2col_3x3s2, "tfasr_im2col_3x3s2")
+    _lib.check(fn(_lib.ptr(a), _lib.ptr(col), B, T1, F1, C, _st(a)), name)
     return col
 
 
@@ -181,7 +188,8 @@ def col2im(dcol, shape):
     lib = _lib.load()
     B, T1, F1, C = shape
     da = torch.empty(shape, dtype=torch.bfloat16, device=dcol.device)
-    _lib.check(lib.tfasr_col2im_3x3s2(_lib.ptr(dcol), _lib.ptr(da), B, T1, F1, C, _st(dcol)), "tfasr_col2im_3x3s2")
+    fn, name = (lib.tfasr_col2im_3x3s2_v2, "tfasr_col2im_3x3s2_v2") if _im2col_v2(C) else (lib.tfasr_col2im_3x3s2, "tfasr_col2im_3x3s2")
+    _lib.check(fn(_lib.ptr(dcol), _lib.ptr(da), B, T1, F1, C, _st(dcol)), name)
     return da
 
 

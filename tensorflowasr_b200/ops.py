@@ -66,6 +66,20 @@ def fused_seq_active(x) -> bool:
     return _FUSED_SEQ and fused_active(x)
 
 
+_IM2COL_V2 = _os.environ.get("TFASR_IM2COL_V2", "0") == "1"
+
+
+def set_im2col_v2(flag: bool):
+    """Conv2dSubsampling's second conv: im2col / col2im on the second-generation kernels (csrc/subsample_v2.cu).  Off by default until
+    measured on a B200."""
+    global _IM2COL_V2
+    _IM2COL_V2 = bool(flag)
+
+
+def im2col_v2_active() -> bool:
+    return _IM2COL_V2
+
+
 _JOINT_V2 = _os.environ.get("TFASR_JOINT_V2", "0") == "1"
 
 

@@ -32,7 +32,7 @@ def load(asan=False):
     import build_emu
 
     lib = ctypes.CDLL(build_emu.build(asan=asan))
-    for name in ("tfasr_greedy_decode_f32", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+    for name in ("tfasr_greedy_decode_f32", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
     return lib
@@ -620,6 +620,36 @@ def check_joint_v2(lib, B, T, U1, J, seed=15):
     close(dpb - init, dz.astype(np.float64).sum(1), 1e-4, "joint reduce v2 dp")
 
 
+# ------------------------------------------------------------------------------------------------ im2col / col2im (3x3 s2 causal), v2
+def check_im2col_v2(lib, B, T1, F1, C, seed=16):
+    rng = np.random.default_rng(seed)
+    g = conv_geom(B, T1, F1, C, 3, 3, 2, 2, "causal")
+    assert (g.To, g.Fo, g.Kp) == ((T1 + 1) // 2, (F1 + 1) // 2, 9 * C)
+    a = rbf(rng.standard_normal((B, T1, F1, C)))
+    ref = im2col_ref(a.astype(np.float64), g)
+    ab, ap = heap(to_bf16(a))
+    cb, cp = heap(np.full((B * g.To * g.Fo, 9 * C), 0x7FC0, np.uint16))
+    assert lib.tfasr_im2col_3x3s2_v2(ap, cp, B, T1, F1, C, None) == 0
+    got = from_bf16(cb).reshape(ref.shape)
+    assert np.isfinite(got).all() and np.array_equal(got.astype(np.float64), ref), "im2col v2 (exact copy expected)"
+    dcol = rbf(rng.standard_normal(ref.shape))
+    da_ref = np.zeros((B, T1, F1, C))
+    for i in range(3):
+        for j in range(3):
+            for to in range(g.To):
+                t = 2 * to - 2 + i
+                if t < 0 or t >= T1:
+                    continue
+                for fo in range(g.Fo):
+                    f = 2 * fo - 2 + j
+                    if 0 <= f < F1:
+                        da_ref[:, t, f, :] += dcol[:, to, fo, (i * 3 + j) * C:(i * 3 + j + 1) * C]
+    db, dp = heap(to_bf16(dcol))
+    ob, op = heap(np.full((B, T1, F1, C), 0x7FC0, np.uint16))
+    assert lib.tfasr_col2im_3x3s2_v2(dp, op, B, T1, F1, C, None) == 0
+    close(from_bf16(ob), da_ref, 5e-3, f"col2im v2 {(B, T1, F1, C)}")
+
+
 # ------------------------------------------------------------------------------------------------ first conv of the subsampling, v2
 def check_conv1_v2(lib, B, T, F, C, seed=13):
     rng = np.random.default_rng(seed)
@@ -693,6 +723,9 @@ CASES = [
     ("joint_v2", lambda lib: check_joint_v2(lib, 2, 7, 11, 40)),  # JV = 5: a warp's 4 column vectors straddle the end
     ("joint_v2_wide", lambda lib: check_joint_v2(lib, 1, 3, 65, 320)),  # the Conformer-S lattice width: U1 = 65, J = 320
     ("joint_v2_tiny", lambda lib: check_joint_v2(lib, 3, 1, 1, 8)),
+    ("im2col_v2", lambda lib: check_im2col_v2(lib, 2, 10, 8, 16)),
+    ("im2col_v2_odd", lambda lib: check_im2col_v2(lib, 1, 7, 5, 24)),
+    ("im2col_v2_tiny", lambda lib: check_im2col_v2(lib, 2, 1, 1, 8)),
     ("conv1_v2_even", lambda lib: check_conv1_v2(lib, 2, 22, 16, 24)),
     ("conv1_v2_odd", lambda lib: check_conv1_v2(lib, 2, 37, 13, 16)),  # odd T and F, T1 not a multiple of the rows per CTA
     ("conv1_v2_tiny", lambda lib: check_conv1_v2(lib, 1, 1, 1, 8)),

@@ -136,3 +136,23 @@ def test_joint_v2_matches_first_generation_kernels():
         assert (res[True][0] - res[False][0]).abs().max().item() <= 1e-2
         torch.testing.assert_close(res[True][1], dz.float().sum(2), rtol=1e-4, atol=1e-3)
         torch.testing.assert_close(res[True][2], dz.float().sum(1), rtol=1e-4, atol=1e-3)
+
+
+def test_im2col_v2_matches_first_generation_kernels():
+    """csrc/subsample_v2.cu (opt-in, TFASR_IM2COL_V2) against conv_bn.cu's im2col / col2im: identical contracts (bit-exact copy / same sums)."""
+    from tensorflowasr_b200 import kernels, ops
+
+    torch.manual_seed(9)
+    for (B, T1, F1, C) in [(4, 500, 40, 144), (2, 7, 5, 24), (1, 1, 1, 8)]:
+        a = torch.randn(B, T1, F1, C, device="cuda").to(torch.bfloat16)
+        res = {}
+        try:
+            for flag in (False, True):
+                ops.set_im2col_v2(flag)
+                col = kernels.im2col(a)
+                dcol = torch.randn(col.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)).to(torch.bfloat16)
+                res[flag] = (col, kernels.col2im(dcol, (B, T1, F1, C)).float())
+        finally:
+            ops.set_im2col_v2(False)
+        assert torch.equal(res[True][0], res[False][0])
+        assert (res[True][1] - res[False][1]).abs().max().item() <= 1e-2 * (res[False][1].abs().max().item() + 1e-6)

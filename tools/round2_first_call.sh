@@ -28,4 +28,5 @@ TFASR_CONV1_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-base
 # 6. second-generation RNN-T gradient kernel, alone and together with the fused log-sum-exp and conv1 v2 (the candidate new default)
 TFASR_RNNT_GRAD_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_rnnt_grad_v2.json 2> gpurun_out/bench_rnnt_grad_v2.err
 TFASR_JOINT_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_joint_v2.json 2> gpurun_out/bench_joint_v2.err
-TFASR_RNNT_GRAD_V2=1 TFASR_FUSED_LSE=1 TFASR_CONV1_V2=1 TFASR_JOINT_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_all_v2.json 2> gpurun_out/bench_all_v2.err
+TFASR_IM2COL_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_im2col_v2.json 2> gpurun_out/bench_im2col_v2.err
+TFASR_RNNT_GRAD_V2=1 TFASR_FUSED_LSE=1 TFASR_CONV1_V2=1 TFASR_JOINT_V2=1 TFASR_IM2COL_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_all_v2.json 2> gpurun_out/bench_all_v2.err
