@@ -300,6 +300,12 @@ int tfasr_dwconv_causal_fwd(const void* x, const float* w, const float* bias, vo
                             tfasr_stream_t stream);
 int tfasr_dwconv_causal_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, float* dbias, int32_t B, int32_t T, int32_t C,
                             int32_t K, tfasr_stream_t stream);
+/* the two halves separately: bwd_dx = the data gradient of tfasr_dwconv_causal_bwd alone; wgrad_v2 (csrc/dwconv_wgrad_v2.cu) = the weight /
+ * bias gradient with one thread per (tap, channel pair) walking the frames from L1/L2 (no SMEM staging, no barriers).  Opt-in pair until
+ * measured on a B200. */
+int tfasr_dwconv_causal_bwd_dx(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t K, tfasr_stream_t stream);
+int tfasr_dwconv_causal_wgrad_v2(const void* dy, const void* x, float* dw, float* dbias, int32_t B, int32_t T, int32_t C, int32_t K,
+                                 tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SpecAugment on the features, in place (augmentations/augmentation.py:67-90, methods/specaugment.py:58-137): n_freq frequency masks

@@ -251,3 +251,26 @@ extern "C" int tfasr_dwconv_causal_bwd(const void* dy, const void* x, const floa
   count_launch();
   return check_launch();
 }
+
+// Data gradient alone (the weight / bias gradient then comes from tfasr_dwconv_causal_wgrad_v2, dwconv_wgrad_v2.cu).
+extern "C" int tfasr_dwconv_causal_bwd_dx(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t K, tfasr_stream_t stream_) {
+  dim3 block;
+  size_t sf, sw;
+  if (!dy || !w || !dx || B < 0 || T < 1 || B > 65535) return TFASR_INVALID_VALUE;
+  int st = dw_cfg(C, K, block, sf, sw);
+  if (st) return st;
+  if (B == 0) return TFASR_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  dim3 grid((unsigned)ceil_div(T, kDwTT), B);
+  if (K == 31 && block.x * block.y <= 640) {
+    const size_t smem = (size_t)(kDwTT + K - 1) * C * 2;
+    if (cudaFuncSetAttribute(dwconv_sliding_kernel<31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return TFASR_EXECUTION_FAILED;
+    dwconv_sliding_kernel<31, true><<<grid, block, smem, stream>>>(static_cast<const __nv_bfloat16*>(dy), w, nullptr, static_cast<__nv_bfloat16*>(dx), T, C);
+  } else {
+    if (cudaFuncSetAttribute(dwconv_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return TFASR_EXECUTION_FAILED;
+    dwconv_bwd_data_kernel<<<grid, block, sf, stream>>>(static_cast<const __nv_bfloat16*>(dy), w, static_cast<__nv_bfloat16*>(dx), T, C, K);
+  }
+  count_launch();
+  return check_launch();
+}

@@ -287,6 +287,13 @@ def dwconv_bwd(dy, x, w, dw, dbias=None):
     lib = _lib.load()
     B, T, C = x.shape
     dx = torch.empty_like(x)
+    from . import ops
+
+    if ops.dwconv_wgrad_v2_active():
+        _lib.check(lib.tfasr_dwconv_causal_bwd_dx(_lib.ptr(dy), _lib.ptr(w), _lib.ptr(dx), B, T, C, w.shape[0], _st(x)), "tfasr_dwconv_causal_bwd_dx")
+        _lib.check(lib.tfasr_dwconv_causal_wgrad_v2(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), _lib.ptr(dbias), B, T, C, w.shape[0], _st(x)),
+                   "tfasr_dwconv_causal_wgrad_v2")
+        return dx
     _lib.check(lib.tfasr_dwconv_causal_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(w), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(dbias), B, T, C, w.shape[0],
                                            _st(x)), "tfasr_dwconv_causal_bwd")
     return dx

@@ -66,6 +66,20 @@ def fused_seq_active(x) -> bool:
     return _FUSED_SEQ and fused_active(x)
 
 
+_DWCONV_WGRAD_V2 = _os.environ.get("TFASR_DWCONV_WGRAD_V2", "0") == "1"
+
+
+def set_dwconv_wgrad_v2(flag: bool):
+    """ConvModule backward: depthwise weight gradient on the second-generation kernel (csrc/dwconv_wgrad_v2.cu).  Off by default until
+    measured on a B200."""
+    global _DWCONV_WGRAD_V2
+    _DWCONV_WGRAD_V2 = bool(flag)
+
+
+def dwconv_wgrad_v2_active() -> bool:
+    return _DWCONV_WGRAD_V2
+
+
 _IM2COL_V2 = _os.environ.get("TFASR_IM2COL_V2", "0") == "1"
 
 

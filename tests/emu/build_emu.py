@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(REPO, "tensorflowasr_b200", "csrc")
 OUT = os.path.join(REPO, "build", "emu")
-SOURCES = ["seqconv.cu", "decode.cu", "rnnt_combine.cu", "conv1.cu", "rnnt_grad_v2.cu", "joint_v2.cu", "subsample_v2.cu"]  # launcher files written against simt.cuh
+SOURCES = ["seqconv.cu", "decode.cu", "rnnt_combine.cu", "conv1.cu", "rnnt_grad_v2.cu", "joint_v2.cu", "subsample_v2.cu", "dwconv_wgrad_v2.cu"]  # launcher files written against simt.cuh
 
 
 def build(asan: bool = False) -> str:
@@ -22,7 +22,7 @@ def build(asan: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, "libtfasr_emu_asan.so" if asan else "libtfasr_emu.so")
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "simt.cuh"), os.path.join(CSRC, "seqconv_kernels.cuh"), os.path.join(CSRC, "decode_kernels.cuh"), os.path.join(CSRC, "rnnt_combine.cu"), os.path.join(CSRC, "conv1.cu"), os.path.join(CSRC, "rnnt_grad_v2.cu"), os.path.join(CSRC, "joint_v2.cu"), os.path.join(CSRC, "subsample_v2.cu"), os.path.join(HERE, "cuda_emu.h"),
+    deps = srcs + [os.path.join(CSRC, "simt.cuh"), os.path.join(CSRC, "seqconv_kernels.cuh"), os.path.join(CSRC, "decode_kernels.cuh"), os.path.join(CSRC, "rnnt_combine.cu"), os.path.join(CSRC, "conv1.cu"), os.path.join(CSRC, "rnnt_grad_v2.cu"), os.path.join(CSRC, "joint_v2.cu"), os.path.join(CSRC, "subsample_v2.cu"), os.path.join(CSRC, "dwconv_wgrad_v2.cu"), os.path.join(HERE, "cuda_emu.h"),
                    os.path.join(REPO, "include", "tfasr_b200.h"), os.path.abspath(__file__)]
     if os.path.exists(lib) and os.path.getmtime(lib) >= max(os.path.getmtime(d) for d in deps):
         return lib

@@ -32,7 +32,7 @@ def load(asan=False):
     import build_emu
 
     lib = ctypes.CDLL(build_emu.build(asan=asan))
-    for name in ("tfasr_greedy_decode_f32", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+    for name in ("tfasr_greedy_decode_f32", "tfasr_dwconv_causal_wgrad_v2", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
     return lib
@@ -650,6 +650,27 @@ def check_im2col_v2(lib, B, T1, F1, C, seed=16):
     close(from_bf16(ob), da_ref, 5e-3, f"col2im v2 {(B, T1, F1, C)}")
 
 
+# ------------------------------------------------------------------------------------------------ ConvModule depthwise weight gradient, v2
+def check_dwconv_wgrad_v2(lib, B, T, C, K, with_bias, seed=17):
+    rng = np.random.default_rng(seed)
+    x = rbf(rng.standard_normal((B, T, C)))
+    dy = rbf(rng.standard_normal((B, T, C)))
+    xp = np.concatenate([np.zeros((B, K - 1, C)), x.astype(np.float64)], 1)
+    dw_ref = np.stack([(dy.astype(np.float64) * xp[:, k:k + T]).sum((0, 1)) for k in range(K)])
+    xb, xp_ = heap(to_bf16(x))
+    db, dp = heap(to_bf16(dy))
+    init = rng.standard_normal((K, C)).astype(np.float32)
+    wb, wp = heap(init)
+    binit = rng.standard_normal(C).astype(np.float32)
+    bb, bp = heap(binit)
+    assert lib.tfasr_dwconv_causal_wgrad_v2(dp, xp_, wp, bp if with_bias else None, B, T, C, K, None) == 0
+    close(wb - init, dw_ref, 2e-4, f"dwconv wgrad v2 {(B, T, C, K)}")
+    if with_bias:
+        close(bb - binit, dy.astype(np.float64).sum((0, 1)), 2e-4, "dwconv dbias v2")
+    else:
+        assert np.array_equal(bb, binit)
+
+
 # ------------------------------------------------------------------------------------------------ first conv of the subsampling, v2
 def check_conv1_v2(lib, B, T, F, C, seed=13):
     rng = np.random.default_rng(seed)
@@ -726,6 +747,9 @@ CASES = [
     ("im2col_v2", lambda lib: check_im2col_v2(lib, 2, 10, 8, 16)),
     ("im2col_v2_odd", lambda lib: check_im2col_v2(lib, 1, 7, 5, 24)),
     ("im2col_v2_tiny", lambda lib: check_im2col_v2(lib, 2, 1, 1, 8)),
+    ("dwconv_wgrad_v2_k31", lambda lib: check_dwconv_wgrad_v2(lib, 2, 70, 16, 31, False)),
+    ("dwconv_wgrad_v2_bias", lambda lib: check_dwconv_wgrad_v2(lib, 3, 37, 24, 5, True)),  # K + 1 rows: the bias row shares the last tap group
+    ("dwconv_wgrad_v2_short", lambda lib: check_dwconv_wgrad_v2(lib, 1, 3, 8, 7, True)),  # T < K: most taps only ever see padding
     ("conv1_v2_even", lambda lib: check_conv1_v2(lib, 2, 22, 16, 24)),
     ("conv1_v2_odd", lambda lib: check_conv1_v2(lib, 2, 37, 13, 16)),  # odd T and F, T1 not a multiple of the rows per CTA
     ("conv1_v2_tiny", lambda lib: check_conv1_v2(lib, 1, 1, 1, 8)),

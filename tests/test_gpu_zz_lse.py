@@ -156,3 +156,26 @@ def test_im2col_v2_matches_first_generation_kernels():
             ops.set_im2col_v2(False)
         assert torch.equal(res[True][0], res[False][0])
         assert (res[True][1] - res[False][1]).abs().max().item() <= 1e-2 * (res[False][1].abs().max().item() + 1e-6)
+
+
+def test_dwconv_wgrad_v2_matches_first_generation_kernel():
+    """csrc/dwconv_wgrad_v2.cu + tfasr_dwconv_causal_bwd_dx (opt-in, TFASR_DWCONV_WGRAD_V2) against tfasr_dwconv_causal_bwd."""
+    from tensorflowasr_b200 import kernels, ops
+
+    torch.manual_seed(10)
+    for (B, T, C, K) in [(32, 250, 144, 31), (3, 37, 24, 5), (1, 3, 8, 7)]:
+        x = torch.randn(B, T, C, device="cuda").to(torch.bfloat16)
+        dy = torch.randn(B, T, C, device="cuda").to(torch.bfloat16)
+        w = torch.randn(K, C, device="cuda") * 0.2
+        res = {}
+        try:
+            for flag in (False, True):
+                ops.set_dwconv_wgrad_v2(flag)
+                dw, db = torch.zeros(K, C, device="cuda"), torch.zeros(C, device="cuda")
+                dx = kernels.dwconv_bwd(dy, x, w, dw, db)
+                res[flag] = (dx.float(), dw, db)
+        finally:
+            ops.set_dwconv_wgrad_v2(False)
+        assert torch.equal(res[True][0], res[False][0])
+        for i in (1, 2):
+            assert (res[True][i] - res[False][i]).abs().max().item() <= 2e-3 * (res[False][i].abs().max().item() + 1e-6)

@@ -29,4 +29,5 @@ TFASR_CONV1_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-base
 TFASR_RNNT_GRAD_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_rnnt_grad_v2.json 2> gpurun_out/bench_rnnt_grad_v2.err
 TFASR_JOINT_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_joint_v2.json 2> gpurun_out/bench_joint_v2.err
 TFASR_IM2COL_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_im2col_v2.json 2> gpurun_out/bench_im2col_v2.err
-TFASR_RNNT_GRAD_V2=1 TFASR_FUSED_LSE=1 TFASR_CONV1_V2=1 TFASR_JOINT_V2=1 TFASR_IM2COL_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_all_v2.json 2> gpurun_out/bench_all_v2.err
+TFASR_DWCONV_WGRAD_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_dwconv_wgrad_v2.json 2> gpurun_out/bench_dwconv_wgrad_v2.err
+TFASR_RNNT_GRAD_V2=1 TFASR_FUSED_LSE=1 TFASR_CONV1_V2=1 TFASR_JOINT_V2=1 TFASR_IM2COL_V2=1 TFASR_DWCONV_WGRAD_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_all_v2.json 2> gpurun_out/bench_all_v2.err
