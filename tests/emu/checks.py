@@ -701,6 +701,45 @@ def check_conv1_v2(lib, B, T, F, C, seed=13):
     close(dwb - init, dw_ref, 2e-4, f"conv1 v2 wgrad {(B, T, F, C)}")
 
 
+# ------------------------------------------------------------------------------------------------ random shapes
+
+def check_random_shapes(lib):
+    """Seeded sweep over odd shapes (lengths not a multiple of any tile, single frames, channel counts around the CTA splits): the edge cases
+    the fixed cases above do not name."""
+    rng = np.random.default_rng(2024)
+    for _ in range(6):
+        B, T, C8, K, s = int(rng.integers(1, 4)), int(rng.integers(1, 70)), int(rng.integers(1, 5)), int(rng.integers(1, 9)), int(rng.integers(1, 4))
+        check_dwconv(lib, B, T, 8 * C8, K, s, seed=int(rng.integers(1 << 30)))
+    for _ in range(4):
+        B, T, C8 = int(rng.integers(1, 4)), int(rng.integers(1, 50)), int(rng.integers(1, 6))
+        lengths = [int(x) for x in rng.integers(-2, T + 3, B)]
+        check_masked_mean(lib, B, T, 8 * C8, lengths, seed=int(rng.integers(1 << 30)))
+        check_se_apply(lib, B, T, 8 * C8, int(rng.integers(0, 3)), bool(rng.integers(0, 2)), [max(0, min(T, x)) for x in lengths],
+                              seed=int(rng.integers(1 << 30)))
+    for _ in range(5):
+        B, T, F, C8 = int(rng.integers(1, 3)), int(rng.integers(1, 30)), int(rng.integers(1, 20)), int(rng.integers(1, 4))
+        check_conv1_v2(lib, B, T, F, 8 * C8, seed=int(rng.integers(1 << 30)))
+        check_im2col_v2(lib, B, T, F, 8 * C8, seed=int(rng.integers(1 << 30)))
+    for _ in range(4):
+        B, T, U1, J8 = int(rng.integers(1, 3)), int(rng.integers(1, 9)), int(rng.integers(1, 20)), int(rng.integers(1, 7))
+        check_joint_v2(lib, B, T, U1, 8 * J8, seed=int(rng.integers(1 << 30)))
+    for _ in range(4):
+        B, T, C2, K = int(rng.integers(1, 4)), int(rng.integers(1, 45)), int(rng.integers(1, 20)), int(rng.integers(1, 34))
+        check_dwconv_wgrad_v2(lib, B, T, 2 * C2, K, bool(rng.integers(0, 2)), seed=int(rng.integers(1 << 30)))
+    for _ in range(4):
+        B, T, U1, V4 = int(rng.integers(1, 3)), int(rng.integers(1, 6)), int(rng.integers(1, 5)), int(rng.integers(1, 80))
+        tl = [int(x) for x in rng.integers(0, T + 1, B)]
+        ul = [int(x) for x in rng.integers(0, U1, B)]
+        check_rnnt_grad_v2(lib, B, T, U1, 4 * V4, tl, ul, bool(rng.integers(0, 2)), seed=int(rng.integers(1 << 30)))
+        check_rnnt_combine(lib, B, T, U1, 4 * V4, tl, ul, seed=int(rng.integers(1 << 30)))
+    for _ in range(4):
+        B, T, F, Cin = int(rng.integers(1, 3)), int(rng.integers(1, 14)), int(rng.integers(1, 14)), int(rng.choice([1, 3, 8, 16]))
+        kh, kw, sh, sw = (int(x) for x in rng.integers(1, 6, 4))
+        sh, sw = min(sh, 3), min(sw, 3)
+        check_conv_lowering(lib, B, T, F, Cin, kh, kw, sh, sw, str(rng.choice(["same", "causal"])), Cin == 1 and bool(rng.integers(0, 2)),
+                                   seed=int(rng.integers(1 << 30)))
+
+
 # ------------------------------------------------------------------------------------------------ error behaviour
 def check_invalid(lib):
     a, p = heap(np.zeros(64, np.float32))
@@ -753,6 +792,7 @@ CASES = [
     ("conv1_v2_even", lambda lib: check_conv1_v2(lib, 2, 22, 16, 24)),
     ("conv1_v2_odd", lambda lib: check_conv1_v2(lib, 2, 37, 13, 16)),  # odd T and F, T1 not a multiple of the rows per CTA
     ("conv1_v2_tiny", lambda lib: check_conv1_v2(lib, 1, 1, 1, 8)),
+    ("random_shapes", check_random_shapes),
     ("invalid_arguments", check_invalid),
 ]
 

@@ -44,3 +44,4 @@ def test_emulated_kernels_under_address_sanitizer():
     env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0")
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "checks.py"), "--asan"], capture_output=True, text=True, env=env, timeout=1500)
     assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
+
