@@ -1,0 +1,104 @@
+"""CPU: line coverage of the Python glue around the C ABI that cannot run without a GPU otherwise — every launcher in kernels.py touched by the
+opt-in switches (both settings) and the training head's forward / backward — with the library replaced by a stub whose entry points do
+nothing and return 0.  Catches NameError / TypeError / wrong ctypes argument counts in paths that the GPU suite and bench.py depend on;
+says nothing about numerics (that is the emulator's and the GPU tests' job)."""
+import pytest
+import torch
+
+BF = torch.bfloat16
+
+
+class _StubLib:
+    def __getattr__(self, name):
+        if name == "tfasr_rnnt_workspace_bytes":
+            return lambda *a: 1024
+        return lambda *a: 0
+
+
+@pytest.fixture
+def stub(monkeypatch):
+    from tensorflowasr_b200 import _lib
+
+    monkeypatch.setattr(_lib, "load", lambda: _StubLib())
+    monkeypatch.setattr(_lib, "stream_ptr", lambda d=None: 0)
+    monkeypatch.setattr(_lib, "ptr", lambda t: None if t is None else t.data_ptr())
+
+
+@pytest.mark.parametrize("flag", [False, True])
+def test_kernel_launchers_run_with_every_switch(stub, flag):
+    from tensorflowasr_b200 import kernels, ops
+
+    setters = (ops.set_conv1_v2, ops.set_im2col_v2, ops.set_joint_v2, ops.set_dwconv_wgrad_v2)
+    try:
+        for s in setters:
+            s(flag)
+        x, w, b = torch.randn(2, 10, 8), torch.randn(3, 3, 1, 16), torch.randn(16)
+        y = kernels.conv1_fwd(x, w, b)
+        assert y.shape == (2, 5, 4, 16) and y.dtype == BF
+        kernels.conv1_wgrad(x, y, torch.zeros_like(w))
+        col = kernels.im2col(y)
+        assert col.shape == (2 * 3 * 2, 9 * 16)
+        assert kernels.col2im(col, tuple(y.shape)).shape == y.shape
+        h = kernels.joint_tanh_fwd(torch.randn(2, 4, 16).to(BF), torch.randn(2, 3, 16).to(BF))
+        de, dp = kernels.joint_reduce_bwd(h)
+        assert h.shape == (2, 4, 3, 16) and de.shape == (2, 4, 16) and dp.shape == (2, 3, 16)
+        dx = kernels.dwconv_bwd(torch.randn(2, 9, 16).to(BF), torch.randn(2, 9, 16).to(BF), torch.randn(5, 16), torch.zeros(5, 16), torch.zeros(16))
+        assert dx.shape == (2, 9, 16)
+    finally:
+        for s in setters:
+            s(False)
+
+
+def test_seqconv_and_decode_launchers(stub):
+    from tensorflowasr_b200 import kernels
+
+    xx = torch.randn(2, 9, 16).to(BF)
+    ln = torch.tensor([9, 3], dtype=torch.int32)
+    assert kernels.seq_dwconv_fwd(xx, torch.randn(5, 16), 2).shape == (2, 5, 16)
+    assert kernels.seq_dwconv_bwd(xx[:, :5].contiguous(), xx, torch.randn(5, 16), torch.zeros(5, 16), 2, need_dx=False) is None
+    m = kernels.seq_masked_mean(xx, ln)
+    W1, b1, W2, b2 = torch.randn(16, 2), torch.randn(2), torch.randn(2, 16), torch.randn(16)
+    z1, s = kernels.se_fc_fwd(m, W1, b1, W2, b2, 1)
+    out = kernels.se_apply_fwd(xx, s, None, 1)
+    dres, ds = kernels.se_apply_bwd(out, xx, s, None, 1)
+    dm = kernels.se_fc_bwd(ds, s, z1, m, W1, W2, ln, 9, 1, torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2))
+    assert kernels.se_dy(dres, s, dm, ln).shape == xx.shape
+    g = kernels.conv_geom(2, 9, 8, 1, 3, 5, 2, 2, "same")
+    col = kernels.conv_im2col(torch.randn(2, 9, 8, 1), g)
+    assert col.shape == (2 * g.To * g.Fo, g.Kp) and g.Kp == 16
+    g8 = kernels.conv_geom(2, 9, 8, 8, 3, 3, 1, 2, "causal")
+    assert kernels.conv_col2im(torch.zeros((2 * g8.To * g8.Fo, g8.Kp), dtype=BF), g8).shape == (2, 9, 8, 8)
+    w = dict(emb=torch.randn(10, 4), w_ih=torch.randn(4, 16), w_hh=torch.randn(4, 16), b=torch.randn(16), ln_g=None, ln_b=None, wp=torch.randn(4, 6),
+             bp=torch.randn(6), wv=torch.randn(6, 10), bv=torch.randn(10))
+    z = torch.zeros(2, dtype=torch.int32)
+    kernels.greedy_decode(w, torch.randn(2, 3, 6), z.clone(), z.clone(), torch.zeros(2, 2, 4), z.clone(), z.clone(), torch.zeros(2, 7, dtype=torch.int32),
+                          z.clone(), z.clone(), 0, mode=0, max_iters=5)
+
+
+@pytest.mark.parametrize("fused_lse,grad_v2", [(False, False), (True, True)])
+def test_training_head_python_path(stub, monkeypatch, fused_lse, grad_v2):
+    from tensorflowasr_b200 import fused, kernels, ops
+
+    def gemm(a, b, *, out=None, out_dtype=BF, mn_major=False, accumulate=False, **kw):
+        c = (a.float().t() @ b.float()) if mn_major else (a.float() @ b.float().t())
+        if out is None:
+            return c.to(out_dtype)
+        return out.add_(c) if accumulate else out.copy_(c)
+
+    monkeypatch.setattr(kernels, "gemm", gemm)
+    monkeypatch.setattr(kernels, "joint_tanh_fwd", lambda e, p: torch.tanh(e.float()[:, :, None] + p.float()[:, None]).to(BF))
+    monkeypatch.setattr(kernels, "joint_reduce_bwd", lambda dz: (dz.float().sum(2), dz.float().sum(1)))
+    try:
+        ops.set_fused_lse(fused_lse)
+        ops.set_rnnt_grad_v2(grad_v2)
+        B, T, U1, J, V = 2, 5, 3, 16, 20
+        e = torch.randn(B, T, J).to(BF).requires_grad_(True)
+        p = torch.randn(B, U1, J).to(BF).requires_grad_(True)
+        w, bv = torch.nn.Parameter(torch.randn(J, V)), torch.nn.Parameter(torch.randn(V))
+        costs = fused.transducer_head(e, p, fused.WeightPack(w, bv), torch.zeros(B, U1 - 1, dtype=torch.int32), torch.full((B,), T, dtype=torch.int32),
+                                      torch.full((B,), U1 - 1, dtype=torch.int32))
+        costs.sum().backward()
+        assert e.grad.shape == e.shape and p.grad.shape == p.shape and w.grad.shape == w.shape
+    finally:
+        ops.set_fused_lse(False)
+        ops.set_rnnt_grad_v2(False)
