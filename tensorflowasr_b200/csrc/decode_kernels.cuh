@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(1024) greedy_decode_kernel(const GreedyParams 
       ++it;
     }
   }
+  __syncthreads();  // every thread has read this utterance's entry state (a loop of zero iterations has no barrier of its own)
   for (int r = tid; r < R; r += nth) {
     p.states[((size_t)b * 2 + 0) * R + r] = s_h[r];
     p.states[((size_t)b * 2 + 1) * R + r] = s_c[r];

@@ -28,10 +28,10 @@ class GreedyParams(ctypes.Structure):
                 + [(n, c_i32) for n in ("T", "E", "R", "J", "V", "max_tokens", "blank", "mode", "max_iters", "per_frame_cap")])
 
 
-def load(asan=False):
+def load(asan=False, tsan=False):
     import build_emu
 
-    lib = ctypes.CDLL(build_emu.build(asan=asan))
+    lib = ctypes.CDLL(build_emu.build(asan=asan, tsan=tsan))
     for name in ("tfasr_greedy_decode_f32", "tfasr_dwconv_causal_wgrad_v2", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
@@ -797,7 +797,7 @@ CASES = [
 ]
 
 if __name__ == "__main__":
-    lib = load(asan="--asan" in sys.argv)
+    lib = load(asan="--asan" in sys.argv, tsan="--tsan" in sys.argv)
     for name, fn in CASES:
         fn(lib)
         print("ok", name, flush=True)

@@ -45,3 +45,19 @@ def test_emulated_kernels_under_address_sanitizer():
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "checks.py"), "--asan"], capture_output=True, text=True, env=env, timeout=1500)
     assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
 
+
+def test_emulated_kernels_under_thread_sanitizer():
+    """Every CUDA thread is an OS thread in the emulator, __syncthreads / __syncwarp / shuffles are real barriers and atomics real atomics:
+    ThreadSanitizer then reports exactly the accesses that are NOT ordered by them — the CPU stand-in for compute-sanitizer racecheck
+    (a deleted __syncthreads is reported; it found an unordered entry-state read in the decode kernel when first run)."""
+    import build_emu
+
+    rt = build_emu.tsan_runtime()
+    if rt is None:
+        pytest.skip("libtsan not available")
+    build_emu.build(tsan=True)
+    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0 halt_on_error=0")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "checks.py"), "--tsan"], capture_output=True, text=True, env=env, timeout=1800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-6000:]
+
