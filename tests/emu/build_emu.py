@@ -15,29 +15,71 @@ OUT = os.path.join(REPO, "build", "emu")
 SOURCES = ["seqconv.cu", "decode.cu", "rnnt_combine.cu", "conv1.cu", "rnnt_grad_v2.cu", "joint_v2.cu", "subsample_v2.cu", "dwconv_wgrad_v2.cu"]  # launcher files written against simt.cuh
 
 
+V1_SOURCES = ["rnnt_loss.cu", "ctc_loss.cu", "logmel.cu", "fused_rows.cu", "conv_bn.cu", "dwconv.cu", "joint.cu", "param_ops.cu", "specaugment.cu"]
+# first-generation files (written against common.cuh, <<<>>> launches): converted by cu2emu.py into build/emu/gen/*.cpp
+
+
+def _generate_v1() -> list[str]:
+    import cu2emu
+
+    gen = os.path.join(OUT, "gen")
+    os.makedirs(gen, exist_ok=True)
+    outs = []
+    for name in V1_SOURCES:
+        src = os.path.join(CSRC, name)
+        dst = os.path.join(gen, name[:-3] + ".cpp")
+        text = cu2emu.convert(open(src).read(), name)
+        if not os.path.exists(dst) or open(dst).read() != text:
+            open(dst, "w").write(text)
+        outs.append(dst)
+    return outs
+
+
 def build(asan: bool = False, tsan: bool = False) -> str:
+    """Compile every source to its own object (in parallel) and link build/emu/libtfasr_emu[_asan|_tsan].so; returns the path."""
+    import concurrent.futures
+    import sys
+
     gxx = shutil.which("g++")
     if gxx is None:
         raise RuntimeError("g++ not found")
-    os.makedirs(OUT, exist_ok=True)
-    lib = os.path.join(OUT, "libtfasr_emu_asan.so" if asan else ("libtfasr_emu_tsan.so" if tsan else "libtfasr_emu.so"))
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "simt.cuh"), os.path.join(CSRC, "seqconv_kernels.cuh"), os.path.join(CSRC, "decode_kernels.cuh"), os.path.join(CSRC, "rnnt_combine.cu"), os.path.join(CSRC, "conv1.cu"), os.path.join(CSRC, "rnnt_grad_v2.cu"), os.path.join(CSRC, "joint_v2.cu"), os.path.join(CSRC, "subsample_v2.cu"), os.path.join(CSRC, "dwconv_wgrad_v2.cu"), os.path.join(HERE, "cuda_emu.h"),
-                   os.path.join(REPO, "include", "tfasr_b200.h"), os.path.abspath(__file__)]
-    if os.path.exists(lib) and os.path.getmtime(lib) >= max(os.path.getmtime(d) for d in deps):
-        return lib
-    cmd = [gxx, "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-DTFASR_EMU_BUILD", "-I", HERE, "-I", os.path.join(REPO, "include")]
+    sys.path.insert(0, HERE)
+    tag = "asan" if asan else ("tsan" if tsan else "plain")
+    objdir = os.path.join(OUT, "obj_" + tag)
+    os.makedirs(objdir, exist_ok=True)
+    lib = os.path.join(OUT, "libtfasr_emu.so" if tag == "plain" else f"libtfasr_emu_{tag}.so")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES] + _generate_v1()
+    hdrs = [os.path.join(CSRC, h) for h in ("simt.cuh", "seqconv_kernels.cuh", "decode_kernels.cuh", "dropout.cuh")] + \
+           [os.path.join(HERE, h) for h in ("cuda_emu.h", "emu_common.h", "cu2emu.py")] + [os.path.join(REPO, "include", "tfasr_b200.h"), os.path.abspath(__file__)]
+    hdr_m = max(os.path.getmtime(h) for h in hdrs)
+    flags = ["-std=c++20", "-O1", "-g", "-fPIC", "-pthread", "-DTFASR_EMU_BUILD", "-I", HERE, "-I", os.path.join(REPO, "include"), "-I", CSRC]
     if asan:
-        cmd += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
     if tsan:
-        cmd += ["-fsanitize=thread", "-fno-omit-frame-pointer"]
-    for s in srcs:
-        cmd += ["-x", "c++", s]
-    cmd += ["-o", lib + ".tmp"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("emulation build failed:\n" + r.stdout + r.stderr)
-    os.replace(lib + ".tmp", lib)
+        flags += ["-fsanitize=thread", "-fno-omit-frame-pointer"]
+    jobs, objs = [], []
+    for src in srcs:
+        obj = os.path.join(objdir, os.path.splitext(os.path.basename(src))[0] + ".o")
+        objs.append(obj)
+        if not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m):
+            jobs.append([gxx, *flags, "-c", "-x", "c++", src, "-o", obj])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("emulation build failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(run, jobs))
+    if jobs or not os.path.exists(lib) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
+        link = [gxx, "-shared", "-pthread", "-o", lib + ".tmp", *objs]
+        if asan:
+            link.append("-fsanitize=address")
+        if tsan:
+            link.append("-fsanitize=thread")
+        run(link)
+        os.replace(lib + ".tmp", lib)
     return lib
 
 

@@ -1,0 +1,103 @@
+"""Source-to-source shim: a first-generation csrc/*.cu file (written against common.cuh, launching with <<<>>>) -> a .cpp that g++ compiles
+against the SIMT emulator.  TEST INFRASTRUCTURE ONLY.  Rewrites, and nothing else:
+  * `#include "common.cuh"`                           -> `#include "emu_common.h"`
+  * `kernel<<<grid, block[, smem[, stream]]>>>(args);` -> `emu::launch(dim3(grid), dim3(block), smem, [&] { kernel(args); });`
+  * `extern __shared__ [__align__(N)] T name[];`       -> `T* name = reinterpret_cast<T*>(emu::g_dyn_smem);`
+  * the tanh.approx inline PTX of joint.cu             -> tanhf
+  * `#include <cuda_*.h>` lines dropped; `template <> __device__` loses the __device__ (it maps to `static` in the emulator)
+Anything it does not understand (another `asm`, a launch it cannot parse) is an error, not a silent pass-through."""
+from __future__ import annotations
+
+import re
+
+
+def _match_paren(s: str, i: int) -> int:
+    """s[i] == '(' -> index of the matching ')'."""
+    depth = 0
+    for j in range(i, len(s)):
+        if s[j] == "(":
+            depth += 1
+        elif s[j] == ")":
+            depth -= 1
+            if depth == 0:
+                return j
+    raise ValueError("unbalanced parentheses")
+
+
+def _split_top(s: str) -> list[str]:
+    out, depth, cur = [], 0, []
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    out.append("".join(cur).strip())
+    return out
+
+
+def _rewrite_launches(src: str) -> str:
+    out, pos = [], 0
+    while True:
+        i = src.find("<<<", pos)
+        if i < 0:
+            out.append(src[pos:])
+            return "".join(out)
+        # kernel expression: identifier (+ optional <template args>) right before <<<
+        j = i
+        if src[j - 1] == ">":  # template arguments
+            depth = 0
+            while True:
+                j -= 1
+                if src[j] == ">":
+                    depth += 1
+                elif src[j] == "<":
+                    depth -= 1
+                    if depth == 0:
+                        break
+        k = j
+        while k > 0 and (src[k - 1].isalnum() or src[k - 1] in "_:"):
+            k -= 1
+        kernel = src[k:i]
+        e = src.find(">>>", i)
+        cfg = _split_top(src[i + 3:e])
+        if not (2 <= len(cfg) <= 4):
+            raise ValueError(f"cannot parse launch configuration of {kernel!r}: {cfg}")
+        a0 = src.index("(", e)
+        a1 = _match_paren(src, a0)
+        semi = a1 + 1
+        while src[semi].isspace():
+            semi += 1
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        out.append(src[pos:k])
+        call = f"emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({smem}), [&] {{ {kernel}({src[a0 + 1:a1]}); }})"
+        if src[semi] == ";":
+            out.append(call + ";")
+            pos = semi + 1
+        else:  # the launch is the tail of a macro body: the `;` comes from the macro's use
+            out.append(call)
+            pos = a1 + 1
+
+
+def convert(src: str, name: str = "?") -> str:
+    src = src.replace('#include "common.cuh"', '#include "emu_common.h"')
+    src = re.sub(r"#include\s+<(cuda[\w.]*|math_constants\.h)>\n", "", src)
+    src = re.sub(r"template\s*<>\s*__device__", "template <>", src)  # an explicit specialisation cannot repeat the storage class
+    src = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu::g_dyn_smem);", src)
+    src = re.sub(r'asm\("tanh\.approx\.f32 %0, %1;"\s*:\s*"=f"\((\w+)\)\s*:\s*"f"\((\w+)\)\);', r"\1 = tanhf(\2);", src)
+    if re.search(r"\basm\b", src):
+        raise ValueError(f"{name}: inline PTX the shim does not know")
+    src = _rewrite_launches(src)
+    if "<<<" in src or "extern __shared__" in src:
+        raise ValueError(f"{name}: unconverted CUDA syntax left")
+    return src
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(convert(open(sys.argv[1]).read(), sys.argv[1]))

@@ -20,8 +20,8 @@
 #include <vector>
 
 #define TFASR_EMU 1
-#define __global__
-#define __device__
+#define __global__ static  // internal linkage: kernels / device helpers of different files may share names
+#define __device__ static
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
@@ -56,6 +56,12 @@ inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return
 // ------------------------------------------------------------------------------------------------ bf16 (round-to-nearest-even)
 struct __nv_bfloat16 {
   uint16_t v;
+  operator float() const {  // as cuda_bf16.h: bf16 -> f32 is exact
+    uint32_t u = (uint32_t)v << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  }
 };
 struct alignas(4) __nv_bfloat162 {
   __nv_bfloat16 x, y;
@@ -88,8 +94,6 @@ inline float __expf(float x) { return expf(x); }
 inline float __logf(float x) { return logf(x); }
 inline float __fdividef(float a, float b) { return a / b; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
-inline float __ldg(const float* p) { return *p; }
-inline int __ldg(const int* p) { return *p; }
 template <class T>
 inline T min(T a, T b) { return a < b ? a : b; }
 template <class T>

@@ -1,6 +1,8 @@
-"""The plain-SIMT kernels of csrc/seqconv_kernels.cuh (ContextNet / DeepSpeech2 encoder bodies) executed on the
-CPU emulator (tests/emu) through their C ABI and checked against numpy references; then once more under AddressSanitizer, the CPU
-stand-in for compute-sanitizer memcheck.  The GPU parity tests of the same entry points are in tests/test_gpu_seqconv.py."""
+"""Plain-SIMT kernels executed on the CPU emulator (tests/emu) through their C ABI: (1) the kernels written against csrc/simt.cuh
+(ContextNet / DeepSpeech2 encoder bodies, persistent decode, second-generation hot-path kernels) against numpy references; (2) the
+first-generation PRODUCT kernels (RNN-T, CTC, log-mel; sources converted by tests/emu/cu2emu.py) against the oracle, the warp-transducer
+known-answer vector and the test.flac golden features; then everything once more under AddressSanitizer and ThreadSanitizer — the CPU
+stand-ins for compute-sanitizer memcheck / racecheck.  GPU parity tests of the same entry points: tests/test_gpu_*.py."""
 import os
 import shutil
 import subprocess
@@ -34,6 +36,29 @@ def test_emulated_kernel(emu_lib, name):
     dict(checks.CASES)[name](emu_lib)
 
 
+def _v1_case_names():
+    import checks_v1
+
+    return [n for n, _ in checks_v1.CASES]
+
+
+@pytest.fixture(scope="module")
+def emu_lib_v1():
+    import checks_v1
+
+    return checks_v1.load()
+
+
+@pytest.mark.parametrize("name", _v1_case_names())
+def test_emulated_product_kernel(emu_lib_v1, name):
+    """The first-generation (default-path, GPU-verified) kernels — csrc/rnnt_loss.cu, ctc_loss.cu, logmel.cu, ... converted by
+    tests/emu/cu2emu.py — on the CPU emulator against the oracle: warp-transducer's known-answer vector, the test.flac golden features,
+    oracle/rnnt.py / ctc.py / logmel.py on ragged batches."""
+    import checks_v1
+
+    dict(checks_v1.CASES)[name](emu_lib_v1)
+
+
 def test_emulated_kernels_under_address_sanitizer():
     import build_emu
 
@@ -42,8 +67,9 @@ def test_emulated_kernels_under_address_sanitizer():
         pytest.skip("libasan not available")
     build_emu.build(asan=True)
     env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0")
-    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "checks.py"), "--asan"], capture_output=True, text=True, env=env, timeout=1500)
-    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
+    for script in ("checks.py", "checks_v1.py"):
+        r = subprocess.run([sys.executable, os.path.join(HERE, "emu", script), "--asan"], capture_output=True, text=True, env=env, timeout=1500)
+        assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, script + "\n" + r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_emulated_kernels_under_thread_sanitizer():
@@ -57,7 +83,8 @@ def test_emulated_kernels_under_thread_sanitizer():
         pytest.skip("libtsan not available")
     build_emu.build(tsan=True)
     env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0 halt_on_error=0")
-    r = subprocess.run([sys.executable, os.path.join(HERE, "emu", "checks.py"), "--tsan"], capture_output=True, text=True, env=env, timeout=1800)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-6000:]
+    for script in ("checks.py", "checks_v1.py"):
+        r = subprocess.run([sys.executable, os.path.join(HERE, "emu", script), "--tsan"], capture_output=True, text=True, env=env, timeout=1800)
+        assert r.returncode == 0, script + "\n" + r.stdout[-2000:] + r.stderr[-4000:]
+        assert "WARNING: ThreadSanitizer" not in r.stderr, script + "\n" + r.stderr[-6000:]
 
