@@ -123,37 +123,43 @@ inline thread_local std::barrier<>* t_bar;
 inline uint8_t* g_dyn_smem = nullptr;  // exact-size heap block: ASan sees overruns
 inline std::atomic<long> g_launches{0};
 
+// One OS thread per CUDA thread of a block, created once per launch; the blocks of the grid run one after another on them (a second
+// barrier separates consecutive blocks, so shared memory — dynamic and function-local statics — always belongs to exactly one block).
+// A kernel in which some threads return before a __syncthreads() that the others still execute would deadlock here (on the GPU exited
+// threads stop counting); none of the kernels does that.
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
   const int nth = (int)(block.x * block.y * block.z);
   if (nth <= 0 || nth > 1024) abort();
   g_launches++;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        std::barrier<> bar(nth);
-        std::vector<std::unique_ptr<Warp>> warps;
-        for (int w = 0; w * 32 < nth; ++w) warps.emplace_back(new Warp(nth - w * 32 < 32 ? nth - w * 32 : 32));
-        uint8_t* smem = smem_bytes ? (uint8_t*)aligned_alloc(16, (smem_bytes + 15) / 16 * 16) : nullptr;
-        // aligned_alloc rounds the request up to 16: the tail (< 16 bytes) is the only slack ASan cannot see
-        g_dyn_smem = smem;
-        std::vector<std::thread> ths;
-        ths.reserve(nth);
-        for (int t = 0; t < nth; ++t)
-          ths.emplace_back([&, t] {
-            t_threadIdx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;
+  std::barrier<> bar(nth), done_bar(nth);
+  std::vector<std::unique_ptr<Warp>> warps;
+  for (int w = 0; w * 32 < nth; ++w) warps.emplace_back(new Warp(nth - w * 32 < 32 ? nth - w * 32 : 32));
+  // exact size (rounded up to 16 by aligned_alloc: the tail of < 16 bytes is the only slack ASan cannot see)
+  uint8_t* smem = smem_bytes ? (uint8_t*)aligned_alloc(16, (smem_bytes + 15) / 16 * 16) : nullptr;
+  g_dyn_smem = smem;
+  std::vector<std::thread> ths;
+  ths.reserve(nth);
+  for (int t = 0; t < nth; ++t)
+    ths.emplace_back([&, t] {
+      t_threadIdx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+      t_blockDim = block;
+      t_gridDim = grid;
+      t_warp = warps[t / 32].get();
+      t_lane = t % 32;
+      t_bar = &bar;
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
             t_blockIdx = {bx, by, bz};
-            t_blockDim = block;
-            t_gridDim = grid;
-            t_warp = warps[t / 32].get();
-            t_lane = t % 32;
-            t_bar = &bar;
             body();
-          });
-        for (auto& th : ths) th.join();
-        free(smem);
-        g_dyn_smem = nullptr;
-      }
+            done_bar.arrive_and_wait();
+          }
+    });
+  for (auto& th : ths) th.join();
+  free(smem);
+  g_dyn_smem = nullptr;
 }
 
 template <class T>
