@@ -600,7 +600,7 @@ def check_rnnt_grad_v2(lib, B, T, U1, V, logit_len, label_len, in_place, seed=14
 
 
 # ------------------------------------------------------------------------------------------------ joint elementwise / reduction, v2
-def check_joint_v2(lib, B, T, U1, J, seed=15):
+def check_joint_v2(lib, B, T, U1, J, seed=15, fwd="tfasr_joint_tanh_fwd_v2", bwd="tfasr_joint_reduce_bwd_v2"):
     rng = np.random.default_rng(seed)
     e = rbf(rng.standard_normal((B, T, J)))
     p = rbf(rng.standard_normal((B, U1, J)))
@@ -608,20 +608,20 @@ def check_joint_v2(lib, B, T, U1, J, seed=15):
     eb, ep = heap(to_bf16(e))
     pb, pp = heap(to_bf16(p))
     hb, hp = heap(np.zeros((B, T, U1, J), np.uint16))
-    assert lib.tfasr_joint_tanh_fwd_v2(ep, pp, hp, B, T, U1, J, None) == 0
+    assert getattr(lib, fwd)(ep, pp, hp, B, T, U1, J, None) == 0
     close(from_bf16(hb), h_ref, 5e-3, f"joint tanh v2 {(B, T, U1, J)}")
     dz = rbf(rng.standard_normal((B, T, U1, J)))
     dzb, dzp = heap(to_bf16(dz))
     deb, dep = heap(np.full((B, T, J), np.nan, np.float32))
     init = rng.standard_normal((B, U1, J)).astype(np.float32)
     dpb, dpp = heap(init)
-    assert lib.tfasr_joint_reduce_bwd_v2(dzp, dep, dpp, B, T, U1, J, None) == 0
+    assert getattr(lib, bwd)(dzp, dep, dpp, B, T, U1, J, None) == 0
     close(deb, dz.astype(np.float64).sum(2), 1e-5, "joint reduce v2 de")
     close(dpb - init, dz.astype(np.float64).sum(1), 1e-4, "joint reduce v2 dp")
 
 
 # ------------------------------------------------------------------------------------------------ im2col / col2im (3x3 s2 causal), v2
-def check_im2col_v2(lib, B, T1, F1, C, seed=16):
+def check_im2col_v2(lib, B, T1, F1, C, seed=16, im2col="tfasr_im2col_3x3s2_v2", col2im="tfasr_col2im_3x3s2_v2"):
     rng = np.random.default_rng(seed)
     g = conv_geom(B, T1, F1, C, 3, 3, 2, 2, "causal")
     assert (g.To, g.Fo, g.Kp) == ((T1 + 1) // 2, (F1 + 1) // 2, 9 * C)
@@ -629,7 +629,7 @@ def check_im2col_v2(lib, B, T1, F1, C, seed=16):
     ref = im2col_ref(a.astype(np.float64), g)
     ab, ap = heap(to_bf16(a))
     cb, cp = heap(np.full((B * g.To * g.Fo, 9 * C), 0x7FC0, np.uint16))
-    assert lib.tfasr_im2col_3x3s2_v2(ap, cp, B, T1, F1, C, None) == 0
+    assert getattr(lib, im2col)(ap, cp, B, T1, F1, C, None) == 0
     got = from_bf16(cb).reshape(ref.shape)
     assert np.isfinite(got).all() and np.array_equal(got.astype(np.float64), ref), "im2col v2 (exact copy expected)"
     dcol = rbf(rng.standard_normal(ref.shape))
@@ -646,7 +646,7 @@ def check_im2col_v2(lib, B, T1, F1, C, seed=16):
                         da_ref[:, t, f, :] += dcol[:, to, fo, (i * 3 + j) * C:(i * 3 + j + 1) * C]
     db, dp = heap(to_bf16(dcol))
     ob, op = heap(np.full((B, T1, F1, C), 0x7FC0, np.uint16))
-    assert lib.tfasr_col2im_3x3s2_v2(dp, op, B, T1, F1, C, None) == 0
+    assert getattr(lib, col2im)(dp, op, B, T1, F1, C, None) == 0
     close(from_bf16(ob), da_ref, 5e-3, f"col2im v2 {(B, T1, F1, C)}")
 
 
@@ -672,7 +672,7 @@ def check_dwconv_wgrad_v2(lib, B, T, C, K, with_bias, seed=17):
 
 
 # ------------------------------------------------------------------------------------------------ first conv of the subsampling, v2
-def check_conv1_v2(lib, B, T, F, C, seed=13):
+def check_conv1_v2(lib, B, T, F, C, seed=13, fwd="tfasr_conv1_3x3s2_fwd_v2", wgrad="tfasr_conv1_3x3s2_wgrad_v2"):
     rng = np.random.default_rng(seed)
     x = rng.standard_normal((B, T, F)).astype(np.float32)
     w = (rng.standard_normal((3, 3, 1, C)) * 0.3).astype(np.float32)
@@ -692,12 +692,12 @@ def check_conv1_v2(lib, B, T, F, C, seed=13):
     wb, wp = heap(w)
     bb, bp = heap(bias)
     yb, yp = heap(np.zeros((B, T1, F1, C), np.uint16))
-    assert lib.tfasr_conv1_3x3s2_fwd_v2(xp_, wp, bp, yp, B, T, F, C, None) == 0
+    assert getattr(lib, fwd)(xp_, wp, bp, yp, B, T, F, C, None) == 0
     close(from_bf16(yb), y_ref, 5e-3, f"conv1 v2 fwd {(B, T, F, C)}")
     dyb, dyp = heap(to_bf16(dy))
     init = rng.standard_normal((3, 3, 1, C)).astype(np.float32)
     dwb, dwp = heap(init)
-    assert lib.tfasr_conv1_3x3s2_wgrad_v2(xp_, dyp, dwp, B, T, F, C, None) == 0
+    assert getattr(lib, wgrad)(xp_, dyp, dwp, B, T, F, C, None) == 0
     close(dwb - init, dw_ref, 2e-4, f"conv1 v2 wgrad {(B, T, F, C)}")
 
 

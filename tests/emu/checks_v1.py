@@ -168,6 +168,201 @@ def check_logmel_golden(lib):
     assert float(err.max()) < 2e-3, f"golden log-mel max abs err {err.max():.2e}"
 
 
+# ------------------------------------------------------------------------------------------------ row kernels (fused_rows.cu)
+def check_layernorm(lib, M, D, x_f32, seed=24):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((M, D)) * 2 + 0.5).astype(np.float32)
+    if not x_f32:
+        x = rbf(x)
+    gamma = (rng.standard_normal(D) * 0.2 + 1).astype(np.float32)
+    beta = (rng.standard_normal(D) * 0.1).astype(np.float32)
+    x64 = x.astype(np.float64)
+    mu, var = x64.mean(1, keepdims=True), x64.var(1, keepdims=True)
+    rs = 1.0 / np.sqrt(var + 1e-3)
+    xh = (x64 - mu) * rs
+    xb, xp = heap(x if x_f32 else to_bf16(x))
+    gb, gp = heap(gamma)
+    bb, bp = heap(beta)
+    yb, yp = heap(np.zeros((M, D), np.uint16))
+    mb, mp = heap(np.zeros(M, np.float32))
+    rb, rp = heap(np.zeros(M, np.float32))
+    assert lib.tfasr_layernorm_fwd(xp, int(x_f32), gp, bp, yp, mp, rp, M, D, c_f(1e-3), None) == 0
+    close(from_bf16(yb), xh * gamma + beta, 6e-3, f"layernorm fwd {(M, D)}")
+    close(mb, mu[:, 0], 1e-5, "layernorm mean")
+    close(rb, rs[:, 0], 1e-4, "layernorm rstd")
+    dy = rbf(rng.standard_normal((M, D)))
+    dres = rbf(rng.standard_normal((M, D)))
+    g = dy.astype(np.float64) * gamma
+    dx_ref = rs * (g - g.mean(1, keepdims=True) - xh * (g * xh).mean(1, keepdims=True)) + dres
+    db, dp = heap(to_bf16(dy))
+    drb, drp = heap(to_bf16(dres))
+    dxb, dxp = heap(np.zeros((M, D), np.uint16))
+    g0, b0 = rng.standard_normal(D).astype(np.float32), rng.standard_normal(D).astype(np.float32)
+    dgb, dgp = heap(g0)
+    dbb, dbp = heap(b0)
+    assert lib.tfasr_layernorm_bwd(dp, xp, int(x_f32), mp, rp, gp, drp, dxp, dgp, dbp, M, D, None) == 0
+    close(from_bf16(dxb), dx_ref, 8e-3, "layernorm bwd dx")
+    close(dgb - g0, (dy.astype(np.float64) * xh).sum(0), 2e-3, "layernorm dgamma")
+    close(dbb - b0, dy.astype(np.float64).sum(0), 1e-4, "layernorm dbeta")
+
+
+def _dropout_keep(seed, salt, M, N, p):
+    """csrc/dropout.cuh in numpy: keep mask of an [M, N] tensor (N even)."""
+    u64 = np.uint64
+    thr = 0 if p * 65536.0 + 0.5 <= 0 else min(65535, int(p * 65536.0 + 0.5))
+    rows = np.arange(M, dtype=u64)
+    with np.errstate(over="ignore"):
+        k = u64((seed + salt) & 0xFFFFFFFFFFFFFFFF) * u64(0xD6E8FEB86659FD93) + rows * u64(0x9E3779B97F4A7C15)
+    h = ((k & u64(0xFFFFFFFF)) ^ (k >> u64(32))).astype(np.uint32)
+    h ^= h >> np.uint32(15)
+    h = (h.astype(u64) * u64(0x2C1B3C6D) & u64(0xFFFFFFFF)).astype(np.uint32)
+    h ^= h >> np.uint32(12)
+    rowkey = h
+    pair = np.arange(N // 2, dtype=u64)
+    hh = ((rowkey[:, None].astype(u64) + pair[None, :] * u64(0x9E3779B9)) & u64(0xFFFFFFFF)).astype(np.uint32)
+    hh ^= hh >> np.uint32(16)
+    hh = (hh.astype(u64) * u64(0x85EBCA6B) & u64(0xFFFFFFFF)).astype(np.uint32)
+    hh ^= hh >> np.uint32(13)
+    hh = (hh.astype(u64) * u64(0xC2B2AE35) & u64(0xFFFFFFFF)).astype(np.uint32)
+    hh ^= hh >> np.uint32(16)
+    keep = np.zeros((M, N), bool)
+    keep[:, 0::2] = (hh & np.uint32(0xFFFF)) >= thr
+    keep[:, 1::2] = (hh >> np.uint32(16)) >= thr
+    return keep
+
+
+def check_scale_mask_glu(lib, M, N, p, seed=25):
+    rng = np.random.default_rng(seed)
+    x = rbf(rng.standard_normal((M, N)))
+    add = rbf(rng.standard_normal((M, N)))
+    dseed, salt, scale = 0x1234567, 77, 0.5
+    keep = _dropout_keep(dseed, salt, M, N, p) if p > 0 else np.ones((M, N), bool)
+    ref = np.where(keep, x.astype(np.float64) * scale / (1 - p), 0.0) + add
+    xb, xp = heap(to_bf16(x))
+    ab, ap = heap(to_bf16(add))
+    ob, op = heap(np.zeros((M, N), np.uint16))
+    c0 = rng.standard_normal(N).astype(np.float32)
+    cb, cp = heap(c0)
+    sb, sp = heap(np.array([dseed], np.uint64))
+    assert lib.tfasr_scale_mask_colsum(xp, ap, op, cp, M, N, c_f(scale), c_f(p), sp, ctypes.c_ulonglong(salt), None) == 0
+    close(from_bf16(ob), ref, 6e-3, f"scale_mask_colsum p={p}")
+    close(cb - c0, ref.sum(0), 8e-3, "scale_mask_colsum colsum")  # sums the fp32 values or their bf16 roundings: within bf16 noise either way
+    if p > 0:
+        frac = 1.0 - keep.mean()
+        assert abs(frac - p) < 0.05, f"dropout rate {frac:.3f} vs {p}"
+    # GLU backward on interleaved (a, b) pairs
+    D = N // 2
+    aux = rbf(rng.standard_normal((M, 2 * D)))
+    dg = rbf(rng.standard_normal((M, D)))
+    a, b = aux[:, 0::2].astype(np.float64), aux[:, 1::2].astype(np.float64)
+    sg = 1 / (1 + np.exp(-b))
+    ref_d = np.zeros((M, 2 * D))
+    ref_d[:, 0::2] = dg * sg
+    ref_d[:, 1::2] = dg * a * sg * (1 - sg)
+    axb, axp = heap(to_bf16(aux))
+    dgb, dgp = heap(to_bf16(dg))
+    dab, dap = heap(np.zeros((M, 2 * D), np.uint16))
+    c2 = np.zeros(2 * D, np.float32)
+    c2b, c2p = heap(c2)
+    assert lib.tfasr_glu_bwd(axp, dgp, dap, c2p, M, D, None) == 0
+    close(from_bf16(dab), ref_d, 6e-3, "glu_bwd")
+    close(c2b, ref_d.sum(0), 3e-3, "glu_bwd colsum")
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm passes (conv_bn.cu)
+def check_batchnorm(lib, R, C, act, seed=26):
+    rng = np.random.default_rng(seed)
+    x = rbf(rng.standard_normal((R, C)) * 1.5 + 0.3)
+    gamma = (rng.uniform(0.5, 1.5, C)).astype(np.float32)
+    beta = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    x64 = x.astype(np.float64)
+    xb, xp = heap(to_bf16(x))
+    sums, sp = heap(np.zeros((2, C), np.float32))
+    assert lib.tfasr_bn_stats(xp, sp, c_i64(R), C, None) == 0
+    close(sums[0], x64.sum(0), 1e-4, "bn sum")
+    close(sums[1], (x64 ** 2).sum(0), 1e-4, "bn sum of squares")
+    mm0, mv0 = rng.standard_normal(C).astype(np.float32), rng.uniform(0.5, 1.5, C).astype(np.float32)
+    mmb, mmp = heap(mm0)
+    mvb, mvp = heap(mv0)
+    gb, gp = heap(gamma)
+    bb, bp = heap(beta)
+    out, op = heap(np.zeros((4, C), np.float32))
+    assert lib.tfasr_bn_finalize(sp, gp, bp, mmp, mvp, op, C, c_f(R), c_f(1e-3), c_f(0.99), None) == 0
+    mean, var = x64.mean(0), x64.var(0)
+    rstd = 1 / np.sqrt(var + 1e-3)
+    close(out[2], mean, 1e-4, "bn mean")
+    close(out[3], rstd, 1e-3, "bn rstd")
+    close(mmb, 0.99 * mm0 + 0.01 * mean, 1e-4, "bn moving mean")
+    close(mvb, 0.99 * mv0 + 0.01 * var, 1e-3, "bn moving variance")
+    scale, shift = out[0].astype(np.float64), out[1].astype(np.float64)
+    z = x64 * scale + shift
+    yb, yp = heap(np.zeros((R, C), np.uint16))
+    scp, shp = c_vp(out[0].ctypes.data), c_vp(out[1].ctypes.data)
+    mnp, rsp = c_vp(out[2].ctypes.data), c_vp(out[3].ctypes.data)
+    assert lib.tfasr_bn_apply(xp, scp, shp, yp, c_i64(R), C, act, None) == 0
+    close(from_bf16(yb), checks.act_f(z, act), 6e-3, f"bn apply act={act}")
+    dy = rbf(rng.standard_normal((R, C)))
+    d = dy.astype(np.float64) * checks.act_g(z, act)
+    xh = (x64 - out[2]) * out[3]
+    db, dp = heap(to_bf16(dy))
+    bs, bsp = heap(np.zeros((2, C), np.float32))
+    assert lib.tfasr_bn_bwd_stats(dp, xp, scp, shp, mnp, rsp, bsp, c_i64(R), C, act, None) == 0
+    close(bs[0], d.sum(0), 2e-3, "bn bwd sum d")
+    close(bs[1], (d * xh).sum(0), 2e-3, "bn bwd sum d xhat")
+    dxb, dxp = heap(np.zeros((R, C), np.uint16))
+    assert lib.tfasr_bn_bwd_apply(dp, xp, scp, shp, mnp, rsp, bsp, c_f(R), dxp, c_i64(R), C, act, None) == 0
+    close(from_bf16(dxb), scale * (d - bs[0] / R - xh * bs[1] / R), 8e-3, "bn bwd apply")
+
+
+# ------------------------------------------------------------------------------------------------ depthwise conv K = 31 (dwconv.cu)
+def check_dwconv_v1(lib, B, T, C, K, seed=27):
+    rng = np.random.default_rng(seed)
+    x = rbf(rng.standard_normal((B, T, C)))
+    w = (rng.standard_normal((K, C)) * 0.2).astype(np.float32)
+    bias = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    dy = rbf(rng.standard_normal((B, T, C)))
+    xp = np.concatenate([np.zeros((B, K - 1, C)), x.astype(np.float64)], 1)
+    y_ref = bias + sum(w[k] * xp[:, k:k + T] for k in range(K))
+    dyp = np.concatenate([dy.astype(np.float64), np.zeros((B, K - 1, C))], 1)
+    dx_ref = sum(w[k] * dyp[:, K - 1 - k:K - 1 - k + T] for k in range(K))
+    dw_ref = np.stack([(dy.astype(np.float64) * xp[:, k:k + T]).sum((0, 1)) for k in range(K)])
+    xb, xptr = heap(to_bf16(x))
+    wb, wp = heap(w)
+    bb, bp = heap(bias)
+    yb, yp = heap(np.zeros((B, T, C), np.uint16))
+    assert lib.tfasr_dwconv_causal_fwd(xptr, wp, bp, yp, B, T, C, K, None) == 0
+    close(from_bf16(yb), y_ref, 6e-3, f"dwconv v1 fwd {(B, T, C, K)}")
+    db, dp = heap(to_bf16(dy))
+    dxb, dxp = heap(np.zeros((B, T, C), np.uint16))
+    dwb, dwp = heap(np.zeros((K, C), np.float32))
+    dbb, dbp = heap(np.zeros(C, np.float32))
+    assert lib.tfasr_dwconv_causal_bwd(dp, xptr, wp, dxp, dwp, dbp, B, T, C, K, None) == 0
+    close(from_bf16(dxb), dx_ref, 6e-3, "dwconv v1 dx")
+    close(dwb, dw_ref, 3e-4, "dwconv v1 dw")
+    close(dbb, dy.astype(np.float64).sum((0, 1)), 3e-4, "dwconv v1 dbias")
+
+
+# ------------------------------------------------------------------------------------------------ flat AdamW (param_ops.cu)
+def check_adamw(lib, n, seed=28):
+    rng = np.random.default_rng(seed)
+    p0, g0 = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    m0, v0 = (rng.standard_normal(n) * 0.1).astype(np.float32), rng.uniform(0, 0.1, n).astype(np.float32)
+    mask = (rng.uniform(size=n) < 0.5).astype(np.uint8)
+    lr, t, b1, b2, eps, wd, l2, gs = 3e-3, 7.0, 0.9, 0.98, 1e-9, 1e-2, 1e-3, 0.5
+    g = g0.astype(np.float64) * gs + 2 * l2 * p0 * mask
+    m = b1 * m0 + (1 - b1) * g
+    v = b2 * v0 + (1 - b2) * g * g
+    pr = p0 * (1 - lr * wd) - lr / (1 - b1 ** t) * m / (np.sqrt(v) / np.sqrt(1 - b2 ** t) + eps)
+    bufs = [heap(a) for a in (p0, g0, m0, v0, mask, np.array([lr], np.float32), np.array([t], np.float32))]
+    st = lib.tfasr_adamw_flat_f32(bufs[0][1], bufs[1][1], bufs[2][1], bufs[3][1], bufs[4][1], c_i64(n), bufs[5][1], bufs[6][1], c_f(b1), c_f(b2),
+                                  c_f(eps), c_f(wd), c_f(l2), c_f(gs), 1, None)
+    assert st == 0, st
+    close(bufs[0][0], pr, 1e-5, "adamw p")
+    close(bufs[2][0], m, 1e-5, "adamw m")
+    close(bufs[3][0], v, 1e-5, "adamw v")
+    assert not bufs[1][0].any(), "gradient buffer not cleared"
+
+
 CASES = [
     ("rnnt_kat", check_rnnt_kat),
     ("rnnt_ragged", lambda lib: check_rnnt(lib, 4, 13, 8, 12, [13, 9, 5, 13], [7, 4, 0, 1])),
@@ -180,6 +375,22 @@ CASES = [
     ("logmel_80", lambda lib: check_logmel(lib, 2, 4000)),
     ("logmel_spectrogram_160", lambda lib: check_logmel(lib, 1, 2500, feature_type=1, nbins=160)),
     ("logmel_golden_testflac", check_logmel_golden),
+    ("layernorm_bf16", lambda lib: check_layernorm(lib, 37, 144, False)),  # vector backward variant (D even, <= 512)
+    ("layernorm_f32_odd", lambda lib: check_layernorm(lib, 5, 73, True)),  # scalar variants
+    ("layernorm_wide", lambda lib: check_layernorm(lib, 3, 576, False)),
+    ("scale_mask_glu_dropout", lambda lib: check_scale_mask_glu(lib, 40, 144, 0.3)),
+    ("scale_mask_glu_plain", lambda lib: check_scale_mask_glu(lib, 9, 20, 0.0)),
+    ("batchnorm_swish_vec", lambda lib: check_batchnorm(lib, 300, 144, 1)),  # C % 8 == 0: the templated 16-byte kernel
+    ("batchnorm_relu_scalar", lambda lib: check_batchnorm(lib, 77, 10, 2)),  # odd vector width: scalar kernels; relu branch (new this round)
+    ("batchnorm_relu_vec", lambda lib: check_batchnorm(lib, 130, 32, 2)),  # relu branch of the vector kernel (DeepSpeech2 conv module)
+    ("batchnorm_linear", lambda lib: check_batchnorm(lib, 50, 32, 0)),
+    ("conv1_v1", lambda lib: checks.check_conv1_v2(lib, 2, 37, 13, 16, fwd="tfasr_conv1_3x3s2_fwd", wgrad="tfasr_conv1_3x3s2_wgrad")),
+    ("im2col_v1", lambda lib: checks.check_im2col_v2(lib, 2, 7, 5, 24, im2col="tfasr_im2col_3x3s2", col2im="tfasr_col2im_3x3s2")),
+    ("dwconv_v1_k31", lambda lib: check_dwconv_v1(lib, 2, 70, 16, 31)),  # the register-blocked sliding kernels
+    ("dwconv_v1_generic", lambda lib: check_dwconv_v1(lib, 2, 37, 24, 5)),
+    ("joint_v1", lambda lib: checks.check_joint_v2(lib, 2, 7, 11, 40, fwd="tfasr_joint_tanh_fwd", bwd="tfasr_joint_reduce_bwd")),
+    ("joint_v1_generic", lambda lib: checks.check_joint_v2(lib, 1, 3, 5, 6, fwd="tfasr_joint_tanh_fwd", bwd="tfasr_joint_reduce_bwd")),  # J % 8 != 0
+    ("adamw_flat", lambda lib: check_adamw(lib, 4 * 517)),
 ]
 
 if __name__ == "__main__":
