@@ -38,7 +38,8 @@ def load(asan=False, tsan=False):
               "tfasr_logmel_nframes", "tfasr_layernorm_fwd", "tfasr_layernorm_bwd", "tfasr_scale_mask_colsum", "tfasr_glu_bwd", "tfasr_bn_stats",
               "tfasr_bn_finalize", "tfasr_bn_apply", "tfasr_bn_bwd_stats", "tfasr_bn_bwd_apply", "tfasr_conv1_3x3s2_fwd", "tfasr_conv1_3x3s2_wgrad",
               "tfasr_im2col_3x3s2", "tfasr_col2im_3x3s2", "tfasr_dwconv_causal_fwd", "tfasr_dwconv_causal_bwd", "tfasr_joint_tanh_fwd",
-              "tfasr_joint_reduce_bwd", "tfasr_adamw_flat_f32"):
+              "tfasr_joint_reduce_bwd", "tfasr_adamw_flat_f32", "tfasr_signal_normalize_f32", "tfasr_feature_normalize_f32", "tfasr_specaugment_f32",
+              "tfasr_pack_weights", "tfasr_unpack_add"):
         getattr(lib, n).restype = c_i32
     return lib
 
@@ -363,6 +364,99 @@ def check_adamw(lib, n, seed=28):
     assert not bufs[1][0].any(), "gradient buffer not cleared"
 
 
+# ------------------------------------------------------------------------------------------------ optional normalisations of the frontend
+def check_normalizations(lib, seed=29):
+    from oracle import logmel
+
+    rng = np.random.default_rng(seed)
+    B, N = 2, 3000
+    sig = np.clip(0.2 * rng.standard_normal((B, N)), -1, 1).astype(np.float32)
+    lens = np.array([N, N], np.int32)
+    for mode, kw in ((0, dict(normalize_zscore=True)), (1, dict(normalize_min_max=True))):
+        ref, _ = logmel.feature_extraction(sig.astype(np.float64), lens, dtype=np.float64, normalize_signal=True, **kw)
+        sb, sp = heap(sig)
+        assert lib.tfasr_signal_normalize_f32(sp, B, N, c_f(1e-6), None) == 0
+        close(sb, sig / (np.abs(sig).max(1, keepdims=True) + 1e-6), 1e-6, "signal normalisation")
+        out, _ = _logmel(lib, sb, lens)
+        ob, op = heap(out)
+        assert lib.tfasr_feature_normalize_f32(op, B, out.shape[1], 80, mode, c_f(1e-6), c_f(np.log(2e-6)), None) == 0
+        close(ob, ref[..., 0], 2e-3, f"feature normalisation mode {mode}")
+
+
+# ------------------------------------------------------------------------------------------------ SpecAugment (statistical parity: properties)
+def check_specaugment(lib, seed=30):
+    rng = np.random.default_rng(seed)
+    B, T, F = 4, 90, 40
+    feat = rng.standard_normal((B, T, F)).astype(np.float32) + 5.0  # never equal to the mask value
+    lens = np.array([90, 60, 33, 0], np.int32)
+    n_time, p_ub, n_freq, freq_factor, mask_value = 5, 0.1, 2, 9, 0.0
+    fb, fp = heap(feat)
+    lb, lp = heap(lens)
+    sb, sp = heap(np.array([12345], np.uint64))
+    st = lib.tfasr_specaugment_f32(fp, lp, B, T, F, n_time, c_f(p_ub), c_f(1.0), n_freq, freq_factor, c_f(1.0), c_f(mask_value), sp,
+                                   ctypes.c_ulonglong(3), None)
+    assert st == 0, st
+    masked = fb == mask_value
+    assert np.array_equal(fb[~masked], feat[~masked]), "unmasked cells must be untouched"
+    total = 0
+    for b in range(B):
+        n = int(lens[b])
+        cols = masked[b].all(0)  # frequency masks: whole columns, over all T frames (specaugment.py:58-95 masks the padded spectrogram too)
+        rows = masked[b].all(1)  # time masks: whole frames, inside the utterance
+        assert cols.sum() <= n_freq * (freq_factor - 1), "frequency masks wider than freq_factor allows"
+        assert rows.sum() <= n_time * max(int(n * p_ub) - 1, 0), "time masks wider than p_upperbound allows"
+        assert not rows[n:].any(), "time mask beyond the utterance length"
+        explained = np.zeros((T, F), bool)
+        explained[:, cols] = True
+        explained[rows, :] = True
+        assert not (masked[b] & ~explained).any(), "masked cells that are neither a full column nor a full frame"
+        total += int(masked[b].sum())
+    assert total > 0, "nothing was masked with probabilities 1"
+
+
+# ------------------------------------------------------------------------------------------------ batched weight pack / gradient unpack
+PACK_DT = np.dtype([("src", "<u8"), ("dst_w", "<u8"), ("dst_wt", "<u8"), ("K", "<i4"), ("N", "<i4"), ("src_ld", "<i4"), ("ldw", "<i4"), ("ldwt", "<i4"),
+                    ("c0", "<i4"), ("cs", "<i4"), ("flags", "<i4")])
+
+
+def check_pack_unpack(lib, seed=31):
+    rng = np.random.default_rng(seed)
+    K, D = 37, 24  # a GLU-style kernel [K, 2D] interleaved as (a_0, b_0, a_1, b_1, ...) plus a plain [K2, N2] matrix
+    K2, N2 = 19, 40
+    glu = rng.standard_normal((K, 2 * D)).astype(np.float32)
+    plain = rng.standard_normal((K2, N2)).astype(np.float32)
+    gb, gp = heap(glu)
+    pb, pp = heap(plain)
+    w1, w1p = heap(np.full((K, 2 * D), 0x7FC0, np.uint16))
+    wt1, wt1p = heap(np.full((2 * D, K), 0x7FC0, np.uint16))
+    w2, w2p = heap(np.full((K2, N2), 0x7FC0, np.uint16))
+    wt2, wt2p = heap(np.full((N2, K2), 0x7FC0, np.uint16))
+    tab = np.zeros(3, PACK_DT)
+    tab[0] = (gp.value, w1p.value, wt1p.value, K, D, 2 * D, 2 * D, K, 0, 2, 0)           # a halves -> even columns
+    tab[1] = (gp.value + 4 * D, w1p.value, wt1p.value, K, D, 2 * D, 2 * D, K, 1, 2, 0)   # b halves -> odd columns
+    tab[2] = (pp.value, w2p.value, wt2p.value, K2, N2, N2, N2, K2, 0, 1, 0)
+    tb, tp = heap(tab.view(np.uint8))
+    assert lib.tfasr_pack_weights(tp, 3, None) == 0
+    inter = np.stack([glu[:, :D], glu[:, D:]], 2).reshape(K, 2 * D)
+    assert np.array_equal(from_bf16(w1), rbf(inter)) and np.array_equal(from_bf16(wt1), rbf(inter).T)
+    assert np.array_equal(from_bf16(w2), rbf(plain)) and np.array_equal(from_bf16(wt2), rbf(plain).T)
+    # gradient side: packed fp32 [K, 2D] interleaved -> grad[k, n] += packed[k, c0 + n cs]; packed cleared
+    packed = rng.standard_normal((K, 2 * D)).astype(np.float32)
+    g0 = rng.standard_normal((K, 2 * D)).astype(np.float32)
+    pk, pkp = heap(packed)
+    gr, grp = heap(g0)
+    ut = np.zeros(2, PACK_DT)
+    ut[0] = (grp.value, pkp.value, 0, K, D, 2 * D, 2 * D, 0, 0, 2, 0)
+    ut[1] = (grp.value + 4 * D, pkp.value, 0, K, D, 2 * D, 2 * D, 0, 1, 2, 0)
+    ub, up = heap(ut.view(np.uint8))
+    assert lib.tfasr_unpack_add(up, 2, None) == 0
+    want = g0.copy()
+    want[:, :D] += packed[:, 0::2]
+    want[:, D:] += packed[:, 1::2]
+    close(gr, want, 1e-6, "unpack_add")
+    assert not pk.any(), "packed gradient buffer not cleared"
+
+
 CASES = [
     ("rnnt_kat", check_rnnt_kat),
     ("rnnt_ragged", lambda lib: check_rnnt(lib, 4, 13, 8, 12, [13, 9, 5, 13], [7, 4, 0, 1])),
@@ -391,6 +485,9 @@ CASES = [
     ("joint_v1", lambda lib: checks.check_joint_v2(lib, 2, 7, 11, 40, fwd="tfasr_joint_tanh_fwd", bwd="tfasr_joint_reduce_bwd")),
     ("joint_v1_generic", lambda lib: checks.check_joint_v2(lib, 1, 3, 5, 6, fwd="tfasr_joint_tanh_fwd", bwd="tfasr_joint_reduce_bwd")),  # J % 8 != 0
     ("adamw_flat", lambda lib: check_adamw(lib, 4 * 517)),
+    ("frontend_normalizations", check_normalizations),
+    ("specaugment_properties", check_specaugment),
+    ("pack_unpack", check_pack_unpack),
 ]
 
 if __name__ == "__main__":
