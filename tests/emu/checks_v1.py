@@ -39,7 +39,7 @@ def load(asan=False, tsan=False):
               "tfasr_bn_finalize", "tfasr_bn_apply", "tfasr_bn_bwd_stats", "tfasr_bn_bwd_apply", "tfasr_conv1_3x3s2_fwd", "tfasr_conv1_3x3s2_wgrad",
               "tfasr_im2col_3x3s2", "tfasr_col2im_3x3s2", "tfasr_dwconv_causal_fwd", "tfasr_dwconv_causal_bwd", "tfasr_joint_tanh_fwd",
               "tfasr_joint_reduce_bwd", "tfasr_adamw_flat_f32", "tfasr_signal_normalize_f32", "tfasr_feature_normalize_f32", "tfasr_specaugment_f32",
-              "tfasr_pack_weights", "tfasr_unpack_add"):
+              "tfasr_pack_weights", "tfasr_unpack_add", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd"):
         getattr(lib, n).restype = c_i32
     return lib
 
@@ -457,6 +457,99 @@ def check_pack_unpack(lib, seed=31):
     assert not pk.any(), "packed gradient buffer not cleared"
 
 
+# ------------------------------------------------------------------------------------------------ relative-position attention (attention.cu)
+def _att_allowed(T, length, chunk, history):
+    t = np.arange(T)[:, None]
+    j = np.arange(T)[None, :]
+    ok = np.broadcast_to(t < length, (T, T)).copy()
+    if chunk > 0:
+        c0 = (t // chunk) * chunk
+        hist = T if history < 0 else history
+        ok &= (j >= np.maximum(0, c0 - hist)) & (j < np.minimum(T, c0 + chunk))
+    return ok
+
+
+def check_rel_attention(lib, B, T, N, H, lengths, chunk=0, history=0, seed=32):
+    """MultiHeadRelativeAttention._compute_attention (multihead_attention.py:543-582) with rel_left_shift as out[t, j] = posattn[t, T-1-t+j]
+    (:27-64), the masked softmax (general.py:30-41) and the streaming mask (:104-143): forward and the full backward of the fused kernels —
+    the mma.sync path when T <= 256 and H % 4 == 0, the FP32 kernels otherwise — against float64 numpy on the valid query rows."""
+    rng = np.random.default_rng(seed)
+    NH, R = N * H, 2 * T - 1
+    qkv = rbf(rng.standard_normal((B, T, 3 * NH)) * 0.7)
+    pos = rbf(rng.standard_normal((B, R, NH)) * 0.7)
+    ub = (rng.standard_normal((N, H)) * 0.3).astype(np.float32)
+    vb = (rng.standard_normal((N, H)) * 0.3).astype(np.float32)
+    ln = np.asarray(lengths, np.int32)
+    dctx = rbf(rng.standard_normal((B, T, NH)))
+    for b in range(B):
+        dctx[b, ln[b]:] = 0.0  # padded frames carry no upstream gradient
+    scale = 1.0 / np.sqrt(H)
+    idx = (T - 1 - np.arange(T)[:, None] + np.arange(T)[None, :])  # rel-shift as an index map
+    ctx_ref = np.zeros((B, T, NH))
+    P_ref = np.zeros((B, N, T, T))
+    dqkv_ref = np.zeros((B, T, 3 * NH))
+    dpos_ref = np.zeros((B, R, NH))
+    du_ref, dv_ref = np.zeros((N, H)), np.zeros((N, H))
+    for b in range(B):
+        ok = _att_allowed(T, int(ln[b]), chunk, history)
+        for n in range(N):
+            q = qkv[b, :, n * H:(n + 1) * H].astype(np.float64)
+            k = qkv[b, :, NH + n * H:NH + (n + 1) * H].astype(np.float64)
+            v = qkv[b, :, 2 * NH + n * H:2 * NH + (n + 1) * H].astype(np.float64)
+            pp = pos[b, :, n * H:(n + 1) * H].astype(np.float64)
+            qu, qv = q + ub[n], q + vb[n]
+            S = scale * (qu @ k.T + np.take_along_axis(qv @ pp.T, idx, 1))
+            S = np.where(ok, S, -np.inf)
+            valid = ok.any(1)
+            Sm = np.where(valid[:, None], S, 0.0)
+            P = np.exp(Sm - Sm.max(1, keepdims=True)) * ok
+            P = np.where(valid[:, None], P / np.maximum(P.sum(1, keepdims=True), 1e-300), 0.0)
+            P_ref[b, n] = P
+            ctx_ref[b, :, n * H:(n + 1) * H] = P @ v
+            do = dctx[b, :, n * H:(n + 1) * H].astype(np.float64)
+            dP = do @ v.T
+            dS = P * (dP - (P * dP).sum(1, keepdims=True)) * scale
+            dqkv_ref[b, :, 2 * NH + n * H:2 * NH + (n + 1) * H] = P.T @ do
+            dqkv_ref[b, :, NH + n * H:NH + (n + 1) * H] = dS.T @ qu
+            pw = pp[idx]  # [T, T, H]: the position row each (t, j) reads
+            dqkv_ref[b, :, n * H:(n + 1) * H] = dS @ k + np.einsum("tj,tjh->th", dS, pw)
+            du_ref[n] += (dS @ k).sum(0)
+            dv_ref[n] += np.einsum("tj,tjh->h", dS, pw)
+            np.add.at(dpos_ref[b, :, n * H:(n + 1) * H], idx.reshape(-1), (dS[:, :, None] * qv[:, None, :]).reshape(T * T, H))
+    qb, qp = heap(to_bf16(qkv.reshape(B * T, 3 * NH)))
+    pb, pp_ = heap(to_bf16(pos.reshape(B * R, NH)))
+    ubb, ubp = heap(ub)
+    vbb, vbp = heap(vb)
+    lb, lp = heap(ln)
+    cb, cp = heap(np.zeros((B * T, NH), np.uint16))
+    prb, prp = heap(np.zeros((B, N, T, T), np.uint16))
+    st = lib.tfasr_rel_attention_fwd(qp, 3 * NH, pp_, ubp, vbp, lp, B, T, N, H, chunk, history, cp, prp, None)
+    assert st == 0, st
+    ctx = from_bf16(cb).reshape(B, T, NH)
+    probs = from_bf16(prb)
+    for b in range(B):
+        n_ok = int(ln[b])
+        close(ctx[b, :n_ok], ctx_ref[b, :n_ok], 1.5e-2, f"attention ctx b={b}")
+        close(probs[b, :, :n_ok], P_ref[b, :, :n_ok], 1e-2, f"attention probs b={b}")
+    assert np.isfinite(ctx).all()
+    db, dp = heap(to_bf16(dctx.reshape(B * T, NH)))
+    dsb, dsp = heap(np.zeros((B, N, T, T), np.uint16))
+    dqb, dqp = heap(np.full((B * T, 3 * NH), 0x7FC0, np.uint16))
+    dpb, dpp = heap(np.full((B * R, NH), 0x7FC0, np.uint16))
+    du0, dv0 = rng.standard_normal((N, H)).astype(np.float32), rng.standard_normal((N, H)).astype(np.float32)
+    dub, dup = heap(du0)
+    dvb_, dvp = heap(dv0)
+    st = lib.tfasr_rel_attention_bwd(qp, 3 * NH, pp_, ubp, vbp, lp, B, T, N, H, chunk, history, prp, dp, cp, dsp, dqp, dpp, dup, dvp, None)
+    assert st == 0, st
+    dqkv = from_bf16(dqb).reshape(B, T, 3 * NH)
+    dpos = from_bf16(dpb).reshape(B, R, NH)
+    assert np.isfinite(dqkv).all() and np.isfinite(dpos).all(), "gradient cells left unwritten"
+    close(dqkv, dqkv_ref, 3e-2, "attention dqkv")
+    close(dpos, dpos_ref, 3e-2, "attention dpos")
+    close(dub - du0, du_ref, 3e-2, "attention du")
+    close(dvb_ - dv0, dv_ref, 3e-2, "attention dvb")
+
+
 CASES = [
     ("rnnt_kat", check_rnnt_kat),
     ("rnnt_ragged", lambda lib: check_rnnt(lib, 4, 13, 8, 12, [13, 9, 5, 13], [7, 4, 0, 1])),
@@ -488,6 +581,9 @@ CASES = [
     ("frontend_normalizations", check_normalizations),
     ("specaugment_properties", check_specaugment),
     ("pack_unpack", check_pack_unpack),
+    ("rel_attention_mma", lambda lib: check_rel_attention(lib, 2, 40, 2, 36, [40, 23])),  # Conformer-S head size: the mma.sync kernels, KS = 3
+    ("rel_attention_mma_streaming", lambda lib: check_rel_attention(lib, 1, 48, 2, 16, [41], chunk=8, history=16)),
+    ("rel_attention_fp32", lambda lib: check_rel_attention(lib, 2, 11, 2, 10, [11, 6])),  # T < 16, H % 4 != 0: the FP32 kernels
 ]
 
 if __name__ == "__main__":

@@ -85,6 +85,7 @@ def _rewrite_launches(src: str) -> str:
 
 def convert(src: str, name: str = "?") -> str:
     src = src.replace('#include "common.cuh"', '#include "emu_common.h"')
+    src = src.replace('#include "attention_mma.cuh"', '#include "emu_attention_mma.h"')  # ldmatrix / mma.sync / cp.async on the emulator
     src = re.sub(r"#include\s+<(cuda[\w.]*|math_constants\.h)>\n", "", src)
     src = re.sub(r"template\s*<>\s*__device__", "template <>", src)  # an explicit specialisation cannot repeat the storage class
     src = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu::g_dyn_smem);", src)

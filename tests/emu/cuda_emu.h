@@ -87,6 +87,8 @@ inline __nv_bfloat16 __float2bfloat16_rn(float f) { return __float2bfloat16(f); 
 inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return {__float2bfloat16(a), __float2bfloat16(b)}; }
 inline float __low2float(__nv_bfloat162 v) { return __bfloat162float(v.x); }
 inline float __high2float(__nv_bfloat162 v) { return __bfloat162float(v.y); }
+inline __nv_bfloat16 __low2bfloat16(__nv_bfloat162 v) { return v.x; }
+inline __nv_bfloat16 __high2bfloat16(__nv_bfloat162 v) { return v.y; }
 inline float2 __bfloat1622float2(__nv_bfloat162 v) { return {__bfloat162float(v.x), __bfloat162float(v.y)}; }
 
 // ------------------------------------------------------------------------------------------------ device math on the host

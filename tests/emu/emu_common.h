@@ -6,6 +6,8 @@
 #include "cuda_emu.h"
 
 #include <atomic>
+#include <mutex>
+#include <utility>
 
 #include "../../include/tfasr_b200.h"
 
