@@ -15,7 +15,7 @@ OUT = os.path.join(REPO, "build", "emu")
 SOURCES = ["seqconv.cu", "decode.cu", "rnnt_combine.cu", "conv1.cu", "rnnt_grad_v2.cu", "joint_v2.cu", "subsample_v2.cu", "dwconv_wgrad_v2.cu"]  # launcher files written against simt.cuh
 
 
-V1_SOURCES = ["rnnt_loss.cu", "ctc_loss.cu", "logmel.cu", "fused_rows.cu", "conv_bn.cu", "dwconv.cu", "joint.cu", "param_ops.cu", "specaugment.cu", "attention.cu"]
+V1_SOURCES = ["rnnt_loss.cu", "ctc_loss.cu", "logmel.cu", "fused_rows.cu", "conv_bn.cu", "dwconv.cu", "joint.cu", "param_ops.cu", "specaugment.cu", "attention.cu", "lstm.cu"]
 # first-generation files (written against common.cuh, <<<>>> launches): converted by cu2emu.py into build/emu/gen/*.cpp
 
 

@@ -39,7 +39,8 @@ def load(asan=False, tsan=False):
               "tfasr_bn_finalize", "tfasr_bn_apply", "tfasr_bn_bwd_stats", "tfasr_bn_bwd_apply", "tfasr_conv1_3x3s2_fwd", "tfasr_conv1_3x3s2_wgrad",
               "tfasr_im2col_3x3s2", "tfasr_col2im_3x3s2", "tfasr_dwconv_causal_fwd", "tfasr_dwconv_causal_bwd", "tfasr_joint_tanh_fwd",
               "tfasr_joint_reduce_bwd", "tfasr_adamw_flat_f32", "tfasr_signal_normalize_f32", "tfasr_feature_normalize_f32", "tfasr_specaugment_f32",
-              "tfasr_pack_weights", "tfasr_unpack_add", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd"):
+              "tfasr_pack_weights", "tfasr_unpack_add", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd", "tfasr_lstm_rec_fwd", "tfasr_lstm_rec_bwd",
+              "tfasr_lstm_supported"):
         getattr(lib, n).restype = c_i32
     return lib
 
@@ -550,6 +551,74 @@ def check_rel_attention(lib, B, T, N, H, lengths, chunk=0, history=0, seed=32):
     close(dvb_ - dv0, dv_ref, 3e-2, "attention dvb")
 
 
+# ------------------------------------------------------------------------------------------------ cluster LSTM (lstm.cu)
+def check_cluster_lstm(lib, B, U, R, lengths, with_state, seed=33):
+    """The prediction network's LSTM time loop (keras LSTM, gate order i, f, c, o; base_transducer.py:74-88): an 8-CTA thread-block cluster
+    (emulated with its 8 x 512 threads running concurrently, distributed shared memory and cluster barriers included), forward and backward,
+    against a float64 BPTT."""
+    assert lib.tfasr_lstm_supported(R) == 1
+    rng = np.random.default_rng(seed)
+    sig = lambda x: 1 / (1 + np.exp(-x))  # noqa: E731
+    gx = (rng.standard_normal((B, U, 4 * R)) * 0.8).astype(np.float32)
+    whh = (rng.standard_normal((R, 4 * R)) / np.sqrt(R)).astype(np.float32)
+    h0 = (rng.standard_normal((B, R)) * 0.5).astype(np.float32) if with_state else None
+    c0 = (rng.standard_normal((B, R)) * 0.5).astype(np.float32) if with_state else None
+    ln = np.asarray(lengths, np.int32)
+    W = rbf(whh).astype(np.float64)  # the kernel keeps W_hh as bf16 in shared memory
+    h = h0.astype(np.float64) if with_state else np.zeros((B, R))
+    c = c0.astype(np.float64) if with_state else np.zeros((B, R))
+    hs, cs, gates = [h], [c], []
+    y_ref = np.zeros((B, U, R))
+    for t in range(U):
+        z = gx[:, t] + rbf(h.astype(np.float32)).astype(np.float64) @ W  # h travels between the CTAs as bf16
+        i, f, g, o = sig(z[:, :R]), sig(z[:, R:2 * R]), np.tanh(z[:, 2 * R:3 * R]), sig(z[:, 3 * R:])
+        c = f * c + i * g
+        h = o * np.tanh(c)
+        gates.append((i, f, g, o))
+        hs.append(h)
+        cs.append(c)
+        y_ref[:, t] = np.where((t < ln)[:, None], h, 0.0)
+    bufs = {k: heap(v) for k, v in dict(gx=gx, whh=whh, ln=ln).items()}
+    h0p = heap(h0) if with_state else (None, None)
+    c0p = heap(c0) if with_state else (None, None)
+    yb, yp = heap(np.full((B, U, R), 0x7FC0, np.uint16))
+    sgb, sgp = heap(np.zeros((B, U, 4 * R), np.uint16))
+    scb, scp = heap(np.zeros((B, U, R), np.float32))
+    hTb, hTp = heap(np.zeros((B, R), np.float32))
+    cTb, cTp = heap(np.zeros((B, R), np.float32))
+    st = lib.tfasr_lstm_rec_fwd(bufs["gx"][1], bufs["whh"][1], h0p[1], c0p[1], bufs["ln"][1], yp, sgp, scp, hTp, cTp, B, U, R, None)
+    assert st == 0, st
+    close(from_bf16(yb), y_ref, 2e-2, f"lstm y {(B, U, R)}")
+    close(scb, np.stack(cs[1:], 1), 2e-2, "lstm saved c")
+    close(hTb, hs[-1], 2e-2, "lstm hT")
+    close(cTb, cs[-1], 2e-2, "lstm cT")
+    # backward: dy -> pre-activation gate gradients (zero on masked steps)
+    dy = rbf(rng.standard_normal((B, U, R)))
+    dg_ref = np.zeros((B, U, 4 * R))
+    dh_next, dc_next = np.zeros((B, R)), np.zeros((B, R))
+    for t in range(U - 1, -1, -1):
+        i, f, g, o = gates[t]
+        m = (t < ln)[:, None]
+        dh = np.where(m, dy[:, t], 0.0) + dh_next
+        tc = np.tanh(cs[t + 1])
+        dc = dh * o * (1 - tc * tc) + dc_next
+        di, df, dgg, do = dc * g * i * (1 - i), dc * cs[t] * f * (1 - f), dc * i * (1 - g * g), dh * tc * o * (1 - o)
+        dz = np.concatenate([di, df, dgg, do], 1)
+        dg_ref[:, t] = dz
+        dh_next, dc_next = dz @ W.T, dc * f
+    db, dp = heap(to_bf16(dy))
+    dgb, dgp = heap(np.full((B, U, 4 * R), 0x7FC0, np.uint16))
+    dh0b, dh0p = heap(np.zeros((B, R), np.float32))
+    dc0b, dc0p = heap(np.zeros((B, R), np.float32))
+    st = lib.tfasr_lstm_rec_bwd(dp, sgp, scp, c0p[1], bufs["whh"][1], bufs["ln"][1], dgp, dh0p, dc0p, B, U, R, None)
+    assert st == 0, st
+    got = from_bf16(dgb)
+    assert np.isfinite(got).all(), "gate gradients left unwritten"
+    close(got, dg_ref, 3e-2, "lstm gate gradients")
+    close(dh0b, dh_next, 3e-2, "lstm dh0")
+    close(dc0b, dc_next, 3e-2, "lstm dc0")
+
+
 CASES = [
     ("rnnt_kat", check_rnnt_kat),
     ("rnnt_ragged", lambda lib: check_rnnt(lib, 4, 13, 8, 12, [13, 9, 5, 13], [7, 4, 0, 1])),
@@ -584,6 +653,8 @@ CASES = [
     ("rel_attention_mma", lambda lib: check_rel_attention(lib, 2, 40, 2, 36, [40, 23])),  # Conformer-S head size: the mma.sync kernels, KS = 3
     ("rel_attention_mma_streaming", lambda lib: check_rel_attention(lib, 1, 48, 2, 16, [41], chunk=8, history=16)),
     ("rel_attention_fp32", lambda lib: check_rel_attention(lib, 2, 11, 2, 10, [11, 6])),  # T < 16, H % 4 != 0: the FP32 kernels
+    ("cluster_lstm", lambda lib: check_cluster_lstm(lib, 3, 4, 64, [4, 2, 3], False)),
+    ("cluster_lstm_state", lambda lib: check_cluster_lstm(lib, 2, 3, 128, [3, 3], True)),
 ]
 
 if __name__ == "__main__":

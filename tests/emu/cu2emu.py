@@ -2,7 +2,8 @@
 against the SIMT emulator.  TEST INFRASTRUCTURE ONLY.  Rewrites, and nothing else:
   * `#include "common.cuh"`                           -> `#include "emu_common.h"`
   * `kernel<<<grid, block[, smem[, stream]]>>>(args);` -> `emu::launch(dim3(grid), dim3(block), smem, [&] { kernel(args); });`
-  * `extern __shared__ [__align__(N)] T name[];`       -> `T* name = reinterpret_cast<T*>(emu::g_dyn_smem);`
+  * `extern __shared__ [__align__(N)] T name[];`       -> `T* name = reinterpret_cast<T*>(emu::t_dyn_smem);`
+  * kernels declared `__cluster_dims__(n, 1, 1)` launch through emu::launch_cluster (the n CTAs of a cluster run concurrently)
   * the tanh.approx inline PTX of joint.cu             -> tanhf
   * `#include <cuda_*.h>` lines dropped; `template <> __device__` loses the __device__ (it maps to `static` in the emulator)
 Anything it does not understand (another `asm`, a launch it cannot parse) is an error, not a silent pass-through."""
@@ -40,7 +41,8 @@ def _split_top(s: str) -> list[str]:
     return out
 
 
-def _rewrite_launches(src: str) -> str:
+def _rewrite_launches(src: str, clusters: dict | None = None) -> str:
+    clusters = clusters or {}
     out, pos = [], 0
     while True:
         i = src.find("<<<", pos)
@@ -74,7 +76,11 @@ def _rewrite_launches(src: str) -> str:
             semi += 1
         smem = cfg[2] if len(cfg) > 2 else "0"
         out.append(src[pos:k])
-        call = f"emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({smem}), [&] {{ {kernel}({src[a0 + 1:a1]}); }})"
+        base = kernel.split("<")[0].split("::")[-1]
+        if base in clusters:  # declared with __cluster_dims__(n, 1, 1): the n CTAs of a cluster run concurrently
+            call = f"emu::launch_cluster(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({smem}), {clusters[base]}, [&] {{ {kernel}({src[a0 + 1:a1]}); }})"
+        else:
+            call = f"emu::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({smem}), [&] {{ {kernel}({src[a0 + 1:a1]}); }})"
         if src[semi] == ";":
             out.append(call + ";")
             pos = semi + 1
@@ -88,11 +94,14 @@ def convert(src: str, name: str = "?") -> str:
     src = src.replace('#include "attention_mma.cuh"', '#include "emu_attention_mma.h"')  # ldmatrix / mma.sync / cp.async on the emulator
     src = re.sub(r"#include\s+<(cuda[\w.]*|math_constants\.h)>\n", "", src)
     src = re.sub(r"template\s*<>\s*__device__", "template <>", src)  # an explicit specialisation cannot repeat the storage class
-    src = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu::g_dyn_smem);", src)
+    src = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu::t_dyn_smem);", src)
+    src = src.replace("#include <cooperative_groups.h>\n", "")  # emu_common.h carries the cluster slice of it
+    clusters = {m.group(2): m.group(1).strip() for m in
+                re.finditer(r"__cluster_dims__\(([^,)]+)[^)]*\)\s*(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(", src)}
     src = re.sub(r'asm\("tanh\.approx\.f32 %0, %1;"\s*:\s*"=f"\((\w+)\)\s*:\s*"f"\((\w+)\)\);', r"\1 = tanhf(\2);", src)
     if re.search(r"\basm\b", src):
         raise ValueError(f"{name}: inline PTX the shim does not know")
-    src = _rewrite_launches(src)
+    src = _rewrite_launches(src, clusters)
     if "<<<" in src or "extern __shared__" in src:
         raise ValueError(f"{name}: unconverted CUDA syntax left")
     return src

@@ -122,7 +122,15 @@ inline thread_local dim3 t_blockDim, t_gridDim;
 inline thread_local Warp* t_warp;
 inline thread_local int t_lane;
 inline thread_local std::barrier<>* t_bar;
-inline uint8_t* g_dyn_smem = nullptr;  // exact-size heap block: ASan sees overruns
+inline thread_local uint8_t* t_dyn_smem = nullptr;  // this CTA's dynamic shared memory: an exact-size heap block, so ASan sees overruns
+struct ClusterCtx {  // thread-block cluster (launch_cluster): the CTAs of one cluster run concurrently
+  int size;
+  std::vector<uint8_t*> smem;  // dynamic shared memory of every CTA of the cluster (distributed shared memory)
+  std::barrier<> bar;
+  ClusterCtx(int size_, int threads) : size(size_), smem(size_, nullptr), bar(threads) {}
+};
+inline thread_local ClusterCtx* t_cluster = nullptr;
+inline thread_local int t_cluster_rank = 0;
 inline std::atomic<long> g_launches{0};
 
 // One OS thread per CUDA thread of a block, created once per launch; the blocks of the grid run one after another on them (a second
@@ -140,7 +148,6 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
   for (int w = 0; w * 32 < nth; ++w) warps.emplace_back(new Warp(nth - w * 32 < 32 ? nth - w * 32 : 32));
   // exact size (rounded up to 16 by aligned_alloc: the tail of < 16 bytes is the only slack ASan cannot see)
   uint8_t* smem = smem_bytes ? (uint8_t*)aligned_alloc(16, (smem_bytes + 15) / 16 * 16) : nullptr;
-  g_dyn_smem = smem;
   std::vector<std::thread> ths;
   ths.reserve(nth);
   for (int t = 0; t < nth; ++t)
@@ -151,6 +158,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
       t_warp = warps[t / 32].get();
       t_lane = t % 32;
       t_bar = &bar;
+      t_dyn_smem = smem;
       for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
           for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -161,7 +169,48 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
     });
   for (auto& th : ths) th.join();
   free(smem);
-  g_dyn_smem = nullptr;
+}
+
+// Thread-block clusters of `csize` CTAs along x (__cluster_dims__(csize, 1, 1)): the CTAs of one cluster run CONCURRENTLY — csize x nth OS
+// threads — each with its own dynamic shared memory, CTA barrier and warps, plus one cluster-wide barrier (cluster.sync()) and the
+// table of peers' shared memory (cluster.map_shared_rank).  Clusters run one after another.  Kernels launched this way must keep their
+// shared data in DYNAMIC shared memory: a function-local __shared__ static would be common to the concurrent CTAs.
+template <class F>
+void launch_cluster(dim3 grid, dim3 block, size_t smem_bytes, int csize, F&& body) {
+  const int nth = (int)(block.x * block.y * block.z);
+  if (nth <= 0 || nth > 1024 || csize < 1 || grid.x % csize) abort();
+  g_launches++;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned cx = 0; cx < grid.x / csize; ++cx) {
+        ClusterCtx ctx(csize, csize * nth);
+        std::vector<std::unique_ptr<std::barrier<>>> bars;
+        std::vector<std::vector<std::unique_ptr<Warp>>> warps(csize);
+        for (int r = 0; r < csize; ++r) {
+          bars.emplace_back(new std::barrier<>(nth));
+          for (int w = 0; w * 32 < nth; ++w) warps[r].emplace_back(new Warp(nth - w * 32 < 32 ? nth - w * 32 : 32));
+          ctx.smem[r] = smem_bytes ? (uint8_t*)aligned_alloc(16, (smem_bytes + 15) / 16 * 16) : nullptr;
+        }
+        std::vector<std::thread> ths;
+        ths.reserve((size_t)csize * nth);
+        for (int r = 0; r < csize; ++r)
+          for (int t = 0; t < nth; ++t)
+            ths.emplace_back([&, r, t] {
+              t_threadIdx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+              t_blockIdx = {cx * csize + r, by, bz};
+              t_blockDim = block;
+              t_gridDim = grid;
+              t_warp = warps[r][t / 32].get();
+              t_lane = t % 32;
+              t_bar = bars[r].get();
+              t_dyn_smem = ctx.smem[r];
+              t_cluster = &ctx;
+              t_cluster_rank = r;
+              body();
+            });
+        for (auto& th : ths) th.join();
+        for (int r = 0; r < csize; ++r) free(ctx.smem[r]);
+      }
 }
 
 template <class T>
@@ -205,4 +254,5 @@ inline void atomicAdd(float4* p, float4 v) {  // red.global.add.v4.f32: four ind
 inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_relaxed); }
 
 // dynamic shared memory: kernels declare it with TFASR_DYN_SMEM(name)
-#define TFASR_DYN_SMEM(name) uint8_t* name = emu::g_dyn_smem
+#define TFASR_DYN_SMEM(name) uint8_t* name = emu::t_dyn_smem
+#define __cluster_dims__(...)

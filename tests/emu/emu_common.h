@@ -36,6 +36,19 @@ inline int64_t max(int64_t a, int b) { return a > b ? a : b; }
 inline int64_t max(int a, int64_t b) { return a > b ? a : b; }
 inline size_t min(size_t a, int b) { return a < (size_t)b ? a : (size_t)b; }
 
+// ---- cooperative_groups: the cluster slice the LSTM kernels use
+namespace cooperative_groups {
+struct cluster_group {
+  unsigned block_rank() const { return (unsigned)emu::t_cluster_rank; }
+  template <class T>
+  T* map_shared_rank(T* p, unsigned rank) const {  // the same offset inside the peer CTA's shared memory
+    return reinterpret_cast<T*>(emu::t_cluster->smem[rank] + (reinterpret_cast<uint8_t*>(p) - emu::t_dyn_smem));
+  }
+  void sync() const { emu::t_cluster->bar.arrive_and_wait(); }
+};
+inline cluster_group this_cluster() { return {}; }
+}  // namespace cooperative_groups
+
 namespace tfasr {
 
 inline std::atomic<int> g_launch_count{0};
