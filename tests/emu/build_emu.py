@@ -48,7 +48,7 @@ def build(asan: bool = False, tsan: bool = False) -> str:
     objdir = os.path.join(OUT, "obj_" + tag)
     os.makedirs(objdir, exist_ok=True)
     lib = os.path.join(OUT, "libtfasr_emu.so" if tag == "plain" else f"libtfasr_emu_{tag}.so")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES] + _generate_v1()
+    srcs = [os.path.join(CSRC, s) for s in SOURCES] + _generate_v1() + [os.path.join(HERE, "emu_support.cpp")]
     hdrs = [os.path.join(CSRC, h) for h in ("simt.cuh", "seqconv_kernels.cuh", "decode_kernels.cuh", "dropout.cuh")] + \
            [os.path.join(HERE, h) for h in ("cuda_emu.h", "emu_common.h", "emu_attention_mma.h", "cu2emu.py")] + [os.path.join(REPO, "include", "tfasr_b200.h"), os.path.abspath(__file__)]
     hdr_m = max(os.path.getmtime(h) for h in hdrs)

@@ -56,7 +56,10 @@ def test_emulated_product_kernel(emu_lib_v1, name):
     oracle/rnnt.py / ctc.py / logmel.py on ragged batches."""
     import checks_v1
 
-    dict(checks_v1.CASES)[name](emu_lib_v1)
+    try:
+        dict(checks_v1.CASES)[name](emu_lib_v1)
+    except checks_v1.SkipCase as e:
+        pytest.skip(str(e))
 
 
 def test_emulated_kernels_under_address_sanitizer():
