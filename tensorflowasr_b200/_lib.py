@@ -141,6 +141,7 @@ SIGNATURES = {
 }
 
 _lib = None
+EMULATED = False  # set by tests/emu_backend.py only: the kernels run as their own source on the CPU emulator, tensors live on the host
 
 
 def load() -> ctypes.CDLL:

@@ -13,6 +13,7 @@ import math
 import torch
 from torch import nn
 
+from . import _lib as _lib_mod
 from . import dist as tdist
 from . import schemas
 from .features import FeatureExtraction
@@ -43,7 +44,7 @@ def make_optimizer(model: nn.Module, learning_rate=None, beta_1=0.9, beta_2=0.98
     (tests of the host logic) torch's AdamW."""
     lr0 = learning_rate(1) if callable(learning_rate) else (learning_rate or 1e-3)
     params = [p for p in model.parameters() if p.requires_grad]
-    on_gpu = params[0].is_cuda
+    on_gpu = params[0].is_cuda or _lib_mod.EMULATED
     # lr lives in a device tensor so that a captured CUDA graph picks up the schedule's new value at every replay
     lr = torch.tensor(float(lr0), device=params[0].device) if on_gpu else lr0
     if on_gpu and flat:

@@ -16,7 +16,7 @@ from . import _lib
 class FlatAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         params = [p for p in params if p.requires_grad]
-        if not params or not params[0].is_cuda:
+        if not params or not (params[0].is_cuda or _lib.EMULATED):
             raise RuntimeError("FlatAdamW needs CUDA parameters (libtfasr_b200 has no CPU path)")
         dev = params[0].device
         if not torch.is_tensor(lr):

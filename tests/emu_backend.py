@@ -121,6 +121,7 @@ def install(monkeypatch):
     monkeypatch.setattr(_lib, "load", lambda: emu)
     monkeypatch.setattr(_lib, "stream_ptr", lambda device=None: None)
     monkeypatch.setattr(_lib, "require_cuda", lambda t, what: None)
+    monkeypatch.setattr(_lib, "EMULATED", True)  # lets make_optimizer build the one-launch FlatAdamW over host tensors
 
     def ptr(t):
         if t is None:
