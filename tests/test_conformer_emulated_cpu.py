@@ -127,3 +127,84 @@ def test_train_step_with_flat_adamw_learns_on_emulated_kernels(monkeypatch):
         ops.set_precision("fp32")
     assert emu.calls.get("tfasr_adamw_flat_f32", 0) == 3
     assert losses[2] < losses[1] < losses[0], losses
+
+
+def _grads_close(ref_g, g, skip, min_checked, cos_min=0.95):
+    checked = 0
+    for n, r in ref_g.items():
+        if any(k in n for k in skip) or n not in g or r.norm() < 1e-5 * max(1.0, r.numel() ** 0.5):
+            continue
+        assert _cos(g[n], r) > cos_min, (n, _cos(g[n], r))
+        checked += 1
+    assert checked >= min_checked, checked
+
+
+def test_contextnet_transducer_fused_route_on_emulated_kernels(monkeypatch):
+    """ContextNet transducer: log-mel -> fused_seq encoder route (depthwise / squeeze-excite kernels, BatchNorm kernels, GEMM
+    contract) -> prediction net -> joint -> RNN-T loss, forward + backward, against the fp32 library route."""
+    import tensorflowasr_b200 as tfasr
+    from tensorflowasr_b200 import ops
+
+    emu = emu_backend.install(monkeypatch)
+    blocks = [dict(nlayers=1, kernel_size=5, filters=32, strides=1, residual=False, activation="silu", padding="causal"),
+              dict(nlayers=2, kernel_size=5, filters=32, strides=2, residual=True, activation="silu", padding="causal"),
+              dict(nlayers=1, kernel_size=3, filters=48, strides=2, residual=True, activation="silu", padding="causal")]
+    V = 16
+    cfg = tfasr.contextnet_config(vocab_size=V, alpha=0.5)
+    cfg.update(encoder_blocks=blocks, prediction_embed_dim=16, prediction_rnn_units=64, joint_dim=16)
+    model = tfasr.ContextNet(**cfg, seed=4)
+    data = _batch(V=V)
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    try:
+        ops.set_precision("fp32")
+        ops.set_fused(False)
+        ref_loss, ref_g = _run(model, data, state0)
+        ops.set_precision("bf16")
+        ops.set_fused(True)
+        ops.set_fused_seq(True)
+        emu.calls.clear()
+        loss, g = _run(model, data, state0)
+    finally:
+        ops.set_fused_seq(False)
+        ops.set_fused(True)
+        ops.set_precision("fp32")
+    for k in ("tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_bwd", "tfasr_se_dy",
+              "tfasr_bn_stats", "tfasr_bn_bwd_apply"):
+        assert emu.calls.get(k, 0) > 0, (k, sorted(emu.calls))
+    torch.testing.assert_close(loss, ref_loss, rtol=4e-2, atol=4e-2)
+    _grads_close(ref_g, g, skip=("conv__bias",), min_checked=30)
+
+
+def test_deepspeech2_ctc_fused_route_on_emulated_kernels(monkeypatch):
+    """DeepSpeech2: spectrogram frontend -> fused_seq conv module (general im2col / col2im, BatchNorm + relu kernels) ->
+    BiLSTM on the cluster LSTM kernels -> fc (bias + relu epilogue contract) -> vocab Dense -> CTC loss kernel, forward + backward."""
+    import tensorflowasr_b200 as tfasr
+    from tensorflowasr_b200 import ops, schemas
+
+    emu = emu_backend.install(monkeypatch)
+    cfg = tfasr.deepspeech2_base_config(vocab_size=12)
+    cfg.update(conv_kernels=[[5, 7], [3, 5]], conv_strides=[[2, 2], [1, 2]], conv_filters=[8, 8], rnn_nlayers=1, rnn_units=64, fc_units=24, rnn_dropout=0.0,
+               fc_dropout=0.0)
+    cfg["speech_config"].update(num_feature_bins=24)
+    model = tfasr.DeepSpeech2(**cfg, seed=2)
+    model.compile(optimizer=torch.optim.SGD(model.parameters(), lr=0.0))
+    g0 = torch.Generator().manual_seed(1)
+    B, N, L = 2, 6400, 4
+    sig = (0.1 * torch.randn(B, N, generator=g0)).clamp(-1, 1)
+    data = schemas.TrainData(schemas.TrainInput(sig, torch.tensor([N, N - 1500], dtype=torch.int32), None, None),
+                             schemas.TrainLabel(torch.randint(1, 12, (B, L), generator=g0, dtype=torch.int32), torch.tensor([L, 2], dtype=torch.int32)))
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    try:
+        ops.set_precision("fp32")
+        ref_loss, ref_g = _run(model, data, state0)
+        ops.set_precision("bf16")
+        ops.set_fused_seq(True)
+        emu.calls.clear()
+        loss, g = _run(model, data, state0)
+    finally:
+        ops.set_fused_seq(False)
+        ops.set_precision("fp32")
+    for k in ("tfasr_conv_im2col", "tfasr_conv_col2im", "tfasr_bn_apply", "tfasr_lstm_rec_fwd", "tfasr_lstm_rec_bwd", "tfasr_ctc_loss_f32"):
+        assert emu.calls.get(k, 0) > 0, (k, sorted(emu.calls))
+    torch.testing.assert_close(loss, ref_loss, rtol=4e-2, atol=4e-2)
+    _grads_close(ref_g, g, skip=("conv2d__bias",), min_checked=12, cos_min=0.93)
