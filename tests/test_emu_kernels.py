@@ -62,7 +62,16 @@ def test_emulated_product_kernel(emu_lib_v1, name):
         pytest.skip(str(e))
 
 
+def _run_sanitized(flag, env):
+    """checks.py and checks_v1.py under one sanitizer, side by side."""
+    procs = [(script, subprocess.Popen([sys.executable, os.path.join(HERE, "emu", script), flag], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                       env=env)) for script in ("checks.py", "checks_v1.py")]
+    return [(script,) + p.communicate(timeout=1800) + (p.returncode,) for script, p in procs]
+
+
 def test_emulated_kernels_under_address_sanitizer():
+    """Every buffer handed to the emulated kernels is an exact-size heap block: an out-of-bounds global or shared access is a hard ASan error —
+    the CPU stand-in for compute-sanitizer memcheck (an injected off-by-one is caught with the kernel's source line)."""
     import build_emu
 
     rt = build_emu.asan_runtime()
@@ -70,15 +79,14 @@ def test_emulated_kernels_under_address_sanitizer():
         pytest.skip("libasan not available")
     build_emu.build(asan=True)
     env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0")
-    for script in ("checks.py", "checks_v1.py"):
-        r = subprocess.run([sys.executable, os.path.join(HERE, "emu", script), "--asan"], capture_output=True, text=True, env=env, timeout=1500)
-        assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, script + "\n" + r.stdout[-2000:] + r.stderr[-4000:]
+    for script, out, err, rc in _run_sanitized("--asan", env):
+        assert rc == 0 and "AddressSanitizer" not in err, script + "\n" + out[-2000:] + err[-4000:]
 
 
 def test_emulated_kernels_under_thread_sanitizer():
-    """Every CUDA thread is an OS thread in the emulator, __syncthreads / __syncwarp / shuffles are real barriers and atomics real atomics:
-    ThreadSanitizer then reports exactly the accesses that are NOT ordered by them — the CPU stand-in for compute-sanitizer racecheck
-    (a deleted __syncthreads is reported; it found an unordered entry-state read in the decode kernel when first run)."""
+    """Every CUDA thread is an OS thread in the emulator, __syncthreads / __syncwarp / shuffles / cluster.sync are real barriers and atomics
+    real atomics: ThreadSanitizer then reports exactly the accesses that are NOT ordered by them — the CPU stand-in for compute-sanitizer
+    racecheck (a deleted __syncthreads is reported; it found an unordered entry-state read in the decode kernel when first run)."""
     import build_emu
 
     rt = build_emu.tsan_runtime()
@@ -86,8 +94,6 @@ def test_emulated_kernels_under_thread_sanitizer():
         pytest.skip("libtsan not available")
     build_emu.build(tsan=True)
     env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0 halt_on_error=0")
-    for script in ("checks.py", "checks_v1.py"):
-        r = subprocess.run([sys.executable, os.path.join(HERE, "emu", script), "--tsan"], capture_output=True, text=True, env=env, timeout=1800)
-        assert r.returncode == 0, script + "\n" + r.stdout[-2000:] + r.stderr[-4000:]
-        assert "WARNING: ThreadSanitizer" not in r.stderr, script + "\n" + r.stderr[-6000:]
-
+    for script, out, err, rc in _run_sanitized("--tsan", env):
+        assert rc == 0, script + "\n" + out[-2000:] + err[-4000:]
+        assert "WARNING: ThreadSanitizer" not in err, script + "\n" + err[-6000:]
