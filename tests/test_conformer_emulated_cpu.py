@@ -208,3 +208,26 @@ def test_deepspeech2_ctc_fused_route_on_emulated_kernels(monkeypatch):
         assert emu.calls.get(k, 0) > 0, (k, sorted(emu.calls))
     torch.testing.assert_close(loss, ref_loss, rtol=4e-2, atol=4e-2)
     _grads_close(ref_g, g, skip=("conv2d__bias",), min_checked=12, cos_min=0.93)
+
+
+def test_feature_extraction_api_reproduces_testflac_goldens(monkeypatch):
+    """tensorflowasr_b200.FeatureExtraction (the product's Python class + the log-mel kernel source on the emulator) on the reference's
+    tests/test.flac: default layer arguments, the 16 000-sample `padding` variant of tests/test_layers.py:37, and the 160-bin spectrogram of
+    the DeepSpeech2 configs — against tests/golden/logmel_testflac.npz."""
+    import os
+
+    import numpy as np
+
+    import tensorflowasr_b200 as tfasr
+
+    emu_backend.install(monkeypatch)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "logmel_testflac.npz"))
+    sig = torch.from_numpy(g["pcm"].astype(np.float32) / 32768.0)[None, :]
+    n = torch.tensor([sig.shape[1]], dtype=torch.int32)
+    for kwargs, feat_key, len_key in ((dict(), "features", "features_length"), (dict(padding=16000), "features_padded", "features_padded_length"),
+                                      (dict(feature_type="spectrogram", num_feature_bins=160), "spectrogram160", "features_length")):
+        feats, flen = tfasr.FeatureExtraction(**kwargs)((sig, n), training=False)
+        want = torch.from_numpy(g[feat_key])
+        assert feats.shape == want.shape and flen.tolist() == g[len_key].tolist()
+        err = (feats - want).abs().max().item()
+        assert err < 2e-3, (feat_key, err)  # north_star: log-mel within 1e-3 relative (values span 1 .. 14 in magnitude)
