@@ -469,4 +469,6 @@ def greedy_decode(weights, e_proj, nframes, prev_tok, states, frame_idx, tok_idx
     assert weights["w_ih"].shape == (E, 4 * R) and weights["wp"].shape == (R, J) and weights["wv"].shape == (J, V) and states.shape == (B, 2, R)
     P.T, P.E, P.R, P.J, P.V, P.max_tokens, P.blank = T, E, R, J, V, tokens.shape[1], int(blank)
     P.mode, P.max_iters, P.per_frame_cap = int(mode), int(max_iters), int(per_frame_cap)
+    if _lib.EMULATED:
+        threads = min(int(threads), 64)  # one OS thread per CUDA thread on the emulator: keep the CTA small
     _lib.check(lib.tfasr_greedy_decode_f32(ctypes.byref(P), B, int(threads), _st(e_proj)), "tfasr_greedy_decode_f32")

@@ -231,3 +231,48 @@ def test_feature_extraction_api_reproduces_testflac_goldens(monkeypatch):
         assert feats.shape == want.shape and flen.tolist() == g[len_key].tolist()
         err = (feats - want).abs().max().item()
         assert err < 2e-3, (feat_key, err)  # north_star: log-mel within 1e-3 relative (values span 1 .. 14 in magnitude)
+
+
+def test_greedy_decode_tokens_bit_exact_vs_oracle_on_emulator(monkeypatch):
+    """The GPU suite's greedy-token gate (north_star: bit-exact token indices) on the CPU: log-mel kernel (emulated) -> Conformer encoder (fp32
+    route) -> both reference decode loops, host-driven AND through the persistent decode kernel (its own source on the emulator), against the
+    float64 oracle's restatement of base_transducer.py:496-712."""
+    import numpy as np
+
+    import tensorflowasr_b200 as tfasr
+    from oracle import conformer as oc
+    from oracle import logmel as ologmel
+    from tensorflowasr_b200 import ops, schemas
+
+    emu_backend.install(monkeypatch)
+    ops.set_precision("fp32")
+    V = 32
+    cfg = tfasr.conformer_small_config(vocab_size=V)
+    cfg["speech_config"].pop("augmentation_config", None)
+    cfg.update(encoder_num_blocks=2, encoder_dropout=0.0)
+    model = tfasr.Conformer(**cfg, seed=1)
+    ocfg = oc.ConformerConfig(vocab_size=V, num_blocks=2)
+    params = oc.init_params(ocfg, seed=5, randomize_all=True)
+    params["joint.vocab.bias"][0] += -0.6  # make random weights emit labels, not only blanks (as tests/test_gpu_model.py does)
+    model.load_named_weights(params)
+    model.eval()
+    g = torch.Generator().manual_seed(0)
+    B, N = 3, 9600
+    sig = (0.1 * torch.randn(B, N, generator=g)).clamp(-1, 1)
+    sig_len = torch.tensor([N, N - 2500, N // 2], dtype=torch.int32)
+    feats, flen = ologmel.feature_extraction(sig.numpy().astype(np.float64), sig_len.numpy(), dtype=np.float64)
+    p = {k: v.double() for k, v in params.items()}
+    enc, elen = oc.conformer_encoder(torch.from_numpy(feats), torch.from_numpy(flen).long(), p, ocfg, training=False)
+    ref, margin = oc.greedy_batch(enc, elen, p, ocfg)
+    ref1, margin1 = oc.greedy_single(enc[:1], int(elen[0]), p, ocfg)
+    assert margin > 1e-3 and margin1 > 1e-3, "pick other weights: the oracle's own arg-max is a near-tie"
+    assert int((ref[:, 2:] != 0).sum()) >= 3
+    try:
+        for flag in (False, True):
+            ops.set_persistent_decode(flag)
+            out = model.recognize(schemas.PredictInput(sig, sig_len))
+            assert out.tokens.shape == ref.shape and out.tokens.long().tolist() == ref.tolist(), ("persistent" if flag else "host loop")
+            out1 = model.recognize(schemas.PredictInput(sig[:1], sig_len[:1]))
+            assert out1.tokens[0].tolist() == ref1, ("persistent" if flag else "host loop", "single")
+    finally:
+        ops.set_persistent_decode(False)
