@@ -276,3 +276,40 @@ def test_greedy_decode_tokens_bit_exact_vs_oracle_on_emulator(monkeypatch):
             assert out1.tokens[0].tolist() == ref1, ("persistent" if flag else "host loop", "single")
     finally:
         ops.set_persistent_decode(False)
+
+
+def test_smoke_parity_check_on_emulator(monkeypatch):
+    """What __graft_entry__.smoke() asserts on cuda:0, on the CPU: log-mel kernel -> Conformer (fp32 route) -> joint -> RNN-T loss kernels against
+    the float64 oracle, 1e-3 relative."""
+    import numpy as np
+
+    import tensorflowasr_b200 as tfasr
+    from oracle import conformer as oc
+    from oracle import logmel as ologmel
+    from tensorflowasr_b200 import ops, schemas
+
+    emu = emu_backend.install(monkeypatch)
+    ops.set_precision("fp32")
+    torch.manual_seed(0)
+    V, B, N, U = 64, 2, 16000, 5
+    cfg = tfasr.conformer_small_config(vocab_size=V)
+    cfg["speech_config"].pop("augmentation_config", None)
+    cfg.update(encoder_num_blocks=2, encoder_dropout=0.0)
+    model = tfasr.Conformer(**cfg, seed=7)
+    ocfg = oc.ConformerConfig(vocab_size=V, num_blocks=2)
+    params = oc.init_params(ocfg, seed=11, randomize_all=True)
+    model.load_named_weights(params)
+    sig = (0.1 * torch.randn(B, N)).clamp(-1, 1)
+    sig_len = torch.tensor([N, N - 3000], dtype=torch.int32)
+    labels = torch.randint(1, V, (B, U), dtype=torch.int32)
+    lab_len = torch.tensor([U, U - 2], dtype=torch.int32)
+    pred = torch.cat([torch.zeros(B, 1, dtype=torch.int32), labels], 1)
+    data = schemas.TrainData(schemas.TrainInput(sig, sig_len, pred, lab_len + 1), schemas.TrainLabel(labels, lab_len))
+    losses = model.compute_losses(data, training=False)
+    feats, flen = ologmel.feature_extraction(sig.numpy().astype(np.float64), sig_len.numpy(), dtype=np.float64)
+    p64 = {k: v.double() for k, v in params.items()}
+    logits, llen = oc.transducer_forward(p64, ocfg, torch.from_numpy(feats), torch.from_numpy(flen).long(), pred, (lab_len + 1).long())
+    ref = oc.rnnt_loss_torch(logits, labels, llen.int(), lab_len)
+    rel = ((losses.detach().double() - ref).abs() / ref.abs()).max().item()
+    assert rel < 1e-3, (losses.tolist(), ref.tolist())
+    assert emu.calls.get("tfasr_logmel_f32", 0) == 1 and emu.calls.get("tfasr_rnnt_loss_fwd_f32", 0) + emu.calls.get("tfasr_rnnt_loss_f32", 0) >= 1, emu.calls
