@@ -15,7 +15,9 @@ OUT = os.path.join(REPO, "build", "emu")
 SOURCES = ["seqconv.cu", "decode.cu", "rnnt_combine.cu", "conv1.cu", "rnnt_grad_v2.cu", "joint_v2.cu", "subsample_v2.cu", "dwconv_wgrad_v2.cu"]  # launcher files written against simt.cuh
 
 
-V1_SOURCES = ["rnnt_loss.cu", "ctc_loss.cu", "logmel.cu", "fused_rows.cu", "conv_bn.cu", "dwconv.cu", "joint.cu", "param_ops.cu", "specaugment.cu", "attention.cu", "lstm.cu"]
+V1_SOURCES = ["rnnt_loss.cu", "ctc_loss.cu", "logmel.cu", "fused_rows.cu", "conv_bn.cu", "dwconv.cu", "joint.cu", "param_ops.cu", "specaugment.cu", "attention.cu", "lstm.cu", "gemm.cu", "gemm_inst_64.cu", "gemm_inst_128.cu",
+              "gemm_inst_160.cu", "gemm_inst_192.cu", "gemm_inst_256.cu"]
+V1_HEADERS = ["gemm_kernel.cuh"]  # converted next to the sources that include them
 # first-generation files (written against common.cuh, <<<>>> launches): converted by cu2emu.py into build/emu/gen/*.cpp
 
 
@@ -25,6 +27,11 @@ def _generate_v1() -> list[str]:
     gen = os.path.join(OUT, "gen")
     os.makedirs(gen, exist_ok=True)
     outs = []
+    for name in V1_HEADERS:
+        dst = os.path.join(gen, name)
+        text = cu2emu.convert(open(os.path.join(CSRC, name)).read(), name)
+        if not os.path.exists(dst) or open(dst).read() != text:
+            open(dst, "w").write(text)
     for name in V1_SOURCES:
         src = os.path.join(CSRC, name)
         dst = os.path.join(gen, name[:-3] + ".cpp")
@@ -50,7 +57,8 @@ def build(asan: bool = False, tsan: bool = False) -> str:
     lib = os.path.join(OUT, "libtfasr_emu.so" if tag == "plain" else f"libtfasr_emu_{tag}.so")
     srcs = [os.path.join(CSRC, s) for s in SOURCES] + _generate_v1() + [os.path.join(HERE, "emu_support.cpp")]
     hdrs = [os.path.join(CSRC, h) for h in ("simt.cuh", "seqconv_kernels.cuh", "decode_kernels.cuh", "dropout.cuh")] + \
-           [os.path.join(HERE, h) for h in ("cuda_emu.h", "emu_common.h", "emu_attention_mma.h", "cu2emu.py")] + [os.path.join(REPO, "include", "tfasr_b200.h"), os.path.abspath(__file__)]
+           [os.path.join(HERE, h) for h in ("cuda_emu.h", "emu_common.h", "emu_attention_mma.h", "emu_sm100.h", "cu2emu.py")] + \
+           [os.path.join(CSRC, "gemm_kernel.cuh")] + [os.path.join(REPO, "include", "tfasr_b200.h"), os.path.abspath(__file__)]
     hdr_m = max(os.path.getmtime(h) for h in hdrs)
     flags = ["-std=c++20", "-O1", "-g", "-fPIC", "-pthread", "-DTFASR_EMU_BUILD", "-I", HERE, "-I", os.path.join(REPO, "include"), "-I", CSRC]
     if asan:

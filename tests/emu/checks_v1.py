@@ -24,6 +24,13 @@ from checks import close, from_bf16, heap, rbf, to_bf16  # noqa: E402
 c_i32, c_i64, c_vp, c_sz, c_f = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float
 
 
+class GemmEpilogue(ctypes.Structure):
+    _fields_ = [("bias", c_vp), ("aux", c_vp), ("residual", c_vp), ("mul", c_vp), ("colsum", c_vp), ("ld_aux", c_i32), ("ld_residual", c_i32),
+                ("ld_mul", c_i32), ("c_f32", c_i32), ("activation", c_i32), ("glu", c_i32), ("mul_mode", c_i32), ("residual_scale", c_f),
+                ("alpha", c_f), ("dropout_p", c_f), ("atomic_out", c_i32), ("k_splits", c_i32), ("dropout_seed_ptr", c_vp),
+                ("dropout_salt", ctypes.c_ulonglong), ("rowstats", c_vp)]
+
+
 class LogmelCfg(ctypes.Structure):
     _fields_ = [(n, c_i32) for n in ("sample_rate", "frame_length", "frame_step", "nfft", "num_feature_bins", "feature_type", "pad_end", "log_base10",
                                      "padding")] + [(n, c_f) for n in ("preemphasis", "epsilon", "lower_edge_hertz", "upper_edge_hertz")]
@@ -40,7 +47,7 @@ def load(asan=False, tsan=False):
               "tfasr_im2col_3x3s2", "tfasr_col2im_3x3s2", "tfasr_dwconv_causal_fwd", "tfasr_dwconv_causal_bwd", "tfasr_joint_tanh_fwd",
               "tfasr_joint_reduce_bwd", "tfasr_adamw_flat_f32", "tfasr_signal_normalize_f32", "tfasr_feature_normalize_f32", "tfasr_specaugment_f32",
               "tfasr_pack_weights", "tfasr_unpack_add", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd", "tfasr_lstm_rec_fwd", "tfasr_lstm_rec_bwd",
-              "tfasr_lstm_supported"):
+              "tfasr_lstm_supported", "tfasr_gemm_bf16"):
         getattr(lib, n).restype = c_i32
     return lib
 
@@ -625,6 +632,106 @@ def check_cluster_lstm(lib, B, U, R, lengths, with_state, seed=33):
     close(dc0b, dc_next, 3e-2, "lstm dc0")
 
 
+# ------------------------------------------------------------------------------------------------ tcgen05 GEMM (gemm.cu, gemm_kernel.cuh)
+def check_gemm(lib, M, N, K, *, f32_out=False, bias=False, act=0, aux=False, glu=False, residual=False, mul_mode=0, colsum=False, mn_major=False,
+               accumulate=False, k_splits=1, rowstats=False, dropout=0.0, alpha=1.0, seed=34):
+    """C = epilogue(alpha * A . B^T) through tfasr_gemm_bf16 on the emulator: TMA tile loads with the 128-byte swizzle, the mbarrier ring, UMMA
+    descriptors (K-major and MN-major), TMEM accumulators, tcgen05.ld epilogue, TMA stores / reduce-adds — against float64 numpy."""
+    rng = np.random.default_rng(seed)
+    if mn_major:
+        a, b = rbf(rng.standard_normal((K, M))), rbf(rng.standard_normal((K, N)) / np.sqrt(K))
+        v = a.astype(np.float64).T @ b
+        lda, ldb = M, N
+    else:
+        a, b = rbf(rng.standard_normal((M, K))), rbf(rng.standard_normal((N, K)) / np.sqrt(K))
+        v = a.astype(np.float64) @ b.astype(np.float64).T
+        lda = ldb = K
+    v = v * alpha
+    e = GemmEpilogue()
+    keep = []
+    if bias:
+        bv = rng.standard_normal(N).astype(np.float32)
+        bb, bp = heap(bv)
+        keep.append(bb)
+        e.bias = bp
+        v = v + bv
+    stats_ref = checks.gemm_rowstats_ref(v.astype(np.float32)) if rowstats else None
+    pre = v.copy()
+    n_out = N
+    if glu:
+        v = v[:, 0::2] / (1 + np.exp(-v[:, 1::2])) * 1.0
+        n_out = N // 2
+    elif act:
+        v = {1: lambda z: z / (1 + np.exp(-z)), 2: lambda z: np.maximum(z, 0), 3: np.tanh}[act](v)
+    if mul_mode:
+        z = rbf(rng.standard_normal((M, n_out)))
+        zb, zp = heap(to_bf16(z))
+        keep.append(zb)
+        e.mul, e.ld_mul, e.mul_mode = zp, n_out, mul_mode
+        z64 = z.astype(np.float64)
+        if mul_mode == 1:
+            sg = 1 / (1 + np.exp(-z64))
+            v = v * sg * (1 + z64 * (1 - sg))
+        elif mul_mode == 2:
+            v = v * (1 - z64 * z64)
+        else:
+            v = v * z64
+    if dropout > 0:
+        import checks_v1 as me  # the counter hash of csrc/dropout.cuh, restated in numpy above
+
+        dseed, salt = 99, 5
+        kp = me._dropout_keep(dseed, salt, M, n_out, dropout)
+        sb, sp = heap(np.array([dseed], np.uint64))
+        keep.append(sb)
+        e.dropout_p, e.dropout_seed_ptr, e.dropout_salt = dropout, sp, salt
+        v = np.where(kp, v / (1 - dropout), 0.0)
+    if residual:
+        r = rbf(rng.standard_normal((M, n_out)))
+        rb_, rp = heap(to_bf16(r))
+        keep.append(rb_)
+        e.residual, e.ld_residual, e.residual_scale = rp, n_out, 0.5
+        v = r + 0.5 * v
+    if colsum:
+        c0 = rng.standard_normal(n_out).astype(np.float32)
+        cb, cp = heap(c0)
+        e.colsum = cp
+    if aux:
+        ab, ap = heap(np.full((M, N), 0x7FC0, np.uint16))
+        e.aux, e.ld_aux = ap, N
+    if rowstats:
+        rsb, rsp = heap(np.full(stats_ref.shape, np.nan, np.float32))
+        e.rowstats = rsp
+    e.c_f32, e.activation, e.glu, e.alpha = int(f32_out), act, int(glu), alpha
+    e.atomic_out, e.k_splits = int(accumulate), k_splits
+    init = rng.standard_normal((M, n_out)).astype(np.float32) if accumulate else None
+    if f32_out:
+        ob, op = heap(init if accumulate else np.full((M, n_out), np.nan, np.float32))
+    else:
+        ob, op = heap(np.full((M, n_out), 0x7FC0, np.uint16))
+    ab_, app = heap(to_bf16(a))
+    bb_, bpp = heap(to_bf16(b))
+    st = lib.tfasr_gemm_bf16(app, bpp, op, M, N, K, lda, ldb, n_out, int(mn_major), int(mn_major), ctypes.byref(e), None)
+    assert st == 0, st
+    got = ob.astype(np.float64) if f32_out else from_bf16(ob).astype(np.float64)
+    want = v + (init if accumulate else 0.0)
+    assert np.isfinite(got).all(), "output cells left unwritten"
+    close(got, want, 2e-3 if f32_out else 8e-3, f"gemm {(M, N, K)} mn={mn_major} f32={f32_out}")
+    if aux:
+        close(from_bf16(ab), pre, 8e-3, "gemm aux (pre-activation copy)")
+    if colsum:
+        close(cb - c0, v.sum(0), 1e-2, "gemm column sums")
+    if rowstats:
+        assert np.isfinite(rsb[..., 1]).all()
+        m = rsb[..., 0].max(1, keepdims=True)
+        lse = (m + np.log((rsb[..., 1] * np.exp(rsb[..., 0] - m)).sum(1, keepdims=True)))[:, 0]
+        mx = pre.max(1, keepdims=True)
+        close(lse, (mx + np.log(np.exp(pre - mx).sum(1, keepdims=True)))[:, 0], 1e-5, "log-sum-exp from the epilogue's row statistics")
+        assert np.array_equal(np.isneginf(rsb[..., 0]), np.isneginf(stats_ref[..., 0])), "empty slices"
+        ok = np.isfinite(stats_ref[..., 0])
+        close(rsb[..., 0][ok], stats_ref[..., 0][ok], 1e-5, "slice maxima")
+        close(rsb[..., 1][ok], stats_ref[..., 1][ok], 1e-4, "slice sums")
+
+
 CASES = [
     ("rnnt_kat", check_rnnt_kat),
     ("rnnt_ragged", lambda lib: check_rnnt(lib, 4, 13, 8, 12, [13, 9, 5, 13], [7, 4, 0, 1])),
@@ -659,6 +766,18 @@ CASES = [
     ("rel_attention_mma", lambda lib: check_rel_attention(lib, 2, 40, 2, 36, [40, 23])),  # Conformer-S head size: the mma.sync kernels, KS = 3
     ("rel_attention_mma_streaming", lambda lib: check_rel_attention(lib, 1, 48, 2, 16, [41], chunk=8, history=16)),
     ("rel_attention_fp32", lambda lib: check_rel_attention(lib, 2, 11, 2, 10, [11, 6])),  # T < 16, H % 4 != 0: the FP32 kernels
+    ("gemm_plain", lambda lib: check_gemm(lib, 200, 72, 136)),  # one ragged M tile, N < tile width, K not a multiple of 64
+    ("gemm_f32_bias", lambda lib: check_gemm(lib, 129, 1000, 320, f32_out=True, bias=True)),  # the joint's shape class: 4 tiles of 256 columns
+    ("gemm_swish_aux", lambda lib: check_gemm(lib, 150, 160, 64, bias=True, act=1, aux=True)),  # FFN-1: tile width 160
+    ("gemm_glu", lambda lib: check_gemm(lib, 130, 288, 144, bias=True, glu=True, aux=True)),  # pointwise conv 1
+    ("gemm_residual_dropout", lambda lib: check_gemm(lib, 140, 144, 576, bias=True, residual=True, dropout=0.25)),  # FFN-2 / out projections
+    ("gemm_bwd_swish_colsum", lambda lib: check_gemm(lib, 133, 192, 144, mul_mode=1, colsum=True)),  # FFN backward epilogue
+    ("gemm_bwd_tanh", lambda lib: check_gemm(lib, 70, 64, 1000, mul_mode=2)),  # joint dgrad
+    ("gemm_mn_major_splitk", lambda lib: check_gemm(lib, 144, 192, 333, f32_out=True, mn_major=True, accumulate=True, k_splits=3)),  # wgrad
+    ("gemm_mn_major_odd", lambda lib: check_gemm(lib, 456, 32, 200, f32_out=True, mn_major=True, accumulate=True)),  # DeepSpeech2 conv wgrad: M = Kp
+    ("gemm_tiny", lambda lib: check_gemm(lib, 1, 8, 8, f32_out=True)),
+    ("gemm_rowstats", lambda lib: check_gemm(lib, 130, 1000, 64, f32_out=True, bias=True, rowstats=True)),  # feature class 8 (fused log-sum-exp)
+    ("gemm_rowstats_narrow", lambda lib: check_gemm(lib, 40, 40, 32, f32_out=True, bias=True, rowstats=True)),  # one tile, second slice empty
     ("cluster_lstm", lambda lib: check_cluster_lstm(lib, 3, 4, 64, [4, 2, 3], False)),
     ("cluster_lstm_state", lambda lib: check_cluster_lstm(lib, 2, 3, 128, [3, 3], True)),
 ]

@@ -98,7 +98,15 @@ def convert(src: str, name: str = "?") -> str:
     src = src.replace("#include <cooperative_groups.h>\n", "")  # emu_common.h carries the cluster slice of it
     clusters = {m.group(2): m.group(1).strip() for m in
                 re.finditer(r"__cluster_dims__\(([^,)]+)[^)]*\)\s*(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(", src)}
-    src = re.sub(r'asm\("tanh\.approx\.f32 %0, %1;"\s*:\s*"=f"\((\w+)\)\s*:\s*"f"\((\w+)\)\);', r"\1 = tanhf(\2);", src)
+    src = re.sub(r'asm\("tanh\.approx\.f32 %0, %1;"\s*:\s*"=f"\((\w+)\)\s*:\s*"f"\(([^;]+)\)\);', r"\1 = tanhf(\2);", src)
+    # ---- the tcgen05 GEMM (gemm_kernel.cuh / gemm.cu / gemm_inst_*.cu): sm100.cuh -> emu_sm100.h, the few other PTX lines by hand
+    src = src.replace('#include "sm100.cuh"', '#include "emu_sm100.h"')
+    src = src.replace('asm volatile("bar.sync 1, 256;" ::: "memory");', "emu::named_barrier_sync(1, 256);")
+    src = src.replace('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));', "t = 0;")
+    src = re.sub(r'const __half2 h = __floats2half2_rn\(0\.5f \* a, 0\.5f \* b\);.*?sb = fmaf\(0\.5f, tf\.y, 0\.5f\);',
+                 "sa = fmaf(0.5f, tanhf(0.5f * a), 0.5f);\n  sb = fmaf(0.5f, tanhf(0.5f * b), 0.5f);", src, flags=re.S)
+    # the host tensor-map encoders of gemm.cu (cuTensorMapEncodeTiled through the driver) are provided by emu_sm100.h
+    src = re.sub(r"// -+ host: tensor maps\n.*?(?=\n// kernels are instantiated per tile width)", "", src, flags=re.S)
     if re.search(r"\basm\b", src):
         raise ValueError(f"{name}: inline PTX the shim does not know")
     src = _rewrite_launches(src, clusters)

@@ -256,3 +256,4 @@ inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(
 // dynamic shared memory: kernels declare it with TFASR_DYN_SMEM(name)
 #define TFASR_DYN_SMEM(name) uint8_t* name = emu::t_dyn_smem
 #define __cluster_dims__(...)
+#define __grid_constant__

@@ -93,7 +93,8 @@ def test_emulated_kernels_under_thread_sanitizer():
     if rt is None:
         pytest.skip("libtsan not available")
     build_emu.build(tsan=True)
-    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0 halt_on_error=0")
+    # numpy's reference matmuls stay on this thread: OpenBLAS's own (uninstrumented) worker threads would show up as races
+    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0 halt_on_error=0", OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
     for script, out, err, rc in _run_sanitized("--tsan", env):
         assert rc == 0, script + "\n" + out[-2000:] + err[-4000:]
         assert "WARNING: ThreadSanitizer" not in err, script + "\n" + err[-6000:]
