@@ -1,10 +1,10 @@
 """Run the PRODUCT's Python stack on the CPU — TEST INFRASTRUCTURE ONLY (tests/test_conformer_emulated_cpu.py).
 
-`install()` points `_lib.load()` at the emulator build of the kernel sources (tests/emu: every hand-written kernel except the tcgen05 GEMM,
-bound with the product's own ctypes signatures), lets the launchers take CPU tensors (host pointers, no stream), and replaces the one
-missing entry point, `kernels.gemm`, by a torch restatement of the tcgen05 GEMM's epilogue contract (bias, activation + aux copy, GLU,
-residual, backward multipliers, column sums, fp32 accumulate-into, row softmax statistics).  Everything else — fused.py, encoder.py,
-transducer.py, optim.py, features.py, the kernels.py launchers — runs unchanged."""
+`install()` points `_lib.load()` at the emulator build of the kernel sources (tests/emu: EVERY hand-written kernel, the tcgen05 GEMM included,
+bound with the product's own ctypes signatures) and lets the launchers take CPU tensors (host pointers, no stream).  Everything else —
+fused.py, encoder.py, transducer.py, optim.py, features.py, the kernels.py launchers — runs unchanged.  `gemm` below is a torch restatement
+of the GEMM's epilogue contract (bias, activation + aux copy, GLU, residual, backward multipliers, column sums, fp32 accumulate-into, row
+softmax statistics), kept as an independent second opinion (`install(real_gemm=False)`)."""
 from __future__ import annotations
 
 import os
@@ -101,8 +101,6 @@ class _EmuLib:
             return lambda st: {0: b"ok", 1: b"invalid value", 2: b"execution failed", 3: b"workspace too small"}.get(int(st), b"unknown")
         if name in ("tfasr_launch_count", "tfasr_launch_count_reset"):
             return lambda *a: 0
-        if name == "tfasr_gemm_bf16":
-            raise AttributeError("the tcgen05 GEMM has no emulator build: kernels.gemm is replaced by emu_backend.gemm")
         fn = getattr(self._lib, name)
 
         def counted(*a):
@@ -112,7 +110,9 @@ class _EmuLib:
         return counted
 
 
-def install(monkeypatch):
+def install(monkeypatch, real_gemm=True):
+    """real_gemm=True: kernels.gemm stays the product launcher and runs the tcgen05 GEMM's own source on the emulator (tests/emu/emu_sm100.h);
+    False: the torch restatement of its epilogue contract above (an independent second opinion)."""
     import checks_v1
 
     from tensorflowasr_b200 import _lib, kernels, ops
@@ -131,6 +131,7 @@ def install(monkeypatch):
 
     monkeypatch.setattr(_lib, "ptr", ptr)
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)  # no CUDA driver here
-    monkeypatch.setattr(kernels, "gemm", gemm)
+    if not real_gemm:
+        monkeypatch.setattr(kernels, "gemm", gemm)
     monkeypatch.setattr(ops, "fused_active", lambda x: ops._FUSED and ops.precision() == "bf16")
     return emu

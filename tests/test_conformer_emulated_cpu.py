@@ -122,11 +122,11 @@ def test_train_step_with_flat_adamw_learns_on_emulated_kernels(monkeypatch):
         model, data = _model(), _batch()
         model.compile(optimizer=tfasr.make_optimizer(model, learning_rate=2e-3))
         model.train()
-        losses = [float(model.train_step(data)["loss"].mean()) for _ in range(3)]
+        losses = [float(model.train_step(data)["loss"].mean()) for _ in range(2)]
     finally:
         ops.set_precision("fp32")
-    assert emu.calls.get("tfasr_adamw_flat_f32", 0) == 3
-    assert losses[2] < losses[1] < losses[0], losses
+    assert emu.calls.get("tfasr_adamw_flat_f32", 0) == 2 and emu.calls.get("tfasr_gemm_bf16", 0) > 50
+    assert losses[1] < losses[0], losses
 
 
 def _grads_close(ref_g, g, skip, min_checked, cos_min=0.95):
