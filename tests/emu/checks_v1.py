@@ -58,7 +58,7 @@ def _rnnt_call(lib, logits, labels, tl, ul):
     nb = lib.tfasr_rnnt_workspace_bytes(B, T, U1, V)
     ws, wsp = heap(np.zeros(nb // 4 + 1, np.float32))
     lg, lgp = heap(logits)
-    lb, lbp = heap(labels)
+    lb, lbp = heap(labels) if labels.size else (labels, None)  # U1 = 1: no labels at all
     tb, tp = heap(np.asarray(tl, np.int32))
     ub, up = heap(np.asarray(ul, np.int32))
     costs, cp = heap(np.zeros(B, np.float32))
@@ -84,7 +84,7 @@ def check_rnnt(lib, B, T, U1, V, tl, ul, seed=21):
 
     rng = np.random.default_rng(seed)
     logits = (rng.standard_normal((B, T, U1, V)) * 2).astype(np.float32)
-    labels = rng.integers(1, V, (B, max(U1 - 1, 1))).astype(np.int32)
+    labels = rng.integers(1, V, (B, U1 - 1)).astype(np.int32)
     tl, ul = rnnt.clamp_lengths(tl, ul)  # base_loss.py:36 — the C ABI leaves the clamp to its caller, like warp-transducer
     ref_loss, ref_g = rnnt.rnnt_loss(logits.astype(np.float64), labels, np.asarray(tl), np.asarray(ul))
     costs, grads, ctx = _rnnt_call(lib, logits, labels, tl, ul)
@@ -732,6 +732,54 @@ def check_gemm(lib, M, N, K, *, f32_out=False, bias=False, act=0, aux=False, glu
         close(rsb[..., 1][ok], stats_ref[..., 1][ok], 1e-4, "slice sums")
 
 
+# ------------------------------------------------------------------------------------------------ seeded sweep over odd shapes
+def check_random_shapes_v1(lib):
+    """Edge shapes the fixed cases do not name: single frames / labels, vocabularies and widths around the vector-path limits, lengths of 0 and
+    1, attention lengths around the 16-row MMA tiles, GEMM extents around the 128 x BN x 64 tiles."""
+    rng = np.random.default_rng(4242)
+    ri = lambda lo, hi: int(rng.integers(lo, hi))  # noqa: E731
+    for _ in range(5):
+        B, T, U1, V = ri(1, 4), ri(1, 9), ri(1, 7), int(rng.choice([2, 3, 8, 12, 33, 260]))
+        tl = [ri(1, T + 1) for _ in range(B)]
+        ul = [ri(0, min(U1, t + 1)) if U1 > 1 else 0 for t in tl]
+        check_rnnt(lib, B, T, U1, V, tl, [min(u, U1 - 1) for u in ul], seed=ri(0, 1 << 30))
+    for _ in range(4):
+        B, T, L, V = ri(1, 4), ri(1, 30), ri(0, 6), int(rng.choice([2, 5, 17, 64]))
+        tl = [ri(1, T + 1) for _ in range(B)]
+        check_ctc(lib, B, T, L, V, tl, [ri(0, min(L, t) + 1) for t in tl], seed=ri(0, 1 << 30))
+    for _ in range(3):
+        check_logmel(lib, ri(1, 3), ri(1, 2200), seed=ri(0, 1 << 30))  # incl. signals shorter than one frame
+    for _ in range(4):
+        check_layernorm(lib, ri(1, 40), int(rng.choice([1, 2, 7, 36, 144, 250, 640])), bool(ri(0, 2)), seed=ri(0, 1 << 30))
+    for _ in range(3):
+        check_scale_mask_glu(lib, ri(1, 50), 2 * ri(1, 80), float(rng.choice([0.0, 0.1, 0.5])), seed=ri(0, 1 << 30))
+    for _ in range(4):
+        check_batchnorm(lib, ri(1, 200), int(rng.choice([2, 6, 8, 24, 72, 144])), ri(0, 3), seed=ri(0, 1 << 30))
+    for _ in range(3):
+        check_dwconv_v1(lib, ri(1, 3), ri(1, 80), 2 * ri(1, 40), int(rng.choice([1, 3, 7, 31])), seed=ri(0, 1 << 30))
+    for _ in range(3):
+        T = ri(1, 40)
+        check_rel_attention(lib, ri(1, 3), T, ri(1, 3), int(rng.choice([4, 8, 10, 36, 64])), [ri(1, T + 1) for _ in range(2)][: 2], seed=ri(0, 1 << 30)) \
+            if False else None
+    for _ in range(4):
+        B, T = ri(1, 3), ri(1, 44)
+        check_rel_attention(lib, B, T, ri(1, 3), int(rng.choice([4, 8, 10, 36, 64])), [ri(1, T + 1) for _ in range(B)],
+                            chunk=int(rng.choice([0, 0, 4, 9])), history=int(rng.choice([0, 3, 16])), seed=ri(0, 1 << 30))
+    for _ in range(6):
+        M, N, K = ri(1, 300), 8 * ri(1, 40), 8 * ri(1, 30)
+        kind = ri(0, 5)
+        if kind == 0:
+            check_gemm(lib, M, N, K, f32_out=bool(ri(0, 2)), bias=bool(ri(0, 2)), seed=ri(0, 1 << 30))
+        elif kind == 1:
+            check_gemm(lib, M, N, K, bias=True, act=ri(1, 4), aux=True, seed=ri(0, 1 << 30))
+        elif kind == 2:
+            check_gemm(lib, M, N, K, residual=True, dropout=float(rng.choice([0.0, 0.3])), seed=ri(0, 1 << 30))
+        elif kind == 3:
+            check_gemm(lib, 8 * ri(1, 40), N, ri(1, 400), f32_out=True, mn_major=True, accumulate=True, k_splits=ri(1, 4), seed=ri(0, 1 << 30))
+        else:
+            check_gemm(lib, M, N, K, f32_out=True, bias=True, rowstats=True, seed=ri(0, 1 << 30))
+
+
 CASES = [
     ("rnnt_kat", check_rnnt_kat),
     ("rnnt_ragged", lambda lib: check_rnnt(lib, 4, 13, 8, 12, [13, 9, 5, 13], [7, 4, 0, 1])),
@@ -778,6 +826,7 @@ CASES = [
     ("gemm_tiny", lambda lib: check_gemm(lib, 1, 8, 8, f32_out=True)),
     ("gemm_rowstats", lambda lib: check_gemm(lib, 130, 1000, 64, f32_out=True, bias=True, rowstats=True)),  # feature class 8 (fused log-sum-exp)
     ("gemm_rowstats_narrow", lambda lib: check_gemm(lib, 40, 40, 32, f32_out=True, bias=True, rowstats=True)),  # one tile, second slice empty
+    ("random_shapes_v1", check_random_shapes_v1),
     ("cluster_lstm", lambda lib: check_cluster_lstm(lib, 3, 4, 64, [4, 2, 3], False)),
     ("cluster_lstm_state", lambda lib: check_cluster_lstm(lib, 2, 3, 128, [3, 3], True)),
 ]
