@@ -799,5 +799,7 @@ CASES = [
 if __name__ == "__main__":
     lib = load(asan="--asan" in sys.argv, tsan="--tsan" in sys.argv)
     for name, fn in CASES:
+        if "--fast" in sys.argv and name in ("random_shapes",):  # the sanitizer passes skip the sweep (it repeats the fixed cases' code paths)
+            continue
         fn(lib)
         print("ok", name, flush=True)

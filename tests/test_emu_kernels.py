@@ -62,39 +62,30 @@ def test_emulated_product_kernel(emu_lib_v1, name):
         pytest.skip(str(e))
 
 
-def _run_sanitized(flag, env):
-    """checks.py and checks_v1.py under one sanitizer, side by side."""
-    procs = [(script, subprocess.Popen([sys.executable, os.path.join(HERE, "emu", script), flag], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
-                                       env=env)) for script in ("checks.py", "checks_v1.py")]
-    return [(script,) + p.communicate(timeout=1800) + (p.returncode,) for script, p in procs]
-
-
-def test_emulated_kernels_under_address_sanitizer():
-    """Every buffer handed to the emulated kernels is an exact-size heap block: an out-of-bounds global or shared access is a hard ASan error —
-    the CPU stand-in for compute-sanitizer memcheck (an injected off-by-one is caught with the kernel's source line)."""
+def test_emulated_kernels_under_sanitizers():
+    """AddressSanitizer = the stand-in for compute-sanitizer memcheck: every buffer handed to the emulated kernels is an exact-size heap block,
+    so an out-of-bounds global or shared access is a hard error (an injected off-by-one is caught with the kernel's source line).
+    ThreadSanitizer = the stand-in for racecheck: every CUDA thread is an OS thread, __syncthreads / __syncwarp / shuffles / cluster.sync /
+    mbarriers are real synchronisation and atomics real atomics, so TSan reports exactly the accesses they do NOT order (a deleted
+    __syncthreads is reported; on its first run it found an unordered entry-state read in the decode kernel).
+    Both sanitizers, both check scripts, side by side."""
     import build_emu
 
-    rt = build_emu.asan_runtime()
-    if rt is None:
-        pytest.skip("libasan not available")
-    build_emu.build(asan=True)
-    env = dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0")
-    for script, out, err, rc in _run_sanitized("--asan", env):
-        assert rc == 0 and "AddressSanitizer" not in err, script + "\n" + out[-2000:] + err[-4000:]
-
-
-def test_emulated_kernels_under_thread_sanitizer():
-    """Every CUDA thread is an OS thread in the emulator, __syncthreads / __syncwarp / shuffles / cluster.sync are real barriers and atomics
-    real atomics: ThreadSanitizer then reports exactly the accesses that are NOT ordered by them — the CPU stand-in for compute-sanitizer
-    racecheck (a deleted __syncthreads is reported; it found an unordered entry-state read in the decode kernel when first run)."""
-    import build_emu
-
-    rt = build_emu.tsan_runtime()
-    if rt is None:
-        pytest.skip("libtsan not available")
-    build_emu.build(tsan=True)
-    # numpy's reference matmuls stay on this thread: OpenBLAS's own (uninstrumented) worker threads would show up as races
-    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0 halt_on_error=0", OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
-    for script, out, err, rc in _run_sanitized("--tsan", env):
-        assert rc == 0, script + "\n" + out[-2000:] + err[-4000:]
-        assert "WARNING: ThreadSanitizer" not in err, script + "\n" + err[-6000:]
+    jobs = []
+    asan, tsan = build_emu.asan_runtime(), build_emu.tsan_runtime()
+    if asan is not None:
+        build_emu.build(asan=True)
+        jobs += [("asan", script, dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")) for script in ("checks.py", "checks_v1.py")]
+    if tsan is not None:
+        build_emu.build(tsan=True)
+        # numpy's reference matmuls stay on their thread: OpenBLAS's own (uninstrumented) worker threads would show up as races
+        env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0 halt_on_error=0", OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+        jobs += [("tsan", script, env) for script in ("checks.py", "checks_v1.py")]
+    if not jobs:
+        pytest.skip("neither libasan nor libtsan available")
+    procs = [(kind, script, subprocess.Popen([sys.executable, os.path.join(HERE, "emu", script), "--" + kind, "--fast"], stdout=subprocess.PIPE,
+                                             stderr=subprocess.PIPE, text=True, env=env)) for kind, script, env in jobs]
+    for kind, script, p in procs:
+        out, err = p.communicate(timeout=2400)
+        assert p.returncode == 0, f"{kind} {script}\n" + out[-2000:] + err[-4000:]
+        assert "AddressSanitizer" not in err and "WARNING: ThreadSanitizer" not in err, f"{kind} {script}\n" + err[-6000:]
