@@ -293,6 +293,7 @@ def _run_ours(args, real_stdout):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    peer_calls = tdist.peer_all_reduce_check()  # opt-in peer-memory sync-BN exchange: raises if a peer ever missed the bounded wait
 
     if rank != 0:
         return
@@ -351,6 +352,8 @@ def _run_ours(args, real_stdout):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_joint_gemm": roofline_joint, "cpu_baseline": cpu,
         "kernel_ms_per_step": kernel_ms,
     }
+    if world > 1:
+        line["config"]["sync_bn_exchange"] = "peer-memory kernel (csrc/peer_allreduce.cu)" if peer_calls else "nccl all-reduce per BatchNorm pass"
     print(json.dumps(line), file=real_stdout, flush=True)
 
 

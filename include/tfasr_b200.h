@@ -384,6 +384,33 @@ typedef struct tfasr_greedy_params {
 } tfasr_greedy_params;
 int tfasr_greedy_decode_f32(const tfasr_greedy_params* params, int32_t B, int32_t threads, tfasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Small all-reduce over peer memory: the sync-BatchNorm statistics exchange of keras BatchNormalization(synchronized=True)
+ * (models/encoders/conformer.py:326-333, models/layers/subsampling.py norms "batch"), 2 x C floats per BatchNorm, forward and backward —
+ * in place of one NCCL all-reduce per call.  One launch, one CTA: push into every rank's window, flag (release.sys), bounded wait
+ * (acquire.sys), sum in rank order (bit-identical on every rank).
+ *   windows   device array [world] of window base addresses AS MAPPED IN THIS PROCESS (cudaIpcOpenMemHandle / symmetric memory); a window
+ *             is tfasr_peer_window_bytes(world, capacity) bytes, zero-initialised before the first call on any rank
+ *   state     2 uint32 of LOCAL device memory, zero-initialised once: [0] calls completed (advanced by the kernel: graph-replay safe),
+ *             [1] becomes 1 when a peer did not arrive within timeout_ms (the call then returns garbage instead of hanging the GPU)
+ *   data      [n] fp32 in/out, n <= capacity; every rank makes the same sequence of calls on one stream
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tfasr_peer_comm {
+  const uint64_t* windows;
+  uint32_t* state;
+  int32_t rank, world, capacity;
+  int32_t timeout_ms; /* 0 = default (30 s) */
+} tfasr_peer_comm;
+size_t tfasr_peer_window_bytes(int32_t world, int32_t capacity);
+/* Windows over plain CUDA IPC, on the calling thread's current device: alloc = cudaMalloc + zero-fill + cudaIpcGetMemHandle (the 64-byte
+ * handle goes to the peers through the host-side process group), open = cudaIpcOpenMemHandle with lazy peer access, close = cudaFree
+ * (owned) / cudaIpcCloseMemHandle. */
+#define TFASR_PEER_IPC_HANDLE_BYTES 64
+int tfasr_peer_window_alloc(size_t bytes, void** window, void* ipc_handle);
+int tfasr_peer_window_open(const void* ipc_handle, void** window);
+int tfasr_peer_window_close(void* window, int32_t owned);
+int tfasr_peer_allreduce_f32(const tfasr_peer_comm* comm, float* data, int32_t n, tfasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

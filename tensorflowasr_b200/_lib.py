@@ -40,6 +40,12 @@ class GreedyParams(ctypes.Structure):
                 + [(n, c_int32) for n in ("T", "E", "R", "J", "V", "max_tokens", "blank", "mode", "max_iters", "per_frame_cap")])
 
 
+class PeerComm(ctypes.Structure):
+    """Mirror of `tfasr_peer_comm`."""
+
+    _fields_ = [("windows", c_void_p), ("state", c_void_p), ("rank", c_int32), ("world", c_int32), ("capacity", c_int32), ("timeout_ms", c_int32)]
+
+
 class GemmEpilogue(ctypes.Structure):
     """Mirror of `tfasr_gemm_epilogue`."""
 
@@ -135,6 +141,11 @@ SIGNATURES = {
     "tfasr_conv_im2col": (c_int32, [c_void_p, c_int32, c_void_p, POINTER(ConvGeom), c_void_p]),
     "tfasr_conv_col2im": (c_int32, [c_void_p, c_void_p, POINTER(ConvGeom), c_void_p]),
     "tfasr_greedy_decode_f32": (c_int32, [POINTER(GreedyParams), c_int32, c_int32, c_void_p]),
+    "tfasr_peer_window_bytes": (ctypes.c_size_t, [c_int32, c_int32]),
+    "tfasr_peer_window_alloc": (c_int32, [ctypes.c_size_t, POINTER(c_void_p), c_void_p]),
+    "tfasr_peer_window_open": (c_int32, [c_void_p, POINTER(c_void_p)]),
+    "tfasr_peer_window_close": (c_int32, [c_void_p, c_int32]),
+    "tfasr_peer_allreduce_f32": (c_int32, [POINTER(PeerComm), c_void_p, c_int32, c_void_p]),
     "tfasr_ctc_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "tfasr_ctc_loss_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -76,3 +76,50 @@ __device__ __forceinline__ float simt_act_grad(float z, int act) {
 }
 
 }  // namespace tfasr
+
+// ---- system-scope flag accesses for exchanges over peer memory (csrc/peer_allreduce.cu) ----
+// Device: PTX release / acquire at .sys scope (the flag lives in another GPU's memory, reached over NVLink).
+// Emulator: std::atomic_ref with the same orders, so ThreadSanitizer checks exactly the ordering the protocol relies on.
+namespace tfasr {
+__device__ __forceinline__ void simt_st_release_sys(uint32_t* p, uint32_t v) {
+#ifdef TFASR_EMU_BUILD
+  std::atomic_ref<uint32_t>(*p).store(v, std::memory_order_release);
+#else
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ uint32_t simt_ld_acquire_sys(const uint32_t* p) {
+#ifdef TFASR_EMU_BUILD
+  return std::atomic_ref<uint32_t>(*const_cast<uint32_t*>(p)).load(std::memory_order_acquire);
+#else
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+// data written by a peer GPU into this GPU's memory: read at the point of coherence (never from a stale L1 line)
+__device__ __forceinline__ float simt_ld_relaxed_sys_f32(const float* p) {
+#ifdef TFASR_EMU_BUILD
+  return *p;
+#else
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void simt_fence_sys() {
+#ifdef TFASR_EMU_BUILD
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+#else
+  __threadfence_system();
+#endif
+}
+// monotonic tick counter for bounded spins (device: SM clock cycles; emulator: nanoseconds)
+__device__ __forceinline__ long long simt_ticks() {
+#ifdef TFASR_EMU_BUILD
+  return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+#else
+  return clock64();
+#endif
+}
+}  // namespace tfasr

@@ -126,6 +126,149 @@ class GradientReducer:
         self._pending = [len(idx) for _, _, idx in self.buckets]
 
 
+class PeerAllReduce:
+    """All-reduce (SUM, fp32, in place) of small vectors over peer memory: `csrc/peer_allreduce.cu` — one launch of one CTA per call in place of
+    an NCCL all-reduce; built for the sync-BatchNorm statistics (C2: 2 x C floats, twice per BatchNorm and step, all on the critical path).
+    Every rank owns one window (device memory shared over CUDA IPC; the 64-byte handles travel through the process group) and maps every
+    peer's.  Every rank must make the same sequence of calls on its current stream; the call counter lives on the device, so the calls can be
+    captured in a CUDA graph.  `check()` (host sync) raises if a peer ever failed to arrive within the kernel's bounded wait."""
+
+    def __init__(self, capacity: int = 4096, device=None, timeout_ms: int = 0):
+        import ctypes
+
+        from . import _lib
+
+        lib = _lib.load()
+        self.world, self.rank, self.capacity = world_size(), rank(), int(capacity)
+        nbytes = int(lib.tfasr_peer_window_bytes(self.world, self.capacity))
+        if nbytes == 0:
+            raise ValueError(f"PeerAllReduce: unsupported world size {self.world} / capacity {capacity}")
+        self._owned, self._mapped, self._shm = None, [], []
+        if _lib.EMULATED:
+            ptrs = self._open_host_windows(nbytes)
+            device = torch.device("cpu")
+        else:
+            device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+            ptrs = self._open_ipc_windows(lib, nbytes, ctypes)
+        self.table = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.state = torch.zeros(2, dtype=torch.int32, device=device)
+        self._comm = _lib.PeerComm(self.table.data_ptr(), self.state.data_ptr(), self.rank, self.world, self.capacity, int(timeout_ms))
+        if self.world > 1:
+            dist.barrier()  # every window is zero-filled and mapped everywhere before the first push
+
+    def _open_ipc_windows(self, lib, nbytes, ctypes):
+        from . import _lib
+
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(lib.tfasr_peer_window_alloc(nbytes, ctypes.byref(own), handle), "tfasr_peer_window_alloc")
+        self._owned = own.value
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle.raw))
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(self._owned)
+                continue
+            p = ctypes.c_void_p()
+            _lib.check(lib.tfasr_peer_window_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(p)), "tfasr_peer_window_open")
+            self._mapped.append(p.value)
+            ptrs.append(p.value)
+        return ptrs
+
+    def _open_host_windows(self, nbytes):
+        """CPU emulator backend (tests): the windows are POSIX shared-memory blocks, mapped at a different address in every process —
+        exactly the situation of CUDA IPC mappings."""
+        import ctypes
+        from multiprocessing import shared_memory
+
+        own = shared_memory.SharedMemory(create=True, size=nbytes)
+        own.buf[:nbytes] = bytes(nbytes)
+        names = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(names, own.name)
+        else:
+            names = [own.name]
+        ptrs = []
+        for r, name in enumerate(names):
+            shm = own if r == self.rank else shared_memory.SharedMemory(name=name)
+            self._shm.append(shm)
+            ptrs.append(ctypes.addressof(ctypes.c_char.from_buffer(shm.buf)))
+        self._own_shm = own
+        return ptrs
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        from . import _lib
+
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() > self.capacity:
+            raise ValueError(f"PeerAllReduce.all_reduce: contiguous fp32 of at most {self.capacity} elements expected, got {t.dtype} x {t.numel()}")
+        import ctypes
+
+        lib = _lib.load()
+        _lib.check(lib.tfasr_peer_allreduce_f32(ctypes.byref(self._comm), _lib.ptr(t), t.numel(), _lib.stream_ptr(t.device)), "tfasr_peer_allreduce_f32")
+        return t
+
+    def check(self):
+        calls, late = (int(v) for v in self.state.tolist())
+        if late:
+            raise RuntimeError(f"PeerAllReduce: a peer did not arrive within the bounded wait (rank {self.rank}, {calls} calls completed)")
+        return calls
+
+    def close(self):
+        from . import _lib
+
+        if self._shm:
+            import gc
+
+            self.table = None
+            gc.collect()
+            for shm in self._shm:
+                try:
+                    shm.close()
+                except BufferError:
+                    pass
+            try:
+                self._own_shm.unlink()
+            except FileNotFoundError:
+                pass
+            self._shm = []
+            return
+        lib = _lib.load()
+        for p in self._mapped:
+            lib.tfasr_peer_window_close(p, 0)
+        self._mapped = []
+        if self._owned:
+            lib.tfasr_peer_window_close(self._owned, 1)
+            self._owned = None
+
+
+_PEER = None
+
+
+def small_all_reduce(t: torch.Tensor) -> torch.Tensor:
+    """C2: in-place SUM of a small fp32 vector over the replicas — NCCL by default, the peer-memory kernel with ops.set_peer_bn(True)."""
+    if world_size() <= 1:
+        return t
+    from . import ops
+
+    if ops.peer_bn_active() and t.dtype == torch.float32 and t.is_contiguous():
+        global _PEER
+        if _PEER is None or _PEER.world != world_size():
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PeerAllReduce must be created before CUDA-graph capture (run one eager step first)")
+            _PEER = PeerAllReduce(capacity=max(4096, t.numel()))
+        if t.numel() <= _PEER.capacity:
+            return _PEER.all_reduce(t)
+    dist.all_reduce(t)
+    return t
+
+
+def peer_all_reduce_check():
+    """Host-side health check of the peer-memory exchange (None when it is not in use)."""
+    return None if _PEER is None else _PEER.check()
+
+
 def all_reduce_mean_scalar(t: torch.Tensor) -> torch.Tensor:
     """C3: loss/metric mean over replicas (base_model.py:257-261)."""
     if world_size() > 1:

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import torch
 
-from . import kernels
+from . import dist, kernels
 
 LN_EPS = 1e-3
 
@@ -424,7 +424,7 @@ def bn_train_fwd(x2d, gamma, beta, moving_mean, moving_var, act=1):
     sums = kernels.bn_stats(x2d)
     world = _world()
     if world > 1:
-        torch.distributed.all_reduce(sums)  # C2: sync-BN statistics
+        dist.small_all_reduce(sums)  # C2: sync-BN statistics
     count = float(R * world)
     with torch.no_grad():
         out = kernels.bn_finalize(sums, gamma.detach(), beta.detach(), moving_mean, moving_var, count, BN_EPS, BN_MOMENTUM)
@@ -439,8 +439,7 @@ def bn_train_bwd(dy2d, x2d, saved, gamma, beta, act=1):
     sums = kernels.bn_bwd_stats(dy2d, x2d, scale, shift, mean, rstd, act)
     kernels.bn_bwd_finalize(sums, _grad(gamma).view(-1), _grad(beta).view(-1))  # local contribution; the gradient all-reduce sums over replicas
     if _world() > 1:
-        sums = sums.clone()
-        torch.distributed.all_reduce(sums)
+        sums = dist.small_all_reduce(sums.clone())
     return kernels.bn_bwd_apply(dy2d, x2d, scale, shift, mean, rstd, sums, count, act)
 
 

@@ -134,6 +134,21 @@ def conv1_v2_active() -> bool:
     return _CONV1_V2
 
 
+_PEER_BN = _os.environ.get("TFASR_PEER_BN", "0") == "1"
+
+
+def set_peer_bn(flag: bool):
+    """Multi-GPU: exchange the sync-BatchNorm statistics with the one-launch all-reduce over peer memory (csrc/peer_allreduce.cu,
+    dist.PeerAllReduce) instead of one NCCL all-reduce per BatchNorm pass.  Off by default until it has run on a
+    multi-GPU B200 box (tools/round2_first_call.sh)."""
+    global _PEER_BN
+    _PEER_BN = bool(flag)
+
+
+def peer_bn_active() -> bool:
+    return _PEER_BN
+
+
 _FUSED_LSE = _os.environ.get("TFASR_FUSED_LSE", "0") == "1"
 
 

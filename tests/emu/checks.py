@@ -32,7 +32,7 @@ def load(asan=False, tsan=False):
     import build_emu
 
     lib = ctypes.CDLL(build_emu.build(asan=asan, tsan=tsan))
-    for name in ("tfasr_greedy_decode_f32", "tfasr_dwconv_causal_wgrad_v2", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+    for name in ("tfasr_greedy_decode_f32", "tfasr_dwconv_causal_wgrad_v2", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_peer_allreduce_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
     return lib
@@ -740,6 +740,77 @@ def check_random_shapes(lib):
                                    seed=int(rng.integers(1 << 30)))
 
 
+
+# ------------------------------------------------------------------------------------------------ all-reduce over peer memory
+class PeerComm(ctypes.Structure):
+    _fields_ = [("windows", c_vp), ("state", c_vp), ("rank", c_i32), ("world", c_i32), ("capacity", c_i32), ("timeout_ms", c_i32)]
+
+
+def check_peer_allreduce(lib, world, capacity, sizes, seed=0, stagger=True):
+    """`world` host threads stand in for the ranks (one address space = every window is 'peer-mapped'); each rank makes the same sequence of
+    calls back to back, with no synchronisation between calls other than the kernel's own flags — the parity / epoch protocol is what keeps
+    call k+1's pushes from overwriting lanes a slower rank is still summing.  Sums must be the rank-order fp32 sums, bit for bit."""
+    import threading
+    import time
+
+    lib.tfasr_peer_window_bytes.restype = ctypes.c_size_t
+    wbytes = lib.tfasr_peer_window_bytes(world, capacity)
+    assert wbytes == 8 * world * capacity + 64 * world
+    rng = np.random.default_rng(seed)
+    wins = [heap(np.zeros(wbytes // 4, np.uint32)) for _ in range(world)]
+    table, tp = heap(np.array([w[0].ctypes.data for w in wins], np.uint64))
+    states = [heap(np.zeros(2, np.uint32)) for _ in range(world)]
+    inputs = [[rng.standard_normal(n).astype(np.float32) for n in sizes] for _ in range(world)]
+    outs = [[None] * len(sizes) for _ in range(world)]
+    errs = []
+
+    def run(r):
+        try:
+            comm = PeerComm(tp, states[r][1], r, world, capacity, 60000)
+            for k, n in enumerate(sizes):
+                if stagger and (r + k) % 3 == 0:
+                    time.sleep(0.01)  # let the ranks drift apart by a call
+                buf, bp = heap(inputs[r][k]) if n else (np.zeros(0, np.float32), None)
+                assert lib.tfasr_peer_allreduce_f32(ctypes.byref(comm), bp, n, None) == 0
+                outs[r][k] = buf
+        except BaseException as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    calls = sum(1 for n in sizes if n)
+    for r in range(world):
+        assert states[r][0][0] == calls and states[r][0][1] == 0, (r, states[r][0])
+    for k, n in enumerate(sizes):
+        ref = np.zeros(n, np.float32)
+        for r in range(world):
+            ref = (ref + inputs[r][k]).astype(np.float32)  # rank order, fp32
+        for r in range(world):
+            assert np.array_equal(outs[r][k], ref), (r, k)
+
+
+def check_peer_allreduce_errors(lib):
+    """A peer that never arrives: the bounded wait gives up, flags state[1] and returns (no hang); invalid arguments."""
+    lib.tfasr_peer_window_bytes.restype = ctypes.c_size_t
+    assert lib.tfasr_peer_window_bytes(0, 8) == 0 and lib.tfasr_peer_window_bytes(2, 0) == 0
+    world, cap = 2, 8
+    wins = [heap(np.zeros(lib.tfasr_peer_window_bytes(world, cap) // 4, np.uint32)) for _ in range(world)]
+    table, tp = heap(np.array([w[0].ctypes.data for w in wins], np.uint64))
+    state, sp = heap(np.zeros(2, np.uint32))
+    buf, bp = heap(np.ones(8, np.float32))
+    comm = PeerComm(tp, sp, 0, world, cap, 50)
+    assert lib.tfasr_peer_allreduce_f32(ctypes.byref(comm), bp, 8, None) == 0
+    assert state[0] == 1 and state[1] == 1
+    assert lib.tfasr_peer_allreduce_f32(ctypes.byref(comm), bp, 9, None) == 1  # n > capacity
+    assert lib.tfasr_peer_allreduce_f32(None, bp, 8, None) == 1
+    bad = PeerComm(tp, sp, 2, world, cap, 50)
+    assert lib.tfasr_peer_allreduce_f32(ctypes.byref(bad), bp, 8, None) == 1  # rank outside the world
+
+
 # ------------------------------------------------------------------------------------------------ error behaviour
 def check_invalid(lib):
     a, p = heap(np.zeros(64, np.float32))
@@ -792,13 +863,19 @@ CASES = [
     ("conv1_v2_even", lambda lib: check_conv1_v2(lib, 2, 22, 16, 24)),
     ("conv1_v2_odd", lambda lib: check_conv1_v2(lib, 2, 37, 13, 16)),  # odd T and F, T1 not a multiple of the rows per CTA
     ("conv1_v2_tiny", lambda lib: check_conv1_v2(lib, 1, 1, 1, 8)),
+    ("peer_allreduce_w2", lambda lib: check_peer_allreduce(lib, 2, 1280, [288, 1280, 288, 2, 0, 641, 288])),
+    ("peer_allreduce_w8", lambda lib: check_peer_allreduce(lib, 8, 320, [288, 288, 320, 1, 288, 17])),  # 8 ranks x 256 threads at once
+    ("peer_allreduce_errors", check_peer_allreduce_errors),
     ("random_shapes", check_random_shapes),
     ("invalid_arguments", check_invalid),
 ]
 
 if __name__ == "__main__":
     lib = load(asan="--asan" in sys.argv, tsan="--tsan" in sys.argv)
+    only = [a[7:] for a in sys.argv if a.startswith("--only=")]
     for name, fn in CASES:
+        if only and not any(name.startswith(o) for o in only):
+            continue
         if "--fast" in sys.argv and name in ("random_shapes",):  # the sanitizer passes skip the sweep (it repeats the fixed cases' code paths)
             continue
         fn(lib)

@@ -15,6 +15,7 @@
 
 #include <atomic>
 #include <barrier>
+#include <chrono>
 #include <memory>
 #include <thread>
 #include <vector>

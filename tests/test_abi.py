@@ -74,7 +74,7 @@ def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
     structs = {"tfasr_logmel_cfg": _lib.LogmelCfg, "tfasr_gemm_epilogue": _lib.GemmEpilogue, "tfasr_conv_geom": _lib.ConvGeom,
-               "tfasr_greedy_params": _lib.GreedyParams}
+               "tfasr_greedy_params": _lib.GreedyParams, "tfasr_peer_comm": _lib.PeerComm}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tfasr_b200.h"', "int main(void) {"]
     for cname, mirror in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

@@ -1,6 +1,7 @@
 """CPU, world_size 2 (gloo) on the emulator backend: the FUSED Conformer path under data parallelism — batch sharding, the synchronized
 BatchNorm statistics exchanged by fused.bn_train_fwd / bn_train_bwd around the BatchNorm kernels (C2), loss / num_replicas and summed
-gradients (C1; base_model.py:166-173) — must reproduce the single-process full-batch gradients of the same fused path."""
+gradients (C1; base_model.py:166-173) — must reproduce the single-process full-batch gradients of the same fused path; and the
+same step with the statistics exchanged through the peer-memory all-reduce kernel (ops.set_peer_bn) must agree with the gloo exchange."""
 import os
 import shutil
 import socket
@@ -67,6 +68,23 @@ def _worker(rank, world, port, out):
 
     lo, hi = tdist.shard_batch(4)
     losses, grads = _fused_grads(_data()(lo, hi), world)
+    # the same step once more with the sync-BatchNorm statistics exchanged by the peer-memory kernel (csrc/peer_allreduce.cu on the emulator;
+    # the windows are shared-memory blocks mapped at different addresses in the two processes, as CUDA IPC mappings would be)
+    from tensorflowasr_b200 import ops
+
+    ops.set_peer_bn(True)
+    try:
+        losses_p, grads_p = _fused_grads(_data()(lo, hi), world)
+        calls = tdist.peer_all_reduce_check()
+    finally:
+        ops.set_peer_bn(False)
+    assert calls is not None and calls >= 6, calls  # 2 subsampling + 1 per block BatchNorms, forward and backward
+    torch.testing.assert_close(losses_p, losses, rtol=1e-3, atol=1e-3)
+    for n, g in grads.items():
+        if g.norm() > 1e-5 * max(1.0, g.numel() ** 0.5):
+            cos = float((grads_p[n] * g).sum() / (grads_p[n].norm() * g.norm() + 1e-30))
+            assert cos > 0.999, (n, cos)  # not bit-identical: the kernels' float atomics commit in a different order from run to run
+    tdist._PEER.close()
     for n in sorted(grads):
         dist.all_reduce(grads[n])  # gradients are SUMMED over replicas
     if rank == 0:  # plain numpy through the queue: torch's shared-memory hand-over needs the producer alive at receive time
