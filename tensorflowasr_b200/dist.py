@@ -163,16 +163,21 @@ class PeerAllReduce:
         handle = ctypes.create_string_buffer(64)
         _lib.check(lib.tfasr_peer_window_alloc(nbytes, ctypes.byref(own), handle), "tfasr_peer_window_alloc")
         self._owned = own.value
+        import socket
+
         handles = [None] * self.world
         if self.world > 1:
-            dist.all_gather_object(handles, bytes(handle.raw))
+            dist.all_gather_object(handles, (socket.gethostname(), bytes(handle.raw)))
+            if len({h for h, _ in handles}) != 1:  # CUDA IPC (and NVLink peer stores) end at the node boundary
+                self.close()
+                raise RuntimeError("PeerAllReduce: all ranks must run on one node (NVLink peer memory); use the NCCL exchange (ops.set_peer_bn(False))")
         ptrs = []
         for r in range(self.world):
             if r == self.rank:
                 ptrs.append(self._owned)
                 continue
             p = ctypes.c_void_p()
-            _lib.check(lib.tfasr_peer_window_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(p)), "tfasr_peer_window_open")
+            _lib.check(lib.tfasr_peer_window_open(ctypes.create_string_buffer(handles[r][1], 64), ctypes.byref(p)), "tfasr_peer_window_open")
             self._mapped.append(p.value)
             ptrs.append(p.value)
         return ptrs

@@ -102,3 +102,71 @@ def test_training_head_python_path(stub, monkeypatch, fused_lse, grad_v2):
     finally:
         ops.set_fused_lse(False)
         ops.set_rnnt_grad_v2(False)
+
+
+def test_peer_allreduce_ipc_wiring(monkeypatch):
+    """dist.PeerAllReduce's CUDA-IPC path with the library and the process group faked (2 ranks, this process = rank 1): own window from
+    tfasr_peer_window_alloc, the peer's from tfasr_peer_window_open on the gathered handle, table in rank order, comm struct fields; ranks on
+    two hosts are refused (and the own window released)."""
+    import torch.distributed as tdist_mod
+
+    from tensorflowasr_b200 import _lib
+    from tensorflowasr_b200 import dist as tdist
+
+    calls = []
+
+    class _IpcStub:
+        def tfasr_peer_window_bytes(self, world, cap):
+            return 8 * world * cap + 64 * world
+
+        def tfasr_peer_window_alloc(self, nbytes, out, handle):
+            calls.append(("alloc", nbytes))
+            out._obj.value = 0x7000
+            handle.raw = b"M" * 64
+            return 0
+
+        def tfasr_peer_window_open(self, handle, out):
+            calls.append(("open", bytes(handle.raw)))
+            out._obj.value = 0x9000
+            return 0
+
+        def tfasr_peer_window_close(self, p, owned):
+            calls.append(("close", p, owned))
+            return 0
+
+        def tfasr_peer_allreduce_f32(self, comm, data, n, stream):
+            c = comm._obj
+            calls.append(("allreduce", c.rank, c.world, c.capacity, n))
+            return 0
+
+    hosts = ["box", "box"]
+
+    def gather(out, obj):
+        out[0] = (hosts[0], b"P" * 64)
+        out[1] = (hosts[1], obj[1])
+
+    monkeypatch.setattr(_lib, "load", lambda: _IpcStub())
+    monkeypatch.setattr(_lib, "stream_ptr", lambda d=None: 0)
+    monkeypatch.setattr(_lib, "ptr", lambda t: None if t is None else t.data_ptr())
+    monkeypatch.setattr(tdist, "world_size", lambda: 2)
+    monkeypatch.setattr(tdist, "rank", lambda: 1)
+    monkeypatch.setattr(tdist_mod, "all_gather_object", gather)
+    monkeypatch.setattr(tdist_mod, "barrier", lambda: None)
+    comm = tdist.PeerAllReduce(capacity=512, device="cpu")
+    assert comm.table.tolist() == [0x9000, 0x7000]
+    assert ("alloc", 8 * 2 * 512 + 128) in calls and ("open", b"P" * 64) in calls
+    t = torch.ones(288)
+    assert comm.all_reduce(t) is t
+    assert calls[-1] == ("allreduce", 1, 2, 512, 288)
+    with pytest.raises(ValueError):
+        comm.all_reduce(torch.ones(513))
+    with pytest.raises(ValueError):
+        comm.all_reduce(torch.ones(8, dtype=torch.float64))
+    assert comm.check() == 0
+    comm.close()
+    assert ("close", 0x9000, 0) in calls and ("close", 0x7000, 1) in calls
+    hosts[0] = "other-box"
+    calls.clear()
+    with pytest.raises(RuntimeError, match="one node"):
+        tdist.PeerAllReduce(capacity=512, device="cpu")
+    assert ("close", 0x7000, 1) in calls and not any(c[0] == "open" for c in calls)
