@@ -318,7 +318,7 @@ class ConformerEncoder(_Params):
             x2 = x.reshape(B * T, D).to(torch.bfloat16)
             a = fused.layer_norm(x2, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
             qkv = fused.linear(a, pk.qkv)
-            pos = fused.linear(relpe.reshape(-1, D).to(torch.bfloat16).contiguous(), pk.pos)
+            pos = fused.linear(relpe if relpe.dtype == torch.bfloat16 else relpe.reshape(-1, D).to(torch.bfloat16).contiguous(), pk.pos)
             ctx = fused.rel_attention(qkv, pos, self["content_attention_bias"], self["positional_attention_bias"], length.to(torch.int32),
                                       B, T, N, H, self.chunk_size, self.history_size)
             y = fused.linear(ctx, pk.out, residual=x2, factor=self.mhsam_residual_factor, drop_p=p,
@@ -366,6 +366,8 @@ class ConformerEncoder(_Params):
         x = ops.dropout(x, self.dropout, training)
         relpe = ops.relative_position_encoding(x.shape[1], length, self.dmodel, x.device)  # not added to x (positional_encoding.py:174)
         relpe = ops.dropout(relpe, 0.0, training)
+        if ops.fused_active(x):
+            relpe = relpe.reshape(-1, self.dmodel).to(torch.bfloat16).contiguous()  # GEMM operand of every block's position projection: cast once
         for b in range(self.num_blocks):
             pre = f"block_{b}"
             x = self._ff(x, pre + ".ff_module_1", training)
