@@ -216,6 +216,17 @@ int tfasr_rel_attention_fwd(const void* qkv, int32_t ld_qkv, const void* pos, co
 int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias, const int32_t* length,
                             int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, const void* probs, const void* dctx,
                             const void* ctx, void* ds_ws, void* dqkv, void* dpos, float* du, float* dvb, tfasr_stream_t stream);
+/* The same with explicit row strides (elements) for pos and dpos: every Conformer block projects the SAME relative position table
+ * (conformer.py:672-701 computes relpe once and hands it to all blocks), so the position projections of all blocks can be ONE GEMM
+ * [B*(2T-1), D] x [D, blocks*N*H]; block b then reads its N*H-wide column slice (pos = base + b*N*H, ld_pos = blocks*N*H) and writes its
+ * slice of the shared gradient.  ld_pos % 4 == 0 and an 8-byte aligned pos keep the tensor-core path (FP32 kernels otherwise). */
+int tfasr_rel_attention_fwd_ld(const void* qkv, int32_t ld_qkv, const void* pos, int32_t ld_pos, const float* ubias, const float* vbias,
+                               const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, void* ctx,
+                               void* probs, tfasr_stream_t stream);
+int tfasr_rel_attention_bwd_ld(const void* qkv, int32_t ld_qkv, const void* pos, int32_t ld_pos, const float* ubias, const float* vbias,
+                               const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history,
+                               const void* probs, const void* dctx, const void* ctx, void* ds_ws, void* dqkv, void* dpos, int32_t ld_dpos,
+                               float* du, float* dvb, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv2dSubsampling pieces and BatchNorm (+ swish), channels-last bf16 (subsampling.py:163-230, convolution.py:25-37,132-144;

@@ -107,6 +107,11 @@ SIGNATURES = {
                                           c_int32, c_void_p, c_void_p, c_void_p]),
     "tfasr_rel_attention_bwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                           c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tfasr_rel_attention_fwd_ld": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                             c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "tfasr_rel_attention_bwd_ld": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                             c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                             c_void_p]),
     "tfasr_lstm_supported": (c_int32, [c_int32]),
     "tfasr_lstm_rec_fwd": (c_int32, [c_void_p] * 10 + [c_int32] * 3 + [c_void_p]),
     "tfasr_lstm_rec_bwd": (c_int32, [c_void_p] * 9 + [c_int32] * 3 + [c_void_p]),
@@ -190,6 +195,18 @@ def ptr(t) -> int | None:
         raise RuntimeError("libtfasr_b200 has no CPU path: tensor must live on a CUDA device")
     if not t.is_contiguous():
         raise RuntimeError("libtfasr_b200 expects contiguous row-major buffers")
+    return t.data_ptr()
+
+
+def ptr_rows(t) -> int | None:
+    """Device pointer of a 2-D CUDA tensor whose rows are contiguous (unit column stride) but may be strided — a column slice of a wider
+    buffer; the row stride travels separately (t.stride(0))."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libtfasr_b200 has no CPU path: tensor must live on a CUDA device")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError("libtfasr_b200 expects unit column stride")
     return t.data_ptr()
 
 

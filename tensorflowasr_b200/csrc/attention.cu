@@ -22,11 +22,12 @@ constexpr int kMaxH = 64;
 
 struct AttParams {
   const __nv_bfloat16* qkv;  // [B*T, ld_qkv]: q at col n*H, k at NH + n*H, v at 2NH + n*H
-  const __nv_bfloat16* pos;  // [B*R, NH]
+  const __nv_bfloat16* pos;  // [B*R, NH] with row stride ld_pos (a column slice of the all-blocks projection when ld_pos > NH)
   const float* ubias;        // [N, H]
   const float* vbias;        // [N, H]
   const int32_t* length;     // [B] or null
   int B, T, N, H, R, ld_qkv;
+  int ld_pos, ld_dpos;       // row strides (elements) of pos and of the dpos output
   int chunk, history;        // streaming mask if chunk > 0
   float scale;
 };
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kAttThreads) rel_attention_fwd_kernel(const At
       const int rr = i / H2, h2 = i % H2;
       const int r = r_lo + rr;
       __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
-      if (r < R) v = *reinterpret_cast<const __nv_bfloat162*>(p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 2 * h2);
+      if (r < R) v = *reinterpret_cast<const __nv_bfloat162*>(p.pos + ((size_t)b * R + r) * p.ld_pos + (size_t)n * H + 2 * h2);
       *reinterpret_cast<__nv_bfloat162*>(sP + rr * S + 2 * h2) = v;
     }
   }
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kAttThreads) rel_attention_bwd_rows_kernel(con
       const int rr = i / H2, h2 = i % H2;
       const int r = r_lo + rr;
       __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
-      if (r < R) v = *reinterpret_cast<const __nv_bfloat162*>(p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 2 * h2);
+      if (r < R) v = *reinterpret_cast<const __nv_bfloat162*>(p.pos + ((size_t)b * R + r) * p.ld_pos + (size_t)n * H + 2 * h2);
       *reinterpret_cast<__nv_bfloat162*>(sP + rr * S + 2 * h2) = v;
     }
     for (int i = threadIdx.x; i < 2 * H; i += kAttThreads) sAcc[i] = 0.f;
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(64) rel_attention_bwd_cols_kernel(const AttPar
       for (int h = 0; h < kMaxH; ++h)
         if (h < H) ap[h] = fmaf(dd, qr[h] + p.vbias[n * H + h], ap[h]);
     }
-    __nv_bfloat16* prow = dpos + ((size_t)b * R + r) * NH + (size_t)n * H;
+    __nv_bfloat16* prow = dpos + ((size_t)b * R + r) * p.ld_dpos + (size_t)n * H;
 #pragma unroll
     for (int h = 0; h < kMaxH; ++h)
       if (h < H) prow[h] = __float2bfloat16(ap[h] * p.scale);
@@ -390,7 +391,7 @@ __device__ __forceinline__ void att_stage_kvp(const AttParams& p, int b, int n, 
   for (int i = threadIdx.x; i < PR * HP4; i += blockDim.x) {
     const int rr = i / HP4, h4 = i % HP4;
     const int r = rr - (Tk - T);
-    if (r >= 0 && r < R && 4 * h4 < H) mma::cp_async8(sP + rr * HS + 4 * h4, p.pos + ((size_t)b * R + r) * NH + (size_t)n * H + 4 * h4);
+    if (r >= 0 && r < R && 4 * h4 < H) mma::cp_async8(sP + rr * HS + 4 * h4, p.pos + ((size_t)b * R + r) * p.ld_pos + (size_t)n * H + 4 * h4);
     else st8(sP + rr * HS + 4 * h4, z);
   }
   mma::cp_async_commit();
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(512, 1) rel_attention_fwd_mma_kernel(const Att
 template <int KS>
 static int launch_att_fwd_mma(const AttParams& p, __nv_bfloat16* ctx, __nv_bfloat16* probs, cudaStream_t stream) {
   const size_t smem = att_mma_fwd_smem<KS>(p.T);
-  if (smem > 227 * 1024 || p.T > 256 || (p.H & 3) || (p.ld_qkv & 3)) return -1;  // caller falls back to the FP32 kernel
+  if (smem > 227 * 1024 || p.T > 256 || (p.H & 3) || (p.ld_qkv & 3) || (p.ld_pos & 3) || (reinterpret_cast<uintptr_t>(p.pos) & 7)) return -1;  // caller falls back to the FP32 kernel
   if (cudaFuncSetAttribute(rel_attention_fwd_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return TFASR_EXECUTION_FAILED;
   dim3 grid(p.N, p.B);
@@ -988,7 +989,7 @@ __global__ void __launch_bounds__(512) rel_attention_bwd_cols_mma_kernel(const A
       for (int mi = 0; mi < 2; ++mi) {
         const int r = (2 * warp + mi) * 16 + g + half * 8;
         if (r < R)
-          *reinterpret_cast<__nv_bfloat162*>(dpos + ((size_t)b * R + r) * NH + (size_t)n * H + h) =
+          *reinterpret_cast<__nv_bfloat162*>(dpos + ((size_t)b * R + r) * p.ld_dpos + (size_t)n * H + h) =
               __floats2bfloat162_rn(aP[mi][nh][2 * half], aP[mi][nh][2 * half + 1]);
       }
     }
@@ -1150,7 +1151,7 @@ __global__ void __launch_bounds__(512) rel_attention_bwd_cols_mma2_kernel(const 
       for (int mi = 0; mi < 2; ++mi) {
         const int r = (2 * warp + mi) * 16 + g + half * 8;
         if (r < R)
-          *reinterpret_cast<__nv_bfloat162*>(dpos + ((size_t)b * R + r) * NH + (size_t)n * H + h) =
+          *reinterpret_cast<__nv_bfloat162*>(dpos + ((size_t)b * R + r) * p.ld_dpos + (size_t)n * H + h) =
               __floats2bfloat162_rn(aP[mi][nh][2 * half], aP[mi][nh][2 * half + 1]);
       }
     }
@@ -1161,7 +1162,9 @@ template <int KS>
 static int launch_att_bwd_mma(const AttParams& p, const __nv_bfloat16* probs, const __nv_bfloat16* dctx, const __nv_bfloat16* octx,
                               __nv_bfloat16* ds_ws, __nv_bfloat16* dqkv, __nv_bfloat16* dpos, float* du, float* dvb, cudaStream_t stream) {
   const size_t smem1 = att_mma_bwd_rows_smem<KS>(p.T), smem2 = att_mma_bwd_cols_smem<KS>(p.T);
-  if (smem1 > 227 * 1024 || smem2 > 227 * 1024 || p.T > 256 || p.T < 16 || (p.H & 3) || (p.ld_qkv & 3) || !octx) return -1;
+  if (smem1 > 227 * 1024 || smem2 > 227 * 1024 || p.T > 256 || p.T < 16 || (p.H & 3) || (p.ld_qkv & 3) || (p.ld_pos & 3) ||
+      (reinterpret_cast<uintptr_t>(p.pos) & 7) || !octx)
+    return -1;
   if (cudaFuncSetAttribute(rel_attention_bwd_rows_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(rel_attention_bwd_cols_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return TFASR_EXECUTION_FAILED;
@@ -1192,6 +1195,7 @@ static size_t att_rows_smem(int T, int H, bool bwd) {
 static int att_check(const AttParams& p) {
   if (p.B < 0 || p.T < 1 || p.N < 1 || p.H < 2 || (p.H & 1) || p.H > kMaxH || p.R != 2 * p.T - 1 || p.T > 1024) return TFASR_INVALID_VALUE;
   if (!p.qkv || !p.pos || !p.ubias || !p.vbias || (p.ld_qkv & 1) || p.B > 65535) return TFASR_INVALID_VALUE;
+  if (p.ld_pos < p.N * p.H || p.ld_dpos < p.N * p.H || (p.ld_pos & 1) || (p.ld_dpos & 1)) return TFASR_INVALID_VALUE;
   return TFASR_OK;
 }
 
@@ -1200,7 +1204,7 @@ static int att_check(const AttParams& p) {
 using namespace tfasr;
 
 static AttParams make_att(const void* qkv, int ld_qkv, const void* pos, const float* u, const float* v, const int32_t* length, int B, int T, int N,
-                          int H, int chunk, int history) {
+                          int H, int chunk, int history, int ld_pos, int ld_dpos) {
   AttParams p;
   p.qkv = static_cast<const __nv_bfloat16*>(qkv);
   p.pos = static_cast<const __nv_bfloat16*>(pos);
@@ -1213,6 +1217,8 @@ static AttParams make_att(const void* qkv, int ld_qkv, const void* pos, const fl
   p.H = H;
   p.R = 2 * T - 1;
   p.ld_qkv = ld_qkv;
+  p.ld_pos = ld_pos;
+  p.ld_dpos = ld_dpos;
   p.chunk = chunk;
   p.history = history;
   p.scale = 1.0f / sqrtf((float)H);
@@ -1228,10 +1234,10 @@ static AttParams make_att(const void* qkv, int ld_qkv, const void* pos, const fl
     else { LAUNCH(KERNEL<32>, __VA_ARGS__); }                                                                      \
   } while (0)
 
-extern "C" int tfasr_rel_attention_fwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias,
-                                       const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, void* ctx,
-                                       void* probs, tfasr_stream_t stream_) {
-  AttParams p = make_att(qkv, ld_qkv, pos, ubias, vbias, length, B, T, N, H, chunk, history);
+static int att_fwd_impl(const void* qkv, int32_t ld_qkv, const void* pos, int32_t ld_pos, const float* ubias, const float* vbias,
+                        const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, void* ctx, void* probs,
+                        tfasr_stream_t stream_) {
+  AttParams p = make_att(qkv, ld_qkv, pos, ubias, vbias, length, B, T, N, H, chunk, history, ld_pos, N * H);
   int st = att_check(p);
   if (st || !ctx || !probs) return st ? st : TFASR_INVALID_VALUE;
   if (B == 0) return TFASR_OK;
@@ -1260,11 +1266,22 @@ extern "C" int tfasr_rel_attention_fwd(const void* qkv, int32_t ld_qkv, const vo
   return check_launch();
 }
 
-extern "C" int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias,
-                                       const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history,
-                                       const void* probs, const void* dctx, const void* ctx, void* ds_ws, void* dqkv, void* dpos, float* du,
-                                       float* dvb, tfasr_stream_t stream_) {
-  AttParams p = make_att(qkv, ld_qkv, pos, ubias, vbias, length, B, T, N, H, chunk, history);
+extern "C" int tfasr_rel_attention_fwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias,
+                                       const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, void* ctx,
+                                       void* probs, tfasr_stream_t stream) {
+  return att_fwd_impl(qkv, ld_qkv, pos, N * H, ubias, vbias, length, B, T, N, H, chunk, history, ctx, probs, stream);
+}
+extern "C" int tfasr_rel_attention_fwd_ld(const void* qkv, int32_t ld_qkv, const void* pos, int32_t ld_pos, const float* ubias, const float* vbias,
+                                          const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history,
+                                          void* ctx, void* probs, tfasr_stream_t stream) {
+  return att_fwd_impl(qkv, ld_qkv, pos, ld_pos, ubias, vbias, length, B, T, N, H, chunk, history, ctx, probs, stream);
+}
+
+static int att_bwd_impl(const void* qkv, int32_t ld_qkv, const void* pos, int32_t ld_pos, const float* ubias, const float* vbias,
+                        const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, const void* probs,
+                        const void* dctx, const void* ctx, void* ds_ws, void* dqkv, void* dpos, int32_t ld_dpos, float* du, float* dvb,
+                        tfasr_stream_t stream_) {
+  AttParams p = make_att(qkv, ld_qkv, pos, ubias, vbias, length, B, T, N, H, chunk, history, ld_pos, ld_dpos);
   int st = att_check(p);
   if (st || !probs || !dctx || !ds_ws || !dqkv || !dpos || !du || !dvb) return st ? st : TFASR_INVALID_VALUE;
   if (B == 0) return TFASR_OK;
@@ -1306,4 +1323,19 @@ extern "C" int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const vo
                                                                           static_cast<__nv_bfloat16*>(dpos));
   count_launch();
   return check_launch();
+}
+
+extern "C" int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias,
+                                       const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history,
+                                       const void* probs, const void* dctx, const void* ctx, void* ds_ws, void* dqkv, void* dpos, float* du,
+                                       float* dvb, tfasr_stream_t stream) {
+  return att_bwd_impl(qkv, ld_qkv, pos, N * H, ubias, vbias, length, B, T, N, H, chunk, history, probs, dctx, ctx, ds_ws, dqkv, dpos, N * H, du, dvb,
+                      stream);
+}
+extern "C" int tfasr_rel_attention_bwd_ld(const void* qkv, int32_t ld_qkv, const void* pos, int32_t ld_pos, const float* ubias, const float* vbias,
+                                          const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history,
+                                          const void* probs, const void* dctx, const void* ctx, void* ds_ws, void* dqkv, void* dpos, int32_t ld_dpos,
+                                          float* du, float* dvb, tfasr_stream_t stream) {
+  return att_bwd_impl(qkv, ld_qkv, pos, ld_pos, ubias, vbias, length, B, T, N, H, chunk, history, probs, dctx, ctx, ds_ws, dqkv, dpos, ld_dpos, du,
+                      dvb, stream);
 }

@@ -267,7 +267,9 @@ class ConformerEncoder(_Params):
     def _prepare_packs(self):
         """bf16 operand copies of the GEMM weights for this forward/backward (weights change every optimizer step): persistent
         buffers, refreshed by one batched launch (fused.PackPlan)."""
-        if getattr(self, "_packs", None) is None or self._pack_plan is None:
+        batched = ops.pos_batched_active()
+        if getattr(self, "_packs", None) is None or self._pack_plan is None or getattr(self, "_packs_pos_batched", None) != batched:
+            self._packs_pos_batched = batched
             plan = fused.PackPlan()
             unplan = fused.UnpackPlan()
             packs = {}
@@ -276,10 +278,12 @@ class ConformerEncoder(_Params):
                     for d in ("dense_1", "dense_2"):
                         n = f"block_{b}.{ff}.{d}"
                         packs[n] = fused.WeightPack(self[n + ".kernel"], self[n + ".bias"], plan=plan)
-                packs[f"block_{b}.mhsa_module"] = fused.MhsaPack(self, f"block_{b}.mhsa_module", plan, unplan)
+                packs[f"block_{b}.mhsa_module"] = fused.MhsaPack(self, f"block_{b}.mhsa_module", plan, unplan, with_pos=not batched)
                 cm = f"block_{b}.conv_module"
                 packs[cm + ".pw_conv_1"] = fused.GluPack(self[cm + ".pw_conv_1.kernel"], self[cm + ".pw_conv_1.bias"], plan, unplan)
                 packs[cm + ".pw_conv_2"] = fused.WeightPack(self[cm + ".pw_conv_2.kernel"], self[cm + ".pw_conv_2.bias"], plan=plan)
+            if batched:
+                packs["pos_all"] = fused.PosAllPack(self, plan, unplan)
             self._packs, self._pack_plan, self._unpack_plan = packs, plan, unplan
         self._pack_plan.run()
 
@@ -303,7 +307,7 @@ class ConformerEncoder(_Params):
         y = ops.dropout(y, self.dropout, training)
         return ops.residual(x, y, self.ffm_residual_factor)
 
-    def _mhsa(self, x, relpe, length, pre, training):
+    def _mhsa(self, x, relpe, length, pre, training, pos_all=None, blk=0):
         # MHSAModule.call, conformer.py:209-239 -> MultiHeadRelativeAttention.call, multihead_attention.py:584-667
         D, N, H = self.dmodel, self.num_heads, self.head_size
         m = pre + ".mhsa"
@@ -318,9 +322,14 @@ class ConformerEncoder(_Params):
             x2 = x.reshape(B * T, D).to(torch.bfloat16)
             a = fused.layer_norm(x2, self[pre + ".ln.gamma"], self[pre + ".ln.beta"])
             qkv = fused.linear(a, pk.qkv)
-            pos = fused.linear(relpe if relpe.dtype == torch.bfloat16 else relpe.reshape(-1, D).to(torch.bfloat16).contiguous(), pk.pos)
-            ctx = fused.rel_attention(qkv, pos, self["content_attention_bias"], self["positional_attention_bias"], length.to(torch.int32),
-                                      B, T, N, H, self.chunk_size, self.history_size)
+            if pos_all is not None:
+                ctx = fused.rel_attention_slice(qkv, pos_all, blk, self._packs["pos_all"], self["content_attention_bias"],
+                                                self["positional_attention_bias"], length.to(torch.int32), B, T, N, H, self.chunk_size,
+                                                self.history_size)
+            else:
+                pos = fused.linear(relpe if relpe.dtype == torch.bfloat16 else relpe.reshape(-1, D).to(torch.bfloat16).contiguous(), pk.pos)
+                ctx = fused.rel_attention(qkv, pos, self["content_attention_bias"], self["positional_attention_bias"], length.to(torch.int32),
+                                          B, T, N, H, self.chunk_size, self.history_size)
             y = fused.linear(ctx, pk.out, residual=x2, factor=self.mhsam_residual_factor, drop_p=p,
                              salt=self._salt(pre, 0), seed=seed)
             return y.view(B, T, D)
@@ -368,10 +377,13 @@ class ConformerEncoder(_Params):
         relpe = ops.dropout(relpe, 0.0, training)
         if ops.fused_active(x):
             relpe = relpe.reshape(-1, self.dmodel).to(torch.bfloat16).contiguous()  # GEMM operand of every block's position projection: cast once
+        pos_all = None
+        if ops.fused_active(x) and self._packs_pos_batched:
+            pos_all = fused.linear(relpe, self._packs["pos_all"])  # [B*R, blocks*NH]: every block's position projection in one GEMM
         for b in range(self.num_blocks):
             pre = f"block_{b}"
             x = self._ff(x, pre + ".ff_module_1", training)
-            x = self._mhsa(x, relpe, length, pre + ".mhsa_module", training)
+            x = self._mhsa(x, relpe, length, pre + ".mhsa_module", training, pos_all=pos_all, blk=b)
             x = self._conv(x, pre + ".conv_module", training)
             x = self._ff(x, pre + ".ff_module_2", training)
             if ops.fused_active(x):

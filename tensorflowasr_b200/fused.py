@@ -571,12 +571,50 @@ class QkvPack(WeightPack):
         self._db = None
 
 
+class PosAllPack(WeightPack):
+    """The position projections of ALL blocks as one GEMM [D -> blocks * NH]: every block projects the same relative position table
+    (conformer.py:672-701 hands one relpe to all blocks; multihead_attention.py:304 `encoding` EinsumDense per block), so one launch replaces
+    `blocks` forward GEMMs, and one column-sum + one weight-gradient GEMM replace `blocks` of each in the backward pass.  Weight / bias
+    gradients fan out to the per-block Keras layers through the UnpackPlan's single launch (as QkvPack)."""
+
+    def __init__(self, enc, plan: PackPlan, unplan: UnpackPlan):
+        D, NH, nb = enc.dmodel, enc.num_heads * enc.head_size, enc.num_blocks
+        self.parts = [(enc[f"block_{b}.mhsa_module.mhsa.encoding.kernel"], enc[f"block_{b}.mhsa_module.mhsa.encoding.bias"]) for b in range(nb)]
+        self.param, self.D, self.NH, self.nb = None, D, NH, nb
+        self.unplan = unplan
+        dev = self.parts[0][0].device
+        W = nb * NH
+        self.shape2d = (D, W)
+        self.dw_packed = torch.zeros((D, W), dtype=torch.float32, device=dev)
+        self.db_packed = torch.zeros(W, dtype=torch.float32, device=dev)
+        self.w = torch.empty((D, W), dtype=torch.bfloat16, device=dev)
+        self.wt = torch.empty((W, D), dtype=torch.bfloat16, device=dev)
+        self._bias = torch.empty(W, dtype=torch.float32, device=dev)
+        for i, (wp, bp) in enumerate(self.parts):
+            unplan.add(wp, D, NH, self.dw_packed, W, c0=i * NH)
+            unplan.add(bp, 1, NH, self.db_packed, W, c0=i * NH)
+            plan.add(wp, D, NH, self.w, self.wt, ldw=W, ldwt=D, c0=i * NH)
+            plan.add(bp, 1, NH, self._bias, None, ldw=W, c0=i * NH, f32=True)
+        self.bias = self._bias
+        self.dpos = None  # the blocks' shared gradient buffer, alive during one backward pass
+
+    def bias_f32(self):
+        return self._bias
+
+    def bias_grad_target(self):
+        return self.db_packed
+
+    def accumulate_wgrad(self, x, dz):
+        kernels.gemm(x, dz, mn_major=True, out=self.dw_packed, accumulate=True, k_splits=_splits(x.shape[0]))
+        self.unplan.request()
+
+
 class MhsaPack:
-    def __init__(self, enc, pre, plan: PackPlan = None, unplan: UnpackPlan = None):
+    def __init__(self, enc, pre, plan: PackPlan = None, unplan: UnpackPlan = None, with_pos: bool = True):
         m = pre + ".mhsa"
         D, N, H = enc.dmodel, enc.num_heads, enc.head_size
         self.qkv = QkvPack(enc, pre, plan, unplan)
-        self.pos = WeightPack(enc[f"{m}.encoding.kernel"], enc[f"{m}.encoding.bias"], plan=plan, shape2d=(D, N * H))
+        self.pos = WeightPack(enc[f"{m}.encoding.kernel"], enc[f"{m}.encoding.bias"], plan=plan, shape2d=(D, N * H)) if with_pos else None
         self.out = WeightPack(enc[f"{m}.attention_output.kernel"], enc[f"{m}.attention_output.bias"], plan=plan, shape2d=(N * H, D))
 
 
@@ -602,6 +640,39 @@ class _RelAttentionFn(torch.autograd.Function):
 
 def rel_attention(qkv, pos, u, v, length, B, T, N, H, chunk=None, history=None):
     return _RelAttentionFn.apply(qkv, pos, u, v, length, B, T, N, H, chunk, history)
+
+
+class _RelAttentionSliceFn(torch.autograd.Function):
+    """_RelAttentionFn on block `blk`'s column slice of the all-blocks position projection `pos_all` [B*R, blocks*NH] (PosAllPack).
+    Backward: every block writes its slice of ONE shared gradient buffer; block 0 — whose backward runs last, every later block depends on
+    its output — hands the buffer to autograd as the gradient of pos_all, the others return None (no `blocks` full-size accumulations)."""
+
+    @staticmethod
+    def forward(ctx, qkv, pos_all, u, v, length, B, T, N, H, chunk, history, blk, pack):
+        NH = N * H
+        out, probs = kernels.rel_attention_fwd(qkv, pos_all[:, blk * NH:(blk + 1) * NH], u.detach(), v.detach(), length, B, T, N, H, chunk, history)
+        ctx.save_for_backward(qkv, pos_all, probs, length, out)
+        ctx.misc = (u, v, B, T, N, H, chunk, history, blk, pack)
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        qkv, pos_all, probs, length, out = ctx.saved_tensors
+        u, v, B, T, N, H, chunk, history, blk, pack = ctx.misc
+        NH = N * H
+        if pack.dpos is None or pack.dpos.shape != pos_all.shape:
+            pack.dpos = torch.zeros_like(pos_all)  # zeros: a backward pass that skips some block must not leave garbage in its slice
+        sl = slice(blk * NH, (blk + 1) * NH)
+        dqkv, _ = kernels.rel_attention_bwd(qkv, pos_all[:, sl], u.detach(), v.detach(), length, B, T, N, H, probs, dctx.contiguous(), _grad(u),
+                                            _grad(v), chunk, history, ctx=out, dpos_out=pack.dpos[:, sl])
+        g = None
+        if blk == 0:
+            g, pack.dpos = pack.dpos, None
+        return dqkv, g, None, None, None, None, None, None, None, None, None, None, None
+
+
+def rel_attention_slice(qkv, pos_all, blk, pack, u, v, length, B, T, N, H, chunk=None, history=None):
+    return _RelAttentionSliceFn.apply(qkv, pos_all, u, v, length, B, T, N, H, chunk, history, blk, pack)
 
 
 # ------------------------------------------------------------------------------------------------ ConvModule

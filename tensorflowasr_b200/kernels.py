@@ -248,25 +248,41 @@ def colsum(x2d, out):
 
 
 def rel_attention_fwd(qkv, pos, ubias, vbias, length, B, T, N, H, chunk=None, history=None):
-    """-> (ctx [B*T, N*H] bf16, probs [B,N,T,T] bf16)."""
+    """-> (ctx [B*T, N*H] bf16, probs [B,N,T,T] bf16).  `pos` [B*R, N*H]: contiguous, or a column slice of the all-blocks projection
+    (row stride = pos.stride(0))."""
     lib = _lib.load()
     ctx = torch.empty((B * T, N * H), dtype=torch.bfloat16, device=qkv.device)
     probs = torch.empty((B, N, T, T), dtype=torch.bfloat16, device=qkv.device)
     ch = int(chunk) if (chunk is not None and history is not None) else 0
     hi = int(history) if (chunk is not None and history is not None) else 0
+    if pos.dim() == 2 and pos.stride(0) != N * H:
+        assert pos.stride(1) == 1
+        _lib.check(lib.tfasr_rel_attention_fwd_ld(_lib.ptr(qkv), qkv.stride(0), _lib.ptr_rows(pos), pos.stride(0), _lib.ptr(ubias), _lib.ptr(vbias),
+                                                  _lib.ptr(length), B, T, N, H, ch, hi, _lib.ptr(ctx), _lib.ptr(probs), _st(qkv)),
+                   "tfasr_rel_attention_fwd_ld")
+        return ctx, probs
     _lib.check(lib.tfasr_rel_attention_fwd(_lib.ptr(qkv), qkv.stride(0), _lib.ptr(pos), _lib.ptr(ubias), _lib.ptr(vbias), _lib.ptr(length), B, T, N, H,
                                            ch, hi, _lib.ptr(ctx), _lib.ptr(probs), _st(qkv)), "tfasr_rel_attention_fwd")
     return ctx, probs
 
 
-def rel_attention_bwd(qkv, pos, ubias, vbias, length, B, T, N, H, probs, dctx, du, dvb, chunk=None, history=None, ctx=None):
-    """-> (dqkv like qkv, dpos like pos); du / dvb (f32 [N,H]) accumulated.  `ctx`: the forward's output (tensor-core path)."""
+def rel_attention_bwd(qkv, pos, ubias, vbias, length, B, T, N, H, probs, dctx, du, dvb, chunk=None, history=None, ctx=None, dpos_out=None):
+    """-> (dqkv like qkv, dpos like pos); du / dvb (f32 [N,H]) accumulated.  `ctx`: the forward's output (tensor-core path).
+    `dpos_out`: where to write dpos ([B*R, N*H] view with unit column stride, e.g. this block's slice of the shared gradient)."""
     lib = _lib.load()
     dqkv = torch.empty_like(qkv)
-    dpos = torch.empty_like(pos)
     ds = torch.empty_like(probs)
     ch = int(chunk) if (chunk is not None and history is not None) else 0
     hi = int(history) if (chunk is not None and history is not None) else 0
+    if dpos_out is not None or (pos.dim() == 2 and pos.stride(0) != N * H):
+        dpos = dpos_out if dpos_out is not None else torch.empty((pos.shape[0], N * H), dtype=torch.bfloat16, device=pos.device)
+        assert pos.stride(-1) == 1 and dpos.stride(-1) == 1
+        _lib.check(lib.tfasr_rel_attention_bwd_ld(_lib.ptr(qkv), qkv.stride(0), _lib.ptr_rows(pos), pos.stride(0), _lib.ptr(ubias), _lib.ptr(vbias),
+                                                  _lib.ptr(length), B, T, N, H, ch, hi, _lib.ptr(probs), _lib.ptr(dctx), _lib.ptr(ctx), _lib.ptr(ds),
+                                                  _lib.ptr(dqkv), _lib.ptr_rows(dpos), dpos.stride(0), _lib.ptr(du), _lib.ptr(dvb), _st(qkv)),
+                   "tfasr_rel_attention_bwd_ld")
+        return dqkv, dpos
+    dpos = torch.empty_like(pos)
     _lib.check(lib.tfasr_rel_attention_bwd(_lib.ptr(qkv), qkv.stride(0), _lib.ptr(pos), _lib.ptr(ubias), _lib.ptr(vbias), _lib.ptr(length), B, T, N, H,
                                            ch, hi, _lib.ptr(probs), _lib.ptr(dctx), _lib.ptr(ctx), _lib.ptr(ds), _lib.ptr(dqkv), _lib.ptr(dpos), _lib.ptr(du),
                                            _lib.ptr(dvb), _st(qkv)), "tfasr_rel_attention_bwd")

@@ -134,6 +134,21 @@ def conv1_v2_active() -> bool:
     return _CONV1_V2
 
 
+_POS_BATCHED = _os.environ.get("TFASR_POS_BATCHED", "0") == "1"
+
+
+def set_pos_batched(flag: bool):
+    """Conformer encoder: project the relative position table for ALL blocks in one GEMM (fused.PosAllPack; the attention kernels read /
+    write column slices through tfasr_rel_attention_*_ld) instead of one projection, one bias column-sum and one weight-gradient GEMM per
+    block.  Off by default until measured on a B200."""
+    global _POS_BATCHED
+    _POS_BATCHED = bool(flag)
+
+
+def pos_batched_active() -> bool:
+    return _POS_BATCHED
+
+
 _PEER_BN = _os.environ.get("TFASR_PEER_BN", "0") == "1"
 
 

@@ -46,7 +46,7 @@ def load(asan=False, tsan=False):
               "tfasr_bn_finalize", "tfasr_bn_apply", "tfasr_bn_bwd_stats", "tfasr_bn_bwd_apply", "tfasr_conv1_3x3s2_fwd", "tfasr_conv1_3x3s2_wgrad",
               "tfasr_im2col_3x3s2", "tfasr_col2im_3x3s2", "tfasr_dwconv_causal_fwd", "tfasr_dwconv_causal_bwd", "tfasr_joint_tanh_fwd",
               "tfasr_joint_reduce_bwd", "tfasr_adamw_flat_f32", "tfasr_signal_normalize_f32", "tfasr_feature_normalize_f32", "tfasr_specaugment_f32",
-              "tfasr_pack_weights", "tfasr_unpack_add", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd", "tfasr_lstm_rec_fwd", "tfasr_lstm_rec_bwd",
+              "tfasr_pack_weights", "tfasr_unpack_add", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd", "tfasr_rel_attention_fwd_ld", "tfasr_rel_attention_bwd_ld", "tfasr_lstm_rec_fwd", "tfasr_lstm_rec_bwd",
               "tfasr_lstm_supported", "tfasr_gemm_bf16"):
         getattr(lib, n).restype = c_i32
     return lib
@@ -477,10 +477,12 @@ def _att_allowed(T, length, chunk, history):
     return ok
 
 
-def check_rel_attention(lib, B, T, N, H, lengths, chunk=0, history=0, seed=32):
+def check_rel_attention(lib, B, T, N, H, lengths, chunk=0, history=0, seed=32, blocks=0, blk=0):
     """MultiHeadRelativeAttention._compute_attention (multihead_attention.py:543-582) with rel_left_shift as out[t, j] = posattn[t, T-1-t+j]
     (:27-64), the masked softmax (general.py:30-41) and the streaming mask (:104-143): forward and the full backward of the fused kernels —
-    the mma.sync path when T <= 256 and H % 4 == 0, the FP32 kernels otherwise — against float64 numpy on the valid query rows."""
+    the mma.sync path when T <= 256 and H % 4 == 0, the FP32 kernels otherwise — against float64 numpy on the valid query rows.
+    blocks > 0: the *_ld entry points — pos is column slice `blk` of a [B*R, blocks*NH] buffer (the all-blocks position projection), dpos
+    goes to the same slice of a shared buffer whose other columns must stay untouched."""
     rng = np.random.default_rng(seed)
     NH, R = N * H, 2 * T - 1
     qkv = rbf(rng.standard_normal((B, T, 3 * NH)) * 0.7)
@@ -525,13 +527,23 @@ def check_rel_attention(lib, B, T, N, H, lengths, chunk=0, history=0, seed=32):
             dv_ref[n] += np.einsum("tj,tjh->h", dS, pw)
             np.add.at(dpos_ref[b, :, n * H:(n + 1) * H], idx.reshape(-1), (dS[:, :, None] * qv[:, None, :]).reshape(T * T, H))
     qb, qp = heap(to_bf16(qkv.reshape(B * T, 3 * NH)))
-    pb, pp_ = heap(to_bf16(pos.reshape(B * R, NH)))
+    W = max(blocks, 1) * NH
+    pos_wide = rbf(rng.standard_normal((B * R, W))) if blocks else None
+    if blocks:
+        pos_wide[:, blk * NH:(blk + 1) * NH] = pos.reshape(B * R, NH)
+        pwb, pwp = heap(to_bf16(pos_wide))
+        pp_ = c_vp(pwb.ctypes.data + 2 * blk * NH)
+    else:
+        pb, pp_ = heap(to_bf16(pos.reshape(B * R, NH)))
     ubb, ubp = heap(ub)
     vbb, vbp = heap(vb)
     lb, lp = heap(ln)
     cb, cp = heap(np.zeros((B * T, NH), np.uint16))
     prb, prp = heap(np.zeros((B, N, T, T), np.uint16))
-    st = lib.tfasr_rel_attention_fwd(qp, 3 * NH, pp_, ubp, vbp, lp, B, T, N, H, chunk, history, cp, prp, None)
+    if blocks:
+        st = lib.tfasr_rel_attention_fwd_ld(qp, 3 * NH, pp_, W, ubp, vbp, lp, B, T, N, H, chunk, history, cp, prp, None)
+    else:
+        st = lib.tfasr_rel_attention_fwd(qp, 3 * NH, pp_, ubp, vbp, lp, B, T, N, H, chunk, history, cp, prp, None)
     assert st == 0, st
     ctx = from_bf16(cb).reshape(B, T, NH)
     probs = from_bf16(prb)
@@ -543,12 +555,21 @@ def check_rel_attention(lib, B, T, N, H, lengths, chunk=0, history=0, seed=32):
     db, dp = heap(to_bf16(dctx.reshape(B * T, NH)))
     dsb, dsp = heap(np.zeros((B, N, T, T), np.uint16))
     dqb, dqp = heap(np.full((B * T, 3 * NH), 0x7FC0, np.uint16))
-    dpb, dpp = heap(np.full((B * R, NH), 0x7FC0, np.uint16))
+    dpb, dpp = heap(np.full((B * R, W), 0x7FC0, np.uint16))
     du0, dv0 = rng.standard_normal((N, H)).astype(np.float32), rng.standard_normal((N, H)).astype(np.float32)
     dub, dup = heap(du0)
     dvb_, dvp = heap(dv0)
-    st = lib.tfasr_rel_attention_bwd(qp, 3 * NH, pp_, ubp, vbp, lp, B, T, N, H, chunk, history, prp, dp, cp, dsp, dqp, dpp, dup, dvp, None)
+    if blocks:
+        st = lib.tfasr_rel_attention_bwd_ld(qp, 3 * NH, pp_, W, ubp, vbp, lp, B, T, N, H, chunk, history, prp, dp, cp, dsp, dqp,
+                                            c_vp(dpb.ctypes.data + 2 * blk * NH), W, dup, dvp, None)
+    else:
+        st = lib.tfasr_rel_attention_bwd(qp, 3 * NH, pp_, ubp, vbp, lp, B, T, N, H, chunk, history, prp, dp, cp, dsp, dqp, dpp, dup, dvp, None)
     assert st == 0, st
+    if blocks:
+        other = np.ones(W, bool)
+        other[blk * NH:(blk + 1) * NH] = False
+        assert (dpb[:, other] == 0x7FC0).all(), "dpos written outside this block's column slice"
+        dpb = np.ascontiguousarray(dpb[:, blk * NH:(blk + 1) * NH])
     dqkv = from_bf16(dqb).reshape(B, T, 3 * NH)
     dpos = from_bf16(dpb).reshape(B, R, NH)
     assert np.isfinite(dqkv).all() and np.isfinite(dpos).all(), "gradient cells left unwritten"
@@ -813,7 +834,9 @@ CASES = [
     ("pack_unpack", check_pack_unpack),
     ("rel_attention_mma", lambda lib: check_rel_attention(lib, 2, 40, 2, 36, [40, 23])),  # Conformer-S head size: the mma.sync kernels, KS = 3
     ("rel_attention_mma_streaming", lambda lib: check_rel_attention(lib, 1, 48, 2, 16, [41], chunk=8, history=16)),
-    ("rel_attention_fp32", lambda lib: check_rel_attention(lib, 2, 11, 2, 10, [11, 6])),  # T < 16, H % 4 != 0: the FP32 kernels
+    ("rel_attention_fp32", lambda lib: check_rel_attention(lib, 2, 11, 2, 10, [11, 6])),
+    ("rel_attention_mma_slice", lambda lib: check_rel_attention(lib, 2, 40, 2, 36, [40, 23], blocks=3, blk=1)),  # column slice of the all-blocks projection
+    ("rel_attention_fp32_slice", lambda lib: check_rel_attention(lib, 1, 11, 2, 10, [9], blocks=2, blk=1)),  # T < 16, H % 4 != 0: the FP32 kernels
     ("gemm_plain", lambda lib: check_gemm(lib, 200, 72, 136)),  # one ragged M tile, N < tile width, K not a multiple of 64
     ("gemm_f32_bias", lambda lib: check_gemm(lib, 129, 1000, 320, f32_out=True, bias=True)),  # the joint's shape class: 4 tiles of 256 columns
     ("gemm_swish_aux", lambda lib: check_gemm(lib, 150, 160, 64, bias=True, act=1, aux=True)),  # FFN-1: tile width 160

@@ -130,6 +130,14 @@ def install(monkeypatch, real_gemm=True):
         return t.data_ptr()
 
     monkeypatch.setattr(_lib, "ptr", ptr)
+
+    def ptr_rows(t):
+        if t is None:
+            return None
+        assert not t.is_cuda and t.dim() == 2 and t.stride(1) == 1, "emulated kernels take host tensors with unit column stride"
+        return t.data_ptr()
+
+    monkeypatch.setattr(_lib, "ptr_rows", ptr_rows)
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)  # no CUDA driver here
     if not real_gemm:
         monkeypatch.setattr(kernels, "gemm", gemm)

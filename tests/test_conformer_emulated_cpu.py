@@ -14,12 +14,12 @@ import emu_backend
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available (emulator build)")
 
 
-def _model(V=16):
+def _model(V=16, blocks=1):
     import tensorflowasr_b200 as tfasr
 
     cfg = tfasr.conformer_small_config(vocab_size=V)
     cfg["speech_config"].pop("augmentation_config", None)
-    cfg.update(encoder_num_blocks=1, encoder_dmodel=16, encoder_head_size=8, encoder_num_heads=2, encoder_dropout=0.0, prediction_embed_dim=16,
+    cfg.update(encoder_num_blocks=blocks, encoder_dmodel=16, encoder_head_size=8, encoder_num_heads=2, encoder_dropout=0.0, prediction_embed_dim=16,
                prediction_rnn_units=64, joint_dim=16, encoder_kernel_size=7)
     cfg["encoder_subsampling"]["config"]["filters"] = [16, 16]
     model = tfasr.Conformer(**cfg, seed=3)
@@ -63,9 +63,10 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
     from tensorflowasr_b200 import ops
 
     emu = emu_backend.install(monkeypatch)
-    model, data = _model(), _batch()
+    model, data = _model(blocks=2), _batch()
     state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    v2 = (ops.set_conv1_v2, ops.set_im2col_v2, ops.set_joint_v2, ops.set_dwconv_wgrad_v2, ops.set_rnnt_grad_v2, ops.set_fused_lse)
+    # + the batched position projection: one GEMM for all blocks, attention kernels on column slices, one shared gradient buffer
+    v2 = (ops.set_conv1_v2, ops.set_im2col_v2, ops.set_joint_v2, ops.set_dwconv_wgrad_v2, ops.set_rnnt_grad_v2, ops.set_fused_lse, ops.set_pos_batched)
     try:
         ops.set_precision("fp32")
         ops.set_fused(False)
@@ -80,6 +81,7 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
         emu.calls.clear()
         loss2, g2 = _run(model, data, state0)  # fused route, every second-generation kernel + fused log-sum-exp
         calls2 = dict(emu.calls)
+        loss3, g3 = _run(model, data, state0)  # once more on the same packs: packed gradient sums and the shared dpos buffer start clean
     finally:
         for s in v2:
             s(False)
@@ -87,14 +89,16 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
         ops.set_precision("fp32")
     second_gen = ("tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2",
                   "tfasr_joint_reduce_bwd_v2", "tfasr_dwconv_causal_wgrad_v2", "tfasr_dwconv_causal_bwd_dx", "tfasr_rnnt_loss_bwd_bf16_v2",
-                  "tfasr_rnnt_loss_fwd_rowstats_f32")
+                  "tfasr_rnnt_loss_fwd_rowstats_f32", "tfasr_rel_attention_fwd_ld", "tfasr_rel_attention_bwd_ld")
     assert not any(k in calls1 for k in second_gen), calls1  # the default route is the first-generation kernels ...
     assert all(calls2.get(k, 0) > 0 for k in second_gen), calls2  # ... and every switch routes to its second-generation kernel
     for k in ("tfasr_logmel_f32", "tfasr_layernorm_fwd", "tfasr_layernorm_bwd", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd", "tfasr_lstm_rec_fwd",
               "tfasr_lstm_rec_bwd", "tfasr_bn_stats", "tfasr_bn_bwd_apply", "tfasr_dwconv_causal_fwd", "tfasr_glu_bwd", "tfasr_pack_weights",
               "tfasr_rnnt_loss_fwd_f32", "tfasr_rnnt_loss_bwd_bf16", "tfasr_conv1_3x3s2_fwd", "tfasr_im2col_3x3s2", "tfasr_joint_tanh_fwd"):
         assert calls1.get(k, 0) > 0, (k, sorted(calls1))  # the step really ran on the hand-written kernels
+    assert calls2["tfasr_rel_attention_fwd_ld"] == 2 and "tfasr_rel_attention_fwd" not in calls2 and "tfasr_rel_attention_bwd" not in calls2
     assert torch.isfinite(loss1).all() and torch.isfinite(loss2).all()
+    torch.testing.assert_close(loss3, loss2, rtol=2e-3, atol=2e-3)
     torch.testing.assert_close(loss1, ref_loss, rtol=3e-2, atol=3e-2)
     torch.testing.assert_close(loss2, loss1, rtol=5e-3, atol=5e-3)
     checked = 0
@@ -106,6 +110,7 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
             continue  # analytically zero gradients are rounding noise
         assert _cos(g1[n], g) > 0.95, (n, _cos(g1[n], g))
         assert _cos(g2[n], g1[n]) > 0.995, (n, _cos(g2[n], g1[n]))
+        assert _cos(g3[n], g2[n]) > 0.995 and abs(float(g3[n].norm() / g2[n].norm()) - 1.0) < 0.05, n
         checked += 1
     assert checked > 40, checked
 

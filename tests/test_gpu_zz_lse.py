@@ -179,3 +179,72 @@ def test_dwconv_wgrad_v2_matches_first_generation_kernel():
         assert torch.equal(res[True][0], res[False][0])
         for i in (1, 2):
             assert (res[True][i] - res[False][i]).abs().max().item() <= 2e-3 * (res[False][i].abs().max().item() + 1e-6)
+
+
+def test_strided_position_slices_match_the_contiguous_attention_kernels():
+    """tfasr_rel_attention_fwd_ld / bwd_ld on a column slice of a wide position buffer == the contiguous entry points, bit for bit (the same
+    kernels, only the row stride differs); columns outside the slice of the shared dpos buffer stay untouched."""
+    from tensorflowasr_b200 import kernels
+
+    torch.manual_seed(11)
+    B, T, N, H, blocks, blk = 4, 250, 4, 36, 16, 5
+    NH, R = N * H, 2 * T - 1
+    qkv = (torch.randn(B * T, 3 * NH, device="cuda") * 0.7).to(torch.bfloat16)
+    pos_all = (torch.randn(B * R, blocks * NH, device="cuda") * 0.7).to(torch.bfloat16)
+    sl = slice(blk * NH, (blk + 1) * NH)
+    pos = pos_all[:, sl].contiguous()
+    u, v = torch.randn(N, H, device="cuda") * 0.3, torch.randn(N, H, device="cuda") * 0.3
+    length = torch.tensor([250, 180, 250, 97], dtype=torch.int32, device="cuda")
+    dctx = torch.randn(B * T, NH, device="cuda").to(torch.bfloat16)
+    ctx0, p0 = kernels.rel_attention_fwd(qkv, pos, u, v, length, B, T, N, H)
+    ctx1, p1 = kernels.rel_attention_fwd(qkv, pos_all[:, sl], u, v, length, B, T, N, H)
+    assert torch.equal(ctx0, ctx1) and torch.equal(p0, p1)
+    du0, dv0, du1, dv1 = (torch.zeros(N, H, device="cuda") for _ in range(4))
+    dq0, dp0 = kernels.rel_attention_bwd(qkv, pos, u, v, length, B, T, N, H, p0, dctx, du0, dv0, ctx=ctx0)
+    shared = torch.full((B * R, blocks * NH), 7.0, device="cuda", dtype=torch.bfloat16)
+    dq1, _ = kernels.rel_attention_bwd(qkv, pos_all[:, sl], u, v, length, B, T, N, H, p1, dctx, du1, dv1, ctx=ctx1, dpos_out=shared[:, sl])
+    assert torch.equal(dq0, dq1) and torch.equal(dp0, shared[:, sl])
+    torch.testing.assert_close(du0, du1, rtol=1e-4, atol=1e-4)  # atomics: order differs from run to run
+    torch.testing.assert_close(dv0, dv1, rtol=1e-4, atol=1e-4)
+    other = torch.ones(blocks * NH, dtype=torch.bool, device="cuda")
+    other[sl] = False
+    assert bool((shared[:, other] == 7.0).all())
+
+
+def test_batched_position_projection_matches_the_per_block_route():
+    """ops.set_pos_batched (one GEMM for every block's position projection, PosAllPack) against the per-block route: losses and every
+    parameter gradient of a 3-block Conformer transducer step, bf16 fused route."""
+    import tensorflowasr_b200 as tfasr
+    from tensorflowasr_b200 import ops
+
+    from test_gpu_model import _batch
+
+    res = {}
+    try:
+        ops.set_precision("bf16")
+        for flag in (False, True):
+            ops.set_pos_batched(flag)
+            cfg = tfasr.conformer_small_config(vocab_size=48)
+            cfg["speech_config"].pop("augmentation_config", None)
+            cfg.update(encoder_num_blocks=3, encoder_dropout=0.0)
+            model = tfasr.Conformer(**cfg, seed=1).cuda()
+            model.train()
+            data, _ = _batch(V=48)
+            losses = model.compute_losses(data, training=True)
+            losses.mean().backward()
+            torch.cuda.synchronize()
+            res[flag] = (losses.detach().float(), {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None})
+    finally:
+        ops.set_pos_batched(False)
+        ops.set_precision("fp32")
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=5e-3, atol=5e-3)
+    assert set(res[True][1]) == set(res[False][1])
+    checked = 0
+    for n, g in res[False][1].items():
+        if g.norm() < 1e-5 * max(1.0, g.numel() ** 0.5) or any(k in n for k in ("key__bias", "encoding__bias", "dw_conv__bias")):
+            continue
+        g2 = res[True][1][n]
+        cos = float((g2 * g).sum() / (g2.norm() * g.norm() + 1e-30))
+        assert cos > 0.995, (n, cos)
+        checked += 1
+    assert checked > 60, checked

@@ -30,9 +30,10 @@ TFASR_RNNT_GRAD_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-
 TFASR_JOINT_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_joint_v2.json 2> gpurun_out/bench_joint_v2.err
 TFASR_IM2COL_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_im2col_v2.json 2> gpurun_out/bench_im2col_v2.err
 TFASR_DWCONV_WGRAD_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_dwconv_wgrad_v2.json 2> gpurun_out/bench_dwconv_wgrad_v2.err
-TFASR_RNNT_GRAD_V2=1 TFASR_FUSED_LSE=1 TFASR_CONV1_V2=1 TFASR_JOINT_V2=1 TFASR_IM2COL_V2=1 TFASR_DWCONV_WGRAD_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_all_v2.json 2> gpurun_out/bench_all_v2.err
+TFASR_POS_BATCHED=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_pos_batched.json 2> gpurun_out/bench_pos_batched.err
+TFASR_POS_BATCHED=1 TFASR_RNNT_GRAD_V2=1 TFASR_FUSED_LSE=1 TFASR_CONV1_V2=1 TFASR_JOINT_V2=1 TFASR_IM2COL_V2=1 TFASR_DWCONV_WGRAD_V2=1 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_all_v2.json 2> gpurun_out/bench_all_v2.err
 # 7. launch list of one step with every second-generation kernel on (compare shares with profiles/launch_summary_r01b.txt)
-TFASR_RNNT_GRAD_V2=1 TFASR_FUSED_LSE=1 TFASR_CONV1_V2=1 TFASR_JOINT_V2=1 TFASR_IM2COL_V2=1 TFASR_DWCONV_WGRAD_V2=1 timeout 600 \
+TFASR_POS_BATCHED=1 TFASR_RNNT_GRAD_V2=1 TFASR_FUSED_LSE=1 TFASR_CONV1_V2=1 TFASR_JOINT_V2=1 TFASR_IM2COL_V2=1 TFASR_DWCONV_WGRAD_V2=1 timeout 600 \
   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r02_all_v2.csv \
   python tools/profile_step.py --ncu > /dev/null 2>&1
 python tools/summarize_launches.py gpurun_out/launches_r02_all_v2.csv > gpurun_out/launch_summary_r02_all_v2.txt 2>&1 || true
