@@ -338,6 +338,44 @@ __global__ void __launch_bounds__(256) scale_mask_colsum_vec_kernel(const __nv_b
   }
 }
 
+// Column sums only, any width with N % 8 == 0: grid (row blocks, column blocks of NVB 8-column vectors); the same four-rows-in-flight loads as
+// the vector kernel above.  Used when N / 8 > 256 (the all-blocks position projection: N = 16 x 144).
+__global__ void __launch_bounds__(256) colsum_wide_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ colsum, int M, int N, int NVB,
+                                                          int rows_per_block) {
+  extern __shared__ float s_col[];  // [8 NVB]
+  const int RL = blockDim.x / NVB;
+  const int cvl = threadIdx.x % NVB, rl = threadIdx.x / NVB;
+  const int c0 = (blockIdx.y * NVB + cvl) * 8;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int i = threadIdx.x; i < 8 * NVB; i += blockDim.x) s_col[i] = 0.f;
+  __syncthreads();
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < RL) {
+    for (int rb = r0 + rl; rb < r1; rb += 4 * RL) {
+      uint4 raw4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = rb + k * RL;
+        if (r < r1) raw4[k] = *reinterpret_cast<const uint4*>(in + (size_t)r * N + c0);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (rb + k * RL >= r1) break;
+        const uint32_t w[4] = {raw4[k].x, raw4[k].y, raw4[k].z, raw4[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(w[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_col[cvl * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * NVB; i += blockDim.x) atomicAdd(colsum + (size_t)blockIdx.y * NVB * 8 + i, s_col[i]);
+}
+
 // GLU backward on interleaved (a, b) pairs: aux [M, 2D] pre-GLU values, dg [M, D] -> daux [M, 2D]; colsum [2D] += column sums.
 __global__ void __launch_bounds__(256) glu_bwd_kernel(const __nv_bfloat16* __restrict__ aux, const __nv_bfloat16* __restrict__ dg,
                                                       __nv_bfloat16* __restrict__ daux, float* __restrict__ colsum, int M, int D,
@@ -429,6 +467,21 @@ extern "C" int tfasr_scale_mask_colsum(const void* in, const void* add, void* ou
         seed_ptr, salt, rows_per_block);
     count_launch();
     return check_launch();
+  }
+  if (!out && !add && scale == 1.0f && dropout_p == 0.f && (N & 7) == 0 && (N >> 3) > 256 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    int nvb = 0;  // widest column block (in 8-column vectors) that divides N / 8 and fits the CTA
+    for (int d = 256; d >= 32 && !nvb; --d)
+      if ((N >> 3) % d == 0) nvb = d;
+    if (nvb) {
+      const int RL = 256 / nvb;
+      int rows_per_block = RL * 4;
+      while ((long long)ceil_div(M, rows_per_block) * ((N >> 3) / nvb) > 8LL * kNumSMs) rows_per_block *= 2;
+      const dim3 grid((unsigned)ceil_div(M, rows_per_block), (unsigned)((N >> 3) / nvb));
+      colsum_wide_kernel<<<grid, 256, sizeof(float) * 8 * nvb, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(in), colsum, M, N,
+                                                                                                   nvb, rows_per_block);
+      count_launch();
+      return check_launch();
+    }
   }
   const int rows_per_block = 32;
   scale_mask_colsum_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, sizeof(uint32_t) * rows_per_block, static_cast<cudaStream_t>(stream)>>>(

@@ -240,6 +240,18 @@ def _dropout_keep(seed, salt, M, N, p):
     return keep
 
 
+def check_colsum_wide(lib, M, N, seed=26):
+    """Pure column sums (out = NULL) of a wide matrix — the bias gradient of the all-blocks position projection: N / 8 > 256 takes
+    colsum_wide_kernel (column blocks on grid.y), N / 8 with no divisor in [32, 256] the scalar kernel; accumulated on top of colsum."""
+    rng = np.random.default_rng(seed)
+    x = rbf(rng.standard_normal((M, N)))
+    c0 = rng.standard_normal(N).astype(np.float32)
+    xb, xp = heap(to_bf16(x))
+    cb, cp = heap(c0.copy())
+    assert lib.tfasr_scale_mask_colsum(xp, None, None, cp, M, N, c_f(1.0), c_f(0.0), None, ctypes.c_ulonglong(0), None) == 0
+    close(cb - c0, x.astype(np.float64).sum(0), 1e-4, f"wide colsum {(M, N)}")
+
+
 def check_scale_mask_glu(lib, M, N, p, seed=25):
     rng = np.random.default_rng(seed)
     x = rbf(rng.standard_normal((M, N)))
@@ -818,6 +830,8 @@ CASES = [
     ("layernorm_wide", lambda lib: check_layernorm(lib, 3, 576, False)),
     ("scale_mask_glu_dropout", lambda lib: check_scale_mask_glu(lib, 40, 144, 0.3)),
     ("scale_mask_glu_plain", lambda lib: check_scale_mask_glu(lib, 9, 20, 0.0)),
+    ("colsum_wide_2304", lambda lib: check_colsum_wide(lib, 61, 2304)),  # 288 vectors -> 2 column blocks of 144
+    ("colsum_wide_prime", lambda lib: check_colsum_wide(lib, 9, 8 * 263)),  # 263 vectors: prime, no block width divides it -> scalar kernel
     ("batchnorm_swish_vec", lambda lib: check_batchnorm(lib, 300, 144, 1)),  # C % 8 == 0: the templated 16-byte kernel
     ("batchnorm_relu_scalar", lambda lib: check_batchnorm(lib, 77, 10, 2)),  # odd vector width: scalar kernels; relu branch (new this round)
     ("batchnorm_relu_vec", lambda lib: check_batchnorm(lib, 130, 32, 2)),  # relu branch of the vector kernel (DeepSpeech2 conv module)

@@ -15,10 +15,20 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not ava
 
 
 class _Patch:
-    """monkeypatch.setattr for a spawned worker (no pytest fixture there; the process ends with the test)."""
+    """monkeypatch.setattr for a spawned worker (no pytest fixture there; the process ends with the test).  In the pytest process itself
+    `undo()` puts everything back."""
+
+    def __init__(self):
+        self._saved = []
 
     def setattr(self, obj, name, value):
+        self._saved.append((obj, name, getattr(obj, name)))
         setattr(obj, name, value)
+
+    def undo(self):
+        for obj, name, value in reversed(self._saved):
+            setattr(obj, name, value)
+        self._saved = []
 
 
 def _free_port():
@@ -52,13 +62,17 @@ def _fused_grads(data, world):
 
     from tensorflowasr_b200 import ops
 
-    emu_backend.install(_Patch())
-    ops.set_precision("bf16")
-    model = _model()
-    model.train()
-    losses = model.compute_losses(data, training=True)
-    (losses.mean() / world).backward()
-    return losses.detach(), {n: p.grad.detach().clone().float() for n, p in model.named_parameters() if p.grad is not None}
+    patch = _Patch()
+    try:
+        emu_backend.install(patch)
+        ops.set_precision("bf16")
+        model = _model()
+        model.train()
+        losses = model.compute_losses(data, training=True)
+        (losses.mean() / world).backward()
+        return losses.detach(), {n: p.grad.detach().clone().float() for n, p in model.named_parameters() if p.grad is not None}
+    finally:
+        patch.undo()
 
 
 def _worker(rank, world, port, out):

@@ -146,6 +146,7 @@ def test_peer_allreduce_ipc_wiring(monkeypatch):
         out[1] = (hosts[1], obj[1])
 
     monkeypatch.setattr(_lib, "load", lambda: _IpcStub())
+    monkeypatch.setattr(_lib, "EMULATED", False)
     monkeypatch.setattr(_lib, "stream_ptr", lambda d=None: 0)
     monkeypatch.setattr(_lib, "ptr", lambda t: None if t is None else t.data_ptr())
     monkeypatch.setattr(tdist, "world_size", lambda: 2)
