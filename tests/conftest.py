@@ -25,6 +25,27 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+def pytest_collection_finish(session):
+    """The sanitizer passes of the emulator checks take ~2 minutes of mostly idle waiting on four subprocesses: start them as soon as it is
+    known that their test will run (never on a `-m gpu` run), so that they overlap with the rest of the CPU suite."""
+    if hasattr(session.config, "workerinput"):  # pytest-xdist worker: the test starts its own passes when it runs
+        return
+    if any(item.nodeid.endswith("test_emulated_kernels_under_sanitizers") and not any(m.name == "skip" for m in item.iter_markers())
+           for item in session.items):
+        import shutil
+
+        if shutil.which("g++") is not None:
+            sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+            import san_runner
+
+            san_runner.start()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if "san_runner" in sys.modules:
+        sys.modules["san_runner"].abort()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

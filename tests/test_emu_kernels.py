@@ -68,24 +68,12 @@ def test_emulated_kernels_under_sanitizers():
     ThreadSanitizer = the stand-in for racecheck: every CUDA thread is an OS thread, __syncthreads / __syncwarp / shuffles / cluster.sync /
     mbarriers are real synchronisation and atomics real atomics, so TSan reports exactly the accesses they do NOT order (a deleted
     __syncthreads is reported; on its first run it found an unordered entry-state read in the decode kernel).
-    Both sanitizers, both check scripts, side by side."""
-    import build_emu
+    Both sanitizers, both check scripts, side by side, overlapping the rest of the suite (tests/emu/san_runner.py)."""
+    import san_runner
 
-    jobs = []
-    asan, tsan = build_emu.asan_runtime(), build_emu.tsan_runtime()
-    if asan is not None:
-        build_emu.build(asan=True)
-        jobs += [("asan", script, dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")) for script in ("checks.py", "checks_v1.py")]
-    if tsan is not None:
-        build_emu.build(tsan=True)
-        # numpy's reference matmuls stay on their thread: OpenBLAS's own (uninstrumented) worker threads would show up as races
-        env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0 halt_on_error=0", OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
-        jobs += [("tsan", script, env) for script in ("checks.py", "checks_v1.py")]
-    if not jobs:
+    results = san_runner.finish()  # started by tests/conftest.py right after collection (or here, when this test runs on its own)
+    if not results:
         pytest.skip("neither libasan nor libtsan available")
-    procs = [(kind, script, subprocess.Popen([sys.executable, os.path.join(HERE, "emu", script), "--" + kind, "--fast"], stdout=subprocess.PIPE,
-                                             stderr=subprocess.PIPE, text=True, env=env)) for kind, script, env in jobs]
-    for kind, script, p in procs:
-        out, err = p.communicate(timeout=2400)
-        assert p.returncode == 0, f"{kind} {script}\n" + out[-2000:] + err[-4000:]
+    for kind, script, rc, out, err in results:
+        assert rc == 0, f"{kind} {script}\n" + out[-2000:] + err[-4000:]
         assert "AddressSanitizer" not in err and "WARNING: ThreadSanitizer" not in err, f"{kind} {script}\n" + err[-6000:]
