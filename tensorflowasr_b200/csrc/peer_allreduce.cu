@@ -53,6 +53,9 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const uint
         state[1] = 1u;
         break;
       }
+#ifndef TFASR_EMU_BUILD
+      __nanosleep(40);  // poll the local L2 a little less eagerly while a peer is still on its way
+#endif
     }
   }
   __syncthreads();
