@@ -318,3 +318,17 @@ def test_smoke_parity_check_on_emulator(monkeypatch):
     rel = ((losses.detach().double() - ref).abs() / ref.abs()).max().item()
     assert rel < 1e-3, (losses.tolist(), ref.tolist())
     assert emu.calls.get("tfasr_logmel_f32", 0) == 1 and emu.calls.get("tfasr_rnnt_loss_fwd_f32", 0) + emu.calls.get("tfasr_rnnt_loss_f32", 0) >= 1, emu.calls
+
+
+def test_decode_bench_tool_dry_run_on_emulator(monkeypatch):
+    """tools/decode_bench.py (round-2 measurement of the persistent decode kernel) end to end on the emulator backend: the tool's own
+    check — host loop and persistent kernel emit the same tokens — must hold, and the script must not die on a Python error on the GPU box."""
+    import os
+    import sys
+
+    emu_backend.install(monkeypatch)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import decode_bench
+
+    res = decode_bench.main(["--batch", "2", "--frames", "5", "--device", "cpu"])
+    assert res["tokens_equal"] and res["iterations"] >= 4 and res["persistent"]["ms"] > 0

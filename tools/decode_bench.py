@@ -16,19 +16,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--frames", type=int, default=250)
     ap.add_argument("--threads", type=int, default=1024)
     ap.add_argument("--blank-bias", type=float, default=4.0, help="added to the blank logit so that random weights emit a realistic token rate")
     ap.add_argument("--out", default=None)
-    args = ap.parse_args()
+    ap.add_argument("--device", default="cuda", help="'cpu' = dry run on the emulator backend (tests/emu_backend.py must be installed by the caller)")
+    args = ap.parse_args(argv)
     import tensorflowasr_b200 as tfasr
     from tensorflowasr_b200 import ops
 
     ops.set_precision("fp32")
-    dev = "cuda"
+    dev = args.device
+    sync = torch.cuda.synchronize if dev.startswith("cuda") else (lambda: None)
     model = tfasr.Conformer(**tfasr.conformer_small_config(vocab_size=1000), seed=1).to(dev).eval()
     with torch.no_grad():
         model.joint_net["vocab.bias"][0] += args.blank_bias
@@ -50,17 +52,17 @@ def main():
     model.call_next = counted
     model._encode_for_decode = lambda inputs: (enc, enc_len, [], prev, states)
     dummy = tfasr.schemas.PredictInput(torch.zeros(B, 1, device=dev), torch.ones(B, dtype=torch.int32, device=dev))
-    res = {"gpu": torch.cuda.get_device_name(0), "batch": B, "frames": T}
+    res = {"gpu": torch.cuda.get_device_name(0) if dev.startswith("cuda") else "cpu emulator (dry run)", "batch": B, "frames": T}
     outs = {}
     for flag in (False, True):
         ops.set_persistent_decode(flag)
         times = []
         for it in range(3):
             calls[0] = 0
-            torch.cuda.synchronize()
+            sync()
             t0 = time.perf_counter()
             out = model.recognize_batch(dummy)
-            torch.cuda.synchronize()
+            sync()
             times.append((time.perf_counter() - t0) * 1e3)
         outs[flag] = out.tokens.cpu()
         key = "persistent" if flag else "host_loop"
@@ -79,6 +81,7 @@ def main():
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         json.dump(res, open(args.out, "w"), indent=1)
+    return res
 
 
 if __name__ == "__main__":

@@ -31,6 +31,16 @@ def flush_l2():
 
 
 def time_ms(fn, iters=10, warmup=3, flush=True):
+    if not torch.cuda.is_available():  # CPU dry run of a tool on the emulator backend (tests): wall clock, no L2 to flush
+        import time
+
+        ts = []
+        for _ in range(max(1, min(iters, 2))):
+            t0 = time.perf_counter()
+            fn()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        return ts[len(ts) // 2], ts[0]
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()

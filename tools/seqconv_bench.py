@@ -17,19 +17,21 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 from microbench import peaks, time_ms  # noqa: E402
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=15.0)
     ap.add_argument("--alpha", type=float, default=1.0)
     ap.add_argument("--out", default=None)
-    args = ap.parse_args()
+    ap.add_argument("--device", default="cuda", help="'cpu' = dry run on the emulator backend (tests/emu_backend.py must be installed by the caller)")
+    args = ap.parse_args(argv)
     import tensorflowasr_b200 as tfasr
     from tensorflowasr_b200 import ctc_models, kernels, ops
 
     pk = peaks()
-    dev = "cuda"
-    res = {"gpu": torch.cuda.get_device_name(0), "peaks": pk}
+    dev = args.device
+    on_gpu = dev.startswith("cuda")
+    res = {"gpu": torch.cuda.get_device_name(0) if on_gpu else "cpu emulator (dry run)", "peaks": pk}
     B, T = args.batch, int(args.seconds * 100)
 
     def gbs(nbytes, ms):
@@ -89,15 +91,17 @@ def main():
         try:
             med, best = time_ms(step, iters=5, warmup=2, flush=False)
             res["encoder_step_fused" if flag else "encoder_step_library"] = {"ms": med, "ms_best": best, "utt_per_s": B / med * 1e3,
-                                                                            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+                                                                            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30 if on_gpu else None}
         except Exception as e:  # keep the other numbers if one route fails
             res["encoder_step_fused" if flag else "encoder_step_library"] = {"error": repr(e)[:300]}
-        torch.cuda.reset_peak_memory_stats()
+        if on_gpu:
+            torch.cuda.reset_peak_memory_stats()
     ops.set_fused_seq(False)
     print(json.dumps(res, indent=1))
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         json.dump(res, open(args.out, "w"), indent=1)
+    return res
 
 
 if __name__ == "__main__":
