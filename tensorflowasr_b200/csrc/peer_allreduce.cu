@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const uint
     }
   }
   __syncthreads();
+  simt_fence_sys();  // belt and braces: the acquires were made by `world` threads, the lanes are read by all of them
   // 4. sum in rank order
   const float* lanes = reinterpret_cast<const float*>(mine) + par * world * capacity;
   for (int i = tid; i < n; i += blockDim.x) {
