@@ -190,6 +190,20 @@ int tfasr_scale_mask_colsum(const void* in, const void* add, void* out, float* c
 int tfasr_glu_bwd(const void* aux, const void* dg, void* daux, float* colsum, int32_t M, int32_t D, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Macaron feed-forward module as one kernel (csrc/ffn_fused.cu; conformer.py:101-109 FFModule.call):
+ *   out = x + factor * Drop2(W2 . Drop1(swish(W1 . LN(x) + b1)) + b2)
+ * x [M, D] bf16; w1t = W1^T [H, D] bf16; w2t = W2^T [D, H] bf16; biases / LayerNorm parameters f32.  Saved for the backward (all written):
+ * xn = LN(x) [M, D] bf16, z = pre-activation [M, H] bf16, h = Drop1(swish(z)) [M, H] bf16, mean / rstd [M] f32.  The dropout masks are the
+ * counter hashes of the GEMM epilogues: hash(*seed_ptr + salt, row, col), salt1 for the hidden activation, salt2 for the output.
+ * Supported: tfasr_ffn_supported(D, H) (D = 144, H a multiple of 64); anything else returns TFASR_INVALID_VALUE.
+ * ---------------------------------------------------------------------------------------------- */
+int tfasr_ffn_supported(int32_t D, int32_t H);
+int tfasr_ffn_fwd_bf16(const void* x, const float* ln_g, const float* ln_b, const void* w1t, const float* b1, const void* w2t, const float* b2,
+                       void* out, void* xn, void* z, void* h, float* mean, float* rstd, int32_t M, int32_t D, int32_t H, float eps, float factor,
+                       float drop_p, const unsigned long long* seed_ptr, unsigned long long salt1, unsigned long long salt2,
+                       tfasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Transducer joint, training path (base_transducer.py:199-207,291): the elementwise / reduction halves around the GEMMs.
  *   joint_tanh_fwd:   h[b,t,u,:] = tanh(e[b,t,:] + p[b,u,:])         e [B,T,J], p [B,U1,J], h [B,T,U1,J]  (all bf16)
  *   joint_reduce_bwd: de[b,t,:] = sum_u dz[b,t,u,:] (written), dp[b,u,:] += sum_t dz[b,t,u,:] (accumulated; zero it first)
@@ -237,7 +251,11 @@ int tfasr_rel_attention_bwd_ld(const void* qkv, int32_t ld_qkv, const void* pos,
  *   bn_apply        : y = act(x * scale[c] + shift[c]), act 0 none / 1 swish
  *   bn_bwd_stats    : d = dy * act'(.), sums[0][c] += sum d, sums[1][c] += sum d * xhat
  *   bn_bwd_apply    : dx = scale * (d - sums[0]/count - xhat * sums[1]/count)   (count <= 0: fixed statistics, dx = scale * d)
+ *   count == TFASR_BN_COUNT_ON_DEVICE (bn_finalize, bn_bwd_apply): the row count is the float stored at sums[2 * C] — synchronized
+ *   BatchNorm over replicas whose row counts differ: every replica stores its own R there before the all-reduce of the sums, so the reduced
+ *   vector carries the global count (keras BatchNormalization(synchronized=True) reduces the count the same way).
  * ---------------------------------------------------------------------------------------------- */
+#define TFASR_BN_COUNT_ON_DEVICE (-2.0f)
 int tfasr_conv1_3x3s2_fwd(const float* x, const float* w, const float* bias, void* y, int32_t B, int32_t T, int32_t F, int32_t C,
                           tfasr_stream_t stream);
 int tfasr_conv1_3x3s2_wgrad(const float* x, const void* dy, float* dw, int32_t B, int32_t T, int32_t F, int32_t C, tfasr_stream_t stream);

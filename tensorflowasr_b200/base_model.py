@@ -177,6 +177,7 @@ class BaseModel(nn.Module):
         losses = self.compute_losses(data, training=True)
         loss = self.tfasr_compute_loss(losses)
         loss.backward()
+        fused.SIDE.join()  # weight-gradient GEMMs on the side stream (normally already joined by the end-of-backward callback)
         self._last_losses = losses.detach()
         return [p.grad for p in self.trainable_weights]
 
@@ -231,7 +232,11 @@ class BaseModel(nn.Module):
             for s, t in zip(static, flat):
                 s.copy_(t)
             sdata = schemas.TrainData(schemas.TrainInput(*static[:4]), schemas.TrainLabel(*static[4:]))
-            # warm-up on a side stream (allocator, cuDNN / cuBLAS handles, lazily built tables), then capture
+            # warm-up on a side stream (allocator, cuDNN / cuBLAS handles, lazily built tables), then capture.  The warm-up steps are
+            # real steps on the first batch: everything they change (parameters, Adam moments and step count, BatchNorm moving
+            # statistics and every other buffer, the schedule position, the dropout counter) is put back afterwards, so that a
+            # graph-mode run is step-equivalent to the eager one
+            snap = self._snapshot_train_state()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -240,6 +245,7 @@ class BaseModel(nn.Module):
                     self._train_step(sdata)
                     self._apply_gradients(lr_from_host=False)
             torch.cuda.current_stream().wait_stream(side)
+            self._restore_train_state(snap)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -255,13 +261,56 @@ class BaseModel(nn.Module):
         g["graph"].replay()
         return {"loss": g["out"]}
 
+    def _snapshot_train_state(self):
+        from . import fused
+
+        snap = {"iterations": self._iterations, "tensors": []}
+        seen = set()
+
+        def keep(t):
+            if torch.is_tensor(t) and t.data_ptr() not in seen:
+                seen.add(t.data_ptr())
+                snap["tensors"].append((t, t.detach().clone()))
+
+        opt = self.optimizer
+        if self._flat_opt:
+            for t in (opt.flat_p, opt.exp_avg, opt.exp_avg_sq, opt.step_t, self._reducer.flat):
+                keep(t)
+        else:
+            for p in self.trainable_weights:
+                keep(p.data)
+                if p.grad is not None:
+                    keep(p.grad)
+            for st in opt.state.values():
+                for v in st.values():
+                    keep(v)
+        for g in opt.param_groups:
+            keep(g["lr"])
+        for b in self.buffers():
+            keep(b)
+        if fused.STATE.seed is not None:
+            keep(fused.STATE.seed)
+        return snap
+
+    def _restore_train_state(self, snap):
+        with torch.no_grad():
+            for t, saved in snap["tensors"]:
+                t.copy_(saved)
+        self._iterations = snap["iterations"]
+
     def train_step_ga(self, data: schemas.TrainData, do_apply=None):
         """Gradient accumulation (base_model.py:200-209): gradients accumulate in .grad across calls; apply on the last one."""
-        self._train_step(data)
+        if self._reducer is not None:
+            self._reducer.defer = True  # no collective may start while later micro-batches still accumulate into the flat buffer
+        try:
+            self._train_step(data)
+        finally:
+            if self._reducer is not None:
+                self._reducer.defer = False
         if do_apply:
             if self.ga_steps > 1:
                 torch._foreach_div_([p.grad for p in self.trainable_weights if p.grad is not None], float(self.ga_steps))
-            self._apply_gradients()
+            self._apply_gradients()  # all_reduce() launches every bucket now (none was launched by the hooks) and waits
         return {"loss": self._last_losses}
 
     @torch.no_grad()

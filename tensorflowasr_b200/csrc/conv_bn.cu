@@ -248,6 +248,10 @@ __global__ void __launch_bounds__(1024) bn_bwd_stats_kernel(const __nv_bfloat16*
   for (int i = tid; i < 2 * C; i += nth) atomicAdd(sums + i, s_acc[i]);
 }
 
+// Sentinel for `count`: the row count is the float stored at sums[2 * C] (sync-BatchNorm over replicas whose row counts differ: every
+// replica puts its own R there before the all-reduce, so the reduced vector carries the global count; keras counts the same way).
+constexpr float kBnCountOnDevice = -2.0f;
+
 // backward pass 2: dx = gamma * rstd * (d - mean_d - xhat * mean_dxhat),  mean_d = sums[0]/count, mean_dxhat = sums[1]/count.
 // (inference-style BN with fixed statistics: pass count <= 0 -> dx = scale * d)
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            int C, int act) {
   const int c2n = C >> 1;
   const int64_t total = R * c2n;
+  if (count == kBnCountOnDevice) count = sums[2 * C];  // the all-reduced row count rides behind the sums
   const float inv = count > 0.f ? 1.0f / count : 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c2 = (int)(i % c2n);
@@ -303,6 +308,7 @@ struct BnVecArgs {
   int64_t R;
   int C, act, rows_per_block;
   float inv_count;
+  int count_on_device;  // MODE 3: 1 / sums_in[2 C] instead of inv_count
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -333,6 +339,11 @@ __global__ void __launch_bounds__(256) bn_vec_kernel(const BnVecArgs a) {
     __syncthreads();
   }
   float sc[8], sh[8], mu[8], rs[8], k0[8], k1[8];
+  [[maybe_unused]] float inv_count = a.inv_count;
+  if (MODE == 3 && a.count_on_device) {
+    const float n = a.sums_in[2 * C];
+    inv_count = n > 0.f ? 1.0f / n : 0.f;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cv * 8 + j;
@@ -340,8 +351,8 @@ __global__ void __launch_bounds__(256) bn_vec_kernel(const BnVecArgs a) {
     sh[j] = (MODE != 0) ? a.shift[c] : 0.f;
     mu[j] = (MODE >= 2) ? a.mean[c] : 0.f;
     rs[j] = (MODE >= 2) ? a.rstd[c] : 0.f;
-    k0[j] = (MODE == 3) ? a.sums_in[c] * a.inv_count : 0.f;
-    k1[j] = (MODE == 3) ? a.sums_in[C + c] * a.inv_count : 0.f;
+    k0[j] = (MODE == 3) ? a.sums_in[c] * inv_count : 0.f;
+    k1[j] = (MODE == 3) ? a.sums_in[C + c] * inv_count : 0.f;
   }
   float s0[8], s1[8];
 #pragma unroll
@@ -435,6 +446,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
                                    float eps, float momentum) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (count == kBnCountOnDevice) count = sums[2 * C];
   const float mean = sums[c] / count;
   const float var = fmaxf(sums[C + c] / count - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
@@ -619,6 +631,7 @@ extern "C" int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* sc
     a.rstd = rstd;
     a.sums_in = sums;
     a.inv_count = count > 0.f ? 1.0f / count : 0.f;
+    a.count_on_device = (count == kBnCountOnDevice) ? 1 : 0;
     a.R = R;
     a.C = C;
     a.act = act;
@@ -635,7 +648,7 @@ extern "C" int tfasr_bn_bwd_apply(const void* dy, const void* x, const float* sc
 
 extern "C" int tfasr_bn_finalize(const float* sums, const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* out,
                                  int32_t C, float count, float eps, float momentum, tfasr_stream_t stream) {
-  if (!sums || !gamma || !beta || !out || C < 1 || !(count > 0.f)) return TFASR_INVALID_VALUE;
+  if (!sums || !gamma || !beta || !out || C < 1 || !(count > 0.f || count == kBnCountOnDevice)) return TFASR_INVALID_VALUE;
   bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, gamma, beta, moving_mean, moving_var, out, C, count,
                                                                                                   eps, momentum);
   count_launch();

@@ -10,6 +10,7 @@
 //
 // Roofline: HBM-bound, algorithmic bytes = 8*B*T*V (read logits + write grads).
 #include "common.cuh"
+#include "lattice_lens.cuh"
 
 namespace tfasr {
 
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(kCtcRowWarps * 32) ctc_lse_kernel(const float*
   const int64_t row = (int64_t)blockIdx.x * kCtcRowWarps + (threadIdx.x >> 5);
   if (row >= (int64_t)B * T) return;
   const int t = (int)(row % T), b = (int)(row / T);
-  if (t >= logit_len[b]) return;
+  if (t >= min(logit_len[b], T)) return;  // a length beyond the tensor: the utterance is infeasible (lattice_lens.cuh), rows stay in bounds
   const float* x = logits + row * V;
   float m = -CUDART_INF_F;
   for (int j = lane; j < V; j += 32) m = fmaxf(m, x[j]);
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(1024) ctc_lattice_kernel(const float* __restri
   const bool is_beta = blockIdx.y == 1;
   const int s = threadIdx.x;
   const int Smax = 2 * L + 1;
-  const int Tb = logit_len[b], Lb = label_len[b];
+  int Tb, Lb;
+  lattice_lens(logit_len, label_len, b, T, L, Tb, Lb);
   const int S = 2 * Lb + 1;
   const int stride = blockDim.x + 4;
   float* buf0 = s_row + 2;
@@ -142,7 +144,8 @@ __global__ void __launch_bounds__(kCtcRowWarps * 32) ctc_grad_kernel(const float
   const int64_t row = (int64_t)blockIdx.x * kCtcRowWarps + w;
   if (row >= (int64_t)B * T) return;
   const int t = (int)(row % T), b = (int)(row / T);
-  const int Tb = logit_len[b], Lb = label_len[b];
+  int Tb, Lb;
+  lattice_lens(logit_len, label_len, b, T, L, Tb, Lb);
   const float* x = logits + row * V;
   float* g = grads + row * V;
   const float cost = costs[b];

@@ -1,0 +1,423 @@
+// Macaron feed-forward module of the Conformer block as ONE kernel per direction (tensorflow_asr/models/encoders/conformer.py:101-109
+// FFModule.call:  out = x + factor * Drop(W2 . Drop(swish(W1 . LN(x) + b1)) + b2)).
+//
+// Why: at d_model = 144 a Dense layer per launch is latency, not work (round 1: LayerNorm + 2 GEMM launches = 33 us forward for 2.65 GFLOP,
+// i.e. ~2 us of tensor time).  Here one CTA owns a 128-row tile for the whole module:
+//   TMA   x tile [128 x D] -> SMEM in the UMMA K-major 128B-swizzle layout
+//   LN    128 threads (one row each) normalise the tile IN PLACE in SMEM (two-pass, fp32) -> the A operand; xn also leaves through a TMA
+//         store (the weight-gradient GEMM of the backward wants it)
+//   loop over the hidden dimension in chunks of 64:
+//     G1  tcgen05.mma 128 x 64 x 16 (x9):   acc1[c & 1] (TMEM, 64 columns) = xn . W1[:, chunk]
+//     E1  8 epilogue warps: tcgen05.ld -> + b1 -> z (saved pre-activation) -> swish -> dropout -> bf16 h chunk: written to global (saved for the
+//         backward) AND into SMEM as the next A operand — the [128 x 576] hidden activation never makes the HBM round trip before GEMM 2
+//     G2  tcgen05.mma 128 x D x 16 (x4):    acc2 (TMEM, D columns) += h_chunk . W2[chunk, :]
+//   E2    acc2 -> + b2 -> dropout -> x + factor * (.) -> bf16 out
+// Weight chunks (W1^T rows [64 x D], W2^T columns [D x 64]: 42 KB per chunk) stream through a 3-stage TMA ring from L2, where the 332 KB of
+// module weights stay resident.  G1 of chunk c+1 overlaps E1 of chunk c (double-buffered acc1 and h).
+//
+// Roofline: tensor pipe; per tile 2 * 128 * D * H * 2 flop = 42.5 MFLOP at D = 144, H = 576 -> 2.7 us at the per-SM bf16 rate; M = 8000 gives
+// 63 tiles on 148 SMs, so the module's floor is one tile time.  See DESIGN.md section 4.
+#include "gemm_kernel.cuh"
+
+namespace tfasr {
+
+constexpr int kFfnThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue / LayerNorm
+constexpr int kHC = 64;           // hidden-dimension chunk = one 128B-swizzle atom of K for GEMM 2
+
+template <int D>
+struct FfnSmem {
+  static_assert(D % 16 == 0 && D <= 192, "model dimension: multiple of 16, at most three swizzle atoms");
+  static constexpr int KA = (D + 63) / 64;                 // K atoms of the model dimension
+  static constexpr int A_BYTES = KA * 128 * 128;           // [128 rows x KA atoms x 128 B]
+  static constexpr int H_BYTES = 128 * 128;                // one atom [128 x 64]
+  static constexpr int W1_BYTES = KA * kHC * 128;          // W1^T chunk: [64 hidden rows x D k]
+  static constexpr int W2_BYTES = ((D * 128 + 1023) / 1024) * 1024;  // W2^T chunk: [D rows x 64 k]
+  static constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int BAR_BYTES = 32 * 8;
+  static constexpr int TOTAL = A_BYTES + 2 * H_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static_assert(TOTAL <= 227 * 1024, "smem budget");
+  static constexpr uint32_t TMEM_COLS = 512;               // acc1 x2 (64 columns each) + acc2 (D columns)
+  static constexpr uint32_t ACC2_COL = 2 * kHC;
+};
+
+struct FfnFwdArgs {
+  const __nv_bfloat16* x;   // [M, D] module input (also the residual)
+  const float *ln_g, *ln_b;  // [D]
+  const float *b1, *b2;      // [H], [D]
+  __nv_bfloat16* out;        // [M, D]
+  __nv_bfloat16* z;          // [M, H] pre-activation (saved for the backward)
+  __nv_bfloat16* h;          // [M, H] Drop(swish(z)) (saved: A operand of the W2 weight gradient)
+  float *mean, *rstd;        // [M]
+  int M, H;
+  float eps, factor, drop_p;
+  const unsigned long long* seed_ptr;
+  unsigned long long salt1, salt2;
+};
+
+// 16-byte chunk j of row r inside a K-major SWIZZLE_128B tile whose atoms are [128 rows x 128 B]
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk) { return (uint32_t)(chunk >> 3) * (128 * 128) + row * 128 + (((chunk & 7) ^ (row & 7)) << 4); }
+
+template <int D>
+__global__ void __launch_bounds__(kFfnThreads, 1)
+ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+               const __grid_constant__ CUtensorMap tmXn, const FfnFwdArgs a) {
+  using S = FfnSmem<D>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = sm100::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem;                       // x tile -> LN(x), K-major swizzled
+  uint8_t* sH = sA + S::A_BYTES;            // [2][128 x 64] hidden chunk
+  uint8_t* sW = sH + 2 * S::H_BYTES;        // [STAGES][W1 chunk | W2 chunk]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + S::STAGES * S::STAGE_BYTES);
+  uint64_t* x_full = bars + 0;
+  uint64_t* a_ready = bars + 1;
+  uint64_t* a_free = bars + 2;
+  uint64_t* acc2_full = bars + 3;
+  uint64_t* acc2_empty = bars + 4;
+  uint64_t* w_full = bars + 5;             // [STAGES]
+  uint64_t* w_empty = w_full + S::STAGES;  // [STAGES]
+  uint64_t* acc1_full = w_empty + S::STAGES;  // [2]
+  uint64_t* acc1_empty = acc1_full + 2;       // [2]
+  uint64_t* h_full = acc1_empty + 2;          // [2]
+  uint64_t* h_empty = h_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = a.M, H = a.H;
+  const int num_tiles = (M + 127) / 128, nch = H / kHC;
+
+  if (warp == 0 && lane == 0) {
+    sm100::prefetch_tensormap(&tmX);
+    sm100::prefetch_tensormap(&tmW1);
+    sm100::prefetch_tensormap(&tmW2);
+    sm100::prefetch_tensormap(&tmXn);
+    sm100::mbar_init(x_full, 1);
+    sm100::mbar_init(a_ready, 1);
+    sm100::mbar_init(a_free, 2);  // the MMA warp (all G1 done) + the xn TMA store (source read)
+    sm100::mbar_init(acc2_full, 1);
+    sm100::mbar_init(acc2_empty, 8);
+    for (int s = 0; s < S::STAGES; ++s) {
+      sm100::mbar_init(&w_full[s], 1);
+      sm100::mbar_init(&w_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      sm100::mbar_init(&acc1_full[i], 1);
+      sm100::mbar_init(&acc1_empty[i], 8);
+      sm100::mbar_init(&h_full[i], 8);
+      sm100::mbar_init(&h_empty[i], 1);
+    }
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc(tmem_slot, S::TMEM_COLS);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        sm100::mbar_wait(a_free, (ti & 1) ^ 1);
+        sm100::mbar_arrive_expect_tx(x_full, S::A_BYTES);
+#pragma unroll
+        for (int ka = 0; ka < S::KA; ++ka) sm100::tma_load_2d(sA + ka * 16384, &tmX, x_full, ka * 64, tile * 128);
+        for (int c = 0; c < nch; ++c, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (it / S::STAGES) & 1;
+          sm100::mbar_wait(&w_empty[s], ph ^ 1);
+          sm100::mbar_arrive_expect_tx(&w_full[s], S::W1_BYTES + D * 128);
+          uint8_t* w1 = sW + s * S::STAGE_BYTES;
+#pragma unroll
+          for (int ka = 0; ka < S::KA; ++ka) sm100::tma_load_2d(w1 + ka * (kHC * 128), &tmW1, &w_full[s], ka * 64, c * kHC);  // [64 rows x 64 k]
+          sm100::tma_load_2d(w1 + S::W1_BYTES, &tmW2, &w_full[s], c * kHC, 0);                                                   // [D rows x 64 k]
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = sm100::make_idesc_bf16_f32(128, kHC, 0, 0);
+      constexpr uint32_t idesc2 = sm100::make_idesc_bf16_f32(128, D, 0, 0);
+      const uint32_t a0 = sm100::smem_u32(sA);
+      uint32_t it = 0, ti = 0;  // `it` counts hidden chunks across tiles: weight stage it % STAGES, acc1 / h buffer it & 1
+      auto gemm2 = [&](uint32_t itc, int c) {  // acc2 += h[chunk c] . W2[chunk c, :]
+        const uint32_t b = itc & 1, bph = (itc >> 1) & 1, s = itc % S::STAGES;
+        sm100::mbar_wait(&h_full[b], bph);
+        if (c == 0) sm100::mbar_wait(acc2_empty, (ti & 1) ^ 1);  // the previous tile's output epilogue has drained acc2
+        sm100::tc_fence_after();
+        const uint32_t h0 = sm100::smem_u32(sH + b * S::H_BYTES);
+        const uint32_t w2 = sm100::smem_u32(sW + s * S::STAGE_BYTES + S::W1_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < kHC / 16; ++kk)
+          sm100::umma_bf16(tmem_base + S::ACC2_COL, sm100::make_smem_desc(h0 + kk * 32, 16, 1024), sm100::make_smem_desc(w2 + kk * 32, 16, 1024), idesc2,
+                           (c | kk) != 0 ? 1u : 0u);
+        sm100::umma_commit(&h_empty[b]);
+        sm100::umma_commit(&w_empty[s]);
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        sm100::mbar_wait(a_ready, ti & 1);
+        sm100::tc_fence_after();
+        for (int c = 0; c < nch; ++c, ++it) {
+          const uint32_t s = it % S::STAGES, ph = (it / S::STAGES) & 1, b = it & 1, bph = (it >> 1) & 1;
+          sm100::mbar_wait(&w_full[s], ph);
+          sm100::mbar_wait(&acc1_empty[b], bph ^ 1);
+          sm100::tc_fence_after();
+          const uint32_t w1 = sm100::smem_u32(sW + s * S::STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const int ka = ks >> 2, kk = ks & 3;
+            sm100::umma_bf16(tmem_base + b * kHC, sm100::make_smem_desc(a0 + ka * 16384 + kk * 32, 16, 1024),
+                             sm100::make_smem_desc(w1 + ka * (kHC * 128) + kk * 32, 16, 1024), idesc1, ks != 0 ? 1u : 0u);
+          }
+          sm100::umma_commit(&acc1_full[b]);
+          if (c > 0) gemm2(it - 1, c - 1);
+        }
+        gemm2(it - 1, nch - 1);
+        sm100::umma_commit(acc2_full);
+        sm100::umma_commit(a_free);  // every G1 of this tile has read sA
+      }
+    }
+  } else {
+    // ===================================================================== LayerNorm + epilogues (warps 2..9)
+    const int q = warp & 3;   // TMEM lane quarter of this warp
+    const int ew = warp - 2;  // 0..7
+    const int half = ew >> 2;
+    const bool has_drop = a.drop_p > 0.f;
+    const float keep_scale = has_drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+    const uint32_t drop_thr = dropout_threshold(a.drop_p);
+    const unsigned long long seed0 = (has_drop && a.seed_ptr) ? *a.seed_ptr : 0ull;
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      const int row_in_tile = q * 32 + lane;
+      const int row = tile * 128 + row_in_tile;
+      const bool row_ok = row < M;
+      if (ew < 4) {
+        // ---- LayerNorm of this thread's row, in place in the swizzled tile (keras LayerNormalization: biased variance, eps inside the sqrt)
+        sm100::mbar_wait(x_full, ti & 1);
+        uint4 pk[D / 8];
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) pk[j] = *reinterpret_cast<const uint4*>(sA + swz_off(row_in_tile, j));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) {
+          const uint32_t w[4] = {pk[j].x, pk[j].y, pk[j].z, pk[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sum += __uint_as_float(w[e] << 16) + __uint_as_float(w[e] & 0xFFFF0000u);
+        }
+        const float mean = sum * (1.0f / D);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) {
+          const uint32_t w[4] = {pk[j].x, pk[j].y, pk[j].z, pk[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float d0 = __uint_as_float(w[e] << 16) - mean, d1 = __uint_as_float(w[e] & 0xFFFF0000u) - mean;
+            sq = fmaf(d0, d0, sq);
+            sq = fmaf(d1, d1, sq);
+          }
+        }
+        const float rstd = rsqrtf(sq * (1.0f / D) + a.eps);
+        if (row_ok) {
+          a.mean[row] = mean;
+          a.rstd[row] = rstd;
+        }
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.ln_g + 8 * j)), g1 = __ldg(reinterpret_cast<const float4*>(a.ln_g + 8 * j + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.ln_b + 8 * j)), b1v = __ldg(reinterpret_cast<const float4*>(a.ln_b + 8 * j + 4));
+          const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
+          const uint32_t w[4] = {pk[j].x, pk[j].y, pk[j].z, pk[j].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = (__uint_as_float(w[e] << 16) - mean) * rstd * g[2 * e] + bb[2 * e];
+            const float v1 = (__uint_as_float(w[e] & 0xFFFF0000u) - mean) * rstd * g[2 * e + 1] + bb[2 * e + 1];
+            o[e] = pack2(v0, v1);
+          }
+          *reinterpret_cast<uint4*>(sA + swz_off(row_in_tile, j)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        sm100::fence_proxy_async();  // generic-proxy writes of the A operand -> visible to tcgen05.mma / TMA (async proxy)
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (ew == 0 && lane == 0) {
+          sm100::mbar_arrive(a_ready);
+          // xn leaves for the backward's weight-gradient GEMM (rows / columns beyond the tensor are clipped by the hardware)
+#pragma unroll
+          for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tmXn, sA + ka * 16384, ka * 64, tile * 128);
+          sm100::tma_store_commit();
+          sm100::tma_store_wait_read<0>();
+          sm100::mbar_arrive(a_free);
+        }
+        __syncwarp();
+      }
+      // ---- hidden chunks: acc1 -> z, h
+      [[maybe_unused]] const uint32_t rowkey1 = has_drop ? dropout_rowkey(seed0 + a.salt1, (unsigned long long)row) : 0u;
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < nch; ++c, ++it) {
+        const uint32_t b = it & 1, bph = (it >> 1) & 1;
+        sm100::mbar_wait(&acc1_full[b], bph);
+        sm100::tc_fence_after();
+        uint32_t r[2][16];
+        sm100::tmem_ld_32x32b_x16(tmem_row + b * kHC + half * 32, r[0]);
+        sm100::tmem_ld_32x32b_x16(tmem_row + b * kHC + half * 32 + 16, r[1]);
+        sm100::tmem_ld_wait();
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&acc1_empty[b]);  // acc1[b] may take chunk c + 2
+        const int col0 = c * kHC + half * 32;               // first hidden column of this thread's 32
+        uint32_t zp[16], hp[16];
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b1 + col0 + ci * 16 + 4 * j));
+            v[4 * j] = __uint_as_float(r[ci][4 * j]) + b4.x;
+            v[4 * j + 1] = __uint_as_float(r[ci][4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(r[ci][4 * j + 2]) + b4.z;
+            v[4 * j + 3] = __uint_as_float(r[ci][4 * j + 3]) + b4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zp[ci * 8 + j] = pack2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float s0, s1;
+            sigmoid2_(v[j], v[j + 1], s0, s1);
+            v[j] *= s0;
+            v[j + 1] *= s1;
+          }
+          if (has_drop) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const uint32_t hsh = dropout_hash(rowkey1, (uint32_t)(col0 + ci * 16 + j));
+              v[j] = ((hsh & 0xFFFFu) >= drop_thr) ? v[j] * keep_scale : 0.f;
+              v[j + 1] = ((hsh >> 16) >= drop_thr) ? v[j + 1] * keep_scale : 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hp[ci * 8 + j] = pack2(v[2 * j], v[2 * j + 1]);
+        }
+        if (row_ok) {
+          uint4* zg = reinterpret_cast<uint4*>(a.z + (size_t)row * H + col0);
+          uint4* hg = reinterpret_cast<uint4*>(a.h + (size_t)row * H + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            zg[j] = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
+            hg[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+          }
+        }
+        sm100::mbar_wait(&h_empty[b], bph ^ 1);  // GEMM 2 of chunk c - 2 has read this buffer
+        uint8_t* hb = sH + b * S::H_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(hb + swz_off(row_in_tile, half * 4 + j)) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+        sm100::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&h_full[b]);
+      }
+      // ---- output: acc2 -> + b2 -> dropout -> residual
+      [[maybe_unused]] const uint32_t rowkey2 = has_drop ? dropout_rowkey(seed0 + a.salt2, (unsigned long long)row) : 0u;
+      sm100::mbar_wait(acc2_full, ti & 1);
+      sm100::tc_fence_after();
+      constexpr int NG = D / 16, G_MID = (NG + 1) / 2;
+      const int g0 = half ? G_MID : 0, g1 = half ? NG : G_MID;
+      for (int g = g0; g < g1; ++g) {
+        uint32_t r[16];
+        sm100::tmem_ld_32x32b_x16(tmem_row + S::ACC2_COL + g * 16, r);
+        sm100::tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b2 + g * 16 + 4 * j));
+          v[4 * j] = __uint_as_float(r[4 * j]) + b4.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+        }
+        if (has_drop) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const uint32_t hsh = dropout_hash(rowkey2, (uint32_t)(g * 16 + j));
+            v[j] = ((hsh & 0xFFFFu) >= drop_thr) ? v[j] * keep_scale : 0.f;
+            v[j + 1] = ((hsh >> 16) >= drop_thr) ? v[j + 1] * keep_scale : 0.f;
+          }
+        }
+        if (row_ok) {
+          float xr[16];
+          load16(a.x + (size_t)row * D + g * 16, xr);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = xr[j] + a.factor * v[j];
+          store16(a.out + (size_t)row * D + g * 16, v);
+        }
+      }
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(acc2_empty);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
+template <int D>
+static int launch_ffn_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmXn, const FfnFwdArgs& a,
+                          cudaStream_t stream) {
+  using S = FfnSmem<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(ffn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return TFASR_EXECUTION_FAILED;
+    attr_set = true;
+  }
+  const int tiles = (a.M + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  ffn_fwd_kernel<D><<<grid, kFfnThreads, S::TOTAL, stream>>>(tmX, tmW1, tmW2, tmXn, a);
+  count_launch();
+  return check_launch();
+}
+
+}  // namespace tfasr
+
+using namespace tfasr;
+
+extern "C" int tfasr_ffn_supported(int32_t D, int32_t H) { return (D == 144 && H >= 64 && H % 64 == 0) ? 1 : 0; }
+
+extern "C" int tfasr_ffn_fwd_bf16(const void* x, const float* ln_g, const float* ln_b, const void* w1t, const float* b1, const void* w2t,
+                                  const float* b2, void* out, void* xn, void* z, void* h, float* mean, float* rstd, int32_t M, int32_t D, int32_t H,
+                                  float eps, float factor, float drop_p, const unsigned long long* seed_ptr, unsigned long long salt1,
+                                  unsigned long long salt2, tfasr_stream_t stream) {
+  if (!x || !ln_g || !ln_b || !w1t || !b1 || !w2t || !b2 || !out || !xn || !z || !h || !mean || !rstd || M < 0) return TFASR_INVALID_VALUE;
+  if (!tfasr_ffn_supported(D, H) || !(drop_p >= 0.f && drop_p < 1.f)) return TFASR_INVALID_VALUE;
+  if (M == 0) return TFASR_OK;
+  CUtensorMap tmX, tmW1, tmW2, tmXn;
+  bool ok = make_tmap_bf16_2d(&tmX, x, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
+  ok = ok && make_tmap_bf16_2d(&tmW1, w1t, (uint64_t)H, (uint64_t)D, (uint64_t)D, kHC, 64);  // W1^T [H, D]: rows = hidden units, K = D
+  ok = ok && make_tmap_bf16_2d(&tmW2, w2t, (uint64_t)D, (uint64_t)H, (uint64_t)H, (uint32_t)D, 64);  // W2^T [D, H]: rows = outputs, K = hidden
+  ok = ok && make_tmap_bf16_2d(&tmXn, xn, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
+  if (!ok) return TFASR_INVALID_VALUE;
+  FfnFwdArgs a{};
+  a.x = static_cast<const __nv_bfloat16*>(x);
+  a.ln_g = ln_g;
+  a.ln_b = ln_b;
+  a.b1 = b1;
+  a.b2 = b2;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.z = static_cast<__nv_bfloat16*>(z);
+  a.h = static_cast<__nv_bfloat16*>(h);
+  a.mean = mean;
+  a.rstd = rstd;
+  a.M = M;
+  a.H = H;
+  a.eps = eps;
+  a.factor = factor;
+  a.drop_p = drop_p;
+  a.seed_ptr = seed_ptr;
+  a.salt1 = salt1;
+  a.salt2 = salt2;
+  return launch_ffn_fwd<144>(tmX, tmW1, tmW2, tmXn, a, static_cast<cudaStream_t>(stream));
+}

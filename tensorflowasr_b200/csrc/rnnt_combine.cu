@@ -5,6 +5,7 @@
 //   blank[row] = logits[row, 0] - lse;   truth[row] = logits[row, labels[b, u]] - lse  (u < U_b; -inf on the last column, :216-231)
 // Plain SIMT: builds twice (nvcc -> libtfasr_b200.so; g++ -DTFASR_EMU_BUILD -> tests/emu, host pointers).
 #include "simt.cuh"
+#include "lattice_lens.cuh"
 
 #ifdef TFASR_EMU_BUILD
 #include "../../include/tfasr_b200.h"
@@ -22,7 +23,8 @@ __global__ void __launch_bounds__(256) rnnt_lse_combine_kernel(const float* __re
     const int u = (int)(row % U1);
     const int t = (int)((row / U1) % T);
     const int b = (int)(row / ((int64_t)U1 * T));
-    const int Tb = logit_len[b], Ub = label_len[b];
+    int Tb, Ub;
+  lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
     if (t >= Tb || u > Ub) continue;  // rows outside the lattice are never read
     const float2* rp = rowstats + (size_t)row * P;
     float m = -CUDART_INF_F;

@@ -12,6 +12,7 @@
 //     and are reduced once per CTA.
 // HBM-bound byte work (12 B per lattice node and vocabulary entry incl. the second read); no tensor cores.  Plain SIMT: builds twice.
 #include "simt.cuh"
+#include "lattice_lens.cuh"
 
 #ifdef TFASR_EMU_BUILD
 #include "../../include/tfasr_b200.h"
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_v2_kernel(con
     const int u = (int)(row % U1);
     const int t = (int)((row / U1) % T);
     const int b = (int)(row / ((int64_t)U1 * T));
-    const int Tb = logit_len[b], Ub = label_len[b];
+    int Tb, Ub;
+  lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
     uint2* g2 = reinterpret_cast<uint2*>(grads + row * ld_g);
     if (!((t < Tb) && (u <= Ub))) {
       for (int j = lane; j < n4; j += 32) g2[j] = make_uint2(0u, 0u);

@@ -14,6 +14,7 @@
 // Roofline: HBM-bound.  Algorithmic bytes = 8*B*T*U1*V (read logits once + write grads once); practical floor with the
 // unavoidable second read = 12*B*T*U1*V.  No tensor cores: the lattice is a log-space scan, not a contraction.
 #include "common.cuh"
+#include "lattice_lens.cuh"
 
 namespace tfasr {
 
@@ -51,7 +52,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_lse_kernel(const float* _
   const int u = (int)(row % U1);
   const int t = (int)((row / U1) % T);
   const int b = (int)(row / ((int64_t)U1 * T));
-  const int Tb = logit_len[b], Ub = label_len[b];
+  int Tb, Ub;
+  lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
   if (t >= Tb || u > Ub) return;  // rows outside the lattice are never read (ragged batches cost nothing)
   const float* x = logits + row * V;
   float m = -CUDART_INF_F, s = 0.f;
@@ -97,7 +99,8 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(const int32_t* __res
   const bool is_beta = blockIdx.y == 1;
   const int i = threadIdx.x;
   const int lane = i & 31, warp = i >> 5;
-  const int Tb = logit_len[b], Ub = label_len[b];
+  int Tb, Ub;
+  lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
   __shared__ float s_edge[2][32];  // [step parity][warp]: emit value leaving the last lane of each warp
   if (Tb <= 0) {                    // empty utterance: no alignment exists
     if (is_beta && i == 0) costs[b] = CUDART_INF_F;
@@ -179,7 +182,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_grad_kernel(const float* 
   const int u = (int)(row % U1);
   const int t = (int)((row / U1) % T);
   const int b = (int)(row / ((int64_t)U1 * T));
-  const int Tb = logit_len[b], Ub = label_len[b];
+  int Tb, Ub;
+  lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
   const float* x = logits + row * V;
   float* g = grads + row * V;
   const bool valid = (t < Tb) && (u <= Ub);
@@ -286,7 +290,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) rnnt_grad_bf16_kernel(const fl
     const int u = (int)(row % U1);
     const int t = (int)((row / U1) % T);
     const int b = (int)(row / ((int64_t)U1 * T));
-    const int Tb = logit_len[b], Ub = label_len[b];
+    int Tb, Ub;
+  lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
     uint2* g2 = reinterpret_cast<uint2*>(grads + row * ld_g);
     if (!((t < Tb) && (u <= Ub))) {
 #pragma unroll

@@ -92,12 +92,17 @@ class GradientReducer:
         self._works = []
         self._launched = [False] * len(self.buckets)
         self.overlap = overlap and world_size() > 1
+        # gradient accumulation: micro-steps must not start collectives on buffers later micro-batches still accumulate into;
+        # `defer` switches the overlap hooks off, the one all_reduce() of the apply step then reduces every bucket
+        self.defer = False
         if self.overlap:
             for i, p in enumerate(self.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
 
     def _make_hook(self, i):
         def hook(param):
+            if self.defer:
+                return
             b = self._bucket_of[i]
             self._pending[b] -= 1
             if self._pending[b] == 0:

@@ -33,6 +33,65 @@ class StepState:
 STATE = StepState()
 
 
+class SideStream:
+    """Weight-gradient GEMMs (and other work nobody on the backward chain waits for) run on a second stream: inside the captured step graph
+    that makes them parallel branches, so the activation-gradient chain — ~1000 dependent, latency-bound launches — no longer queues behind
+    them.  `run(fn, *tensors)` orders the side stream after everything issued so far, calls fn on it and keeps `tensors` (fn's inputs) alive
+    until `join()`, which the end of every backward pass performs (autograd engine callback) and which UnpackPlan.run / BaseModel call before
+    they touch the gradients."""
+
+    def __init__(self):
+        import os
+
+        self.enabled = os.environ.get("TFASR_SIDE_WGRAD", "1") == "1"
+        self.stream = None
+        self.keep = []
+        self.dirty = False
+        self._queued = False
+
+    def active(self, t) -> bool:
+        from . import _lib
+
+        return self.enabled and t.is_cuda and not _lib.EMULATED and not _lib.TIMERS.on
+
+    def run(self, fn, *tensors):
+        if not tensors or not self.active(tensors[0]):
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        if self.stream is None or self.stream.device != tensors[0].device:
+            self.stream = torch.cuda.Stream(device=tensors[0].device)
+        self.stream.wait_stream(main)
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(tensors)
+        self.dirty = True
+        if not self._queued:
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(self._end_of_backward)
+                self._queued = True
+            except RuntimeError:  # not inside a backward pass: the caller joins
+                pass
+
+    def _end_of_backward(self):
+        self._queued = False
+        self.join()
+
+    def join(self):
+        if self.dirty:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.keep.clear()
+            self.dirty = False
+
+
+SIDE = SideStream()
+
+
+def _wgrad(x, dz, out, k_splits):
+    """out (fp32, a parameter's gradient or a packed gradient buffer) += x^T dz on the side stream."""
+    SIDE.run(lambda: kernels.gemm(x, dz, mn_major=True, out=out, accumulate=True, k_splits=k_splits), x, dz, out)
+
+
 def _grad(p: torch.Tensor) -> torch.Tensor:
     """fp32 gradient buffer of a parameter (allocated zeroed on first use; kernels accumulate into it)."""
     if p.grad is None:
@@ -107,6 +166,7 @@ class UnpackPlan:
         self.run()
 
     def run(self):
+        SIDE.join()  # the packed buffers are written by weight-gradient GEMMs on the side stream
         if not self.entries:
             return
         import numpy as np
@@ -167,7 +227,7 @@ class WeightPack:
         return None if self.bias is None else _grad(self.bias).view(-1)
 
     def accumulate_wgrad(self, x, dz):
-        kernels.gemm(x, dz, mn_major=True, out=_grad(self.param).view(self.w.shape), accumulate=True, k_splits=_splits(x.shape[0]))
+        _wgrad(x, dz, _grad(self.param).view(self.w.shape), _splits(x.shape[0]))
 
 
 def _splits(rows: int) -> int:
@@ -182,12 +242,19 @@ class _FFModuleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ln_g, ln_b, p1: WeightPack, p2: WeightPack, factor, drop_p, salt, seed):
         M, D = x.shape
-        a, mean, rstd = kernels.layernorm_fwd(x, ln_g, ln_b, LN_EPS)
         H = p1.wt.shape[0]
-        z = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
-        h = kernels.gemm(a, p1.wt, bias=p1.bias, activation="swish", aux=z, dropout_p=drop_p, dropout_seed=seed, dropout_salt=salt)
-        out = kernels.gemm(h, p2.wt, bias=p2.bias, residual=x, residual_scale=factor, dropout_p=drop_p, dropout_seed=seed,
-                           dropout_salt=salt + 1)
+        from . import ops
+
+        if ops.fused_ffn_active() and kernels.ffn_supported(D, H) and p1.bias is not None and p2.bias is not None:
+            # the whole module in one launch: LN in the A-operand prologue, the hidden activation handed from GEMM 1 to GEMM 2 through SMEM
+            out, a, z, h, mean, rstd = kernels.ffn_fwd(x, ln_g.detach(), ln_b.detach(), p1.wt, p1.bias.detach(), p2.wt, p2.bias.detach(), factor, drop_p,
+                                                       seed, salt, salt + 1, LN_EPS)
+        else:
+            a, mean, rstd = kernels.layernorm_fwd(x, ln_g, ln_b, LN_EPS)
+            z = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
+            h = kernels.gemm(a, p1.wt, bias=p1.bias, activation="swish", aux=z, dropout_p=drop_p, dropout_seed=seed, dropout_salt=salt)
+            out = kernels.gemm(h, p2.wt, bias=p2.bias, residual=x, residual_scale=factor, dropout_p=drop_p, dropout_seed=seed,
+                               dropout_salt=salt + 1)
         ctx.save_for_backward(x, mean, rstd, a, z, h)
         ctx.misc = (ln_g, ln_b, p1, p2, factor, drop_p, salt, seed)
         return out
@@ -201,11 +268,11 @@ class _FFModuleFn(torch.autograd.Function):
         ks = _splits(M)
         # d(out)/d(y): residual factor and the second dropout; bias-2 gradient = column sums
         dy = kernels.scale_mask_colsum(dout, scale=factor, dropout_p=drop_p, seed=seed, salt=salt + 1, colsum=_grad(p2.bias))
-        kernels.gemm(h, dy, mn_major=True, out=_grad(p2.param), accumulate=True, k_splits=ks)  # dW2 += h^T dy
+        _wgrad(h, dy, _grad(p2.param), ks)  # dW2 += h^T dy
         # dz = (dy W2^T) * dropout1 * swish'(z); bias-1 gradient = column sums (fused in the epilogue)
         dz = kernels.gemm(dy, p2.w, mul=z, mul_mode="swish_grad", dropout_p=drop_p, dropout_seed=seed, dropout_salt=salt,
                           colsum=_grad(p1.bias))
-        kernels.gemm(a, dz, mn_major=True, out=_grad(p1.param), accumulate=True, k_splits=ks)  # dW1 += a^T dz
+        _wgrad(a, dz, _grad(p1.param), ks)  # dW1 += a^T dz
         da = kernels.gemm(dz, p1.w)
         dx = kernels.layernorm_bwd(da, x, mean, rstd, ln_g, _grad(ln_g), _grad(ln_b), dres=dout)
         return dx, None, None, None, None, None, None, None, None
@@ -313,11 +380,11 @@ class _LstmFn(torch.autograd.Function):
         dg = kernels.lstm_rec_bwd(dy.to(torch.bfloat16).contiguous(), (saved_g, saved_c), whh, length).view(B * U, 4 * R)
         kernels.colsum(dg, _grad(bias).view(-1))
         ks = _splits(B * U)
-        kernels.gemm(x2, dg, mn_major=True, out=_grad(kernel).view(E, 4 * R), accumulate=True, k_splits=ks)  # dW_ih += x^T dgates
+        _wgrad(x2, dg, _grad(kernel).view(E, 4 * R), ks)  # dW_ih += x^T dgates
         # h_{t-1}: the outputs shifted by one label step (masked steps carry zero gate gradients, so their zeros are harmless)
         hprev = torch.zeros_like(y)
         hprev[:, 1:] = y[:, :-1]
-        kernels.gemm(hprev.view(B * U, R), dg, mn_major=True, out=_grad(recurrent_kernel).view(R, 4 * R), accumulate=True, k_splits=ks)
+        _wgrad(hprev.view(B * U, R), dg, _grad(recurrent_kernel).view(R, 4 * R), ks)
         dx = kernels.gemm(dg, pack.w).view(B, U, E) if need_dx else None
         return dx, None, None, None, None
 
@@ -397,7 +464,7 @@ class _TransducerHeadFn(torch.autograd.Function):
         with _lib.TIMERS.region("joint_gemm_dgrad"):
             dz = kernels.gemm(dlv, pack.w, mul=h2, mul_mode="tanh_grad")  # [M, J]
         with _lib.TIMERS.region("joint_gemm_wgrad"):
-            kernels.gemm(h2, dlv, mn_major=True, out=_grad(pack.param), accumulate=True, k_splits=32)  # dWv [J, V]
+            _wgrad(h2, dlv, _grad(pack.param), 32)  # dWv [J, V]  (the timers switch the side stream off: the region then times the GEMM)
         de, dp = kernels.joint_reduce_bwd(dz.view(B, T, U1, J))
         return de.to(de_dtype), dp.to(dp_dtype), None, None, None, None
 
@@ -421,11 +488,13 @@ def bn_train_fwd(x2d, gamma, beta, moving_mean, moving_var, act=1):
     """Training-mode keras BatchNormalization(synchronized=True) (+ swish) on x2d [R, C] bf16.
     Returns (y, saved) where saved = (scale, shift, mean, rstd, count) for the backward.  Updates the moving statistics."""
     R, C = x2d.shape
-    sums = kernels.bn_stats(x2d)
     world = _world()
+    # replicas may hold different numbers of rows (each pads to its own longest utterance): the local row count travels with the sums
+    # and the kernels divide by the reduced count (keras counts the same way, and so does ops._SyncBatchNormFn)
+    sums = kernels.bn_stats(x2d, with_count=world > 1)
     if world > 1:
-        dist.small_all_reduce(sums)  # C2: sync-BN statistics
-    count = float(R * world)
+        dist.small_all_reduce(sums)  # C2: sync-BN statistics (+ row count)
+    count = kernels.BN_COUNT_ON_DEVICE if world > 1 else float(R)
     with torch.no_grad():
         out = kernels.bn_finalize(sums, gamma.detach(), beta.detach(), moving_mean, moving_var, count, BN_EPS, BN_MOMENTUM)
     scale, shift, mean, rstd = out[0], out[1], out[2], out[3]
@@ -436,9 +505,10 @@ def bn_train_fwd(x2d, gamma, beta, moving_mean, moving_var, act=1):
 def bn_train_bwd(dy2d, x2d, saved, gamma, beta, act=1):
     """-> dx2d; accumulates dgamma / dbeta into the parameters' .grad."""
     scale, shift, mean, rstd, count = saved
-    sums = kernels.bn_bwd_stats(dy2d, x2d, scale, shift, mean, rstd, act)
+    world = _world()
+    sums = kernels.bn_bwd_stats(dy2d, x2d, scale, shift, mean, rstd, act, with_count=world > 1)
     kernels.bn_bwd_finalize(sums, _grad(gamma).view(-1), _grad(beta).view(-1))  # local contribution; the gradient all-reduce sums over replicas
-    if _world() > 1:
+    if world > 1:
         sums = dist.small_all_reduce(sums.clone())
     return kernels.bn_bwd_apply(dy2d, x2d, scale, shift, mean, rstd, sums, count, act)
 
@@ -497,7 +567,7 @@ class _SubsamplingFn(torch.autograd.Function):
             raise RuntimeError("Conv2dSubsampling fused backward needs training-mode batch statistics")
         dy2 = bn_train_bwd(dout.contiguous().view(-1, C), y2, s1, sub["bn_1.gamma"], sub["bn_1.beta"])
         col = kernels.im2col(a1)  # recomputed: cheaper than keeping 9x the activation alive
-        kernels.gemm(col, dy2, mn_major=True, out=_grad(pack.param).view(9 * C, C), accumulate=True, k_splits=32)
+        _wgrad(col, dy2, _grad(pack.param).view(9 * C, C), 32)
         del col
         dcol = kernels.gemm(dy2, pack.w)  # [M2, 9C]
         da1 = kernels.col2im(dcol, (B, T1, F1, C))
@@ -559,7 +629,7 @@ class QkvPack(WeightPack):
     def accumulate_wgrad(self, x, dz):
         D, NH = self.D, self.NH
         if self.unplan is not None:  # packed accumulation; fanned out to the three layers by the plan's single launch
-            kernels.gemm(x, dz, mn_major=True, out=self.dw_packed, accumulate=True, k_splits=_splits(x.shape[0]))
+            _wgrad(x, dz, self.dw_packed, _splits(x.shape[0]))
             self.unplan.request()
             return
         dw = torch.zeros((D, 3 * NH), dtype=torch.float32, device=x.device)
@@ -605,7 +675,7 @@ class PosAllPack(WeightPack):
         return self.db_packed
 
     def accumulate_wgrad(self, x, dz):
-        kernels.gemm(x, dz, mn_major=True, out=self.dw_packed, accumulate=True, k_splits=_splits(x.shape[0]))
+        _wgrad(x, dz, self.dw_packed, _splits(x.shape[0]))
         self.unplan.request()
 
 
@@ -752,7 +822,7 @@ class _ConvModuleFn(torch.autograd.Function):
         dg = kernels.dwconv_bwd(dc.view(B, T, D), g.view(B, T, D), w32, _grad(dw_w).view(-1, D), None).view(M, D)
         if getattr(p1, "unplan", None) is not None:
             daux = kernels.glu_bwd(aux, dg, colsum=p1.db_packed)
-            kernels.gemm(a, daux, mn_major=True, out=p1.dw_packed, accumulate=True, k_splits=_splits(M))
+            _wgrad(a, daux, p1.dw_packed, _splits(M))
             p1.unplan.request()
         else:
             db1 = torch.zeros(2 * D, dtype=torch.float32, device=x.device)

@@ -78,6 +78,30 @@ def layernorm_fwd(x, gamma, beta, eps=1e-3):
     return y, mean, rstd
 
 
+def ffn_supported(D: int, H: int) -> bool:
+    return bool(_lib.load().tfasr_ffn_supported(int(D), int(H)))
+
+
+def ffn_fwd(x, ln_g, ln_b, w1t, b1, w2t, b2, factor, drop_p=0.0, seed=None, salt1=0, salt2=0, eps=1e-3):
+    """The whole FFModule forward in one launch (csrc/ffn_fused.cu).  x [M, D] bf16, w1t [H, D], w2t [D, H] bf16.
+    -> (out [M, D], xn [M, D], z [M, H], h [M, H] bf16, mean [M], rstd [M] f32)."""
+    lib = _lib.load()
+    M, D = x.shape
+    H = w1t.shape[0]
+    dev = x.device
+    out = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+    xn = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+    z = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
+    h = torch.empty((M, H), dtype=torch.bfloat16, device=dev)
+    mean = torch.empty(M, dtype=torch.float32, device=dev)
+    rstd = torch.empty(M, dtype=torch.float32, device=dev)
+    _lib.check(lib.tfasr_ffn_fwd_bf16(_lib.ptr(x), _lib.ptr(ln_g), _lib.ptr(ln_b), _lib.ptr(w1t), _lib.ptr(b1), _lib.ptr(w2t), _lib.ptr(b2), _lib.ptr(out),
+                                      _lib.ptr(xn), _lib.ptr(z), _lib.ptr(h), _lib.ptr(mean), _lib.ptr(rstd), M, D, H, float(eps), float(factor),
+                                      float(drop_p), _lib.ptr(seed) if drop_p > 0 else None, int(salt1) & (2 ** 64 - 1), int(salt2) & (2 ** 64 - 1),
+                                      _lib.stream_ptr(dev)), "tfasr_ffn_fwd_bf16")
+    return out, xn, z, h, mean, rstd
+
+
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
     """-> dx bf16 [M, D] (= LN backward of dy, + dres); dgamma / dbeta (f32 [D]) are accumulated in place."""
     lib = _lib.load()
@@ -132,7 +156,9 @@ def joint_reduce_bwd(dz):
     B, T, U1, J = dz.shape
     de = torch.empty((B, T, J), dtype=torch.float32, device=dz.device)
     dp = torch.zeros((B, U1, J), dtype=torch.float32, device=dz.device)
-    fn, name = (lib.tfasr_joint_reduce_bwd_v2, "tfasr_joint_reduce_bwd_v2") if _joint_v2(U1, J) else (lib.tfasr_joint_reduce_bwd, "tfasr_joint_reduce_bwd")
+    from . import ops
+
+    fn, name = (lib.tfasr_joint_reduce_bwd_v2, "tfasr_joint_reduce_bwd_v2") if (_joint_v2(U1, J) and ops.joint_reduce_v2_active()) else (lib.tfasr_joint_reduce_bwd, "tfasr_joint_reduce_bwd")
     _lib.check(fn(_lib.ptr(dz), _lib.ptr(de), _lib.ptr(dp), B, T, U1, J, _lib.stream_ptr(dz.device)), name)
     return de, dp
 
@@ -193,10 +219,29 @@ def col2im(dcol, shape):
     return da
 
 
-def bn_stats(x2d):
+BN_COUNT_ON_DEVICE = -2.0  # `count` sentinel of tfasr_bn_finalize / tfasr_bn_bwd_apply: the row count is the float at sums[2 * C]
+
+_BN_TEMPLATES = {}
+
+
+def _bn_sums(C, R, device, with_count):
+    """Zeroed accumulator [2, C]; with_count: flat [2 C + 1] whose last slot holds this replica's row count R, so that the all-reduce of
+    the statistics also delivers the global count (replicas may pad to different lengths).  One copy launch instead of one fill launch."""
+    if not with_count:
+        return torch.zeros((2, C), dtype=torch.float32, device=device)
+    key = (C, int(R), str(device))
+    t = _BN_TEMPLATES.get(key)
+    if t is None:
+        t = torch.zeros(2 * C + 1, dtype=torch.float32)
+        t[2 * C] = float(R)
+        t = _BN_TEMPLATES[key] = t.to(device)
+    return t.clone()
+
+
+def bn_stats(x2d, with_count=False):
     lib = _lib.load()
     R, C = x2d.shape
-    sums = torch.zeros((2, C), dtype=torch.float32, device=x2d.device)
+    sums = _bn_sums(C, R, x2d.device, with_count)
     _lib.check(lib.tfasr_bn_stats(_lib.ptr(x2d), _lib.ptr(sums), R, C, _st(x2d)), "tfasr_bn_stats")
     return sums
 
@@ -204,7 +249,7 @@ def bn_stats(x2d):
 def bn_finalize(sums, gamma, beta, moving_mean, moving_var, count, eps, momentum):
     """-> out [4, C] f32 = (scale, shift, mean, rstd); moving statistics updated in place."""
     lib = _lib.load()
-    C = sums.shape[1]
+    C = gamma.numel()
     out = torch.empty((4, C), dtype=torch.float32, device=sums.device)
     _lib.check(lib.tfasr_bn_finalize(_lib.ptr(sums), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(moving_mean), _lib.ptr(moving_var), _lib.ptr(out), C,
                                      float(count), float(eps), float(momentum), _st(sums)), "tfasr_bn_finalize")
@@ -213,7 +258,7 @@ def bn_finalize(sums, gamma, beta, moving_mean, moving_var, count, eps, momentum
 
 def bn_bwd_finalize(sums, dgamma, dbeta):
     lib = _lib.load()
-    _lib.check(lib.tfasr_bn_bwd_finalize(_lib.ptr(sums), _lib.ptr(dgamma), _lib.ptr(dbeta), sums.shape[1], _st(sums)), "tfasr_bn_bwd_finalize")
+    _lib.check(lib.tfasr_bn_bwd_finalize(_lib.ptr(sums), _lib.ptr(dgamma), _lib.ptr(dbeta), dgamma.numel(), _st(sums)), "tfasr_bn_bwd_finalize")
 
 
 def bn_apply(x2d, scale, shift, act=1):
@@ -224,10 +269,10 @@ def bn_apply(x2d, scale, shift, act=1):
     return y
 
 
-def bn_bwd_stats(dy, x2d, scale, shift, mean, rstd, act=1):
+def bn_bwd_stats(dy, x2d, scale, shift, mean, rstd, act=1, with_count=False):
     lib = _lib.load()
     R, C = x2d.shape
-    sums = torch.zeros((2, C), dtype=torch.float32, device=x2d.device)
+    sums = _bn_sums(C, R, x2d.device, with_count)
     _lib.check(lib.tfasr_bn_bwd_stats(_lib.ptr(dy), _lib.ptr(x2d), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(sums),
                                       R, C, int(act), _st(x2d)), "tfasr_bn_bwd_stats")
     return sums

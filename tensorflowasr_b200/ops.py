@@ -70,8 +70,8 @@ _DWCONV_WGRAD_V2 = _os.environ.get("TFASR_DWCONV_WGRAD_V2", "0") == "1"
 
 
 def set_dwconv_wgrad_v2(flag: bool):
-    """ConvModule backward: depthwise weight gradient on the second-generation kernel (csrc/dwconv_wgrad_v2.cu).  Off by default until
-    measured on a B200."""
+    """ConvModule backward: depthwise weight gradient on the second-generation kernel (csrc/dwconv_wgrad_v2.cu).  Stays OFF: measured on
+    a B200 in round 2 it is slower than the first generation at the Conformer-S shape (461 vs 383 us per step over 16 blocks)."""
     global _DWCONV_WGRAD_V2
     _DWCONV_WGRAD_V2 = bool(flag)
 
@@ -80,12 +80,25 @@ def dwconv_wgrad_v2_active() -> bool:
     return _DWCONV_WGRAD_V2
 
 
-_IM2COL_V2 = _os.environ.get("TFASR_IM2COL_V2", "0") == "1"
+_JOINT_REDUCE_V2 = _os.environ.get("TFASR_JOINT_REDUCE_V2", "0") == "1"
+
+
+def set_joint_reduce_v2(flag: bool):
+    """Training head: de / dp reductions on csrc/joint_v2.cu's kernel.  Stays OFF: measured slower on a B200 (317 vs 162 us)."""
+    global _JOINT_REDUCE_V2
+    _JOINT_REDUCE_V2 = bool(flag)
+
+
+def joint_reduce_v2_active() -> bool:
+    return _JOINT_REDUCE_V2
+
+
+_IM2COL_V2 = _os.environ.get("TFASR_IM2COL_V2", "1") == "1"
 
 
 def set_im2col_v2(flag: bool):
-    """Conv2dSubsampling's second conv: im2col / col2im on the second-generation kernels (csrc/subsample_v2.cu).  Off by default until
-    measured on a B200."""
+    """Conv2dSubsampling's second conv: im2col / col2im on the second-generation kernels (csrc/subsample_v2.cu).  Default since round 2: 15.51 -> 14.86 ms per
+    bench step on a B200 (TFASR_IM2COL_V2=0 selects the first generation)."""
     global _IM2COL_V2
     _IM2COL_V2 = bool(flag)
 
@@ -94,12 +107,12 @@ def im2col_v2_active() -> bool:
     return _IM2COL_V2
 
 
-_JOINT_V2 = _os.environ.get("TFASR_JOINT_V2", "0") == "1"
+_JOINT_V2 = _os.environ.get("TFASR_JOINT_V2", "1") == "1"
 
 
 def set_joint_v2(flag: bool):
-    """Training head: tanh(e + p) and the de / dp reductions on the second-generation kernels (csrc/joint_v2.cu).  Off by default until
-    measured on a B200."""
+    """Training head: tanh(e + p) on the second-generation kernel (csrc/joint_v2.cu; 77 vs 153 us on a B200).  The de / dp reduction stays
+    on the first-generation wide kernel (set_joint_reduce_v2)."""
     global _JOINT_V2
     _JOINT_V2 = bool(flag)
 
@@ -108,11 +121,12 @@ def joint_v2_active() -> bool:
     return _JOINT_V2
 
 
-_RNNT_GRAD_V2 = _os.environ.get("TFASR_RNNT_GRAD_V2", "0") == "1"
+_RNNT_GRAD_V2 = _os.environ.get("TFASR_RNNT_GRAD_V2", "1") == "1"
 
 
 def set_rnnt_grad_v2(flag: bool):
-    """Training head: RNN-T gradient on the second-generation kernel (csrc/rnnt_grad_v2.cu).  Off by default until measured on a B200."""
+    """Training head: RNN-T gradient on the second-generation kernel (csrc/rnnt_grad_v2.cu).  Default since round 2 (688 vs 739 us
+    on a B200)."""
     global _RNNT_GRAD_V2
     _RNNT_GRAD_V2 = bool(flag)
 
@@ -121,11 +135,12 @@ def rnnt_grad_v2_active() -> bool:
     return _RNNT_GRAD_V2
 
 
-_CONV1_V2 = _os.environ.get("TFASR_CONV1_V2", "0") == "1"
+_CONV1_V2 = _os.environ.get("TFASR_CONV1_V2", "1") == "1"
 
 
 def set_conv1_v2(flag: bool):
-    """Conv2dSubsampling's first conv on the second-generation kernels (csrc/conv1.cu).  Off by default until measured on a B200."""
+    """Conv2dSubsampling's first conv on the second-generation kernels (csrc/conv1.cu).  Default since round 2: forward 195 vs 435 us,
+    weight gradient 345 vs 417 us on a B200."""
     global _CONV1_V2
     _CONV1_V2 = bool(flag)
 
@@ -134,13 +149,13 @@ def conv1_v2_active() -> bool:
     return _CONV1_V2
 
 
-_POS_BATCHED = _os.environ.get("TFASR_POS_BATCHED", "0") == "1"
+_POS_BATCHED = _os.environ.get("TFASR_POS_BATCHED", "1") == "1"
 
 
 def set_pos_batched(flag: bool):
     """Conformer encoder: project the relative position table for ALL blocks in one GEMM (fused.PosAllPack; the attention kernels read /
     write column slices through tfasr_rel_attention_*_ld) instead of one projection, one bias column-sum and one weight-gradient GEMM per
-    block.  Off by default until measured on a B200."""
+    block.  Default since round 2 (15.51 -> 15.23 ms per bench step on a B200)."""
     global _POS_BATCHED
     _POS_BATCHED = bool(flag)
 
@@ -164,13 +179,13 @@ def peer_bn_active() -> bool:
     return _PEER_BN
 
 
-_FUSED_LSE = _os.environ.get("TFASR_FUSED_LSE", "0") == "1"
+_FUSED_LSE = _os.environ.get("TFASR_FUSED_LSE", "1") == "1"
 
 
 def set_fused_lse(flag: bool):
     """Training head: take the RNN-T log-softmax normaliser from softmax statistics computed in the joint GEMM's epilogue (gemm feature
-    class 8 + csrc/rnnt_combine.cu) instead of a separate pass over the 2 GB of logits (first step).  Off by default until
-    tests/test_gpu_zz_lse.py has run green on a B200."""
+    class 8 + csrc/rnnt_combine.cu) instead of a separate pass over the 2 GB of logits (first step).  Default since round 2: tests/test_gpu_lse.py green
+    on a B200, RNN-T group 0.50 -> 0.71 of the HBM roofline on algorithmic bytes."""
     global _FUSED_LSE
     _FUSED_LSE = bool(flag)
 
@@ -179,18 +194,46 @@ def fused_lse_active() -> bool:
     return _FUSED_LSE
 
 
-_PERSISTENT_DECODE = _os.environ.get("TFASR_PERSISTENT_DECODE", "0") == "1"
+_PERSISTENT_DECODE = _os.environ.get("TFASR_PERSISTENT_DECODE", "1") == "1"
 
 
 def set_persistent_decode(flag: bool):
-    """Greedy decoding through the one-launch persistent kernel (csrc/decode.cu) instead of the host-driven loop.  Off by
-    default until tests/test_gpu_zz_decode.py (written without GPU time; emulator-verified) has run green on a B200."""
+    """Greedy decoding through the one-launch persistent kernel (csrc/decode.cu) instead of the host-driven loop.  Default since
+    round 2: tokens bit-exact vs the host loop and the oracle on a B200, 54.5 vs 750.7 us per decode iteration at batch 32."""
     global _PERSISTENT_DECODE
     _PERSISTENT_DECODE = bool(flag)
 
 
 def persistent_decode_active() -> bool:
     return _PERSISTENT_DECODE
+
+
+_FUSED_FFN = _os.environ.get("TFASR_FUSED_FFN", "1") == "1"
+
+
+def set_fused_ffn(flag: bool):
+    """Conformer FFModule forward as ONE kernel (csrc/ffn_fused.cu: LayerNorm prologue, both GEMMs, the hidden activation handed over in
+    SMEM) instead of LayerNorm + two GEMM launches."""
+    global _FUSED_FFN
+    _FUSED_FFN = bool(flag)
+
+
+def fused_ffn_active() -> bool:
+    return _FUSED_FFN
+
+
+_SWITCHES = ("_FUSED_FFN", "_FUSED", "_FUSED_SEQ", "_DWCONV_WGRAD_V2", "_JOINT_REDUCE_V2", "_IM2COL_V2", "_JOINT_V2", "_RNNT_GRAD_V2", "_CONV1_V2", "_POS_BATCHED",
+             "_PEER_BN", "_FUSED_LSE", "_PERSISTENT_DECODE")
+
+
+def switch_state() -> dict:
+    """Snapshot of every kernel-route switch (tests flip them and put them back with restore_switches)."""
+    g = globals()
+    return {k: g[k] for k in _SWITCHES}
+
+
+def restore_switches(state: dict):
+    globals().update({k: bool(v) for k, v in state.items() if k in _SWITCHES})
 
 
 def compute_dtype():

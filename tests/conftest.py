@@ -49,3 +49,16 @@ def pytest_sessionfinish(session, exitstatus):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _kernel_route_switches_restored():
+    """Tests flip the kernel-route switches of tensorflowasr_b200.ops (and the precision); every test starts from, and leaves behind, the
+    defaults — so each test runs the route a user gets unless it says otherwise."""
+    from tensorflowasr_b200 import ops
+
+    saved, prec = ops.switch_state(), ops.precision()
+    yield
+    ops.restore_switches(saved)
+    if ops.precision() != prec:
+        ops.set_precision(prec)

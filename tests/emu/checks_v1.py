@@ -47,7 +47,7 @@ def load(asan=False, tsan=False):
               "tfasr_im2col_3x3s2", "tfasr_col2im_3x3s2", "tfasr_dwconv_causal_fwd", "tfasr_dwconv_causal_bwd", "tfasr_joint_tanh_fwd",
               "tfasr_joint_reduce_bwd", "tfasr_adamw_flat_f32", "tfasr_signal_normalize_f32", "tfasr_feature_normalize_f32", "tfasr_specaugment_f32",
               "tfasr_pack_weights", "tfasr_unpack_add", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd", "tfasr_rel_attention_fwd_ld", "tfasr_rel_attention_bwd_ld", "tfasr_lstm_rec_fwd", "tfasr_lstm_rec_bwd",
-              "tfasr_lstm_supported", "tfasr_gemm_bf16"):
+              "tfasr_lstm_supported", "tfasr_gemm_bf16", "tfasr_ffn_fwd_bf16", "tfasr_ffn_supported"):
         getattr(lib, n).restype = c_i32
     return lib
 
@@ -813,6 +813,63 @@ def check_random_shapes_v1(lib):
             check_gemm(lib, M, N, K, f32_out=True, bias=True, rowstats=True, seed=ri(0, 1 << 30))
 
 
+# ------------------------------------------------------------------------------------------------ fused FFModule (ffn_fused.cu)
+def _ffn_case(M, H, D, seed):
+    rng = np.random.default_rng(seed)
+    x = rbf(rng.standard_normal((M, D)) * 1.5 + 0.3)
+    g, b = (1 + 0.2 * rng.standard_normal(D)).astype(np.float32), (0.1 * rng.standard_normal(D)).astype(np.float32)
+    w1 = rbf(rng.standard_normal((D, H)) / np.sqrt(D))
+    w2 = rbf(rng.standard_normal((H, D)) / np.sqrt(H))
+    b1, b2 = (0.2 * rng.standard_normal(H)).astype(np.float32), (0.2 * rng.standard_normal(D)).astype(np.float32)
+    return x, g, b, w1, b1, w2, b2
+
+
+def check_ffn_fwd(lib, M, H, dropout=0.0, D=144, seed=71):
+    """out = x + 0.5 Drop2(W2 Drop1(swish(W1 LN(x) + b1)) + b2) in ONE launch (TMA x tile, in-SMEM LayerNorm, chunked GEMM 1 -> SMEM -> GEMM 2,
+    3-stage weight ring) against float64 numpy with the kernel's bf16 rounding points (xn, h)."""
+    assert lib.tfasr_ffn_supported(D, H) == 1
+    x, g, b, w1, b1, w2, b2 = _ffn_case(M, H, D, seed)
+    x64 = x.astype(np.float64)
+    mean = x64.mean(1, keepdims=True)
+    var = ((x64 - mean) ** 2).mean(1, keepdims=True)
+    rstd = 1 / np.sqrt(var + 1e-3)
+    xn = rbf((x64 - mean) * rstd * g + b).astype(np.float64)
+    z = xn @ w1.astype(np.float64) + b1
+    h = z / (1 + np.exp(-z))
+    dseed, salt1, salt2 = 1234, 7, 8
+    if dropout > 0:
+        h = np.where(_dropout_keep(dseed, salt1, M, H, dropout), h / (1 - dropout), 0.0)
+    hb = rbf(h).astype(np.float64)
+    y = hb @ w2.astype(np.float64) + b2
+    if dropout > 0:
+        y = np.where(_dropout_keep(dseed, salt2, M, D, dropout), y / (1 - dropout), 0.0)
+    out = x64 + 0.5 * y
+    nan16 = lambda shape: heap(np.full(shape, 0x7FC0, np.uint16))  # noqa: E731
+    xb, xp = heap(to_bf16(x))
+    w1b, w1p = heap(to_bf16(np.ascontiguousarray(w1.T)))
+    w2b, w2p = heap(to_bf16(np.ascontiguousarray(w2.T)))
+    gb, gp = heap(g)
+    bb, bp = heap(b)
+    b1b, b1p = heap(b1)
+    b2b, b2p = heap(b2)
+    ob, op = nan16((M, D))
+    xnb, xnp = nan16((M, D))
+    zb, zp = nan16((M, H))
+    hbuf, hp = nan16((M, H))
+    mb, mp = heap(np.full(M, np.nan, np.float32))
+    rb_, rp = heap(np.full(M, np.nan, np.float32))
+    sb, sp = heap(np.array([dseed], np.uint64))
+    st = lib.tfasr_ffn_fwd_bf16(xp, gp, bp, w1p, b1p, w2p, b2p, op, xnp, zp, hp, mp, rp, M, D, H, c_f(1e-3), c_f(0.5), c_f(dropout), sp,
+                                ctypes.c_ulonglong(salt1), ctypes.c_ulonglong(salt2), None)
+    assert st == 0, st
+    close(mb, mean[:, 0], 1e-5, "ffn mean")
+    close(rb_, rstd[:, 0], 1e-4, "ffn rstd")
+    close(from_bf16(xnb), xn, 8e-3, "ffn xn")
+    close(from_bf16(zb), z, 8e-3, "ffn z (pre-activation)")
+    close(from_bf16(hbuf), h, 8e-3, "ffn h")
+    close(from_bf16(ob), out, 8e-3, "ffn out")
+
+
 CASES = [
     ("rnnt_kat", check_rnnt_kat),
     ("rnnt_ragged", lambda lib: check_rnnt(lib, 4, 13, 8, 12, [13, 9, 5, 13], [7, 4, 0, 1])),
@@ -863,6 +920,8 @@ CASES = [
     ("gemm_tiny", lambda lib: check_gemm(lib, 1, 8, 8, f32_out=True)),
     ("gemm_rowstats", lambda lib: check_gemm(lib, 130, 1000, 64, f32_out=True, bias=True, rowstats=True)),  # feature class 8 (fused log-sum-exp)
     ("gemm_rowstats_narrow", lambda lib: check_gemm(lib, 40, 40, 32, f32_out=True, bias=True, rowstats=True)),  # one tile, second slice empty
+    ("ffn_fwd_one_tile", lambda lib: check_ffn_fwd(lib, 100, 128)),  # ragged tile, two hidden chunks
+    ("ffn_fwd_conformer_s", lambda lib: check_ffn_fwd(lib, 300, 576, dropout=0.1)),  # 3 tiles x 9 chunks: every ring / double-buffer phase wraps
     ("random_shapes_v1", check_random_shapes_v1),
     ("cluster_lstm", lambda lib: check_cluster_lstm(lib, 3, 4, 64, [4, 2, 3], False)),
     ("cluster_lstm_state", lambda lib: check_cluster_lstm(lib, 2, 3, 128, [3, 3], True)),

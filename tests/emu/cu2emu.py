@@ -101,7 +101,7 @@ def convert(src: str, name: str = "?") -> str:
     src = re.sub(r'asm\("tanh\.approx\.f32 %0, %1;"\s*:\s*"=f"\((\w+)\)\s*:\s*"f"\(([^;]+)\)\);', r"\1 = tanhf(\2);", src)
     # ---- the tcgen05 GEMM (gemm_kernel.cuh / gemm.cu / gemm_inst_*.cu): sm100.cuh -> emu_sm100.h, the few other PTX lines by hand
     src = src.replace('#include "sm100.cuh"', '#include "emu_sm100.h"')
-    src = src.replace('asm volatile("bar.sync 1, 256;" ::: "memory");', "emu::named_barrier_sync(1, 256);")
+    src = re.sub(r'asm volatile\("bar\.sync (\d+), (\d+);" ::: "memory"\);', r"emu::named_barrier_sync(\1, \2);", src)
     src = src.replace('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));', "t = 0;")
     src = re.sub(r'const __half2 h = __floats2half2_rn\(0\.5f \* a, 0\.5f \* b\);.*?sb = fmaf\(0\.5f, tf\.y, 0\.5f\);',
                  "sa = fmaf(0.5f, tanhf(0.5f * a), 0.5f);\n  sb = fmaf(0.5f, tanhf(0.5f * b), 0.5f);", src, flags=re.S)

@@ -61,12 +61,26 @@ def gemm(a, b, *, out=None, out_dtype=None, bias=None, activation=None, aux=None
     return out
 
 
-def bn_stats(x2d):
+BN_COUNT_ON_DEVICE = -2.0
+
+
+def _with_count(sums, R, with_count):
+    return torch.cat([sums.reshape(-1), torch.tensor([float(R)])]) if with_count else sums
+
+
+def _split_count(sums, count, C):
+    if count == BN_COUNT_ON_DEVICE:
+        return sums.reshape(-1)[:2 * C].view(2, C), sums.reshape(-1)[2 * C]
+    return sums.reshape(-1)[:2 * C].view(2, C), count
+
+
+def bn_stats(x2d, with_count=False):
     x = x2d.float()
-    return torch.stack([x.sum(0), (x * x).sum(0)])
+    return _with_count(torch.stack([x.sum(0), (x * x).sum(0)]), x2d.shape[0], with_count)
 
 
 def bn_finalize(sums, gamma, beta, moving_mean, moving_var, count, eps, momentum):
+    sums, count = _split_count(sums, count, gamma.numel())
     mean = sums[0] / count
     var = (sums[1] / count - mean * mean).clamp(min=0)
     rstd = torch.rsqrt(var + eps)
@@ -84,17 +98,19 @@ def _bn_d(dy, x2d, scale, shift, act):
     return dy.float() * _act_grad(x2d.float() * scale + shift, act)
 
 
-def bn_bwd_stats(dy, x2d, scale, shift, mean, rstd, act=1):
+def bn_bwd_stats(dy, x2d, scale, shift, mean, rstd, act=1, with_count=False):
     d = _bn_d(dy, x2d, scale, shift, act)
-    return torch.stack([d.sum(0), (d * (x2d.float() - mean) * rstd).sum(0)])
+    return _with_count(torch.stack([d.sum(0), (d * (x2d.float() - mean) * rstd).sum(0)]), x2d.shape[0], with_count)
 
 
 def bn_bwd_finalize(sums, dgamma, dbeta):
+    sums = sums.reshape(-1)[:2 * dgamma.numel()].view(2, -1)
     dgamma.add_(sums[1])
     dbeta.add_(sums[0])
 
 
 def bn_bwd_apply(dy, x2d, scale, shift, mean, rstd, sums, count, act=1):
+    sums, count = _split_count(sums, count, x2d.shape[1])
     d = _bn_d(dy, x2d, scale, shift, act)
     xh = (x2d.float() - mean) * rstd
     return (scale * (d - sums[0] / count - xh * sums[1] / count)).to(BF)

@@ -66,8 +66,12 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
     model, data = _model(blocks=2), _batch()
     state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
     # + the batched position projection: one GEMM for all blocks, attention kernels on column slices, one shared gradient buffer
-    v2 = (ops.set_conv1_v2, ops.set_im2col_v2, ops.set_joint_v2, ops.set_dwconv_wgrad_v2, ops.set_rnnt_grad_v2, ops.set_fused_lse, ops.set_pos_batched)
+    v2 = (ops.set_conv1_v2, ops.set_im2col_v2, ops.set_joint_v2, ops.set_joint_reduce_v2, ops.set_dwconv_wgrad_v2, ops.set_rnnt_grad_v2,
+          ops.set_fused_lse, ops.set_pos_batched)
+    saved = ops.switch_state()
     try:
+        for s in v2:
+            s(False)
         ops.set_precision("fp32")
         ops.set_fused(False)
         ref_loss, ref_g = _run(model, data, state0)  # library route, fp32: the reference
@@ -83,14 +87,12 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
         calls2 = dict(emu.calls)
         loss3, g3 = _run(model, data, state0)  # once more on the same packs: packed gradient sums and the shared dpos buffer start clean
     finally:
-        for s in v2:
-            s(False)
-        ops.set_fused(True)
+        ops.restore_switches(saved)
         ops.set_precision("fp32")
     second_gen = ("tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2",
                   "tfasr_joint_reduce_bwd_v2", "tfasr_dwconv_causal_wgrad_v2", "tfasr_dwconv_causal_bwd_dx", "tfasr_rnnt_loss_bwd_bf16_v2",
                   "tfasr_rnnt_loss_fwd_rowstats_f32", "tfasr_rel_attention_fwd_ld", "tfasr_rel_attention_bwd_ld")
-    assert not any(k in calls1 for k in second_gen), calls1  # the default route is the first-generation kernels ...
+    assert not any(k in calls1 for k in second_gen), calls1  # every switch off: the first-generation kernels ...
     assert all(calls2.get(k, 0) > 0 for k in second_gen), calls2  # ... and every switch routes to its second-generation kernel
     for k in ("tfasr_logmel_f32", "tfasr_layernorm_fwd", "tfasr_layernorm_bwd", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd", "tfasr_lstm_rec_fwd",
               "tfasr_lstm_rec_bwd", "tfasr_bn_stats", "tfasr_bn_bwd_apply", "tfasr_dwconv_causal_fwd", "tfasr_glu_bwd", "tfasr_pack_weights",

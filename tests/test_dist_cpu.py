@@ -53,7 +53,7 @@ def _worker(rank, world, port, out):
     red.all_reduce()
     mean_loss = tdist.all_reduce_mean_scalar(losses.mean().detach())
     if rank == 0:
-        out.put(([w.grad.clone() for w in ws], mean_loss))
+        out.put(([w.grad.clone().numpy() for w in ws], float(mean_loss)))  # by value: a torch tensor would travel as a file descriptor this process must outlive
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,6 +74,6 @@ def test_two_rank_gradients_match_single_process_full_batch():
     ws = _model()
     losses = _forward(ws, x)
     losses.mean().backward()
-    torch.testing.assert_close(mean_loss, losses.mean().detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(torch.tensor(mean_loss), losses.mean().detach(), rtol=1e-5, atol=1e-6)
     for g, w in zip(grads, ws):
-        torch.testing.assert_close(g, w.grad, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(torch.from_numpy(g), w.grad, rtol=1e-4, atol=1e-6)

@@ -1,7 +1,7 @@
 """CPU: the autograd wiring of fused_seq.py (ContextNet / DeepSpeech2 fused encoder routes) against the library
 route of the same encoder — outputs, lengths, moving statistics and every parameter gradient.  The seqconv kernels run as their real
 source on the CPU emulator; GEMM / BatchNorm launchers are torch stand-ins of their contracts (tests/mock_kernels.py).  The GPU twin of
-this test is tests/test_gpu_zz_seqconv.py."""
+this test is tests/test_gpu_seqconv.py."""
 import shutil
 
 import pytest

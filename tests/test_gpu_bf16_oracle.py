@@ -1,0 +1,187 @@
+"""GPU parity of the BENCHMARKED path — bf16, every default kernel route (fused Conformer modules on the tcgen05 GEMM, tensor-core attention,
+cluster LSTM, fused log-sum-exp head, persistent decode) — held directly against the float64 CPU oracle (oracle/conformer.py, oracle/logmel.py),
+not against another route of this library.
+
+Round 1 only tied the bf16 path to the oracle transitively (fp32 library route vs oracle, fused vs library route); these tests close that gap:
+  * a 2-block model: logits, per-utterance RNN-T losses and the gradient list of tests/test_gpu_model.py, training mode (batch statistics);
+  * BASELINE config-3 size (Conformer-S, 16 blocks, B = 32 x 10 s, U = 64, V = 1000): per-utterance losses, a sample of the logits and the
+    gradients of 20 parameters against tests/golden/conformer_s_config3_fp64.npz (minted once by tools/mint_full_size_golden.py: the float64
+    oracle needs ~15 CPU-minutes and ~30 GB at this size);
+  * greedy tokens through the bf16 encoder + the persistent decode kernel against the oracle's walk, with a per-decision margin guard.
+
+Tolerances (bf16 has an 8-bit mantissa: one rounding = 2^-9 = 2.0e-3 relative; activations are rounded to bf16 between kernels, accumulation
+and statistics are fp32):
+  * per-utterance loss: 2e-2 relative.  The loss is a sum of ~U + T' log-probabilities whose errors are dominated by the logits' error
+    (each logit: 320-term bf16 dot product + the encoder's accumulated rounding through 16 blocks).
+  * logits: |err| <= 4e-2 * (|ref| + std(ref)).
+  * gradients: max |err| <= 8e-2 * max |ref| per tensor AND cosine similarity >= 0.99 (small model), 0.98 (16 blocks).  Gradients are sums of
+    thousands of signed bf16-rounded products: the element-wise bound is loose, the cosine is the sharp check (a wrong formula, a missing term
+    or a transposed operand gives cosines far below 0.9).
+The measured values are printed (pytest -s) so that the margins stay visible.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import conformer as oc
+from oracle import logmel as ologmel
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 2e-2
+LOGIT_TOL = 4e-2
+GRAD_TOL = 8e-2
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "conformer_s_config3_fp64.npz")
+
+
+def _grad_check(name, got, ref, cos_min, report):
+    got, ref = got.reshape(-1).double(), ref.reshape(-1).double()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item() if scale > 0 else 1.0
+    report.append((name, err / max(scale, 1e-30), cos))
+    assert err <= GRAD_TOL * scale + 1e-9 and cos >= cos_min, (name, err, scale, cos)
+
+
+def test_default_bf16_route_vs_float64_oracle_two_blocks():
+    from tensorflowasr_b200 import ops
+
+    from test_gpu_model import _batch, _oracle_losses, _setup
+
+    model, ocfg, params = _setup()
+    ops.set_precision("bf16")  # _setup selects fp32; every kernel-route switch is at its default
+    data, host = _batch()
+    # inference-mode logits (moving statistics)
+    model.eval()
+    out = model(data.inputs, training=False)
+    _, ref_logits, ref_len, _ = _oracle_losses(params, ocfg, host, training=False)
+    assert out.logits_length.tolist() == ref_len.tolist()
+    got = out.logits.detach().cpu().double()
+    std = ref_logits.std().item()
+    lerr = ((got - ref_logits).abs() / (ref_logits.abs() + std)).max().item()
+    # training mode: losses and gradients
+    model.train()
+    losses = model.compute_losses(data, training=True)
+    losses.mean().backward()
+    names = ["encoder.linear.kernel", "encoder.block_0.mhsa_module.mhsa.query.kernel", "encoder.block_1.conv_module.dw_conv.kernel",
+             "encoder.block_0.ff_module_1.dense_1.bias", "encoder.content_attention_bias", "encoder.positional_attention_bias",
+             "encoder.subsampling.conv_0.kernel", "encoder.block_1.conv_module.dw_bn.gamma", "prediction.lstm_0.recurrent_kernel",
+             "prediction.embedding.embeddings", "joint.vocab.kernel", "joint.vocab.bias", "joint.enc.kernel", "joint.pred.bias",
+             "encoder.block_1.ln.beta", "encoder.block_0.mhsa_module.mhsa.encoding.kernel"]
+    ref_losses, _, _, p = _oracle_losses(params, ocfg, host, training=True, requires_grad=names)
+    ref_losses.mean().backward()
+    rel = ((losses.detach().cpu().double() - ref_losses.detach()).abs() / ref_losses.detach().abs()).max().item()
+    print(f"\n[bf16 vs fp64, 2 blocks] logits err {lerr:.3e} (tol {LOGIT_TOL}), loss rel err {rel:.3e} (tol {LOSS_RTOL})")
+    assert lerr <= LOGIT_TOL, lerr
+    assert rel <= LOSS_RTOL, (losses.tolist(), ref_losses.tolist())
+    w = model.named_weights()
+    report = []
+    for n in names:
+        _grad_check(n, w[n].grad.detach().cpu(), p[n].grad, 0.99, report)
+    for n, e, c in report:
+        print(f"  grad {n}: max err / max {e:.3e}, cosine {c:.5f}")
+
+
+def _full_size_reference():
+    """-> dict like the golden file; minted on the spot (slow: minutes of CPU) when the fixture is absent."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import mint_full_size_golden as mint
+
+    if os.path.exists(GOLDEN):
+        return mint, dict(np.load(GOLDEN))
+    pytest.skip("tests/golden/conformer_s_config3_fp64.npz missing: run tools/mint_full_size_golden.py (float64 oracle at config-3 size)")
+
+
+def test_default_bf16_route_vs_float64_oracle_config3_size():
+    """The bench.py step itself (same model, same shapes, same switches; dropout and SpecAugment off because they are RNG-dependent)."""
+    import tensorflowasr_b200 as tfasr
+    from tensorflowasr_b200 import ops, schemas
+
+    mint, gold = _full_size_reference()
+    B, seconds, U = int(gold["batch"]), int(gold["seconds"]), int(gold["labels"])
+    ocfg, params, host = mint.full_size_case(B, seconds, U)
+    sig, sig_len, pred, pred_len, labels, lab_len = host
+    ops.set_precision("bf16")
+    cfg = tfasr.conformer_small_config(vocab_size=ocfg.vocab_size)
+    cfg["speech_config"].pop("augmentation_config", None)
+    cfg.update(encoder_dropout=0.0)
+    model = tfasr.Conformer(**cfg, seed=1).cuda()
+    model.load_named_weights(params)
+    data = schemas.TrainData(schemas.TrainInput(sig.cuda(), sig_len.cuda(), pred.cuda(), pred_len.cuda()), schemas.TrainLabel(labels.cuda(), lab_len.cuda()))
+    model.train()
+    out = model(data.inputs, training=True)
+    assert out.logits_length.cpu().tolist() == gold["logits_length"].tolist()
+    got_sample = torch.from_numpy(mint.sample(out.logits.detach().float().cpu()))
+    ref_sample = torch.from_numpy(gold["logits_sample"])
+    std = float(gold["logits_std"])
+    lerr = ((got_sample - ref_sample).abs() / (ref_sample.abs() + std)).max().item()
+    del out
+    for p in model.parameters():
+        p.grad = None
+    losses = model.compute_losses(data, training=True)  # the fused head: joint GEMM + row statistics + lattice + in-place bf16 gradient
+    losses.mean().backward()
+    ref_losses = torch.from_numpy(gold["losses"])
+    rel = ((losses.detach().cpu().double() - ref_losses).abs() / ref_losses.abs()).max().item()
+    print(f"\n[bf16 vs fp64, config-3 size B={B}] logits err {lerr:.3e} (tol {LOGIT_TOL}), loss rel err {rel:.3e} (tol {LOSS_RTOL})")
+    assert lerr <= LOGIT_TOL, lerr
+    assert rel <= LOSS_RTOL, (losses.tolist()[:4], ref_losses.tolist()[:4])
+    w = model.named_weights()
+    report = []
+    for n in mint.GRAD_NAMES:
+        got = torch.from_numpy(mint.sample(w[n].grad.detach().float().cpu()))
+        _grad_check(n, got, torch.from_numpy(gold["grad:" + n]), 0.98, report)
+    for n, e, c in report:
+        print(f"  grad {n}: max err / max {e:.3e}, cosine {c:.5f}")
+
+
+def test_bf16_persistent_greedy_tokens_vs_oracle_with_margin_guard():
+    """Greedy tokens of the default decode route in bf16 (fused encoder + persistent kernel) against the float64 oracle's walk
+    (base_transducer.py:577-712).  A bf16 encoder cannot promise the argmax of a near-tie, so the comparison covers every decision up to the
+    first one whose top-2 log-probability margin in the oracle is below MARGIN; the test demands that this covers a real stretch of decoding."""
+    from tensorflowasr_b200 import ops, schemas
+
+    from test_gpu_model import _batch, _setup
+
+    MARGIN = 0.25
+    model, ocfg, params = _setup(V=32, seed=5, blank_bias=-0.6)
+    ops.set_precision("bf16")
+    assert ops.persistent_decode_active()
+    data, host = _batch(V=32, B=3, N=16000, ragged=True)
+    sig, sig_len = host[0], host[1]
+    model.eval()
+    feats, flen = ologmel.feature_extraction(sig.numpy().astype(np.float64), sig_len.numpy(), dtype=np.float64)
+    p = {k: v.double() for k, v in params.items()}
+    enc, elen = oc.conformer_encoder(torch.from_numpy(feats), torch.from_numpy(flen).long(), p, ocfg, training=False)
+    compared = 0
+    for b in range(sig.shape[0]):
+        got = model.recognize(schemas.PredictInput(sig[b:b + 1].cuda(), sig_len[b:b + 1].cuda())).tokens[0].cpu().tolist()
+        # the oracle's walk with per-decision margins (oc.greedy_single restated with the margin recorded per step)
+        R = ocfg.rnn_units
+        h, c = enc.new_zeros(1, R), enc.new_zeros(1, R)
+        tok, frame, per, ref = torch.tensor([[0]]), 0, 0, []
+        n = int(elen[b])
+        safe = True
+        while frame < n and safe:
+            lp, h2, c2 = oc._call_next(enc[b:b + 1, frame:frame + 1], tok, h, c, p)
+            if oc._margin(lp) < MARGIN:
+                safe = False
+                break
+            k = int(lp[0].argmax())
+            compared += 1
+            if k == 0:
+                frame, per = frame + 1, 0
+            else:
+                per += 1
+                ref.append(k)
+                tok, h, c = torch.tensor([[k]]), h2, c2
+                if per >= 3:
+                    frame, per = frame + 1, 0
+        assert got[: len(ref)] == ref, (b, got[: len(ref) + 2], ref)
+        if safe:
+            assert all(t == 0 for t in got[len(ref):])
+    print(f"\n[bf16 greedy vs fp64] {compared} decisions compared under margin guard {MARGIN}")
+    assert compared >= 20, compared

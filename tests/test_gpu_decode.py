@@ -1,8 +1,7 @@
 """GPU parity of the persistent greedy decode kernel (csrc/decode.cu): tokens bit-exact against the host-driven loops
 (the verbatim mirror of base_transducer.py:496-712) and against the float64 oracle, fp32 mode.
 
-STATUS: written in a session with no GPU minutes left; the kernel is verified on the CPU emulator (tests/test_emu_kernels.py: greedy_*,
-incl. AddressSanitizer) but has not run on a B200, hence xfail(strict=False) and a file name that sorts last (see test_gpu_zz_seqconv.py).
+First run on a B200 in round 2: green, and the persistent kernel became the default decode route (54.5 vs 750.7 us per iteration at batch 32).
 """
 import numpy as np
 import pytest
@@ -11,7 +10,7 @@ import torch
 from oracle import conformer as oc
 from oracle import logmel as ologmel
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet run on a B200 (emulator-verified only)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_persistent_greedy_decode_matches_host_loop_and_oracle():

@@ -28,7 +28,7 @@ def stub(monkeypatch):
 def test_kernel_launchers_run_with_every_switch(stub, flag):
     from tensorflowasr_b200 import kernels, ops
 
-    setters = (ops.set_conv1_v2, ops.set_im2col_v2, ops.set_joint_v2, ops.set_dwconv_wgrad_v2)
+    setters = (ops.set_conv1_v2, ops.set_im2col_v2, ops.set_joint_v2, ops.set_joint_reduce_v2, ops.set_dwconv_wgrad_v2)
     try:
         for s in setters:
             s(flag)
