@@ -196,8 +196,14 @@ int tfasr_glu_bwd(const void* aux, const void* dg, void* daux, float* colsum, in
  * xn = LN(x) [M, D] bf16, z = pre-activation [M, H] bf16, h = Drop1(swish(z)) [M, H] bf16, mean / rstd [M] f32.  The dropout masks are the
  * counter hashes of the GEMM epilogues: hash(*seed_ptr + salt, row, col), salt1 for the hidden activation, salt2 for the output.
  * Supported: tfasr_ffn_supported(D, H) (D = 144, H a multiple of 64); anything else returns TFASR_INVALID_VALUE.
+ * Backward gradient chain in one launch (the weight / bias gradients and the LayerNorm backward stay separate kernels):
+ *   dy = factor * Drop2'(dout) [M, D];  dz = (dy . W2^T) * Drop1' * swish'(z) [M, H];  da = dz . W1^T [M, D]   (all bf16, all written)
+ * w2 = W2 [H, D] bf16, w1 = W1 [D, H] bf16 (the untransposed operand copies), z the saved pre-activation.
  * ---------------------------------------------------------------------------------------------- */
 int tfasr_ffn_supported(int32_t D, int32_t H);
+int tfasr_ffn_bwd_bf16(const void* dout, const void* z, const void* w2, const void* w1, void* dy, void* dz, void* da, int32_t M, int32_t D, int32_t H,
+                       float factor, float drop_p, const unsigned long long* seed_ptr, unsigned long long salt1, unsigned long long salt2,
+                       tfasr_stream_t stream);
 int tfasr_ffn_fwd_bf16(const void* x, const float* ln_g, const float* ln_b, const void* w1t, const float* b1, const void* w2t, const float* b2,
                        void* out, void* xn, void* z, void* h, float* mean, float* rstd, int32_t M, int32_t D, int32_t H, float eps, float factor,
                        float drop_p, const unsigned long long* seed_ptr, unsigned long long salt1, unsigned long long salt2,

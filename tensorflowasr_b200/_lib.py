@@ -132,6 +132,7 @@ SIGNATURES = {
     "tfasr_ffn_supported": (c_int32, [c_int32, c_int32]),
     "tfasr_ffn_fwd_bf16": (c_int32, [c_void_p] * 13 + [c_int32, c_int32, c_int32, c_float, c_float, c_float, c_void_p, ctypes.c_uint64, ctypes.c_uint64,
                                      c_void_p]),
+    "tfasr_ffn_bwd_bf16": (c_int32, [c_void_p] * 7 + [c_int32, c_int32, c_int32, c_float, c_float, c_void_p, ctypes.c_uint64, ctypes.c_uint64, c_void_p]),
     "tfasr_layernorm_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "tfasr_layernorm_bwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int32, c_int32, c_void_p]),

@@ -15,6 +15,12 @@
 // Weight chunks (W1^T rows [64 x D], W2^T columns [D x 64]: 42 KB per chunk) stream through a 3-stage TMA ring from L2, where the 332 KB of
 // module weights stay resident.  G1 of chunk c+1 overlaps E1 of chunk c (double-buffered acc1 and h).
 //
+// Backward (MODE 1) is the same two-GEMM skeleton run on the gradient chain of FFModule's backward:
+//   TMA   dout tile -> SMEM;  prologue: dy = factor * Drop2'(dout) in place (the A operand; dy also leaves through the TMA store for dW2 / db2)
+//   G1    acc1 = dy . W2[chunk, :]^T            E1: dz = acc1 * Drop1' * swish'(z) -> global (for dW1 / db1) and SMEM
+//   G2    acc2 += dz_chunk . W1[:, chunk]^T     E2: da = acc2 -> bf16 (LayerNorm's input gradient; the LayerNorm backward kernel follows)
+// i.e. scale_mask_colsum + the swish' GEMM + the dgrad GEMM of round 1 in one launch; weight / bias gradients run beside it on the side stream.
+//
 // Roofline: tensor pipe; per tile 2 * 128 * D * H * 2 flop = 42.5 MFLOP at D = 144, H = 576 -> 2.7 us at the per-SM bf16 rate; M = 8000 gives
 // 63 tiles on 148 SMs, so the module's floor is one tile time.  See DESIGN.md section 4.
 #include "gemm_kernel.cuh"
@@ -42,13 +48,13 @@ struct FfnSmem {
 };
 
 struct FfnFwdArgs {
-  const __nv_bfloat16* x;   // [M, D] module input (also the residual)
-  const float *ln_g, *ln_b;  // [D]
-  const float *b1, *b2;      // [H], [D]
-  __nv_bfloat16* out;        // [M, D]
-  __nv_bfloat16* z;          // [M, H] pre-activation (saved for the backward)
-  __nv_bfloat16* h;          // [M, H] Drop(swish(z)) (saved: A operand of the W2 weight gradient)
-  float *mean, *rstd;        // [M]
+  const __nv_bfloat16* x;   // fwd: [M, D] module input (also the residual)
+  const float *ln_g, *ln_b;  // fwd: [D]
+  const float *b1, *b2;      // fwd: [H], [D]
+  __nv_bfloat16* out;        // fwd: [M, D] module output;  bwd: da [M, D] = gradient of LN(x)
+  __nv_bfloat16* z;          // fwd: [M, H] pre-activation (written, saved for the backward);  bwd: the same tensor (read)
+  __nv_bfloat16* h;          // fwd: [M, H] Drop(swish(z)) (saved: A operand of the W2 weight gradient);  bwd: dz [M, H] (written)
+  float *mean, *rstd;        // fwd: [M]
   int M, H;
   float eps, factor, drop_p;
   const unsigned long long* seed_ptr;
@@ -58,9 +64,9 @@ struct FfnFwdArgs {
 // 16-byte chunk j of row r inside a K-major SWIZZLE_128B tile whose atoms are [128 rows x 128 B]
 __device__ __forceinline__ uint32_t swz_off(int row, int chunk) { return (uint32_t)(chunk >> 3) * (128 * 128) + row * 128 + (((chunk & 7) ^ (row & 7)) << 4); }
 
-template <int D>
+template <int D, int MODE>
 __global__ void __launch_bounds__(kFfnThreads, 1)
-ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                const __grid_constant__ CUtensorMap tmXn, const FfnFwdArgs a) {
   using S = FfnSmem<D>;
   extern __shared__ uint8_t smem_raw[];
@@ -194,7 +200,30 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int row_in_tile = q * 32 + lane;
       const int row = tile * 128 + row_in_tile;
       const bool row_ok = row < M;
-      if (ew < 4) {
+      if (ew < 4 && MODE == 1) {
+        // ---- backward prologue: dy = factor * Drop2'(dout) on this thread's row, in place (what scale_mask_colsum did in its own launch)
+        sm100::mbar_wait(x_full, ti & 1);
+        const uint32_t rowkey2b = has_drop ? dropout_rowkey(seed0 + a.salt2, (unsigned long long)row) : 0u;
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) {
+          uint8_t* p = sA + swz_off(row_in_tile, j);
+          const uint4 u = *reinterpret_cast<const uint4*>(p);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v0 = __uint_as_float(w[e] << 16) * a.factor, v1 = __uint_as_float(w[e] & 0xFFFF0000u) * a.factor;
+            if (has_drop) {
+              const uint32_t hsh = dropout_hash(rowkey2b, (uint32_t)(8 * j + 2 * e));
+              v0 = ((hsh & 0xFFFFu) >= drop_thr) ? v0 * keep_scale : 0.f;
+              v1 = ((hsh >> 16) >= drop_thr) ? v1 * keep_scale : 0.f;
+            }
+            o[e] = pack2(v0, v1);
+          }
+          *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      if (ew < 4 && MODE == 0) {
         // ---- LayerNorm of this thread's row, in place in the swizzled tile (keras LayerNormalization: biased variance, eps inside the sqrt)
         sm100::mbar_wait(x_full, ti & 1);
         uint4 pk[D / 8];
@@ -240,11 +269,13 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
           *reinterpret_cast<uint4*>(sA + swz_off(row_in_tile, j)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
+      }
+      if (ew < 4) {
         sm100::fence_proxy_async();  // generic-proxy writes of the A operand -> visible to tcgen05.mma / TMA (async proxy)
         asm volatile("bar.sync 2, 128;" ::: "memory");
         if (ew == 0 && lane == 0) {
           sm100::mbar_arrive(a_ready);
-          // xn leaves for the backward's weight-gradient GEMM (rows / columns beyond the tensor are clipped by the hardware)
+          // fwd: xn, bwd: dy leave for the weight-gradient GEMMs (rows / columns beyond the tensor are clipped by the hardware)
 #pragma unroll
           for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tmXn, sA + ka * 16384, ka * 64, tile * 128);
           sm100::tma_store_commit();
@@ -269,25 +300,50 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (lane == 0) sm100::mbar_arrive(&acc1_empty[b]);  // acc1[b] may take chunk c + 2
         const int col0 = c * kHC + half * 32;               // first hidden column of this thread's 32
         uint32_t zp[16], hp[16];
+        if constexpr (MODE == 1) {  // the saved pre-activation of this thread's 32 hidden units
+          if (row_ok) {
+            const uint4* zg = reinterpret_cast<const uint4*>(a.z + (size_t)row * H + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = zg[j];
+              zp[4 * j] = u.x, zp[4 * j + 1] = u.y, zp[4 * j + 2] = u.z, zp[4 * j + 3] = u.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) zp[j] = 0u;
+          }
+        }
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           float v[16];
+          if constexpr (MODE == 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b1 + col0 + ci * 16 + 4 * j));
-            v[4 * j] = __uint_as_float(r[ci][4 * j]) + b4.x;
-            v[4 * j + 1] = __uint_as_float(r[ci][4 * j + 1]) + b4.y;
-            v[4 * j + 2] = __uint_as_float(r[ci][4 * j + 2]) + b4.z;
-            v[4 * j + 3] = __uint_as_float(r[ci][4 * j + 3]) + b4.w;
-          }
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b1 + col0 + ci * 16 + 4 * j));
+              v[4 * j] = __uint_as_float(r[ci][4 * j]) + b4.x;
+              v[4 * j + 1] = __uint_as_float(r[ci][4 * j + 1]) + b4.y;
+              v[4 * j + 2] = __uint_as_float(r[ci][4 * j + 2]) + b4.z;
+              v[4 * j + 3] = __uint_as_float(r[ci][4 * j + 3]) + b4.w;
+            }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) zp[ci * 8 + j] = pack2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 8; ++j) zp[ci * 8 + j] = pack2(v[2 * j], v[2 * j + 1]);
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            float s0, s1;
-            sigmoid2_(v[j], v[j + 1], s0, s1);
-            v[j] *= s0;
-            v[j + 1] *= s1;
+            for (int j = 0; j < 16; j += 2) {
+              float s0, s1;
+              sigmoid2_(v[j], v[j + 1], s0, s1);
+              v[j] *= s0;
+              v[j + 1] *= s1;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {  // * d swish / dz at the saved pre-activation
+              const uint32_t zw = zp[ci * 8 + (j >> 1)];
+              const float z0 = __uint_as_float(zw << 16), z1 = __uint_as_float(zw & 0xFFFF0000u);
+              float s0, s1;
+              sigmoid2_(z0, z1, s0, s1);
+              v[j] = __uint_as_float(r[ci][j]) * (s0 * (1.0f + z0 * (1.0f - s0)));
+              v[j + 1] = __uint_as_float(r[ci][j + 1]) * (s1 * (1.0f + z1 * (1.0f - s1)));
+            }
           }
           if (has_drop) {
 #pragma unroll
@@ -305,7 +361,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           uint4* hg = reinterpret_cast<uint4*>(a.h + (size_t)row * H + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            zg[j] = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
+            if constexpr (MODE == 0) zg[j] = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
             hg[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
           }
         }
@@ -329,6 +385,12 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         sm100::tmem_ld_32x32b_x16(tmem_row + S::ACC2_COL + g * 16, r);
         sm100::tmem_ld_wait();
         float v[16];
+        if constexpr (MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (row_ok) store16(a.out + (size_t)row * D + g * 16, v);
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b2 + g * 16 + 4 * j));
@@ -365,18 +427,18 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
-template <int D>
-static int launch_ffn_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmXn, const FfnFwdArgs& a,
+template <int D, int MODE>
+static int launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmXn, const FfnFwdArgs& a,
                           cudaStream_t stream) {
   using S = FfnSmem<D>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(ffn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return TFASR_EXECUTION_FAILED;
+    if (cudaFuncSetAttribute(ffn_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return TFASR_EXECUTION_FAILED;
     attr_set = true;
   }
   const int tiles = (a.M + 127) / 128;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  ffn_fwd_kernel<D><<<grid, kFfnThreads, S::TOTAL, stream>>>(tmX, tmW1, tmW2, tmXn, a);
+  ffn_kernel<D, MODE><<<grid, kFfnThreads, S::TOTAL, stream>>>(tmX, tmW1, tmW2, tmXn, a);
   count_launch();
   return check_launch();
 }
@@ -419,5 +481,31 @@ extern "C" int tfasr_ffn_fwd_bf16(const void* x, const float* ln_g, const float*
   a.seed_ptr = seed_ptr;
   a.salt1 = salt1;
   a.salt2 = salt2;
-  return launch_ffn_fwd<144>(tmX, tmW1, tmW2, tmXn, a, static_cast<cudaStream_t>(stream));
+  return launch_ffn<144, 0>(tmX, tmW1, tmW2, tmXn, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tfasr_ffn_bwd_bf16(const void* dout, const void* z, const void* w2, const void* w1, void* dy, void* dz, void* da, int32_t M, int32_t D,
+                                  int32_t H, float factor, float drop_p, const unsigned long long* seed_ptr, unsigned long long salt1,
+                                  unsigned long long salt2, tfasr_stream_t stream) {
+  if (!dout || !z || !w2 || !w1 || !dy || !dz || !da || M < 0) return TFASR_INVALID_VALUE;
+  if (!tfasr_ffn_supported(D, H) || !(drop_p >= 0.f && drop_p < 1.f)) return TFASR_INVALID_VALUE;
+  if (M == 0) return TFASR_OK;
+  CUtensorMap tmX, tmW1, tmW2, tmXn;
+  bool ok = make_tmap_bf16_2d(&tmX, dout, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
+  ok = ok && make_tmap_bf16_2d(&tmW1, w2, (uint64_t)H, (uint64_t)D, (uint64_t)D, kHC, 64);          // W2 [H, D]: ds = dy . W2^T, rows = hidden units
+  ok = ok && make_tmap_bf16_2d(&tmW2, w1, (uint64_t)D, (uint64_t)H, (uint64_t)H, (uint32_t)D, 64);  // W1 [D, H]: da = dz . W1^T, rows = model dim
+  ok = ok && make_tmap_bf16_2d(&tmXn, dy, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
+  if (!ok) return TFASR_INVALID_VALUE;
+  FfnFwdArgs a{};
+  a.out = static_cast<__nv_bfloat16*>(da);
+  a.z = static_cast<__nv_bfloat16*>(const_cast<void*>(z));
+  a.h = static_cast<__nv_bfloat16*>(dz);
+  a.M = M;
+  a.H = H;
+  a.factor = factor;
+  a.drop_p = drop_p;
+  a.seed_ptr = seed_ptr;
+  a.salt1 = salt1;
+  a.salt2 = salt2;
+  return launch_ffn<144, 1>(tmX, tmW1, tmW2, tmXn, a, static_cast<cudaStream_t>(stream));
 }

@@ -266,6 +266,18 @@ class _FFModuleFn(torch.autograd.Function):
         dout = dout.contiguous()
         M = x.shape[0]
         ks = _splits(M)
+        from . import ops
+
+        if ops.fused_ffn_active() and kernels.ffn_supported(x.shape[1], z.shape[1]) and p1.bias is not None and p2.bias is not None:
+            # the gradient chain dout -> dy -> dz -> da in one launch; everything nobody downstream waits for goes to the side stream
+            dy, dz, da = kernels.ffn_bwd(dout, z, p2.w, p1.w, factor, drop_p, seed, salt, salt + 1)
+            db2, db1 = _grad(p2.bias), _grad(p1.bias)
+            SIDE.run(lambda: kernels.colsum(dy, db2), dy, db2)
+            _wgrad(h, dy, _grad(p2.param), ks)
+            SIDE.run(lambda: kernels.colsum(dz, db1), dz, db1)
+            _wgrad(a, dz, _grad(p1.param), ks)
+            dx = kernels.layernorm_bwd(da, x, mean, rstd, ln_g, _grad(ln_g), _grad(ln_b), dres=dout)
+            return dx, None, None, None, None, None, None, None, None
         # d(out)/d(y): residual factor and the second dropout; bias-2 gradient = column sums
         dy = kernels.scale_mask_colsum(dout, scale=factor, dropout_p=drop_p, seed=seed, salt=salt + 1, colsum=_grad(p2.bias))
         _wgrad(h, dy, _grad(p2.param), ks)  # dW2 += h^T dy

@@ -102,6 +102,21 @@ def ffn_fwd(x, ln_g, ln_b, w1t, b1, w2t, b2, factor, drop_p=0.0, seed=None, salt
     return out, xn, z, h, mean, rstd
 
 
+def ffn_bwd(dout, z, w2, w1, factor, drop_p=0.0, seed=None, salt1=0, salt2=0):
+    """FFModule's gradient chain in one launch.  dout [M, D], z [M, H] (saved), w2 = W2 [H, D], w1 = W1 [D, H] bf16.
+    -> (dy [M, D] = factor * Drop2'(dout), dz [M, H], da [M, D] = gradient of LN(x)), all bf16."""
+    lib = _lib.load()
+    M, D = dout.shape
+    H = z.shape[1]
+    dy = torch.empty_like(dout)
+    dz = torch.empty_like(z)
+    da = torch.empty_like(dout)
+    _lib.check(lib.tfasr_ffn_bwd_bf16(_lib.ptr(dout), _lib.ptr(z), _lib.ptr(w2), _lib.ptr(w1), _lib.ptr(dy), _lib.ptr(dz), _lib.ptr(da), M, D, H, float(factor),
+                                      float(drop_p), _lib.ptr(seed) if drop_p > 0 else None, int(salt1) & (2 ** 64 - 1), int(salt2) & (2 ** 64 - 1),
+                                      _lib.stream_ptr(dout.device)), "tfasr_ffn_bwd_bf16")
+    return dy, dz, da
+
+
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None):
     """-> dx bf16 [M, D] (= LN backward of dy, + dres); dgamma / dbeta (f32 [D]) are accumulated in place."""
     lib = _lib.load()

@@ -47,7 +47,7 @@ def load(asan=False, tsan=False):
               "tfasr_im2col_3x3s2", "tfasr_col2im_3x3s2", "tfasr_dwconv_causal_fwd", "tfasr_dwconv_causal_bwd", "tfasr_joint_tanh_fwd",
               "tfasr_joint_reduce_bwd", "tfasr_adamw_flat_f32", "tfasr_signal_normalize_f32", "tfasr_feature_normalize_f32", "tfasr_specaugment_f32",
               "tfasr_pack_weights", "tfasr_unpack_add", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd", "tfasr_rel_attention_fwd_ld", "tfasr_rel_attention_bwd_ld", "tfasr_lstm_rec_fwd", "tfasr_lstm_rec_bwd",
-              "tfasr_lstm_supported", "tfasr_gemm_bf16", "tfasr_ffn_fwd_bf16", "tfasr_ffn_supported"):
+              "tfasr_lstm_supported", "tfasr_gemm_bf16", "tfasr_ffn_fwd_bf16", "tfasr_ffn_bwd_bf16", "tfasr_ffn_supported"):
         getattr(lib, n).restype = c_i32
     return lib
 
@@ -870,6 +870,42 @@ def check_ffn_fwd(lib, M, H, dropout=0.0, D=144, seed=71):
     close(from_bf16(ob), out, 8e-3, "ffn out")
 
 
+def check_ffn_bwd(lib, M, H, dropout=0.0, D=144, seed=72):
+    """dy = 0.5 Drop2'(dout); dz = (dy W2^T) Drop1' swish'(z); da = dz W1^T in ONE launch, against float64 numpy with the kernel's bf16 rounding
+    points (dy, dz)."""
+    rng = np.random.default_rng(seed)
+    _, _, _, w1, _, w2, _ = _ffn_case(M, H, D, seed)
+    dout = rbf(rng.standard_normal((M, D)))
+    z = rbf(rng.standard_normal((M, H)) * 1.5)
+    dseed, salt1, salt2 = 4321, 9, 10
+    dy = dout.astype(np.float64) * 0.5
+    if dropout > 0:
+        dy = np.where(_dropout_keep(dseed, salt2, M, D, dropout), dy / (1 - dropout), 0.0)
+    dyb = rbf(dy).astype(np.float64)
+    z64 = z.astype(np.float64)
+    sg = 1 / (1 + np.exp(-z64))
+    dz = (dyb @ w2.astype(np.float64).T) * sg * (1 + z64 * (1 - sg))
+    if dropout > 0:
+        dz = np.where(_dropout_keep(dseed, salt1, M, H, dropout), dz / (1 - dropout), 0.0)
+    dzb = rbf(dz).astype(np.float64)
+    da = dzb @ w1.astype(np.float64).T
+    nan16 = lambda shape: heap(np.full(shape, 0x7FC0, np.uint16))  # noqa: E731
+    db, dp_ = heap(to_bf16(dout))
+    zb, zp = heap(to_bf16(z))
+    w2b, w2p = heap(to_bf16(w2))  # W2 [H, D]
+    w1b, w1p = heap(to_bf16(w1))  # W1 [D, H]
+    dyo, dyp = nan16((M, D))
+    dzo, dzp = nan16((M, H))
+    dao, dap = nan16((M, D))
+    sb, sp = heap(np.array([dseed], np.uint64))
+    st = lib.tfasr_ffn_bwd_bf16(dp_, zp, w2p, w1p, dyp, dzp, dap, M, D, H, c_f(0.5), c_f(dropout), sp, ctypes.c_ulonglong(salt1), ctypes.c_ulonglong(salt2),
+                                None)
+    assert st == 0, st
+    close(from_bf16(dyo), dy, 8e-3, "ffn bwd dy")
+    close(from_bf16(dzo), dz, 1e-2, "ffn bwd dz")
+    close(from_bf16(dao), da, 1e-2, "ffn bwd da")
+
+
 CASES = [
     ("rnnt_kat", check_rnnt_kat),
     ("rnnt_ragged", lambda lib: check_rnnt(lib, 4, 13, 8, 12, [13, 9, 5, 13], [7, 4, 0, 1])),
@@ -922,6 +958,8 @@ CASES = [
     ("gemm_rowstats_narrow", lambda lib: check_gemm(lib, 40, 40, 32, f32_out=True, bias=True, rowstats=True)),  # one tile, second slice empty
     ("ffn_fwd_one_tile", lambda lib: check_ffn_fwd(lib, 100, 128)),  # ragged tile, two hidden chunks
     ("ffn_fwd_conformer_s", lambda lib: check_ffn_fwd(lib, 300, 576, dropout=0.1)),  # 3 tiles x 9 chunks: every ring / double-buffer phase wraps
+    ("ffn_bwd_one_tile", lambda lib: check_ffn_bwd(lib, 100, 128)),
+    ("ffn_bwd_conformer_s", lambda lib: check_ffn_bwd(lib, 300, 576, dropout=0.1)),
     ("random_shapes_v1", check_random_shapes_v1),
     ("cluster_lstm", lambda lib: check_cluster_lstm(lib, 3, 4, 64, [4, 2, 3], False)),
     ("cluster_lstm_state", lambda lib: check_cluster_lstm(lib, 2, 3, 128, [3, 3], True)),

@@ -51,6 +51,29 @@ def test_ffn_fwd_matches_unfused_route_and_torch(shape, drop):
         assert (out.float() - ref).abs().max().item() <= 2e-2 * scale
 
 
+@pytest.mark.parametrize("shape", [(8000, 576), (100, 128), (1, 64)])
+@pytest.mark.parametrize("drop", [0.0, 0.1])
+def test_ffn_bwd_chain_matches_unfused_route(shape, drop):
+    """dy / dz / da of the one-launch gradient chain vs scale_mask_colsum + the swish' GEMM + the dgrad GEMM (same rounding points)."""
+    from tensorflowasr_b200 import kernels
+
+    M, H = shape
+    _, _, _, w1, _, w2, _ = _case(M, H, seed=M)
+    torch.manual_seed(M + 1)
+    dout = torch.randn(M, 144, device="cuda").to(torch.bfloat16)
+    z = (1.5 * torch.randn(M, H, device="cuda")).to(torch.bfloat16)
+    seed = torch.tensor([777], dtype=torch.int64, device="cuda")
+    dy, dz, da = kernels.ffn_bwd(dout, z, w2.contiguous(), w1.contiguous(), 0.5, drop, seed, 21, 22)
+    dy_ref = kernels.scale_mask_colsum(dout, scale=0.5, dropout_p=drop, seed=seed, salt=22)
+    dz_ref = kernels.gemm(dy_ref, w2.contiguous(), mul=z, mul_mode="swish_grad", dropout_p=drop, dropout_seed=seed, dropout_salt=21)
+    da_ref = kernels.gemm(dz_ref, w1.contiguous())
+    for name, got, ref in (("dy", dy, dy_ref), ("dz", dz, dz_ref), ("da", da, da_ref)):
+        gf, rf = got.float(), ref.float()
+        assert ((gf == 0) == (rf == 0)).float().mean().item() > 0.9999, name
+        torch.testing.assert_close(gf, rf, rtol=1.6e-2, atol=1e-2 * max(1.0, rf.abs().max().item()), msg=lambda m: f"{name}: {m}")
+        assert (gf != rf).float().mean().item() < 0.03, (name, (gf != rf).float().mean().item())
+
+
 def test_ffn_module_autograd_matches_unfused_module():
     """fused.ff_module with the one-kernel forward vs the same module on the three-launch forward: outputs and every gradient."""
     from tensorflowasr_b200 import fused, ops

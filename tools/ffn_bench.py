@@ -35,8 +35,26 @@ def main():
             y = kernels.gemm(h, w2t, bias=b2, residual=y, residual_scale=0.5, dropout_p=0.1, dropout_seed=seed, dropout_salt=2)
         return y
 
+    w2 = w2t.t().contiguous()  # W2 [H, D]
+    w1 = w1t.t().contiguous()  # W1 [D, H]
+    zz = torch.randn(M, H, device=dev).to(torch.bfloat16)
+
+    def fused_bwd_chain(n):
+        d = x
+        for _ in range(n):
+            d = kernels.ffn_bwd(d, zz, w2, w1, 0.5, 0.1, seed, 1, 2)[2]
+        return d
+
+    def unfused_bwd_chain(n):
+        d = x
+        for _ in range(n):
+            dy = kernels.scale_mask_colsum(d, scale=0.5, dropout_p=0.1, seed=seed, salt=2)
+            dz = kernels.gemm(dy, w2, mul=zz, mul_mode="swish_grad", dropout_p=0.1, dropout_seed=seed, dropout_salt=1)
+            d = kernels.gemm(dz, w1)
+        return d
+
     out = {}
-    for name, fn in (("fused", fused_chain), ("unfused", unfused_chain)):
+    for name, fn in (("fused", fused_chain), ("unfused", unfused_chain), ("fused_bwd", fused_bwd_chain), ("unfused_bwd", unfused_bwd_chain)):
         n = 32
         fn(2)
         torch.cuda.synchronize()
