@@ -185,13 +185,34 @@ def time_cpu_subprocess(batch, steps, warmup, timeout_s=240):
     return None
 
 
+def pick_cpu_batch(steps, warmup, budget_s=170.0):
+    """The CPU arm's batch: the GPU arm's 32 utterances per step when the whole --steps/--warmup run fits `budget_s` on this host, else the
+    largest of {16, 8, 4, 2, 1} that does (the arm must end within a few minutes).  Probe: one step at batch 2 after one warm-up step; the
+    step time of this model grows about linearly with the batch (the lattice and the logits dominate)."""
+    step, _ = cpu_reference_step_fn(2)
+    torch.set_num_threads(min(host_threads(), 32))
+    step()
+    t0 = time.perf_counter()
+    step()
+    per_utt = (time.perf_counter() - t0) / 2
+    n_steps = steps + max(1, warmup) + 4  # + the thread-count probe steps
+    for b in (32, 16, 8, 4, 2, 1):
+        if b * per_utt * n_steps <= budget_s:
+            return b, per_utt
+    return 1, per_utt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = args.cpu_batch
+    batch, how = args.cpu_batch, "as requested"
+    if batch <= 0:
+        batch, per_utt = pick_cpu_batch(args.steps, args.warmup)
+        how = (f"largest batch of 32/16/8/4/2/1 whose whole run fits ~170 s on this host (probe: {per_utt:.2f} s per utterance and step); "
+               "the GPU arm runs 32 per step")
     val, ms, cores = time_cpu(batch, args.steps, args.warmup)
-    sample = (f"{batch} x 10 s utterance(s) per step (full Conformer-S train step, fp32 oracle port), {args.steps} steps after "
+    sample = (f"{batch} x 10 s utterance(s) per step ({how}; full Conformer-S train step, fp32 oracle port), {args.steps} steps after "
               f"{max(1, args.warmup)} warm-up + thread-count probe ({cores} threads chosen of {host_threads()} granted)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -225,6 +246,10 @@ def run_ours(args):
 
 
 def _run_ours(args, real_stdout):
+    if args.config != "conformer":
+        import bench_configs
+
+        return bench_configs.run(args, real_stdout, {"ClockSampler": ClockSampler, "peaks": peaks, "host_threads": host_threads})
     import tensorflowasr_b200 as tfasr
     from tensorflowasr_b200 import _lib, ops
     from tensorflowasr_b200 import dist as tdist
@@ -338,8 +363,9 @@ def _run_ours(args, real_stdout):
                           "ms_per_launch": jg_ms, "share_of_step": jg_ms / ms, "peak_source": pk["_source"], "timing": timing}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ref = time_cpu_subprocess(args.cpu_batch, 3, 1)
-        sample = f"{args.cpu_batch} x 10 s utterance(s) per step (full train step, fp32 oracle port), 3 steps after 1 warm-up + thread-count probe"
+        cb = args.cpu_batch if args.cpu_batch > 0 else 4  # ~20 s of CPU work inside the default run; `--impl reference` sizes its own batch
+        ref = time_cpu_subprocess(cb, 3, 1)
+        sample = f"{cb} x 10 s utterance(s) per step (full train step, fp32 oracle port), 3 steps after 1 warm-up + thread-count probe"
         if ref is None:
             cpu = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample + " -- did not finish within 240 s"}
         else:
@@ -363,8 +389,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-batch", type=int, default=1, help="utterances per CPU step (bounded sample of the workload)")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="utterances per CPU step (bounded sample of the workload); 0 = the largest of 32/16/8/4/2/1 that keeps the run within minutes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="conformer", choices=["conformer", "ds2", "contextnet", "decode"],
+                    help="conformer = BASELINE.json configs[2], the headline (default); ds2 / contextnet / decode = configs[1] / [3] / [4] (bench_configs.py)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -41,7 +41,9 @@ struct FfnSmem {
   static constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES;
   static constexpr int STAGES = 3;
   static constexpr int BAR_BYTES = 32 * 8;
-  static constexpr int TOTAL = A_BYTES + 2 * H_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int H_MAX = 1024;                       // hidden units (b1 staged in SMEM)
+  static constexpr int PARAM_BYTES = (H_MAX + 3 * D) * 4;  // b1 | b2 | ln gamma | ln beta: read once per CTA, not once per chunk from L2
+  static constexpr int TOTAL = A_BYTES + 2 * H_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + PARAM_BYTES + 1024;
   static_assert(TOTAL <= 227 * 1024, "smem budget");
   static constexpr uint32_t TMEM_COLS = 512;               // acc1 x2 (64 columns each) + acc2 (D columns)
   static constexpr uint32_t ACC2_COL = 2 * kHC;
@@ -65,7 +67,7 @@ struct FfnFwdArgs {
 __device__ __forceinline__ uint32_t swz_off(int row, int chunk) { return (uint32_t)(chunk >> 3) * (128 * 128) + row * 128 + (((chunk & 7) ^ (row & 7)) << 4); }
 
 template <int D, int MODE>
-__global__ void __launch_bounds__(kFfnThreads, 1)
+__global__ void __maxnreg__(200)  // 320 threads x 200 registers = 64 000 of the SM's 65 536 (one CTA per SM: shared memory)
 ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                const __grid_constant__ CUtensorMap tmXn, const FfnFwdArgs a) {
   using S = FfnSmem<D>;
@@ -88,6 +90,10 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   uint64_t* h_full = acc1_empty + 2;          // [2]
   uint64_t* h_empty = h_full + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + 2);
+  float* sB1 = reinterpret_cast<float*>(bars + S::BAR_BYTES / 8);  // [H_MAX]
+  float* sB2 = sB1 + S::H_MAX;                                    // [D]
+  float* sG = sB2 + D;                                            // [D]
+  float* sBeta = sG + D;                                          // [D]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = a.M, H = a.H;
@@ -114,6 +120,14 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       sm100::mbar_init(&h_empty[i], 1);
     }
     sm100::fence_barrier_init();
+  }
+  if constexpr (MODE == 0) {
+    for (int i = threadIdx.x; i < a.H; i += kFfnThreads) sB1[i] = a.b1[i];
+    for (int i = threadIdx.x; i < D; i += kFfnThreads) {
+      sB2[i] = a.b2[i];
+      sG[i] = a.ln_g[i];
+      sBeta[i] = a.ln_b[i];
+    }
   }
   if (warp == 1) sm100::tmem_alloc(tmem_slot, S::TMEM_COLS);
   sm100::tc_fence_before();
@@ -255,8 +269,8 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         }
 #pragma unroll
         for (int j = 0; j < D / 8; ++j) {
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.ln_g + 8 * j)), g1 = __ldg(reinterpret_cast<const float4*>(a.ln_g + 8 * j + 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.ln_b + 8 * j)), b1v = __ldg(reinterpret_cast<const float4*>(a.ln_b + 8 * j + 4));
+          const float4 g0 = *reinterpret_cast<const float4*>(sG + 8 * j), g1 = *reinterpret_cast<const float4*>(sG + 8 * j + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(sBeta + 8 * j), b1v = *reinterpret_cast<const float4*>(sBeta + 8 * j + 4);
           const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
           const uint32_t w[4] = {pk[j].x, pk[j].y, pk[j].z, pk[j].w};
@@ -289,6 +303,21 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int c = 0; c < nch; ++c, ++it) {
         const uint32_t b = it & 1, bph = (it >> 1) & 1;
+        const int col0 = c * kHC + half * 32;               // first hidden column of this thread's 32
+        uint32_t zp[16], hp[16];
+        if constexpr (MODE == 1) {  // the saved pre-activation of this thread's 32 hidden units: issued BEFORE the wait for the accumulator
+          if (row_ok) {
+            const uint4* zg = reinterpret_cast<const uint4*>(a.z + (size_t)row * H + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = ld_stream_u4(zg + j);
+              zp[4 * j] = u.x, zp[4 * j + 1] = u.y, zp[4 * j + 2] = u.z, zp[4 * j + 3] = u.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) zp[j] = 0u;
+          }
+        }
         sm100::mbar_wait(&acc1_full[b], bph);
         sm100::tc_fence_after();
         uint32_t r[2][16];
@@ -298,28 +327,13 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         sm100::tc_fence_before();
         __syncwarp();
         if (lane == 0) sm100::mbar_arrive(&acc1_empty[b]);  // acc1[b] may take chunk c + 2
-        const int col0 = c * kHC + half * 32;               // first hidden column of this thread's 32
-        uint32_t zp[16], hp[16];
-        if constexpr (MODE == 1) {  // the saved pre-activation of this thread's 32 hidden units
-          if (row_ok) {
-            const uint4* zg = reinterpret_cast<const uint4*>(a.z + (size_t)row * H + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = zg[j];
-              zp[4 * j] = u.x, zp[4 * j + 1] = u.y, zp[4 * j + 2] = u.z, zp[4 * j + 3] = u.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) zp[j] = 0u;
-          }
-        }
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           float v[16];
           if constexpr (MODE == 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b1 + col0 + ci * 16 + 4 * j));
+              const float4 b4 = *reinterpret_cast<const float4*>(sB1 + col0 + ci * 16 + 4 * j);
               v[4 * j] = __uint_as_float(r[ci][4 * j]) + b4.x;
               v[4 * j + 1] = __uint_as_float(r[ci][4 * j + 1]) + b4.y;
               v[4 * j + 2] = __uint_as_float(r[ci][4 * j + 2]) + b4.z;
@@ -376,43 +390,61 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       }
       // ---- output: acc2 -> + b2 -> dropout -> residual
       [[maybe_unused]] const uint32_t rowkey2 = has_drop ? dropout_rowkey(seed0 + a.salt2, (unsigned long long)row) : 0u;
+      constexpr int NG = D / 16, G_MID = (NG + 1) / 2;
+      const int g0 = half ? G_MID : 0, ng = half ? NG - G_MID : G_MID;
+      // the residual x of this thread's columns is requested before the wait for the accumulator (its latency hides behind GEMM 2)
+      [[maybe_unused]] uint4 xres[G_MID][2];
+      if constexpr (MODE == 0) {
+#pragma unroll
+        for (int gi = 0; gi < G_MID; ++gi)
+          if (gi < ng && row_ok) {
+            const uint4* xp = reinterpret_cast<const uint4*>(a.x + (size_t)row * D + (g0 + gi) * 16);
+            xres[gi][0] = ld_stream_u4(xp);
+            xres[gi][1] = ld_stream_u4(xp + 1);
+          }
+      }
       sm100::mbar_wait(acc2_full, ti & 1);
       sm100::tc_fence_after();
-      constexpr int NG = D / 16, G_MID = (NG + 1) / 2;
-      const int g0 = half ? G_MID : 0, g1 = half ? NG : G_MID;
-      for (int g = g0; g < g1; ++g) {
-        uint32_t r[16];
-        sm100::tmem_ld_32x32b_x16(tmem_row + S::ACC2_COL + g * 16, r);
-        sm100::tmem_ld_wait();
+      uint32_t racc[G_MID][16];
+#pragma unroll
+      for (int gi = 0; gi < G_MID; ++gi)
+        if (gi < ng) sm100::tmem_ld_32x32b_x16(tmem_row + S::ACC2_COL + (g0 + gi) * 16, racc[gi]);
+      sm100::tmem_ld_wait();
+#pragma unroll
+      for (int gi = 0; gi < G_MID; ++gi) {
+        if (gi >= ng) break;
+        const int g = g0 + gi;
         float v[16];
         if constexpr (MODE == 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(racc[gi][j]);
           if (row_ok) store16(a.out + (size_t)row * D + g * 16, v);
-          continue;
-        }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b2 + g * 16 + 4 * j));
-          v[4 * j] = __uint_as_float(r[4 * j]) + b4.x;
-          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
-          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
-        }
-        if (has_drop) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const uint32_t hsh = dropout_hash(rowkey2, (uint32_t)(g * 16 + j));
-            v[j] = ((hsh & 0xFFFFu) >= drop_thr) ? v[j] * keep_scale : 0.f;
-            v[j + 1] = ((hsh >> 16) >= drop_thr) ? v[j + 1] * keep_scale : 0.f;
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sB2 + g * 16 + 4 * j);
+            v[4 * j] = __uint_as_float(racc[gi][4 * j]) + b4.x;
+            v[4 * j + 1] = __uint_as_float(racc[gi][4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(racc[gi][4 * j + 2]) + b4.z;
+            v[4 * j + 3] = __uint_as_float(racc[gi][4 * j + 3]) + b4.w;
           }
-        }
-        if (row_ok) {
-          float xr[16];
-          load16(a.x + (size_t)row * D + g * 16, xr);
+          if (has_drop) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = xr[j] + a.factor * v[j];
-          store16(a.out + (size_t)row * D + g * 16, v);
+            for (int j = 0; j < 16; j += 2) {
+              const uint32_t hsh = dropout_hash(rowkey2, (uint32_t)(g * 16 + j));
+              v[j] = ((hsh & 0xFFFFu) >= drop_thr) ? v[j] * keep_scale : 0.f;
+              v[j + 1] = ((hsh >> 16) >= drop_thr) ? v[j + 1] * keep_scale : 0.f;
+            }
+          }
+          if (row_ok) {
+            const uint32_t w[8] = {xres[gi][0].x, xres[gi][0].y, xres[gi][0].z, xres[gi][0].w, xres[gi][1].x, xres[gi][1].y, xres[gi][1].z, xres[gi][1].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[2 * j] = __uint_as_float(w[j] << 16) + a.factor * v[2 * j];
+              v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u) + a.factor * v[2 * j + 1];
+            }
+            store16(a.out + (size_t)row * D + g * 16, v);
+          }
         }
       }
       sm100::tc_fence_before();
@@ -447,7 +479,7 @@ static int launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUt
 
 using namespace tfasr;
 
-extern "C" int tfasr_ffn_supported(int32_t D, int32_t H) { return (D == 144 && H >= 64 && H % 64 == 0) ? 1 : 0; }
+extern "C" int tfasr_ffn_supported(int32_t D, int32_t H) { return (D == 144 && H >= 64 && H % 64 == 0 && H <= FfnSmem<144>::H_MAX) ? 1 : 0; }
 
 extern "C" int tfasr_ffn_fwd_bf16(const void* x, const float* ln_g, const float* ln_b, const void* w1t, const float* b1, const void* w2t,
                                   const float* b2, void* out, void* xn, void* z, void* h, float* mean, float* rstd, int32_t M, int32_t D, int32_t H,

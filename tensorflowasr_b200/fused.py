@@ -54,6 +54,16 @@ class SideStream:
 
         return self.enabled and t.is_cuda and not _lib.EMULATED and not _lib.TIMERS.on
 
+    def branch_stream(self, t):
+        """A second side stream for an independent branch of the step (the prediction network), or None when side streams are off."""
+        import os
+
+        if not self.active(t) or os.environ.get("TFASR_SIDE_PRED", "1") != "1":
+            return None
+        if getattr(self, "_branch", None) is None or self._branch.device != t.device:
+            self._branch = torch.cuda.Stream(device=t.device)
+        return self._branch
+
     def run(self, fn, *tensors):
         if not tensors or not self.active(tensors[0]):
             fn()

@@ -134,9 +134,21 @@ class Transducer(BaseModel):
 
     # ------------------------------------------------------------------ reference `call`
     def _branches(self, inputs: schemas.TrainInput, training):
+        # The prediction network (embedding -> LSTM -> LN: ~65 dependent label steps) does not depend on the encoder until the joint: on the
+        # GPU it runs on a second stream — a parallel branch of the captured step graph — and autograd runs its backward there as well.
+        side = fused.SIDE.branch_stream(inputs.inputs)
+        if side is not None:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                pred, *_ = self.predict_net((inputs.predictions, inputs.predictions_length), training=training)
         features, features_length = self.feature_extraction((inputs.inputs, inputs.inputs_length), training=training)
         enc, logits_length, *_ = self.encoder((features, features_length), training=training)
-        pred, *_ = self.predict_net((inputs.predictions, inputs.predictions_length), training=training)
+        if side is not None:
+            main.wait_stream(side)
+            pred.record_stream(main)  # allocated on the side stream, consumed by the joint on the main stream
+        else:
+            pred, *_ = self.predict_net((inputs.predictions, inputs.predictions_length), training=training)
         return enc, logits_length, pred
 
     def call(self, inputs: schemas.TrainInput, training=False):

@@ -100,6 +100,7 @@ def convert(src: str, name: str = "?") -> str:
                 re.finditer(r"__cluster_dims__\(([^,)]+)[^)]*\)\s*(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(", src)}
     src = re.sub(r'asm\("tanh\.approx\.f32 %0, %1;"\s*:\s*"=f"\((\w+)\)\s*:\s*"f"\(([^;]+)\)\);', r"\1 = tanhf(\2);", src)
     # ---- the tcgen05 GEMM (gemm_kernel.cuh / gemm.cu / gemm_inst_*.cu): sm100.cuh -> emu_sm100.h, the few other PTX lines by hand
+    src = re.sub(r"__maxnreg__\(\d+\)", "", src)  # a register budget means nothing on the emulator
     src = src.replace('#include "sm100.cuh"', '#include "emu_sm100.h"')
     src = re.sub(r'asm volatile\("bar\.sync (\d+), (\d+);" ::: "memory"\);', r"emu::named_barrier_sync(\1, \2);", src)
     src = src.replace('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));', "t = 0;")

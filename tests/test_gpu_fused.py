@@ -152,8 +152,10 @@ def test_cuda_graph_train_step_matches_eager():
             for _ in range(6):
                 ls.append(model.train_step(data)["loss"].mean().item())
             out[use_graph] = ls
-        # the graph path runs 3 extra warm-up steps before capture; compare the trajectories step-aligned
-        assert out[True][0] == pytest.approx(out[False][3], rel=5e-2)
+        # graph mode is step-equivalent to eager mode: the warm-up steps before capture are undone (parameters, Adam moments and step
+        # count, BatchNorm moving statistics, schedule position), so the trajectories agree step by step (bf16 atomics: not bit for bit)
+        for a, b in zip(out[True], out[False]):
+            assert a == pytest.approx(b, rel=2e-2), (out[True], out[False])
         assert out[True][-1] < out[True][0] and out[False][-1] < out[False][0]
     finally:
         ops.set_precision("fp32")
