@@ -62,7 +62,7 @@ def _build(name, dev, world):
                     workload="BASELINE.json configs[1]: DeepSpeech2 CTC (base.yml.j2: 2 conv + 5 x BiLSTM(512) + FC 1024), synthetic 16 kHz batch=8 x 10 s",
                     extra={"labels_per_utterance": L, "vocab": V})
     elif name == "contextnet":
-        V, B, S, U = 1000, 64, 15, 96
+        V, B, S, U = 1000, 64, 15, 64
         cfg = tfasr.contextnet_config(vocab_size=V, alpha=1.0)
         model = tfasr.ContextNet(**cfg, seed=42).to(dev)
 

@@ -236,6 +236,13 @@ int tfasr_rel_attention_fwd(const void* qkv, int32_t ld_qkv, const void* pos, co
 int tfasr_rel_attention_bwd(const void* qkv, int32_t ld_qkv, const void* pos, const float* ubias, const float* vbias, const int32_t* length,
                             int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, const void* probs, const void* dctx,
                             const void* ctx, void* ds_ws, void* dqkv, void* dpos, float* du, float* dvb, tfasr_stream_t stream);
+/* Forward on tcgen05 (csrc/attention_tc.cu: TMA-fed operands, S / BD / context accumulators in TMEM, rel-shift through a per-warp SMEM
+ * transpose); same contract and outputs as tfasr_rel_attention_fwd_ld, for the shapes tfasr_rel_attention_tc_supported accepts (even head
+ * dimension <= 64, 16-byte aligned row pitches); TFASR_INVALID_VALUE otherwise.  Any T (keys walked in chunks of 64, queries in tiles of 128). */
+int tfasr_rel_attention_tc_supported(int32_t T, int32_t N, int32_t H, int32_t ld_qkv, int32_t ld_pos);
+int tfasr_rel_attention_fwd_tc(const void* qkv, int32_t ld_qkv, const void* pos, int32_t ld_pos, const float* ubias, const float* vbias,
+                               const int32_t* length, int32_t B, int32_t T, int32_t N, int32_t H, int32_t chunk, int32_t history, void* ctx,
+                               void* probs, tfasr_stream_t stream);
 /* The same with explicit row strides (elements) for pos and dpos: every Conformer block projects the SAME relative position table
  * (conformer.py:672-701 computes relpe once and hands it to all blocks), so the position projections of all blocks can be ONE GEMM
  * [B*(2T-1), D] x [D, blocks*N*H]; block b then reads its N*H-wide column slice (pos = base + b*N*H, ld_pos = blocks*N*H) and writes its

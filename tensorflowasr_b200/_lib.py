@@ -107,6 +107,9 @@ SIGNATURES = {
                                           c_int32, c_void_p, c_void_p, c_void_p]),
     "tfasr_rel_attention_bwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                           c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tfasr_rel_attention_tc_supported": (c_int32, [c_int32] * 5),
+    "tfasr_rel_attention_fwd_tc": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                             c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "tfasr_rel_attention_fwd_ld": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                              c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "tfasr_rel_attention_bwd_ld": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,

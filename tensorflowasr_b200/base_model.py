@@ -226,11 +226,12 @@ class BaseModel(nn.Module):
     def _graph_train_step(self, data: schemas.TrainData):
         flat = [data.inputs.inputs, data.inputs.inputs_length, data.inputs.predictions, data.inputs.predictions_length,
                 data.labels.labels, data.labels.labels_length]
-        key = tuple((tuple(t.shape), t.dtype) for t in flat)
+        key = tuple(None if t is None else (tuple(t.shape), t.dtype) for t in flat)  # CTC models carry no predictions
         if self._graph is None or self._graph["key"] != key:
-            static = [torch.empty_like(t) for t in flat]
+            static = [None if t is None else torch.empty_like(t) for t in flat]
             for s, t in zip(static, flat):
-                s.copy_(t)
+                if t is not None:
+                    s.copy_(t)
             sdata = schemas.TrainData(schemas.TrainInput(*static[:4]), schemas.TrainLabel(*static[4:]))
             # warm-up on a side stream (allocator, cuDNN / cuBLAS handles, lazily built tables), then capture.  The warm-up steps are
             # real steps on the first batch: everything they change (parameters, Adam moments and step count, BatchNorm moving
@@ -255,7 +256,7 @@ class BaseModel(nn.Module):
             self._graph = {"key": key, "graph": graph, "static": static, "out": out}
         g = self._graph
         for s, t in zip(g["static"], flat):
-            if s.data_ptr() != t.data_ptr():
+            if t is not None and s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
         self._advance_schedule()
         g["graph"].replay()

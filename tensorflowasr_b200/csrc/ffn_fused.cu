@@ -63,11 +63,8 @@ struct FfnFwdArgs {
   unsigned long long salt1, salt2;
 };
 
-// 16-byte chunk j of row r inside a K-major SWIZZLE_128B tile whose atoms are [128 rows x 128 B]
-__device__ __forceinline__ uint32_t swz_off(int row, int chunk) { return (uint32_t)(chunk >> 3) * (128 * 128) + row * 128 + (((chunk & 7) ^ (row & 7)) << 4); }
-
 template <int D, int MODE>
-__global__ void __maxnreg__(200)  // 320 threads x 200 registers = 64 000 of the SM's 65 536 (one CTA per SM: shared memory)
+__global__ void __launch_bounds__(kFfnThreads, 1)  // (a 200-register budget does not launch with 320 threads: per-warp allocation granularity)
 ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                const __grid_constant__ CUtensorMap tmXn, const FfnFwdArgs a) {
   using S = FfnSmem<D>;

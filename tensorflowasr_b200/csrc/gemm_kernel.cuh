@@ -135,6 +135,10 @@ __device__ __forceinline__ void store16(__nv_bfloat16* p, const float* f) {
   *reinterpret_cast<uint4*>(p + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
+// byte offset of 16-byte chunk `chunk` (8 bf16) of row `row` inside a K-major SWIZZLE_128B operand tile whose 64-column atoms are
+// [128 rows x 128 B] (what TMA writes for a [128 x 64] bf16 box, and what the UMMA descriptors of this library read)
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk) { return (uint32_t)(chunk >> 3) * (128 * 128) + row * 128 + (((chunk & 7) ^ (row & 7)) << 4); }
+
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&t);

@@ -222,7 +222,21 @@ def fused_ffn_active() -> bool:
     return _FUSED_FFN
 
 
-_SWITCHES = ("_FUSED_FFN", "_FUSED", "_FUSED_SEQ", "_DWCONV_WGRAD_V2", "_JOINT_REDUCE_V2", "_IM2COL_V2", "_JOINT_V2", "_RNNT_GRAD_V2", "_CONV1_V2", "_POS_BATCHED",
+_ATTENTION_TC = _os.environ.get("TFASR_ATTENTION_TC", "1") == "1"
+
+
+def set_attention_tc(flag: bool):
+    """Relative-position attention forward on tcgen05 (csrc/attention_tc.cu: TMA-fed operands, TMEM accumulators) instead of the mma.sync
+    generation (csrc/attention.cu), which stays the backward and the fallback for odd head sizes."""
+    global _ATTENTION_TC
+    _ATTENTION_TC = bool(flag)
+
+
+def attention_tc_active() -> bool:
+    return _ATTENTION_TC
+
+
+_SWITCHES = ("_FUSED_FFN", "_ATTENTION_TC", "_FUSED", "_FUSED_SEQ", "_DWCONV_WGRAD_V2", "_JOINT_REDUCE_V2", "_IM2COL_V2", "_JOINT_V2", "_RNNT_GRAD_V2", "_CONV1_V2", "_POS_BATCHED",
              "_PEER_BN", "_FUSED_LSE", "_PERSISTENT_DECODE")
 
 

@@ -16,7 +16,7 @@ SOURCES = ["seqconv.cu", "decode.cu", "rnnt_combine.cu", "conv1.cu", "rnnt_grad_
 
 
 V1_SOURCES = ["rnnt_loss.cu", "ctc_loss.cu", "logmel.cu", "fused_rows.cu", "conv_bn.cu", "dwconv.cu", "joint.cu", "param_ops.cu", "specaugment.cu", "attention.cu", "lstm.cu", "gemm.cu", "gemm_inst_64.cu", "gemm_inst_128.cu",
-              "gemm_inst_160.cu", "gemm_inst_192.cu", "gemm_inst_256.cu", "ffn_fused.cu"]
+              "gemm_inst_160.cu", "gemm_inst_192.cu", "gemm_inst_256.cu", "ffn_fused.cu", "attention_tc.cu"]
 V1_HEADERS = ["gemm_kernel.cuh"]  # converted next to the sources that include them
 # first-generation files (written against common.cuh, <<<>>> launches): converted by cu2emu.py into build/emu/gen/*.cpp
 

@@ -47,7 +47,8 @@ def load(asan=False, tsan=False):
               "tfasr_im2col_3x3s2", "tfasr_col2im_3x3s2", "tfasr_dwconv_causal_fwd", "tfasr_dwconv_causal_bwd", "tfasr_joint_tanh_fwd",
               "tfasr_joint_reduce_bwd", "tfasr_adamw_flat_f32", "tfasr_signal_normalize_f32", "tfasr_feature_normalize_f32", "tfasr_specaugment_f32",
               "tfasr_pack_weights", "tfasr_unpack_add", "tfasr_rel_attention_fwd", "tfasr_rel_attention_bwd", "tfasr_rel_attention_fwd_ld", "tfasr_rel_attention_bwd_ld", "tfasr_lstm_rec_fwd", "tfasr_lstm_rec_bwd",
-              "tfasr_lstm_supported", "tfasr_gemm_bf16", "tfasr_ffn_fwd_bf16", "tfasr_ffn_bwd_bf16", "tfasr_ffn_supported"):
+              "tfasr_lstm_supported", "tfasr_gemm_bf16", "tfasr_ffn_fwd_bf16", "tfasr_ffn_bwd_bf16", "tfasr_ffn_supported", "tfasr_rel_attention_fwd_tc",
+              "tfasr_rel_attention_tc_supported"):
         getattr(lib, n).restype = c_i32
     return lib
 
@@ -489,7 +490,7 @@ def _att_allowed(T, length, chunk, history):
     return ok
 
 
-def check_rel_attention(lib, B, T, N, H, lengths, chunk=0, history=0, seed=32, blocks=0, blk=0):
+def check_rel_attention(lib, B, T, N, H, lengths, chunk=0, history=0, seed=32, blocks=0, blk=0, tc=False):
     """MultiHeadRelativeAttention._compute_attention (multihead_attention.py:543-582) with rel_left_shift as out[t, j] = posattn[t, T-1-t+j]
     (:27-64), the masked softmax (general.py:30-41) and the streaming mask (:104-143): forward and the full backward of the fused kernels —
     the mma.sync path when T <= 256 and H % 4 == 0, the FP32 kernels otherwise — against float64 numpy on the valid query rows.
@@ -552,7 +553,10 @@ def check_rel_attention(lib, B, T, N, H, lengths, chunk=0, history=0, seed=32, b
     lb, lp = heap(ln)
     cb, cp = heap(np.zeros((B * T, NH), np.uint16))
     prb, prp = heap(np.zeros((B, N, T, T), np.uint16))
-    if blocks:
+    if tc:  # forward on the tcgen05 kernel (attention_tc.cu); the backward below then runs on ITS probabilities
+        assert lib.tfasr_rel_attention_tc_supported(T, N, H, 3 * NH, W) == 1
+        st = lib.tfasr_rel_attention_fwd_tc(qp, 3 * NH, pp_, W, ubp, vbp, lp, B, T, N, H, chunk, history, cp, prp, None)
+    elif blocks:
         st = lib.tfasr_rel_attention_fwd_ld(qp, 3 * NH, pp_, W, ubp, vbp, lp, B, T, N, H, chunk, history, cp, prp, None)
     else:
         st = lib.tfasr_rel_attention_fwd(qp, 3 * NH, pp_, ubp, vbp, lp, B, T, N, H, chunk, history, cp, prp, None)
@@ -944,6 +948,10 @@ CASES = [
     ("rel_attention_fp32", lambda lib: check_rel_attention(lib, 2, 11, 2, 10, [11, 6])),
     ("rel_attention_mma_slice", lambda lib: check_rel_attention(lib, 1, 24, 2, 36, [19], blocks=3, blk=1)),  # column slice of the all-blocks projection
     ("rel_attention_fp32_slice", lambda lib: check_rel_attention(lib, 1, 11, 2, 10, [9], blocks=2, blk=1)),  # T < 16, H % 4 != 0: the FP32 kernels
+    ("rel_attention_tc", lambda lib: check_rel_attention(lib, 2, 40, 2, 36, [40, 23], tc=True)),  # tcgen05 forward, Conformer-S head size, one key chunk
+    ("rel_attention_tc_two_tiles", lambda lib: check_rel_attention(lib, 1, 150, 2, 36, [131], tc=True)),  # 2 query tiles x 3 key chunks
+    ("rel_attention_tc_streaming", lambda lib: check_rel_attention(lib, 1, 200, 1, 64, [200], chunk=16, history=32, tc=True)),  # H = 64, chunk skipping
+    ("rel_attention_tc_slice", lambda lib: check_rel_attention(lib, 1, 70, 2, 36, [61], blocks=3, blk=1, tc=True)),  # column slice of the all-blocks projection
     ("gemm_plain", lambda lib: check_gemm(lib, 200, 72, 136)),  # one ragged M tile, N < tile width, K not a multiple of 64
     ("gemm_f32_bias", lambda lib: check_gemm(lib, 129, 1000, 320, f32_out=True, bias=True)),  # the joint's shape class: 4 tiles of 256 columns
     ("gemm_swish_aux", lambda lib: check_gemm(lib, 150, 160, 64, bias=True, act=1, aux=True)),  # FFN-1: tile width 160
