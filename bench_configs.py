@@ -141,6 +141,8 @@ def run(args, real_stdout, shared):
     if meta["train"]:
         model.compile(optimizer=tfasr.make_optimizer(model, learning_rate=1e-4, beta_1=0.9, beta_2=0.98, epsilon=1e-9, weight_decay=1e-6))
         model.train()
+        if args.config == "ds2":
+            args.no_graph = True  # the 512-unit BiLSTM runs on cuDNN's packed-sequence path, whose length bookkeeping syncs with the host
         model.enable_cuda_graph(not args.no_graph)
 
         def step_resident():

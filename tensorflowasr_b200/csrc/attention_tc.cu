@@ -152,7 +152,9 @@ rel_attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
     if (lane == 0) {
       constexpr uint32_t idesc_s = sm100::make_idesc_bf16_f32(128, kKC, 0, 0);
       constexpr uint32_t idesc_bd = sm100::make_idesc_bf16_f32(128, kPW, 0, 0);
-      constexpr uint32_t idesc_o = sm100::make_idesc_bf16_f32(128, HP, 0, 1);  // B = V chunk, MN-major
+      // B = V chunk, MN-major.  N = 64 whatever the head size: an MN-major operand is addressed in whole 64-element swizzle atoms (N = 48
+      // raised an illegal-instruction exception on the B200); columns beyond the head are never read back from TMEM.
+      constexpr uint32_t idesc_o = sm100::make_idesc_bf16_f32(128, 64, 0, 1);
       const uint32_t qu = sm100::smem_u32(sQu), qv = sm100::smem_u32(sQv);
       sm100::mbar_wait(q_ready, 0);
       sm100::tc_fence_after();

@@ -8,16 +8,19 @@
 //         store (the weight-gradient GEMM of the backward wants it)
 //   loop over the hidden dimension in chunks of 64:
 //     G1  tcgen05.mma 128 x 64 x 16 (x9):   acc1[c & 1] (TMEM, 64 columns) = xn . W1[:, chunk]
-//     E1  8 epilogue warps: tcgen05.ld -> + b1 -> z (saved pre-activation) -> swish -> dropout -> bf16 h chunk: written to global (saved for the
-//         backward) AND into SMEM as the next A operand — the [128 x 576] hidden activation never makes the HBM round trip before GEMM 2
+//     E1  8 epilogue warps: tcgen05.ld -> + b1 -> z (saved pre-activation) -> swish -> dropout -> bf16 h chunk, written into SMEM as the next
+//         A operand — the [128 x 576] hidden activation never makes the HBM round trip before GEMM 2 — and, from the same SMEM tiles, to
+//         global by TMA stores (z, h: saved for the backward)
 //     G2  tcgen05.mma 128 x D x 16 (x4):    acc2 (TMEM, D columns) += h_chunk . W2[chunk, :]
-//   E2    acc2 -> + b2 -> dropout -> x + factor * (.) -> bf16 out
-// Weight chunks (W1^T rows [64 x D], W2^T columns [D x 64]: 42 KB per chunk) stream through a 3-stage TMA ring from L2, where the 332 KB of
-// module weights stay resident.  G1 of chunk c+1 overlaps E1 of chunk c (double-buffered acc1 and h).
+//   E2    acc2 -> + b2 -> dropout -> x + factor * (.) -> bf16 out -> SMEM -> TMA store
+// Weight chunks (W1^T rows [64 x D], W2^T columns [D x 64]: 42 KB per chunk) stream through a 2-stage TMA ring from L2, where the 332 KB of
+// module weights stay resident.  G1 of chunk c+1 overlaps E1 of chunk c (double-buffered acc1, h and z tiles).
+// Every global access of the hot loop is a TMA transfer: thread-per-row 16-byte accesses to [M, 576] rows (32 cache lines per warp
+// instruction) made the first version of this kernel slower than the three launches it replaces.
 //
 // Backward (MODE 1) is the same two-GEMM skeleton run on the gradient chain of FFModule's backward:
 //   TMA   dout tile -> SMEM;  prologue: dy = factor * Drop2'(dout) in place (the A operand; dy also leaves through the TMA store for dW2 / db2)
-//   G1    acc1 = dy . W2[chunk, :]^T            E1: dz = acc1 * Drop1' * swish'(z) -> global (for dW1 / db1) and SMEM
+//   G1    acc1 = dy . W2[chunk, :]^T            E1: dz = acc1 * Drop1' * swish'(z) (z chunk by TMA, with the weights) -> SMEM -> TMA store
 //   G2    acc2 += dz_chunk . W1[:, chunk]^T     E2: da = acc2 -> bf16 (LayerNorm's input gradient; the LayerNorm backward kernel follows)
 // i.e. scale_mask_colsum + the swish' GEMM + the dgrad GEMM of round 1 in one launch; weight / bias gradients run beside it on the side stream.
 //
@@ -27,7 +30,7 @@
 
 namespace tfasr {
 
-constexpr int kFfnThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue / LayerNorm
+constexpr int kFfnThreads = 320;  // warp 0 TMA, warp 1 MMA (+ the chunk stores), warps 2-9 epilogue / LayerNorm
 constexpr int kHC = 64;           // hidden-dimension chunk = one 128B-swizzle atom of K for GEMM 2
 
 template <int D>
@@ -38,24 +41,23 @@ struct FfnSmem {
   static constexpr int H_BYTES = 128 * 128;                // one atom [128 x 64]
   static constexpr int W1_BYTES = KA * kHC * 128;          // W1^T chunk: [64 hidden rows x D k]
   static constexpr int W2_BYTES = ((D * 128 + 1023) / 1024) * 1024;  // W2^T chunk: [D rows x 64 k]
-  static constexpr int STAGE_BYTES = W1_BYTES + W2_BYTES;
-  static constexpr int STAGES = 3;
+  static constexpr int W_BYTES = W1_BYTES + W2_BYTES;
+  static constexpr int STAGES = 2;
+  // forward: two z staging tiles + weight stages; backward: every stage also carries the z chunk (same total)
+  static constexpr int REST_BYTES = STAGES * (W_BYTES + H_BYTES);
   static constexpr int BAR_BYTES = 32 * 8;
   static constexpr int H_MAX = 1024;                       // hidden units (b1 staged in SMEM)
   static constexpr int PARAM_BYTES = (H_MAX + 3 * D) * 4;  // b1 | b2 | ln gamma | ln beta: read once per CTA, not once per chunk from L2
-  static constexpr int TOTAL = A_BYTES + 2 * H_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + PARAM_BYTES + 1024;
+  static constexpr int TOTAL = A_BYTES + 2 * H_BYTES + REST_BYTES + BAR_BYTES + PARAM_BYTES + 1024;
   static_assert(TOTAL <= 227 * 1024, "smem budget");
   static constexpr uint32_t TMEM_COLS = 512;               // acc1 x2 (64 columns each) + acc2 (D columns)
   static constexpr uint32_t ACC2_COL = 2 * kHC;
 };
 
-struct FfnFwdArgs {
-  const __nv_bfloat16* x;   // fwd: [M, D] module input (also the residual)
+struct FfnArgs {
+  const __nv_bfloat16* x;    // fwd: [M, D] module input (the residual is re-read from here)
   const float *ln_g, *ln_b;  // fwd: [D]
   const float *b1, *b2;      // fwd: [H], [D]
-  __nv_bfloat16* out;        // fwd: [M, D] module output;  bwd: da [M, D] = gradient of LN(x)
-  __nv_bfloat16* z;          // fwd: [M, H] pre-activation (written, saved for the backward);  bwd: the same tensor (read)
-  __nv_bfloat16* h;          // fwd: [M, H] Drop(swish(z)) (saved: A operand of the W2 weight gradient);  bwd: dz [M, H] (written)
   float *mean, *rstd;        // fwd: [M]
   int M, H;
   float eps, factor, drop_p;
@@ -63,18 +65,31 @@ struct FfnFwdArgs {
   unsigned long long salt1, salt2;
 };
 
+struct FfnMaps {
+  CUtensorMap x;     // load : fwd x, bwd dout            [M, D], box [128 x 64]
+  CUtensorMap w1;    // load : fwd W1^T [H, D], bwd W2 [H, D]          box [64 x 64]
+  CUtensorMap w2;    // load : fwd W2^T [D, H], bwd W1 [D, H]          box [D x 64]
+  CUtensorMap xn;    // store: fwd LN(x), bwd dy         [M, D], box [128 x 64]
+  CUtensorMap h;     // store: fwd h, bwd dz             [M, H], box [128 x 64]
+  CUtensorMap z;     // fwd store / bwd load: z          [M, H], box [128 x 64]
+  CUtensorMap out;   // store: fwd out, bwd da           [M, D], box [128 x 64]
+};
+
 template <int D, int MODE>
 __global__ void __launch_bounds__(kFfnThreads, 1)  // (a 200-register budget does not launch with 320 threads: per-warp allocation granularity)
-ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-               const __grid_constant__ CUtensorMap tmXn, const FfnFwdArgs a) {
+ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
   using S = FfnSmem<D>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = sm100::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* sA = smem;                       // x tile -> LN(x), K-major swizzled
-  uint8_t* sH = sA + S::A_BYTES;            // [2][128 x 64] hidden chunk
-  uint8_t* sW = sH + 2 * S::H_BYTES;        // [STAGES][W1 chunk | W2 chunk]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + S::STAGES * S::STAGE_BYTES);
+  uint8_t* sA = smem;                 // x tile -> LN(x) (bwd: dout -> dy), K-major swizzled; at the end the output tile
+  uint8_t* sH = sA + S::A_BYTES;      // [2][128 x 64] hidden chunk (bwd: dz chunk)
+  uint8_t* sRest = sH + 2 * S::H_BYTES;
+  // fwd: [2] z staging tiles, then [STAGES] weight stages;  bwd: [STAGES] (weights | z chunk)
+  uint8_t* sZ = sRest;
+  uint8_t* sW = (MODE == 0) ? sRest + 2 * S::H_BYTES : sRest;
+  constexpr int STAGE_BYTES = (MODE == 0) ? S::W_BYTES : S::W_BYTES + S::H_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRest + S::REST_BYTES);
   uint64_t* x_full = bars + 0;
   uint64_t* a_ready = bars + 1;
   uint64_t* a_free = bars + 2;
@@ -97,24 +112,27 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   const int num_tiles = (M + 127) / 128, nch = H / kHC;
 
   if (warp == 0 && lane == 0) {
-    sm100::prefetch_tensormap(&tmX);
-    sm100::prefetch_tensormap(&tmW1);
-    sm100::prefetch_tensormap(&tmW2);
-    sm100::prefetch_tensormap(&tmXn);
+    sm100::prefetch_tensormap(&tm.x);
+    sm100::prefetch_tensormap(&tm.w1);
+    sm100::prefetch_tensormap(&tm.w2);
+    sm100::prefetch_tensormap(&tm.xn);
+    sm100::prefetch_tensormap(&tm.h);
+    sm100::prefetch_tensormap(&tm.z);
+    sm100::prefetch_tensormap(&tm.out);
     sm100::mbar_init(x_full, 1);
     sm100::mbar_init(a_ready, 1);
-    sm100::mbar_init(a_free, 2);  // the MMA warp (all G1 done) + the xn TMA store (source read)
+    sm100::mbar_init(a_free, 3);  // the MMA warp (all G1 done) + the xn / dy TMA store + the output TMA store (sources read)
     sm100::mbar_init(acc2_full, 1);
     sm100::mbar_init(acc2_empty, 8);
     for (int s = 0; s < S::STAGES; ++s) {
       sm100::mbar_init(&w_full[s], 1);
-      sm100::mbar_init(&w_empty[s], 1);
+      sm100::mbar_init(&w_empty[s], MODE == 0 ? 1 : 9);  // GEMM 2 has read the weights (+ bwd: the 8 epilogue warps have read the z chunk)
     }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&acc1_full[i], 1);
       sm100::mbar_init(&acc1_empty[i], 8);
       sm100::mbar_init(&h_full[i], 8);
-      sm100::mbar_init(&h_empty[i], 1);
+      sm100::mbar_init(&h_empty[i], 2);  // GEMM 2 has read the tile + its TMA stores have read it
     }
     sm100::fence_barrier_init();
   }
@@ -140,41 +158,56 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         sm100::mbar_wait(a_free, (ti & 1) ^ 1);
         sm100::mbar_arrive_expect_tx(x_full, S::A_BYTES);
 #pragma unroll
-        for (int ka = 0; ka < S::KA; ++ka) sm100::tma_load_2d(sA + ka * 16384, &tmX, x_full, ka * 64, tile * 128);
+        for (int ka = 0; ka < S::KA; ++ka) sm100::tma_load_2d(sA + ka * 16384, &tm.x, x_full, ka * 64, tile * 128);
         for (int c = 0; c < nch; ++c, ++it) {
           const int s = it % S::STAGES;
           const uint32_t ph = (it / S::STAGES) & 1;
           sm100::mbar_wait(&w_empty[s], ph ^ 1);
-          sm100::mbar_arrive_expect_tx(&w_full[s], S::W1_BYTES + D * 128);
-          uint8_t* w1 = sW + s * S::STAGE_BYTES;
+          sm100::mbar_arrive_expect_tx(&w_full[s], S::W1_BYTES + D * 128 + (MODE == 1 ? S::H_BYTES : 0));
+          uint8_t* w1 = sW + s * STAGE_BYTES;
 #pragma unroll
-          for (int ka = 0; ka < S::KA; ++ka) sm100::tma_load_2d(w1 + ka * (kHC * 128), &tmW1, &w_full[s], ka * 64, c * kHC);  // [64 rows x 64 k]
-          sm100::tma_load_2d(w1 + S::W1_BYTES, &tmW2, &w_full[s], c * kHC, 0);                                                   // [D rows x 64 k]
+          for (int ka = 0; ka < S::KA; ++ka) sm100::tma_load_2d(w1 + ka * (kHC * 128), &tm.w1, &w_full[s], ka * 64, c * kHC);  // [64 rows x 64 k]
+          sm100::tma_load_2d(w1 + S::W1_BYTES, &tm.w2, &w_full[s], c * kHC, 0);                                                   // [D rows x 64 k]
+          if constexpr (MODE == 1) sm100::tma_load_2d(w1 + S::W_BYTES, &tm.z, &w_full[s], c * kHC, tile * 128);                    // z chunk [128 x 64]
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+    // ===================================================================== MMA issuer (+ TMA stores of the chunk tiles)
     if (lane == 0) {
       constexpr uint32_t idesc1 = sm100::make_idesc_bf16_f32(128, kHC, 0, 0);
       constexpr uint32_t idesc2 = sm100::make_idesc_bf16_f32(128, D, 0, 0);
       const uint32_t a0 = sm100::smem_u32(sA);
       uint32_t it = 0, ti = 0;  // `it` counts hidden chunks across tiles: weight stage it % STAGES, acc1 / h buffer it & 1
+      int tile_cur = 0;
+      bool store_pending = false;  // a chunk-store group whose SMEM reads have not been waited for
+      uint32_t pending_b = 0;
       auto gemm2 = [&](uint32_t itc, int c) {  // acc2 += h[chunk c] . W2[chunk c, :]
         const uint32_t b = itc & 1, bph = (itc >> 1) & 1, s = itc % S::STAGES;
         sm100::mbar_wait(&h_full[b], bph);
         if (c == 0) sm100::mbar_wait(acc2_empty, (ti & 1) ^ 1);  // the previous tile's output epilogue has drained acc2
         sm100::tc_fence_after();
+        // the tiles the epilogue just published leave for global memory (saved for the backward / operands of the weight gradients)
+        sm100::tma_store_2d(&tm.h, sH + b * S::H_BYTES, c * kHC, tile_cur * 128);
+        if constexpr (MODE == 0) sm100::tma_store_2d(&tm.z, sZ + b * S::H_BYTES, c * kHC, tile_cur * 128);
+        sm100::tma_store_commit();
         const uint32_t h0 = sm100::smem_u32(sH + b * S::H_BYTES);
-        const uint32_t w2 = sm100::smem_u32(sW + s * S::STAGE_BYTES + S::W1_BYTES);
+        const uint32_t w2 = sm100::smem_u32(sW + s * STAGE_BYTES + S::W1_BYTES);
 #pragma unroll
         for (int kk = 0; kk < kHC / 16; ++kk)
           sm100::umma_bf16(tmem_base + S::ACC2_COL, sm100::make_smem_desc(h0 + kk * 32, 16, 1024), sm100::make_smem_desc(w2 + kk * 32, 16, 1024), idesc2,
                            (c | kk) != 0 ? 1u : 0u);
         sm100::umma_commit(&h_empty[b]);
         sm100::umma_commit(&w_empty[s]);
+        if (store_pending) {  // the previous chunk's stores have read their tiles: second arrival on that buffer's h_empty
+          sm100::tma_store_wait_read<1>();
+          sm100::mbar_arrive(&h_empty[pending_b]);
+        }
+        store_pending = true;
+        pending_b = b;
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        tile_cur = tile;
         sm100::mbar_wait(a_ready, ti & 1);
         sm100::tc_fence_after();
         for (int c = 0; c < nch; ++c, ++it) {
@@ -182,7 +215,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           sm100::mbar_wait(&w_full[s], ph);
           sm100::mbar_wait(&acc1_empty[b], bph ^ 1);
           sm100::tc_fence_after();
-          const uint32_t w1 = sm100::smem_u32(sW + s * S::STAGE_BYTES);
+          const uint32_t w1 = sm100::smem_u32(sW + s * STAGE_BYTES);
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const int ka = ks >> 2, kk = ks & 3;
@@ -195,6 +228,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         gemm2(it - 1, nch - 1);
         sm100::umma_commit(acc2_full);
         sm100::umma_commit(a_free);  // every G1 of this tile has read sA
+        sm100::tma_store_wait_read<0>();
+        sm100::mbar_arrive(&h_empty[pending_b]);
+        store_pending = false;
       }
     }
   } else {
@@ -288,32 +324,31 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           sm100::mbar_arrive(a_ready);
           // fwd: xn, bwd: dy leave for the weight-gradient GEMMs (rows / columns beyond the tensor are clipped by the hardware)
 #pragma unroll
-          for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tmXn, sA + ka * 16384, ka * 64, tile * 128);
+          for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tm.xn, sA + ka * 16384, ka * 64, tile * 128);
           sm100::tma_store_commit();
           sm100::tma_store_wait_read<0>();
           sm100::mbar_arrive(a_free);
         }
         __syncwarp();
       }
-      // ---- hidden chunks: acc1 -> z, h
+      // ---- hidden chunks: acc1 -> z, h  (bwd: acc1, z -> dz)
       [[maybe_unused]] const uint32_t rowkey1 = has_drop ? dropout_rowkey(seed0 + a.salt1, (unsigned long long)row) : 0u;
       const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int c = 0; c < nch; ++c, ++it) {
         const uint32_t b = it & 1, bph = (it >> 1) & 1;
-        const int col0 = c * kHC + half * 32;               // first hidden column of this thread's 32
+        const int col0 = c * kHC + half * 32;  // first hidden column of this thread's 32
         uint32_t zp[16], hp[16];
-        if constexpr (MODE == 1) {  // the saved pre-activation of this thread's 32 hidden units: issued BEFORE the wait for the accumulator
-          if (row_ok) {
-            const uint4* zg = reinterpret_cast<const uint4*>(a.z + (size_t)row * H + col0);
+        if constexpr (MODE == 1) {  // the saved pre-activation of this thread's 32 hidden units: arrived by TMA with the weights of the chunk
+          const uint32_t s = it % S::STAGES, ph = (it / S::STAGES) & 1;
+          sm100::mbar_wait(&w_full[s], ph);
+          const uint8_t* zt = sW + s * STAGE_BYTES + S::W_BYTES;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = ld_stream_u4(zg + j);
-              zp[4 * j] = u.x, zp[4 * j + 1] = u.y, zp[4 * j + 2] = u.z, zp[4 * j + 3] = u.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) zp[j] = 0u;
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(zt + swz_off(row_in_tile, half * 4 + j));
+            zp[4 * j] = u.x, zp[4 * j + 1] = u.y, zp[4 * j + 2] = u.z, zp[4 * j + 3] = u.w;
           }
+          __syncwarp();
+          if (lane == 0) sm100::mbar_arrive(&w_empty[s]);
         }
         sm100::mbar_wait(&acc1_full[b], bph);
         sm100::tc_fence_after();
@@ -367,20 +402,17 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 #pragma unroll
           for (int j = 0; j < 8; ++j) hp[ci * 8 + j] = pack2(v[2 * j], v[2 * j + 1]);
         }
-        if (row_ok) {
-          uint4* zg = reinterpret_cast<uint4*>(a.z + (size_t)row * H + col0);
-          uint4* hg = reinterpret_cast<uint4*>(a.h + (size_t)row * H + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if constexpr (MODE == 0) zg[j] = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
-            hg[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
-          }
-        }
-        sm100::mbar_wait(&h_empty[b], bph ^ 1);  // GEMM 2 of chunk c - 2 has read this buffer
+        sm100::mbar_wait(&h_empty[b], bph ^ 1);  // GEMM 2 of chunk c - 2 and its tile stores have read these buffers
         uint8_t* hb = sH + b * S::H_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(hb + swz_off(row_in_tile, half * 4 + j)) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+        if constexpr (MODE == 0) {
+          uint8_t* zb = sZ + b * S::H_BYTES;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(zb + swz_off(row_in_tile, half * 4 + j)) = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
+        }
         sm100::fence_proxy_async();
         __syncwarp();
         if (lane == 0) sm100::mbar_arrive(&h_full[b]);
@@ -407,6 +439,9 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       for (int gi = 0; gi < G_MID; ++gi)
         if (gi < ng) sm100::tmem_ld_32x32b_x16(tmem_row + S::ACC2_COL + (g0 + gi) * 16, racc[gi]);
       sm100::tmem_ld_wait();
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(acc2_empty);
 #pragma unroll
       for (int gi = 0; gi < G_MID; ++gi) {
         if (gi >= ng) break;
@@ -415,7 +450,6 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         if constexpr (MODE == 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(racc[gi][j]);
-          if (row_ok) store16(a.out + (size_t)row * D + g * 16, v);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -440,13 +474,25 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
               v[2 * j] = __uint_as_float(w[j] << 16) + a.factor * v[2 * j];
               v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u) + a.factor * v[2 * j + 1];
             }
-            store16(a.out + (size_t)row * D + g * 16, v);
           }
         }
+        // the output tile takes the place of the A operand (every GEMM 1 of the tile has completed: acc2_full follows them)
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = pack2(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4*>(sA + swz_off(row_in_tile, 2 * g)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(sA + swz_off(row_in_tile, 2 * g + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
       }
-      sm100::tc_fence_before();
+      sm100::fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ew == 0 && lane == 0) {
+#pragma unroll
+        for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tm.out, sA + ka * 16384, ka * 64, tile * 128);
+        sm100::tma_store_commit();
+        sm100::tma_store_wait_read<0>();
+        sm100::mbar_arrive(a_free);
+      }
       __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(acc2_empty);
     }
   }
   __syncthreads();
@@ -457,8 +503,7 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 }
 
 template <int D, int MODE>
-static int launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUtensorMap& tmW2, const CUtensorMap& tmXn, const FfnFwdArgs& a,
-                          cudaStream_t stream) {
+static int launch_ffn(const FfnMaps& tm, const FfnArgs& a, cudaStream_t stream) {
   using S = FfnSmem<D>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -467,9 +512,22 @@ static int launch_ffn(const CUtensorMap& tmX, const CUtensorMap& tmW1, const CUt
   }
   const int tiles = (a.M + 127) / 128;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  ffn_kernel<D, MODE><<<grid, kFfnThreads, S::TOTAL, stream>>>(tmX, tmW1, tmW2, tmXn, a);
+  ffn_kernel<D, MODE><<<grid, kFfnThreads, S::TOTAL, stream>>>(tm, a);
   count_launch();
   return check_launch();
+}
+
+// x / xn / out share [M, D]; z / h share [M, H]
+static bool ffn_maps(FfnMaps* tm, const void* x, const void* w1, const void* w2, const void* xn, const void* h, const void* z, const void* out, int M, int D,
+                     int H) {
+  bool ok = make_tmap_bf16_2d(&tm->x, x, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
+  ok = ok && make_tmap_bf16_2d(&tm->w1, w1, (uint64_t)H, (uint64_t)D, (uint64_t)D, kHC, 64);          // [H, D]: rows = hidden units, K = D
+  ok = ok && make_tmap_bf16_2d(&tm->w2, w2, (uint64_t)D, (uint64_t)H, (uint64_t)H, (uint32_t)D, 64);  // [D, H]: rows = model dim, K = hidden
+  ok = ok && make_tmap_bf16_2d(&tm->xn, xn, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
+  ok = ok && make_tmap_bf16_2d(&tm->h, h, (uint64_t)M, (uint64_t)H, (uint64_t)H, 128, 64);
+  ok = ok && make_tmap_bf16_2d(&tm->z, z, (uint64_t)M, (uint64_t)H, (uint64_t)H, 128, 64);
+  ok = ok && make_tmap_bf16_2d(&tm->out, out, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
+  return ok;
 }
 
 }  // namespace tfasr
@@ -485,21 +543,14 @@ extern "C" int tfasr_ffn_fwd_bf16(const void* x, const float* ln_g, const float*
   if (!x || !ln_g || !ln_b || !w1t || !b1 || !w2t || !b2 || !out || !xn || !z || !h || !mean || !rstd || M < 0) return TFASR_INVALID_VALUE;
   if (!tfasr_ffn_supported(D, H) || !(drop_p >= 0.f && drop_p < 1.f)) return TFASR_INVALID_VALUE;
   if (M == 0) return TFASR_OK;
-  CUtensorMap tmX, tmW1, tmW2, tmXn;
-  bool ok = make_tmap_bf16_2d(&tmX, x, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
-  ok = ok && make_tmap_bf16_2d(&tmW1, w1t, (uint64_t)H, (uint64_t)D, (uint64_t)D, kHC, 64);  // W1^T [H, D]: rows = hidden units, K = D
-  ok = ok && make_tmap_bf16_2d(&tmW2, w2t, (uint64_t)D, (uint64_t)H, (uint64_t)H, (uint32_t)D, 64);  // W2^T [D, H]: rows = outputs, K = hidden
-  ok = ok && make_tmap_bf16_2d(&tmXn, xn, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
-  if (!ok) return TFASR_INVALID_VALUE;
-  FfnFwdArgs a{};
+  FfnMaps tm;
+  if (!ffn_maps(&tm, x, w1t, w2t, xn, h, z, out, M, D, H)) return TFASR_INVALID_VALUE;
+  FfnArgs a{};
   a.x = static_cast<const __nv_bfloat16*>(x);
   a.ln_g = ln_g;
   a.ln_b = ln_b;
   a.b1 = b1;
   a.b2 = b2;
-  a.out = static_cast<__nv_bfloat16*>(out);
-  a.z = static_cast<__nv_bfloat16*>(z);
-  a.h = static_cast<__nv_bfloat16*>(h);
   a.mean = mean;
   a.rstd = rstd;
   a.M = M;
@@ -510,7 +561,7 @@ extern "C" int tfasr_ffn_fwd_bf16(const void* x, const float* ln_g, const float*
   a.seed_ptr = seed_ptr;
   a.salt1 = salt1;
   a.salt2 = salt2;
-  return launch_ffn<144, 0>(tmX, tmW1, tmW2, tmXn, a, static_cast<cudaStream_t>(stream));
+  return launch_ffn<144, 0>(tm, a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tfasr_ffn_bwd_bf16(const void* dout, const void* z, const void* w2, const void* w1, void* dy, void* dz, void* da, int32_t M, int32_t D,
@@ -519,16 +570,10 @@ extern "C" int tfasr_ffn_bwd_bf16(const void* dout, const void* z, const void* w
   if (!dout || !z || !w2 || !w1 || !dy || !dz || !da || M < 0) return TFASR_INVALID_VALUE;
   if (!tfasr_ffn_supported(D, H) || !(drop_p >= 0.f && drop_p < 1.f)) return TFASR_INVALID_VALUE;
   if (M == 0) return TFASR_OK;
-  CUtensorMap tmX, tmW1, tmW2, tmXn;
-  bool ok = make_tmap_bf16_2d(&tmX, dout, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
-  ok = ok && make_tmap_bf16_2d(&tmW1, w2, (uint64_t)H, (uint64_t)D, (uint64_t)D, kHC, 64);          // W2 [H, D]: ds = dy . W2^T, rows = hidden units
-  ok = ok && make_tmap_bf16_2d(&tmW2, w1, (uint64_t)D, (uint64_t)H, (uint64_t)H, (uint32_t)D, 64);  // W1 [D, H]: da = dz . W1^T, rows = model dim
-  ok = ok && make_tmap_bf16_2d(&tmXn, dy, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
-  if (!ok) return TFASR_INVALID_VALUE;
-  FfnFwdArgs a{};
-  a.out = static_cast<__nv_bfloat16*>(da);
-  a.z = static_cast<__nv_bfloat16*>(const_cast<void*>(z));
-  a.h = static_cast<__nv_bfloat16*>(dz);
+  FfnMaps tm;
+  // W2 [H, D]: ds = dy . W2^T (rows = hidden units);  W1 [D, H]: da = dz . W1^T (rows = model dim)
+  if (!ffn_maps(&tm, dout, w2, w1, dy, dz, z, da, M, D, H)) return TFASR_INVALID_VALUE;
+  FfnArgs a{};
   a.M = M;
   a.H = H;
   a.factor = factor;
@@ -536,5 +581,5 @@ extern "C" int tfasr_ffn_bwd_bf16(const void* dout, const void* z, const void* w
   a.seed_ptr = seed_ptr;
   a.salt1 = salt1;
   a.salt2 = salt2;
-  return launch_ffn<144, 1>(tmX, tmW1, tmW2, tmXn, a, static_cast<cudaStream_t>(stream));
+  return launch_ffn<144, 1>(tm, a, static_cast<cudaStream_t>(stream));
 }
