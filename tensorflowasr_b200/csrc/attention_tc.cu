@@ -15,8 +15,10 @@
 // Softmax is two-pass over the chunks (the MMAs are nearly free, the [128 x T] fp32 scores do not fit anywhere): pass 0 = running row max /
 // sum, pass 1 = recompute the scores, write the NORMALISED probabilities (bf16) to global (the backward reads them) and into SMEM as the A
 // operand of   O [128 x HP] += P_chunk . V_chunk   (V as an MN-major B operand: no transpose).
-// The head dimension 36 is not a multiple of the MMA K = 16: Qu / Qv are written by this kernel with zeros in columns 36..47, so whatever the
-// K / pos boxes carry there (the next head's columns) is multiplied by zero.
+// The head dimension 36 is not a multiple of the MMA K = 16, and a head's first column (36 n) is not always a multiple of 8 — but a TMA box must
+// start on a 16-byte boundary of the row (an unaligned start raised an illegal-instruction exception on the B200).  So every box starts at
+// the aligned column below the head, the head's data sits at columns dl .. dl + H - 1 of the tile (dl = 0 or 4), and Qu / Qv are written by
+// this kernel at the same columns with zeros everywhere else: whatever the K / pos boxes carry outside the head is multiplied by zero.
 //
 // Roofline: latency / issue — 18 MFLOP per (utterance, head) at T = 250; the point of tcgen05 here is that the tensor work and the operand
 // movement cost no instruction slots of the 8 softmax warps (the mma.sync generation spent 94 % of its issue slots on index arithmetic).
@@ -87,6 +89,8 @@ rel_attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
   const int R = 2 * T - 1;
   const int bn = blockIdx.y, b = bn / N, n = bn % N;
   const int t0 = blockIdx.x * 128;
+  const int dl = (n * H) & 7;        // the head starts `dl` columns into its (16-byte aligned) TMA boxes
+  const int c_head = n * H - dl;     // aligned first column of the q box; k / v / pos boxes are offset likewise (N * H % 8 == 0)
   const int len_b = a.length ? min(max(a.length[b], 0), T) : T;
   const bool streaming = a.chunk > 0;
   // key chunks this tile has to visit: all of them unless the streaming window of every row in the tile (all of them valid queries) ends earlier /
@@ -131,8 +135,8 @@ rel_attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
     // ===================================================================== TMA producer
     if (lane == 0) {
       sm100::mbar_arrive_expect_tx(q_full, S::Q_BYTES);
-      sm100::tma_load_2d(sQraw, &tmQKV, q_full, n * H, b * T + t0);
-      sm100::tma_load_2d(sQraw + 64 * 128, &tmQKV, q_full, n * H, b * T + t0 + 64);
+      sm100::tma_load_2d(sQraw, &tmQKV, q_full, c_head, b * T + t0);
+      sm100::tma_load_2d(sQraw + 64 * 128, &tmQKV, q_full, c_head, b * T + t0 + 64);
       for (int it = 0; it < total_it; ++it) {
         const int pass = it / nkc, kc = kc_lo + it % nkc;
         const int s = it & 1;
@@ -140,11 +144,11 @@ rel_attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
         sm100::mbar_wait(&st_empty[s], ph ^ 1);
         uint8_t* st = sStage + s * S::STAGE_BYTES;
         sm100::mbar_arrive_expect_tx(&st_full[s], S::K_BYTES + S::P_BYTES + (pass ? S::K_BYTES : 0));
-        sm100::tma_load_2d(st, &tmQKV, &st_full[s], N * H + n * H, b * T + kc * kKC);                        // K chunk
-        if (pass) sm100::tma_load_2d(st + S::K_BYTES, &tmQKV, &st_full[s], 2 * N * H + n * H, b * T + kc * kKC);  // V chunk
+        sm100::tma_load_2d(st, &tmQKV, &st_full[s], N * H + c_head, b * T + kc * kKC);                        // K chunk
+        if (pass) sm100::tma_load_2d(st + S::K_BYTES, &tmQKV, &st_full[s], 2 * N * H + c_head, b * T + kc * kKC);  // V chunk
         const int rlo = T - 1 - (t0 + 127) + kc * kKC;  // may be negative / run past R: those rows are never addressed by a valid (t, j)
 #pragma unroll
-        for (int k = 0; k < kPW / 64; ++k) sm100::tma_load_2d(st + 2 * S::K_BYTES + k * 64 * 128, &tmPos, &st_full[s], n * H, b * R + rlo + k * 64);
+        for (int k = 0; k < kPW / 64; ++k) sm100::tma_load_2d(st + 2 * S::K_BYTES + k * 64 * 128, &tmPos, &st_full[s], c_head, b * R + rlo + k * 64);
       }
     }
   } else if (warp == 1) {
@@ -223,10 +227,11 @@ rel_attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
         uint32_t ou[4], ov[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int col = c * 8 + 2 * e;
+          const int h0 = c * 8 + 2 * e - dl;  // head column of this pair (dl is even: pairs never straddle the head's edge)
+          const bool in = h0 >= 0 && h0 + 1 < H;
           const float q0 = __uint_as_float(w[e] << 16), q1 = __uint_as_float(w[e] & 0xFFFF0000u);
-          const float u0 = col < H ? q0 + __ldg(ub + col) : 0.f, u1 = col + 1 < H ? q1 + __ldg(ub + col + 1) : 0.f;
-          const float v0 = col < H ? q0 + __ldg(vb + col) : 0.f, v1 = col + 1 < H ? q1 + __ldg(vb + col + 1) : 0.f;
+          const float u0 = in ? q0 + __ldg(ub + h0) : 0.f, u1 = in ? q1 + __ldg(ub + h0 + 1) : 0.f;
+          const float v0 = in ? q0 + __ldg(vb + h0) : 0.f, v1 = in ? q1 + __ldg(vb + h0 + 1) : 0.f;
           ou[e] = pack2(u0, u1);
           ov[e] = pack2(v0, v1);
         }
@@ -365,9 +370,8 @@ rel_attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
         for (int g = 0; g < HP / 16; ++g)
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
-            const int col = g * 16 + e;
-            if (col + 1 < H) *reinterpret_cast<uint32_t*>(cp + col) = pack2(__uint_as_float(o[g][e]), __uint_as_float(o[g][e + 1]));
-            else if (col < H) cp[col] = __float2bfloat16(__uint_as_float(o[g][e]));
+            const int h0 = g * 16 + e - dl;  // accumulator column -> head column
+            if (h0 >= 0 && h0 + 1 < H) *reinterpret_cast<uint32_t*>(cp + h0) = pack2(__uint_as_float(o[g][e]), __uint_as_float(o[g][e + 1]));
           }
       }
     }
@@ -400,7 +404,10 @@ using namespace tfasr;
 
 // 1 when the tcgen05 forward covers the shape: head dimension even and <= 64, 16-byte aligned row pitches.
 extern "C" int tfasr_rel_attention_tc_supported(int32_t T, int32_t N, int32_t H, int32_t ld_qkv, int32_t ld_pos) {
-  return (T >= 1 && H >= 2 && H <= 64 && (H & 1) == 0 && (ld_qkv % 8) == 0 && (ld_pos % 8) == 0 && ((N * H) & 1) == 0) ? 1 : 0;
+  if (!(T >= 1 && N >= 1 && H >= 2 && (H & 1) == 0 && (ld_qkv % 8) == 0 && (ld_pos % 8) == 0 && ((N * H) % 8) == 0)) return 0;
+  int dl_max = 0;  // a head starts up to 6 columns into its aligned box: the padded head dimension must hold dl + H
+  for (int n = 0; n < N; ++n) dl_max = (n * H) % 8 > dl_max ? (n * H) % 8 : dl_max;
+  return H + dl_max <= 64 ? 1 : 0;
 }
 
 extern "C" int tfasr_rel_attention_fwd_tc(const void* qkv, int32_t ld_qkv, const void* pos, int32_t ld_pos, const float* ubias, const float* vbias,
@@ -423,6 +430,8 @@ extern "C" int tfasr_rel_attention_fwd_tc(const void* qkv, int32_t ld_qkv, const
   a.probs = static_cast<__nv_bfloat16*>(probs);
   a.B = B, a.T = T, a.N = N, a.H = H, a.chunk = chunk, a.history = history;
   a.scale = 1.0f / sqrtf((float)H);
-  if (H <= 48) return launch_att_tc<48>(tmQKV, tmPos, a, static_cast<cudaStream_t>(stream));
+  int dl_max = 0;
+  for (int n = 0; n < N; ++n) dl_max = (n * H) % 8 > dl_max ? (n * H) % 8 : dl_max;
+  if (H + dl_max <= 48) return launch_att_tc<48>(tmQKV, tmPos, a, static_cast<cudaStream_t>(stream));
   return launch_att_tc<64>(tmQKV, tmPos, a, static_cast<cudaStream_t>(stream));
 }

@@ -30,7 +30,9 @@
 
 namespace tfasr {
 
-constexpr int kFfnThreads = 320;  // warp 0 TMA, warp 1 MMA (+ the chunk stores), warps 2-9 epilogue / LayerNorm
+constexpr int kFfnEpiWarps = 16;                   // 4 per TMEM lane quarter: the epilogue is a per-thread dependent chain (sigmoid, dropout hash,
+                                                   // packing) — 16 columns per thread and chunk instead of 32 halves its latency
+constexpr int kFfnThreads = 64 + 32 * kFfnEpiWarps;  // warp 0 TMA, warp 1 MMA (+ the chunk stores), warps 2-17 epilogue / LayerNorm
 constexpr int kHC = 64;           // hidden-dimension chunk = one 128B-swizzle atom of K for GEMM 2
 
 template <int D>
@@ -76,7 +78,7 @@ struct FfnMaps {
 };
 
 template <int D, int MODE>
-__global__ void __launch_bounds__(kFfnThreads, 1)  // (a 200-register budget does not launch with 320 threads: per-warp allocation granularity)
+__global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
   using S = FfnSmem<D>;
   extern __shared__ uint8_t smem_raw[];
@@ -123,15 +125,15 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
     sm100::mbar_init(a_ready, 1);
     sm100::mbar_init(a_free, 3);  // the MMA warp (all G1 done) + the xn / dy TMA store + the output TMA store (sources read)
     sm100::mbar_init(acc2_full, 1);
-    sm100::mbar_init(acc2_empty, 8);
+    sm100::mbar_init(acc2_empty, kFfnEpiWarps);
     for (int s = 0; s < S::STAGES; ++s) {
       sm100::mbar_init(&w_full[s], 1);
-      sm100::mbar_init(&w_empty[s], MODE == 0 ? 1 : 9);  // GEMM 2 has read the weights (+ bwd: the 8 epilogue warps have read the z chunk)
+      sm100::mbar_init(&w_empty[s], MODE == 0 ? 1 : 1 + kFfnEpiWarps);  // GEMM 2 has read the weights (+ bwd: the epilogue warps have read the z chunk)
     }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&acc1_full[i], 1);
-      sm100::mbar_init(&acc1_empty[i], 8);
-      sm100::mbar_init(&h_full[i], 8);
+      sm100::mbar_init(&acc1_empty[i], kFfnEpiWarps);
+      sm100::mbar_init(&h_full[i], kFfnEpiWarps);
       sm100::mbar_init(&h_empty[i], 2);  // GEMM 2 has read the tile + its TMA stores have read it
     }
     sm100::fence_barrier_init();
@@ -234,10 +236,10 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
       }
     }
   } else {
-    // ===================================================================== LayerNorm + epilogues (warps 2..9)
+    // ===================================================================== LayerNorm + epilogues (warps 2..17)
     const int q = warp & 3;   // TMEM lane quarter of this warp
-    const int ew = warp - 2;  // 0..7
-    const int half = ew >> 2;
+    const int ew = warp - 2;  // 0..15
+    const int sub = ew >> 2;  // which 16 of a chunk's 64 hidden columns this warp takes (4 warps share a lane quarter)
     const bool has_drop = a.drop_p > 0.f;
     const float keep_scale = has_drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
     const uint32_t drop_thr = dropout_threshold(a.drop_p);
@@ -273,13 +275,13 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
       if (ew < 4 && MODE == 0) {
         // ---- LayerNorm of this thread's row, in place in the swizzled tile (keras LayerNormalization: biased variance, eps inside the sqrt)
         sm100::mbar_wait(x_full, ti & 1);
-        uint4 pk[D / 8];
-#pragma unroll
-        for (int j = 0; j < D / 8; ++j) pk[j] = *reinterpret_cast<const uint4*>(sA + swz_off(row_in_tile, j));
+        // three sweeps over the row in SMEM (sum, centred squares, normalise) instead of holding its 18 x 16 bytes in registers: the 576-thread
+        // CTA leaves each thread 96 registers
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < D / 8; ++j) {
-          const uint32_t w[4] = {pk[j].x, pk[j].y, pk[j].z, pk[j].w};
+          const uint4 u = *reinterpret_cast<const uint4*>(sA + swz_off(row_in_tile, j));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) sum += __uint_as_float(w[e] << 16) + __uint_as_float(w[e] & 0xFFFF0000u);
         }
@@ -287,7 +289,8 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
         float sq = 0.f;
 #pragma unroll
         for (int j = 0; j < D / 8; ++j) {
-          const uint32_t w[4] = {pk[j].x, pk[j].y, pk[j].z, pk[j].w};
+          const uint4 u = *reinterpret_cast<const uint4*>(sA + swz_off(row_in_tile, j));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float d0 = __uint_as_float(w[e] << 16) - mean, d1 = __uint_as_float(w[e] & 0xFFFF0000u) - mean;
@@ -306,7 +309,9 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
           const float4 b0 = *reinterpret_cast<const float4*>(sBeta + 8 * j), b1v = *reinterpret_cast<const float4*>(sBeta + 8 * j + 4);
           const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
-          const uint32_t w[4] = {pk[j].x, pk[j].y, pk[j].z, pk[j].w};
+          uint8_t* p = sA + swz_off(row_in_tile, j);
+          const uint4 u = *reinterpret_cast<const uint4*>(p);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
           uint32_t o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -314,7 +319,7 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
             const float v1 = (__uint_as_float(w[e] & 0xFFFF0000u) - mean) * rstd * g[2 * e + 1] + bb[2 * e + 1];
             o[e] = pack2(v0, v1);
           }
-          *reinterpret_cast<uint4*>(sA + swz_off(row_in_tile, j)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
       if (ew < 4) {
@@ -336,15 +341,15 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
       const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int c = 0; c < nch; ++c, ++it) {
         const uint32_t b = it & 1, bph = (it >> 1) & 1;
-        const int col0 = c * kHC + half * 32;  // first hidden column of this thread's 32
-        uint32_t zp[16], hp[16];
+        const int col0 = c * kHC + sub * 16;  // first hidden column of this thread's 16
+        uint32_t zp[8], hp[8];
         if constexpr (MODE == 1) {  // the saved pre-activation of this thread's 32 hidden units: arrived by TMA with the weights of the chunk
           const uint32_t s = it % S::STAGES, ph = (it / S::STAGES) & 1;
           sm100::mbar_wait(&w_full[s], ph);
           const uint8_t* zt = sW + s * STAGE_BYTES + S::W_BYTES;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(zt + swz_off(row_in_tile, half * 4 + j));
+          for (int j = 0; j < 2; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(zt + swz_off(row_in_tile, sub * 2 + j));
             zp[4 * j] = u.x, zp[4 * j + 1] = u.y, zp[4 * j + 2] = u.z, zp[4 * j + 3] = u.w;
           }
           __syncwarp();
@@ -352,15 +357,14 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
         }
         sm100::mbar_wait(&acc1_full[b], bph);
         sm100::tc_fence_after();
-        uint32_t r[2][16];
-        sm100::tmem_ld_32x32b_x16(tmem_row + b * kHC + half * 32, r[0]);
-        sm100::tmem_ld_32x32b_x16(tmem_row + b * kHC + half * 32 + 16, r[1]);
+        uint32_t r[1][16];
+        sm100::tmem_ld_32x32b_x16(tmem_row + b * kHC + sub * 16, r[0]);
         sm100::tmem_ld_wait();
         sm100::tc_fence_before();
         __syncwarp();
         if (lane == 0) sm100::mbar_arrive(&acc1_empty[b]);  // acc1[b] may take chunk c + 2
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
+        for (int ci = 0; ci < 1; ++ci) {
           float v[16];
           if constexpr (MODE == 0) {
 #pragma unroll
@@ -405,13 +409,13 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
         sm100::mbar_wait(&h_empty[b], bph ^ 1);  // GEMM 2 of chunk c - 2 and its tile stores have read these buffers
         uint8_t* hb = sH + b * S::H_BYTES;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(hb + swz_off(row_in_tile, half * 4 + j)) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+        for (int j = 0; j < 2; ++j)
+          *reinterpret_cast<uint4*>(hb + swz_off(row_in_tile, sub * 2 + j)) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
         if constexpr (MODE == 0) {
           uint8_t* zb = sZ + b * S::H_BYTES;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(zb + swz_off(row_in_tile, half * 4 + j)) = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
+          for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<uint4*>(zb + swz_off(row_in_tile, sub * 2 + j)) = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
         }
         sm100::fence_proxy_async();
         __syncwarp();
@@ -419,8 +423,8 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
       }
       // ---- output: acc2 -> + b2 -> dropout -> residual
       [[maybe_unused]] const uint32_t rowkey2 = has_drop ? dropout_rowkey(seed0 + a.salt2, (unsigned long long)row) : 0u;
-      constexpr int NG = D / 16, G_MID = (NG + 1) / 2;
-      const int g0 = half ? G_MID : 0, ng = half ? NG - G_MID : G_MID;
+      constexpr int NG = D / 16, G_MID = NG - (NG * 3) / 4;  // the 16-column groups of the output, split over the 4 warps of a lane quarter
+      const int g0 = (NG * sub) / 4, ng = (NG * (sub + 1)) / 4 - g0;
       // the residual x of this thread's columns is requested before the wait for the accumulator (its latency hides behind GEMM 2)
       [[maybe_unused]] uint4 xres[G_MID][2];
       if constexpr (MODE == 0) {
@@ -434,30 +438,25 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
       }
       sm100::mbar_wait(acc2_full, ti & 1);
       sm100::tc_fence_after();
-      uint32_t racc[G_MID][16];
-#pragma unroll
-      for (int gi = 0; gi < G_MID; ++gi)
-        if (gi < ng) sm100::tmem_ld_32x32b_x16(tmem_row + S::ACC2_COL + (g0 + gi) * 16, racc[gi]);
-      sm100::tmem_ld_wait();
-      sm100::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(acc2_empty);
 #pragma unroll
       for (int gi = 0; gi < G_MID; ++gi) {
         if (gi >= ng) break;
         const int g = g0 + gi;
+        uint32_t racc[16];  // one 16-column group at a time: the 576-thread CTA has no registers for the whole row slice
+        sm100::tmem_ld_32x32b_x16(tmem_row + S::ACC2_COL + g * 16, racc);
+        sm100::tmem_ld_wait();
         float v[16];
         if constexpr (MODE == 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(racc[gi][j]);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(racc[j]);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b4 = *reinterpret_cast<const float4*>(sB2 + g * 16 + 4 * j);
-            v[4 * j] = __uint_as_float(racc[gi][4 * j]) + b4.x;
-            v[4 * j + 1] = __uint_as_float(racc[gi][4 * j + 1]) + b4.y;
-            v[4 * j + 2] = __uint_as_float(racc[gi][4 * j + 2]) + b4.z;
-            v[4 * j + 3] = __uint_as_float(racc[gi][4 * j + 3]) + b4.w;
+            v[4 * j] = __uint_as_float(racc[4 * j]) + b4.x;
+            v[4 * j + 1] = __uint_as_float(racc[4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(racc[4 * j + 2]) + b4.z;
+            v[4 * j + 3] = __uint_as_float(racc[4 * j + 3]) + b4.w;
           }
           if (has_drop) {
 #pragma unroll
@@ -483,8 +482,11 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
         *reinterpret_cast<uint4*>(sA + swz_off(row_in_tile, 2 * g)) = make_uint4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<uint4*>(sA + swz_off(row_in_tile, 2 * g + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
       }
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(acc2_empty);  // this warp's slice of acc2 has been read
       sm100::fence_proxy_async();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       if (ew == 0 && lane == 0) {
 #pragma unroll
         for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tm.out, sA + ka * 16384, ka * 64, tile * 128);

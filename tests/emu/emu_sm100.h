@@ -150,6 +150,7 @@ static inline void prefetch_tensormap(const CUtensorMap*) {}
 // box element (r, c) <-> global element (c1 + r, c0 + c); shared memory: row r at r * inner bytes, swizzled
 static inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
   const uint32_t inner = m->box_cols * m->elem_bytes, base = smem_u32(smem_dst);
+  if (((int64_t)c0 * m->elem_bytes) % 16 != 0) abort();  // seen on the B200: a box that does not start on a 16-byte boundary of the row is an illegal instruction
   for (uint32_t r = 0; r < m->box_rows; ++r)
     for (uint32_t c = 0; c < m->box_cols; ++c) {
       const int64_t gr = (int64_t)c1 + r, gc = (int64_t)c0 + c;
@@ -161,6 +162,7 @@ static inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* b
 }
 static inline void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   const uint32_t inner = m->box_cols * m->elem_bytes, base = smem_u32(smem_src);
+  if (((int64_t)c0 * m->elem_bytes) % 16 != 0) abort();
   for (uint32_t r = 0; r < m->box_rows; ++r)
     for (uint32_t c = 0; c < m->box_cols; ++c) {
       const int64_t gr = (int64_t)c1 + r, gc = (int64_t)c0 + c;
