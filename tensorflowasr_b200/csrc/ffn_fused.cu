@@ -30,9 +30,13 @@
 
 namespace tfasr {
 
-constexpr int kFfnEpiWarps = 16;                   // 4 per TMEM lane quarter: the epilogue is a per-thread dependent chain (sigmoid, dropout hash,
-                                                   // packing) — 16 columns per thread and chunk instead of 32 halves its latency
-constexpr int kFfnThreads = 64 + 32 * kFfnEpiWarps;  // warp 0 TMA, warp 1 MMA (+ the chunk stores), warps 2-17 epilogue / LayerNorm
+// Tile = 64 rows (of a 128-row MMA: TMEM lanes 64..127 compute on stale SMEM and are never read).  The epilogue — sigmoid, dropout hash,
+// packing: ~19 instructions per hidden activation — is what a tile costs, not the tensor work (9 % of the tensor pipe at 128 rows), so the
+// module spreads over 125 SMs instead of 63.  Warps: 2 = TMA producer, 3 = MMA issuer (+ the chunk stores); 0,1 / 4,5 / 8,9 / 12,13 =
+// epilogue + LayerNorm (TMEM lane quarters 0 and 1 = the 64 rows; `sub` = which 16 of a chunk's 64 columns); 6,7,10,11 idle.
+constexpr int kFfnEpiWarps = 8;
+constexpr int kFfnThreads = 448;
+constexpr int kFfnRows = 64;
 constexpr int kHC = 64;           // hidden-dimension chunk = one 128B-swizzle atom of K for GEMM 2
 
 template <int D>
@@ -49,7 +53,7 @@ struct FfnSmem {
   static constexpr int REST_BYTES = STAGES * (W_BYTES + H_BYTES);
   static constexpr int BAR_BYTES = 32 * 8;
   static constexpr int H_MAX = 1024;                       // hidden units (b1 staged in SMEM)
-  static constexpr int PARAM_BYTES = (H_MAX + 3 * D) * 4;  // b1 | b2 | ln gamma | ln beta: read once per CTA, not once per chunk from L2
+  static constexpr int PARAM_BYTES = (H_MAX + 3 * D + 2 * kFfnRows * 4) * 4;  // b1 | b2 | ln gamma | ln beta (read once per CTA) | LN partial sums
   static constexpr int TOTAL = A_BYTES + 2 * H_BYTES + REST_BYTES + BAR_BYTES + PARAM_BYTES + 1024;
   static_assert(TOTAL <= 227 * 1024, "smem budget");
   static constexpr uint32_t TMEM_COLS = 512;               // acc1 x2 (64 columns each) + acc2 (D columns)
@@ -65,7 +69,17 @@ struct FfnArgs {
   float eps, factor, drop_p;
   const unsigned long long* seed_ptr;
   unsigned long long salt1, salt2;
+  unsigned long long* trace;  // debug: phase timestamps of CTA 0 (tools/ffn_trace.py); null in production
 };
+
+// phase timestamps (globaltimer, ns) of CTA 0 -> trace[slot]; compiled in, costs one predictable branch per event when trace is null
+__device__ __forceinline__ void ffn_trace(const FfnArgs& a, int slot) {
+  if (a.trace && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[slot] = t;
+  }
+}
 
 struct FfnMaps {
   CUtensorMap x;     // load : fwd x, bwd dout            [M, D], box [128 x 64]
@@ -108,12 +122,13 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
   float* sB2 = sB1 + S::H_MAX;                                    // [D]
   float* sG = sB2 + D;                                            // [D]
   float* sBeta = sG + D;                                          // [D]
+  float* sRed = sBeta + D;                                        // [2][64 rows][4 row quarters]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = a.M, H = a.H;
-  const int num_tiles = (M + 127) / 128, nch = H / kHC;
+  const int num_tiles = (M + kFfnRows - 1) / kFfnRows, nch = H / kHC;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 2 && lane == 0) {
     sm100::prefetch_tensormap(&tm.x);
     sm100::prefetch_tensormap(&tm.w1);
     sm100::prefetch_tensormap(&tm.w2);
@@ -146,35 +161,36 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
       sBeta[i] = a.ln_b[i];
     }
   }
-  if (warp == 1) sm100::tmem_alloc(tmem_slot, S::TMEM_COLS);
+  if (warp == 3) sm100::tmem_alloc(tmem_slot, S::TMEM_COLS);
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) ffn_trace(a, 0);  // setup done
 
-  if (warp == 0) {
+  if (warp == 2) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       uint32_t it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
         sm100::mbar_wait(a_free, (ti & 1) ^ 1);
-        sm100::mbar_arrive_expect_tx(x_full, S::A_BYTES);
+        sm100::mbar_arrive_expect_tx(x_full, S::KA * kFfnRows * 128);
 #pragma unroll
-        for (int ka = 0; ka < S::KA; ++ka) sm100::tma_load_2d(sA + ka * 16384, &tm.x, x_full, ka * 64, tile * 128);
+        for (int ka = 0; ka < S::KA; ++ka) sm100::tma_load_2d(sA + ka * 16384, &tm.x, x_full, ka * 64, tile * kFfnRows);  // rows 0..63 of each atom
         for (int c = 0; c < nch; ++c, ++it) {
           const int s = it % S::STAGES;
           const uint32_t ph = (it / S::STAGES) & 1;
           sm100::mbar_wait(&w_empty[s], ph ^ 1);
-          sm100::mbar_arrive_expect_tx(&w_full[s], S::W1_BYTES + D * 128 + (MODE == 1 ? S::H_BYTES : 0));
+          sm100::mbar_arrive_expect_tx(&w_full[s], S::W1_BYTES + D * 128 + (MODE == 1 ? kFfnRows * 128 : 0));
           uint8_t* w1 = sW + s * STAGE_BYTES;
 #pragma unroll
           for (int ka = 0; ka < S::KA; ++ka) sm100::tma_load_2d(w1 + ka * (kHC * 128), &tm.w1, &w_full[s], ka * 64, c * kHC);  // [64 rows x 64 k]
           sm100::tma_load_2d(w1 + S::W1_BYTES, &tm.w2, &w_full[s], c * kHC, 0);                                                   // [D rows x 64 k]
-          if constexpr (MODE == 1) sm100::tma_load_2d(w1 + S::W_BYTES, &tm.z, &w_full[s], c * kHC, tile * 128);                    // z chunk [128 x 64]
+          if constexpr (MODE == 1) sm100::tma_load_2d(w1 + S::W_BYTES, &tm.z, &w_full[s], c * kHC, tile * kFfnRows);               // z chunk [64 x 64]
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 3) {
     // ===================================================================== MMA issuer (+ TMA stores of the chunk tiles)
     if (lane == 0) {
       constexpr uint32_t idesc1 = sm100::make_idesc_bf16_f32(128, kHC, 0, 0);
@@ -189,9 +205,10 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
         sm100::mbar_wait(&h_full[b], bph);
         if (c == 0) sm100::mbar_wait(acc2_empty, (ti & 1) ^ 1);  // the previous tile's output epilogue has drained acc2
         sm100::tc_fence_after();
+        if (c < 12) ffn_trace(a, 40 + c);  // MMA thread: h chunk c published
         // the tiles the epilogue just published leave for global memory (saved for the backward / operands of the weight gradients)
-        sm100::tma_store_2d(&tm.h, sH + b * S::H_BYTES, c * kHC, tile_cur * 128);
-        if constexpr (MODE == 0) sm100::tma_store_2d(&tm.z, sZ + b * S::H_BYTES, c * kHC, tile_cur * 128);
+        sm100::tma_store_2d(&tm.h, sH + b * S::H_BYTES, c * kHC, tile_cur * kFfnRows);
+        if constexpr (MODE == 0) sm100::tma_store_2d(&tm.z, sZ + b * S::H_BYTES, c * kHC, tile_cur * kFfnRows);
         sm100::tma_store_commit();
         const uint32_t h0 = sm100::smem_u32(sH + b * S::H_BYTES);
         const uint32_t w2 = sm100::smem_u32(sW + s * STAGE_BYTES + S::W1_BYTES);
@@ -215,8 +232,10 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
         for (int c = 0; c < nch; ++c, ++it) {
           const uint32_t s = it % S::STAGES, ph = (it / S::STAGES) & 1, b = it & 1, bph = (it >> 1) & 1;
           sm100::mbar_wait(&w_full[s], ph);
+          if (c < 12) ffn_trace(a, 16 + c);  // MMA thread: weights of chunk c landed
           sm100::mbar_wait(&acc1_empty[b], bph ^ 1);
           sm100::tc_fence_after();
+          if (c < 12) ffn_trace(a, 28 + c);  // MMA thread: issuing G1(c)
           const uint32_t w1 = sm100::smem_u32(sW + s * STAGE_BYTES);
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
@@ -228,6 +247,7 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
           if (c > 0) gemm2(it - 1, c - 1);
         }
         gemm2(it - 1, nch - 1);
+        ffn_trace(a, 2);  // MMA thread: last GEMM 2 issued
         sm100::umma_commit(acc2_full);
         sm100::umma_commit(a_free);  // every G1 of this tile has read sA
         sm100::tma_store_wait_read<0>();
@@ -235,11 +255,13 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
         store_pending = false;
       }
     }
-  } else {
-    // ===================================================================== LayerNorm + epilogues (warps 2..17)
-    const int q = warp & 3;   // TMEM lane quarter of this warp
-    const int ew = warp - 2;  // 0..15
-    const int sub = ew >> 2;  // which 16 of a chunk's 64 hidden columns this warp takes (4 warps share a lane quarter)
+  } else if ((warp & 3) < 2) {
+    // ===================================================================== LayerNorm + epilogues (warps 0,1,4,5,8,9,12,13)
+    const int q = warp & 3;     // TMEM lane quarter of this warp: 0 or 1 = rows 0..63
+    const int sub = warp >> 2;  // which 16 of a chunk's 64 hidden columns this warp takes; which quarter of a row in the prologue
+    const int ew = sub * 2 + q;  // 0..7
+    const int jb = sub < 2 ? sub * 5 : 10 + (sub - 2) * 4, je = jb + (sub < 2 ? 5 : 4);  // this thread's 16-byte chunks of its row (D = 144: 18)
+    static_assert(D / 8 == 18, "row split of the prologue is written for 18 chunks");
     const bool has_drop = a.drop_p > 0.f;
     const float keep_scale = has_drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
     const uint32_t drop_thr = dropout_threshold(a.drop_p);
@@ -247,14 +269,15 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
     uint32_t it = 0, ti = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       const int row_in_tile = q * 32 + lane;
-      const int row = tile * 128 + row_in_tile;
+      const int row = tile * kFfnRows + row_in_tile;
       const bool row_ok = row < M;
-      if (ew < 4 && MODE == 1) {
-        // ---- backward prologue: dy = factor * Drop2'(dout) on this thread's row, in place (what scale_mask_colsum did in its own launch)
+      if constexpr (MODE == 1) {
+        // ---- backward prologue: dy = factor * Drop2'(dout) on this thread's quarter of its row, in place (scale_mask_colsum's job in round 1)
         sm100::mbar_wait(x_full, ti & 1);
         const uint32_t rowkey2b = has_drop ? dropout_rowkey(seed0 + a.salt2, (unsigned long long)row) : 0u;
 #pragma unroll
         for (int j = 0; j < D / 8; ++j) {
+          if (j < jb || j >= je) continue;
           uint8_t* p = sA + swz_off(row_in_tile, j);
           const uint4 u = *reinterpret_cast<const uint4*>(p);
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -272,23 +295,27 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
           *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
-      if (ew < 4 && MODE == 0) {
-        // ---- LayerNorm of this thread's row, in place in the swizzled tile (keras LayerNormalization: biased variance, eps inside the sqrt)
+      if constexpr (MODE == 0) {
+        // ---- LayerNorm in place in the swizzled tile (keras LayerNormalization: biased variance, eps inside the sqrt): four threads per row
+        // (one per lane-quarter warp group), partial sums through SMEM, two-pass statistics in fp32
         sm100::mbar_wait(x_full, ti & 1);
-        // three sweeps over the row in SMEM (sum, centred squares, normalise) instead of holding its 18 x 16 bytes in registers: the 576-thread
-        // CTA leaves each thread 96 registers
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < D / 8; ++j) {
+          if (j < jb || j >= je) continue;
           const uint4 u = *reinterpret_cast<const uint4*>(sA + swz_off(row_in_tile, j));
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) sum += __uint_as_float(w[e] << 16) + __uint_as_float(w[e] & 0xFFFF0000u);
         }
-        const float mean = sum * (1.0f / D);
+        sRed[row_in_tile * 4 + sub] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float4 s4 = *reinterpret_cast<const float4*>(sRed + row_in_tile * 4);
+        const float mean = (s4.x + s4.y + s4.z + s4.w) * (1.0f / D);
         float sq = 0.f;
 #pragma unroll
         for (int j = 0; j < D / 8; ++j) {
+          if (j < jb || j >= je) continue;
           const uint4 u = *reinterpret_cast<const uint4*>(sA + swz_off(row_in_tile, j));
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -298,13 +325,17 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
             sq = fmaf(d1, d1, sq);
           }
         }
-        const float rstd = rsqrtf(sq * (1.0f / D) + a.eps);
-        if (row_ok) {
+        sRed[kFfnRows * 4 + row_in_tile * 4 + sub] = sq;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float4 q4 = *reinterpret_cast<const float4*>(sRed + kFfnRows * 4 + row_in_tile * 4);
+        const float rstd = rsqrtf((q4.x + q4.y + q4.z + q4.w) * (1.0f / D) + a.eps);
+        if (row_ok && sub == 0) {
           a.mean[row] = mean;
           a.rstd[row] = rstd;
         }
 #pragma unroll
         for (int j = 0; j < D / 8; ++j) {
+          if (j < jb || j >= je) continue;
           const float4 g0 = *reinterpret_cast<const float4*>(sG + 8 * j), g1 = *reinterpret_cast<const float4*>(sG + 8 * j + 4);
           const float4 b0 = *reinterpret_cast<const float4*>(sBeta + 8 * j), b1v = *reinterpret_cast<const float4*>(sBeta + 8 * j + 4);
           const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -322,14 +353,15 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
           *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
-      if (ew < 4) {
+      {
         sm100::fence_proxy_async();  // generic-proxy writes of the A operand -> visible to tcgen05.mma / TMA (async proxy)
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (ew == 0 && lane == 0) {
+          ffn_trace(a, 1);  // LayerNorm / prologue done
           sm100::mbar_arrive(a_ready);
           // fwd: xn, bwd: dy leave for the weight-gradient GEMMs (rows / columns beyond the tensor are clipped by the hardware)
 #pragma unroll
-          for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tm.xn, sA + ka * 16384, ka * 64, tile * 128);
+          for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tm.xn, sA + ka * 16384, ka * 64, tile * kFfnRows);
           sm100::tma_store_commit();
           sm100::tma_store_wait_read<0>();
           sm100::mbar_arrive(a_free);
@@ -357,6 +389,7 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
         }
         sm100::mbar_wait(&acc1_full[b], bph);
         sm100::tc_fence_after();
+        if (ew == 0 && lane == 0 && c < 12) ffn_trace(a, 52 + c);  // epilogue warp 0: accumulator of chunk c ready
         uint32_t r[1][16];
         sm100::tmem_ld_32x32b_x16(tmem_row + b * kHC + sub * 16, r[0]);
         sm100::tmem_ld_wait();
@@ -406,7 +439,9 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) hp[ci * 8 + j] = pack2(v[2 * j], v[2 * j + 1]);
         }
+        if (ew == 0 && lane == 0 && c < 12) ffn_trace(a, 64 + c);  // epilogue warp 0: chunk c computed
         sm100::mbar_wait(&h_empty[b], bph ^ 1);  // GEMM 2 of chunk c - 2 and its tile stores have read these buffers
+        if (ew == 0 && lane == 0 && c < 12) ffn_trace(a, 76 + c);  // epilogue warp 0: buffer free
         uint8_t* hb = sH + b * S::H_BYTES;
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -438,6 +473,7 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
       }
       sm100::mbar_wait(acc2_full, ti & 1);
       sm100::tc_fence_after();
+      if (ew == 0 && lane == 0) ffn_trace(a, 3);  // output accumulator ready
 #pragma unroll
       for (int gi = 0; gi < G_MID; ++gi) {
         if (gi >= ng) break;
@@ -486,19 +522,20 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
       __syncwarp();
       if (lane == 0) sm100::mbar_arrive(acc2_empty);  // this warp's slice of acc2 has been read
       sm100::fence_proxy_async();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (ew == 0 && lane == 0) {
 #pragma unroll
-        for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tm.out, sA + ka * 16384, ka * 64, tile * 128);
+        for (int ka = 0; ka < S::KA; ++ka) sm100::tma_store_2d(&tm.out, sA + ka * 16384, ka * 64, tile * kFfnRows);
         sm100::tma_store_commit();
         sm100::tma_store_wait_read<0>();
         sm100::mbar_arrive(a_free);
+        ffn_trace(a, 4);  // output tile handed to the TMA
       }
       __syncwarp();
     }
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 3) {
     sm100::tc_fence_after();
     sm100::tmem_dealloc(tmem_base, S::TMEM_COLS);
   }
@@ -512,7 +549,7 @@ static int launch_ffn(const FfnMaps& tm, const FfnArgs& a, cudaStream_t stream) 
     if (cudaFuncSetAttribute(ffn_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return TFASR_EXECUTION_FAILED;
     attr_set = true;
   }
-  const int tiles = (a.M + 127) / 128;
+  const int tiles = (a.M + kFfnRows - 1) / kFfnRows;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
   ffn_kernel<D, MODE><<<grid, kFfnThreads, S::TOTAL, stream>>>(tm, a);
   count_launch();
@@ -522,19 +559,23 @@ static int launch_ffn(const FfnMaps& tm, const FfnArgs& a, cudaStream_t stream) 
 // x / xn / out share [M, D]; z / h share [M, H]
 static bool ffn_maps(FfnMaps* tm, const void* x, const void* w1, const void* w2, const void* xn, const void* h, const void* z, const void* out, int M, int D,
                      int H) {
-  bool ok = make_tmap_bf16_2d(&tm->x, x, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
+  bool ok = make_tmap_bf16_2d(&tm->x, x, (uint64_t)M, (uint64_t)D, (uint64_t)D, kFfnRows, 64);
   ok = ok && make_tmap_bf16_2d(&tm->w1, w1, (uint64_t)H, (uint64_t)D, (uint64_t)D, kHC, 64);          // [H, D]: rows = hidden units, K = D
   ok = ok && make_tmap_bf16_2d(&tm->w2, w2, (uint64_t)D, (uint64_t)H, (uint64_t)H, (uint32_t)D, 64);  // [D, H]: rows = model dim, K = hidden
-  ok = ok && make_tmap_bf16_2d(&tm->xn, xn, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
-  ok = ok && make_tmap_bf16_2d(&tm->h, h, (uint64_t)M, (uint64_t)H, (uint64_t)H, 128, 64);
-  ok = ok && make_tmap_bf16_2d(&tm->z, z, (uint64_t)M, (uint64_t)H, (uint64_t)H, 128, 64);
-  ok = ok && make_tmap_bf16_2d(&tm->out, out, (uint64_t)M, (uint64_t)D, (uint64_t)D, 128, 64);
+  ok = ok && make_tmap_bf16_2d(&tm->xn, xn, (uint64_t)M, (uint64_t)D, (uint64_t)D, kFfnRows, 64);
+  ok = ok && make_tmap_bf16_2d(&tm->h, h, (uint64_t)M, (uint64_t)H, (uint64_t)H, kFfnRows, 64);
+  ok = ok && make_tmap_bf16_2d(&tm->z, z, (uint64_t)M, (uint64_t)H, (uint64_t)H, kFfnRows, 64);
+  ok = ok && make_tmap_bf16_2d(&tm->out, out, (uint64_t)M, (uint64_t)D, (uint64_t)D, kFfnRows, 64);
   return ok;
 }
 
 }  // namespace tfasr
 
 using namespace tfasr;
+
+static unsigned long long* g_ffn_trace = nullptr;
+// debug: device buffer of 128 u64 that the next launches' CTA 0 fills with phase timestamps (null = off)
+extern "C" void tfasr_ffn_set_trace(unsigned long long* dev_buffer) { g_ffn_trace = dev_buffer; }
 
 extern "C" int tfasr_ffn_supported(int32_t D, int32_t H) { return (D == 144 && H >= 64 && H % 64 == 0 && H <= FfnSmem<144>::H_MAX) ? 1 : 0; }
 
@@ -563,6 +604,7 @@ extern "C" int tfasr_ffn_fwd_bf16(const void* x, const float* ln_g, const float*
   a.seed_ptr = seed_ptr;
   a.salt1 = salt1;
   a.salt2 = salt2;
+  a.trace = g_ffn_trace;
   return launch_ffn<144, 0>(tm, a, static_cast<cudaStream_t>(stream));
 }
 
@@ -583,5 +625,6 @@ extern "C" int tfasr_ffn_bwd_bf16(const void* dout, const void* z, const void* w
   a.seed_ptr = seed_ptr;
   a.salt1 = salt1;
   a.salt2 = salt2;
+  a.trace = g_ffn_trace;
   return launch_ffn<144, 1>(tm, a, static_cast<cudaStream_t>(stream));
 }

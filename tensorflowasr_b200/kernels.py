@@ -317,7 +317,7 @@ def rel_attention_fwd(qkv, pos, ubias, vbias, length, B, T, N, H, chunk=None, hi
     hi = int(history) if (chunk is not None and history is not None) else 0
     from . import ops
 
-    if ops.attention_tc_active() and pos.dim() == 2 and pos.stride(1) == 1 and lib.tfasr_rel_attention_tc_supported(T, N, H, qkv.stride(0), pos.stride(0)):
+    if ops.attention_tc_active(T) and pos.dim() == 2 and pos.stride(1) == 1 and lib.tfasr_rel_attention_tc_supported(T, N, H, qkv.stride(0), pos.stride(0)):
         # forward on tcgen05 (csrc/attention_tc.cu): any T, contiguous pos or a column slice of the all-blocks projection
         _lib.check(lib.tfasr_rel_attention_fwd_tc(_lib.ptr(qkv), qkv.stride(0), _lib.ptr_rows(pos), pos.stride(0), _lib.ptr(ubias), _lib.ptr(vbias),
                                                   _lib.ptr(length), B, T, N, H, ch, hi, _lib.ptr(ctx), _lib.ptr(probs), _st(qkv)),

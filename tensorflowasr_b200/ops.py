@@ -222,32 +222,42 @@ def fused_ffn_active() -> bool:
     return _FUSED_FFN
 
 
-_ATTENTION_TC = _os.environ.get("TFASR_ATTENTION_TC", "1") == "1"
+_ATTENTION_TC = _os.environ.get("TFASR_ATTENTION_TC", "auto")  # "1" always, "0" never, "auto": where the mma.sync generation has no kernel
 
 
-def set_attention_tc(flag: bool):
-    """Relative-position attention forward on tcgen05 (csrc/attention_tc.cu: TMA-fed operands, TMEM accumulators) instead of the mma.sync
-    generation (csrc/attention.cu), which stays the backward and the fallback for odd head sizes."""
+def set_attention_tc(flag):
+    """Relative-position attention forward on tcgen05 (csrc/attention_tc.cu: TMA-fed operands, TMEM accumulators, any sequence length).
+    True / False force the route; "auto" (default) takes it for T' > 256 — the Conformer-L streaming decode of BASELINE configs[4], which
+    the mma.sync generation (csrc/attention.cu: whole-utterance SMEM staging, T' <= 256) cannot run — and keeps the mma.sync kernels at
+    T' <= 256, where they measured faster on a B200 in round 2 (39.6 vs 59.1 us per layer at B = 32, T' = 250: the softmax warps of the
+    tcgen05 kernel are its critical path)."""
     global _ATTENTION_TC
-    _ATTENTION_TC = bool(flag)
+    _ATTENTION_TC = flag if flag == "auto" else ("1" if flag else "0")
 
 
-def attention_tc_active() -> bool:
-    return _ATTENTION_TC
+def attention_tc_active(T: int = 0) -> bool:
+    if _ATTENTION_TC == "auto":
+        return T > 256
+    return _ATTENTION_TC == "1"
 
 
-_SWITCHES = ("_FUSED_FFN", "_ATTENTION_TC", "_FUSED", "_FUSED_SEQ", "_DWCONV_WGRAD_V2", "_JOINT_REDUCE_V2", "_IM2COL_V2", "_JOINT_V2", "_RNNT_GRAD_V2", "_CONV1_V2", "_POS_BATCHED",
+_SWITCHES = ("_FUSED_FFN", "_FUSED", "_FUSED_SEQ", "_DWCONV_WGRAD_V2", "_JOINT_REDUCE_V2", "_IM2COL_V2", "_JOINT_V2", "_RNNT_GRAD_V2", "_CONV1_V2", "_POS_BATCHED",
              "_PEER_BN", "_FUSED_LSE", "_PERSISTENT_DECODE")
 
 
 def switch_state() -> dict:
     """Snapshot of every kernel-route switch (tests flip them and put them back with restore_switches)."""
     g = globals()
-    return {k: g[k] for k in _SWITCHES}
+    st = {k: g[k] for k in _SWITCHES}
+    st["_ATTENTION_TC"] = _ATTENTION_TC
+    return st
 
 
 def restore_switches(state: dict):
+    global _ATTENTION_TC
     globals().update({k: bool(v) for k, v in state.items() if k in _SWITCHES})
+    if "_ATTENTION_TC" in state:
+        _ATTENTION_TC = state["_ATTENTION_TC"]
 
 
 def compute_dtype():

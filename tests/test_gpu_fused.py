@@ -252,10 +252,13 @@ def test_subsampling_kernels_vs_torch():
 
 @pytest.mark.parametrize("cfg", [(3, 50, 4, 36, None, None), (2, 37, 2, 16, 4, 8), (1, 250, 4, 36, None, None), (2, 64, 2, 64, None, None),
                                  (2, 129, 3, 36, 16, 32), (1, 300, 2, 36, None, None), (2, 9, 2, 36, None, None), (3, 250, 4, 36, 32, 64)])
-def test_rel_attention_kernels_vs_torch(cfg):
-    """Fused relative-position attention fwd/bwd vs the torch restatement (ops.rel_attention) in fp32 on the same bf16 inputs."""
+@pytest.mark.parametrize("tc", [False, True])
+def test_rel_attention_kernels_vs_torch(cfg, tc):
+    """Fused relative-position attention fwd/bwd vs the torch restatement (ops.rel_attention) in fp32 on the same bf16 inputs.
+    tc: the forward on the tcgen05 kernel (csrc/attention_tc.cu) — the backward then runs on ITS probabilities."""
     from tensorflowasr_b200 import kernels, ops
 
+    ops.set_attention_tc(tc)
     B, T, N, H, chunk, hist = cfg
     NH, R = N * H, 2 * T - 1
     torch.manual_seed(T)
@@ -280,6 +283,28 @@ def test_rel_attention_kernels_vs_torch(cfg):
     _close(dpos.view(B, R, NH), p3.grad, 3e-2)
     _close(du, ur.grad, 3e-2)
     _close(dv, vr.grad, 3e-2)
+
+
+def test_rel_attention_tc_long_streaming_forward_vs_torch():
+    """Conformer-L streaming decode shape (BASELINE configs[4]): T' = 750, 8 heads x 64, chunk 16 / history 64 — only the tcgen05 kernel runs it."""
+    from tensorflowasr_b200 import kernels, ops
+
+    B, T, N, H, chunk, hist = 2, 750, 8, 64, 16, 64
+    NH, R = N * H, 2 * T - 1
+    torch.manual_seed(7)
+    qkv = (torch.randn(B * T, 3 * NH, device="cuda") * 0.7).to(torch.bfloat16)
+    pos = (torch.randn(B * R, NH, device="cuda") * 0.7).to(torch.bfloat16)
+    u, v = torch.randn(N, H, device="cuda") * 0.2, torch.randn(N, H, device="cuda") * 0.2
+    length = torch.tensor([T, T - 100], device="cuda", dtype=torch.int32)
+    assert ops.attention_tc_active(T)  # "auto" takes the tcgen05 kernel beyond T' = 256
+    ctx, probs = kernels.rel_attention_fwd(qkv, pos, u, v, length, B, T, N, H, chunk, hist)
+    ops.set_precision("fp32")
+    q3, p3 = qkv.float().view(B, T, 3 * NH), pos.float().view(B, R, NH)
+    ref = ops.rel_attention(q3[..., :NH], q3[..., NH:2 * NH], q3[..., 2 * NH:], p3, u, v, length, N, H, chunk_size=chunk, history_size=hist)
+    for b in range(B):
+        n = int(length[b])
+        _close(ctx.view(B, T, NH)[b, :n], ref[b, :n], 2e-2)
+    torch.testing.assert_close(probs.float().sum(-1)[0], torch.ones(N, T, device="cuda"), rtol=2e-2, atol=2e-2)
 
 
 def test_dwconv_kernels_vs_torch():
