@@ -393,6 +393,7 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
         uint32_t r[1][16];
         sm100::tmem_ld_32x32b_x16(tmem_row + b * kHC + sub * 16, r[0]);
         sm100::tmem_ld_wait();
+        if (ew == 0 && lane == 0 && c < 12) ffn_trace(a, 88 + c);  // epilogue warp 0: accumulator in registers
         sm100::tc_fence_before();
         __syncwarp();
         if (lane == 0) sm100::mbar_arrive(&acc1_empty[b]);  // acc1[b] may take chunk c + 2
@@ -452,9 +453,11 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
           for (int j = 0; j < 2; ++j)
             *reinterpret_cast<uint4*>(zb + swz_off(row_in_tile, sub * 2 + j)) = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
         }
+        if (ew == 0 && lane == 0 && c < 12) ffn_trace(a, 100 + c);  // epilogue warp 0: tiles written
         sm100::fence_proxy_async();
         __syncwarp();
         if (lane == 0) sm100::mbar_arrive(&h_full[b]);
+        if (ew == 0 && lane == 0 && c < 12) ffn_trace(a, 112 + c);  // epilogue warp 0: published
       }
       // ---- output: acc2 -> + b2 -> dropout -> residual
       [[maybe_unused]] const uint32_t rowkey2 = has_drop ? dropout_rowkey(seed0 + a.salt2, (unsigned long long)row) : 0u;

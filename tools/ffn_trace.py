@@ -35,6 +35,7 @@ for mode in ("fwd", "bwd"):
     t0 = t[0]
     rel = lambda i: (t[i] - t0) / 1e3 if t[i] else float("nan")  # noqa: E731
     print(f"== {mode}: setup->0; prologue done {rel(1):.2f} us; last G2 issued {rel(2):.2f}; acc2 ready {rel(3):.2f}; out stored {rel(4):.2f}")
-    print(" c | W landed | G1 issue | acc1 ready(epi) | computed | buf free | h published(MMA)")
+    print(" c | W landed | G1 issue | acc1 ready(epi) | in regs | computed | buf free | written | published(w0) | h published(MMA)")
     for c in range(9):
-        print(f" {c} | {rel(16 + c):8.2f} | {rel(28 + c):8.2f} | {rel(52 + c):8.2f} | {rel(64 + c):8.2f} | {rel(76 + c):8.2f} | {rel(40 + c):8.2f}")
+        print(f" {c} | {rel(16 + c):8.2f} | {rel(28 + c):8.2f} | {rel(52 + c):8.2f} | {rel(88 + c):8.2f} | {rel(64 + c):8.2f} | {rel(76 + c):8.2f} | "
+              f"{rel(100 + c):8.2f} | {rel(112 + c):8.2f} | {rel(40 + c):8.2f}")
