@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 # 1. one GPU: the protocol with a world of one rank (eager + graph replay)
-timeout 300 python -m pytest tests/test_gpu_peer.py -m gpu -q -x --tb=short 2>&1 | tail -20 > gpurun_out/peer_single.log
+timeout 300 python -m pytest tests/test_gpu_peer.py tests/test_gpu_peer_multi.py -m gpu -q --tb=short 2>&1 | tail -20 > gpurun_out/peer_single.log
 # 2. N GPUs: correctness vs NCCL, identical sums on every rank, latency of 36 dependent exchanges in one graph
 timeout 300 $RUN --master-port 29517 tools/peer_bn_check.py --out gpurun_out/peer_bn_check_n$N.json > gpurun_out/peer_bn_check_n$N.log 2>&1
 echo "peer_bn_check exit $?" >> gpurun_out/peer_bn_check_n$N.log
