@@ -1,17 +1,19 @@
 // One-shot all-reduce (sum) of a SMALL fp32 vector over peer memory — the sync-BatchNorm statistics exchange (SURVEY.md 8e C2:
 // keras BatchNormalization(synchronized=True), reference conformer.py:326-333 / subsampling.py norms=["batch", ...]; here fused.bn_train_fwd /
 // bn_train_bwd).  36 of these sit on the critical path of every Conformer-S training step (18 BatchNorms, forward + backward), 2 x C
-// floats each: an NCCL all-reduce costs its launch + protocol latency per call; this kernel is one launch of one CTA:
-//   1. PUSH   every rank stores its n values into ITS lane of every rank's window (posted NVLink stores, no round trip),
-//   2. SIGNAL fence, then one st.release.sys per peer: flag[parity][my rank] = epoch,
-//   3. WAIT   one thread per peer spins (ld.acquire.sys, bounded) on the local flag lane of that peer,
-//   4. SUM    the lanes in RANK ORDER (every rank computes bit-identical sums — replicas must not drift apart).
-// Window of one rank:  float data[2][world][capacity];  uint32 flag[2][world][8] (one 32-byte sector per flag).
+// floats each: an NCCL all-reduce costs its launch + protocol latency per call; this kernel is one launch of one CTA and no fence:
+//   1. PUSH   every rank stores (value, epoch) PAIRS — one 8-byte store each, single-copy atomic over NVLink — into ITS lane of every
+//             rank's window: the epoch half vouches for the value half, so there is no flag, no release fence and no second round
+//             (the low-latency protocol of NCCL's LL mode; round 2's first version, data + fence.sys + flag, measured 12.1 us per
+//             exchange on two B200s, slower than NCCL's 10.6),
+//   2. GATHER thread i polls slot i of every rank's lane in its own window (ld.relaxed.sys: the point of coherence, never a stale L1
+//             line; bounded spin) and sums the values in RANK ORDER (every rank computes bit-identical sums — replicas must not drift).
+// Window of one rank:  uint64 slot[2][world][capacity]  (value bits | epoch << 32).
 // The epoch counter lives in device memory and is advanced by the kernel itself, so a captured CUDA graph replays correctly.
-// Two parities: a rank can be at most one call ahead of a peer (it needs the peer's flag of call k to finish call k), so the lane
-// it overwrites in call k+1 was last read in call k-1.
+// Two parities: a rank can be at most one call ahead of a peer (it needs the peer's slots of call k to finish call k), so the lane
+// it overwrites in call k+1 was last read in call k-1; a slot of call k-2 carries epoch k-2 and can never be mistaken for call k's.
 // Plain SIMT: builds twice (nvcc -> libtfasr_b200.so; g++ -DTFASR_EMU_BUILD -> tests/emu, where the ranks are host threads sharing one
-// address space and ThreadSanitizer checks the release / acquire protocol).
+// address space and ThreadSanitizer checks the protocol).
 #include <string.h>
 
 #include "simt.cuh"
@@ -25,48 +27,41 @@ namespace tfasr {
 
 constexpr int kPeerThreads = 256;
 constexpr int kPeerMaxWorld = 64;
-constexpr int kPeerFlagStride = 8;  // uint32 per flag: one 32-byte sector each
 
 __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const uint64_t* __restrict__ windows, int rank, int world, int capacity,
                                                                       uint32_t* __restrict__ state, float* __restrict__ data, int n,
                                                                       long long timeout_ticks) {
   const int tid = threadIdx.x;
   const uint32_t epoch = state[0] + 1u;  // written by the previous launch of this kernel (stream order)
+  __syncthreads();                       // every thread has read the counter before thread 0 advances it
   const size_t par = epoch & 1u;
-  const size_t flag_off = (size_t)2 * world * capacity * sizeof(float);
-  // 1. push
-  for (int p = 0; p < world; ++p) {
-    float* dst = reinterpret_cast<float*>(windows[p]) + (par * world + rank) * capacity;
-    for (int i = tid; i < n; i += blockDim.x) dst[i] = data[i];
-  }
-  simt_fence_sys();
-  __syncthreads();
-  uint8_t* mine = reinterpret_cast<uint8_t*>(windows[rank]);
-  // 2. signal, 3. wait: thread r talks to rank r
-  if (tid < world) {
-    uint32_t* theirs = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(windows[tid]) + flag_off) + (par * world + rank) * kPeerFlagStride;
-    simt_st_release_sys(theirs, epoch);
-    const uint32_t* from = reinterpret_cast<const uint32_t*>(mine + flag_off) + (par * world + tid) * kPeerFlagStride;
-    const long long t0 = simt_ticks();
-    while ((int32_t)(simt_ld_acquire_sys(from) - epoch) < 0) {
-      if (simt_ticks() - t0 > timeout_ticks) {  // a peer never arrived: flag it and fall through rather than hang the GPU
-        state[1] = 1u;
-        break;
-      }
-#ifndef TFASR_EMU_BUILD
-      __nanosleep(40);  // poll the local L2 a little less eagerly while a peer is still on its way
-#endif
+  const unsigned long long tag = (unsigned long long)epoch << 32;
+  // 1. push (value, epoch) pairs into every rank's window (the own one included)
+  for (int i = tid; i < n; i += blockDim.x) {
+    const unsigned long long packed = tag | (unsigned long long)__float_as_uint(data[i]);
+    for (int p = 0; p < world; ++p) {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(windows[p]) + (par * world + rank) * capacity;
+      simt_st_relaxed_sys_u64(dst + i, packed);
     }
   }
-  __syncthreads();
-  simt_fence_sys();  // belt and braces: the acquires were made by `world` threads, the lanes are read by all of them
-  // 4. sum in rank order
-  const float* lanes = reinterpret_cast<const float*>(mine) + par * world * capacity;
+  // 2. gather: wait for every rank's slot i, sum in rank order
+  const unsigned long long* lanes = reinterpret_cast<const unsigned long long*>(windows[rank]) + par * world * capacity;
+  const long long t0 = simt_ticks();
+  bool late = false;
   for (int i = tid; i < n; i += blockDim.x) {
     float s = 0.f;
-    for (int r = 0; r < world; ++r) s += simt_ld_relaxed_sys_f32(lanes + (size_t)r * capacity + i);
+    for (int r = 0; r < world; ++r) {
+      const unsigned long long* slot = lanes + (size_t)r * capacity + i;
+      unsigned long long w = simt_ld_relaxed_sys_u64(slot);
+      while ((uint32_t)(w >> 32) != epoch && !late) {
+        if (simt_ticks() - t0 > timeout_ticks) late = true;  // a peer never arrived: flag it and fall through rather than hang the GPU
+        w = simt_ld_relaxed_sys_u64(slot);
+      }
+      s += __uint_as_float((uint32_t)w);
+    }
     data[i] = s;
   }
+  if (late) state[1] = 1u;
   if (tid == 0) state[0] = epoch;
 }
 
@@ -76,7 +71,7 @@ using namespace tfasr;
 
 extern "C" size_t tfasr_peer_window_bytes(int32_t world, int32_t capacity) {
   if (world < 1 || world > kPeerMaxWorld || capacity < 1) return 0;
-  return (size_t)2 * world * capacity * sizeof(float) + (size_t)2 * world * kPeerFlagStride * sizeof(uint32_t);
+  return (size_t)2 * world * capacity * sizeof(unsigned long long);
 }
 
 // Window management: plain CUDA IPC on the CURRENT device (one process per GPU; the 64-byte handles travel through the host-side process group).

@@ -107,6 +107,23 @@ __device__ __forceinline__ float simt_ld_relaxed_sys_f32(const float* p) {
   return v;
 #endif
 }
+// 8-byte (value, epoch) slots of the LL exchange: single-copy atomic over NVLink, so the epoch half vouches for the value half
+__device__ __forceinline__ void simt_st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+#ifdef TFASR_EMU_BUILD
+  std::atomic_ref<unsigned long long>(*p).store(v, std::memory_order_relaxed);
+#else
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned long long simt_ld_relaxed_sys_u64(const unsigned long long* p) {
+#ifdef TFASR_EMU_BUILD
+  return std::atomic_ref<unsigned long long>(*const_cast<unsigned long long*>(p)).load(std::memory_order_relaxed);
+#else
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
 __device__ __forceinline__ void simt_fence_sys() {
 #ifdef TFASR_EMU_BUILD
   std::atomic_thread_fence(std::memory_order_seq_cst);

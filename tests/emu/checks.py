@@ -755,7 +755,7 @@ def check_peer_allreduce(lib, world, capacity, sizes, seed=0, stagger=True):
 
     lib.tfasr_peer_window_bytes.restype = ctypes.c_size_t
     wbytes = lib.tfasr_peer_window_bytes(world, capacity)
-    assert wbytes == 8 * world * capacity + 64 * world
+    assert wbytes == 16 * world * capacity  # (value, epoch) pairs: 8 bytes per slot, two parities
     rng = np.random.default_rng(seed)
     wins = [heap(np.zeros(wbytes // 4, np.uint32)) for _ in range(world)]
     table, tp = heap(np.array([w[0].ctypes.data for w in wins], np.uint64))
