@@ -254,6 +254,13 @@ class PeerAllReduce:
 
 
 _PEER = None
+_PEER_FAILED = False
+
+
+def _lib_emulated() -> bool:
+    from . import _lib
+
+    return _lib.EMULATED
 
 
 def small_all_reduce(t: torch.Tensor) -> torch.Tensor:
@@ -263,12 +270,15 @@ def small_all_reduce(t: torch.Tensor) -> torch.Tensor:
     from . import ops
 
     if ops.peer_bn_active() and t.dtype == torch.float32 and t.is_contiguous():
-        global _PEER
-        if _PEER is None or _PEER.world != world_size():
+        global _PEER, _PEER_FAILED
+        if (_PEER is None or _PEER.world != world_size()) and not _PEER_FAILED and (t.is_cuda or _lib_emulated()):
             if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("PeerAllReduce must be created before CUDA-graph capture (run one eager step first)")
-            _PEER = PeerAllReduce(capacity=max(4096, t.numel()))
-        if t.numel() <= _PEER.capacity:
+            try:
+                _PEER = PeerAllReduce(capacity=max(4096, t.numel()))
+            except RuntimeError:  # ranks on several nodes, or no peer access: the NCCL exchange stays
+                _PEER_FAILED = True
+        if _PEER is not None and not _PEER_FAILED and t.numel() <= _PEER.capacity:
             return _PEER.all_reduce(t)
     dist.all_reduce(t)
     return t

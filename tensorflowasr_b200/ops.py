@@ -164,13 +164,14 @@ def pos_batched_active() -> bool:
     return _POS_BATCHED
 
 
-_PEER_BN = _os.environ.get("TFASR_PEER_BN", "0") == "1"
+_PEER_BN = _os.environ.get("TFASR_PEER_BN", "1") == "1"
 
 
 def set_peer_bn(flag: bool):
     """Multi-GPU: exchange the sync-BatchNorm statistics with the one-launch all-reduce over peer memory (csrc/peer_allreduce.cu,
-    dist.PeerAllReduce) instead of one NCCL all-reduce per BatchNorm pass.  Off by default until it has run on a
-    multi-GPU B200 box (tools/round2_first_call.sh)."""
+    dist.PeerAllReduce) instead of one NCCL all-reduce per BatchNorm pass.  Default since round 2: on two B200s the
+    exchange takes 5.2 us against NCCL's 10.6 (36 of them per step), sums bit-identical on every rank (tests/test_gpu_peer_multi.py);
+    ranks on different nodes fall back to NCCL (dist.small_all_reduce)."""
     global _PEER_BN
     _PEER_BN = bool(flag)
 

@@ -80,7 +80,10 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tensorflowasr_b200 import dist as tdist
 
+    from tensorflowasr_b200 import ops as _ops
+
     lo, hi = tdist.shard_batch(4)
+    _ops.set_peer_bn(False)  # first the gloo / NCCL-style exchange (the peer-memory kernel is the default route on GPUs)
     losses, grads = _fused_grads(_data()(lo, hi), world)
     # the same step once more with the sync-BatchNorm statistics exchanged by the peer-memory kernel (csrc/peer_allreduce.cu on the emulator;
     # the windows are shared-memory blocks mapped at different addresses in the two processes, as CUDA IPC mappings would be)
