@@ -172,7 +172,9 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(const int32_t* __res
 // on the PREVIOUS step only, so a step is NU independent log-add-exps per lane and ONE shuffle (the emit term crossing a lane boundary) — no
 // shared memory, no __syncthreads.  The multi-warp kernel above pays a CTA barrier per step (3 warps at U + 1 = 65): 150 us for the 314
 // dependent steps of the bench shape (profiles/rnnt_logmel_ncu_r02.txt), i.e. 0.48 us per step against ~0.07 us of arithmetic.
-template <int NU>
+// With steps that short the operand prefetch must run PF = 16 steps ahead (4 was enough at 0.48 us per step: one warp per SM has nothing
+// else to hide a global-load latency behind).
+template <int NU, int PF>
 __global__ void __launch_bounds__(32) rnnt_lattice_warp_kernel(const int32_t* __restrict__ logit_len, const int32_t* __restrict__ label_len, int T, int U1,
                                                                RnntWs ws, float* __restrict__ costs) {
   const int b = blockIdx.x;
@@ -192,23 +194,23 @@ __global__ void __launch_bounds__(32) rnnt_lattice_warp_kernel(const int32_t* __
   // cell j of this lane: position i = lane * NU + j in "own" coordinates (alpha: u = i; beta: u = Ub - i), own-time tt = n - i
   auto cell = [&](int i, int tt) -> size_t { return (size_t)(is_beta ? (Tb - 1 - tt) : tt) * U1 + (is_beta ? Ub - i : i); };
   float stay[NU], emit[NU];       // emit[j]: value cell j offers to position i + 1 at the next step
-  float pb[NU][kPrefetch], pt[NU][kPrefetch];
+  float pb[NU][PF], pt[NU][PF];
 #pragma unroll
   for (int j = 0; j < NU; ++j) {
     const int i = lane * NU + j;
     stay[j] = (i == 0) ? 0.f : -CUDART_INF_F;
     emit[j] = -CUDART_INF_F;
 #pragma unroll
-    for (int k = 0; k < kPrefetch; ++k) {
-      const int tt0 = (((k - i) % kPrefetch) + kPrefetch) % kPrefetch;
+    for (int k = 0; k < PF; ++k) {
+      const int tt0 = (((k - i) % PF) + PF) % PF;
       const bool ok = i <= Ub && tt0 < Tb;
       pb[j][k] = ok ? blank[cell(i, tt0)] : 0.f;
       pt[j][k] = ok ? truth[cell(i, tt0)] : 0.f;
     }
   }
-  for (int n0 = 0; n0 < nsteps; n0 += kPrefetch) {
+  for (int n0 = 0; n0 < nsteps; n0 += PF) {
 #pragma unroll
-    for (int k = 0; k < kPrefetch; ++k) {
+    for (int k = 0; k < PF; ++k) {
       const int n = n0 + k;
       float from_left = __shfl_up_sync(0xffffffffu, emit[NU - 1], 1);
       if (lane == 0) from_left = -CUDART_INF_F;
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(32) rnnt_lattice_warp_kernel(const int32_t* __
           }
           out[cell(i, tt)] = val;
           if (is_beta && tt == Tb - 1 && i == Ub) costs[b] = -val;
-          const int tn = tt + kPrefetch;
+          const int tn = tt + PF;
           if (tn < Tb) {
             pb[j][k] = blank[cell(i, tn)];
             pt[j][k] = truth[cell(i, tn)];
@@ -249,11 +251,11 @@ __global__ void __launch_bounds__(32) rnnt_lattice_warp_kernel(const int32_t* __
 // K2 dispatch: the one-warp kernel where a warp covers the label axis with at most 8 positions per lane, else one thread per position.
 static void launch_rnnt_lattice(const int32_t* tl, const int32_t* ul, int B, int T, int U1, const RnntWs& ws, float* costs, cudaStream_t stream) {
   const dim3 grid(B, 2);
-  if (U1 <= 32) rnnt_lattice_warp_kernel<1><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
-  else if (U1 <= 64) rnnt_lattice_warp_kernel<2><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
-  else if (U1 <= 96) rnnt_lattice_warp_kernel<3><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
-  else if (U1 <= 128) rnnt_lattice_warp_kernel<4><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
-  else if (U1 <= 256) rnnt_lattice_warp_kernel<8><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
+  if (U1 <= 32) rnnt_lattice_warp_kernel<1, 16><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
+  else if (U1 <= 64) rnnt_lattice_warp_kernel<2, 16><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
+  else if (U1 <= 96) rnnt_lattice_warp_kernel<3, 16><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
+  else if (U1 <= 128) rnnt_lattice_warp_kernel<4, 16><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
+  else if (U1 <= 256) rnnt_lattice_warp_kernel<8, 8><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
   else rnnt_lattice_kernel<<<grid, 32 * (int)ceil_div(U1, 32), 0, stream>>>(tl, ul, T, U1, ws, costs);
 }
 
