@@ -168,97 +168,6 @@ __global__ void __launch_bounds__(1024) rnnt_lattice_kernel(const int32_t* __res
   }
 }
 
-// K2, one-warp variant (U1 <= 32 * NU): lane l owns the NU consecutive label positions u = l * NU + j.  All cells of one wavefront step depend
-// on the PREVIOUS step only, so a step is NU independent log-add-exps per lane and ONE shuffle (the emit term crossing a lane boundary) — no
-// shared memory, no __syncthreads.  The multi-warp kernel above pays a CTA barrier per step (3 warps at U + 1 = 65): 150 us for the 314
-// dependent steps of the bench shape (profiles/rnnt_logmel_ncu_r02.txt), i.e. 0.48 us per step against ~0.07 us of arithmetic.
-// With steps that short the operand prefetch must run PF = 16 steps ahead (4 was enough at 0.48 us per step: one warp per SM has nothing
-// else to hide a global-load latency behind).
-template <int NU, int PF>
-__global__ void __launch_bounds__(32) rnnt_lattice_warp_kernel(const int32_t* __restrict__ logit_len, const int32_t* __restrict__ label_len, int T, int U1,
-                                                               RnntWs ws, float* __restrict__ costs) {
-  const int b = blockIdx.x;
-  const bool is_beta = blockIdx.y == 1;
-  const int lane = threadIdx.x;
-  int Tb, Ub;
-  lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
-  if (Tb <= 0) {
-    if (is_beta && lane == 0) costs[b] = CUDART_INF_F;
-    return;
-  }
-  const size_t base = (size_t)b * T * U1;
-  const float* __restrict__ blank = ws.blank + base;
-  const float* __restrict__ truth = ws.truth + base;
-  float* __restrict__ out = (is_beta ? ws.beta : ws.alpha) + base;
-  const int nsteps = Tb + Ub;
-  // cell j of this lane: position i = lane * NU + j in "own" coordinates (alpha: u = i; beta: u = Ub - i), own-time tt = n - i
-  auto cell = [&](int i, int tt) -> size_t { return (size_t)(is_beta ? (Tb - 1 - tt) : tt) * U1 + (is_beta ? Ub - i : i); };
-  float stay[NU], emit[NU];       // emit[j]: value cell j offers to position i + 1 at the next step
-  float pb[NU][PF], pt[NU][PF];
-#pragma unroll
-  for (int j = 0; j < NU; ++j) {
-    const int i = lane * NU + j;
-    stay[j] = (i == 0) ? 0.f : -CUDART_INF_F;
-    emit[j] = -CUDART_INF_F;
-#pragma unroll
-    for (int k = 0; k < PF; ++k) {
-      const int tt0 = (((k - i) % PF) + PF) % PF;
-      const bool ok = i <= Ub && tt0 < Tb;
-      pb[j][k] = ok ? blank[cell(i, tt0)] : 0.f;
-      pt[j][k] = ok ? truth[cell(i, tt0)] : 0.f;
-    }
-  }
-  for (int n0 = 0; n0 < nsteps; n0 += PF) {
-#pragma unroll
-    for (int k = 0; k < PF; ++k) {
-      const int n = n0 + k;
-      float from_left = __shfl_up_sync(0xffffffffu, emit[NU - 1], 1);
-      if (lane == 0) from_left = -CUDART_INF_F;
-      float new_emit[NU];
-#pragma unroll
-      for (int j = 0; j < NU; ++j) {
-        const int i = lane * NU + j;
-        const int tt = n - i;
-        const float emit_in = (j == 0) ? from_left : emit[j - 1];
-        new_emit[j] = -CUDART_INF_F;
-        if (i <= Ub && tt >= 0 && tt < Tb) {
-          const float bl = pb[j][k], tr = pt[j][k];
-          float val;
-          if (!is_beta) {
-            val = log_add_exp_fast(stay[j], emit_in);
-            stay[j] = val + bl;
-            new_emit[j] = val + tr;
-          } else {
-            val = log_add_exp_fast(stay[j] + bl, emit_in + tr);
-            stay[j] = val;
-            new_emit[j] = val;
-          }
-          out[cell(i, tt)] = val;
-          if (is_beta && tt == Tb - 1 && i == Ub) costs[b] = -val;
-          const int tn = tt + PF;
-          if (tn < Tb) {
-            pb[j][k] = blank[cell(i, tn)];
-            pt[j][k] = truth[cell(i, tn)];
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NU; ++j) emit[j] = new_emit[j];
-    }
-  }
-}
-
-// K2 dispatch: the one-warp kernel where a warp covers the label axis with at most 8 positions per lane, else one thread per position.
-static void launch_rnnt_lattice(const int32_t* tl, const int32_t* ul, int B, int T, int U1, const RnntWs& ws, float* costs, cudaStream_t stream) {
-  const dim3 grid(B, 2);
-  if (U1 <= 32) rnnt_lattice_warp_kernel<1, 16><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
-  else if (U1 <= 64) rnnt_lattice_warp_kernel<2, 16><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
-  else if (U1 <= 96) rnnt_lattice_warp_kernel<3, 16><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
-  else if (U1 <= 128) rnnt_lattice_warp_kernel<4, 16><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
-  else if (U1 <= 256) rnnt_lattice_warp_kernel<8, 8><<<grid, 32, 0, stream>>>(tl, ul, T, U1, ws, costs);
-  else rnnt_lattice_kernel<<<grid, 32 * (int)ceil_div(U1, 32), 0, stream>>>(tl, ul, T, U1, ws, costs);
-}
-
 // ---------------------------------------------------------------------------------------------- K3
 template <int NV4>
 __global__ void __launch_bounds__(kRowWarps * 32) rnnt_grad_kernel(const float* logits, const int32_t* __restrict__ labels,
@@ -488,7 +397,8 @@ static int rnnt_forward(const float* logits, const int32_t* labels, const int32_
     default: rnnt_lse_kernel<0><<<grid, kRowWarps * 32, 0, stream>>>(logits, labels, tl, ul, B, T, U1, V, ws); break;
   }
   count_launch();
-  launch_rnnt_lattice(tl, ul, B, T, U1, ws, costs, stream);
+  const int threads = 32 * (int)ceil_div(U1, 32);
+  rnnt_lattice_kernel<<<dim3(B, 2), threads, 0, stream>>>(tl, ul, T, U1, ws, costs);
   count_launch();
   return check_launch();
 }
@@ -572,7 +482,8 @@ extern "C" int tfasr_rnnt_loss_fwd_rowstats_f32(const float* logits, const float
   const RnntWs ws = rnnt_ws_carve(workspace, B, T, U1);
   st = tfasr_rnnt_lse_from_rowstats_f32(logits, rowstats, parts, labels, logit_len, label_len, B, T, U1, V, ws.lse, ws.blank, ws.truth, stream_);
   if (st != TFASR_OK) return st;
-  launch_rnnt_lattice(logit_len, label_len, B, T, U1, ws, costs, static_cast<cudaStream_t>(stream_));
+  const int threads = 32 * (int)ceil_div(U1, 32);
+  rnnt_lattice_kernel<<<dim3(B, 2), threads, 0, static_cast<cudaStream_t>(stream_)>>>(logit_len, label_len, T, U1, ws, costs);
   count_launch();
   return check_launch();
 }
