@@ -1,6 +1,6 @@
 """Augmentation — host-side mirror of tensorflow_asr/augmentations/augmentation.py for the feature-level SpecAugment
 (`feature_augment: {time_masking: {...}, freq_masking: {...}}`, e.g. conformer small.yml.j2:13-24), run by ONE in-place CUDA kernel
-(`tfasr_specaugment_f32`).  Signal-level augmentations (gauss noise) are outside the hot path."""
+(`tfasr_specaugment_f32`), and for the signal-level `gauss_noise`."""
 from __future__ import annotations
 
 import torch
@@ -10,10 +10,24 @@ from . import _lib
 _SALT = 0x5EC0A06
 
 
-def signal_augment(config, signals, signals_length):
-    if config.get("signal_augment"):
-        raise NotImplementedError("signal_augment (GaussNoise, augmentations/methods/gaussnoise.py:19) is outside the B200 hot path")
-    return signals, signals_length
+def signal_augment(config, signals, signals_length, generator=None):
+    """`signal_augment: {gauss_noise: {mean, stddev, prob}}` (augmentations/methods/gaussnoise.py:19-40, applied per utterance by
+    Augmentation.signal_augment's map_fn, augmentation.py:43-65): with probability `prob` per utterance add N(mean, stddev) noise to the
+    samples inside the utterance's length.  Device-side random draws (torch's generator: the stream differs from TF's, like SpecAugment's)."""
+    sa = config.get("signal_augment") or {}
+    unknown = set(sa) - {"gauss_noise"}
+    if unknown:
+        raise KeyError(f"No augmentation named: {sorted(unknown)}; available: ['gauss_noise'] (signal), ['freq_masking', 'time_masking'] (feature)")
+    if "gauss_noise" not in sa:
+        return signals, signals_length
+    gn = sa["gauss_noise"] or {}
+    mean, stddev, prob = float(gn.get("mean", 0.0)), float(gn.get("stddev", 0.075)), float(gn.get("prob", 0.5))
+    B, N = signals.shape
+    dev = signals.device
+    apply = (torch.rand(B, device=dev, generator=generator) <= prob).to(signals.dtype)[:, None]
+    noise = torch.randn(B, N, device=dev, dtype=signals.dtype, generator=generator) * stddev + mean
+    inside = (torch.arange(N, device=dev)[None, :] < signals_length.to(dev)[:, None]).to(signals.dtype)
+    return signals + noise * inside * apply, signals_length
 
 
 def feature_augment(config, features, features_length, seed=None):

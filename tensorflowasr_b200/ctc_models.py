@@ -224,8 +224,24 @@ class CtcModel(BaseModel):
         tokens[rows[keep], pos[keep]] = best[keep].to(torch.int32)
         return schemas.PredictOutput(tokens=tokens, next_tokens=None, next_encoder_states=None, next_decoder_states=None)
 
-    def recognize_beam(self, inputs, beam_width=10, **kwargs):
-        raise NotImplementedError("CTC beam search (tf.nn.ctc_beam_search_decoder, base_ctc.py:128-160) is outside the hot path (SURVEY.md §8)")
+    @torch.no_grad()
+    def recognize_beam(self, inputs: schemas.PredictInput, beam_width: int = 10, blank=None, **kwargs):
+        """tf.nn.ctc_beam_search_decoder(inputs, sequence_length, beam_width) (base_ctc.py:128-160): the encoder / decoder run on the GPU,
+        the prefix beam search on the host like TensorFlow's own CPU op (ctc_decode.py).  `blank=None` keeps the reference call's quirk
+        (TensorFlow's default blank = the last class); pass `self.blank` for the index the model trains with.  tokens [B, max_decoded]
+        int32, zero padded (tf.sparse.to_dense)."""
+        from .ctc_decode import ctc_beam_search
+
+        out = self.call(schemas.TrainInput(inputs.inputs, inputs.inputs_length, None, None), training=False)
+        logits = out.logits.float().cpu().numpy()
+        lens = out.logits_length.cpu().tolist()
+        paths = [ctc_beam_search(logits[b], lens[b], beam_width=beam_width, blank=blank) for b in range(logits.shape[0])]
+        maxn = max((len(p) for p in paths), default=0)
+        tokens = torch.zeros(len(paths), maxn, dtype=torch.int32, device=out.logits.device)
+        for b, p in enumerate(paths):
+            if p:
+                tokens[b, : len(p)] = torch.tensor(p, dtype=torch.int32)
+        return schemas.PredictOutput(tokens=tokens, next_tokens=None, next_encoder_states=None, next_decoder_states=None)
 
     def _weight_groups(self):
         return {"encoder": self.encoder, "decoder": self.decoder}

