@@ -52,12 +52,12 @@ def fused_active(x) -> bool:
 
 import os as _os
 
-_FUSED_SEQ = _os.environ.get("TFASR_FUSED_SEQCONV", "0") == "1"
+_FUSED_SEQ = _os.environ.get("TFASR_FUSED_SEQCONV", "1") == "1"
 
 
 def set_fused_seq(flag: bool):
-    """Route the ContextNet / DeepSpeech2 encoder bodies through fused_seq.py's kernels.  Off by default until the
-    GPU parity tests of that path (tests/test_gpu_zz_seqconv.py, written without GPU time) have run green on a B200."""
+    """Route the ContextNet / DeepSpeech2 encoder bodies through fused_seq.py's kernels.  Default since round 2:
+    tests/test_gpu_seqconv.py green on a B200 (kernel level vs torch, both encoders vs the fp32 library route)."""
     global _FUSED_SEQ
     _FUSED_SEQ = bool(flag)
 
