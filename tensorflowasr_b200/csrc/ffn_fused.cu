@@ -32,7 +32,10 @@ namespace tfasr {
 
 // Tile = 64 rows (of a 128-row MMA: TMEM lanes 64..127 compute on stale SMEM and are never read).  The epilogue — sigmoid, dropout hash,
 // packing: ~19 instructions per hidden activation — is what a tile costs, not the tensor work (9 % of the tensor pipe at 128 rows), so the
-// module spreads over 125 SMs instead of 63.  Warps: 2 = TMA producer, 3 = MMA issuer (+ the chunk stores); 0,1 / 4,5 / 8,9 / 12,13 =
+// module spreads over 125 SMs instead of 63.  (Measured: a tile's 64 rows sit in TMEM lane quarters 0 and 1, so its epilogue warps are the
+// warps with id % 4 in {0, 1} — two of the SM's four schedulers; 125 SMs x 2 schedulers is the issue capacity of 63 SMs x 4, which is why this
+// layout gained 3 us per module, not 2x, and why 16 epilogue warps of 8 columns each (1024 threads) measured the same 0.85 us per chunk.  The
+// next step is a 2-CTA cluster per 128-row tile that splits the HIDDEN dimension and reduces the output accumulator over DSMEM.)  Warps: 2 = TMA producer, 3 = MMA issuer (+ the chunk stores); 0,1 / 4,5 / 8,9 / 12,13 =
 // epilogue + LayerNorm (TMEM lane quarters 0 and 1 = the 64 rows; `sub` = which 16 of a chunk's 64 columns); 6,7,10,11 idle.
 constexpr int kFfnEpiWarps = 8;
 constexpr int kFfnThreads = 448;

@@ -266,6 +266,12 @@ static inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   if (lane >= 128 || col + 16 > 512) abort();
   for (int j = 0; j < 16; ++j) r[j] = t->cell[lane][col + j];
 }
+static inline void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  Tmem* t = tmem_of_cta();
+  const uint32_t lane = (taddr >> 16) + (uint32_t)emu::t_lane, col = taddr & 0xFFFF;
+  if (lane >= 128 || col + 8 > 512) abort();
+  for (int j = 0; j < 8; ++j) r[j] = t->cell[lane][col + j];
+}
 static inline void tmem_ld_wait() {}
 
 }  // namespace sm100
