@@ -339,25 +339,37 @@ def _run_ours(args, real_stdout):
     except (OSError, ValueError):
         pass
     timing = "CUDA events on the launching stream around the launches, same step run eagerly right after the timed region"
-    alg_bytes = 8 * rows * VOCAB
+    from tensorflowasr_b200 import ops as _ops
+
+    # algorithmic bytes per lattice node and vocabulary entry: the survey's 8 B (f32 logits read once + gradient written once) on the
+    # f32-logits route; 2 + 2 B with bf16 logits (ops.bf16_logits), where the tensors are half the size — the fraction is quoted on the
+    # bytes the route has to move, the survey's count is kept beside it
+    lb = 2 if _ops.bf16_logits_active() else 4
+    alg_bytes = (lb + (2 if lb == 2 else 4)) * rows * VOCAB
+    tkey = "rnnt_loss_grad_bf16_logits" if lb == 2 else "rnnt_loss_grad"
     rn_ms = kernel_ms.get("rnnt_fwd", 0.0) + kernel_ms.get("rnnt_bwd", 0.0)
     roofline = None
     if rn_ms > 0:
         ach = alg_bytes / (rn_ms * 1e-3) / 1e9
+        gk_ms = kernel_ms.get("rnnt_bwd", 0.0)
         roofline = {"kernel": ("rnnt_lse_combine_kernel (log-softmax normaliser from the joint GEMM's row statistics) + rnnt_lattice_kernel + "
-                               "rnnt_grad_bf16_v2_kernel (RNN-T loss + gradient, one launch each per step)"),
+                               + ("rnnt_grad_bf16_io_kernel (bf16 logits -> bf16 gradient in place)" if lb == 2 else "rnnt_grad_bf16_v2_kernel")
+                               + " (RNN-T loss + gradient, one launch each per step)"),
                     "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                    "traffic": traffic.get("rnnt_loss_grad", {}).get("bytes"), "traffic_source": traffic.get("rnnt_loss_grad", {}).get("source"),
-                    "peak_source": pk["_source"], "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": rn_ms, "share_of_step": rn_ms / ms,
+                    "traffic": traffic.get(tkey, {}).get("bytes"), "traffic_source": traffic.get(tkey, {}).get("source"),
+                    "peak_source": pk["_source"], "algorithmic_bytes_per_launch": alg_bytes, "logit_bytes": lb,
+                    "survey_bytes_per_launch": 8 * rows * VOCAB, "ms_per_launch": rn_ms, "share_of_step": rn_ms / ms,
+                    "gradient_kernel": {"ms": gk_ms, "frac": (alg_bytes / (gk_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if gk_ms > 0 else None,
+                                        "note": "the byte-moving launch alone; the group also holds the latency-bound lattice wavefronts"},
                     "timing": timing}
     jg_ms = kernel_ms.get("joint_gemm_fwd", 0.0)
     roofline_joint = None
     if jg_ms > 0:
         gemm_flops = 2.0 * rows * J * VOCAB
-        gemm_bytes = 2.0 * rows * J + 2.0 * VOCAB * J + 4.0 * rows * VOCAB
+        gemm_bytes = 2.0 * rows * J + 2.0 * VOCAB * J + float(lb) * rows * VOCAB
         ach = gemm_bytes / (jg_ms * 1e-3) / 1e9
         tpeak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        roofline_joint = {"kernel": "gemm_bf16_kernel<256> (joint logits = tanh(e+p) . Wv + bv, f32 out through TMA stores)", "bound": "hbm",
+        roofline_joint = {"kernel": f"gemm_bf16_kernel<256> (joint logits = tanh(e+p) . Wv + bv, {'bf16' if lb == 2 else 'f32'} out through TMA stores)", "bound": "hbm",
                           "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                           "traffic": traffic.get("joint_gemm", {}).get("bytes"), "traffic_source": traffic.get("joint_gemm", {}).get("source"),
                           "algorithmic_bytes_per_launch": gemm_bytes, "algorithmic_flops_per_launch": gemm_flops,

@@ -125,6 +125,19 @@ int tfasr_rnnt_loss_bwd_bf16_v2(const float* logits, const int32_t* labels, cons
                                 int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
                                 int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
 
+/* bf16-logits variants (ops.bf16_logits; SURVEY 8f N1, second step): the joint GEMM stores bf16 logits and takes its row statistics over the
+ * ROUNDED values, so the head computes the exact RNN-T loss and gradient of the stored logits; the [B,T,U1,V] tensor is 2 bytes per entry
+ * and its gradient replaces it in place (grads == logits, ld_grads = V).  Same workspace layout; V % 4 == 0, V <= 2048. */
+int tfasr_rnnt_lse_from_rowstats_bf16(const void* logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
+                                      const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V, float* lse, float* blank,
+                                      float* truth, tfasr_stream_t stream);
+int tfasr_rnnt_loss_fwd_rowstats_bf16(const void* logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
+                                      const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V, int32_t blank, float* costs,
+                                      void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
+int tfasr_rnnt_loss_bwd_bf16_io(const void* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
+                                int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
+                                int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * CTC loss + gradient (tf.nn.ctc_loss, dense labels, batch-major logits [B, T, V], blank_index 0).
  *   costs [B] f32; grads [B, T, V] f32 = d costs[b] / d logits (may alias logits).  Infeasible

@@ -391,6 +391,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if constexpr (F::rs) {
+            if (!c_f32) {  // bf16 output: the statistics describe the values as stored, so that exp(stored - lse) sums to one exactly
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+            }
             // online log-sum-exp over the valid columns of this 16-column chunk
             float cm = -CUDART_INF_F;
 #pragma unroll

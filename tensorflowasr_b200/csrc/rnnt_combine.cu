@@ -14,7 +14,12 @@ typedef void* cudaStream_t;
 
 namespace tfasr {
 
-__global__ void __launch_bounds__(256) rnnt_lse_combine_kernel(const float* __restrict__ logits, const float2* __restrict__ rowstats, int P,
+__device__ __forceinline__ float logit_f(const float* x, int j) { return x[j]; }
+__device__ __forceinline__ float logit_f(const __nv_bfloat16* x, int j) { return __bfloat162float(x[j]); }
+
+// LT = float, or __nv_bfloat16 (the joint GEMM writes bf16 logits and takes its statistics over the rounded values: ops.bf16_logits)
+template <typename LT>
+__global__ void __launch_bounds__(256) rnnt_lse_combine_kernel(const LT* __restrict__ logits, const float2* __restrict__ rowstats, int P,
                                                                const int32_t* __restrict__ labels, const int32_t* __restrict__ logit_len,
                                                                const int32_t* __restrict__ label_len, int B, int T, int U1, int V,
                                                                float* __restrict__ lse, float* __restrict__ blank, float* __restrict__ truth) {
@@ -35,10 +40,10 @@ __global__ void __launch_bounds__(256) rnnt_lse_combine_kernel(const float* __re
       if (ps.y > 0.f) acc = fmaf(ps.y, __expf(ps.x - m), acc);
     }
     const float l = m + logf(acc);
-    const float* x = logits + (size_t)row * V;
+    const LT* x = logits + (size_t)row * V;
     lse[row] = l;
-    blank[row] = x[0] - l;
-    truth[row] = (u < Ub) ? x[labels[(size_t)b * (U1 - 1) + u]] - l : -CUDART_INF_F;
+    blank[row] = logit_f(x, 0) - l;
+    truth[row] = (u < Ub) ? logit_f(x, labels[(size_t)b * (U1 - 1) + u]) - l : -CUDART_INF_F;
   }
 }
 
@@ -46,9 +51,10 @@ __global__ void __launch_bounds__(256) rnnt_lse_combine_kernel(const float* __re
 
 using namespace tfasr;
 
-extern "C" int tfasr_rnnt_lse_from_rowstats_f32(const float* logits, const float* rowstats, int32_t parts, const int32_t* labels,
-                                                const int32_t* logit_len, const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V,
-                                                float* lse, float* blank, float* truth, tfasr_stream_t stream_) {
+template <typename LT>
+static int lse_from_rowstats(const LT* logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
+                             const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V, float* lse, float* blank, float* truth,
+                             tfasr_stream_t stream_) {
   if (!logits || !rowstats || parts < 1 || !logit_len || !label_len || (U1 > 1 && !labels) || B < 0 || T < 1 || U1 < 1 || V < 2 || !lse || !blank ||
       !truth || (reinterpret_cast<uintptr_t>(rowstats) & 7))
     return TFASR_INVALID_VALUE;
@@ -59,13 +65,26 @@ extern "C" int tfasr_rnnt_lse_from_rowstats_f32(const float* logits, const float
 #ifdef TFASR_EMU_BUILD
   (void)stream_;
   emu::launch(dim3((unsigned)g), dim3(256), 0, [&] {
-    rnnt_lse_combine_kernel(logits, reinterpret_cast<const float2*>(rowstats), parts, labels, logit_len, label_len, B, T, U1, V, lse, blank, truth);
+    rnnt_lse_combine_kernel<LT>(logits, reinterpret_cast<const float2*>(rowstats), parts, labels, logit_len, label_len, B, T, U1, V, lse, blank, truth);
   });
   return TFASR_OK;
 #else
-  rnnt_lse_combine_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream_)>>>(logits, reinterpret_cast<const float2*>(rowstats), parts, labels,
-                                                                                      logit_len, label_len, B, T, U1, V, lse, blank, truth);
+  rnnt_lse_combine_kernel<LT><<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream_)>>>(logits, reinterpret_cast<const float2*>(rowstats), parts,
+                                                                                          labels, logit_len, label_len, B, T, U1, V, lse, blank, truth);
   count_launch();
   return check_launch();
 #endif
+}
+
+extern "C" int tfasr_rnnt_lse_from_rowstats_f32(const float* logits, const float* rowstats, int32_t parts, const int32_t* labels,
+                                                const int32_t* logit_len, const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V,
+                                                float* lse, float* blank, float* truth, tfasr_stream_t stream) {
+  return lse_from_rowstats<float>(logits, rowstats, parts, labels, logit_len, label_len, B, T, U1, V, lse, blank, truth, stream);
+}
+
+extern "C" int tfasr_rnnt_lse_from_rowstats_bf16(const void* logits, const float* rowstats, int32_t parts, const int32_t* labels,
+                                                 const int32_t* logit_len, const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V,
+                                                 float* lse, float* blank, float* truth, tfasr_stream_t stream) {
+  return lse_from_rowstats<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(logits), rowstats, parts, labels, logit_len, label_len, B, T, U1, V, lse,
+                                          blank, truth, stream);
 }

@@ -125,6 +125,100 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_v2_kernel(con
   }
 }
 
+// bf16 logits in, bf16 gradient out (ops.bf16_logits): element j of a row is read and written by the same lane, so grads may alias logits
+// (ld_g = V) with no ordering concern.  NV2 = uint2 (4 bf16) per lane (V <= 128 * NV2): 4 B per lattice node and vocabulary entry.
+template <int NV2>
+__global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_io_kernel(const __nv_bfloat16* logits, const int32_t* __restrict__ labels,
+                                                                             const int32_t* __restrict__ logit_len,
+                                                                             const int32_t* __restrict__ label_len, int B, int T, int U1, int V,
+                                                                             RnntPlanes ws, const float* __restrict__ costs,
+                                                                             const float* __restrict__ grad_scale, __nv_bfloat16* grads, int64_t ld_g,
+                                                                             float* __restrict__ dbias) {
+  TFASR_DYN_SMEM(smem_raw);
+  float* s_cs = reinterpret_cast<float*>(smem_raw);  // [kG2Warps][V] when dbias
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nrows = (int64_t)B * T * U1;
+  const int n4 = V >> 2;
+  if (dbias) {
+    for (int j = threadIdx.x; j < kG2Warps * V; j += blockDim.x) s_cs[j] = 0.f;
+    __syncthreads();
+  }
+  float4* cs4 = reinterpret_cast<float4*>(s_cs + (size_t)warp * V);
+  for (int64_t row = (int64_t)blockIdx.x * kG2Warps + warp; row < nrows; row += (int64_t)gridDim.x * kG2Warps) {
+    const int u = (int)(row % U1);
+    const int t = (int)((row / U1) % T);
+    const int b = (int)(row / ((int64_t)U1 * T));
+    int Tb, Ub;
+    lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
+    uint2* g2 = reinterpret_cast<uint2*>(grads + row * ld_g);
+    if (!((t < Tb) && (u <= Ub))) {
+      for (int j = lane; j < n4; j += 32) g2[j] = make_uint2(0u, 0u);
+      continue;
+    }
+    const float logz = -costs[b];
+    const float a = ws.alpha[row];
+    const float lse = ws.lse[row];
+    float gb = 0.f, gt = 0.f;
+    int label = -1;
+    if (t < Tb - 1) gb = -expf(a + ws.beta[row + U1] + ws.blank[row] - logz);
+    else if (u == Ub) gb = -1.0f;
+    if (u < Ub) {
+      gt = -expf(a + ws.beta[row + 1] + ws.truth[row] - logz);
+      label = labels[(int64_t)b * (U1 - 1) + u];
+    }
+    const float sc = grad_scale ? grad_scale[b] : 1.0f;
+    gb *= sc;
+    gt *= sc;
+    const float gsum = gb + gt;
+    const uint2* x2 = reinterpret_cast<const uint2*>(logits + row * V);
+    uint2 v[NV2];
+#pragma unroll
+    for (int i = 0; i < NV2; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n4) v[i] = simt_ld_stream_u2(x2 + j);
+    }
+#pragma unroll
+    for (int i = 0; i < NV2; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n4) {
+        float4 o;
+        o.x = -__expf(__uint_as_float(v[i].x << 16) - lse) * gsum;
+        o.y = -__expf(__uint_as_float(v[i].x & 0xffff0000u) - lse) * gsum;
+        o.z = -__expf(__uint_as_float(v[i].y << 16) - lse) * gsum;
+        o.w = -__expf(__uint_as_float(v[i].y & 0xffff0000u) - lse) * gsum;
+        const int c0 = 4 * j;
+        if (c0 == 0) o.x += gb;
+        if (label >= c0 && label < c0 + 4) {
+          const int r = label - c0;
+          if (r == 0) o.x += gt;
+          else if (r == 1) o.y += gt;
+          else if (r == 2) o.z += gt;
+          else o.w += gt;
+        }
+        if (dbias) {
+          float4 c = cs4[j];
+          c.x += o.x;
+          c.y += o.y;
+          c.z += o.z;
+          c.w += o.w;
+          cs4[j] = c;
+        }
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        g2[j] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      }
+    }
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kG2Warps; ++w) s += s_cs[(size_t)w * V + j];
+      atomicAdd(dbias + j, s);
+    }
+  }
+}
+
 }  // namespace tfasr
 
 using namespace tfasr;
@@ -171,6 +265,57 @@ extern "C" int tfasr_rnnt_loss_bwd_bf16_v2(const float* logits, const int32_t* l
   else if (V <= 512) G2_LAUNCH(2);
   else if (V <= 1024) G2_LAUNCH(4);
   else G2_LAUNCH(8);
+#undef G2_LAUNCH
+#ifdef TFASR_EMU_BUILD
+  return TFASR_OK;
+#else
+  return check_launch();
+#endif
+}
+
+/* bf16 logits -> bf16 gradient (may be in place: grads == logits, ld_grads = V); everything else as tfasr_rnnt_loss_bwd_bf16_v2 */
+extern "C" int tfasr_rnnt_loss_bwd_bf16_io(const void* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
+                                           int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
+                                           int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream_) {
+  if (blank != 0 || B < 0 || T < 1 || U1 < 1 || V < 2 || U1 > 1024) return TFASR_INVALID_VALUE;
+  if (!logits || !logit_len || !label_len || !workspace || (U1 > 1 && !labels) || !costs || !grads || ld_grads < V || (ld_grads & 3))
+    return TFASR_INVALID_VALUE;
+  if ((V & 3) || V > 2048 || (reinterpret_cast<uintptr_t>(logits) & 7) || (reinterpret_cast<uintptr_t>(grads) & 7)) return TFASR_INVALID_VALUE;
+  const size_t plane = (sizeof(float) * (size_t)B * T * U1 + 255) / 256 * 256;
+  if (workspace_bytes < 5 * plane) return TFASR_WORKSPACE_TOO_SMALL;
+  if (B == 0) return TFASR_OK;
+  const char* wp = static_cast<const char*>(workspace);
+  RnntPlanes ws;
+  ws.lse = reinterpret_cast<const float*>(wp);
+  ws.blank = reinterpret_cast<const float*>(wp + plane);
+  ws.truth = reinterpret_cast<const float*>(wp + 2 * plane);
+  ws.alpha = reinterpret_cast<const float*>(wp + 3 * plane);
+  ws.beta = reinterpret_cast<const float*>(wp + 4 * plane);
+  const int64_t nrows = (int64_t)B * T * U1;
+  int64_t ctas = ceil_div(nrows, kG2Warps);
+  if (ctas > (int64_t)kNumSMs * 12) ctas = (int64_t)kNumSMs * 12;
+  const size_t smem = dbias ? sizeof(float) * (size_t)kG2Warps * V : 0;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(logits);
+  __nv_bfloat16* g = static_cast<__nv_bfloat16*>(grads);
+#ifdef TFASR_EMU_BUILD
+  (void)stream_;
+#define G2_LAUNCH(N) \
+  emu::launch(dim3((unsigned)ctas), dim3(kG2Warps * 32), smem, [&] { rnnt_grad_bf16_io_kernel<N>(x, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, ld_grads, dbias); })
+#else
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+#define G2_LAUNCH(N)                                                                                                                         \
+  do {                                                                                                                                       \
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(rnnt_grad_bf16_io_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+      return TFASR_EXECUTION_FAILED;                                                                                                         \
+    rnnt_grad_bf16_io_kernel<N><<<(unsigned)ctas, kG2Warps * 32, smem, stream>>>(x, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, \
+                                                                                 ld_grads, dbias);                                          \
+    count_launch();                                                                                                                          \
+  } while (0)
+#endif
+  if (V <= 256) G2_LAUNCH(2);
+  else if (V <= 512) G2_LAUNCH(4);
+  else if (V <= 1024) G2_LAUNCH(8);
+  else G2_LAUNCH(16);
 #undef G2_LAUNCH
 #ifdef TFASR_EMU_BUILD
   return TFASR_OK;

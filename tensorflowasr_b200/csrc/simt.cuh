@@ -59,6 +59,18 @@ __device__ __forceinline__ float4 simt_ld_stream_f4(const float4* p) {
 #endif
 }
 
+// read-once 8-byte global load
+__device__ __forceinline__ uint2 simt_ld_stream_u2(const uint2* p) {
+#ifdef TFASR_EMU_BUILD
+  if (reinterpret_cast<uintptr_t>(p) & 7) abort();
+  return *p;
+#else
+  uint2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+#endif
+}
+
 __device__ __forceinline__ float simt_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // activation codes shared with the BatchNorm kernels: 0 none, 1 swish, 2 relu
 __device__ __forceinline__ float simt_act(float z, int act) {

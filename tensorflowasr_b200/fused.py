@@ -442,14 +442,21 @@ class _TransducerHeadFn(torch.autograd.Function):
         h = kernels.joint_tanh_fwd(e.contiguous(), p.contiguous())
         fused_lse = ops.fused_lse_active()
         parts = 2 * ((V + 255) // 256)
+        bf16_logits = ops.bf16_logits_active() and V % 4 == 0
         rowstats = torch.empty((M, parts, 2), dtype=torch.float32, device=e.device) if fused_lse else None
         with _lib.TIMERS.region("joint_gemm_fwd"):
-            logits = kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out_dtype=torch.float32, rowstats=rowstats)
+            logits = kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out_dtype=torch.bfloat16 if bf16_logits else torch.float32,
+                                  rowstats=rowstats)
         ws_bytes = lib.tfasr_rnnt_workspace_bytes(B, T, U1, V)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=e.device)
         costs = torch.empty(B, dtype=torch.float32, device=e.device)
         with _lib.TIMERS.region("rnnt_fwd"):
-            if fused_lse:
+            if bf16_logits:
+                _lib.check(lib.tfasr_rnnt_loss_fwd_rowstats_bf16(logits.data_ptr(), rowstats.data_ptr(), parts, labels.data_ptr(),
+                                                                 logit_length.data_ptr(), label_length.data_ptr(), B, T, U1, V, 0, costs.data_ptr(),
+                                                                 ws.data_ptr(), ws_bytes, _lib.stream_ptr(e.device)),
+                           "tfasr_rnnt_loss_fwd_rowstats_bf16")
+            elif fused_lse:
                 # the log-softmax normaliser comes from the GEMM epilogue's row statistics: the logits are not read again before K3
                 _lib.check(lib.tfasr_rnnt_loss_fwd_rowstats_f32(logits.data_ptr(), rowstats.data_ptr(), parts, labels.data_ptr(),
                                                                 logit_length.data_ptr(), label_length.data_ptr(), B, T, U1, V, 0, costs.data_ptr(),
@@ -472,14 +479,18 @@ class _TransducerHeadFn(torch.autograd.Function):
         pack, (B, T, U1, J, V), de_dtype, dp_dtype = ctx.misc
         M = B * T * U1
         scale = dcosts.float().contiguous()
-        dl = logits.view(M, V).view(torch.bfloat16)  # [M, 2V] bf16 view of the same memory; gradient lands in [:, :V]
         from . import ops
 
-        bwd_fn, bwd_name = ((lib.tfasr_rnnt_loss_bwd_bf16_v2, "tfasr_rnnt_loss_bwd_bf16_v2") if ops.rnnt_grad_v2_active()
-                            else (lib.tfasr_rnnt_loss_bwd_bf16, "tfasr_rnnt_loss_bwd_bf16"))
+        if logits.dtype == torch.bfloat16:  # bf16 logits: the gradient replaces them element for element
+            dl, ld = logits.view(M, V), V
+            bwd_fn, bwd_name = lib.tfasr_rnnt_loss_bwd_bf16_io, "tfasr_rnnt_loss_bwd_bf16_io"
+        else:
+            dl, ld = logits.view(M, V).view(torch.bfloat16), 2 * V  # [M, 2V] bf16 view of the same memory; gradient lands in [:, :V]
+            bwd_fn, bwd_name = ((lib.tfasr_rnnt_loss_bwd_bf16_v2, "tfasr_rnnt_loss_bwd_bf16_v2") if ops.rnnt_grad_v2_active()
+                                else (lib.tfasr_rnnt_loss_bwd_bf16, "tfasr_rnnt_loss_bwd_bf16"))
         with _lib.TIMERS.region("rnnt_bwd"):
             _lib.check(bwd_fn(logits.data_ptr(), labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(), B, T, U1, V, 0,
-                              costs.data_ptr(), scale.data_ptr(), dl.data_ptr(), 2 * V, _grad(pack.bias).data_ptr(), ws.data_ptr(), ws.numel(),
+                              costs.data_ptr(), scale.data_ptr(), dl.data_ptr(), ld, _grad(pack.bias).data_ptr(), ws.data_ptr(), ws.numel(),
                               _lib.stream_ptr(h.device)), bwd_name)
         dlv = dl[:, :V]
         h2 = h.view(M, J)

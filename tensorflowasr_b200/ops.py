@@ -195,6 +195,22 @@ def fused_lse_active() -> bool:
     return _FUSED_LSE
 
 
+_BF16_LOGITS = _os.environ.get("TFASR_BF16_LOGITS", "0") == "1"
+
+
+def set_bf16_logits(flag: bool):
+    """Training head (needs fused_lse): the joint GEMM stores the [B,T,U+1,V] logits as bf16 — statistics taken over the rounded values, so
+    the loss and the gradient are exact for the stored logits — and csrc/rnnt_grad_v2.cu (bf16_io) replaces them by their gradient in
+    place: 4 B per lattice node and vocabulary entry instead of 8, and the joint's backward GEMMs read rows of pitch V instead of 2V
+    (second step)."""
+    global _BF16_LOGITS
+    _BF16_LOGITS = bool(flag)
+
+
+def bf16_logits_active() -> bool:
+    return _BF16_LOGITS and _FUSED_LSE
+
+
 _PERSISTENT_DECODE = _os.environ.get("TFASR_PERSISTENT_DECODE", "1") == "1"
 
 
@@ -243,7 +259,7 @@ def attention_tc_active(T: int = 0) -> bool:
 
 
 _SWITCHES = ("_FUSED_FFN", "_FUSED", "_FUSED_SEQ", "_DWCONV_WGRAD_V2", "_JOINT_REDUCE_V2", "_IM2COL_V2", "_JOINT_V2", "_RNNT_GRAD_V2", "_CONV1_V2", "_POS_BATCHED",
-             "_PEER_BN", "_FUSED_LSE", "_PERSISTENT_DECODE")
+             "_PEER_BN", "_FUSED_LSE", "_PERSISTENT_DECODE", "_BF16_LOGITS")
 
 
 def switch_state() -> dict:

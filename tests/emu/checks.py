@@ -32,7 +32,7 @@ def load(asan=False, tsan=False):
     import build_emu
 
     lib = ctypes.CDLL(build_emu.build(asan=asan, tsan=tsan))
-    for name in ("tfasr_greedy_decode_f32", "tfasr_dwconv_causal_wgrad_v2", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_peer_allreduce_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
+    for name in ("tfasr_greedy_decode_f32", "tfasr_dwconv_causal_wgrad_v2", "tfasr_im2col_3x3s2_v2", "tfasr_col2im_3x3s2_v2", "tfasr_joint_tanh_fwd_v2", "tfasr_joint_reduce_bwd_v2", "tfasr_rnnt_loss_bwd_bf16_v2", "tfasr_conv1_3x3s2_fwd_v2", "tfasr_conv1_3x3s2_wgrad_v2", "tfasr_rnnt_lse_from_rowstats_f32", "tfasr_rnnt_lse_from_rowstats_bf16", "tfasr_rnnt_loss_bwd_bf16_io", "tfasr_peer_allreduce_f32", "tfasr_seq_dwconv_fwd", "tfasr_seq_dwconv_bwd", "tfasr_seq_masked_mean", "tfasr_se_fc_fwd", "tfasr_se_fc_bwd", "tfasr_se_apply_fwd",
                  "tfasr_se_apply_bwd", "tfasr_se_dy", "tfasr_conv_im2col", "tfasr_conv_col2im"):
         getattr(lib, name).restype = c_i32
     return lib
@@ -468,18 +468,21 @@ def gemm_rowstats_ref(logits2d, BN=256):
     return out
 
 
-def check_rnnt_combine(lib, B, T, U1, V, logit_len, label_len, seed=12):
+def check_rnnt_combine(lib, B, T, U1, V, logit_len, label_len, seed=12, bf16=False):
     rng = np.random.default_rng(seed)
     logits = (rng.standard_normal((B, T, U1, V)) * 3).astype(np.float32)
+    if bf16:  # bf16 logits (ops.bf16_logits): the statistics describe the rounded values
+        logits = rbf(logits)
     labels = rng.integers(1, V, (B, max(U1 - 1, 1))).astype(np.int32)
     tl, ul = np.asarray(logit_len, np.int32), np.asarray(label_len, np.int32)
     stats = gemm_rowstats_ref(logits.reshape(-1, V))
     x = logits.astype(np.float64)
     mx = x.max(-1, keepdims=True)
     lse_ref = (mx + np.log(np.exp(x - mx).sum(-1, keepdims=True)))[..., 0]
-    bufs = [heap(a) for a in (logits, stats, labels, tl, ul)]
+    bufs = [heap(a) for a in (to_bf16(logits) if bf16 else logits, stats, labels, tl, ul)]
     outs = [heap(np.full((B, T, U1), np.nan, np.float32)) for _ in range(3)]
-    assert lib.tfasr_rnnt_lse_from_rowstats_f32(bufs[0][1], bufs[1][1], stats.shape[1], bufs[2][1], bufs[3][1], bufs[4][1], B, T, U1, V,
+    fn = lib.tfasr_rnnt_lse_from_rowstats_bf16 if bf16 else lib.tfasr_rnnt_lse_from_rowstats_f32
+    assert fn(bufs[0][1], bufs[1][1], stats.shape[1], bufs[2][1], bufs[3][1], bufs[4][1], B, T, U1, V,
                                                 outs[0][1], outs[1][1], outs[2][1], None) == 0
     lse, blank, truth = (o[0] for o in outs)
     for b in range(B):
@@ -545,9 +548,11 @@ def rnnt_grad_ref(x, labels, Tb, Ub, planes):
     return g
 
 
-def check_rnnt_grad_v2(lib, B, T, U1, V, logit_len, label_len, in_place, seed=14):
+def check_rnnt_grad_v2(lib, B, T, U1, V, logit_len, label_len, in_place, seed=14, bf16_io=False):
     rng = np.random.default_rng(seed)
     logits = rng.standard_normal((B, T, U1, V)).astype(np.float32)
+    if bf16_io:  # tfasr_rnnt_loss_bwd_bf16_io: bf16 logits, gradient element for element over them when in place (pitch V)
+        logits = rbf(logits)
     labels = rng.integers(1, V, (B, max(U1 - 1, 1))).astype(np.int32)
     tl, ul = np.asarray(logit_len, np.int32), np.asarray(label_len, np.int32)
     scale = rng.uniform(0.5, 1.5, B).astype(np.float32)
@@ -582,16 +587,17 @@ def check_rnnt_grad_v2(lib, B, T, U1, V, logit_len, label_len, in_place, seed=14
     sb, sp = heap(scale)
     dbias0 = rng.standard_normal(V).astype(np.float32)
     db, dp = heap(dbias0)
-    xb, xp_ = heap(logits)
+    xb, xp_ = heap(to_bf16(logits) if bf16_io else logits)
     if in_place:
-        gp, ld = xp_, 2 * V  # bf16 gradient of row r in the first half of row r's fp32 logits
+        gp, ld = xp_, (V if bf16_io else 2 * V)  # f32 logits: bf16 gradient of row r in the first half of row r's fp32 logits
     else:
         gb_, gp = heap(np.full((B, T, U1, V + 4), 0x7FC0, np.uint16))
         ld = V + 4
-    st = lib.tfasr_rnnt_loss_bwd_bf16_v2(xp_, lp, tp, up, B, T, U1, V, 0, cp, sp, gp, ctypes.c_int64(ld), dp, wsp, ctypes.c_size_t(ws.nbytes), None)
+    fn = lib.tfasr_rnnt_loss_bwd_bf16_io if bf16_io else lib.tfasr_rnnt_loss_bwd_bf16_v2
+    st = fn(xp_, lp, tp, up, B, T, U1, V, 0, cp, sp, gp, ctypes.c_int64(ld), dp, wsp, ctypes.c_size_t(ws.nbytes), None)
     assert st == 0, st
     if in_place:
-        got = from_bf16(xb.view(np.uint16).reshape(B, T, U1, 2 * V)[..., :V])
+        got = from_bf16(xb.view(np.uint16).reshape(B, T, U1, ld)[..., :V])
     else:
         got = from_bf16(gb_[..., :V])
         assert (gb_[..., V:] == 0x7FC0).all(), "wrote past the row's V columns"
@@ -732,6 +738,8 @@ def check_random_shapes(lib):
         ul = [int(x) for x in rng.integers(0, U1, B)]
         check_rnnt_grad_v2(lib, B, T, U1, 4 * V4, tl, ul, bool(rng.integers(0, 2)), seed=int(rng.integers(1 << 30)))
         check_rnnt_combine(lib, B, T, U1, 4 * V4, tl, ul, seed=int(rng.integers(1 << 30)))
+        check_rnnt_grad_v2(lib, B, T, U1, 4 * V4, tl, ul, bool(rng.integers(0, 2)), seed=int(rng.integers(1 << 30)), bf16_io=True)
+        check_rnnt_combine(lib, B, T, U1, 4 * V4, tl, ul, seed=int(rng.integers(1 << 30)), bf16=True)
     for _ in range(4):
         B, T, F, Cin = int(rng.integers(1, 3)), int(rng.integers(1, 14)), int(rng.integers(1, 14)), int(rng.choice([1, 3, 8, 16]))
         kh, kw, sh, sw = (int(x) for x in rng.integers(1, 6, 4))
@@ -848,6 +856,10 @@ CASES = [
     ("greedy_single", lambda lib: check_greedy_single(lib, 6, 16, 24, 20, 12, 6, 3, 96, seed=8, blank_bias=0.5)),
     ("rnnt_combine_v1000", lambda lib: check_rnnt_combine(lib, 2, 5, 4, 1000, [5, 3], [3, 1])),  # 4 tiles, last one 232 columns wide
     ("rnnt_combine_small_v", lambda lib: check_rnnt_combine(lib, 3, 4, 3, 40, [4, 0, 2], [2, 2, 0])),  # one tile, second slice empty for 1 group
+    ("rnnt_combine_bf16_logits", lambda lib: check_rnnt_combine(lib, 2, 5, 4, 1000, [5, 3], [3, 1], bf16=True)),
+    ("rnnt_grad_bf16_io_in_place", lambda lib: check_rnnt_grad_v2(lib, 3, 5, 4, 1000, [5, 3, 0], [3, 1, 2], True, bf16_io=True)),  # 8 uint2 per lane
+    ("rnnt_grad_bf16_io_pitched", lambda lib: check_rnnt_grad_v2(lib, 2, 4, 3, 40, [4, 2], [2, 0], False, bf16_io=True)),
+    ("rnnt_grad_bf16_io_wide", lambda lib: check_rnnt_grad_v2(lib, 1, 3, 2, 1500, [3], [1], True, bf16_io=True)),  # V > 1024: 16 uint2 per lane
     ("rnnt_grad_v2_in_place", lambda lib: check_rnnt_grad_v2(lib, 3, 5, 4, 1000, [5, 3, 0], [3, 1, 2], True)),  # V = 1000: 4 float4 per lane and half
     ("rnnt_grad_v2_pitched", lambda lib: check_rnnt_grad_v2(lib, 2, 4, 3, 40, [4, 2], [2, 0], False)),  # small V, separate output, ragged
     ("rnnt_grad_v2_wide_in_place", lambda lib: check_rnnt_grad_v2(lib, 1, 3, 2, 1500, [3], [1], True)),  # V > 1024: 8 float4 per lane and half

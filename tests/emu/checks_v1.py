@@ -757,6 +757,9 @@ def check_gemm(lib, M, N, K, *, f32_out=False, bias=False, act=0, aux=False, glu
         close(from_bf16(ab), pre, 8e-3, "gemm aux (pre-activation copy)")
     if colsum:
         close(cb - c0, v.sum(0), 1e-2, "gemm column sums")
+    if rowstats and not f32_out:  # bf16 output: the statistics are those of the values as stored
+        pre = got
+        stats_ref = checks.gemm_rowstats_ref(got.astype(np.float32))
     if rowstats:
         assert np.isfinite(rsb[..., 1]).all()
         m = rsb[..., 0].max(1, keepdims=True)
@@ -963,6 +966,7 @@ CASES = [
     ("gemm_mn_major_odd", lambda lib: check_gemm(lib, 456, 32, 200, f32_out=True, mn_major=True, accumulate=True)),  # DeepSpeech2 conv wgrad: M = Kp
     ("gemm_tiny", lambda lib: check_gemm(lib, 1, 8, 8, f32_out=True)),
     ("gemm_rowstats", lambda lib: check_gemm(lib, 130, 1000, 64, f32_out=True, bias=True, rowstats=True)),  # feature class 8 (fused log-sum-exp)
+    ("gemm_rowstats_bf16_out", lambda lib: check_gemm(lib, 130, 1000, 64, bias=True, rowstats=True)),  # bf16 logits: statistics of the rounded values
     ("gemm_rowstats_narrow", lambda lib: check_gemm(lib, 40, 40, 32, f32_out=True, bias=True, rowstats=True)),  # one tile, second slice empty
     ("ffn_fwd_one_tile", lambda lib: check_ffn_fwd(lib, 100, 128)),  # ragged tile, two hidden chunks
     ("ffn_fwd_conformer_s", lambda lib: check_ffn_fwd(lib, 300, 576, dropout=0.1)),  # 3 tiles x 9 chunks: every ring / double-buffer phase wraps

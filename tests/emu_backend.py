@@ -40,6 +40,8 @@ def gemm(a, b, *, out=None, out_dtype=BF, bias=None, activation=None, aux=None, 
         v = v + bias.float().reshape(-1)
     if rowstats is not None:
         M, N = v.shape
+        if out_dtype == BF and out is None or (out is not None and out.dtype == BF):
+            v = v.to(BF).float()  # bf16 output: the statistics describe the stored values
         for s in range(rowstats.shape[1]):
             nb, half = s // 2, s % 2
             n_cols = min(256, N - nb * 256)

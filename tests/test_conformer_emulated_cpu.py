@@ -86,6 +86,10 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
         loss2, g2 = _run(model, data, state0)  # fused route, every second-generation kernel + fused log-sum-exp
         calls2 = dict(emu.calls)
         loss3, g3 = _run(model, data, state0)  # once more on the same packs: packed gradient sums and the shared dpos buffer start clean
+        ops.set_bf16_logits(True)
+        emu.calls.clear()
+        loss4, g4 = _run(model, data, state0)  # + bf16 logits: combine / gradient kernels on the 2-byte tensor, gradient in place at pitch V
+        calls4 = dict(emu.calls)
     finally:
         ops.restore_switches(saved)
         ops.set_precision("fp32")
@@ -99,6 +103,9 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
               "tfasr_rnnt_loss_fwd_f32", "tfasr_rnnt_loss_bwd_bf16", "tfasr_conv1_3x3s2_fwd", "tfasr_im2col_3x3s2", "tfasr_joint_tanh_fwd"):
         assert calls1.get(k, 0) > 0, (k, sorted(calls1))  # the step really ran on the hand-written kernels
     assert calls2["tfasr_rel_attention_fwd_ld"] == 2 and "tfasr_rel_attention_fwd" not in calls2 and "tfasr_rel_attention_bwd" not in calls2
+    assert calls4.get("tfasr_rnnt_loss_fwd_rowstats_bf16", 0) > 0 and calls4.get("tfasr_rnnt_loss_bwd_bf16_io", 0) > 0, calls4
+    assert "tfasr_rnnt_loss_bwd_bf16_v2" not in calls4 and "tfasr_rnnt_loss_fwd_rowstats_f32" not in calls4
+    torch.testing.assert_close(loss4, loss2, rtol=5e-3, atol=5e-3)
     assert torch.isfinite(loss1).all() and torch.isfinite(loss2).all()
     torch.testing.assert_close(loss3, loss2, rtol=2e-3, atol=2e-3)
     torch.testing.assert_close(loss1, ref_loss, rtol=3e-2, atol=3e-2)
@@ -113,6 +120,7 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
         assert _cos(g1[n], g) > 0.95, (n, _cos(g1[n], g))
         assert _cos(g2[n], g1[n]) > 0.995, (n, _cos(g2[n], g1[n]))
         assert _cos(g3[n], g2[n]) > 0.995 and abs(float(g3[n].norm() / g2[n].norm()) - 1.0) < 0.05, n
+        assert _cos(g4[n], g2[n]) > 0.995 and abs(float(g4[n].norm() / g2[n].norm()) - 1.0) < 0.05, (n, _cos(g4[n], g2[n]))
         checked += 1
     assert checked > 40, checked
 

@@ -58,6 +58,68 @@ def test_transducer_head_costs_and_gradients_match_with_fused_lse():
         assert (a.float() - b.float()).abs().max().item() <= 2e-3 * (b.float().abs().max().item() + 1e-6)
 
 
+@pytest.mark.parametrize("shape", [(4097, 1000, 320), (300, 256, 64), (129, 40, 320)])
+def test_gemm_row_statistics_of_bf16_output_describe_the_stored_values(shape):
+    """bf16 logits (ops.bf16_logits): the epilogue rounds first and takes the statistics of what it stores."""
+    from tensorflowasr_b200 import kernels
+
+    M, N, K = shape
+    torch.manual_seed(M + N + 1)
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda") * (3.0 / K ** 0.5)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    parts = 2 * ((N + 255) // 256)
+    stats = torch.full((M, parts, 2), float("nan"), device="cuda")
+    out = kernels.gemm(a, b, bias=bias, out_dtype=torch.bfloat16, rowstats=stats)
+    ref = a.float() @ b.float().t() + bias
+    assert (out.float() - ref).abs().max().item() <= 8e-3 * ref.abs().max().item()
+    m = stats[..., 0].max(1, keepdim=True).values
+    lse = (m + torch.log((stats[..., 1] * torch.exp(stats[..., 0] - m)).sum(1, keepdim=True)))[:, 0]
+    torch.testing.assert_close(lse, torch.logsumexp(out.float(), dim=1), rtol=1e-5, atol=1e-4)
+
+
+def test_transducer_head_with_bf16_logits():
+    """The bf16-logits head against (a) the exact float32 RNN-T loss of the SAME rounded logits (tfasr_rnnt_loss_f32 through losses.rnnt_loss,
+    itself pinned to the oracle in test_gpu_losses.py) — costs to 1e-5, the head's own claim — and (b) the f32-logits head: costs within
+    2e-3 relative (the rounding of ~T+U log-probabilities), gradients within 2e-2 of the maximum and cosine >= 0.999."""
+    from tensorflowasr_b200 import fused, kernels, losses, ops
+
+    torch.manual_seed(12)
+    B, T, U1, J, V = 4, 41, 11, 64, 1000
+    e = (torch.randn(B, T, J, device="cuda") * 0.5).to(torch.bfloat16)
+    p = (torch.randn(B, U1, J, device="cuda") * 0.5).to(torch.bfloat16)
+    labels = torch.randint(1, V, (B, U1 - 1), device="cuda", dtype=torch.int32)
+    tl = torch.tensor([41, 30, 7, 1], device="cuda", dtype=torch.int32)
+    ul = torch.tensor([10, 4, 0, 2], device="cuda", dtype=torch.int32)
+    weights = torch.tensor([1.0, 0.5, 2.0, 1.5], device="cuda")
+    res = {}
+    saved = ops.switch_state()
+    try:
+        ops.set_fused_lse(True)
+        for flag in (False, True):
+            ops.set_bf16_logits(flag)
+            assert ops.bf16_logits_active() == flag
+            w = torch.nn.Parameter((torch.randn(J, V, generator=torch.Generator().manual_seed(5)) / J ** 0.5).cuda())
+            bvec = torch.nn.Parameter(torch.randn(V, generator=torch.Generator().manual_seed(6)).cuda() * 0.1)
+            er, pr = e.clone().requires_grad_(True), p.clone().requires_grad_(True)
+            pack = fused.WeightPack(w, bvec)
+            costs = fused.transducer_head(er, pr, pack, labels, tl, ul)
+            (costs * weights).sum().backward()
+            res[flag] = (costs.detach().clone(), er.grad.clone(), pr.grad.clone(), w.grad.clone(), bvec.grad.clone())
+            if flag:
+                h = kernels.joint_tanh_fwd(e, p)
+                stored = kernels.gemm(h.view(-1, J), pack.wt, bias=pack.bias, out_dtype=torch.bfloat16).view(B, T, U1, V)
+                exact = losses.rnnt_loss(stored.float(), tl, labels, ul)
+    finally:
+        ops.restore_switches(saved)
+    torch.testing.assert_close(res[True][0], exact, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=2e-3, atol=1e-3)
+    for a, b in zip(res[True][1:], res[False][1:]):
+        a, b = a.float().reshape(-1), b.float().reshape(-1)
+        assert (a - b).abs().max().item() <= 2e-2 * (b.abs().max().item() + 1e-6)
+        assert torch.nn.functional.cosine_similarity(a, b, dim=0).item() >= 0.999
+
+
 def test_conv1_v2_matches_first_generation_kernels():
     """csrc/conv1.cu (opt-in, TFASR_CONV1_V2) against the verified conv_bn.cu kernels: identical contract."""
     from tensorflowasr_b200 import kernels, ops
