@@ -316,9 +316,25 @@ def _run_ours(args, real_stdout):
     ops.TIMERS.enable(False)
     launches = lib.tfasr_launch_count() // 3 * args.steps
     model.enable_cuda_graph(not args.no_graph)
+    # end to end through the public training loop (BaseModel.fit, tensorflowasr_b200/training.py): every step copies its batch from pinned host
+    # memory (on the loop's copy stream, one batch ahead) and reads its loss back to the host (one step late); fit returns after the last
+    # loss arrived.  The unpipelined figure (copy -> step -> blocking read, one after the other) is kept beside it.
+    def host_batches(n):
+        for _ in range(n):
+            yield to_train_data(host)
+
+    e2e_io = {}
+
+    def fit_e2e(n):
+        h = model.fit(host_batches(n), epochs=1)
+        assert len(h.steps["loss"]) == n and all(v == v for v in h.steps["loss"]), h.steps
+        e2e_io.update(h2d=h.h2d_bytes // n, d2h=h.d2h_bytes // n)
+
+    fit_e2e(3)
+    ms_e2e = timed(lambda: fit_e2e(args.steps), 1) / args.steps
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e_serial = timed(step_e2e, max(3, args.steps // 2))
     peer_calls = tdist.peer_all_reduce_check()  # opt-in peer-memory sync-BN exchange: raises if a peer ever missed the bounded wait
 
     if rank != 0:
@@ -388,7 +404,9 @@ def _run_ours(args, real_stdout):
         "metric": METRIC, "value": gb / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(world),
-        "e2e": {"value": gb / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "e2e": {"value": gb / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": e2e_io.get("h2d", h2d), "d2h_bytes_per_step": e2e_io.get("d2h", 4),
+                "ms_per_step": ms_e2e, "api": "BaseModel.fit over pinned host batches (copy stream one batch ahead, loss read one step late)",
+                "unpipelined_ms_per_step": ms_e2e_serial},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_joint_gemm": roofline_joint, "cpu_baseline": cpu,
         "kernel_ms_per_step": kernel_ms,
     }

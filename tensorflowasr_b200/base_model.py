@@ -314,6 +314,14 @@ class BaseModel(nn.Module):
             self._apply_gradients()  # all_reduce() launches every bucket now (none was launched by the hooks) and waits
         return {"loss": self._last_losses}
 
+    def fit(self, x=None, epochs=1, steps_per_epoch=None, callbacks=None, initial_epoch=0, verbose=0, **kwargs):
+        """keras.Model.fit for this path (scripts/train.py:113-121): drives `train_step` over an iterable of TrainData batches with the next
+        batch's host->device copy on a copy stream and the per-step loss read back one step late (training.py).  Returns a History."""
+        from . import training
+
+        return training.fit(self, x, epochs=epochs, steps_per_epoch=steps_per_epoch, callbacks=callbacks, initial_epoch=initial_epoch,
+                            verbose=verbose)
+
     @torch.no_grad()
     def test_step(self, data: schemas.TrainData):
         losses = self.compute_losses(data, training=False)

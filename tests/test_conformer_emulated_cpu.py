@@ -126,8 +126,8 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
 
 
 def test_train_step_with_flat_adamw_learns_on_emulated_kernels(monkeypatch):
-    """BaseModel.train_step end to end (forward, backward, the one-launch flat AdamW, gradient zeroing) on the emulator backend: the loss of a
-    fixed batch goes down step after step."""
+    """BaseModel.fit -> train_step end to end (forward, backward, the one-launch flat AdamW, gradient zeroing) on the emulator backend: the loss
+    of a fixed batch goes down step after step; the loop reports every step's loss to the callbacks and the History (scripts/train.py:113-121)."""
     import tensorflowasr_b200 as tfasr
     from tensorflowasr_b200 import ops
 
@@ -137,9 +137,21 @@ def test_train_step_with_flat_adamw_learns_on_emulated_kernels(monkeypatch):
         model, data = _model(), _batch()
         model.compile(optimizer=tfasr.make_optimizer(model, learning_rate=2e-3))
         model.train()
-        losses = [float(model.train_step(data)["loss"].mean()) for _ in range(2)]
+        seen = []
+
+        class Log:
+            def on_train_batch_end(self, step, logs):
+                seen.append((step, logs["loss"]))
+
+            def on_epoch_end(self, epoch, logs):
+                seen.append(("epoch", epoch, logs["loss"]))
+
+        hist = model.fit([data, data], epochs=1, callbacks=[Log()])
+        losses = hist.steps["loss"]
     finally:
         ops.set_precision("fp32")
+    assert len(losses) == 2 and [s[0] for s in seen] == [0, 1, "epoch"] and seen[0][1] == losses[0]
+    assert abs(hist.history["loss"][0] - sum(losses) / 2) < 1e-6 and hist.epoch == [0]
     assert emu.calls.get("tfasr_adamw_flat_f32", 0) == 2 and emu.calls.get("tfasr_gemm_bf16", 0) > 50
     assert losses[1] < losses[0], losses
 

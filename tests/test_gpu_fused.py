@@ -161,6 +161,44 @@ def test_cuda_graph_train_step_matches_eager():
         ops.set_precision("fp32")
 
 
+def test_fit_loop_with_prefetch_matches_train_step_loop():
+    """BaseModel.fit (training.py: host batches from pinned memory on a copy stream one batch ahead, losses read one step late, graph replay)
+    against the plain loop `train_step(device batch)`: same per-step losses, different batches per step (so a stale or swapped buffer shows),
+    every byte accounted."""
+    import tensorflowasr_b200 as tfasr
+    from tensorflowasr_b200 import ops, training
+
+    ops.set_precision("bf16")
+    try:
+        dev_batches = [_mini_batch(seed=s) for s in (0, 1, 2, 3, 4)]
+        host_batches = [training._map(lambda t: t.cpu().pin_memory(), d) for d in dev_batches]
+        out = {}
+        for mode in ("loop", "fit"):
+            model = _mini_model(dropout=0.0, seed=3)
+            model.compile(optimizer=tfasr.make_optimizer(model, learning_rate=1e-3))
+            model.train()
+            model.enable_cuda_graph(True)
+            if mode == "loop":
+                out[mode] = [model.train_step(d)["loss"].mean().item() for d in dev_batches]
+            else:
+                seen = []
+
+                class Log:
+                    def on_train_batch_end(self, step, logs):
+                        seen.append(step)
+
+                hist = model.fit(host_batches, epochs=1, callbacks=[Log()])
+                out[mode] = hist.steps["loss"]
+                assert seen == [0, 1, 2, 3, 4]
+                assert hist.h2d_bytes == sum(t.numel() * t.element_size() for d in host_batches for t in training._tensors(d))
+                assert hist.d2h_bytes == 4 * 5
+        for a, b in zip(out["fit"], out["loop"]):
+            assert a == pytest.approx(b, rel=2e-2), out
+        assert len(set(round(v, 3) for v in out["fit"])) > 1  # the batches differ: so do their losses
+    finally:
+        ops.set_precision("fp32")
+
+
 def test_transducer_head_kernels_vs_torch():
     """joint tanh / GEMM / RNN-T loss (bf16 in-place gradient) / reductions vs a plain PyTorch fp32 evaluation of the same head."""
     from tensorflowasr_b200 import fused, rnnt_loss
