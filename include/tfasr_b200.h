@@ -127,16 +127,26 @@ int tfasr_rnnt_loss_bwd_bf16_v2(const float* logits, const int32_t* labels, cons
 
 /* bf16-logits variants (ops.bf16_logits; SURVEY 8f N1, second step): the joint GEMM stores bf16 logits and takes its row statistics over the
  * ROUNDED values, so the head computes the exact RNN-T loss and gradient of the stored logits; the [B,T,U1,V] tensor is 2 bytes per entry
- * and its gradient replaces it in place (grads == logits, ld_grads = V).  Same workspace layout; V % 4 == 0, V <= 2048. */
-int tfasr_rnnt_lse_from_rowstats_bf16(const void* logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
+ * and its gradient replaces it in place (grads == logits, ld_grads = ld_logits).  ld_logits = row pitch in elements (>= V, multiple of 4;
+ * a multiple of 64 keeps every row on a 128-byte boundary for the TMA loads of the backward GEMMs).  Same workspace layout; V % 4 == 0,
+ * V <= 2048; 16-byte accesses when V, both pitches are multiples of 8 and the bases are 16-byte aligned. */
+int tfasr_rnnt_lse_from_rowstats_bf16(const void* logits, int64_t ld_logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
                                       const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V, float* lse, float* blank,
                                       float* truth, tfasr_stream_t stream);
-int tfasr_rnnt_loss_fwd_rowstats_bf16(const void* logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
+int tfasr_rnnt_loss_fwd_rowstats_bf16(const void* logits, int64_t ld_logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
                                       const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V, int32_t blank, float* costs,
                                       void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
-int tfasr_rnnt_loss_bwd_bf16_io(const void* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
+int tfasr_rnnt_loss_bwd_bf16_io(const void* logits, int64_t ld_logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
                                 int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
                                 int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream);
+
+/* Alpha / beta wavefronts alone, second generation (csrc/rnnt_lattice_v2.cu; ops.lattice_v2): the utterance's blank / truth planes staged
+ * in shared memory, direction as a template parameter.  blank / truth / alpha / beta are the [B,T,U1] f32 planes of the workspace
+ * (tfasr_rnnt_lse_from_rowstats_* fills the first two); costs [B] = -beta[0,0] (+inf for an empty utterance).  Needs 8 T U1 + 256 bytes
+ * of shared memory: tfasr_rnnt_lattice_smem_supported(T, U1) says whether the shape fits (else TFASR_INVALID_VALUE). */
+int tfasr_rnnt_lattice_smem_supported(int32_t T, int32_t U1);
+int tfasr_rnnt_lattice_smem_f32(const float* blank, const float* truth, const int32_t* logit_len, const int32_t* label_len, int32_t B, int32_t T,
+                                int32_t U1, float* alpha, float* beta, float* costs, tfasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CTC loss + gradient (tf.nn.ctc_loss, dense labels, batch-major logits [B, T, V], blank_index 0).

@@ -85,12 +85,15 @@ SIGNATURES = {
                                            c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tfasr_rnnt_loss_bwd_bf16_v2": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                               c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "tfasr_rnnt_lse_from_rowstats_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+    "tfasr_rnnt_lse_from_rowstats_bf16": (c_int32, [c_void_p, ctypes.c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                                     c_void_p, c_void_p, c_void_p, c_void_p]),
-    "tfasr_rnnt_loss_fwd_rowstats_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+    "tfasr_rnnt_loss_fwd_rowstats_bf16": (c_int32, [c_void_p, ctypes.c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                                     c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "tfasr_rnnt_loss_bwd_bf16_io": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+    "tfasr_rnnt_loss_bwd_bf16_io": (c_int32, [c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                               c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tfasr_rnnt_lattice_smem_supported": (c_int32, [c_int32, c_int32]),
+    "tfasr_rnnt_lattice_smem_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                              c_void_p]),
     "tfasr_joint_tanh_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_joint_reduce_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "tfasr_joint_tanh_fwd_v2": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),

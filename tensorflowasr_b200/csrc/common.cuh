@@ -52,6 +52,14 @@ __device__ __forceinline__ float log_add_exp_fast(float a, float b) {
   return (m == -CUDART_INF_F) ? -CUDART_INF_F : r;
 }
 
+// 2^x as ONE MUFU (flush-to-zero: no range fix-up around it) — for softmax terms, where underflow to zero is the right answer
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // streaming 128-bit global accesses (read-once / write-once data should not pollute L1)
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;

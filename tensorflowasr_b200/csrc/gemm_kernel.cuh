@@ -395,18 +395,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
             }
-            // online log-sum-exp over the valid columns of this 16-column chunk
+            // online log-sum-exp over the valid columns of this 16-column chunk; a term is FFMA + ex2 + FADD (base-2 exponent with the
+            // running maximum folded into the FFMA), and full chunks carry no per-column predicates
+            const bool full = c0 + 16 <= n_cols;
             float cm = -CUDART_INF_F;
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < n_cols) cm = fmaxf(cm, v[j]);
-            if (cm > -CUDART_INF_F) {
-              const float mn = fmaxf(rs_m, cm);
-              float acc = 0.f;
+              for (int j = 0; j < 16; ++j) cm = fmaxf(cm, v[j]);
+            } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (c0 + j < n_cols) acc += __expf(v[j] - mn);
-              rs_s = fmaf(rs_s, __expf(rs_m - mn), acc);  // rs_m = -inf on the first chunk: exp(-inf) = 0
+                if (c0 + j < n_cols) cm = fmaxf(cm, v[j]);
+            }
+            if (cm > -CUDART_INF_F) {
+              const float mn = fmaxf(rs_m, cm);
+              const float nm = -mn * kLog2e;
+              float acc = 0.f;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc += fast_ex2(fmaf(v[j], kLog2e, nm));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j < n_cols) acc += fast_ex2(fmaf(v[j], kLog2e, nm));
+              }
+              rs_s = fmaf(rs_s, fast_ex2((rs_m - mn) * kLog2e), acc);  // rs_m = -inf on the first chunk: 2^-inf = 0
               rs_m = mn;
             }
           }

@@ -19,15 +19,16 @@ __device__ __forceinline__ float logit_f(const __nv_bfloat16* x, int j) { return
 
 // LT = float, or __nv_bfloat16 (the joint GEMM writes bf16 logits and takes its statistics over the rounded values: ops.bf16_logits)
 template <typename LT>
-__global__ void __launch_bounds__(256) rnnt_lse_combine_kernel(const LT* __restrict__ logits, const float2* __restrict__ rowstats, int P,
+__global__ void __launch_bounds__(256) rnnt_lse_combine_kernel(const LT* __restrict__ logits, int64_t ld, const float2* __restrict__ rowstats, int P,
                                                                const int32_t* __restrict__ labels, const int32_t* __restrict__ logit_len,
                                                                const int32_t* __restrict__ label_len, int B, int T, int U1, int V,
                                                                float* __restrict__ lse, float* __restrict__ blank, float* __restrict__ truth) {
   const int64_t nrows = (int64_t)B * T * U1;
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += (int64_t)gridDim.x * blockDim.x) {
-    const int u = (int)(row % U1);
-    const int t = (int)((row / U1) % T);
-    const int b = (int)(row / ((int64_t)U1 * T));
+    const uint32_t r32 = (uint32_t)row;  // B T U1 < 2^31 (checked by the launcher): 32-bit divisions
+    const int u = (int)(r32 % (uint32_t)U1);
+    const int t = (int)((r32 / (uint32_t)U1) % (uint32_t)T);
+    const int b = (int)(r32 / ((uint32_t)U1 * (uint32_t)T));
     int Tb, Ub;
   lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
     if (t >= Tb || u > Ub) continue;  // rows outside the lattice are never read
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) rnnt_lse_combine_kernel(const LT* __restr
       if (ps.y > 0.f) acc = fmaf(ps.y, __expf(ps.x - m), acc);
     }
     const float l = m + logf(acc);
-    const LT* x = logits + (size_t)row * V;
+    const LT* x = logits + (size_t)row * ld;
     lse[row] = l;
     blank[row] = logit_f(x, 0) - l;
     truth[row] = (u < Ub) ? logit_f(x, labels[(size_t)b * (U1 - 1) + u]) - l : -CUDART_INF_F;
@@ -52,10 +53,11 @@ __global__ void __launch_bounds__(256) rnnt_lse_combine_kernel(const LT* __restr
 using namespace tfasr;
 
 template <typename LT>
-static int lse_from_rowstats(const LT* logits, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
+static int lse_from_rowstats(const LT* logits, int64_t ld, const float* rowstats, int32_t parts, const int32_t* labels, const int32_t* logit_len,
                              const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V, float* lse, float* blank, float* truth,
                              tfasr_stream_t stream_) {
-  if (!logits || !rowstats || parts < 1 || !logit_len || !label_len || (U1 > 1 && !labels) || B < 0 || T < 1 || U1 < 1 || V < 2 || !lse || !blank ||
+  if ((int64_t)B * T * U1 > 0x7fffffff) return TFASR_INVALID_VALUE;
+  if (!logits || ld < V || !rowstats || parts < 1 || !logit_len || !label_len || (U1 > 1 && !labels) || B < 0 || T < 1 || U1 < 1 || V < 2 || !lse || !blank ||
       !truth || (reinterpret_cast<uintptr_t>(rowstats) & 7))
     return TFASR_INVALID_VALUE;
   if (B == 0) return TFASR_OK;
@@ -65,11 +67,11 @@ static int lse_from_rowstats(const LT* logits, const float* rowstats, int32_t pa
 #ifdef TFASR_EMU_BUILD
   (void)stream_;
   emu::launch(dim3((unsigned)g), dim3(256), 0, [&] {
-    rnnt_lse_combine_kernel<LT>(logits, reinterpret_cast<const float2*>(rowstats), parts, labels, logit_len, label_len, B, T, U1, V, lse, blank, truth);
+    rnnt_lse_combine_kernel<LT>(logits, ld, reinterpret_cast<const float2*>(rowstats), parts, labels, logit_len, label_len, B, T, U1, V, lse, blank, truth);
   });
   return TFASR_OK;
 #else
-  rnnt_lse_combine_kernel<LT><<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream_)>>>(logits, reinterpret_cast<const float2*>(rowstats), parts,
+  rnnt_lse_combine_kernel<LT><<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream_)>>>(logits, ld, reinterpret_cast<const float2*>(rowstats), parts,
                                                                                           labels, logit_len, label_len, B, T, U1, V, lse, blank, truth);
   count_launch();
   return check_launch();
@@ -79,12 +81,12 @@ static int lse_from_rowstats(const LT* logits, const float* rowstats, int32_t pa
 extern "C" int tfasr_rnnt_lse_from_rowstats_f32(const float* logits, const float* rowstats, int32_t parts, const int32_t* labels,
                                                 const int32_t* logit_len, const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V,
                                                 float* lse, float* blank, float* truth, tfasr_stream_t stream) {
-  return lse_from_rowstats<float>(logits, rowstats, parts, labels, logit_len, label_len, B, T, U1, V, lse, blank, truth, stream);
+  return lse_from_rowstats<float>(logits, V, rowstats, parts, labels, logit_len, label_len, B, T, U1, V, lse, blank, truth, stream);
 }
 
-extern "C" int tfasr_rnnt_lse_from_rowstats_bf16(const void* logits, const float* rowstats, int32_t parts, const int32_t* labels,
+extern "C" int tfasr_rnnt_lse_from_rowstats_bf16(const void* logits, int64_t ld_logits, const float* rowstats, int32_t parts, const int32_t* labels,
                                                  const int32_t* logit_len, const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V,
                                                  float* lse, float* blank, float* truth, tfasr_stream_t stream) {
-  return lse_from_rowstats<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(logits), rowstats, parts, labels, logit_len, label_len, B, T, U1, V, lse,
+  return lse_from_rowstats<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(logits), ld_logits, rowstats, parts, labels, logit_len, label_len, B, T, U1, V, lse,
                                           blank, truth, stream);
 }

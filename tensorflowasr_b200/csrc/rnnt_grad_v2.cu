@@ -46,9 +46,10 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_v2_kernel(con
   }
   float4* cs4 = reinterpret_cast<float4*>(s_cs + (size_t)warp * V);
   for (int64_t row = (int64_t)blockIdx.x * kG2Warps + warp; row < nrows; row += (int64_t)gridDim.x * kG2Warps) {
-    const int u = (int)(row % U1);
-    const int t = (int)((row / U1) % T);
-    const int b = (int)(row / ((int64_t)U1 * T));
+    const uint32_t r32 = (uint32_t)row;  // B T U1 < 2^31 (checked by the launcher): 32-bit divisions
+    const int u = (int)(r32 % (uint32_t)U1);
+    const int t = (int)((r32 / (uint32_t)U1) % (uint32_t)T);
+    const int b = (int)(r32 / ((uint32_t)U1 * (uint32_t)T));
     int Tb, Ub;
   lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
     uint2* g2 = reinterpret_cast<uint2*>(grads + row * ld_g);
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_v2_kernel(con
 // bf16 logits in, bf16 gradient out (ops.bf16_logits): element j of a row is read and written by the same lane, so grads may alias logits
 // (ld_g = V) with no ordering concern.  NV2 = uint2 (4 bf16) per lane (V <= 128 * NV2): 4 B per lattice node and vocabulary entry.
 template <int NV2>
-__global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_io_kernel(const __nv_bfloat16* logits, const int32_t* __restrict__ labels,
+__global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_io_kernel(const __nv_bfloat16* logits, int64_t ld_x, const int32_t* __restrict__ labels,
                                                                              const int32_t* __restrict__ logit_len,
                                                                              const int32_t* __restrict__ label_len, int B, int T, int U1, int V,
                                                                              RnntPlanes ws, const float* __restrict__ costs,
@@ -145,9 +146,10 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_io_kernel(con
   }
   float4* cs4 = reinterpret_cast<float4*>(s_cs + (size_t)warp * V);
   for (int64_t row = (int64_t)blockIdx.x * kG2Warps + warp; row < nrows; row += (int64_t)gridDim.x * kG2Warps) {
-    const int u = (int)(row % U1);
-    const int t = (int)((row / U1) % T);
-    const int b = (int)(row / ((int64_t)U1 * T));
+    const uint32_t r32 = (uint32_t)row;  // B T U1 < 2^31 (checked by the launcher): 32-bit divisions
+    const int u = (int)(r32 % (uint32_t)U1);
+    const int t = (int)((r32 / (uint32_t)U1) % (uint32_t)T);
+    const int b = (int)(r32 / ((uint32_t)U1 * (uint32_t)T));
     int Tb, Ub;
     lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
     uint2* g2 = reinterpret_cast<uint2*>(grads + row * ld_g);
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_io_kernel(con
     gb *= sc;
     gt *= sc;
     const float gsum = gb + gt;
-    const uint2* x2 = reinterpret_cast<const uint2*>(logits + row * V);
+    const uint2* x2 = reinterpret_cast<const uint2*>(logits + row * ld_x);
     uint2 v[NV2];
 #pragma unroll
     for (int i = 0; i < NV2; ++i) {
@@ -219,6 +221,113 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_io_kernel(con
   }
 }
 
+// The same, 16 bytes (8 logits) per access and a short instruction stream (V % 8 == 0, 16-byte aligned rows): the first version spent
+// 22 thread-instructions per logit (profiles/head_bf16_ncu_r02.txt: 355 M warp instructions, issue slots 57 % busy, 3.8 TB/s) on the
+// range fix-up of __expf, the per-group label compares and the 8-byte accesses.  Here a softmax term is FFMA + ex2.approx.ftz + FMUL, and
+// the two columns that get an extra term (blank: column 0, truth: column `label`) are patched after the vector pass by the lane that
+// owns them — it re-reads its own logit before its own stores, so the in-place update needs no cross-lane ordering.
+template <int NV8>
+__global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_io8_kernel(const __nv_bfloat16* logits, int64_t ld_x, const int32_t* __restrict__ labels,
+                                                                              const int32_t* __restrict__ logit_len,
+                                                                              const int32_t* __restrict__ label_len, int B, int T, int U1, int V,
+                                                                              RnntPlanes ws, const float* __restrict__ costs,
+                                                                              const float* __restrict__ grad_scale, __nv_bfloat16* grads, int64_t ld_g,
+                                                                              float* __restrict__ dbias) {
+  TFASR_DYN_SMEM(smem_raw);
+  float* s_cs = reinterpret_cast<float*>(smem_raw);  // [kG2Warps][V] when dbias
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nrows = (int64_t)B * T * U1;
+  const int n8 = V >> 3;
+  if (dbias) {
+    for (int j = threadIdx.x; j < kG2Warps * V; j += blockDim.x) s_cs[j] = 0.f;
+    __syncthreads();
+  }
+  float* cs = s_cs + (size_t)warp * V;
+  float4* cs4 = reinterpret_cast<float4*>(cs);
+  for (int64_t row = (int64_t)blockIdx.x * kG2Warps + warp; row < nrows; row += (int64_t)gridDim.x * kG2Warps) {
+    const uint32_t r32 = (uint32_t)row;  // B T U1 < 2^31 (checked by the launcher): 32-bit divisions
+    const int u = (int)(r32 % (uint32_t)U1);
+    const int t = (int)((r32 / (uint32_t)U1) % (uint32_t)T);
+    const int b = (int)(r32 / ((uint32_t)U1 * (uint32_t)T));
+    int Tb, Ub;
+    lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
+    __nv_bfloat16* gr = grads + row * ld_g;
+    uint4* g8 = reinterpret_cast<uint4*>(gr);
+    if (!((t < Tb) && (u <= Ub))) {
+      for (int j = lane; j < n8; j += 32) g8[j] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    const float logz = -costs[b];
+    const float a = ws.alpha[row];
+    const float lse = ws.lse[row];
+    float gb = 0.f, gt = 0.f;
+    int label = -1;
+    if (t < Tb - 1) gb = -expf(a + ws.beta[row + U1] + ws.blank[row] - logz);
+    else if (u == Ub) gb = -1.0f;
+    if (u < Ub) {
+      gt = -expf(a + ws.beta[row + 1] + ws.truth[row] - logz);
+      label = labels[(int64_t)b * (U1 - 1) + u];
+    }
+    const float sc = grad_scale ? grad_scale[b] : 1.0f;
+    gb *= sc;
+    gt *= sc;
+    const float ng = -(gb + gt), nl = -lse * kLog2e;
+    const __nv_bfloat16* xr = logits + row * ld_x;
+    const bool own_label = label >= 0 && ((label >> 3) & 31) == lane;
+    const float x0 = lane == 0 ? __bfloat162float(xr[0]) : 0.f;
+    const float xl = own_label ? __bfloat162float(xr[label]) : 0.f;
+    const uint4* x8 = reinterpret_cast<const uint4*>(xr);
+    uint4 v[NV8];
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n8) v[i] = simt_ld_stream_u4(x8 + j);
+    }
+#pragma unroll
+    for (int i = 0; i < NV8; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n8) {
+        float f[8];
+        bf8_unpack(v[i], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = ng * simt_ex2(fmaf(f[k], kLog2e, nl));
+        if (dbias) {
+          float4 c0 = cs4[2 * j], c1 = cs4[2 * j + 1];
+          c0.x += f[0];
+          c0.y += f[1];
+          c0.z += f[2];
+          c0.w += f[3];
+          c1.x += f[4];
+          c1.y += f[5];
+          c1.z += f[6];
+          c1.w += f[7];
+          cs4[2 * j] = c0;
+          cs4[2 * j + 1] = c1;
+        }
+        g8[j] = bf8_pack(f);
+      }
+    }
+    // the two columns with an extra term, by their owners (same thread as the vector store above: program order)
+    if (lane == 0) {
+      gr[0] = __float2bfloat16_rn(ng * simt_ex2(fmaf(x0, kLog2e, nl)) + gb);
+      if (dbias) cs[0] += gb;
+    }
+    if (own_label) {
+      gr[label] = __float2bfloat16_rn(ng * simt_ex2(fmaf(xl, kLog2e, nl)) + gt);
+      if (dbias) cs[label] += gt;
+    }
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kG2Warps; ++w) s += s_cs[(size_t)w * V + j];
+      atomicAdd(dbias + j, s);
+    }
+  }
+}
+
 }  // namespace tfasr
 
 using namespace tfasr;
@@ -226,7 +335,7 @@ using namespace tfasr;
 extern "C" int tfasr_rnnt_loss_bwd_bf16_v2(const float* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
                                            int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
                                            int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream_) {
-  if (blank != 0 || B < 0 || T < 1 || U1 < 1 || V < 2 || U1 > 1024) return TFASR_INVALID_VALUE;
+  if (blank != 0 || B < 0 || T < 1 || U1 < 1 || V < 2 || U1 > 1024 || (int64_t)B * T * U1 > 0x7fffffff) return TFASR_INVALID_VALUE;
   if (!logits || !logit_len || !label_len || !workspace || (U1 > 1 && !labels) || !costs || !grads || ld_grads < V || (ld_grads & 3))
     return TFASR_INVALID_VALUE;
   if ((V & 3) || V > 2048 || (reinterpret_cast<uintptr_t>(logits) & 15) || (reinterpret_cast<uintptr_t>(grads) & 7)) return TFASR_INVALID_VALUE;
@@ -273,14 +382,15 @@ extern "C" int tfasr_rnnt_loss_bwd_bf16_v2(const float* logits, const int32_t* l
 #endif
 }
 
-/* bf16 logits -> bf16 gradient (may be in place: grads == logits, ld_grads = V); everything else as tfasr_rnnt_loss_bwd_bf16_v2 */
-extern "C" int tfasr_rnnt_loss_bwd_bf16_io(const void* logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
+/* bf16 logits (row pitch ld_logits) -> bf16 gradient (may be in place: grads == logits, ld_grads = ld_logits); else as tfasr_rnnt_loss_bwd_bf16_v2 */
+extern "C" int tfasr_rnnt_loss_bwd_bf16_io(const void* logits, int64_t ld_logits, const int32_t* labels, const int32_t* logit_len, const int32_t* label_len, int32_t B,
                                            int32_t T, int32_t U1, int32_t V, int32_t blank, const float* costs, const float* grad_scale, void* grads,
                                            int64_t ld_grads, float* dbias, const void* workspace, size_t workspace_bytes, tfasr_stream_t stream_) {
-  if (blank != 0 || B < 0 || T < 1 || U1 < 1 || V < 2 || U1 > 1024) return TFASR_INVALID_VALUE;
+  if (blank != 0 || B < 0 || T < 1 || U1 < 1 || V < 2 || U1 > 1024 || (int64_t)B * T * U1 > 0x7fffffff) return TFASR_INVALID_VALUE;
   if (!logits || !logit_len || !label_len || !workspace || (U1 > 1 && !labels) || !costs || !grads || ld_grads < V || (ld_grads & 3))
     return TFASR_INVALID_VALUE;
-  if ((V & 3) || V > 2048 || (reinterpret_cast<uintptr_t>(logits) & 7) || (reinterpret_cast<uintptr_t>(grads) & 7)) return TFASR_INVALID_VALUE;
+  if ((V & 3) || V > 2048 || ld_logits < V || (ld_logits & 3) || (reinterpret_cast<uintptr_t>(logits) & 7) || (reinterpret_cast<uintptr_t>(grads) & 7))
+    return TFASR_INVALID_VALUE;
   const size_t plane = (sizeof(float) * (size_t)B * T * U1 + 255) / 256 * 256;
   if (workspace_bytes < 5 * plane) return TFASR_WORKSPACE_TOO_SMALL;
   if (B == 0) return TFASR_OK;
@@ -296,26 +406,33 @@ extern "C" int tfasr_rnnt_loss_bwd_bf16_io(const void* logits, const int32_t* la
   if (ctas > (int64_t)kNumSMs * 12) ctas = (int64_t)kNumSMs * 12;
   const size_t smem = dbias ? sizeof(float) * (size_t)kG2Warps * V : 0;
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(logits);
+  // 16-byte accesses when every row allows them
+  const bool wide = !(V & 7) && !(ld_logits & 7) && !(ld_grads & 7) && !(reinterpret_cast<uintptr_t>(logits) & 15) && !(reinterpret_cast<uintptr_t>(grads) & 15);
   __nv_bfloat16* g = static_cast<__nv_bfloat16*>(grads);
 #ifdef TFASR_EMU_BUILD
   (void)stream_;
-#define G2_LAUNCH(N) \
-  emu::launch(dim3((unsigned)ctas), dim3(kG2Warps * 32), smem, [&] { rnnt_grad_bf16_io_kernel<N>(x, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, ld_grads, dbias); })
+#define G2_LAUNCH(KERNEL, N) \
+  emu::launch(dim3((unsigned)ctas), dim3(kG2Warps * 32), smem, [&] { KERNEL<N>(x, ld_logits, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, ld_grads, dbias); })
 #else
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-#define G2_LAUNCH(N)                                                                                                                         \
-  do {                                                                                                                                       \
-    if (smem > 48 * 1024 && cudaFuncSetAttribute(rnnt_grad_bf16_io_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
-      return TFASR_EXECUTION_FAILED;                                                                                                         \
-    rnnt_grad_bf16_io_kernel<N><<<(unsigned)ctas, kG2Warps * 32, smem, stream>>>(x, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, \
-                                                                                 ld_grads, dbias);                                          \
-    count_launch();                                                                                                                          \
+#define G2_LAUNCH(KERNEL, N)                                                                                                         \
+  do {                                                                                                                               \
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(KERNEL<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+      return TFASR_EXECUTION_FAILED;                                                                                                 \
+    KERNEL<N><<<(unsigned)ctas, kG2Warps * 32, smem, stream>>>(x, ld_logits, labels, logit_len, label_len, B, T, U1, V, ws, costs, grad_scale, g, \
+                                                               ld_grads, dbias);                                                    \
+    count_launch();                                                                                                                  \
   } while (0)
 #endif
-  if (V <= 256) G2_LAUNCH(2);
-  else if (V <= 512) G2_LAUNCH(4);
-  else if (V <= 1024) G2_LAUNCH(8);
-  else G2_LAUNCH(16);
+  if (wide) {
+    if (V <= 256) G2_LAUNCH(rnnt_grad_bf16_io8_kernel, 1);
+    else if (V <= 512) G2_LAUNCH(rnnt_grad_bf16_io8_kernel, 2);
+    else if (V <= 1024) G2_LAUNCH(rnnt_grad_bf16_io8_kernel, 4);
+    else G2_LAUNCH(rnnt_grad_bf16_io8_kernel, 8);
+  } else if (V <= 256) G2_LAUNCH(rnnt_grad_bf16_io_kernel, 2);
+  else if (V <= 512) G2_LAUNCH(rnnt_grad_bf16_io_kernel, 4);
+  else if (V <= 1024) G2_LAUNCH(rnnt_grad_bf16_io_kernel, 8);
+  else G2_LAUNCH(rnnt_grad_bf16_io_kernel, 16);
 #undef G2_LAUNCH
 #ifdef TFASR_EMU_BUILD
   return TFASR_OK;

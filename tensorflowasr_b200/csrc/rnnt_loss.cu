@@ -488,7 +488,7 @@ extern "C" int tfasr_rnnt_loss_fwd_rowstats_f32(const float* logits, const float
   return check_launch();
 }
 
-extern "C" int tfasr_rnnt_loss_fwd_rowstats_bf16(const void* logits, const float* rowstats, int32_t parts, const int32_t* labels,
+extern "C" int tfasr_rnnt_loss_fwd_rowstats_bf16(const void* logits, int64_t ld_logits, const float* rowstats, int32_t parts, const int32_t* labels,
                                                  const int32_t* logit_len, const int32_t* label_len, int32_t B, int32_t T, int32_t U1, int32_t V,
                                                  int32_t blank, float* costs, void* workspace, size_t workspace_bytes, tfasr_stream_t stream_) {
   int st = rnnt_check(logits, labels, logit_len, label_len, B, T, U1, V, blank, workspace, workspace_bytes);
@@ -496,7 +496,7 @@ extern "C" int tfasr_rnnt_loss_fwd_rowstats_bf16(const void* logits, const float
   if (!costs || !rowstats || parts < 1) return TFASR_INVALID_VALUE;
   if (B == 0) return TFASR_OK;
   const RnntWs ws = rnnt_ws_carve(workspace, B, T, U1);
-  st = tfasr_rnnt_lse_from_rowstats_bf16(logits, rowstats, parts, labels, logit_len, label_len, B, T, U1, V, ws.lse, ws.blank, ws.truth, stream_);
+  st = tfasr_rnnt_lse_from_rowstats_bf16(logits, ld_logits, rowstats, parts, labels, logit_len, label_len, B, T, U1, V, ws.lse, ws.blank, ws.truth, stream_);
   if (st != TFASR_OK) return st;
   const int threads = 32 * (int)ceil_div(U1, 32);
   rnnt_lattice_kernel<<<dim3(B, 2), threads, 0, static_cast<cudaStream_t>(stream_)>>>(logit_len, label_len, T, U1, ws, costs);

@@ -10,6 +10,10 @@
 namespace tfasr {
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 constexpr int kNumSMs = 148;
+#ifndef TFASR_KLOG2E_DEFINED
+#define TFASR_KLOG2E_DEFINED
+constexpr float kLog2e = 1.4426950408889634f;
+#endif
 }  // namespace tfasr
 #else
 #include "common.cuh"
@@ -59,6 +63,16 @@ __device__ __forceinline__ float4 simt_ld_stream_f4(const float4* p) {
 #endif
 }
 
+// read-once 16-byte global load of raw bits
+__device__ __forceinline__ uint4 simt_ld_stream_u4(const uint4* p) {
+#ifdef TFASR_EMU_BUILD
+  if (reinterpret_cast<uintptr_t>(p) & 15) abort();
+  return *p;
+#else
+  return ld_stream_u4(p);
+#endif
+}
+
 // read-once 8-byte global load
 __device__ __forceinline__ uint2 simt_ld_stream_u2(const uint2* p) {
 #ifdef TFASR_EMU_BUILD
@@ -67,6 +81,17 @@ __device__ __forceinline__ uint2 simt_ld_stream_u2(const uint2* p) {
 #else
   uint2 r;
   asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+#endif
+}
+
+// 2^x, flush-to-zero approximation (one MUFU, no range fix-up): for softmax terms whose underflow to zero is the right answer
+__device__ __forceinline__ float simt_ex2(float x) {
+#ifdef TFASR_EMU_BUILD
+  return exp2f(x);
+#else
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 #endif
 }

@@ -445,14 +445,35 @@ class _TransducerHeadFn(torch.autograd.Function):
         bf16_logits = ops.bf16_logits_active() and V % 4 == 0
         rowstats = torch.empty((M, parts, 2), dtype=torch.float32, device=e.device) if fused_lse else None
         with _lib.TIMERS.region("joint_gemm_fwd"):
-            logits = kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out_dtype=torch.bfloat16 if bf16_logits else torch.float32,
-                                  rowstats=rowstats)
+            if bf16_logits:
+                # row pitch rounded up to 64 elements: every row starts on a 128-byte line, so the TMA boxes of this GEMM's stores and of the
+                # backward GEMMs' loads never straddle an extra 32-byte sector (a pitch of V = 1000 made the dgrad GEMM 16 % slower)
+                ldv = (V + 63) // 64 * 64
+                logits = torch.empty((M, ldv), dtype=torch.bfloat16, device=e.device)[:, :V]
+                kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out=logits, rowstats=rowstats)
+            else:
+                logits = kernels.gemm(h.view(M, J), pack.wt, bias=pack.bias, out_dtype=torch.float32, rowstats=rowstats)
+        ldx = logits.stride(0)
         ws_bytes = lib.tfasr_rnnt_workspace_bytes(B, T, U1, V)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=e.device)
         costs = torch.empty(B, dtype=torch.float32, device=e.device)
+        lattice_v2 = fused_lse and ops.lattice_v2_active() and bool(lib.tfasr_rnnt_lattice_smem_supported(T, U1))
         with _lib.TIMERS.region("rnnt_fwd"):
-            if bf16_logits:
-                _lib.check(lib.tfasr_rnnt_loss_fwd_rowstats_bf16(logits.data_ptr(), rowstats.data_ptr(), parts, labels.data_ptr(),
+            if lattice_v2:
+                # the two steps of tfasr_rnnt_loss_fwd_rowstats_* called one by one, the wavefronts on the shared-memory kernel; the planes
+                # are the workspace's (rnnt_loss.cu rnnt_ws_carve: lse, blank, truth, alpha, beta, each rounded up to 256 bytes)
+                plane = (4 * M + 255) // 256 * 256
+                wp = ws.data_ptr()
+                comb, comb_name = ((lib.tfasr_rnnt_lse_from_rowstats_bf16, "tfasr_rnnt_lse_from_rowstats_bf16") if bf16_logits
+                                   else (lib.tfasr_rnnt_lse_from_rowstats_f32, "tfasr_rnnt_lse_from_rowstats_f32"))
+                ld_arg = (ldx,) if bf16_logits else ()
+                _lib.check(comb(logits.data_ptr(), *ld_arg, rowstats.data_ptr(), parts, labels.data_ptr(), logit_length.data_ptr(),
+                                label_length.data_ptr(), B, T, U1, V, wp, wp + plane, wp + 2 * plane, _lib.stream_ptr(e.device)), comb_name)
+                _lib.check(lib.tfasr_rnnt_lattice_smem_f32(wp + plane, wp + 2 * plane, logit_length.data_ptr(), label_length.data_ptr(), B, T, U1,
+                                                           wp + 3 * plane, wp + 4 * plane, costs.data_ptr(), _lib.stream_ptr(e.device)),
+                           "tfasr_rnnt_lattice_smem_f32")
+            elif bf16_logits:
+                _lib.check(lib.tfasr_rnnt_loss_fwd_rowstats_bf16(logits.data_ptr(), ldx, rowstats.data_ptr(), parts, labels.data_ptr(),
                                                                  logit_length.data_ptr(), label_length.data_ptr(), B, T, U1, V, 0, costs.data_ptr(),
                                                                  ws.data_ptr(), ws_bytes, _lib.stream_ptr(e.device)),
                            "tfasr_rnnt_loss_fwd_rowstats_bf16")
@@ -481,17 +502,22 @@ class _TransducerHeadFn(torch.autograd.Function):
         scale = dcosts.float().contiguous()
         from . import ops
 
-        if logits.dtype == torch.bfloat16:  # bf16 logits: the gradient replaces them element for element
-            dl, ld = logits.view(M, V), V
-            bwd_fn, bwd_name = lib.tfasr_rnnt_loss_bwd_bf16_io, "tfasr_rnnt_loss_bwd_bf16_io"
+        if logits.dtype == torch.bfloat16:  # bf16 logits: the gradient replaces them element for element (row pitch of the forward's buffer)
+            ld = logits.stride(0)
+            dl = torch.as_strided(logits, (M, ld), (ld, 1))
+            with _lib.TIMERS.region("rnnt_bwd"):
+                _lib.check(lib.tfasr_rnnt_loss_bwd_bf16_io(logits.data_ptr(), ld, labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(),
+                                                           B, T, U1, V, 0, costs.data_ptr(), scale.data_ptr(), dl.data_ptr(), ld,
+                                                           _grad(pack.bias).data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(h.device)),
+                           "tfasr_rnnt_loss_bwd_bf16_io")
         else:
             dl, ld = logits.view(M, V).view(torch.bfloat16), 2 * V  # [M, 2V] bf16 view of the same memory; gradient lands in [:, :V]
             bwd_fn, bwd_name = ((lib.tfasr_rnnt_loss_bwd_bf16_v2, "tfasr_rnnt_loss_bwd_bf16_v2") if ops.rnnt_grad_v2_active()
                                 else (lib.tfasr_rnnt_loss_bwd_bf16, "tfasr_rnnt_loss_bwd_bf16"))
-        with _lib.TIMERS.region("rnnt_bwd"):
-            _lib.check(bwd_fn(logits.data_ptr(), labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(), B, T, U1, V, 0,
-                              costs.data_ptr(), scale.data_ptr(), dl.data_ptr(), ld, _grad(pack.bias).data_ptr(), ws.data_ptr(), ws.numel(),
-                              _lib.stream_ptr(h.device)), bwd_name)
+            with _lib.TIMERS.region("rnnt_bwd"):
+                _lib.check(bwd_fn(logits.data_ptr(), labels.data_ptr(), logit_length.data_ptr(), label_length.data_ptr(), B, T, U1, V, 0,
+                                  costs.data_ptr(), scale.data_ptr(), dl.data_ptr(), ld, _grad(pack.bias).data_ptr(), ws.data_ptr(), ws.numel(),
+                                  _lib.stream_ptr(h.device)), bwd_name)
         dlv = dl[:, :V]
         h2 = h.view(M, J)
         with _lib.TIMERS.region("joint_gemm_dgrad"):

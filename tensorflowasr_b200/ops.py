@@ -211,6 +211,20 @@ def bf16_logits_active() -> bool:
     return _BF16_LOGITS and _FUSED_LSE
 
 
+_LATTICE_V2 = _os.environ.get("TFASR_LATTICE_V2", "0") == "1"
+
+
+def set_lattice_v2(flag: bool):
+    """Training head (needs fused_lse): alpha / beta wavefronts with the utterance's transition planes staged in shared memory
+    (csrc/rnnt_lattice_v2.cu) when the lattice fits (8 T (U+1) bytes <= 227 KB), else the first-generation kernel."""
+    global _LATTICE_V2
+    _LATTICE_V2 = bool(flag)
+
+
+def lattice_v2_active() -> bool:
+    return _LATTICE_V2 and _FUSED_LSE
+
+
 _PERSISTENT_DECODE = _os.environ.get("TFASR_PERSISTENT_DECODE", "1") == "1"
 
 
@@ -259,7 +273,7 @@ def attention_tc_active(T: int = 0) -> bool:
 
 
 _SWITCHES = ("_FUSED_FFN", "_FUSED", "_FUSED_SEQ", "_DWCONV_WGRAD_V2", "_JOINT_REDUCE_V2", "_IM2COL_V2", "_JOINT_V2", "_RNNT_GRAD_V2", "_CONV1_V2", "_POS_BATCHED",
-             "_PEER_BN", "_FUSED_LSE", "_PERSISTENT_DECODE", "_BF16_LOGITS")
+             "_PEER_BN", "_FUSED_LSE", "_PERSISTENT_DECODE", "_BF16_LOGITS", "_LATTICE_V2")
 
 
 def switch_state() -> dict:

@@ -37,15 +37,30 @@ def _tensors(data: schemas.TrainData):
 
 
 class DevicePrefetcher:
-    """Iterates TrainData batches, host -> device one batch ahead on its own stream.  Batches already on the device pass through."""
+    """Iterates TrainData batches, host -> device one batch ahead on its own stream.  Batches already on the device pass through.
 
-    def __init__(self, batches, device: torch.device):
+    The device side is a ring of `depth` preallocated staging sets (no allocation per step): set k is rewritten by the copy stream only after
+    the step that consumed it has been enqueued and finished on the consumer's stream (an event recorded at the following __next__)."""
+
+    def __init__(self, batches, device: torch.device, depth: int = 2):
         self.it = iter(batches)
         self.dev = device
         self.stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.bytes_moved = 0
+        self.ring = [None] * depth      # staging tensors per slot
+        self.consumed = [None] * depth  # event: the consumer of the slot's previous content is done
+        self.slot = 0
+        self._handed = None  # slot handed out by the last __next__ (its consumer is enqueued by the time __next__ runs again)
         self._next = None
         self._load()
+
+    def _staging(self, k, ts):
+        ring = self.ring[k]
+        if ring is None or len(ring) != len(ts) or any(r.shape != t.shape or r.dtype != t.dtype for r, t in zip(ring, ts)):
+            ring = [torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in ts]
+            self.ring[k] = ring
+            self.consumed[k] = None
+        return ring
 
     def _load(self):
         try:
@@ -57,26 +72,37 @@ class DevicePrefetcher:
         if self.stream is None or all(t.device == self.dev for t in ts):
             self._next = (data if self.stream is not None else _map(lambda t: t.to(self.dev), data), None, None)
             return
+        k = self.slot
+        self.slot = (k + 1) % len(self.ring)
+        ring = self._staging(k, ts)
+        if self.consumed[k] is not None:
+            self.stream.wait_event(self.consumed[k])
         with torch.cuda.stream(self.stream):
-            moved = _map(lambda t: t.to(self.dev, non_blocking=True), data)
+            for r, t in zip(ring, ts):
+                r.copy_(t, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self.bytes_moved += sum(t.numel() * t.element_size() for t in ts if t.device != self.dev)
-        self._next = (moved, ev, data)  # the host batch stays referenced until its copy has been consumed
+        self.bytes_moved += sum(t.numel() * t.element_size() for t in ts)
+        it = iter(ring)
+        moved = _map(lambda t: next(it), data)
+        self._next = (moved, ev, (data, k))  # the host batch stays referenced until its copy has been consumed
 
     def __iter__(self):
         return self
 
     def __next__(self) -> schemas.TrainData:
+        if self._handed is not None:  # everything enqueued since the last hand-out is that slot's consumer
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.dev))
+            self.consumed[self._handed] = ev
+            self._handed = None
         cur = self._next
         if cur is None:
             raise StopIteration
-        data, ev, _host = cur
+        data, ev, host = cur
         if ev is not None:
-            main = torch.cuda.current_stream(self.dev)
-            main.wait_event(ev)
-            for t in _tensors(data):
-                t.record_stream(main)  # allocated on the copy stream, consumed on the step's stream
+            torch.cuda.current_stream(self.dev).wait_event(ev)
+            self._handed = host[1]
         self._load()  # the next batch's copy overlaps the step that is about to be enqueued
         return data
 

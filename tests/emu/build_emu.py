@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(REPO, "tensorflowasr_b200", "csrc")
 OUT = os.path.join(REPO, "build", "emu")
-SOURCES = ["seqconv.cu", "decode.cu", "rnnt_combine.cu", "conv1.cu", "rnnt_grad_v2.cu", "joint_v2.cu", "subsample_v2.cu", "dwconv_wgrad_v2.cu", "peer_allreduce.cu"]  # launcher files written against simt.cuh
+SOURCES = ["seqconv.cu", "decode.cu", "rnnt_combine.cu", "conv1.cu", "rnnt_grad_v2.cu", "rnnt_lattice_v2.cu", "joint_v2.cu", "subsample_v2.cu", "dwconv_wgrad_v2.cu", "peer_allreduce.cu"]  # launcher files written against simt.cuh
 
 
 V1_SOURCES = ["rnnt_loss.cu", "ctc_loss.cu", "logmel.cu", "fused_rows.cu", "conv_bn.cu", "dwconv.cu", "joint.cu", "param_ops.cu", "specaugment.cu", "attention.cu", "lstm.cu", "gemm.cu", "gemm_inst_64.cu", "gemm_inst_128.cu",

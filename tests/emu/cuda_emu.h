@@ -244,6 +244,8 @@ template <class T>
 inline T __shfl_down_sync(unsigned, T v, int delta) { return emu::shfl(v, emu::t_lane + delta); }
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl(v, src); }
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, int delta) { return emu::shfl(v, emu::t_lane - delta); }
 
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 inline void atomicAdd(float4* p, float4 v) {  // red.global.add.v4.f32: four independent float adds

@@ -26,9 +26,14 @@ inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
 
 template <class T>
 inline T __ldg(const T* p) { return *p; }
-template <class T>
-inline T __shfl_up_sync(unsigned, T v, int delta) { return emu::shfl(v, emu::t_lane - delta); }
 inline float log1pf_(float x) { return log1pf(x); }
+namespace tfasr {
+#ifndef TFASR_KLOG2E_DEFINED
+#define TFASR_KLOG2E_DEFINED
+constexpr float kLog2e = 1.4426950408889634f;
+#endif
+inline float fast_ex2(float x) { return exp2f(x); }
+}  // namespace tfasr
 // mixed-width min / max as CUDA's overload set resolves them
 inline int64_t min(int64_t a, int b) { return a < b ? a : b; }
 inline int64_t min(int a, int64_t b) { return a < b ? a : b; }

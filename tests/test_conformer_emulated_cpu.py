@@ -87,8 +87,9 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
         calls2 = dict(emu.calls)
         loss3, g3 = _run(model, data, state0)  # once more on the same packs: packed gradient sums and the shared dpos buffer start clean
         ops.set_bf16_logits(True)
+        ops.set_lattice_v2(True)
         emu.calls.clear()
-        loss4, g4 = _run(model, data, state0)  # + bf16 logits: combine / gradient kernels on the 2-byte tensor, gradient in place at pitch V
+        loss4, g4 = _run(model, data, state0)  # + bf16 logits (combine / gradient kernels on the 2-byte tensor, gradient in place at pitch V) + shared-memory wavefronts
         calls4 = dict(emu.calls)
     finally:
         ops.restore_switches(saved)
@@ -103,7 +104,8 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
               "tfasr_rnnt_loss_fwd_f32", "tfasr_rnnt_loss_bwd_bf16", "tfasr_conv1_3x3s2_fwd", "tfasr_im2col_3x3s2", "tfasr_joint_tanh_fwd"):
         assert calls1.get(k, 0) > 0, (k, sorted(calls1))  # the step really ran on the hand-written kernels
     assert calls2["tfasr_rel_attention_fwd_ld"] == 2 and "tfasr_rel_attention_fwd" not in calls2 and "tfasr_rel_attention_bwd" not in calls2
-    assert calls4.get("tfasr_rnnt_loss_fwd_rowstats_bf16", 0) > 0 and calls4.get("tfasr_rnnt_loss_bwd_bf16_io", 0) > 0, calls4
+    assert calls4.get("tfasr_rnnt_loss_bwd_bf16_io", 0) > 0, calls4
+    assert calls4.get("tfasr_rnnt_lse_from_rowstats_bf16", 0) > 0 and calls4.get("tfasr_rnnt_lattice_smem_f32", 0) > 0, calls4
     assert "tfasr_rnnt_loss_bwd_bf16_v2" not in calls4 and "tfasr_rnnt_loss_fwd_rowstats_f32" not in calls4
     torch.testing.assert_close(loss4, loss2, rtol=5e-3, atol=5e-3)
     assert torch.isfinite(loss1).all() and torch.isfinite(loss2).all()

@@ -120,6 +120,42 @@ def test_transducer_head_with_bf16_logits():
         assert torch.nn.functional.cosine_similarity(a, b, dim=0).item() >= 0.999
 
 
+@pytest.mark.parametrize("bf16_logits", [False, True])
+def test_transducer_head_with_shared_memory_wavefronts(bf16_logits):
+    """csrc/rnnt_lattice_v2.cu through the training head against the first-generation wavefront kernel: same costs (1e-5), same gradients;
+    ragged lengths incl. an empty utterance and one with more labels than frames' worth of slack."""
+    from tensorflowasr_b200 import fused, ops
+
+    torch.manual_seed(13)
+    B, T, U1, J, V = 5, 57, 65, 64, 1000
+    e = (torch.randn(B, T, J, device="cuda") * 0.5).to(torch.bfloat16)
+    p = (torch.randn(B, U1, J, device="cuda") * 0.5).to(torch.bfloat16)
+    labels = torch.randint(1, V, (B, U1 - 1), device="cuda", dtype=torch.int32)
+    tl = torch.tensor([57, 30, 7, 1, 0], device="cuda", dtype=torch.int32)
+    ul = torch.tensor([64, 33, 0, 2, 5], device="cuda", dtype=torch.int32)
+    weights = torch.tensor([1.0, 0.5, 2.0, 1.5, 1.0], device="cuda")
+    res = {}
+    saved = ops.switch_state()
+    try:
+        ops.set_fused_lse(True)
+        ops.set_bf16_logits(bf16_logits)
+        for flag in (False, True):
+            ops.set_lattice_v2(flag)
+            w = torch.nn.Parameter((torch.randn(J, V, generator=torch.Generator().manual_seed(5)) / J ** 0.5).cuda())
+            bvec = torch.nn.Parameter(torch.randn(V, generator=torch.Generator().manual_seed(6)).cuda() * 0.1)
+            er, pr = e.clone().requires_grad_(True), p.clone().requires_grad_(True)
+            costs = fused.transducer_head(er, pr, fused.WeightPack(w, bvec), labels, tl, ul)
+            finite = torch.isfinite(costs)
+            (costs[finite] * weights[finite]).sum().backward()
+            res[flag] = (costs.detach().clone(), er.grad.clone(), pr.grad.clone(), w.grad.clone(), bvec.grad.clone())
+    finally:
+        ops.restore_switches(saved)
+    assert torch.isinf(res[True][0][4]) and torch.isinf(res[False][0][4])  # the empty utterance
+    torch.testing.assert_close(res[True][0][:4], res[False][0][:4], rtol=1e-5, atol=1e-4)
+    for a, b in zip(res[True][1:], res[False][1:]):
+        assert (a.float() - b.float()).abs().max().item() <= 2e-3 * (b.float().abs().max().item() + 1e-6)
+
+
 def test_conv1_v2_matches_first_generation_kernels():
     """csrc/conv1.cu (opt-in, TFASR_CONV1_V2) against the verified conv_bn.cu kernels: identical contract."""
     from tensorflowasr_b200 import kernels, ops
