@@ -244,77 +244,97 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_io8_kernel(co
   }
   float* cs = s_cs + (size_t)warp * V;
   float4* cs4 = reinterpret_cast<float4*>(cs);
-  for (int64_t row = (int64_t)blockIdx.x * kG2Warps + warp; row < nrows; row += (int64_t)gridDim.x * kG2Warps) {
-    const uint32_t r32 = (uint32_t)row;  // B T U1 < 2^31 (checked by the launcher): 32-bit divisions
-    const int u = (int)(r32 % (uint32_t)U1);
-    const int t = (int)((r32 / (uint32_t)U1) % (uint32_t)T);
-    const int b = (int)(r32 / ((uint32_t)U1 * (uint32_t)T));
-    int Tb, Ub;
-    lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
-    __nv_bfloat16* gr = grads + row * ld_g;
-    uint4* g8 = reinterpret_cast<uint4*>(gr);
-    if (!((t < Tb) && (u <= Ub))) {
-      for (int j = lane; j < n8; j += 32) g8[j] = make_uint4(0u, 0u, 0u, 0u);
-      continue;
-    }
-    const float logz = -costs[b];
-    const float a = ws.alpha[row];
-    const float lse = ws.lse[row];
-    float gb = 0.f, gt = 0.f;
-    int label = -1;
-    if (t < Tb - 1) gb = -expf(a + ws.beta[row + U1] + ws.blank[row] - logz);
-    else if (u == Ub) gb = -1.0f;
-    if (u < Ub) {
-      gt = -expf(a + ws.beta[row + 1] + ws.truth[row] - logz);
-      label = labels[(int64_t)b * (U1 - 1) + u];
-    }
-    const float sc = grad_scale ? grad_scale[b] : 1.0f;
-    gb *= sc;
-    gt *= sc;
-    const float ng = -(gb + gt), nl = -lse * kLog2e;
-    const __nv_bfloat16* xr = logits + row * ld_x;
-    const bool own_label = label >= 0 && ((label >> 3) & 31) == lane;
-    const float x0 = lane == 0 ? __bfloat162float(xr[0]) : 0.f;
-    const float xl = own_label ? __bfloat162float(xr[label]) : 0.f;
-    const uint4* x8 = reinterpret_cast<const uint4*>(xr);
-    uint4 v[NV8];
-#pragma unroll
-    for (int i = 0; i < NV8; ++i) {
-      const int j = lane + 32 * i;
-      if (j < n8) v[i] = simt_ld_stream_u4(x8 + j);
-    }
-#pragma unroll
-    for (int i = 0; i < NV8; ++i) {
-      const int j = lane + 32 * i;
-      if (j < n8) {
-        float f[8];
-        bf8_unpack(v[i], f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = ng * simt_ex2(fmaf(f[k], kLog2e, nl));
-        if (dbias) {
-          float4 c0 = cs4[2 * j], c1 = cs4[2 * j + 1];
-          c0.x += f[0];
-          c0.y += f[1];
-          c0.z += f[2];
-          c0.w += f[3];
-          c1.x += f[4];
-          c1.y += f[5];
-          c1.z += f[6];
-          c1.w += f[7];
-          cs4[2 * j] = c0;
-          cs4[2 * j + 1] = c1;
+  // A warp takes 32 consecutive rows at a time: lane l derives the per-row scalars of row base + l (lattice position, the two transition
+  // gradients — two expf —, the label) with coalesced reads of the [B,T,U1] planes, and the row loop fetches them by shuffle.  The first
+  // version derived them per row on every lane: ~150 warp instructions per row against ~200 for the row's 1000 logits
+  // (profiles/head_bf16_ncu_r02.txt: 266 M warp instructions, issue slots 55 % busy, 4.7 TB/s).
+  const int64_t nchunks = (nrows + 31) >> 5;
+  for (int64_t chunk = (int64_t)blockIdx.x * kG2Warps + warp; chunk < nchunks; chunk += (int64_t)gridDim.x * kG2Warps) {
+    const int64_t row0 = chunk << 5;
+    float nl_l = 0.f, ng_l = 0.f, gb_l = 0.f, gt_l = 0.f;
+    int label_l = -2;  // -2: row outside its utterance's lattice (zero gradient); -1: inside, no truth transition
+    if (row0 + lane < nrows) {
+      const int64_t rl = row0 + lane;
+      const uint32_t r32 = (uint32_t)rl;  // B T U1 < 2^31 (checked by the launcher): 32-bit divisions
+      const int u = (int)(r32 % (uint32_t)U1);
+      const int t = (int)((r32 / (uint32_t)U1) % (uint32_t)T);
+      const int b = (int)(r32 / ((uint32_t)U1 * (uint32_t)T));
+      int Tb, Ub;
+      lattice_lens(logit_len, label_len, b, T, U1 - 1, Tb, Ub);
+      if ((t < Tb) && (u <= Ub)) {
+        const float logz = -costs[b];
+        const float al = ws.alpha[rl];
+        float gb = 0.f, gt = 0.f;
+        label_l = -1;
+        if (t < Tb - 1) gb = -expf(al + ws.beta[rl + U1] + ws.blank[rl] - logz);
+        else if (u == Ub) gb = -1.0f;
+        if (u < Ub) {
+          gt = -expf(al + ws.beta[rl + 1] + ws.truth[rl] - logz);
+          label_l = labels[(int64_t)b * (U1 - 1) + u];
         }
-        g8[j] = bf8_pack(f);
+        const float sc = grad_scale ? grad_scale[b] : 1.0f;
+        gb_l = gb * sc;
+        gt_l = gt * sc;
+        ng_l = -(gb_l + gt_l);
+        nl_l = -ws.lse[rl] * kLog2e;
       }
     }
-    // the two columns with an extra term, by their owners (same thread as the vector store above: program order)
-    if (lane == 0) {
-      gr[0] = __float2bfloat16_rn(ng * simt_ex2(fmaf(x0, kLog2e, nl)) + gb);
-      if (dbias) cs[0] += gb;
-    }
-    if (own_label) {
-      gr[label] = __float2bfloat16_rn(ng * simt_ex2(fmaf(xl, kLog2e, nl)) + gt);
-      if (dbias) cs[label] += gt;
+    const int nr = (int)((nrows - row0 < 32) ? (nrows - row0) : 32);
+    for (int r = 0; r < nr; ++r) {
+      const int label = __shfl_sync(0xffffffffu, label_l, r);
+      const float nl = __shfl_sync(0xffffffffu, nl_l, r), ng = __shfl_sync(0xffffffffu, ng_l, r);
+      const float gb = __shfl_sync(0xffffffffu, gb_l, r), gt = __shfl_sync(0xffffffffu, gt_l, r);
+      const int64_t row = row0 + r;
+      __nv_bfloat16* gr = grads + row * ld_g;
+      uint4* g8 = reinterpret_cast<uint4*>(gr);
+      if (label == -2) {
+        for (int j = lane; j < n8; j += 32) g8[j] = make_uint4(0u, 0u, 0u, 0u);
+        continue;
+      }
+      const __nv_bfloat16* xr = logits + row * ld_x;
+      const bool own_label = label >= 0 && ((label >> 3) & 31) == lane;
+      const float x0 = lane == 0 ? __bfloat162float(xr[0]) : 0.f;
+      const float xl = own_label ? __bfloat162float(xr[label]) : 0.f;
+      const uint4* x8 = reinterpret_cast<const uint4*>(xr);
+      uint4 v[NV8];
+#pragma unroll
+      for (int i = 0; i < NV8; ++i) {
+        const int j = lane + 32 * i;
+        if (j < n8) v[i] = simt_ld_stream_u4(x8 + j);
+      }
+#pragma unroll
+      for (int i = 0; i < NV8; ++i) {
+        const int j = lane + 32 * i;
+        if (j < n8) {
+          float f[8];
+          bf8_unpack(v[i], f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = ng * simt_ex2(fmaf(f[k], kLog2e, nl));
+          if (dbias) {
+            float4 c0 = cs4[2 * j], c1 = cs4[2 * j + 1];
+            c0.x += f[0];
+            c0.y += f[1];
+            c0.z += f[2];
+            c0.w += f[3];
+            c1.x += f[4];
+            c1.y += f[5];
+            c1.z += f[6];
+            c1.w += f[7];
+            cs4[2 * j] = c0;
+            cs4[2 * j + 1] = c1;
+          }
+          g8[j] = bf8_pack(f);
+        }
+      }
+      // the two columns with an extra term, by their owners (same thread as the vector store above: program order)
+      if (lane == 0) {
+        gr[0] = __float2bfloat16_rn(ng * simt_ex2(fmaf(x0, kLog2e, nl)) + gb);
+        if (dbias) cs[0] += gb;
+      }
+      if (own_label) {
+        gr[label] = __float2bfloat16_rn(ng * simt_ex2(fmaf(xl, kLog2e, nl)) + gt);
+        if (dbias) cs[label] += gt;
+      }
     }
   }
   if (dbias) {
@@ -425,6 +445,8 @@ extern "C" int tfasr_rnnt_loss_bwd_bf16_io(const void* logits, int64_t ld_logits
   } while (0)
 #endif
   if (wide) {
+    ctas = ceil_div(ceil_div(nrows, 32), kG2Warps);  // one 32-row chunk per warp and pass: CTAs retire and refill, which balances the SMs
+    if (ctas > (int64_t)kNumSMs * 16) ctas = (int64_t)kNumSMs * 16;
     if (V <= 256) G2_LAUNCH(rnnt_grad_bf16_io8_kernel, 1);
     else if (V <= 512) G2_LAUNCH(rnnt_grad_bf16_io8_kernel, 2);
     else if (V <= 1024) G2_LAUNCH(rnnt_grad_bf16_io8_kernel, 4);

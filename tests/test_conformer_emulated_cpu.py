@@ -72,6 +72,8 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
     try:
         for s in v2:
             s(False)
+        ops.set_bf16_logits(False)  # the head's round-2 defaults come back on for the fourth configuration below
+        ops.set_lattice_v2(False)
         ops.set_precision("fp32")
         ops.set_fused(False)
         ref_loss, ref_g = _run(model, data, state0)  # library route, fp32: the reference

@@ -43,6 +43,7 @@ def test_transducer_head_costs_and_gradients_match_with_fused_lse():
     ul = torch.tensor([8, 3, 0], device="cuda", dtype=torch.int32)
     res = {}
     try:
+        ops.set_bf16_logits(False)  # this test isolates the normaliser: f32 logits on both sides
         for flag in (False, True):
             ops.set_fused_lse(flag)
             w = torch.nn.Parameter((torch.randn(J, V, generator=torch.Generator().manual_seed(5)) / J ** 0.5).cuda())
@@ -194,6 +195,7 @@ def test_rnnt_grad_v2_matches_first_generation_kernel():
     ul = torch.tensor([10, 4, 0, 2], device="cuda", dtype=torch.int32)
     res = {}
     try:
+        ops.set_bf16_logits(False)  # the f32-logits gradient kernels are the subject here
         for key, (g2, lse) in {"base": (False, False), "grad_v2": (True, False), "both": (True, True)}.items():
             ops.set_rnnt_grad_v2(g2)
             ops.set_fused_lse(lse)
