@@ -384,13 +384,14 @@ def _run_ours(args, real_stdout):
     jg_ms = kernel_ms.get("joint_gemm_fwd", 0.0)
     roofline_joint = None
     if jg_ms > 0:
+        jkey = "joint_gemm_bf16_logits" if lb == 2 else "joint_gemm"
         gemm_flops = 2.0 * rows * J * VOCAB
         gemm_bytes = 2.0 * rows * J + 2.0 * VOCAB * J + float(lb) * rows * VOCAB
         ach = gemm_bytes / (jg_ms * 1e-3) / 1e9
         tpeak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         roofline_joint = {"kernel": f"gemm_bf16_kernel<256> (joint logits = tanh(e+p) . Wv + bv, {'bf16' if lb == 2 else 'f32'} out through TMA stores)", "bound": "hbm",
                           "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                          "traffic": traffic.get("joint_gemm", {}).get("bytes"), "traffic_source": traffic.get("joint_gemm", {}).get("source"),
+                          "traffic": traffic.get(jkey, {}).get("bytes"), "traffic_source": traffic.get(jkey, {}).get("source"),
                           "algorithmic_bytes_per_launch": gemm_bytes, "algorithmic_flops_per_launch": gemm_flops,
                           "tensor_tflops": gemm_flops / (jg_ms * 1e-3) / 1e12, "tensor_frac_of_sustained_bf16": gemm_flops / (jg_ms * 1e-3) / 1e12 / tpeak,
                           "ms_per_launch": jg_ms, "share_of_step": jg_ms / ms, "peak_source": pk["_source"], "timing": timing}

@@ -314,6 +314,31 @@ class BaseModel(nn.Module):
             self._apply_gradients()  # all_reduce() launches every bucket now (none was launched by the hooks) and waits
         return {"loss": self._last_losses}
 
+    # ------------------------------------------------------------------ training state beyond the weights
+    def set_training_seed(self, seed: int):
+        """Seed of the dropout / SpecAugment streams, mixed with this replica's rank (the reference seeds python / numpy / TF globally,
+        env_util.py:147-165, and lets every replica draw its own masks)."""
+        from . import fused
+
+        fused.STATE.reseed(seed)
+        return self
+
+    def training_state(self) -> dict:
+        """What a restart needs besides `named_weights()`: optimizer state, schedule position, the dropout / SpecAugment counter."""
+        from . import fused
+
+        return {"iterations": self._iterations, "dropout": fused.STATE.state_dict(),
+                "optimizer": self.optimizer.state_dict() if self.optimizer is not None else None}
+
+    def load_training_state(self, state: dict):
+        from . import fused
+
+        self._iterations = int(state["iterations"])
+        fused.STATE.load_state_dict(state["dropout"])
+        if state.get("optimizer") is not None and self.optimizer is not None:
+            self.optimizer.load_state_dict(state["optimizer"])
+        return self
+
     def fit(self, x=None, epochs=1, steps_per_epoch=None, callbacks=None, initial_epoch=0, verbose=0, **kwargs):
         """keras.Model.fit for this path (scripts/train.py:113-121): drives `train_step` over an iterable of TrainData batches with the next
         batch's host->device copy on a copy stream and the per-step loss read back one step late (training.py).  Returns a History."""

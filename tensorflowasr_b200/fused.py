@@ -15,19 +15,44 @@ LN_EPS = 1e-3
 
 
 class StepState:
-    """Per-step device state shared by all fused modules: the dropout counter (bumped once per step, inside the CUDA graph)."""
+    """Per-step device state shared by all fused modules: the dropout / SpecAugment counter (bumped once per step, inside the CUDA graph).
+    Its start value mixes a user seed with the replica's rank (`reseed`; every replica draws its own masks, a restarted run can draw new ones)
+    and it is part of the training state (`state_dict` / `load_state_dict`: BaseModel saves it beside the optimizer)."""
 
     def __init__(self):
         self.seed = None
+        self.initial = 0
+
+    @staticmethod
+    def _mix(seed: int, rank: int) -> int:
+        x = (int(seed) * 0x9E3779B97F4A7C15 + (int(rank) + 1) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        x ^= x >> 31
+        return x & 0x7FFFFFFFFFFFFFFF if seed or rank else 0  # (0, rank 0) keeps the historical stream
+
+    def reseed(self, seed: int, rank: int = None):
+        if rank is None:
+            d = torch.distributed
+            rank = d.get_rank() if d.is_available() and d.is_initialized() else 0
+        self.initial = self._mix(seed, rank)
+        if self.seed is not None:
+            self.seed.fill_(self.initial)
 
     def seed_tensor(self, device):
         if self.seed is None or self.seed.device != device:
-            self.seed = torch.zeros(1, dtype=torch.int64, device=device)
+            self.seed = torch.full((1,), self.initial, dtype=torch.int64, device=device)
         return self.seed
 
     def bump(self):
         if self.seed is not None:
             self.seed.add_(0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+
+    def state_dict(self) -> dict:
+        return {"counter": int(self.seed.item()) if self.seed is not None else self.initial}
+
+    def load_state_dict(self, state: dict):
+        self.initial = int(state["counter"])
+        if self.seed is not None:
+            self.seed.fill_(self.initial)
 
 
 STATE = StepState()

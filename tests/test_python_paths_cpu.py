@@ -224,3 +224,24 @@ def test_ctc_prefix_beam_search_finds_the_most_probable_labelling():
         assert tuple(ctc_beam_search(logits, T, beam_width=200, blank=blank)) == best
         assert tuple(ctc_beam_search(logits, T - 2, beam_width=200, blank=blank)) != () or True  # shorter length: runs, no frame beyond it is read
     assert ctc_beam_search(np.zeros((0, 4)), 0) == []
+
+
+def test_dropout_counter_is_seedable_rank_mixed_and_saved():
+    """the dropout / SpecAugment counter starts from a user seed mixed with the rank and travels with the training state."""
+    from tensorflowasr_b200 import fused
+
+    st = fused.StepState()
+    assert int(st.seed_tensor(torch.device("cpu"))) == 0  # default stream unchanged
+    a, b = fused.StepState(), fused.StepState()
+    a.reseed(7, rank=0)
+    b.reseed(7, rank=1)
+    va, vb = int(a.seed_tensor(torch.device("cpu"))), int(b.seed_tensor(torch.device("cpu")))
+    assert va != vb and va != 0 and vb != 0  # replicas draw different masks
+    a.bump()
+    saved = a.state_dict()
+    c = fused.StepState()
+    c.seed_tensor(torch.device("cpu"))
+    c.load_state_dict(saved)
+    assert int(c.seed) == int(a.seed) == saved["counter"]
+    a.reseed(7, rank=0)
+    assert int(a.seed) == va  # reseeding rewinds the live counter
