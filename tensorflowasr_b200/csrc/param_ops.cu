@@ -11,7 +11,9 @@
 
 namespace tfasr {
 
-// p, g, m, v: flat fp32 [n].  AdamW with decoupled weight decay exactly as torch.optim.AdamW / Keras Adam(weight_decay):
+// p, g, m, v: flat fp32 [n].  AdamW with decoupled weight decay in the form of torch.optim.AdamW.  Keras Adam(weight_decay) differs in ONE
+// place: it adds epsilon to sqrt(v) before the bias correction (p -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps)), i.e. its effective epsilon
+// is eps / sqrt(1 - b2^t) — with the reference's eps = 1e-9 (small.yml.j2:73-87) the two updates agree to ~1e-8 relative from the first step on:
 //   g' = g * grad_scale + 2 * l2 * p * mask      (Keras l2 regularizers of conformer.py:27, applied through their gradient)
 //   p *= 1 - lr * wd;  m = b1 m + (1 - b1) g';  v = b2 v + (1 - b2) g'^2
 //   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)

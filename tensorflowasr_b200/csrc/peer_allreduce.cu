@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const uint
     }
     data[i] = s;
   }
-  if (late) state[1] = 1u;
+  if (late) atomicAdd(reinterpret_cast<int*>(state) + 1, 1);  // any non-zero value = a peer missed the wait (one atomic per late thread: no plain-store race)
   if (tid == 0) state[0] = epoch;
 }
 

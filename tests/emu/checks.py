@@ -883,7 +883,7 @@ def check_peer_allreduce_errors(lib):
     buf, bp = heap(np.ones(8, np.float32))
     comm = PeerComm(tp, sp, 0, world, cap, 50)
     assert lib.tfasr_peer_allreduce_f32(ctypes.byref(comm), bp, 8, None) == 0
-    assert state[0] == 1 and state[1] == 1
+    assert state[0] == 1 and state[1] >= 1  # one count per thread that gave up
     assert lib.tfasr_peer_allreduce_f32(ctypes.byref(comm), bp, 9, None) == 1  # n > capacity
     assert lib.tfasr_peer_allreduce_f32(None, bp, 8, None) == 1
     bad = PeerComm(tp, sp, 2, world, cap, 50)
