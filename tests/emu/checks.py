@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -966,5 +967,6 @@ if __name__ == "__main__":
             continue
         if "--fast" in sys.argv and name in ("random_shapes",):  # the sanitizer passes skip the sweep (it repeats the fixed cases' code paths)
             continue
+        t0 = time.time()
         fn(lib)
-        print("ok", name, flush=True)
+        print("ok", name, f"{time.time() - t0:.1f}s", flush=True)

@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -987,7 +988,8 @@ if __name__ == "__main__":
         if "--fast" in flags and name in ("random_shapes_v1", "rnnt_wide_u"):  # sanitizer passes: skip the sweep and the largest lattice
             continue
         try:
+            t0 = time.time()
             fn(lib)
-            print("ok", name, flush=True)
+            print("ok", name, f"{time.time() - t0:.1f}s", flush=True)
         except SkipCase as e:
             print("skip", name, e, flush=True)
