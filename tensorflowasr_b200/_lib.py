@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_size_t, c_void_p
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtfasr_b200.so")
+LIB_PATH = os.environ.get("TFASR_LIB_PATH") or os.path.join(_PKG, "libtfasr_b200.so")  # the override is for A/B runs of two builds (tools/)
 
 
 class LogmelCfg(ctypes.Structure):

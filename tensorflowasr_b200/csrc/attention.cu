@@ -43,6 +43,30 @@ __device__ __forceinline__ bool att_allowed(int t, int j, int len, int T, int ch
   return true;
 }
 
+// The same predicate as a per-row key window, derived ONCE per row: key j is allowed iff (unsigned)(j - lo) < (unsigned)n  (n = 0: the whole
+// row is masked).  The tensor-core kernels test it per score: one subtract + one unsigned compare instead of a division by the chunk size.
+struct AttWin {
+  int lo;
+  unsigned n;
+};
+__device__ __forceinline__ AttWin att_window(int t, int len, int T, int chunk, int history) {
+  AttWin w;
+  w.lo = 0;
+  w.n = 0u;
+  if (t >= len) return w;  // query-side mask
+  if (chunk > 0) {
+    const int c0 = (t / chunk) * chunk;
+    const int hist = history < 0 ? T : history;
+    const int start = max(0, c0 - hist), end = min(T, c0 + chunk);
+    w.lo = start;
+    w.n = (unsigned)max(end - start, 0);
+    return w;
+  }
+  w.n = 0x7fffffffu;  // no key-side mask without streaming (padded key columns are handled by the callers)
+  return w;
+}
+__device__ __forceinline__ bool att_in(const AttWin& w, int j) { return (unsigned)(j - w.lo) < w.n; }
+
 // smem row stride (in bf16 elements) for K / V / P tiles: H + 2 keeps 4-byte alignment and an odd word stride (H = 36 -> 19 words)
 __device__ __forceinline__ int att_stride(int H) { return ((H + 2) | 2); }
 
@@ -425,7 +449,7 @@ __device__ __forceinline__ void att_stage_q(const AttParams& p, int b, int n, __
 template <int KS>
 __device__ __forceinline__ void att_chunk_scores(float (&s)[8][4], const uint32_t (&aqu)[KS][4], const uint32_t (&aqv)[KS][4],
                                                  const __nv_bfloat16* sK, const __nv_bfloat16* sP, float* scratch, int rr0, int c0, int lane,
-                                                 int tA, int tB, int len, const AttParams& p) {
+                                                 const AttWin& wA, const AttWin& wB, const AttParams& p) {
   constexpr int HS = AttMma<KS>::HS, SCW = AttMma<KS>::SCW;
   const int g = lane >> 2, tq = lane & 3;
   const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
@@ -456,10 +480,10 @@ __device__ __forceinline__ void att_chunk_scores(float (&s)[8][4], const uint32_
     const float* rb = scratch + (g + 8) * SCW + jl + 7 - g;
     float s0 = acc[0] + ra[0], s1 = acc[1] + ra[1], s2 = acc[2] + rb[0], s3 = acc[3] + rb[1];
     // masked_fill(-1e9) of general.py:30-41; padded key columns do not exist (-inf)
-    if (!att_allowed(tA, j, len, p.T, p.chunk, p.history)) s0 = -1e9f;
-    if (!att_allowed(tA, j + 1, len, p.T, p.chunk, p.history)) s1 = -1e9f;
-    if (!att_allowed(tB, j, len, p.T, p.chunk, p.history)) s2 = -1e9f;
-    if (!att_allowed(tB, j + 1, len, p.T, p.chunk, p.history)) s3 = -1e9f;
+    if (!att_in(wA, j)) s0 = -1e9f;
+    if (!att_in(wA, j + 1)) s1 = -1e9f;
+    if (!att_in(wB, j)) s2 = -1e9f;
+    if (!att_in(wB, j + 1)) s3 = -1e9f;
     if (j >= p.T) s0 = s2 = -CUDART_INF_F;
     if (j + 1 >= p.T) s1 = s3 = -CUDART_INF_F;
     s[nt][0] = s0;
@@ -520,11 +544,12 @@ __global__ void __launch_bounds__(512, 1) rel_attention_fwd_mma_kernel(const Att
   float* scratch = reinterpret_cast<float*>(U) + (size_t)warp * 16 * C::SCW;
   const int rr0 = Tk - 16 - tw;
   const int tA = tw + g, tB = tw + g + 8;
+  const AttWin wA = att_window(tA, len, T, p.chunk, p.history), wB = att_window(tB, len, T, p.chunk, p.history);
   // ---- pass 1: row max and sum
   float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
   for (int c0 = 0; c0 < Tc; c0 += C::CH) {
     float s[8][4];
-    att_chunk_scores<KS>(s, aqu, aqv, sK, sP, scratch, rr0, c0, lane, tA, tB, len, p);
+    att_chunk_scores<KS>(s, aqu, aqv, sK, sP, scratch, rr0, c0, lane, wA, wB, p);
     float x0 = -CUDART_INF_F, x1 = -CUDART_INF_F;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -532,18 +557,22 @@ __global__ void __launch_bounds__(512, 1) rel_attention_fwd_mma_kernel(const Att
       x1 = fmaxf(x1, fmaxf(s[nt][2], s[nt][3]));
     }
     const float n0 = fmaxf(m0, quad_max(x0)), n1 = fmaxf(m1, quad_max(x1));  // finite from the first chunk on (key 0 exists)
+    // a term is FADD + FMUL + ex2.approx.ftz instead of __expf's six instructions (the exponentials were a quarter of this kernel's issue
+    // slots, profiles/attention_ncu_r01.txt).  The subtraction stays a separate, exact step: a fully masked row has s = m = -1e9, and folding
+    // m into an FFMA would leave the rounding error of 1e9 * log2(e) in the exponent
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      a0 += __expf(s[nt][0] - n0) + __expf(s[nt][1] - n0);
-      a1 += __expf(s[nt][2] - n1) + __expf(s[nt][3] - n1);
+      a0 += fast_ex2((s[nt][0] - n0) * kLog2e) + fast_ex2((s[nt][1] - n0) * kLog2e);
+      a1 += fast_ex2((s[nt][2] - n1) * kLog2e) + fast_ex2((s[nt][3] - n1) * kLog2e);
     }
-    l0 = l0 * __expf(m0 - n0) + a0;
-    l1 = l1 * __expf(m1 - n1) + a1;
+    l0 = l0 * fast_ex2((m0 - n0) * kLog2e) + a0;  // m = -inf on the first chunk: 2^-inf = 0
+    l1 = l1 * fast_ex2((m1 - n1) * kLog2e) + a1;
     m0 = n0;
     m1 = n1;
   }
-  const float inv0 = 1.0f / quad_sum(l0), inv1 = 1.0f / quad_sum(l1);
+  // p = 2^((s - m) log2e - log2 l): the normaliser rides in the exponent
+  const float e0 = -log2f(quad_sum(l0)), e1 = -log2f(quad_sum(l1));
   // ---- pass 2: probabilities and O = P . V
   float o[KS * 2][4];
 #pragma unroll
@@ -553,12 +582,12 @@ __global__ void __launch_bounds__(512, 1) rel_attention_fwd_mma_kernel(const Att
   const bool even = (T & 1) == 0;
   for (int c0 = 0; c0 < Tc; c0 += C::CH) {
     float s[8][4];
-    att_chunk_scores<KS>(s, aqu, aqv, sK, sP, scratch, rr0, c0, lane, tA, tB, len, p);
+    att_chunk_scores<KS>(s, aqu, aqv, sK, sP, scratch, rr0, c0, lane, wA, wB, p);
     uint32_t pa[8], pb[8];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      pa[nt] = pack_bf16(__expf(s[nt][0] - m0) * inv0, __expf(s[nt][1] - m0) * inv0);
-      pb[nt] = pack_bf16(__expf(s[nt][2] - m1) * inv1, __expf(s[nt][3] - m1) * inv1);
+      pa[nt] = pack_bf16(fast_ex2(fmaf(s[nt][0] - m0, kLog2e, e0)), fast_ex2(fmaf(s[nt][1] - m0, kLog2e, e0)));
+      pb[nt] = pack_bf16(fast_ex2(fmaf(s[nt][2] - m1, kLog2e, e1)), fast_ex2(fmaf(s[nt][3] - m1, kLog2e, e1)));
       const int j = c0 + nt * 8 + 2 * tq;
       if (even) {
         if (j < T) {
@@ -680,6 +709,8 @@ __global__ void __launch_bounds__(512, 1) rel_attention_bwd_rows_mma_kernel(cons
     const int rr0 = Tk - 16 - tw;
     const int tA = tw + g, tB = tw + g + 8;
     const int rA = min(tA, T - 1), rB = min(tB, T - 1);
+    // rows past the sequence (tA >= T) have an empty window: len <= T, so att_window masks them through its query-side test
+    const AttWin wA = att_window(tA, min(len, T), T, p.chunk, p.history), wB = att_window(tB, min(len, T), T, p.chunk, p.history);
     // delta = dO . O over the head dimension (quad-split)
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -738,10 +769,10 @@ __global__ void __launch_bounds__(512, 1) rel_attention_bwd_rows_mma_kernel(cons
         const int jl = nt * 8 + 2 * tq, j = c0 + jl;
         float s0 = pA[nt].x * (acc[0] - d0), s1 = pA[nt].y * (acc[1] - d0);
         float s2 = pB[nt].x * (acc[2] - d1), s3 = pB[nt].y * (acc[3] - d1);
-        if (tA >= T || !att_allowed(tA, j, len, T, p.chunk, p.history)) s0 = 0.f;  // masked scores are constants
-        if (tA >= T || !att_allowed(tA, j + 1, len, T, p.chunk, p.history)) s1 = 0.f;
-        if (tB >= T || !att_allowed(tB, j, len, T, p.chunk, p.history)) s2 = 0.f;
-        if (tB >= T || !att_allowed(tB, j + 1, len, T, p.chunk, p.history)) s3 = 0.f;
+        if (!att_in(wA, j)) s0 = 0.f;  // masked scores are constants
+        if (!att_in(wA, j + 1)) s1 = 0.f;
+        if (!att_in(wB, j)) s2 = 0.f;
+        if (!att_in(wB, j + 1)) s3 = 0.f;
         da[nt] = pack_bf16(s0, s1);
         db[nt] = pack_bf16(s2, s3);
         const __nv_bfloat162 va = *reinterpret_cast<const __nv_bfloat162*>(&da[nt]), vb = *reinterpret_cast<const __nv_bfloat162*>(&db[nt]);

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_v2_kernel(con
     const float sc = grad_scale ? grad_scale[b] : 1.0f;
     gb *= sc;
     gt *= sc;
-    const float gsum = gb + gt;
+    const float ng = -(gb + gt), nl = -lse * kLog2e;
     const float4* x4 = reinterpret_cast<const float4*>(logits + row * V);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -88,10 +88,10 @@ __global__ void __launch_bounds__(kG2Warps * 32, 3) rnnt_grad_bf16_v2_kernel(con
         const int j = j0 + lane + 32 * i;
         if (j < j1) {
           float4 o;
-          o.x = -__expf(v[i].x - lse) * gsum;
-          o.y = -__expf(v[i].y - lse) * gsum;
-          o.z = -__expf(v[i].z - lse) * gsum;
-          o.w = -__expf(v[i].w - lse) * gsum;
+          o.x = ng * simt_ex2(fmaf(v[i].x, kLog2e, nl));  // -softmax * sum(g): FFMA + ex2.approx.ftz + FMUL per logit
+          o.y = ng * simt_ex2(fmaf(v[i].y, kLog2e, nl));
+          o.z = ng * simt_ex2(fmaf(v[i].z, kLog2e, nl));
+          o.w = ng * simt_ex2(fmaf(v[i].w, kLog2e, nl));
           const int c0 = 4 * j;
           if (c0 == 0) o.x += gb;
           if (label >= c0 && label < c0 + 4) {
