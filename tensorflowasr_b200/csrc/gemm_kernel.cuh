@@ -344,22 +344,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       sm100::tc_fence_after();
       if (warp == 2 && lane == 0 && acc_it < 2) TRACE(5 + 2 * acc_it);
       asm volatile("bar.sync 1, 256;" ::: "memory");  // bias slice visible to the 8 epilogue warps
-      // The accumulator columns of group gi + 1 are requested (tcgen05.ld is asynchronous) before group gi is processed: with two epilogue
-      // warps per scheduler nothing else hides the TMEM read latency of a group behind the ~500 instructions of the previous one
-      uint32_t rn[2][16];
-      bool two_n = false;
-      if (my_groups > 0 && num_k > 0) {
-        two_n = c_begin + 16 < c_end;
-        sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)c_begin, rn[0]);
-        if (two_n) sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)(c_begin + 16), rn[1]);
-      }
 #pragma unroll 1
       for (int gi = 0; gi < my_groups && num_k > 0; ++gi) {
         const int cg0 = c_begin + gi * 32;
         uint8_t* sbuf = sbuf0 + ((aux_tma ? 2 * gi : gi) & nbuf_mask) * gbytes;
         [[maybe_unused]] uint8_t* abuf = sbuf0 + ((2 * gi + 1) & 3) * 2048;
         uint32_t r[2][16];
-        const bool two = two_n;
+        const bool two = cg0 + 16 < c_end;
+        sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)cg0, r[0]);
+        if (two) sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)(cg0 + 16), r[1]);
         if (tma_out && gi >= 2 && (c_f32 || aux_tma)) {
           // buffers come round again: the stores issued two groups ago must have finished reading them
           if (lane == 0) {
@@ -373,16 +366,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           side_phase ^= 1u << gi;
         }
         sm100::tmem_ld_wait();
-#pragma unroll
-        for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[ci][j] = rn[ci][j];
-        if (gi + 1 < my_groups) {
-          const int cn = cg0 + 32;
-          two_n = cn + 16 < c_end;
-          sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)cn, rn[0]);
-          if (two_n) sm100::tmem_ld_32x32b_x16(tmem_row + (uint32_t)(cn + 16), rn[1]);
-        }
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           if (ci == 1 && !two) break;
