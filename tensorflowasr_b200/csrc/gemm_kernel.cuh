@@ -25,6 +25,7 @@
 
 namespace tfasr {
 
+bool gemm_pdl_enabled();  // gemm.cu: environment switch TFASR_PDL, read once
 bool make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 bool make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 
@@ -206,6 +207,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  sm100::grid_dependency_wait();  // everything above touched only this CTA's shared memory and TMEM; global memory from here on
   if (threadIdx.x == 0) TRACE(1);
 
   // tile -> (split, m_blk, n_blk), n fastest
@@ -723,6 +725,24 @@ int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, int N, 
   }
   const long long tiles = (long long)ceil_div(M, kBM) * ceil_div(N, BN) * splits;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+#ifndef TFASR_EMU_BUILD
+  if (gemm_pdl_enabled()) {  // TFASR_PDL=1: the launch may overlap its prologue with the tail of the kernel before it (sm100::grid_dependency_wait)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, A_MN, B_MN, FEAT>, tmA, tmB, tmC, tmR, tmX, e2, M, N, K, splits) != cudaSuccess)
+      return TFASR_EXECUTION_FAILED;
+    count_launch();
+    return check_launch();
+  }
+#endif
   gemm_bf16_kernel<BN, A_MN, B_MN, FEAT><<<grid, kGemmThreads, S::TOTAL, stream>>>(tmA, tmB, tmC, tmR, tmX, e2, M, N, K, splits);
   count_launch();
   return check_launch();
