@@ -510,6 +510,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 template <int KS>
 __global__ void __launch_bounds__(512, 1) rel_attention_fwd_mma_kernel(const AttParams p, __nv_bfloat16* __restrict__ ctx,
                                                                        __nv_bfloat16* __restrict__ probs) {
+  grid_dependency_wait();  // launched through launch_pdl: nothing global before this line
   using C = AttMma<KS>;
   constexpr int HS = C::HS;
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -634,7 +635,7 @@ static int launch_att_fwd_mma(const AttParams& p, __nv_bfloat16* ctx, __nv_bfloa
   if (cudaFuncSetAttribute(rel_attention_fwd_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return TFASR_EXECUTION_FAILED;
   dim3 grid(p.N, p.B);
-  rel_attention_fwd_mma_kernel<KS><<<grid, 512, smem, stream>>>(p, ctx, probs);
+  launch_pdl(rel_attention_fwd_mma_kernel<KS>, dim3(grid), dim3(512), smem, stream, p, ctx, probs);
   count_launch();
   return check_launch();
 }
@@ -659,6 +660,7 @@ __global__ void __launch_bounds__(512, 1) rel_attention_bwd_rows_mma_kernel(cons
                                                                             const __nv_bfloat16* __restrict__ octx,
                                                                             __nv_bfloat16* __restrict__ ds_out, __nv_bfloat16* __restrict__ dqkv,
                                                                             float* __restrict__ du, float* __restrict__ dvb) {
+  grid_dependency_wait();  // launched through launch_pdl: nothing global before this line
   using C = AttMma<KS>;
   constexpr int HS = C::HS, SKW = C::SKW;
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -1041,6 +1043,7 @@ __global__ void __launch_bounds__(512) rel_attention_bwd_cols_mma2_kernel(const 
                                                                           const __nv_bfloat16* __restrict__ ds,
                                                                           const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv,
                                                                           __nv_bfloat16* __restrict__ dpos) {
+  grid_dependency_wait();  // launched through launch_pdl: nothing global before this line
   constexpr int HS = AttMma<KS>::HS;
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int T = p.T, H = p.H, NH = p.N * p.H, R = p.R;
@@ -1200,13 +1203,13 @@ static int launch_att_bwd_mma(const AttParams& p, const __nv_bfloat16* probs, co
       cudaFuncSetAttribute(rel_attention_bwd_cols_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return TFASR_EXECUTION_FAILED;
   dim3 grid(p.N, p.B);
-  rel_attention_bwd_rows_mma_kernel<KS><<<grid, 512, smem1, stream>>>(p, probs, dctx, octx, ds_ws, dqkv, du, dvb);
+  launch_pdl(rel_attention_bwd_rows_mma_kernel<KS>, dim3(grid), dim3(512), smem1, stream, p, probs, dctx, octx, ds_ws, dqkv, du, dvb);
   count_launch();
   const size_t smem3 = att_mma_bwd_cols2_smem<KS>(p.T);
   if ((p.T & 1) == 0 && smem3 <= 227 * 1024) {
     if (cudaFuncSetAttribute(rel_attention_bwd_cols_mma2_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return TFASR_EXECUTION_FAILED;
-    rel_attention_bwd_cols_mma2_kernel<KS><<<grid, 512, smem3, stream>>>(p, probs, ds_ws, dctx, dqkv, dpos);
+    launch_pdl(rel_attention_bwd_cols_mma2_kernel<KS>, dim3(grid), dim3(512), smem3, stream, p, probs, ds_ws, dctx, dqkv, dpos);
   } else {
     rel_attention_bwd_cols_mma_kernel<KS><<<grid, 512, smem2, stream>>>(p, probs, ds_ws, dctx, dqkv, dpos);
   }

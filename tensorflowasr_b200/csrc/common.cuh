@@ -1,5 +1,6 @@
 // Shared helpers for libtfasr_b200 kernels (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -50,6 +51,34 @@ __device__ __forceinline__ float log_add_exp_fast(float a, float b) {
   const float d = -fabsf(a - b);  // -inf - -inf = NaN only when both are -inf
   const float r = m + __logf(1.0f + __expf(d));
   return (m == -CUDART_INF_F) ? -CUDART_INF_F : r;
+}
+
+// ---- programmatic dependent launch (TFASR_PDL, default on): a kernel launched through launch_pdl may be scheduled while its predecessor in
+// the stream is still draining, so its launch latency (and whatever it does before grid_dependency_wait()) overlaps the predecessor's tail;
+// grid_dependency_wait() returns once the predecessor has completed and its memory operations are visible (a no-op for an ordinary launch).
+// RULE: every kernel launched through launch_pdl calls grid_dependency_wait() before its first global-memory access.  The step graph keeps
+// these launches as programmatic edges; the training step is a chain of ~700 dependent, few-microsecond kernels.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("TFASR_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // 2^x as ONE MUFU (flush-to-zero: no range fix-up around it) — for softmax terms, where underflow to zero is the right answer

@@ -331,6 +331,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) bn_vec_kernel(const BnVecArgs a) {
+  grid_dependency_wait();  // launched through launch_pdl: nothing global before this line
   extern __shared__ float s_acc[];  // [2][C] (stats modes)
   const int C = a.C, cv = threadIdx.x, ty = threadIdx.y, RY = blockDim.y;
   const int tid = ty * blockDim.x + cv, nth = blockDim.x * blockDim.y;
@@ -432,7 +433,7 @@ static bool launch_bn_vec(BnVecArgs a, cudaStream_t stream, int* status) {
   if (rpb < 4 * ry) rpb = 4 * ry;
   a.rows_per_block = (int)rpb;
   const unsigned grid = (unsigned)ceil_div(a.R, rpb);
-  bn_vec_kernel<MODE><<<grid, dim3(cvn, ry), (MODE == 0 || MODE == 2) ? sizeof(float) * 2 * C : 0, stream>>>(a);
+  launch_pdl(bn_vec_kernel<MODE>, dim3(grid), dim3(cvn, ry), (MODE == 0 || MODE == 2) ? sizeof(float) * 2 * C : 0, stream, a);
   count_launch();
   *status = check_launch();
   return true;

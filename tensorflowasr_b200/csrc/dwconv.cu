@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(1024) dwconv_bwd_weight_kernel(const __nv_bflo
 template <int K, bool REVERSE>
 __global__ void __launch_bounds__(640) dwconv_sliding_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
                                                               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int T, int C) {
+  grid_dependency_wait();  // launched through launch_pdl: nothing global before this line
   constexpr int TPT = 8;  // frames per thread; kDwTT / TPT row groups per CTA
   extern __shared__ __align__(16) uint8_t dw_smem[];
   __nv_bfloat162* sx = reinterpret_cast<__nv_bfloat162*>(dw_smem);  // [(TT + K - 1)][C/2]
@@ -214,7 +215,7 @@ extern "C" int tfasr_dwconv_causal_fwd(const void* x, const float* w, const floa
     const size_t smem = (size_t)(kDwTT + K - 1) * C * 2;
     if (cudaFuncSetAttribute(dwconv_sliding_kernel<31, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return TFASR_EXECUTION_FAILED;
-    dwconv_sliding_kernel<31, false><<<dim3((unsigned)ceil_div(T, kDwTT), B), block, smem, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(dwconv_sliding_kernel<31, false>, dim3((unsigned)ceil_div(T, kDwTT), B), dim3(block), smem, static_cast<cudaStream_t>(stream),
         static_cast<const __nv_bfloat16*>(x), w, bias, static_cast<__nv_bfloat16*>(y), T, C);
     count_launch();
     return check_launch();
@@ -242,7 +243,7 @@ extern "C" int tfasr_dwconv_causal_bwd(const void* dy, const void* x, const floa
     const size_t smem = (size_t)(kDwTT + K - 1) * C * 2;
     if (cudaFuncSetAttribute(dwconv_sliding_kernel<31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return TFASR_EXECUTION_FAILED;
-    dwconv_sliding_kernel<31, true><<<grid, block, smem, stream>>>(static_cast<const __nv_bfloat16*>(dy), w, nullptr, static_cast<__nv_bfloat16*>(dx), T, C);
+    launch_pdl(dwconv_sliding_kernel<31, true>, dim3(grid), dim3(block), smem, stream, static_cast<const __nv_bfloat16*>(dy), w, nullptr, static_cast<__nv_bfloat16*>(dx), T, C);
   } else {
     dwconv_bwd_data_kernel<<<grid, block, sf, stream>>>(static_cast<const __nv_bfloat16*>(dy), w, static_cast<__nv_bfloat16*>(dx), T, C, K);
   }
@@ -266,7 +267,7 @@ extern "C" int tfasr_dwconv_causal_bwd_dx(const void* dy, const float* w, void* 
     const size_t smem = (size_t)(kDwTT + K - 1) * C * 2;
     if (cudaFuncSetAttribute(dwconv_sliding_kernel<31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return TFASR_EXECUTION_FAILED;
-    dwconv_sliding_kernel<31, true><<<grid, block, smem, stream>>>(static_cast<const __nv_bfloat16*>(dy), w, nullptr, static_cast<__nv_bfloat16*>(dx), T, C);
+    launch_pdl(dwconv_sliding_kernel<31, true>, dim3(grid), dim3(block), smem, stream, static_cast<const __nv_bfloat16*>(dy), w, nullptr, static_cast<__nv_bfloat16*>(dx), T, C);
   } else {
     if (cudaFuncSetAttribute(dwconv_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return TFASR_EXECUTION_FAILED;
     dwconv_bwd_data_kernel<<<grid, block, sf, stream>>>(static_cast<const __nv_bfloat16*>(dy), w, static_cast<__nv_bfloat16*>(dx), T, C, K);

@@ -156,6 +156,10 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
     }
     sm100::fence_barrier_init();
   }
+  if (warp == 3) sm100::tmem_alloc(tmem_slot, S::TMEM_COLS);
+  // launched through launch_pdl: barrier initialisation and the TMEM allocation above overlap the tail of the previous kernel; nothing global
+  // (not even the bias / LayerNorm parameters) is read before this line
+  grid_dependency_wait();
   if constexpr (MODE == 0) {
     for (int i = threadIdx.x; i < a.H; i += kFfnThreads) sB1[i] = a.b1[i];
     for (int i = threadIdx.x; i < D; i += kFfnThreads) {
@@ -164,7 +168,6 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
       sBeta[i] = a.ln_b[i];
     }
   }
-  if (warp == 3) sm100::tmem_alloc(tmem_slot, S::TMEM_COLS);
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
@@ -557,7 +560,7 @@ static int launch_ffn(const FfnMaps& tm, const FfnArgs& a, cudaStream_t stream) 
   }
   const int tiles = (a.M + kFfnRows - 1) / kFfnRows;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  ffn_kernel<D, MODE><<<grid, kFfnThreads, S::TOTAL, stream>>>(tm, a);
+  launch_pdl(ffn_kernel<D, MODE>, dim3(grid), dim3(kFfnThreads), S::TOTAL, stream, tm, a);
   count_launch();
   return check_launch();
 }

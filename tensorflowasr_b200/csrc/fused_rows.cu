@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32) layernorm_fwd_kernel(const TI
                                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
                                                                         float eps) {
+  grid_dependency_wait();  // launched through launch_pdl: nothing global before this line
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kRowsWarps + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32) layernorm_bwd_vec_kernel(cons
                                                                             const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
                                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                                                                             float* __restrict__ dbeta, int M, int D) {
+  grid_dependency_wait();  // launched through launch_pdl: nothing global before this line
   extern __shared__ float s_acc[];  // [2][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D2 = D >> 1;
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(256) scale_mask_colsum_vec_kernel(const __nv_b
                                                                     __nv_bfloat16* __restrict__ out, float* __restrict__ colsum, int M, int N,
                                                                     float scale, float drop_p, const unsigned long long* __restrict__ seed_ptr,
                                                                     unsigned long long salt, int rows_per_block) {
+  grid_dependency_wait();  // launched through launch_pdl: nothing global before this line
   extern __shared__ float s_col[];  // [N]
   const int NV = N >> 3, RL = blockDim.x / NV;
   const int cv = threadIdx.x % NV, rl = threadIdx.x / NV;
@@ -412,7 +415,7 @@ extern "C" int tfasr_layernorm_fwd(const void* x, int32_t x_is_f32, const float*
   if (M == 0) return TFASR_OK;
   const unsigned grid = (unsigned)ceil_div(M, kRowsWarps);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define LN_FWD(T, NPL) layernorm_fwd_kernel<T, NPL><<<grid, kRowsWarps * 32, 0, st>>>(static_cast<const T*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps)
+#define LN_FWD(T, NPL) launch_pdl(layernorm_fwd_kernel<T, NPL>, dim3(grid), dim3(kRowsWarps * 32), 0, st, static_cast<const T*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps)
   if (x_is_f32) {
     if (D <= 160) LN_FWD(float, 5); else if (D <= 320) LN_FWD(float, 10); else if (D <= 640) LN_FWD(float, 20); else LN_FWD(float, 32);
   } else {
@@ -433,7 +436,7 @@ extern "C" int tfasr_layernorm_bwd(const void* dy, const void* x, int32_t x_is_f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!x_is_f32 && (D & 1) == 0 && D <= 512) {
 #define LN_BWD_VEC(NP2)                                                                                                                 \
-  layernorm_bwd_vec_kernel<NP2, 4><<<grid, kRowsWarps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), \
+  launch_pdl(layernorm_bwd_vec_kernel<NP2, 4>, dim3(grid), dim3(kRowsWarps * 32), smem, st, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), \
                                                                         mean, rstd, gamma, static_cast<const __nv_bfloat16*>(dres),       \
                                                                         static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, M, D)
     if (D <= 192) LN_BWD_VEC(3); else if (D <= 320) LN_BWD_VEC(5); else LN_BWD_VEC(8);
@@ -462,7 +465,7 @@ extern "C" int tfasr_scale_mask_colsum(const void* in, const void* add, void* ou
     const int RL = 256 / (N >> 3);
     int rows_per_block = RL * 4;
     while ((long long)ceil_div(M, rows_per_block) > 8LL * kNumSMs) rows_per_block *= 2;  // bounded atomic traffic on colsum
-    scale_mask_colsum_vec_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, sizeof(float) * N, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(scale_mask_colsum_vec_kernel, dim3((unsigned)ceil_div(M, rows_per_block)), dim3(256), sizeof(float) * N, static_cast<cudaStream_t>(stream),
         static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(out), colsum, M, N, scale, dropout_p,
         seed_ptr, salt, rows_per_block);
     count_launch();
@@ -497,6 +500,7 @@ namespace tfasr {
 __global__ void __launch_bounds__(256) glu_bwd_vec_kernel(const __nv_bfloat16* __restrict__ aux, const __nv_bfloat16* __restrict__ dg,
                                                           __nv_bfloat16* __restrict__ daux, float* __restrict__ colsum, int M, int D,
                                                           int rows_per_block) {
+  grid_dependency_wait();  // launched through launch_pdl: nothing global before this line
   extern __shared__ float s_col[];  // [2 D]
   const int NV = D >> 2, RL = blockDim.x / NV;
   const int cv = threadIdx.x % NV, rl = threadIdx.x / NV;
@@ -559,7 +563,7 @@ extern "C" int tfasr_glu_bwd(const void* aux, const void* dg, void* daux, float*
     const int RL = 256 / (D >> 2);
     int rpb = RL * 4;
     while ((long long)ceil_div(M, rpb) > 8LL * kNumSMs) rpb *= 2;
-    glu_bwd_vec_kernel<<<(unsigned)ceil_div(M, rpb), 256, sizeof(float) * 2 * D, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(glu_bwd_vec_kernel, dim3((unsigned)ceil_div(M, rpb)), dim3(256), sizeof(float) * 2 * D, static_cast<cudaStream_t>(stream),
         static_cast<const __nv_bfloat16*>(aux), static_cast<const __nv_bfloat16*>(dg), static_cast<__nv_bfloat16*>(daux), colsum, M, D, rpb);
     count_launch();
     return check_launch();

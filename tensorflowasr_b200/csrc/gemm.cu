@@ -68,15 +68,6 @@ bool make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t r
 
 // kernels are instantiated per tile width in gemm_inst_*.cu (parallel compilation)
 
-#ifndef TFASR_EMU_BUILD
-bool gemm_pdl_enabled() {
-  static const bool on = [] {
-    const char* v = getenv("TFASR_PDL");
-    return v && v[0] == '1';
-  }();
-  return on;
-}
-#endif
 #define TFASR_GEMM_EXTERN(BN)                                                                                                               \
   extern template int launch_gemm<BN, false, false, 0u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \
   extern template int launch_gemm<BN, false, false, 1u>(const void*, const void*, const GemmEpi&, int, int, int, int, int, int, cudaStream_t); \

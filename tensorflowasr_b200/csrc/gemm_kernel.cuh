@@ -25,7 +25,6 @@
 
 namespace tfasr {
 
-bool gemm_pdl_enabled();  // gemm.cu: environment switch TFASR_PDL, read once
 bool make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 bool make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 
@@ -726,7 +725,7 @@ int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, int N, 
   const long long tiles = (long long)ceil_div(M, kBM) * ceil_div(N, BN) * splits;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
 #ifndef TFASR_EMU_BUILD
-  if (gemm_pdl_enabled()) {  // TFASR_PDL=1: the launch may overlap its prologue with the tail of the kernel before it (sm100::grid_dependency_wait)
+  if (pdl_enabled()) {  // TFASR_PDL (default on): the launch may overlap its prologue with the tail of the kernel before it (sm100::grid_dependency_wait)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);

@@ -28,6 +28,12 @@ template <class T>
 inline T __ldg(const T* p) { return *p; }
 inline float log1pf_(float x) { return log1pf(x); }
 namespace tfasr {
+inline void grid_dependency_wait() {}  // launches are serialised on the emulator
+template <class... KArgs, class... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
+  emu::launch(grid, block, smem, [&] { kernel(static_cast<KArgs>(args)...); });
+  return 0;
+}
 #ifndef TFASR_KLOG2E_DEFINED
 #define TFASR_KLOG2E_DEFINED
 constexpr float kLog2e = 1.4426950408889634f;
