@@ -7,6 +7,10 @@
  * caller (the library never allocates, frees or retains them), except where a parameter is marked
  * HOST.  Return value: tfasr_status_t (0 = ok).
  *
+ * Launches: the frequent kernels are enqueued as programmatic dependent launches (cudaLaunchAttributeProgrammaticStreamSerialization);
+ * each of them executes griddepcontrol.wait before its first global-memory access, so the stream order the caller sees is unchanged, and a
+ * stream capture records programmatic edges.  TFASR_PDL=0 in the environment (read once) restores ordinary launches.
+ *
  * What each entry point replaces in the reference (paths relative to the TensorFlowASR tree):
  *   tfasr_logmel_*        tensorflow_asr/models/layers/feature_extraction.py:255-303 (FeatureExtraction.call:
  *                         preemphasis :170-175, stft :192-212, log_mel_spectrogram :220-231, spectrogram :233-235)
