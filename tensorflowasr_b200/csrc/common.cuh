@@ -59,6 +59,18 @@ __device__ __forceinline__ float log_add_exp_fast(float a, float b) {
 // RULE: every kernel launched through launch_pdl calls grid_dependency_wait() before its first global-memory access.  The step graph keeps
 // these launches as programmatic edges; the training step is a chain of ~700 dependent, few-microsecond kernels.
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// The other half: a kernel that executes this in every CTA lets its programmatic dependents be SCHEDULED from then on (they still block in
+// their grid_dependency_wait() until this grid has completed).  Used by the persistent tcgen05 kernels only — their grid is at most one CTA
+// per SM, all resident from the start, so an early-resident dependent can never hold back a CTA of the primary.  TFASR_PDL_TRIGGER=0: off.
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled();
+inline bool pdl_trigger_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("TFASR_PDL_TRIGGER");
+    return !(v && v[0] == '0');
+  }();
+  return on && pdl_enabled();
+}
 inline bool pdl_enabled() {
   static const bool on = [] {
     const char* v = getenv("TFASR_PDL");

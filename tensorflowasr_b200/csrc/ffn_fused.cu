@@ -73,6 +73,7 @@ struct FfnArgs {
   const unsigned long long* seed_ptr;
   unsigned long long salt1, salt2;
   unsigned long long* trace;  // debug: phase timestamps of CTA 0 (tools/ffn_trace.py); null in production
+  int pdl_trigger;            // 1: programmatic dependents may be scheduled as soon as this grid is resident (common.cuh)
 };
 
 // phase timestamps (globaltimer, ns) of CTA 0 -> trace[slot]; compiled in, costs one predictable branch per event when trace is null
@@ -159,6 +160,7 @@ ffn_kernel(const __grid_constant__ FfnMaps tm, const FfnArgs a) {
   if (warp == 3) sm100::tmem_alloc(tmem_slot, S::TMEM_COLS);
   // launched through launch_pdl: barrier initialisation and the TMEM allocation above overlap the tail of the previous kernel; nothing global
   // (not even the bias / LayerNorm parameters) is read before this line
+  if (a.pdl_trigger) grid_launch_dependents();
   grid_dependency_wait();
   if constexpr (MODE == 0) {
     for (int i = threadIdx.x; i < a.H; i += kFfnThreads) sB1[i] = a.b1[i];
@@ -560,7 +562,9 @@ static int launch_ffn(const FfnMaps& tm, const FfnArgs& a, cudaStream_t stream) 
   }
   const int tiles = (a.M + kFfnRows - 1) / kFfnRows;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  launch_pdl(ffn_kernel<D, MODE>, dim3(grid), dim3(kFfnThreads), S::TOTAL, stream, tm, a);
+  FfnArgs a2 = a;
+  a2.pdl_trigger = pdl_trigger_enabled() ? 1 : 0;
+  launch_pdl(ffn_kernel<D, MODE>, dim3(grid), dim3(kFfnThreads), S::TOTAL, stream, tm, a2);
   count_launch();
   return check_launch();
 }

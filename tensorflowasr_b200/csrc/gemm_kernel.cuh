@@ -68,6 +68,7 @@ struct GemmEpi {
   int tma_store;        // 1: C leaves through SMEM staging + cp.async.bulk.tensor stores (coalesced, clipped by hardware)
   int tma_side;         // 1: residual, 2: mul arrives through a TMA load into the staging buffer ahead of the accumulator
   int tma_aux;          // 1: the pre-activation copy leaves through its own staging buffer + TMA store
+  int pdl_trigger;      // 1: let programmatic dependents be scheduled as soon as this (persistent) grid is resident
   float* rowstats;      // feature class 8 only: [M, rs_parts, 2] f32 = per row and column slice (max, sum exp(v - max)) of the final values
   int rs_parts;         // 2 * ceil(N / BN): every tile contributes two slices per row (the two epilogue warps of a TMEM lane quarter)
 #ifdef TFASR_GEMM_TRACE
@@ -206,6 +207,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (epi.pdl_trigger) sm100::grid_launch_dependents();  // dependents may become resident now; they block until this grid has completed
   sm100::grid_dependency_wait();  // everything above touched only this CTA's shared memory and TMEM; global memory from here on
   if (threadIdx.x == 0) TRACE(1);
 
@@ -696,6 +698,11 @@ int launch_gemm(const void* A, const void* B, const GemmEpi& epi, int M, int N, 
   e2.tma_store = 0;
   e2.tma_side = 0;
   e2.tma_aux = 0;
+#ifndef TFASR_EMU_BUILD
+  e2.pdl_trigger = pdl_trigger_enabled() ? 1 : 0;
+#else
+  e2.pdl_trigger = 0;
+#endif
 #ifdef TFASR_GEMM_TRACE
   e2.trace = g_gemm_trace_host;
 #endif

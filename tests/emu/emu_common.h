@@ -29,6 +29,8 @@ inline T __ldg(const T* p) { return *p; }
 inline float log1pf_(float x) { return log1pf(x); }
 namespace tfasr {
 inline void grid_dependency_wait() {}  // launches are serialised on the emulator
+inline void grid_launch_dependents() {}
+inline bool pdl_trigger_enabled() { return false; }
 template <class... KArgs, class... Args>
 inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
   emu::launch(grid, block, smem, [&] { kernel(static_cast<KArgs>(args)...); });

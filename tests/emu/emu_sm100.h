@@ -148,6 +148,7 @@ static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------------------------------------- TMA
 static inline void prefetch_tensormap(const CUtensorMap*) {}
 static inline void grid_dependency_wait() {}  // launches are serialised on the emulator
+static inline void grid_launch_dependents() {}
 // box element (r, c) <-> global element (c1 + r, c0 + c); shared memory: row r at r * inner bytes, swizzled
 static inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
   const uint32_t inner = m->box_cols * m->elem_bytes, base = smem_u32(smem_dst);
