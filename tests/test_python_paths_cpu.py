@@ -245,3 +245,61 @@ def test_dropout_counter_is_seedable_rank_mixed_and_saved():
     assert int(c.seed) == int(a.seed) == saved["counter"]
     a.reseed(7, rank=0)
     assert int(a.seed) == va  # reseeding rewinds the live counter
+
+
+def test_fit_loop_epochs_steps_and_callbacks_on_cpu():
+    """training.fit's bookkeeping without any kernel (a stand-in model whose train_step returns a known loss): epochs re-iterate a list,
+    steps_per_epoch draws from ONE iterator across epochs and an exhausted iterator ends training (keras semantics), every step's loss reaches
+    the callbacks in order, the History holds per-epoch means and per-step values, initial_epoch is honoured."""
+    import torch
+
+    from tensorflowasr_b200 import schemas, training
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.seen = []
+
+        def train_step(self, data):
+            self.seen.append(int(data.inputs.inputs_length[0]))
+            return {"loss": data.inputs.inputs.float().mean().reshape(1) * torch.ones(3)}
+
+    def batch(v):
+        x = torch.full((2, 4), float(v))
+        ln = torch.full((2,), v, dtype=torch.int32)
+        return schemas.TrainData(schemas.TrainInput(x, ln, None, None), schemas.TrainLabel(ln, ln))
+
+    events = []
+
+    class Log:
+        def on_train_begin(self):
+            events.append("begin")
+
+        def on_epoch_begin(self, epoch):
+            events.append(("epoch_begin", epoch))
+
+        def on_train_batch_end(self, step, logs):
+            events.append(("batch", step, logs["loss"]))
+
+        def on_epoch_end(self, epoch, logs):
+            events.append(("epoch_end", epoch, logs["loss"]))
+
+        def on_train_end(self):
+            events.append("end")
+
+    m = Model()
+    h = training.fit(m, [batch(1), batch(2), batch(3)], epochs=2, callbacks=[Log()])
+    assert m.seen == [1, 2, 3, 1, 2, 3] and h.epoch == [0, 1] and h.history["loss"] == [2.0, 2.0]
+    assert h.steps["loss"] == [1.0, 2.0, 3.0, 1.0, 2.0, 3.0]
+    assert events[0] == "begin" and events[-1] == "end"
+    assert [e for e in events if isinstance(e, tuple) and e[0] == "batch"][:3] == [("batch", 0, 1.0), ("batch", 1, 2.0), ("batch", 2, 3.0)]
+    assert ("epoch_end", 1, 2.0) in events
+    # one iterator, two steps per epoch: epoch 0 sees 1, 2; epoch 1 sees 3, 4; epoch 2 gets the last batch and training ends there
+    m2 = Model()
+    h2 = training.fit(m2, iter([batch(v) for v in (1, 2, 3, 4, 5)]), epochs=5, steps_per_epoch=2)
+    assert m2.seen == [1, 2, 3, 4, 5] and h2.epoch == [0, 1, 2] and h2.history["loss"] == [1.5, 3.5, 5.0]
+    # initial_epoch: resumes the epoch count
+    m3 = Model()
+    h3 = training.fit(m3, [batch(7)], epochs=3, initial_epoch=2)
+    assert h3.epoch == [2] and m3.seen == [7]
