@@ -339,13 +339,14 @@ class BaseModel(nn.Module):
             self.optimizer.load_state_dict(state["optimizer"])
         return self
 
-    def fit(self, x=None, epochs=1, steps_per_epoch=None, callbacks=None, initial_epoch=0, verbose=0, **kwargs):
-        """keras.Model.fit for this path (scripts/train.py:113-121): drives `train_step` over an iterable of TrainData batches with the next
+    def fit(self, x=None, epochs=1, steps_per_epoch=None, callbacks=None, initial_epoch=0, verbose=0, validation_data=None,
+            validation_steps=None, **kwargs):
+        """keras.Model.fit for this path (tensorflow_asr/scripts/train.py:113-121): drives `train_step` over an iterable of TrainData batches with the next
         batch's host->device copy on a copy stream and the per-step loss read back one step late (training.py).  Returns a History."""
         from . import training
 
         return training.fit(self, x, epochs=epochs, steps_per_epoch=steps_per_epoch, callbacks=callbacks, initial_epoch=initial_epoch,
-                            verbose=verbose)
+                            verbose=verbose, validation_data=validation_data, validation_steps=validation_steps)
 
     @torch.no_grad()
     def test_step(self, data: schemas.TrainData):

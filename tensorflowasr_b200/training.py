@@ -1,4 +1,4 @@
-"""The training loop around `train_step`: what `keras.Model.fit` does for the reference (`scripts/train.py:113-121` calls
+"""The training loop around `train_step`: what `keras.Model.fit` does for the reference (`tensorflow_asr/scripts/train.py:113-121` calls
 `model.fit(train_dataset, epochs, steps_per_epoch, callbacks, initial_epoch)`; the step function it drives is `base_model.py:194-269`).
 
 B200-first shape of that loop — nothing here computes, it only keeps the device busy:
@@ -145,10 +145,32 @@ def _call(callbacks, name, *args):
             fn(*args)
 
 
-def fit(model, x, epochs=1, steps_per_epoch=None, callbacks=None, initial_epoch=0, verbose=0) -> History:
+def _validate(model, validation_data, validation_steps, dev) -> float | None:
+    """Mean of `test_step` losses over the validation batches (keras: evaluate at the end of every epoch) — same prefetcher, same late reads."""
+    source = DevicePrefetcher(validation_data, dev)
+    reader = _LossReader(dev)
+    vals, step = [], 0
+    while validation_steps is None or step < validation_steps:
+        try:
+            data = next(source)
+        except StopIteration:
+            break
+        reader.push(model.test_step(data)["loss"])
+        step += 1
+        if reader.full():
+            vals.append(reader.pop())
+    while reader.pending:
+        vals.append(reader.pop())
+    return sum(vals) / len(vals) if vals else None
+
+
+def fit(model, x, epochs=1, steps_per_epoch=None, callbacks=None, initial_epoch=0, verbose=0, validation_data=None,
+        validation_steps=None) -> History:
     """`x`: an iterable of schemas.TrainData batches (host — ideally pinned — or device tensors), re-iterated every epoch, or an iterator when
-    `steps_per_epoch` bounds each epoch (an exhausted iterator ends training, like keras).  Returns the History; callbacks may implement
-    on_train_begin / on_epoch_begin(epoch) / on_train_batch_end(step, logs) / on_epoch_end(epoch, logs) / on_train_end."""
+    `steps_per_epoch` bounds each epoch (an exhausted iterator ends training, like keras).  `validation_data` (re-iterable, same batch type) is
+    evaluated with `test_step` at the end of every epoch -> `val_loss` (tensorflow_asr/scripts/train.py:113-121 passes both).  Returns the
+    History; callbacks may implement on_train_begin / on_epoch_begin(epoch) / on_train_batch_end(step, logs) / on_epoch_end(epoch, logs) /
+    on_train_end."""
     dev = next(model.parameters()).device
     hist = History()
     model.train()
@@ -187,11 +209,17 @@ def fit(model, x, epochs=1, steps_per_epoch=None, callbacks=None, initial_epoch=
         if not losses:
             break
         logs = {"loss": sum(losses) / len(losses)}
+        if validation_data is not None:
+            val = _validate(model, validation_data, validation_steps, dev)
+            if val is not None:
+                logs["val_loss"] = val
+                hist.history.setdefault("val_loss", []).append(val)
+            model.train()
         hist.epoch.append(epoch)
         hist.history.setdefault("loss", []).append(logs["loss"])
         hist.steps["loss"].extend(losses)
         if verbose:
-            print(f"epoch {epoch + 1}/{epochs}: {len(losses)} steps, loss {logs['loss']:.4f}")
+            print(f"epoch {epoch + 1}/{epochs}: {len(losses)} steps, " + ", ".join(f"{k} {v:.4f}" for k, v in logs.items()))
         _call(callbacks, "on_epoch_end", epoch, logs)
         if exhausted and steps_per_epoch is not None:
             break

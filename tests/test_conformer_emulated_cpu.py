@@ -131,7 +131,7 @@ def test_conformer_train_step_on_emulated_kernels(monkeypatch):
 
 def test_train_step_with_flat_adamw_learns_on_emulated_kernels(monkeypatch):
     """BaseModel.fit -> train_step end to end (forward, backward, the one-launch flat AdamW, gradient zeroing) on the emulator backend: the loss
-    of a fixed batch goes down step after step; the loop reports every step's loss to the callbacks and the History (scripts/train.py:113-121)."""
+    of a fixed batch goes down step after step; the loop reports every step's loss to the callbacks and the History (tensorflow_asr/scripts/train.py:113-121)."""
     import tensorflowasr_b200 as tfasr
     from tensorflowasr_b200 import ops
 

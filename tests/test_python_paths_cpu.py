@@ -265,6 +265,9 @@ def test_fit_loop_epochs_steps_and_callbacks_on_cpu():
             self.seen.append(int(data.inputs.inputs_length[0]))
             return {"loss": data.inputs.inputs.float().mean().reshape(1) * torch.ones(3)}
 
+        def test_step(self, data):
+            return {"loss": 10.0 * data.inputs.inputs.float().mean().reshape(1) * torch.ones(3)}
+
     def batch(v):
         x = torch.full((2, 4), float(v))
         ln = torch.full((2,), v, dtype=torch.int32)
@@ -299,6 +302,10 @@ def test_fit_loop_epochs_steps_and_callbacks_on_cpu():
     m2 = Model()
     h2 = training.fit(m2, iter([batch(v) for v in (1, 2, 3, 4, 5)]), epochs=5, steps_per_epoch=2)
     assert m2.seen == [1, 2, 3, 4, 5] and h2.epoch == [0, 1, 2] and h2.history["loss"] == [1.5, 3.5, 5.0]
+    # validation at every epoch end through test_step, bounded by validation_steps
+    m4 = Model()
+    h4 = training.fit(m4, [batch(1), batch(3)], epochs=2, validation_data=[batch(2), batch(4), batch(9)], validation_steps=2)
+    assert h4.history["loss"] == [2.0, 2.0] and h4.history["val_loss"] == [30.0, 30.0] and m4.training
     # initial_epoch: resumes the epoch count
     m3 = Model()
     h3 = training.fit(m3, [batch(7)], epochs=3, initial_epoch=2)
