@@ -931,6 +931,8 @@ CASES = [
     ("rnnt_lattice_v2_three_warps", lambda lib: check_rnnt_lattice_v2(lib, 3, 40, 65, [40, 17, 0], [64, 9, 3])),  # U1 = 65: three warps, edge hand-off
     ("rnnt_lattice_v2_one_warp_ragged", lambda lib: check_rnnt_lattice_v2(lib, 4, 23, 9, [23, 1, 5, 30], [8, 0, 2, 4])),  # incl. T_b > T: infeasible
     ("rnnt_lattice_v2_wide", lambda lib: check_rnnt_lattice_v2(lib, 1, 7, 130, [7], [129])),  # five warps, longer than it is tall
+    ("rnnt_lattice_v2_no_labels", lambda lib: check_rnnt_lattice_v2(lib, 2, 6, 1, [6, 3], [0, 0])),  # U + 1 = 1: a blank-only chain
+    ("rnnt_lattice_v2_single_frame", lambda lib: check_rnnt_lattice_v2(lib, 2, 1, 5, [1, 1], [4, 0])),  # T = 1: emissions only, then the final blank
     ("rnnt_combine_bf16_logits", lambda lib: check_rnnt_combine(lib, 2, 5, 4, 1000, [5, 3], [3, 1], bf16=True)),
     ("rnnt_grad_bf16_io_in_place", lambda lib: check_rnnt_grad_v2(lib, 3, 5, 4, 1000, [5, 3, 0], [3, 1, 2], True, bf16_io=True)),  # 8 uint2 per lane
     ("rnnt_grad_bf16_io_padded_rows", lambda lib: check_rnnt_grad_v2(lib, 3, 5, 4, 1000, [5, 3, 0], [3, 1, 2], True, bf16_io=True, pitch=1024)),  # the head's layout: 16-byte accesses
